@@ -1,0 +1,144 @@
+"""ctypes binding of libccb200.so (the C ABI declared in include/ccb200.h).
+
+There is no CPU implementation behind this module: if the library is missing it is built with
+nvcc, and if that fails the import raises.  Every compute entry point fails loudly when no GPU is
+present (``ccb_last_error`` -> RuntimeError).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+c_double_p = C.POINTER(C.c_double)
+c_float_p = C.POINTER(C.c_float)
+c_int_p = C.POINTER(C.c_int)
+
+
+class CParams(C.Structure):
+    """``ccb_params`` (reference parameters.h:49-175)."""
+
+    _fields_ = [
+        ("pNumRobots", C.c_int),
+        ("pResolution", C.c_double),
+        ("pWorldMapSize", C.c_int),
+        ("pRobotMapSize", C.c_int),
+        ("pLocalMapSize", C.c_int),
+        ("pUpdateRobotMap", C.c_int),
+        ("pUpdateExplorationMap", C.c_int),
+        ("pUpdateSensorView", C.c_int),
+        ("pUpdateSystemMap", C.c_int),
+        ("pTruncationBND", C.c_double),
+        ("pNorm", C.c_double),
+        ("pUnknownImportance", C.c_double),
+        ("pRobotMapUseUnknownImportance", C.c_int),
+        ("pSensorSize", C.c_int),
+        ("pCommunicationRange", C.c_double),
+        ("pMaxRobotSpeed", C.c_double),
+        ("pRobotPosHistorySize", C.c_int),
+        ("pTimeStep", C.c_double),
+        ("pCheckOscillations", C.c_int),
+    ]
+
+
+# name -> (restype, argtypes).  Kept in one table so tests can check it against include/ccb200.h.
+SIGNATURES = {
+    "ccb_abi_version": (C.c_int, []),
+    "ccb_last_error": (C.c_char_p, []),
+    "ccb_cuda_available": (C.c_int, []),
+    "ccb_device_count": (C.c_int, []),
+    "ccb_params_default": (None, [C.POINTER(CParams)]),
+    "ccb_idf_create": (C.c_void_p, [C.POINTER(CParams), C.c_int, C.c_void_p]),
+    "ccb_idf_destroy": (None, [C.c_void_p]),
+    "ccb_idf_add_bnd": (C.c_int, [C.c_void_p] + [C.c_double] * 6),
+    "ccb_idf_add_polygon": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_float]),
+    "ccb_idf_num_features": (C.c_int, [C.c_void_p]),
+    "ccb_idf_generate": (C.c_int, [C.c_void_p, C.c_int]),
+    "ccb_idf_get_map": (C.c_int, [C.c_void_p, c_float_p]),
+    "ccb_idf_set_map": (C.c_int, [C.c_void_p, c_float_p]),
+    "ccb_idf_map_dev": (C.c_void_p, [C.c_void_p]),
+    "ccb_idf_norm_factor": (C.c_int, [C.c_void_p, c_float_p]),
+    "ccb_idf_get_bnds": (C.c_int, [C.c_void_p, c_double_p, C.c_int]),
+    "ccb_idf_num_bnds": (C.c_int, [C.c_void_p]),
+    "ccb_idf_num_polygons": (C.c_int, [C.c_void_p]),
+    "ccb_idf_get_polygon": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int, c_float_p]),
+    "ccb_env_create": (C.c_void_p, [C.POINTER(CParams), C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ccb_env_destroy": (None, [C.c_void_p]),
+    "ccb_env_num_envs": (C.c_int, [C.c_void_p]),
+    "ccb_env_num_robots": (C.c_int, [C.c_void_p]),
+    "ccb_env_set_world_idf": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "ccb_env_set_world_host": (C.c_int, [C.c_void_p, C.c_int, c_float_p]),
+    "ccb_env_set_world_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "ccb_env_reset": (C.c_int, [C.c_void_p, c_double_p]),
+    "ccb_env_step_actions": (C.c_int, [C.c_void_p, c_double_p, c_int_p]),
+    "ccb_env_step_control": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
+    "ccb_env_set_positions": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
+    "ccb_env_get_positions": (C.c_int, [C.c_void_p, c_double_p]),
+    "ccb_env_clear_robot_maps": (C.c_int, [C.c_void_p, C.c_int]),
+    "ccb_env_clear_explored_idf": (C.c_int, [C.c_void_p, C.c_int]),
+    "ccb_env_get_map": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p]),
+    "ccb_env_get_map_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ccb_env_map_dim": (C.c_int, [C.c_void_p, C.c_int]),
+    "ccb_env_local_maps_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ccb_env_obstacle_maps_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ccb_env_comm_maps_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "ccb_env_cnn_input_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ccb_env_comm_maps_cpp": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
+    "ccb_env_compute_voronoi": (C.c_int, [C.c_void_p]),
+    "ccb_env_get_cells": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p,
+                                    c_int_p, c_double_p]),
+    "ccb_env_objective": (C.c_int, [C.c_void_p, c_double_p]),
+    "ccb_env_voronoi_labels": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]),
+    "ccb_env_voronoi_features": (C.c_int, [C.c_void_p, c_double_p]),
+    "ccb_env_exploration_ratios": (C.c_int, [C.c_void_p, c_double_p]),
+    "ccb_env_check_oscillation": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int_p]),
+    "ccb_env_sync": (C.c_int, [C.c_void_p]),
+    "ccb_env_world_dev": (C.c_void_p, [C.c_void_p]),
+    "ccb_env_positions_dev": (C.c_void_p, [C.c_void_p]),
+    "ccb_ctrl_create": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "ccb_ctrl_destroy": (None, [C.c_void_p]),
+    "ccb_ctrl_compute_actions": (C.c_int, [C.c_void_p]),
+    "ccb_ctrl_get_actions": (C.c_int, [C.c_void_p, c_double_p]),
+    "ccb_ctrl_get_goals": (C.c_int, [C.c_void_p, c_double_p]),
+    "ccb_ctrl_is_converged": (C.c_int, [C.c_void_p, c_int_p]),
+    "ccb_ctrl_rollout": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ccb_ctrl_actions_dev": (C.c_void_p, [C.c_void_p]),
+    "ccb_kernel_launch_count": (C.c_uint64, []),
+}
+
+CCB_MAX_CELL_VERTS = 64
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building first if needed) the shared library and declare every prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_build.LIB):
+        _build.build()
+    lib = C.CDLL(_build.LIB)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ccb_abi_version() != 1:
+        raise RuntimeError("libccb200.so ABI version mismatch; rebuild with python -m coveragecontrol_b200.build --force")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    msg = load().ccb_last_error()
+    return msg.decode() if msg else ""
+
+
+def check(status: int, exc=RuntimeError) -> None:
+    if status != 0:
+        raise exc(last_error() or f"libccb200 call failed with status {status}")

@@ -1,0 +1,67 @@
+"""Build libccb200.so (hand-written sm_100a CUDA + the C ABI of include/ccb200.h) in-tree.
+
+    python -m coveragecontrol_b200.build [--force]
+
+nvcc cross-compiles without a GPU; the resulting .so is git-ignored but travels with the tree.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB = os.path.join(_HERE, "libccb200.so")
+SOURCES = ["ccb200.cu"]
+HEADERS = ["common.cuh", "idf.cuh", "voronoi.cuh", "maps.cuh", "obs.cuh"]
+
+NVCC_FLAGS = [
+    "-std=c++17",
+    "-O3",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-fmad=false",          # explicit fma()/fmaf() only: see ccb200.cu header comment
+    "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    "-Xcompiler", "-fPIC",
+    "-Xptxas", "-v",
+    "-shared",
+]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: coveragecontrol_b200 needs the CUDA toolkit to build")
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    deps.append(os.path.join(_HERE, "..", "include", "ccb200.h"))
+    deps.append(os.path.abspath(__file__))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    log = out.stdout + out.stderr
+    with open(os.path.join(_HERE, "build.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + log)
+    if out.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + log)
+    if verbose:
+        print(log)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print("built", LIB)

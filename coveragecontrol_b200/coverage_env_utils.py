@@ -1,0 +1,142 @@
+"""Mirror of reference ``python/coverage_control/coverage_env_utils.py`` (CoverageEnvUtils).
+
+Same static-method names and tensor layouts; the per-robot Python loops and the CPU
+``torchvision`` resize are replaced by batched CUDA kernels that write straight into a torch
+tensor allocated on the GPU (zero-copy hand-off to LPAC).  Pass ``device="cpu"`` to get host
+tensors as the reference returns.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy
+import torch
+
+from . import _lib
+from .core import (BatchedCoverageSystem, CoverageSystem, DblVector, DblVectorVector, Parameters,
+                   PointVector, _EnvBase)
+
+
+def _cuda_device(env: _EnvBase) -> torch.device:
+    return torch.device("cuda", env._device)
+
+
+def _finish(t: torch.Tensor, env: _EnvBase, device):
+    """Make the kernel output visible to torch and move it if the caller asked for another device."""
+    if env._stream != torch.cuda.current_stream(t.device).cuda_stream:
+        _lib.check(_lib.load().ccb_env_sync(env._h))
+    if isinstance(env, CoverageSystem):
+        t = t[0]
+    if device is not None and torch.device(device) != t.device:
+        t = t.to(device)
+    return t
+
+
+class CoverageEnvUtils:
+    """Utility functions for the coverage environment (reference coverage_env_utils.py:42)."""
+
+    @staticmethod
+    def to_tensor(data: object) -> torch.Tensor:
+        """reference :46-95."""
+        if isinstance(data, numpy.ndarray):
+            return torch.from_numpy(numpy.copy(data.astype(numpy.float32)))
+        if isinstance(data, PointVector):
+            return torch.from_numpy(numpy.asarray(data.to_numpy(), numpy.float32).reshape(len(data), 2).copy())
+        if isinstance(data, DblVectorVector):
+            return torch.tensor([[float(v) for v in row] for row in data], dtype=torch.float32)
+        if isinstance(data, DblVector):
+            return torch.tensor([float(v) for v in data], dtype=torch.float32)
+        raise ValueError(f"Unknown data type: {type(data)}")
+
+    @staticmethod
+    def get_raw_local_maps(env, params: Parameters, device=None) -> torch.Tensor:
+        """reference :97-117 -> [R, L, L] (or [E, R, L, L] for a batched environment)."""
+        L = params.pLocalMapSize
+        out = torch.empty((env._E, env._R, L, L), dtype=torch.float32, device=_cuda_device(env))
+        _lib.check(_lib.load().ccb_env_local_maps_dev(env._h, out.data_ptr()))
+        return _finish(out, env, device)
+
+    @staticmethod
+    def get_raw_obstacle_maps(env, params: Parameters, device=None) -> torch.Tensor:
+        """reference :119-141."""
+        L = params.pLocalMapSize
+        out = torch.empty((env._E, env._R, L, L), dtype=torch.float32, device=_cuda_device(env))
+        _lib.check(_lib.load().ccb_env_obstacle_maps_dev(env._h, out.data_ptr()))
+        return _finish(out, env, device)
+
+    @staticmethod
+    def get_communication_maps(env, params: Parameters, map_size: int, device=None) -> torch.Tensor:
+        """reference :143-191 (float32, round-half-even) -> [R, 2, C, C]."""
+        out = torch.empty((env._E, env._R, 2, map_size, map_size), dtype=torch.float32, device=_cuda_device(env))
+        _lib.check(_lib.load().ccb_env_comm_maps_dev(env._h, int(map_size), out.data_ptr()))
+        return _finish(out, env, device)
+
+    @staticmethod
+    def resize_maps(maps: torch.Tensor, resized_map_size: int) -> torch.Tensor:
+        """reference :200-225; kept for callers that resize stored raw maps (torchvision, any device)."""
+        import torchvision
+
+        shape = maps.shape
+        maps = maps.reshape(-1, maps.shape[-2], maps.shape[-1])
+        maps = torchvision.transforms.functional.resize(
+            maps, (resized_map_size, resized_map_size),
+            interpolation=torchvision.transforms.InterpolationMode.BILINEAR, antialias=True)
+        return maps.reshape(shape[:-2] + maps.shape[-2:])
+
+    @staticmethod
+    def get_maps(env, params: Parameters, resized_map_size: int, use_comm_map: bool, device=None) -> torch.Tensor:
+        """reference :227-277 -> [R, 4 or 2, C, C]: crop, mask, antialias resize and the
+        communication channels fused on the GPU."""
+        C = int(resized_map_size)
+        nch = 4 if use_comm_map else 2
+        out = torch.empty((env._E, env._R, nch, C, C), dtype=torch.float32, device=_cuda_device(env))
+        _lib.check(_lib.load().ccb_env_cnn_input_dev(env._h, C, int(bool(use_comm_map)), out.data_ptr()))
+        return _finish(out, env, device)
+
+    @staticmethod
+    def get_voronoi_features(env, device=None) -> torch.Tensor:
+        """reference :279-292 -> [R, 7]."""
+        if isinstance(env, BatchedCoverageSystem):
+            return torch.from_numpy(env.voronoi_features().astype(numpy.float32))
+        feats = env.GetRobotVoronoiFeatures()
+        return torch.tensor([[float(v) for v in row] for row in feats], dtype=torch.float32)
+
+    @staticmethod
+    def get_robot_positions(env) -> torch.Tensor:
+        """reference :294-305."""
+        if isinstance(env, BatchedCoverageSystem):
+            return torch.from_numpy(env.positions().astype(numpy.float32))
+        return CoverageEnvUtils.to_tensor(env.GetRobotPositions())
+
+    @staticmethod
+    def get_weights(env, params: Parameters) -> torch.Tensor:
+        """reference :313-335."""
+        onebyexp = 1.0 / math.exp(1.0)
+        robot_positions = CoverageEnvUtils.get_robot_positions(env)
+        pairwise_distances = torch.cdist(robot_positions, robot_positions, 2)
+        edge_weights = torch.exp(-(pairwise_distances.square()) / (params.pCommunicationRange * params.pCommunicationRange))
+        edge_weights.masked_fill_(edge_weights < onebyexp, 0)
+        if edge_weights.dim() == 2:
+            edge_weights.fill_diagonal_(0)
+        else:
+            edge_weights.diagonal(dim1=-2, dim2=-1).zero_()
+        return edge_weights
+
+    @staticmethod
+    def get_torch_geometric_data(env, params: Parameters, use_cnn: bool, use_comm_map: bool, map_size: int):
+        """reference :337-377 (needs torch_geometric, which this image does not ship)."""
+        try:
+            import torch_geometric
+        except ImportError as exc:  # pragma: no cover
+            raise ImportError("get_torch_geometric_data needs torch_geometric") from exc
+        if use_cnn:
+            features = CoverageEnvUtils.get_maps(env, params, map_size, use_comm_map)
+        else:
+            features = CoverageEnvUtils.get_voronoi_features(env)
+        edge_weights = CoverageEnvUtils.get_weights(env, params).to_sparse().coalesce()
+        edge_index = edge_weights.indices().long()
+        weights = edge_weights.values().float()
+        pos = CoverageEnvUtils.get_robot_positions(env)
+        pos = (pos + params.pWorldMapSize / 2.0) / params.pWorldMapSize
+        return torch_geometric.data.Data(x=features, edge_index=edge_index.clone().detach(),
+                                         edge_weight=weights.clone().detach(), pos=pos.clone().detach())

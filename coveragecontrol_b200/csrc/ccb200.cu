@@ -1,0 +1,1116 @@
+// ccb200.cu -- host side of the C ABI declared in include/ccb200.h.
+//
+// One translation unit: kernels live in idf.cuh / voronoi.cuh / maps.cuh / obs.cuh.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false ... (build.py).
+// -fmad=false keeps every implicit a*b+c un-contracted so the fp64 host-visible arithmetic
+// (kinematics, distances, clipping) rounds like the reference's x86-64 build; FMAs are written
+// explicitly where they are wanted.
+#include <algorithm>
+#include <array>
+#include <map>
+#include <memory>
+
+#include "common.cuh"
+#include "idf.cuh"
+#include "maps.cuh"
+#include "obs.cuh"
+#include "voronoi.cuh"
+
+namespace ccb {
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+}  // namespace ccb
+
+using namespace ccb;
+
+// =================================================================================================
+// WorldIDF
+// =================================================================================================
+struct ccb_idf {
+  ccb_params p;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<std::array<double, 6>> bnds;  // mean_x, mean_y, sigma_x, sigma_y, scale, rho
+  struct Poly {
+    std::vector<double> xy;
+    float imp;
+  };
+  std::vector<Poly> polys;
+  float *d_map = nullptr;
+  int *d_max = nullptr;
+  float *d_factor = nullptr;
+  float h_factor = 0.f;
+  bool factor_valid = true;
+};
+
+namespace {
+
+// Ear-clipping triangulation of a simple polygon.  The reference partitions each polygon into
+// y-monotone pieces with CGAL (polygon_utils.cpp:38-68) before the GPU test; triangles are
+// y-monotone pieces with the same union, so the per-cell result is the same.
+static double cross2(double ax, double ay, double bx, double by, double cx, double cy) {
+  return (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+}
+static bool in_tri(double px, double py, const double *a, const double *b, const double *c) {
+  double d1 = cross2(a[0], a[1], b[0], b[1], px, py);
+  double d2 = cross2(b[0], b[1], c[0], c[1], px, py);
+  double d3 = cross2(c[0], c[1], a[0], a[1], px, py);
+  bool neg = (d1 < 0) || (d2 < 0) || (d3 < 0);
+  bool pos = (d1 > 0) || (d2 > 0) || (d3 > 0);
+  return !(neg && pos);
+}
+static void triangulate(const std::vector<double> &xy, std::vector<std::array<double, 6>> &tris) {
+  int n = (int)xy.size() / 2;
+  if (n < 3) return;
+  std::vector<int> idx(n);
+  double area = 0;
+  for (int i = 0; i < n; ++i) {
+    int j = (i + 1) % n;
+    area += xy[2 * i] * xy[2 * j + 1] - xy[2 * j] * xy[2 * i + 1];
+  }
+  for (int i = 0; i < n; ++i) idx[i] = area >= 0 ? i : n - 1 - i;  // make CCW (polygon_utils.cpp:48-50)
+  int guard = 0;
+  while ((int)idx.size() > 3 && guard < 10 * n * n) {
+    int m = (int)idx.size();
+    bool clipped = false;
+    for (int i = 0; i < m; ++i) {
+      int ia = idx[(i + m - 1) % m], ib = idx[i], ic = idx[(i + 1) % m];
+      const double *a = &xy[2 * ia], *b = &xy[2 * ib], *c = &xy[2 * ic];
+      if (cross2(a[0], a[1], b[0], b[1], c[0], c[1]) <= 0) continue;  // reflex or degenerate
+      bool ear = true;
+      for (int k = 0; k < m && ear; ++k) {
+        int ik = idx[k];
+        if (ik == ia || ik == ib || ik == ic) continue;
+        if (in_tri(xy[2 * ik], xy[2 * ik + 1], a, b, c)) ear = false;
+      }
+      if (!ear) continue;
+      tris.push_back({a[0], a[1], b[0], b[1], c[0], c[1]});
+      idx.erase(idx.begin() + i);
+      clipped = true;
+      break;
+    }
+    ++guard;
+    if (!clipped) break;  // numerically degenerate: emit what is left as a fan
+  }
+  for (size_t i = 1; i + 1 < idx.size(); ++i) {
+    const double *a = &xy[2 * idx[0]], *b = &xy[2 * idx[i]], *c = &xy[2 * idx[i + 1]];
+    tris.push_back({a[0], a[1], b[0], b[1], c[0], c[1]});
+  }
+}
+
+}  // namespace
+
+extern "C" int ccb_abi_version(void) { return CCB_ABI_VERSION; }
+extern "C" const char *ccb_last_error(void) { return g_last_error.c_str(); }
+extern "C" uint64_t ccb_kernel_launch_count(void) { return g_launches.load(); }
+
+extern "C" int ccb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+extern "C" int ccb_cuda_available(void) { return ccb_device_count() > 0 ? 1 : 0; }
+
+extern "C" void ccb_params_default(ccb_params *p) {
+  p->pNumRobots = 32;
+  p->pResolution = 1.0;
+  p->pWorldMapSize = 1024;
+  p->pRobotMapSize = 1024;
+  p->pLocalMapSize = 256;
+  p->pUpdateRobotMap = 1;
+  p->pUpdateExplorationMap = 1;
+  p->pUpdateSensorView = 1;
+  p->pUpdateSystemMap = 1;
+  p->pTruncationBND = 2;
+  p->pNorm = 1;
+  p->pUnknownImportance = 0.5;
+  p->pRobotMapUseUnknownImportance = 0;
+  p->pSensorSize = 64;
+  p->pCommunicationRange = 128;
+  p->pMaxRobotSpeed = 5;
+  p->pRobotPosHistorySize = 20;
+  p->pTimeStep = 1;
+  p->pCheckOscillations = 1;
+}
+
+static int require_gpu() {
+  if (!ccb_cuda_available()) return fail("no CUDA device: this library has no CPU fallback");
+  return 0;
+}
+
+extern "C" ccb_idf *ccb_idf_create(const ccb_params *p, int device, void *stream) {
+  if (require_gpu()) return nullptr;
+  if (p->pWorldMapSize <= 0) {
+    fail("pWorldMapSize must be positive");
+    return nullptr;
+  }
+  auto idf = std::make_unique<ccb_idf>();
+  idf->p = *p;
+  idf->device = device;
+  idf->stream = (cudaStream_t)stream;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    fail("cudaSetDevice failed");
+    return nullptr;
+  }
+  size_t nn = (size_t)p->pWorldMapSize * p->pWorldMapSize;
+  if (cudaMalloc(&idf->d_map, nn * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&idf->d_max, sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&idf->d_factor, sizeof(float)) != cudaSuccess) {
+    fail("cudaMalloc failed (WorldIDF map)");
+    return nullptr;
+  }
+  cudaMemsetAsync(idf->d_map, 0, nn * sizeof(float), idf->stream);
+  return idf.release();
+}
+
+extern "C" void ccb_idf_destroy(ccb_idf *idf) {
+  if (!idf) return;
+  cudaSetDevice(idf->device);
+  cudaFree(idf->d_map);
+  cudaFree(idf->d_max);
+  cudaFree(idf->d_factor);
+  delete idf;
+}
+
+extern "C" int ccb_idf_add_bnd(ccb_idf *idf, double mx, double my, double sx, double sy, double rho, double sc) {
+  (void)rho;
+  // bivariate_normal_distribution.h:103-112: the general constructor tests the member rho_ (always
+  // 0) instead of its argument, so every distribution the reference ever holds has rho = 0.
+  idf->bnds.push_back({mx, my, sx, sy, sc, 0.0});
+  return 0;
+}
+
+extern "C" int ccb_idf_add_polygon(ccb_idf *idf, const double *xy, int n, float imp) {
+  if (n < 3) return fail("polygon needs at least 3 vertices");
+  ccb_idf::Poly poly;
+  poly.xy.assign(xy, xy + 2 * n);
+  poly.imp = imp;
+  idf->polys.push_back(std::move(poly));
+  return 0;
+}
+
+extern "C" int ccb_idf_num_features(const ccb_idf *idf) { return (int)(idf->bnds.size() + idf->polys.size()); }
+extern "C" int ccb_idf_num_bnds(const ccb_idf *idf) { return (int)idf->bnds.size(); }
+extern "C" int ccb_idf_num_polygons(const ccb_idf *idf) { return (int)idf->polys.size(); }
+extern "C" int ccb_idf_get_bnds(const ccb_idf *idf, double *out6, int cap) {
+  int n = std::min<int>(cap, (int)idf->bnds.size());
+  for (int i = 0; i < n; ++i) memcpy(out6 + 6 * i, idf->bnds[i].data(), 6 * sizeof(double));
+  return n;
+}
+extern "C" int ccb_idf_get_polygon(const ccb_idf *idf, int k, double *xy, int cap, float *imp) {
+  if (k < 0 || k >= (int)idf->polys.size()) return -1;
+  const auto &poly = idf->polys[k];
+  int n = (int)poly.xy.size() / 2;
+  if (imp) *imp = poly.imp;
+  if (xy) memcpy(xy, poly.xy.data(), sizeof(double) * 2 * std::min(n, cap));
+  return n;
+}
+
+extern "C" int ccb_idf_generate(ccb_idf *idf, int mode) {
+  if (mode != 0 && mode != 1) return fail("ccb_idf_generate: mode must be 0 or 1");
+  CCB_CUDA(cudaSetDevice(idf->device));
+  const ccb_params &p = idf->p;
+  const int N = p.pWorldMapSize;
+  const int F = (int)idf->bnds.size();
+  cudaStream_t st = idf->stream;
+
+  // feature records, fp32 as the reference packs them (world_idf.cpp:111-123)
+  std::vector<BndF> hb(std::max(F, 1));
+  for (int i = 0; i < F; ++i) {
+    const auto &b = idf->bnds[i];
+    hb[i] = {(float)b[0], (float)b[1], (float)b[2], (float)b[3], (float)b[4], (float)b[5]};
+  }
+  // polygon pieces (world_idf.cpp:125-153)
+  std::vector<float> px, py, imp;
+  std::vector<int> start, sz;
+  std::vector<float4> bounds;
+  for (const auto &poly : idf->polys) {
+    std::vector<std::array<double, 6>> tris;
+    triangulate(poly.xy, tris);
+    for (const auto &t : tris) {
+      float4 b = make_float4(3.4028235e38f, 1.17549435e-38f, 3.4028235e38f, 1.17549435e-38f);  // generate_world_map.h:49-54
+      start.push_back((int)px.size());
+      for (int v = 0; v < 3; ++v) {
+        float x = (float)t[2 * v], y = (float)t[2 * v + 1];
+        px.push_back(x), py.push_back(y);
+        if (x < b.x) b.x = x;
+        if (x > b.y) b.y = x;
+        if (y < b.z) b.z = y;
+        if (y > b.w) b.w = y;
+      }
+      sz.push_back(3);
+      imp.push_back(poly.imp);
+      bounds.push_back(b);
+    }
+  }
+  const int NP = (int)sz.size();
+
+  BndF *d_b = nullptr;
+  float *d_px = nullptr, *d_py = nullptr, *d_imp = nullptr;
+  int *d_start = nullptr, *d_sz = nullptr;
+  float4 *d_bounds = nullptr;
+  CCB_CUDA(cudaMallocAsync(&d_b, sizeof(BndF) * hb.size(), st));
+  CCB_CUDA(cudaMemcpyAsync(d_b, hb.data(), sizeof(BndF) * hb.size(), cudaMemcpyHostToDevice, st));
+  if (NP > 0) {
+    CCB_CUDA(cudaMallocAsync(&d_px, sizeof(float) * px.size(), st));
+    CCB_CUDA(cudaMallocAsync(&d_py, sizeof(float) * py.size(), st));
+    CCB_CUDA(cudaMallocAsync(&d_imp, sizeof(float) * NP, st));
+    CCB_CUDA(cudaMallocAsync(&d_start, sizeof(int) * NP, st));
+    CCB_CUDA(cudaMallocAsync(&d_sz, sizeof(int) * NP, st));
+    CCB_CUDA(cudaMallocAsync(&d_bounds, sizeof(float4) * NP, st));
+    CCB_CUDA(cudaMemcpyAsync(d_px, px.data(), sizeof(float) * px.size(), cudaMemcpyHostToDevice, st));
+    CCB_CUDA(cudaMemcpyAsync(d_py, py.data(), sizeof(float) * py.size(), cudaMemcpyHostToDevice, st));
+    CCB_CUDA(cudaMemcpyAsync(d_imp, imp.data(), sizeof(float) * NP, cudaMemcpyHostToDevice, st));
+    CCB_CUDA(cudaMemcpyAsync(d_start, start.data(), sizeof(int) * NP, cudaMemcpyHostToDevice, st));
+    CCB_CUDA(cudaMemcpyAsync(d_sz, sz.data(), sizeof(int) * NP, cudaMemcpyHostToDevice, st));
+    CCB_CUDA(cudaMemcpyAsync(d_bounds, bounds.data(), sizeof(float4) * NP, cudaMemcpyHostToDevice, st));
+  }
+  PolyDev pd{d_px, d_py, d_start, d_sz, d_imp, d_bounds, NP};
+
+  const int init = (int)0x80000000;
+  CCB_CUDA(cudaMemcpyAsync(idf->d_max, &init, sizeof(int), cudaMemcpyHostToDevice, st));
+  const float res = (float)p.pResolution;
+  const float trun = (float)p.pTruncationBND;
+  const float trun_sq = trun * trun;                       // generate_world_map.cu:188-189
+  const float one_by_sqrt2 = (float)(1. / std::sqrt(2.));  // generate_world_map.cu:190-192
+  dim3 grid((N + IDF_TY - 1) / IDF_TY, (N + IDF_TX - 1) / IDF_TX);
+  if (mode == 0)
+    k_idf_generate<0><<<grid, IDF_THREADS, 0, st>>>(d_b, F, pd, N, res, trun_sq, one_by_sqrt2, idf->d_map, idf->d_max);
+  else
+    k_idf_generate<1><<<grid, IDF_THREADS, 0, st>>>(d_b, F, pd, N, res, trun_sq, one_by_sqrt2, idf->d_map, idf->d_max);
+  CCB_LAUNCH_CHECK();
+  k_idf_factor<<<1, 1, 0, st>>>(idf->d_max, (float)p.pNorm, idf->d_factor);
+  CCB_LAUNCH_CHECK();
+  size_t nn = (size_t)N * N;
+  k_idf_normalize<<<148 * 4, 256, 0, st>>>(idf->d_map, nn / 4, nn, idf->d_factor);
+  CCB_LAUNCH_CHECK();
+  idf->factor_valid = false;
+  CCB_CUDA(cudaFreeAsync(d_b, st));
+  if (NP > 0) {
+    CCB_CUDA(cudaFreeAsync(d_px, st));
+    CCB_CUDA(cudaFreeAsync(d_py, st));
+    CCB_CUDA(cudaFreeAsync(d_imp, st));
+    CCB_CUDA(cudaFreeAsync(d_start, st));
+    CCB_CUDA(cudaFreeAsync(d_sz, st));
+    CCB_CUDA(cudaFreeAsync(d_bounds, st));
+  }
+  return 0;
+}
+
+extern "C" int ccb_idf_get_map(ccb_idf *idf, float *out) {
+  CCB_CUDA(cudaSetDevice(idf->device));
+  size_t nn = (size_t)idf->p.pWorldMapSize * idf->p.pWorldMapSize;
+  CCB_CUDA(cudaMemcpyAsync(out, idf->d_map, nn * sizeof(float), cudaMemcpyDeviceToHost, idf->stream));
+  CCB_CUDA(cudaStreamSynchronize(idf->stream));
+  return 0;
+}
+
+extern "C" int ccb_idf_set_map(ccb_idf *idf, const float *in) {
+  CCB_CUDA(cudaSetDevice(idf->device));
+  size_t nn = (size_t)idf->p.pWorldMapSize * idf->p.pWorldMapSize;
+  CCB_CUDA(cudaMemcpyAsync(idf->d_map, in, nn * sizeof(float), cudaMemcpyHostToDevice, idf->stream));
+  CCB_CUDA(cudaStreamSynchronize(idf->stream));
+  return 0;
+}
+
+extern "C" const float *ccb_idf_map_dev(const ccb_idf *idf) { return idf->d_map; }
+
+extern "C" int ccb_idf_norm_factor(ccb_idf *idf, float *out) {
+  if (!idf->factor_valid) {
+    CCB_CUDA(cudaSetDevice(idf->device));
+    CCB_CUDA(cudaMemcpyAsync(&idf->h_factor, idf->d_factor, sizeof(float), cudaMemcpyDeviceToHost, idf->stream));
+    CCB_CUDA(cudaStreamSynchronize(idf->stream));
+    idf->factor_valid = true;
+  }
+  *out = idf->h_factor;
+  return 0;
+}
+
+// =================================================================================================
+// CoverageSystem batch
+// =================================================================================================
+struct ResizeTab {
+  int C = 0, kmax = 0;
+  int *d_xmin = nullptr, *d_xsize = nullptr;
+  float *d_w = nullptr;
+};
+
+struct ccb_env {
+  ccb_params p;
+  int E = 0, R = 0, device = 0;
+  cudaStream_t stream = nullptr;
+  EnvDev d{};
+  double *d_sums = nullptr;     // [E][R][4] global Voronoi moments (world map)
+  CellsOut cells{};             // env-level cells (ComputeVoronoiCells)
+  double *d_objective = nullptr;  // [E]
+  double *d_stage = nullptr;    // [E][R][2] staging for host-provided actions / positions
+  double *d_feat = nullptr;     // [E][R][7]
+  double *d_ratio = nullptr;    // [E][3]
+  float *d_scratch = nullptr;   // max(N*N, L*L) floats for host getters
+  double *h_pin = nullptr;      // pinned host staging, E*R*CCB_MAX_CELL_VERTS*2 doubles
+  size_t h_pin_bytes = 0;
+  uint64_t pos_version = 1;     // bumped whenever positions or the world map change
+  uint64_t cells_version = 0;   // pos_version the env-level cells were computed for
+  bool cells_have_polys = false;
+  bool initialised = false;
+  std::map<int, ResizeTab> resize;
+  int vor_rpw_override = 0;
+};
+
+static int pick_rpw(const ccb_env *env, int region_rows, int region_cols, int regions) {
+  if (env->vor_rpw_override > 0) return env->vor_rpw_override;
+  const int tiles_y = (region_cols + VOR_TY - 1) / VOR_TY + 1;
+  for (int rpw = 16; rpw > 1; rpw >>= 1) {
+    long tiles_x = (region_rows + VOR_WARPS * rpw - 1) / (VOR_WARPS * rpw);
+    if ((long)regions * tiles_x * tiles_y >= 4L * 148) return rpw;
+  }
+  return 1;
+}
+
+static size_t vor_smem(int R) { return (size_t)R * (2 * sizeof(double) + 2 * sizeof(int)) + VOR_WARPS * 32 * sizeof(int); }
+
+// Voronoi label + reduce over the full map of every environment; sums must be a [E][R][4] buffer.
+static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *labels = nullptr) {
+  const EnvDev &d = env->d;
+  CCB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * d.E * d.R, env->stream));
+  VorArgs a;
+  a.d = d, a.single = 0, a.src = src, a.sums = sums, a.labels = labels;
+  a.rpw = pick_rpw(env, d.N, d.N, d.E);
+  a.tiles_y = (d.N + VOR_TY - 1) / VOR_TY;
+  a.tiles_x = (d.N + VOR_WARPS * a.rpw - 1) / (VOR_WARPS * a.rpw);
+  dim3 grid(a.tiles_x * a.tiles_y, 1, d.E);
+  k_voronoi<<<grid, VOR_THREADS, vor_smem(d.R), env->stream>>>(a);
+  CCB_LAUNCH_CHECK();
+  return 0;
+}
+
+// per-robot L-window variant (DecentralizedCVT): only the robot's own cell is reduced
+static int launch_voronoi_single(ccb_env *env, double *sums) {
+  const EnvDev &d = env->d;
+  CCB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * d.E * d.R, env->stream));
+  VorArgs a;
+  a.d = d, a.single = 1, a.src = SRC_ROBOT, a.sums = sums, a.labels = nullptr;
+  a.rpw = pick_rpw(env, d.L, d.L, d.E * d.R);
+  a.tiles_y = (d.L + VOR_TY - 1) / VOR_TY + 1;  // the window is not 128-aligned
+  a.tiles_x = (d.L + VOR_WARPS * a.rpw - 1) / (VOR_WARPS * a.rpw);
+  dim3 grid(a.tiles_x * a.tiles_y, d.R, d.E);
+  k_voronoi<<<grid, VOR_THREADS, vor_smem(d.R), env->stream>>>(a);
+  CCB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_finalize(ccb_env *env, const double *sums, CellsOut out, int want_polys) {
+  const EnvDev &d = env->d;
+  int threads = std::min(256, ((d.R + 31) / 32) * 32);
+  k_finalize_cells<<<d.E, threads, 2 * d.R * sizeof(double), env->stream>>>(d, sums, out, want_polys);
+  CCB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int ensure_cells(ccb_env *env, bool want_polys) {
+  if (!env->initialised) return fail("environment has no robot positions yet (call ccb_env_reset)");
+  if (env->cells_version != env->pos_version) {
+    if (launch_voronoi_global(env, SRC_WORLD, env->d_sums)) return 1;
+    if (launch_finalize(env, env->d_sums, env->cells, want_polys ? 1 : 0)) return 1;
+    env->cells_version = env->pos_version;
+    env->cells_have_polys = want_polys;
+  } else if (want_polys && !env->cells_have_polys) {
+    if (launch_finalize(env, env->d_sums, env->cells, 1)) return 1;
+    env->cells_have_polys = true;
+  }
+  return 0;
+}
+
+static int alloc_cells(CellsOut &c, int E, int R, bool with_polys) {
+  size_t er = (size_t)E * R;
+  CCB_CUDA(cudaMalloc(&c.mass, er * sizeof(double)));
+  CCB_CUDA(cudaMalloc(&c.centroid, er * 2 * sizeof(double)));
+  CCB_CUDA(cudaMalloc(&c.obj, er * sizeof(double)));
+  if (with_polys) {
+    CCB_CUDA(cudaMalloc(&c.nverts, er * sizeof(int)));
+    CCB_CUDA(cudaMalloc(&c.verts, er * CCB_MAX_CELL_VERTS * 2 * sizeof(double)));
+  }
+  return 0;
+}
+static void free_cells(CellsOut &c) {
+  cudaFree(c.mass), cudaFree(c.centroid), cudaFree(c.obj), cudaFree(c.nverts), cudaFree(c.verts);
+  c = CellsOut{};
+}
+
+static int env_alloc(ccb_env *env) {
+  EnvDev &d = env->d;
+  const ccb_params &p = env->p;
+  const size_t nn = (size_t)d.N * d.N, er = (size_t)d.E * d.R;
+  CCB_CUDA(cudaMalloc(&d.world, sizeof(float) * nn * d.E));
+  CCB_CUDA(cudaMalloc(&d.seen, sizeof(uint32_t) * nn * d.W * d.E));
+  if (p.pUpdateExplorationMap) CCB_CUDA(cudaMalloc(&d.xseen, sizeof(uint32_t) * nn * d.W * d.E));
+  CCB_CUDA(cudaMalloc(&d.sys, nn * d.E));
+  CCB_CUDA(cudaMalloc(&d.pos_g, sizeof(double) * 2 * er));
+  CCB_CUDA(cudaMalloc(&d.pos_s, sizeof(double) * 2 * er));
+  CCB_CUDA(cudaMalloc(&d.pos_l, sizeof(double) * 2 * er));
+  CCB_CUDA(cudaMalloc(&d.hist, sizeof(double) * 2 * er * d.H));
+  CCB_CUDA(cudaMalloc(&d.hist_start, sizeof(int) * er));
+  CCB_CUDA(cudaMalloc(&d.hist_len, sizeof(int) * er));
+  CCB_CUDA(cudaMalloc(&d.status, sizeof(int) * d.E));
+  CCB_CUDA(cudaMalloc(&env->d_sums, sizeof(double) * 4 * er));
+  if (alloc_cells(env->cells, d.E, d.R, true)) return 1;
+  CCB_CUDA(cudaMalloc(&env->d_objective, sizeof(double) * d.E));
+  CCB_CUDA(cudaMalloc(&env->d_stage, sizeof(double) * 2 * er));
+  CCB_CUDA(cudaMalloc(&env->d_feat, sizeof(double) * 7 * er));
+  CCB_CUDA(cudaMalloc(&env->d_ratio, sizeof(double) * 3 * d.E));
+  CCB_CUDA(cudaMalloc(&env->d_scratch, sizeof(float) * std::max(nn, (size_t)d.L * d.L)));
+  env->h_pin_bytes = sizeof(double) * std::max<size_t>(er * CCB_MAX_CELL_VERTS * 2, 64);
+  CCB_CUDA(cudaMallocHost(&env->h_pin, env->h_pin_bytes));
+  CCB_CUDA(cudaMemsetAsync(d.world, 0, sizeof(float) * nn * d.E, env->stream));
+  CCB_CUDA(cudaMemsetAsync(d.seen, 0, sizeof(uint32_t) * nn * d.W * d.E, env->stream));
+  if (d.xseen) CCB_CUDA(cudaMemsetAsync(d.xseen, 0, sizeof(uint32_t) * nn * d.W * d.E, env->stream));
+  CCB_CUDA(cudaMemsetAsync(d.sys, 0, nn * d.E, env->stream));
+  CCB_CUDA(cudaMemsetAsync(d.status, 0, sizeof(int) * d.E, env->stream));
+  return 0;
+}
+
+extern "C" ccb_env *ccb_env_create(const ccb_params *p, int num_envs, int num_robots, int device, void *stream) {
+  if (require_gpu()) return nullptr;
+  if (num_envs < 1 || num_robots < 1) {
+    fail("ccb_env_create: need at least one environment and one robot");
+    return nullptr;
+  }
+  if (p->pRobotMapSize != p->pWorldMapSize) {
+    fail("pRobotMapSize must equal pWorldMapSize (robot maps share the world grid, robot_model.h:69)");
+    return nullptr;
+  }
+  if (p->pSensorSize <= 0 || p->pLocalMapSize <= 0 || p->pWorldMapSize <= 0) {
+    fail("map sizes must be positive");
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    fail("cudaSetDevice failed");
+    return nullptr;
+  }
+  auto env = std::make_unique<ccb_env>();
+  env->p = *p;
+  env->E = num_envs, env->R = num_robots, env->device = device;
+  env->stream = (cudaStream_t)stream;
+  EnvDev &d = env->d;
+  d.E = num_envs, d.R = num_robots, d.N = p->pWorldMapSize, d.S = p->pSensorSize, d.L = p->pLocalMapSize;
+  d.H = std::max(1, p->pRobotPosHistorySize);
+  d.W = (num_robots + 31) / 32;
+  d.res = p->pResolution;
+  d.fill = p->pRobotMapUseUnknownImportance ? (float)(p->pUnknownImportance * p->pNorm) : 0.f;
+  d.use_sensor = p->pUpdateSensorView, d.upd_robot = p->pUpdateRobotMap;
+  d.upd_expl = p->pUpdateExplorationMap, d.upd_sys = p->pUpdateSystemMap;
+  d.check_osc = p->pCheckOscillations;
+  d.comm_range = p->pCommunicationRange, d.max_speed = p->pMaxRobotSpeed, d.dt = p->pTimeStep;
+  if (const char *s = getenv("CCB_VOR_RPW")) env->vor_rpw_override = atoi(s);
+  if (env_alloc(env.get())) {
+    ccb_env_destroy(env.release());
+    return nullptr;
+  }
+  size_t smem = vor_smem(num_robots);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_voronoi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return env.release();
+}
+
+extern "C" void ccb_env_destroy(ccb_env *env) {
+  if (!env) return;
+  cudaSetDevice(env->device);
+  cudaStreamSynchronize(env->stream);
+  EnvDev &d = env->d;
+  cudaFree(d.world), cudaFree(d.seen), cudaFree(d.xseen), cudaFree(d.sys);
+  cudaFree(d.pos_g), cudaFree(d.pos_s), cudaFree(d.pos_l);
+  cudaFree(d.hist), cudaFree(d.hist_start), cudaFree(d.hist_len), cudaFree(d.status);
+  cudaFree(env->d_sums);
+  free_cells(env->cells);
+  cudaFree(env->d_objective), cudaFree(env->d_stage), cudaFree(env->d_feat), cudaFree(env->d_ratio);
+  cudaFree(env->d_scratch);
+  cudaFreeHost(env->h_pin);
+  for (auto &kv : env->resize) cudaFree(kv.second.d_xmin), cudaFree(kv.second.d_xsize), cudaFree(kv.second.d_w);
+  delete env;
+}
+
+extern "C" int ccb_env_num_envs(const ccb_env *env) { return env->E; }
+extern "C" int ccb_env_num_robots(const ccb_env *env) { return env->R; }
+extern "C" const float *ccb_env_world_dev(const ccb_env *env) { return env->d.world; }
+extern "C" const double *ccb_env_positions_dev(const ccb_env *env) { return env->d.pos_g; }
+
+static int check_env_index(const ccb_env *env, int e) {
+  if (e < 0 || e >= env->E) return fail("environment index out of range");
+  return 0;
+}
+static int check_robot(const ccb_env *env, int r) {
+  if (r < 0 || r >= env->R) return fail("Robot index more than the number of robots");  // coverage_system.h:365-369
+  return 0;
+}
+
+extern "C" int ccb_env_set_world_dev(ccb_env *env, int e, const float *map_dev) {
+  if (check_env_index(env, e)) return 1;
+  CCB_CUDA(cudaSetDevice(env->device));
+  size_t nn = cell_count(env->d);
+  CCB_CUDA(cudaMemcpyAsync(env->d.world + nn * e, map_dev, nn * sizeof(float), cudaMemcpyDeviceToDevice, env->stream));
+  env->pos_version++;
+  return 0;
+}
+extern "C" int ccb_env_set_world_idf(ccb_env *env, int e, const ccb_idf *idf) {
+  if (idf->p.pWorldMapSize != env->p.pWorldMapSize) return fail("World map size does not match the specified size");
+  if (idf->stream != env->stream) cudaStreamSynchronize(idf->stream);
+  return ccb_env_set_world_dev(env, e, idf->d_map);
+}
+extern "C" int ccb_env_set_world_host(ccb_env *env, int e, const float *map) {
+  if (check_env_index(env, e)) return 1;
+  CCB_CUDA(cudaSetDevice(env->device));
+  size_t nn = cell_count(env->d);
+  CCB_CUDA(cudaMemcpyAsync(env->d.world + nn * e, map, nn * sizeof(float), cudaMemcpyHostToDevice, env->stream));
+  CCB_CUDA(cudaStreamSynchronize(env->stream));
+  env->pos_version++;
+  return 0;
+}
+
+static int launch_mark(ccb_env *env, int e, int robot, int mark_robot, int mark_sys) {
+  const EnvDev &d = env->d;
+  int chunks = std::max(1, (d.S * d.S + 1023) / 1024);
+  dim3 grid(chunks, robot >= 0 ? 1 : d.R, e >= 0 ? 1 : d.E);
+  k_mark_windows<<<grid, 256, 0, env->stream>>>(d, e, robot, mark_robot, mark_sys);
+  CCB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int stage_to_device(ccb_env *env, const double *host, size_t count, double *dev) {
+  // host -> pinned -> device on the env stream; the pinned buffer is reused, so wait for the copy
+  if (count * sizeof(double) > env->h_pin_bytes) return fail("staging buffer too small");
+  memcpy(env->h_pin, host, count * sizeof(double));
+  CCB_CUDA(cudaMemcpyAsync(dev, env->h_pin, count * sizeof(double), cudaMemcpyHostToDevice, env->stream));
+  CCB_CUDA(cudaStreamSynchronize(env->stream));
+  return 0;
+}
+
+extern "C" int ccb_env_reset(ccb_env *env, const double *positions) {
+  CCB_CUDA(cudaSetDevice(env->device));
+  const EnvDev &d = env->d;
+  const size_t nn = cell_count(d), er = (size_t)d.E * d.R;
+  if (stage_to_device(env, positions, 2 * er, env->d_stage)) return 1;
+  CCB_CUDA(cudaMemsetAsync(d.seen, 0, sizeof(uint32_t) * nn * d.W * d.E, env->stream));
+  if (d.xseen) CCB_CUDA(cudaMemsetAsync(d.xseen, 0, sizeof(uint32_t) * nn * d.W * d.E, env->stream));
+  CCB_CUDA(cudaMemsetAsync(d.sys, 0, nn * d.E, env->stream));
+  CCB_CUDA(cudaMemsetAsync(d.status, 0, sizeof(int) * d.E, env->stream));
+  k_init_positions<<<(int)((er + 255) / 256), 256, 0, env->stream>>>(d, env->d_stage);
+  CCB_LAUNCH_CHECK();
+  if (launch_mark(env, -1, -1, 1, 1)) return 1;
+  env->initialised = true;
+  env->pos_version++;
+  return 0;
+}
+
+extern "C" int ccb_env_step_actions(ccb_env *env, const double *actions, int *bad_env) {
+  CCB_CUDA(cudaSetDevice(env->device));
+  const EnvDev &d = env->d;
+  const size_t er = (size_t)d.E * d.R;
+  if (bad_env) *bad_env = -1;
+  if (stage_to_device(env, actions, 2 * er, env->d_stage)) return 1;
+  k_move<<<(int)((er + 255) / 256), 256, 0, env->stream>>>(d, env->d_stage, nullptr);
+  CCB_LAUNCH_CHECK();
+  if (launch_mark(env, -1, -1, 1, 1)) return 1;
+  env->pos_version++;
+  return 0;
+}
+
+// device-resident variant used by the roll-out (actions already on the device)
+static int step_actions_dev(ccb_env *env, const double *actions_dev) {
+  const EnvDev &d = env->d;
+  const size_t er = (size_t)d.E * d.R;
+  k_move<<<(int)((er + 255) / 256), 256, 0, env->stream>>>(d, actions_dev, nullptr);
+  CCB_LAUNCH_CHECK();
+  if (launch_mark(env, -1, -1, 1, 1)) return 1;
+  env->pos_version++;
+  return 0;
+}
+
+__global__ void k_step_control(EnvDev d, int e, int r, double dx, double dy, double sp) {
+  // robot_model.h:200-226 after the validity test, then SetRobotPosition
+  const size_t er = (size_t)e * d.R + r;
+  eigen_normalize(dx, dy);
+  double lx = d.pos_l[2 * er], ly = d.pos_l[2 * er + 1];
+  if (sp > kEps) lx = lx + dx * sp * d.dt, ly = ly + dy * sp * d.dt;
+  double gx = lx + d.pos_s[2 * er], gy = ly + d.pos_s[2 * er + 1];
+  clamp_global(d, gx, gy);
+  d.pos_l[2 * er] = gx - d.pos_s[2 * er], d.pos_l[2 * er + 1] = gy - d.pos_s[2 * er + 1];
+  d.pos_g[2 * er] = gx, d.pos_g[2 * er + 1] = gy;
+}
+__global__ void k_post_history(EnvDev d, int e, int robot) {
+  // coverage_system.cpp:263-271 for all robots of env e (robot < 0) or one robot (:228-255)
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int r = robot < 0 ? t : robot;
+  if (t >= (robot < 0 ? d.R : 1)) return;
+  const size_t er = (size_t)e * d.R + r;
+  history_post_step(d, e, r, d.pos_g[2 * er], d.pos_g[2 * er + 1]);
+}
+
+extern "C" int ccb_env_step_control(ccb_env *env, int e, int robot, double dir_x, double dir_y, double speed) {
+  if (check_env_index(env, e) || check_robot(env, robot)) return 1;
+  CCB_CUDA(cudaSetDevice(env->device));
+  const EnvDev &d = env->d;
+  double sp = speed;
+  if (sp > d.max_speed) sp = d.max_speed;
+  double dn = std::sqrt(dir_x * dir_x + dir_y * dir_y);
+  bool invalid_dir = dn < kEps && sp >= kEps;
+  if (sp < 0 || invalid_dir) return 2;  // robot_model.h:208-216 (the reference throws)
+  k_step_control<<<1, 1, 0, env->stream>>>(d, e, robot, dir_x, dir_y, sp);
+  CCB_LAUNCH_CHECK();
+  if (launch_mark(env, e, robot, 1, 0)) return 1;
+  // PostStepCommands() for all robots (coverage_system.h:326-333)
+  if (launch_mark(env, e, -1, 0, 1)) return 1;
+  k_post_history<<<(d.R + 127) / 128, 128, 0, env->stream>>>(d, e, -1);
+  CCB_LAUNCH_CHECK();
+  env->pos_version++;
+  return 0;
+}
+
+extern "C" int ccb_env_set_positions(ccb_env *env, int e, int robot, int local, const double *positions) {
+  if (check_env_index(env, e)) return 1;
+  if (robot >= 0 && check_robot(env, robot)) return 1;
+  CCB_CUDA(cudaSetDevice(env->device));
+  const EnvDev &d = env->d;
+  const int count = robot < 0 ? d.R : 1;
+  if (stage_to_device(env, positions, 2 * (size_t)count, env->d_stage)) return 1;
+  // all robots: PostStepCommands() (history for all); one robot: PostStepCommands(robot_id)
+  k_set_positions<<<(count + 127) / 128, 128, 0, env->stream>>>(d, e, robot, local, env->d_stage, 1);
+  CCB_LAUNCH_CHECK();
+  if (launch_mark(env, e, robot, 1, 1)) return 1;
+  env->pos_version++;
+  return 0;
+}
+
+extern "C" int ccb_env_get_positions(ccb_env *env, double *out) {
+  CCB_CUDA(cudaSetDevice(env->device));
+  const size_t n = (size_t)env->E * env->R * 2;
+  CCB_CUDA(cudaMemcpyAsync(env->h_pin, env->d.pos_g, n * sizeof(double), cudaMemcpyDeviceToHost, env->stream));
+  CCB_CUDA(cudaStreamSynchronize(env->stream));
+  memcpy(out, env->h_pin, n * sizeof(double));
+  return 0;
+}
+
+extern "C" int ccb_env_clear_robot_maps(ccb_env *env, int e) {
+  // coverage_system.h:399-403 -> robot_model.h:180-196: refill, then re-sense at the current position
+  if (check_env_index(env, e)) return 1;
+  CCB_CUDA(cudaSetDevice(env->device));
+  const EnvDev &d = env->d;
+  const size_t nn = cell_count(d);
+  CCB_CUDA(cudaMemsetAsync(d.seen + nn * d.W * e, 0, sizeof(uint32_t) * nn * d.W, env->stream));
+  // the per-robot exploration maps are NOT cleared by the reference; only the robot-map bits are
+  // re-marked here (mark_robot also ORs xseen bits that are already set)
+  return launch_mark(env, e, -1, 1, 0);
+}
+
+__global__ void k_clear_explored(EnvDev d, int e) {
+  const size_t nn = cell_count(d);
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < nn; c += (size_t)gridDim.x * blockDim.x)
+    d.sys[(size_t)e * nn + c] &= (uint8_t)2;
+}
+extern "C" int ccb_env_clear_explored_idf(ccb_env *env, int e) {
+  if (check_env_index(env, e)) return 1;
+  CCB_CUDA(cudaSetDevice(env->device));
+  k_clear_explored<<<148 * 2, 256, 0, env->stream>>>(env->d, e);
+  CCB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ccb_env_map_dim(const ccb_env *env, int kind) {
+  if (kind <= CCB_MAP_ROBOT) return env->d.N;
+  if (kind == CCB_MAP_SENSOR_VIEW) return env->d.S;
+  return env->d.L;
+}
+
+extern "C" int ccb_env_get_map_dev(ccb_env *env, int e, int kind, int robot, float *out_dev) {
+  if (check_env_index(env, e)) return 1;
+  if (kind < 0 || kind > CCB_MAP_ROBOT_SYSTEM) return fail("unknown map kind");
+  if (kind >= CCB_MAP_ROBOT && check_robot(env, robot)) return 1;
+  if (kind >= CCB_MAP_SENSOR_VIEW && !env->initialised) return fail("environment has no robot positions yet");
+  CCB_CUDA(cudaSetDevice(env->device));
+  int dim = ccb_env_map_dim(env, kind);
+  int blocks = std::min(148 * 8, (dim * dim + 255) / 256);
+  k_materialize<<<blocks, 256, 0, env->stream>>>(env->d, e, kind, robot, out_dev);
+  CCB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ccb_env_get_map(ccb_env *env, int e, int kind, int robot, float *out) {
+  if (ccb_env_get_map_dev(env, e, kind, robot, env->d_scratch)) return 1;
+  int dim = ccb_env_map_dim(env, kind);
+  CCB_CUDA(cudaMemcpyAsync(out, env->d_scratch, sizeof(float) * dim * dim, cudaMemcpyDeviceToHost, env->stream));
+  CCB_CUDA(cudaStreamSynchronize(env->stream));
+  return 0;
+}
+
+extern "C" int ccb_env_local_maps_dev(ccb_env *env, float *out_dev) {
+  CCB_CUDA(cudaSetDevice(env->device));
+  const EnvDev &d = env->d;
+  k_raw_window_maps<<<dim3(d.L, d.R, d.E), 256, 0, env->stream>>>(d, CCB_MAP_LOCAL, out_dev);
+  CCB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int ccb_env_obstacle_maps_dev(ccb_env *env, float *out_dev) {
+  CCB_CUDA(cudaSetDevice(env->device));
+  const EnvDev &d = env->d;
+  k_raw_window_maps<<<dim3(d.L, d.R, d.E), 256, 0, env->stream>>>(d, CCB_MAP_OBSTACLE, out_dev);
+  CCB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int ccb_env_comm_maps_dev(ccb_env *env, int C, float *out_dev) {
+  CCB_CUDA(cudaSetDevice(env->device));
+  const EnvDev &d = env->d;
+  k_comm_maps<<<dim3(d.R, d.E), 128, 0, env->stream>>>(d, C, out_dev, (size_t)2 * C * C, 0);
+  CCB_LAUNCH_CHECK();
+  return 0;
+}
+
+// torch's antialias bilinear index/weight computation (ATen UpSampleKernel.cpp,
+// _compute_indices_weights_aa with the triangle filter), float arithmetic.
+static int get_resize_table(ccb_env *env, int C, ResizeTab **out) {
+  auto it = env->resize.find(C);
+  if (it != env->resize.end()) {
+    *out = &it->second;
+    return 0;
+  }
+  const int L = env->d.L;
+  const float scale = (float)L / (float)C;
+  const float support = scale >= 1.f ? scale : 1.f;  // interp_size/2 * scale
+  const float invscale = scale >= 1.f ? 1.f / scale : 1.f;
+  const int kmax = (int)std::ceil(support) * 2 + 1;
+  std::vector<int> xmin(C), xsize(C);
+  std::vector<float> w((size_t)C * kmax, 0.f);
+  for (int i = 0; i < C; ++i) {
+    float center = scale * ((float)i + 0.5f);
+    int lo = std::max((int)(center - support + 0.5f), 0);
+    int hi = std::min((int)(center + support + 0.5f), L);
+    xmin[i] = lo, xsize[i] = hi - lo;
+    float total = 0.f;
+    for (int j = 0; j < xsize[i]; ++j) {
+      float x = ((float)(j + lo) - center + 0.5f) * invscale;
+      x = std::fabs(x);
+      float v = x < 1.f ? 1.f - x : 0.f;
+      w[(size_t)i * kmax + j] = v;
+      total += v;
+    }
+    for (int j = 0; j < xsize[i]; ++j)
+      if (total != 0.f) w[(size_t)i * kmax + j] /= total;
+  }
+  ResizeTab t;
+  t.C = C, t.kmax = kmax;
+  CCB_CUDA(cudaMalloc(&t.d_xmin, sizeof(int) * C));
+  CCB_CUDA(cudaMalloc(&t.d_xsize, sizeof(int) * C));
+  CCB_CUDA(cudaMalloc(&t.d_w, sizeof(float) * C * kmax));
+  CCB_CUDA(cudaMemcpy(t.d_xmin, xmin.data(), sizeof(int) * C, cudaMemcpyHostToDevice));
+  CCB_CUDA(cudaMemcpy(t.d_xsize, xsize.data(), sizeof(int) * C, cudaMemcpyHostToDevice));
+  CCB_CUDA(cudaMemcpy(t.d_w, w.data(), sizeof(float) * C * kmax, cudaMemcpyHostToDevice));
+  env->resize[C] = t;
+  *out = &env->resize[C];
+  return 0;
+}
+
+extern "C" int ccb_env_cnn_input_dev(ccb_env *env, int C, int use_comm, float *out_dev) {
+  if (C < 1) return fail("CNN map size must be positive");
+  if (!env->initialised) return fail("environment has no robot positions yet");
+  CCB_CUDA(cudaSetDevice(env->device));
+  const EnvDev &d = env->d;
+  ResizeTab *t = nullptr;
+  if (get_resize_table(env, C, &t)) return 1;
+  const int nch = use_comm ? 4 : 2;
+  const size_t cc = (size_t)C * C, stride = cc * nch;
+  ResizeTable tab{t->d_xmin, t->d_xsize, t->d_w, t->kmax};
+  size_t smem = sizeof(float) * ((size_t)t->kmax * d.L + (size_t)t->kmax * C);
+  if (smem > 48 * 1024)
+    CCB_CUDA(cudaFuncSetAttribute(k_cnn_local_obstacle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // channel order of coverage_env_utils.py:264-276: [local, comm_x, comm_y, obstacle]
+  k_cnn_local_obstacle<<<dim3(C, d.R, d.E), 256, smem, env->stream>>>(d, C, tab, out_dev, stride, 0, cc * (nch - 1));
+  CCB_LAUNCH_CHECK();
+  if (use_comm) {
+    k_comm_maps<<<dim3(d.R, d.E), 128, 0, env->stream>>>(d, C, out_dev, stride, cc);
+    CCB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int ccb_env_comm_maps_cpp(ccb_env *env, int e, int C, float *out) {
+  // coverage_system.cpp:177-199, evaluated on the host from the current positions (R^2 work)
+  if (check_env_index(env, e)) return 1;
+  std::vector<double> pos((size_t)env->E * env->R * 2);
+  if (ccb_env_get_positions(env, pos.data())) return 1;
+  const int R = env->R;
+  const double *p = pos.data() + (size_t)e * R * 2;
+  const double res = env->p.pResolution, cr = env->p.pCommunicationRange;
+  std::fill(out, out + (size_t)R * 2 * C * C, 0.f);
+  const double center = C / 2. - res / 2.;
+  for (int r = 0; r < R; ++r) {
+    float *ox = out + (size_t)r * 2 * C * C, *oy = ox + (size_t)C * C;
+    for (int j = 0; j < R; ++j) {
+      if (j == r) continue;
+      double dx, dy;
+      if (j > r) dx = p[2 * j] - p[2 * r], dy = p[2 * j + 1] - p[2 * r + 1];
+      else dx = -(p[2 * r] - p[2 * j]), dy = -(p[2 * r + 1] - p[2 * j + 1]);
+      if (!(std::sqrt(dx * dx + dy * dy) < cr)) continue;
+      int ix = (int)std::round(dx * C / (cr * res * 2.) + center);
+      int iy = (int)std::round(dy * C / (cr * res * 2.) + center);
+      if (ix < 0 || ix >= C || iy < 0 || iy >= C) continue;
+      ox[ix * C + iy] += (float)(dx / cr);
+      oy[ix * C + iy] += (float)(dy / cr);
+    }
+  }
+  return 0;
+}
+
+extern "C" int ccb_env_compute_voronoi(ccb_env *env) {
+  CCB_CUDA(cudaSetDevice(env->device));
+  return ensure_cells(env, false);
+}
+
+extern "C" int ccb_env_get_cells(ccb_env *env, int e, double *mass, double *centroid, double *site,
+                                 double *sum_dist_sqr, int *nverts, double *verts) {
+  if (check_env_index(env, e)) return 1;
+  CCB_CUDA(cudaSetDevice(env->device));
+  const bool polys = nverts != nullptr || verts != nullptr;
+  if (ensure_cells(env, polys)) return 1;
+  const int R = env->R;
+  const size_t off = (size_t)e * R;
+  cudaStream_t st = env->stream;
+  if (mass) CCB_CUDA(cudaMemcpyAsync(mass, env->cells.mass + off, sizeof(double) * R, cudaMemcpyDeviceToHost, st));
+  if (centroid) CCB_CUDA(cudaMemcpyAsync(centroid, env->cells.centroid + 2 * off, sizeof(double) * 2 * R, cudaMemcpyDeviceToHost, st));
+  if (site) CCB_CUDA(cudaMemcpyAsync(site, env->d.pos_g + 2 * off, sizeof(double) * 2 * R, cudaMemcpyDeviceToHost, st));
+  if (sum_dist_sqr) CCB_CUDA(cudaMemcpyAsync(sum_dist_sqr, env->cells.obj + off, sizeof(double) * R, cudaMemcpyDeviceToHost, st));
+  if (nverts) CCB_CUDA(cudaMemcpyAsync(nverts, env->cells.nverts + off, sizeof(int) * R, cudaMemcpyDeviceToHost, st));
+  if (verts)
+    CCB_CUDA(cudaMemcpyAsync(verts, env->cells.verts + off * CCB_MAX_CELL_VERTS * 2,
+                             sizeof(double) * R * CCB_MAX_CELL_VERTS * 2, cudaMemcpyDeviceToHost, st));
+  CCB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int ccb_env_voronoi_labels(ccb_env *env, int src, int32_t *out /* E x N x N, host */) {
+  // parity-test accessor: the label the fused kernel assigns to every cell (never stored otherwise)
+  if (!env->initialised) return fail("environment has no robot positions yet");
+  if (src != SRC_WORLD && src != SRC_EXPLORED) return fail("labels: src must be 0 (world) or 1 (explored)");
+  CCB_CUDA(cudaSetDevice(env->device));
+  const EnvDev &d = env->d;
+  const size_t n = cell_count(d) * d.E;
+  int *d_labels = nullptr;
+  double *d_tmp = nullptr;
+  CCB_CUDA(cudaMalloc(&d_labels, sizeof(int) * n));
+  CCB_CUDA(cudaMalloc(&d_tmp, sizeof(double) * 4 * d.E * d.R));
+  CCB_CUDA(cudaMemsetAsync(d_labels, 0xff, sizeof(int) * n, env->stream));
+  int st = launch_voronoi_global(env, src, d_tmp, d_labels);
+  if (!st) {
+    cudaError_t err = cudaMemcpyAsync(out, d_labels, sizeof(int) * n, cudaMemcpyDeviceToHost, env->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(env->stream);
+    if (err != cudaSuccess) st = fail("CUDA error", cudaGetErrorString(err));
+  }
+  cudaFree(d_labels);
+  cudaFree(d_tmp);
+  return st;
+}
+
+static int objective_dev(ccb_env *env, double *out_dev) {
+  if (ensure_cells(env, false)) return 1;
+  k_objective<<<env->E, 32, 0, env->stream>>>(env->d, env->cells.obj, out_dev);
+  CCB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ccb_env_objective(ccb_env *env, double *out) {
+  CCB_CUDA(cudaSetDevice(env->device));
+  if (objective_dev(env, env->d_objective)) return 1;
+  CCB_CUDA(cudaMemcpyAsync(env->h_pin, env->d_objective, sizeof(double) * env->E, cudaMemcpyDeviceToHost, env->stream));
+  CCB_CUDA(cudaStreamSynchronize(env->stream));
+  memcpy(out, env->h_pin, sizeof(double) * env->E);
+  return 0;
+}
+
+extern "C" int ccb_env_voronoi_features(ccb_env *env, double *out) {
+  if (!env->initialised) return fail("environment has no robot positions yet");
+  CCB_CUDA(cudaSetDevice(env->device));
+  k_voronoi_features<<<dim3(env->R, env->E), 256, 0, env->stream>>>(env->d, env->d_feat);
+  CCB_LAUNCH_CHECK();
+  const size_t n = (size_t)env->E * env->R * 7;
+  CCB_CUDA(cudaMemcpyAsync(env->h_pin, env->d_feat, sizeof(double) * n, cudaMemcpyDeviceToHost, env->stream));
+  CCB_CUDA(cudaStreamSynchronize(env->stream));
+  memcpy(out, env->h_pin, sizeof(double) * n);
+  return 0;
+}
+
+extern "C" int ccb_env_exploration_ratios(ccb_env *env, double *out) {
+  CCB_CUDA(cudaSetDevice(env->device));
+  const EnvDev &d = env->d;
+  CCB_CUDA(cudaMemsetAsync(env->d_ratio, 0, sizeof(double) * 3 * d.E, env->stream));
+  k_ratio_sums<<<dim3(148, d.E), 256, 0, env->stream>>>(d, env->d_ratio);
+  CCB_LAUNCH_CHECK();
+  CCB_CUDA(cudaMemcpyAsync(env->h_pin, env->d_ratio, sizeof(double) * 3 * d.E, cudaMemcpyDeviceToHost, env->stream));
+  CCB_CUDA(cudaStreamSynchronize(env->stream));
+  for (int e = 0; e < d.E; ++e) {
+    const double *s = env->h_pin + 3 * e;
+    // coverage_system.h:557-571; exploration_map_ counts cells NOT yet explored
+    out[2 * e] = 1.0 - ((double)d.N * d.N - s[0]) / ((double)d.N * d.N);
+    out[2 * e + 1] = s[1] / s[2];
+  }
+  return 0;
+}
+
+__global__ void k_check_osc(EnvDev d, int e, int r, int *out) { *out = check_oscillation(d, e, r) ? 1 : 0; }
+extern "C" int ccb_env_check_oscillation(ccb_env *env, int e, int robot, int *out) {
+  if (check_env_index(env, e) || check_robot(env, robot)) return 1;
+  CCB_CUDA(cudaSetDevice(env->device));
+  int *d_flag = reinterpret_cast<int *>(env->d_ratio);
+  k_check_osc<<<1, 1, 0, env->stream>>>(env->d, e, robot, d_flag);
+  CCB_LAUNCH_CHECK();
+  CCB_CUDA(cudaMemcpyAsync(env->h_pin, d_flag, sizeof(int), cudaMemcpyDeviceToHost, env->stream));
+  CCB_CUDA(cudaStreamSynchronize(env->stream));
+  *out = *reinterpret_cast<int *>(env->h_pin);
+  return 0;
+}
+
+extern "C" int ccb_env_sync(ccb_env *env) {
+  CCB_CUDA(cudaSetDevice(env->device));
+  CCB_CUDA(cudaStreamSynchronize(env->stream));
+  return 0;
+}
+
+// =================================================================================================
+// CVT controllers
+// =================================================================================================
+struct ccb_ctrl {
+  ccb_env *env = nullptr;
+  int kind = 0;
+  double *d_goals = nullptr;    // [E][R][2]
+  double *d_actions = nullptr;  // [E][R][2]
+  int *d_conv = nullptr;        // [E]
+  double *d_sums = nullptr;     // [E][R][4] (centralized / decentralized)
+  CellsOut cells{};             // centralized
+};
+
+static int ctrl_compute_goals(ccb_ctrl *c) {
+  ccb_env *env = c->env;
+  const EnvDev &d = env->d;
+  const size_t er = (size_t)d.E * d.R;
+  if (c->kind == CCB_CLAIRVOYANT) {
+    // clairvoyant_cvt.h:89-98: Voronoi on the world map == the env-level cells
+    if (ensure_cells(env, false)) return 1;
+    CCB_CUDA(cudaMemcpyAsync(c->d_goals, env->cells.centroid, sizeof(double) * 2 * er, cudaMemcpyDeviceToDevice, env->stream));
+  } else if (c->kind == CCB_CENTRALIZED) {
+    // centralized_cvt.h:90-100: Voronoi on the explored-IDF map
+    if (launch_voronoi_global(env, SRC_EXPLORED, c->d_sums)) return 1;
+    if (launch_finalize(env, c->d_sums, c->cells, 0)) return 1;
+    CCB_CUDA(cudaMemcpyAsync(c->d_goals, c->cells.centroid, sizeof(double) * 2 * er, cudaMemcpyDeviceToDevice, env->stream));
+  } else {
+    if (launch_voronoi_single(env, c->d_sums)) return 1;
+    int threads = std::min(256, ((d.R + 31) / 32) * 32);
+    k_finalize_single<<<d.E, threads, 0, env->stream>>>(d, c->d_sums, c->d_goals);
+    CCB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" ccb_ctrl *ccb_ctrl_create(ccb_env *env, int kind) {
+  if (kind < CCB_CLAIRVOYANT || kind > CCB_DECENTRALIZED) {
+    fail("unknown controller kind");
+    return nullptr;
+  }
+  if (!env->initialised) {
+    fail("environment has no robot positions yet (call ccb_env_reset)");
+    return nullptr;
+  }
+  cudaSetDevice(env->device);
+  auto c = std::make_unique<ccb_ctrl>();
+  c->env = env, c->kind = kind;
+  const size_t er = (size_t)env->E * env->R;
+  bool ok = cudaMalloc(&c->d_goals, sizeof(double) * 2 * er) == cudaSuccess &&
+            cudaMalloc(&c->d_actions, sizeof(double) * 2 * er) == cudaSuccess &&
+            cudaMalloc(&c->d_conv, sizeof(int) * env->E) == cudaSuccess &&
+            cudaMalloc(&c->d_sums, sizeof(double) * 4 * er) == cudaSuccess;
+  if (ok && kind == CCB_CENTRALIZED) ok = alloc_cells(c->cells, env->E, env->R, false) == 0;
+  if (!ok) {
+    fail("cudaMalloc failed (controller)");
+    ccb_ctrl_destroy(c.release());
+    return nullptr;
+  }
+  cudaMemsetAsync(c->d_actions, 0, sizeof(double) * 2 * er, env->stream);
+  cudaMemsetAsync(c->d_conv, 0, sizeof(int) * env->E, env->stream);
+  if (ctrl_compute_goals(c.get())) {  // the reference constructors call ComputeGoals()
+    ccb_ctrl_destroy(c.release());
+    return nullptr;
+  }
+  return c.release();
+}
+
+extern "C" void ccb_ctrl_destroy(ccb_ctrl *c) {
+  if (!c) return;
+  cudaSetDevice(c->env->device);
+  cudaStreamSynchronize(c->env->stream);
+  cudaFree(c->d_goals), cudaFree(c->d_actions), cudaFree(c->d_conv), cudaFree(c->d_sums);
+  free_cells(c->cells);
+  delete c;
+}
+
+static int ctrl_compute_actions_async(ccb_ctrl *c) {
+  ccb_env *env = c->env;
+  const EnvDev &d = env->d;
+  if (ctrl_compute_goals(c)) return 1;
+  int threads = std::min(1024, ((d.R + 31) / 32) * 32);
+  k_actions<<<d.E, threads, 0, env->stream>>>(d, c->d_goals, c->d_actions, c->d_conv);
+  CCB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ccb_ctrl_compute_actions(ccb_ctrl *c) {
+  CCB_CUDA(cudaSetDevice(c->env->device));
+  return ctrl_compute_actions_async(c);
+}
+
+static int d2h_doubles(ccb_env *env, const double *dev, double *out, size_t n) {
+  if (n * sizeof(double) > env->h_pin_bytes) return fail("staging buffer too small");
+  CCB_CUDA(cudaMemcpyAsync(env->h_pin, dev, n * sizeof(double), cudaMemcpyDeviceToHost, env->stream));
+  CCB_CUDA(cudaStreamSynchronize(env->stream));
+  memcpy(out, env->h_pin, n * sizeof(double));
+  return 0;
+}
+
+extern "C" int ccb_ctrl_get_actions(ccb_ctrl *c, double *out) {
+  CCB_CUDA(cudaSetDevice(c->env->device));
+  if (d2h_doubles(c->env, c->d_actions, out, (size_t)c->env->E * c->env->R * 2)) return 1;
+  if (c->kind == CCB_DECENTRALIZED) {
+    // surface the reference's "Goal out of bounds" exception (decentralized_cvt.h:127-141)
+    std::vector<int> st(c->env->E);
+    CCB_CUDA(cudaMemcpy(st.data(), c->env->d.status, sizeof(int) * c->env->E, cudaMemcpyDeviceToHost));
+    for (int e = 0; e < c->env->E; ++e)
+      if (st[e] & 1) {
+        fail("Goal out of bounds: this should not have happened for convex environments");
+        return 2;
+      }
+  }
+  return 0;
+}
+extern "C" int ccb_ctrl_get_goals(ccb_ctrl *c, double *out) {
+  CCB_CUDA(cudaSetDevice(c->env->device));
+  return d2h_doubles(c->env, c->d_goals, out, (size_t)c->env->E * c->env->R * 2);
+}
+extern "C" int ccb_ctrl_is_converged(ccb_ctrl *c, int *out) {
+  CCB_CUDA(cudaSetDevice(c->env->device));
+  ccb_env *env = c->env;
+  CCB_CUDA(cudaMemcpyAsync(env->h_pin, c->d_conv, sizeof(int) * env->E, cudaMemcpyDeviceToHost, env->stream));
+  CCB_CUDA(cudaStreamSynchronize(env->stream));
+  memcpy(out, env->h_pin, sizeof(int) * env->E);
+  return 0;
+}
+extern "C" const double *ccb_ctrl_actions_dev(const ccb_ctrl *c) { return c->d_actions; }
+
+extern "C" int ccb_ctrl_rollout(ccb_ctrl *c, int steps, int with_objective, double *objective_dev_out) {
+  CCB_CUDA(cudaSetDevice(c->env->device));
+  ccb_env *env = c->env;
+  for (int s = 0; s < steps; ++s) {
+    if (ctrl_compute_actions_async(c)) return 1;
+    if (step_actions_dev(env, c->d_actions)) return 1;
+    if (with_objective) {
+      double *dst = objective_dev_out ? objective_dev_out + (size_t)s * env->E : env->d_objective;
+      if (objective_dev(env, dst)) return 1;
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,309 @@
+// idf.cuh -- WorldIDF generation on the GPU.
+//
+// Replaces reference cppsrc/core/src/cuda/generate_world_map.cu:146-280 (kernel, normalize,
+// thrust::max_element, host wrapper).  Same arithmetic, different machine mapping:
+//   * threadIdx.x runs along y (the contiguous axis) and each thread owns 4 consecutive cells,
+//     so stores are coalesced float4 (the reference strides by N);
+//   * the features are culled per tile and their 1-D erfc factors are tabulated once per tile
+//     in shared memory: every cell-feature pair costs one FFMA + compare for the truncation test
+//     and 4 FMUL + 4 FFMA when in range, instead of 8 erfcf + 10 IEEE divides.
+// Mode 0 reproduces the reference kernel's floating-point operation order exactly (the 1-D
+// factors are the same function of the same fp32 arguments, so tabulating them changes no bit).
+#pragma once
+
+#include "common.cuh"
+
+namespace ccb {
+
+struct BndF {
+  float mx, my, sx, sy, sc, rho;  // generate_world_map.h:42-46
+};
+
+struct PolyDev {
+  const float *x, *y;   // concatenated piece vertices
+  const int *start;     // piece k occupies [start[k], start[k]+sz[k])
+  const int *sz;
+  const float *imp;
+  const float4 *bounds; // xmin, xmax, ymin, ymax
+  int num;
+};
+
+constexpr int IDF_TX = 32;   // tile rows (x)
+constexpr int IDF_TY = 32;   // tile cols (y)
+constexpr int IDF_FC = 16;   // features tabulated per chunk
+constexpr int IDF_THREADS = 256;
+constexpr int IDF_MAXPOLY = 64;  // polygon pieces kept per tile before falling back to the full list
+
+// geometry_utils.cuh:44-54
+__device__ __forceinline__ int orientation_f(float px, float py, float qx, float qy, float rx, float ry) {
+  float qpx = __fsub_rn(qx, px), qpy = __fsub_rn(qy, py);
+  float rpx = __fsub_rn(rx, px), rpy = __fsub_rn(ry, py);
+  float c1 = __fmul_rn(qpx, rpy);
+  float c2 = __fmul_rn(qpy, rpx);
+  if (c1 > c2) return 1;
+  if (c1 < c2) return -1;
+  return 0;
+}
+
+// geometry_utils.cuh:60-101
+__device__ inline bool point_in_monotone_polygon(const float *x, const float *y, int sz, float rx, float ry) {
+  bool left = false, right = false;
+  for (int ct = 0; ct < sz; ++ct) {
+    int ctp1 = ct + 1;
+    if (ctp1 == sz) ctp1 = 0;
+    float yct = y[ct], yctp1 = y[ctp1];
+    float px, py, qx, qy;
+    if (yct < yctp1) {
+      if (ry < yct || ry > yctp1) continue;
+      px = x[ct], py = yct, qx = x[ctp1], qy = yctp1;
+    } else {
+      if (ry < yctp1 || ry > yct) continue;
+      qx = x[ct], qy = yct, px = x[ctp1], py = yctp1;
+    }
+    int o = orientation_f(px, py, qx, qy, rx, ry);
+    if (o == 0) return true;
+    if (o == 1) left = true;
+    if (o == -1) right = true;
+    if (left & right) return true;
+  }
+  return false;
+}
+
+__device__ __forceinline__ int float_to_ordered(float f) {
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) {
+  return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff);
+}
+
+// One CTA per IDF_TX x IDF_TY tile.  MODE 0: reference operation order.  MODE 1: separable
+// differences tabulated in fp64 (more accurate than the reference, same truncation support).
+template <int MODE>
+__global__ void __launch_bounds__(IDF_THREADS)
+k_idf_generate(const BndF *__restrict__ bnd, int F, PolyDev poly, int N, float res, float trun_sq,
+               float one_by_sqrt2, float *__restrict__ out, int *__restrict__ max_ordered) {
+  __shared__ int s_list[IDF_FC];
+  __shared__ int s_nlist;
+  __shared__ int s_scan_base;
+  __shared__ float s_tx[IDF_FC][IDF_TX];    // (mid.x - mu_x)/sigma_x
+  __shared__ float s_axl[IDF_FC][IDF_TX];   // MODE0: scale*erfc(left x) ; MODE1: scale/4*(erfc l - erfc r)
+  __shared__ float s_axr[IDF_FC][IDF_TX];   // MODE0: scale*erfc(right x)
+  __shared__ float s_ty2[IDF_FC][IDF_TY];   // ((mid.y - mu_y)/sigma_y)^2
+  __shared__ float s_eyl[IDF_FC][IDF_TY];   // MODE0: erfc(lower y)      ; MODE1: erfc l - erfc r
+  __shared__ float s_eyr[IDF_FC][IDF_TY];   // MODE0: erfc(upper y)
+  __shared__ int s_poly[IDF_MAXPOLY];
+  __shared__ int s_npoly;
+  __shared__ float s_red[IDF_THREADS / 32];
+
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.y * IDF_TX, y0 = blockIdx.x * IDF_TY;
+  const int lrow = tid >> 3, lcol = (tid & 7) * 4;
+  const int gx = x0 + lrow, gy = y0 + lcol;
+
+  // tile extent of the cell mid points, used for conservative culling
+  const float tile_xlo = x0 * res, tile_xhi = (min(x0 + IDF_TX, N)) * res;
+  const float tile_ylo = y0 * res, tile_yhi = (min(y0 + IDF_TY, N)) * res;
+
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+
+  if (tid == 0) s_scan_base = 0;
+  __syncthreads();
+  while (true) {
+    // ---- gather the next <= IDF_FC features whose truncation box touches this tile (ascending
+    //      feature index, so the accumulation order is the reference's loop order) -------------
+    const int base = s_scan_base;
+    __syncthreads();  // everyone has read the cursor before warp 0 advances it
+    if (base >= F) break;
+    if (tid < 32) {
+      const float T = sqrtf(trun_sq) * 1.0001f + 1e-3f;
+      int n = 0;
+      int f = base;
+      while (f < F && n < IDF_FC) {
+        const int ff = f + tid;
+        bool keep = false;
+        if (ff < F) {
+          BndF b = bnd[ff];
+          float rx = T * b.sx + res, ry = T * b.sy + res;
+          keep = !(b.mx + rx < tile_xlo || b.mx - rx > tile_xhi || b.my + ry < tile_ylo || b.my - ry > tile_yhi);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, keep);
+        const int room = IDF_FC - n;
+        int next_f = f + 32;
+        if (__popc(m) > room) {  // keep the first `room` hits, resume right after the last kept one
+          unsigned mm = m;
+          int last = 0;
+          for (int k = 0; k < room; ++k) {
+            last = __ffs(mm) - 1;
+            mm &= mm - 1;
+          }
+          m &= (last == 31) ? 0xffffffffu : ((1u << (last + 1)) - 1u);
+          next_f = f + last + 1;
+        }
+        if ((m >> tid) & 1u) s_list[n + __popc(m & ((1u << tid) - 1u))] = ff;
+        n += __popc(m);
+        f = next_f;
+      }
+      if (tid == 0) {
+        s_nlist = n;
+        s_scan_base = (n == IDF_FC) ? min(f, F) : F;
+      }
+    }
+    __syncthreads();
+    const int nl = s_nlist;
+    // ---- tabulate the 1-D factors ------------------------------------------------------------
+    for (int t = tid; t < nl * (IDF_TX + IDF_TY); t += IDF_THREADS) {
+      int k = t / (IDF_TX + IDF_TY);
+      int u = t - k * (IDF_TX + IDF_TY);
+      BndF b = bnd[s_list[k]];
+      bool is_x = u < IDF_TX;
+      int li = is_x ? u : u - IDF_TX;
+      int gi = (is_x ? x0 : y0) + li;
+      float mu = is_x ? b.mx : b.my, sg = is_x ? b.sx : b.sy;
+      float idx = (float)gi;
+      // generate_world_map.cu:155-159 as compiled: tr = fma(idx,res,res); mid = fma(idx,res,tr)*0.5
+      float hi = fmaf(idx, res, res);
+      float mid = __fmul_rn(fmaf(idx, res, hi), 0.5f);
+      float tm = __fdiv_rn(__fsub_rn(mid, mu), sg);  // generate_world_map.cu:105-106
+      if (MODE == 0) {
+        float al = __fdiv_rn(fmaf(idx, res, -mu), sg);     // generate_world_map.cu:80-81
+        float ar = __fdiv_rn(__fsub_rn(hi, mu), sg);
+        float el = erfcf(__fmul_rn(al, one_by_sqrt2));     // generate_world_map.cu:92
+        float er = erfcf(__fmul_rn(ar, one_by_sqrt2));
+        if (is_x) {
+          s_tx[k][li] = tm;
+          s_axl[k][li] = __fmul_rn(b.sc, el);
+          s_axr[k][li] = __fmul_rn(b.sc, er);
+        } else {
+          s_ty2[k][li] = __fmul_rn(tm, tm);
+          s_eyl[k][li] = el;
+          s_eyr[k][li] = er;
+        }
+      } else {
+        const double c = 0.70710678118654752440;
+        double lo = ((double)gi * (double)res - (double)mu) / (double)sg * c;
+        double up = ((double)(gi + 1) * (double)res - (double)mu) / (double)sg * c;
+        double diff = erfc(lo) - erfc(up);
+        if (is_x) {
+          s_tx[k][li] = tm;
+          s_axl[k][li] = (float)(0.25 * (double)b.sc * diff);
+        } else {
+          s_ty2[k][li] = __fmul_rn(tm, tm);
+          s_eyl[k][li] = (float)diff;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- accumulate ----------------------------------------------------------------------------
+    for (int k = 0; k < nl; ++k) {
+      float tx = s_tx[k][lrow];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float r2 = fmaf(tx, tx, s_ty2[k][lcol + c]);  // generate_world_map.cu:113 as compiled
+        if (r2 > trun_sq) continue;
+        if (MODE == 0) {
+          float axl = s_axl[k][lrow], axr = s_axr[k][lrow];
+          float eyl = s_eyl[k][lcol + c], eyr = s_eyr[k][lcol + c];
+          // generate_world_map.cu:116-119: +Q(bl) -Q(br) -Q(tl) +Q(tr), Q = (sc*ex)*ey/4
+          acc[c] = fmaf(__fmul_rn(axl, eyl), 0.25f, acc[c]);
+          acc[c] = fmaf(__fmul_rn(axr, eyl), -0.25f, acc[c]);
+          acc[c] = fmaf(__fmul_rn(axl, eyr), -0.25f, acc[c]);
+          acc[c] = fmaf(__fmul_rn(axr, eyr), 0.25f, acc[c]);
+        } else {
+          acc[c] = fmaf(s_axl[k][lrow], s_eyl[k][lcol + c], acc[c]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- polygon features (generate_world_map.cu:124-144) ----------------------------------------
+  if (poly.num > 0) {
+    if (tid == 0) s_npoly = 0;
+    __syncthreads();
+    for (int k = tid; k < poly.num; k += IDF_THREADS) {
+      float4 b = poly.bounds[k];
+      // mid points of the tile span [lo + res/2, hi - res/2]; test against the closed bbox
+      bool keep = !(tile_xhi < b.x || tile_xlo > b.y || tile_yhi < b.z || tile_ylo > b.w);
+      if (keep) {
+        int slot = atomicAdd(&s_npoly, 1);
+        if (slot < IDF_MAXPOLY) s_poly[slot] = k;
+      }
+    }
+    __syncthreads();
+    const int np = s_npoly;
+    if (np > 0 && gx < N) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (gy + c >= N) continue;
+        float fx = (float)gx, fy = (float)(gy + c);
+        float midx = __fmul_rn(fmaf(fx, res, fmaf(fx, res, res)), 0.5f);
+        float midy = __fmul_rn(fmaf(fy, res, fmaf(fy, res, res)), 0.5f);
+        float pim = 0.f;
+        int cnt = np <= IDF_MAXPOLY ? np : poly.num;
+        for (int q = 0; q < cnt; ++q) {
+          int k = np <= IDF_MAXPOLY ? s_poly[q] : q;
+          float4 b = poly.bounds[k];
+          if (midx < b.x || midx > b.y || midy < b.z || midy > b.w) continue;
+          int st = poly.start[k];
+          if (point_in_monotone_polygon(poly.x + st, poly.y + st, poly.sz[k], midx, midy))
+            pim = fmaxf(pim, poly.imp[k]);
+        }
+        acc[c] = __fadd_rn(acc[c], pim);  // generate_world_map.cu:161-163
+      }
+    }
+  }
+
+  // ---- store + tile max ------------------------------------------------------------------------
+  float vmax = -INFINITY;
+  if (gx < N) {
+    float *row = out + (size_t)gx * N;
+    if ((N & 3) == 0 && gy + 3 < N) {
+      *reinterpret_cast<float4 *>(row + gy) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      vmax = fmaxf(fmaxf(acc[0], acc[1]), fmaxf(acc[2], acc[3]));
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (gy + c < N) {
+          row[gy + c] = acc[c];
+          vmax = fmaxf(vmax, acc[c]);
+        }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  if ((tid & 31) == 0) s_red[tid >> 5] = vmax;
+  __syncthreads();
+  if (tid == 0) {
+    float m = s_red[0];
+#pragma unroll
+    for (int w = 1; w < IDF_THREADS / 32; ++w) m = fmaxf(m, s_red[w]);
+    if (m > -INFINITY) atomicMax(max_ordered, float_to_ordered(m));
+  }
+}
+
+// generate_world_map.cu:252-259 (factor) + :166-174 (normalize); the factor is computed on the
+// device from the map maximum so that no host round trip sits between the two kernels.
+__global__ void k_idf_factor(const int *max_ordered, float norm, float *factor) {
+  float mx = ordered_to_float(*max_ordered);
+  float f;
+  if ((double)mx < kEps) f = norm;
+  else f = __fdiv_rn(norm, mx);
+  *factor = f;
+}
+
+__global__ void k_idf_normalize(float *__restrict__ map, size_t n4, size_t n, const float *factor) {
+  const float f = *factor;
+  if (!((double)f > 1e-5)) return;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  float4 *m4 = reinterpret_cast<float4 *>(map);
+  for (size_t k = i; k < n4; k += stride) {
+    float4 v = m4[k];
+    v.x = __fmul_rn(v.x, f), v.y = __fmul_rn(v.y, f), v.z = __fmul_rn(v.z, f), v.w = __fmul_rn(v.w, f);
+    m4[k] = v;
+  }
+  for (size_t k = n4 * 4 + i; k < n; k += stride) map[k] = __fmul_rn(map[k], f);
+}
+
+}  // namespace ccb

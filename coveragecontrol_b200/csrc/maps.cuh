@@ -1,0 +1,466 @@
+// maps.cuh -- robot kinematics, sensor-window map updates, Voronoi cell finalisation, CVT actions
+// and dense map materialisation.
+//
+// Replaces reference robot_model.h:87-122,180-345, coverage_system.h:104-130,279-363 and
+// coverage_system.cpp:201-291.  The reference keeps (3 + 2R) dense N x N float maps per
+// environment and rewrites system_map_ = explored - exploration over the full map every step;
+// here the state is the world map plus per-cell "seen" bit masks (common.cuh) and every other map
+// is a view computed on demand.
+#pragma once
+
+#include "common.cuh"
+
+namespace ccb {
+
+// ---- value of the derived maps at one cell -----------------------------------------------------
+__device__ __forceinline__ float robot_map_value(const EnvDev &d, int e, int r, size_t cell) {
+  const size_t nn = cell_count(d);
+  uint32_t w = d.seen[((size_t)e * d.W + (r >> 5)) * nn + cell];
+  if (w & (1u << (r & 31))) return d.use_sensor ? d.world[(size_t)e * nn + cell] : 0.f;
+  return d.fill;
+}
+__device__ __forceinline__ float explored_value(const EnvDev &d, int e, size_t cell) {
+  const size_t nn = cell_count(d);
+  if (d.sys[(size_t)e * nn + cell] & 1) return d.use_sensor ? d.world[(size_t)e * nn + cell] : 0.f;
+  return 0.f;
+}
+__device__ __forceinline__ float exploration_value(const EnvDev &d, int e, size_t cell) {
+  return (d.sys[(size_t)e * cell_count(d) + cell] & 2) ? 0.f : 1.f;
+}
+// robot_model.h:137-148: per-robot exploration map (1 = unexplored), all zeros when disabled
+__device__ __forceinline__ float robot_exploration_value(const EnvDev &d, int e, int r, size_t cell) {
+  if (!d.upd_expl) return 0.f;
+  uint32_t w = d.xseen[((size_t)e * d.W + (r >> 5)) * cell_count(d) + cell];
+  return (w & (1u << (r & 31))) ? 0.f : 1.f;
+}
+
+// ---- sensor window marking ---------------------------------------------------------------------
+// robot_model.h:98-122 (UpdateRobotMap / UpdateExplorationMap) and coverage_system.h:104-118
+// (explored_idf / exploration windows).  grid = (chunks, R, E); env_sel/robot_sel < 0 means all.
+__global__ void k_mark_windows(EnvDev d, int env_sel, int robot_sel, int mark_robot, int mark_sys) {
+  const int e = env_sel >= 0 ? env_sel : blockIdx.z;
+  const int r = robot_sel >= 0 ? robot_sel : blockIdx.y;
+  const double *p = d.pos_g + ((size_t)e * d.R + r) * 2;
+  const Window w = make_window(d.res, p[0], p[1], d.S, d.N);
+  const int wh = w.y1 - w.y0, ww = w.x1 - w.x0;
+  const int total = ww * wh;
+  const size_t nn = cell_count(d);
+  uint32_t *seen = d.seen + ((size_t)e * d.W + (r >> 5)) * nn;
+  uint32_t *xseen = d.xseen ? d.xseen + ((size_t)e * d.W + (r >> 5)) * nn : nullptr;
+  uint8_t *sys = d.sys + (size_t)e * nn;
+  const uint32_t bit = 1u << (r & 31);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    int a = t / wh, b = t - a * wh;
+    size_t cell = (size_t)(w.x0 + a) * d.N + (w.y0 + b);
+    if (mark_robot) {
+      if (d.upd_robot) atomicOr(seen + cell, bit);
+      if (d.upd_expl) atomicOr(xseen + cell, bit);
+    }
+    if (mark_sys && d.upd_sys) sys[cell] = 3;  // every writer stores the same value
+  }
+}
+
+// ---- history (coverage_system.cpp:263-271) -----------------------------------------------------
+__device__ inline void history_post_step(const EnvDev &d, int e, int r, double gx, double gy) {
+  const size_t er = (size_t)e * d.R + r;
+  double *h = d.hist + er * d.H * 2;
+  int start = d.hist_start[er], len = d.hist_len[er];
+  if (len > 0 && len == d.H) {
+    // pop_front WITHOUT pushing, exactly as the reference does when the history is full
+    start = (start + 1) % d.H;
+    len -= 1;
+  } else {
+    int slot = (start + len) % d.H;
+    h[2 * slot] = gx, h[2 * slot + 1] = gy;
+    len += 1;
+  }
+  d.hist_start[er] = start, d.hist_len[er] = len;
+}
+
+// coverage_system.h:341-363
+__device__ inline bool check_oscillation(const EnvDev &d, int e, int r) {
+  if (!d.check_osc) return false;
+  const size_t er = (size_t)e * d.R + r;
+  const int len = d.hist_len[er], start = d.hist_start[er];
+  if (len < 3) return false;
+  const double *h = d.hist + er * d.H * 2;
+  const int last = (start + len - 1) % d.H;
+  const double lx = h[2 * last], ly = h[2 * last + 1];
+  const int span = min(6, len - 1);
+  int count = 0;
+  for (int k = 0; k < span; ++k) {
+    int s = (start + len - 1 - k) % d.H;
+    double dx = h[2 * s] - lx, dy = h[2 * s + 1] - ly;
+    if (sqrt(dx * dx + dy * dy) < kLargeEps) ++count;
+  }
+  return count > 2;
+}
+
+// robot_model.h:229-243
+__device__ __forceinline__ void clamp_global(const EnvDev &d, double &gx, double &gy) {
+  if (gx <= 0) gx = 0 + kLargeEps;
+  if (gy <= 0) gy = 0 + kLargeEps;
+  const double max_xy = d.N * d.res;
+  if (gx >= max_xy) gx = max_xy - kLargeEps;
+  if (gy >= max_xy) gy = max_xy - kLargeEps;
+}
+
+// Eigen normalized(): v / sqrt(v.v) when v.v > 0
+__device__ __forceinline__ void eigen_normalize(double &x, double &y) {
+  double z = x * x + y * y;
+  if (z > 0) {
+    double s = sqrt(z);
+    x = x / s;
+    y = y / s;
+  }
+}
+
+// coverage_system.h:279-291 StepActions + robot_model.h:200-256 StepControl/SetRobotPosition.
+// One thread per (env, robot).  limit[e] (may be null) = number of leading robots to move when the
+// host found an invalid control (the reference returns before PostStepCommands in that case).
+__global__ void k_move(EnvDev d, const double *__restrict__ actions, const int *__restrict__ limit) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= d.E * d.R) return;
+  const int e = idx / d.R, r = idx - e * d.R;
+  const int lim = limit ? limit[e] : d.R;
+  if (r >= lim) return;
+  const size_t er = (size_t)idx;
+  double ax = actions[2 * er], ay = actions[2 * er + 1];
+  double speed = sqrt(ax * ax + ay * ay);
+  double dx = ax, dy = ay;
+  eigen_normalize(dx, dy);
+  double sp = speed;
+  if (sp > d.max_speed) sp = d.max_speed;
+  eigen_normalize(dx, dy);
+  double lx = d.pos_l[2 * er], ly = d.pos_l[2 * er + 1];
+  if (sp > kEps) {
+    lx = lx + dx * sp * d.dt;
+    ly = ly + dy * sp * d.dt;
+  }
+  double gx = lx + d.pos_s[2 * er], gy = ly + d.pos_s[2 * er + 1];
+  clamp_global(d, gx, gy);
+  d.pos_l[2 * er] = gx - d.pos_s[2 * er];
+  d.pos_l[2 * er + 1] = gy - d.pos_s[2 * er + 1];
+  d.pos_g[2 * er] = gx;
+  d.pos_g[2 * er + 1] = gy;
+  if (lim == d.R) history_post_step(d, e, r, gx, gy);
+}
+
+// robot_model.h:228-286 SetRobotPosition (local != 0) / SetGlobalRobotPosition; positions are
+// R x 2 for env e (robot < 0) or one pair.  post != 0 pushes the history (PostStepCommands).
+__global__ void k_set_positions(EnvDev d, int e, int robot, int local, const double *__restrict__ pos,
+                                int post) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int count = robot < 0 ? d.R : 1;
+  if (t >= count) return;
+  const int r = robot < 0 ? t : robot;
+  const size_t er = (size_t)e * d.R + r;
+  double gx = pos[2 * t], gy = pos[2 * t + 1];
+  if (local) gx = gx + d.pos_s[2 * er], gy = gy + d.pos_s[2 * er + 1];
+  clamp_global(d, gx, gy);
+  d.pos_l[2 * er] = gx - d.pos_s[2 * er];
+  d.pos_l[2 * er + 1] = gy - d.pos_s[2 * er + 1];
+  d.pos_g[2 * er] = gx;
+  d.pos_g[2 * er + 1] = gy;
+  if (post) history_post_step(d, e, r, gx, gy);
+}
+
+// RobotModel::Initialize (robot_model.h:124-153) positions part + InitSetup history push
+__global__ void k_init_positions(EnvDev d, const double *__restrict__ pos) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= d.E * d.R) return;
+  const size_t er = (size_t)idx;
+  double gx = pos[2 * er], gy = pos[2 * er + 1];
+  d.pos_s[2 * er] = gx, d.pos_s[2 * er + 1] = gy;
+  d.pos_g[2 * er] = gx, d.pos_g[2 * er + 1] = gy;
+  d.pos_l[2 * er] = 0, d.pos_l[2 * er + 1] = 0;
+  d.hist_start[er] = 0, d.hist_len[er] = 0;
+  history_post_step(d, idx / d.R, idx % d.R, gx, gy);
+}
+
+// ---- convex cell polygon: rectangle clipped by the bisector half-planes --------------------------
+// Stands in for the CGAL arrangement face of voronoi.cpp:184-326; same vertex set.
+__device__ inline int clip_cell(const double *sx, const double *sy, int n, int k, double w, double h,
+                                double (*poly)[2], double (*tmp)[2]) {
+  int na = 4;
+  poly[0][0] = 0, poly[0][1] = 0, poly[1][0] = w, poly[1][1] = 0;
+  poly[2][0] = w, poly[2][1] = h, poly[3][0] = 0, poly[3][1] = h;
+  const double kx = sx[k], ky = sy[k];
+  for (int j = 0; j < n && na > 0; ++j) {
+    if (j == k) continue;
+    const double jx = sx[j], jy = sy[j];
+    const double nx = jx - kx, ny = jy - ky;
+    if (nx == 0 && ny == 0) continue;
+    const double c = ((jx * jx + jy * jy) - (kx * kx + ky * ky)) / 2.;
+    int nb = 0;
+    for (int v = 0; v < na; ++v) {
+      int u = (v + 1 == na) ? 0 : v + 1;
+      double vx = poly[v][0], vy = poly[v][1], ux = poly[u][0], uy = poly[u][1];
+      double dv = nx * vx + ny * vy - c, du = nx * ux + ny * uy - c;
+      bool vin = dv <= 0, uin = du <= 0;
+      if (vin && nb < CCB_MAX_CELL_VERTS) tmp[nb][0] = vx, tmp[nb][1] = vy, ++nb;
+      if (vin != uin && nb < CCB_MAX_CELL_VERTS) {
+        double t = dv / (dv - du);
+        tmp[nb][0] = vx + t * (ux - vx), tmp[nb][1] = vy + t * (uy - vy), ++nb;
+      }
+    }
+    int nc = 0;
+    for (int v = 0; v < nb; ++v) {
+      int pv = (v + nb - 1) % nb;
+      if (nb > 1 && tmp[v][0] == tmp[pv][0] && tmp[v][1] == tmp[pv][1]) continue;
+      poly[nc][0] = tmp[v][0], poly[nc][1] = tmp[v][1], ++nc;
+    }
+    na = nc;
+  }
+  return na;
+}
+
+struct CellsOut {
+  double *mass;      // [E][R]
+  double *centroid;  // [E][R][2]
+  double *obj;       // [E][R]  sum |c - site|^2 v
+  int *nverts;       // [E][R]
+  double *verts;     // [E][R][CCB_MAX_CELL_VERTS][2]
+};
+
+// Finalise the global Voronoi cells of every environment from the reduced moments
+// (voronoi.cpp:41-53 ComputeFinalCentroid incl. the vertex-mean fallback; voronoi.h:89-95 sums).
+// One CTA per environment, robots strided over threads.  Dynamic smem: 2 * R doubles.
+__global__ void k_finalize_cells(EnvDev d, const double *__restrict__ sums, CellsOut out, int want_polys) {
+  extern __shared__ double s_sites[];
+  double *s_x = s_sites, *s_y = s_sites + d.R;
+  const int e = blockIdx.x;
+  const double *pos = d.pos_g + (size_t)e * d.R * 2;
+  for (int k = threadIdx.x; k < d.R; k += blockDim.x) s_x[k] = pos[2 * k], s_y[k] = pos[2 * k + 1];
+  __syncthreads();
+  for (int r = threadIdx.x; r < d.R; r += blockDim.x) {
+    const size_t er = (size_t)e * d.R + r;
+    const double *s = sums + er * 4;
+    const double m = s[0];
+    const double px = s_x[r], py = s_y[r];
+    const double res = d.res;
+    const double mx = res * s[1], my = res * s[2];
+    out.mass[er] = m;
+    out.obj[er] = res * res * s[3] - 2. * (px * mx + py * my) + (px * px + py * py) * m;
+    double cx, cy;
+    int nv = 0;
+    if (m < kEps || want_polys) {
+      double poly[CCB_MAX_CELL_VERTS][2], tmp[CCB_MAX_CELL_VERTS][2];
+      // box = (pWorldMapSize, pWorldMapSize), not scaled by the resolution (coverage_system.h:373-375)
+      nv = clip_cell(s_x, s_y, d.R, r, (double)d.N, (double)d.N, poly, tmp);
+      double ax = 0, ay = 0;
+      for (int v = 0; v < nv; ++v) ax += poly[v][0], ay += poly[v][1];
+      cx = nv > 0 ? ax / nv : px;
+      cy = nv > 0 ? ay / nv : py;
+      if (want_polys) {
+        double *dst = out.verts + er * CCB_MAX_CELL_VERTS * 2;
+        for (int v = 0; v < nv; ++v) dst[2 * v] = poly[v][0], dst[2 * v + 1] = poly[v][1];
+      }
+    }
+    if (!(m < kEps)) cx = mx / m, cy = my / m;
+    out.centroid[2 * er] = cx, out.centroid[2 * er + 1] = cy;
+    if (want_polys) out.nverts[er] = nv;
+  }
+}
+
+// Goals of DecentralizedCVT (decentralized_cvt.h:85-143) from the per-robot window moments.
+// One CTA per environment.  Dynamic smem: 2 * R doubles per thread-independent scratch is avoided
+// by rebuilding the (small) neighbour list per robot in local memory.
+__global__ void k_finalize_single(EnvDev d, const double *__restrict__ sums, double *__restrict__ goals) {
+  const int e = blockIdx.x;
+  const double *pos = d.pos_g + (size_t)e * d.R * 2;
+  for (int r = threadIdx.x; r < d.R; r += blockDim.x) {
+    const size_t er = (size_t)e * d.R + r;
+    const double *s = sums + er * 4;
+    const double m = s[0], res = d.res;
+    double gx, gy;
+    if (m < kEps) {
+      // vertex mean of (window rectangle ∩ bisector half-planes), in window coordinates
+      const double sxr = pos[2 * r], syr = pos[2 * r + 1];
+      const Window w = make_window(res, sxr, syr, d.L, d.N);
+      const double tx = w.x0 * res, ty = w.y0 * res;
+      double lx[CCB_MAX_CELL_VERTS], ly[CCB_MAX_CELL_VERTS];
+      int n = 1;
+      lx[0] = sxr - tx, ly[0] = syr - ty;
+      for (int j = 0; j < d.R && n < CCB_MAX_CELL_VERTS; ++j) {
+        if (j == r) continue;
+        double dx = pos[2 * j] - sxr, dy = pos[2 * j + 1] - syr;
+        if (sqrt(dx * dx + dy * dy) < d.comm_range) lx[n] = pos[2 * j] - tx, ly[n] = pos[2 * j + 1] - ty, ++n;
+      }
+      double poly[CCB_MAX_CELL_VERTS][2], tmp[CCB_MAX_CELL_VERTS][2];
+      int nv = clip_cell(lx, ly, n, 0, (double)(w.x1 - w.x0), (double)(w.y1 - w.y0), poly, tmp);
+      double ax = 0, ay = 0;
+      for (int v = 0; v < nv; ++v) ax += poly[v][0], ay += poly[v][1];
+      // voronoi.cpp:49: centroid_ += origin_shift (= -site0); decentralized_cvt.h:126 adds it back
+      double cxs = (nv > 0 ? ax / nv : lx[0]) + (-lx[0]);
+      double cys = (nv > 0 ? ay / nv : ly[0]) + (-ly[0]);
+      gx = cxs + lx[0] + tx;
+      gy = cys + ly[0] + ty;
+    } else {
+      gx = res * s[1] / m;
+      gy = res * s[2] / m;
+    }
+    goals[2 * er] = gx, goals[2 * er + 1] = gy;
+    if (gx < 0 || gx > d.N || gy < 0 || gy > d.N) atomicOr(d.status + e, 1);  // decentralized_cvt.h:127-141
+  }
+}
+
+// clairvoyant_cvt.h:100-127 ComputeActions (identical in centralized_cvt.h / decentralized_cvt.h)
+__global__ void k_actions(EnvDev d, const double *__restrict__ goals, double *__restrict__ actions,
+                          int *__restrict__ converged) {
+  const int e = blockIdx.x;
+  int all_zero = 1;
+  for (int r = threadIdx.x; r < d.R; r += blockDim.x) {
+    const size_t er = (size_t)e * d.R + r;
+    double ax = 0, ay = 0;
+    double dx = goals[2 * er] - d.pos_g[2 * er], dy = goals[2 * er + 1] - d.pos_g[2 * er + 1];
+    double dist = sqrt(dx * dx + dy * dy);
+    if (!(dist < kEps) && !check_oscillation(d, e, r)) {
+      double speed = dist / d.dt;
+      speed = speed < d.max_speed ? speed : d.max_speed;
+      eigen_normalize(dx, dy);
+      ax = speed * dx, ay = speed * dy;
+      all_zero = 0;
+    }
+    actions[2 * er] = ax, actions[2 * er + 1] = ay;
+  }
+  int conv = __syncthreads_and(all_zero);
+  if (threadIdx.x == 0) converged[e] = conv;
+}
+
+// objective = sum over robots of obj (voronoi.h:179-185), one CTA per environment
+__global__ void k_objective(EnvDev d, const double *__restrict__ obj, double *__restrict__ out) {
+  const int e = blockIdx.x;
+  if (threadIdx.x == 0) {
+    double o = 0;
+    for (int r = 0; r < d.R; ++r) o = o + obj[(size_t)e * d.R + r];  // reference order
+    out[e] = o;
+  }
+}
+
+// ---- dense map materialisation (getters) ---------------------------------------------------------
+// kind: ccb_map_kind.  N x N kinds write N*N floats; window kinds write dim*dim floats.
+__global__ void k_materialize(EnvDev d, int e, int kind, int robot, float *__restrict__ out) {
+  const size_t nn = cell_count(d);
+  if (kind <= CCB_MAP_ROBOT) {
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < nn; c += (size_t)gridDim.x * blockDim.x) {
+      float v;
+      switch (kind) {
+        case CCB_MAP_WORLD: v = d.world[(size_t)e * nn + c]; break;
+        case CCB_MAP_SYSTEM: v = explored_value(d, e, c) - exploration_value(d, e, c); break;  // coverage_system.h:119
+        case CCB_MAP_EXPLORED_IDF: v = explored_value(d, e, c); break;
+        case CCB_MAP_EXPLORATION: v = exploration_value(d, e, c); break;
+        default: v = robot_map_value(d, e, robot, c); break;
+      }
+      out[c] = v;
+    }
+    return;
+  }
+  const int dim = (kind == CCB_MAP_SENSOR_VIEW) ? d.S : d.L;
+  const double *p = d.pos_g + ((size_t)e * d.R + robot) * 2;
+  const Window w = make_window(d.res, p[0], p[1], dim, d.N);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < dim * dim; t += gridDim.x * blockDim.x) {
+    int a = t / dim, b = t - a * dim;
+    int gx = w.ox + a, gy = w.oy + b;
+    bool in = gx >= 0 && gx < d.N && gy >= 0 && gy < d.N;
+    size_t c = in ? (size_t)gx * d.N + gy : 0;
+    float v;
+    switch (kind) {
+      case CCB_MAP_SENSOR_VIEW:  // robot_model.h:87-96: zero-padded world window
+        v = (in && d.use_sensor) ? d.world[(size_t)e * nn + c] : 0.f;
+        break;
+      case CCB_MAP_LOCAL:  // robot_model.h:303-313
+        v = in ? robot_map_value(d, e, robot, c) : 0.f;
+        break;
+      case CCB_MAP_OBSTACLE:  // robot_model.h:336-345
+        v = in ? 0.f : 1.f;
+        break;
+      case CCB_MAP_ROBOT_EXPLORATION:  // robot_model.h:321-334: -1 padded
+        v = in ? robot_exploration_value(d, e, robot, c) : -1.f;
+        break;
+      default:  // CCB_MAP_ROBOT_SYSTEM, robot_model.h:183-187: local - local_exploration
+        v = (in ? robot_map_value(d, e, robot, c) : 0.f) - (in ? robot_exploration_value(d, e, robot, c) : -1.f);
+        break;
+    }
+    out[t] = v;
+  }
+}
+
+// coverage_system.h:557-571: [cells with exploration cleared, sum of explored IDF, sum of world]
+__global__ void k_ratio_sums(EnvDev d, double *__restrict__ out /* [E][3] */) {
+  const int e = blockIdx.y;
+  const size_t nn = cell_count(d);
+  double cnt = 0, ex = 0, tot = 0;
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < nn; c += (size_t)gridDim.x * blockDim.x) {
+    uint8_t s = d.sys[(size_t)e * nn + c];
+    float w = d.world[(size_t)e * nn + c];
+    cnt += (s & 2) ? 1.0 : 0.0;
+    ex += (s & 1) ? (d.use_sensor ? (double)w : 0.0) : 0.0;
+    tot += (double)w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    ex += __shfl_xor_sync(0xffffffffu, ex, o);
+    tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out + 3 * e + 0, cnt);
+    atomicAdd(out + 3 * e + 1, ex);
+    atomicAdd(out + 3 * e + 2, tot);
+  }
+}
+
+// robot_model.h:408-430 GetVoronoiFeatures: single-site "Voronoi" over the robot's clipped
+// L-window of its own map.  One CTA per (robot, env).  out: [E][R][7].
+__global__ void k_voronoi_features(EnvDev d, double *__restrict__ out) {
+  const int r = blockIdx.x, e = blockIdx.y;
+  const size_t er = (size_t)e * d.R + r;
+  const double *p = d.pos_g + er * 2;
+  const double res = d.res;
+  const Window w = make_window(res, p[0], p[1], d.L, d.N);
+  const double tx = w.x0 * res, ty = w.y0 * res;
+  const double s0x = p[0] - tx, s0y = p[1] - ty;  // site in window coordinates
+  const int ww = w.x1 - w.x0, wh = w.y1 - w.y0;
+  double m = 0, cx = 0, cy = 0, sd = 0, sd2 = 0;
+  for (int t = threadIdx.x; t < ww * wh; t += blockDim.x) {
+    int a = t / wh, b = t - a * wh;
+    float vf = robot_map_value(d, e, r, (size_t)(w.x0 + a) * d.N + (w.y0 + b));
+    if (vf == 0.f) continue;
+    double v = vf;
+    // voronoi.h:89-95 with origin_shift = -site0 (voronoi.h:171): pt is shifted, then (pt - site)
+    // shifts a second time -- the reference's quirk, kept.
+    double ptx = (a * res + res / 2.) - s0x, pty = (b * res + res / 2.) - s0y;
+    double ddx = ptx - s0x, ddy = pty - s0y;
+    double d2 = ddx * ddx + ddy * ddy;
+    m += v, cx += ptx * v, cy += pty * v, sd += sqrt(d2) * v, sd2 += d2 * v;
+  }
+  __shared__ double s_red[5][32];
+  double vals[5] = {m, cx, cy, sd, sd2};
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    double x = vals[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) s_red[q][threadIdx.x >> 5] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int nw = blockDim.x >> 5;
+    for (int q = 0; q < 5; ++q) {
+      double x = 0;
+      for (int k = 0; k < nw; ++k) x += s_red[q][k];
+      vals[q] = x;
+    }
+    double *o = out + er * 7;
+    if (vals[0] < kEps) {
+      // vertex mean of the window rectangle + origin_shift (voronoi.cpp:41-50)
+      o[0] = (0 + ww + ww + 0) / 4. - s0x, o[1] = (0 + 0 + wh + wh) / 4. - s0y;
+    } else {
+      o[0] = vals[1] / vals[0], o[1] = vals[2] / vals[0];
+    }
+    o[2] = vals[0], o[3] = vals[4], o[4] = 0, o[5] = vals[3], o[6] = 0;  // voronoi.h:73-78
+  }
+}
+
+}  // namespace ccb

@@ -1,0 +1,124 @@
+// obs.cuh -- LPAC observation tensors produced directly on the device.
+//
+// Replaces the per-robot Python loop of reference python/coverage_control/coverage_env_utils.py:
+// get_raw_local_maps (:97-117), get_raw_obstacle_maps (:119-141), get_communication_maps
+// (:143-191), resize_maps (:200-225, torchvision antialias bilinear) and get_maps (:227-277),
+// which call RobotModel::GetRobotLocalMap / GetObstacleMap (robot_model.h:303-345) R times per
+// step, copy every L x L map twice and resize on the CPU.
+#pragma once
+
+#include "common.cuh"
+#include "maps.cuh"
+
+namespace ccb {
+
+// E x R x L x L raw local maps (kind CCB_MAP_LOCAL) or obstacle maps (CCB_MAP_OBSTACLE).
+// grid = (L, R, E): one CTA per output row, coalesced along y.
+__global__ void k_raw_window_maps(EnvDev d, int kind, float *__restrict__ out) {
+  const int a = blockIdx.x, r = blockIdx.y, e = blockIdx.z;
+  const size_t er = (size_t)e * d.R + r;
+  const double *p = d.pos_g + er * 2;
+  const Window w = make_window(d.res, p[0], p[1], d.L, d.N);
+  const int gx = w.ox + a;
+  float *dst = out + (er * d.L + a) * d.L;
+  for (int b = threadIdx.x; b < d.L; b += blockDim.x) {
+    const int gy = w.oy + b;
+    const bool in = gx >= 0 && gx < d.N && gy >= 0 && gy < d.N;
+    float v;
+    if (kind == CCB_MAP_OBSTACLE) v = in ? 0.f : 1.f;
+    else v = in ? robot_map_value(d, e, r, (size_t)gx * d.N + gy) : 0.f;
+    dst[b] = v;
+  }
+}
+
+// Communication maps with the semantics LPAC consumes (coverage_env_utils.py:143-191): float32
+// arithmetic, torch.round = round-half-even, duplicates summed.  out: E x R x 2 x C x C, or a
+// channel slice of a wider tensor (chan_stride = floats between robots, chan_off = first channel).
+// One CTA per (robot, env).
+__global__ void k_comm_maps(EnvDev d, int C, float *__restrict__ out, size_t robot_stride, size_t chan_off) {
+  const int r = blockIdx.x, e = blockIdx.y;
+  const size_t er = (size_t)e * d.R + r;
+  float *ox = out + er * robot_stride + chan_off;
+  float *oy = ox + (size_t)C * C;
+  for (int t = threadIdx.x; t < 2 * C * C; t += blockDim.x) ox[t] = 0.f;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const double *pos = d.pos_g + (size_t)e * d.R * 2;
+  const float denom = (float)(d.comm_range * d.res * 2.0);
+  const float center = (float)(C / 2.0 - d.res / 2.0);
+  const float cr = (float)d.comm_range;
+  const double sx = pos[2 * r], sy = pos[2 * r + 1];
+  for (int j = 0; j < d.R; ++j) {
+    if (j == r) continue;
+    // coverage_system.cpp:274-291: relative position p_j - p_r (stored negated for j < r)
+    double dx, dy;
+    if (j > r) dx = pos[2 * j] - sx, dy = pos[2 * j + 1] - sy;
+    else dx = -(sx - pos[2 * j]), dy = -(sy - pos[2 * j + 1]);
+    if (!(sqrt(dx * dx + dy * dy) < d.comm_range)) continue;
+    const float fx = (float)dx, fy = (float)dy;
+    const float ix = rintf(__fadd_rn(__fdiv_rn(__fmul_rn(fx, (float)C), denom), center));
+    const float iy = rintf(__fadd_rn(__fdiv_rn(__fmul_rn(fy, (float)C), denom), center));
+    const int xi = (int)ix, yi = (int)iy;
+    if (xi < 0 || xi >= C || yi < 0 || yi >= C) continue;
+    ox[xi * C + yi] += __fdiv_rn(fx, cr);
+    oy[xi * C + yi] += __fdiv_rn(fy, cr);
+  }
+}
+
+// Separable antialiased bilinear down-sampling weights (what torchvision resize(antialias=True)
+// applies): for output index o the taps are input indices [xmin[o], xmin[o]+xsize[o]).
+struct ResizeTable {
+  const int *xmin;    // [C]
+  const int *xsize;   // [C]
+  const float *w;     // [C][kmax]
+  int kmax;
+};
+
+// Fused crop -> mask -> antialias resize for the local-map and obstacle channels, writing
+// straight into the E x R x nch x C x C CNN input.  grid = (C, R, E): one CTA per output row ox.
+//   pass 1 (width, as torch does first): tmp[a][oy] = sum_t w[oy][t] * in[xmin[ox]+a][ymin[oy]+t]
+//   pass 2 (height):                      out[ox][oy] = sum_a w[ox][a] * tmp[a][oy]
+// Dynamic smem: kmax * L floats (input rows) + kmax * C floats (tmp).
+__global__ void k_cnn_local_obstacle(EnvDev d, int C, ResizeTable tab, float *__restrict__ out,
+                                     size_t robot_stride, size_t local_off, size_t obst_off) {
+  extern __shared__ float s_obs[];
+  float *s_in = s_obs;                       // [kmax][L]
+  float *s_tmp = s_obs + (size_t)tab.kmax * d.L;  // [kmax][C]
+  const int ox = blockIdx.x, r = blockIdx.y, e = blockIdx.z;
+  const size_t er = (size_t)e * d.R + r;
+  const double *p = d.pos_g + er * 2;
+  const Window w = make_window(d.res, p[0], p[1], d.L, d.N);
+  const int a0 = tab.xmin[ox], na = tab.xsize[ox];
+  const float *wrow = tab.w + (size_t)ox * tab.kmax;
+
+  for (int pass = 0; pass < 2; ++pass) {  // 0: local map, 1: obstacle map
+    for (int t = threadIdx.x; t < na * d.L; t += blockDim.x) {
+      const int a = t / d.L, b = t - a * d.L;
+      const int gx = w.ox + a0 + a, gy = w.oy + b;
+      const bool in = gx >= 0 && gx < d.N && gy >= 0 && gy < d.N;
+      float v;
+      if (pass == 0) v = in ? robot_map_value(d, e, r, (size_t)gx * d.N + gy) : 0.f;
+      else v = in ? 0.f : 1.f;
+      s_in[a * d.L + b] = v;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < na * C; t += blockDim.x) {
+      const int a = t / C, oy = t - a * C;
+      const int b0 = tab.xmin[oy], nb = tab.xsize[oy];
+      const float *wc = tab.w + (size_t)oy * tab.kmax;
+      float acc = 0.f;
+      for (int q = 0; q < nb; ++q) acc = fmaf(wc[q], s_in[a * d.L + b0 + q], acc);
+      s_tmp[a * C + oy] = acc;
+    }
+    __syncthreads();
+    float *dst = out + er * robot_stride + (pass == 0 ? local_off : obst_off) + (size_t)ox * C;
+    for (int oy = threadIdx.x; oy < C; oy += blockDim.x) {
+      float acc = 0.f;
+      for (int a = 0; a < na; ++a) acc = fmaf(wrow[a], s_tmp[a * C + oy], acc);
+      dst[oy] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace ccb

@@ -1,0 +1,105 @@
+"""LPAC observation tensors (coverage_env_utils.py) from the CUDA path vs oracle + torchvision."""
+import numpy as np
+import pytest
+
+from conftest import random_world
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(N=1024, R=8, L=256, S=64, seed=21, steps=6):
+    import coverage_control as cc
+    from coverage_control.algorithms import DecentralizedCVT
+    from oracle import oracle as orc
+
+    p = cc.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    p.pNumRobots = R
+    p.pLocalMapSize = L
+    p.pSensorSize = S
+    bnd, pos = random_world(seed, N, 10, R)
+    pos[0] = [20.0, 30.0]
+    pos[1] = [N - 40.0, 60.0]
+    pos[2] = pos[3] + [8.0, -8.0]  # exact .5 index in the comm map: round-half-even vs half-away
+    op = orc.params_from(p)
+    wm, _ = orc.idf_generate(op, bnd, mode=1)
+    oenv = orc.Env(op, wm, pos)
+    env = cc.CoverageSystem(p, cc.WorldIDF(p, wm), cc.PointVector(pos))
+    ctrl = DecentralizedCVT(p, env)
+    for _ in range(steps):
+        ctrl.ComputeActions()
+        a = ctrl.GetActions()
+        env.StepActions(a)
+        oenv.step_actions(np.array(a))
+    return cc, orc, p, env, oenv
+
+
+def test_raw_local_obstacle_and_comm_maps():
+    import torch
+
+    cc, orc, p, env, oenv = _setup()
+    U = cc.CoverageEnvUtils
+    R = env.GetNumRobots()
+    local = U.get_raw_local_maps(env, p).cpu().numpy()
+    obst = U.get_raw_obstacle_maps(env, p).cpu().numpy()
+    comm = U.get_communication_maps(env, p, 32).cpu().numpy()
+    assert local.shape == (R, 256, 256) and comm.shape == (R, 2, 32, 32)
+    for r in range(R):
+        assert np.array_equal(local[r], oenv.local_map(r))
+        assert np.array_equal(obst[r], oenv.obstacle_map(r))
+        ox, oy = oenv.comm_maps(r, 32, "py")
+        assert np.array_equal(comm[r, 0], ox) and np.array_equal(comm[r, 1], oy)
+    cpp = env.GetCommunicationMaps(32)
+    for r in range(R):
+        ox, oy = oenv.comm_maps(r, 32, "cpp")
+        assert np.array_equal(cpp[2 * r], ox) and np.array_equal(cpp[2 * r + 1], oy)
+    # python semantics, restated with torch exactly as coverage_env_utils.py:164-186 does
+    for r in range(R):
+        nb = torch.from_numpy(oenv.neighbors(r).astype(np.float32))
+        if len(nb) == 0:
+            assert not comm[r].any()
+            continue
+        idx = torch.round(nb * 32 / (p.pCommunicationRange * p.pResolution * 2.0) + (32 / 2.0 - p.pResolution / 2.0))
+        idx = torch.transpose(idx, 1, 0).long()
+        val = nb / p.pCommunicationRange
+        for ch in range(2):
+            dense = torch.sparse_coo_tensor(idx, val[:, ch], torch.Size([32, 32])).to_dense().numpy()
+            assert np.allclose(comm[r, ch], dense, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("C", [32, 64])
+def test_cnn_input_matches_torchvision_resize(C):
+    import torch
+    import torchvision
+
+    cc, orc, p, env, oenv = _setup()
+    U = cc.CoverageEnvUtils
+    R = env.GetNumRobots()
+    maps = U.get_maps(env, p, C, True).cpu()
+    assert maps.shape == (R, 4, C, C)
+    raw_local = torch.from_numpy(np.stack([oenv.local_map(r) for r in range(R)]))
+    raw_obst = torch.from_numpy(np.stack([oenv.obstacle_map(r) for r in range(R)]))
+    rs = lambda t: torchvision.transforms.functional.resize(  # noqa: E731
+        t, (C, C), interpolation=torchvision.transforms.InterpolationMode.BILINEAR, antialias=True)
+    # torch.allclose defaults, as the reference's test_coverage_env_utils.py uses
+    assert torch.allclose(maps[:, 0], rs(raw_local), rtol=1e-5, atol=1e-8)
+    assert torch.allclose(maps[:, 3], rs(raw_obst), rtol=1e-5, atol=1e-8)
+    comm = U.get_communication_maps(env, p, C).cpu()
+    assert torch.equal(maps[:, 1:3], comm)
+    two = U.get_maps(env, p, C, False).cpu()
+    assert torch.equal(two[:, 0], maps[:, 0]) and torch.equal(two[:, 1], maps[:, 3])
+
+
+def test_weights_and_positions():
+    import torch
+
+    cc, orc, p, env, oenv = _setup(steps=2)
+    U = cc.CoverageEnvUtils
+    pos = U.get_robot_positions(env)
+    assert torch.allclose(pos, torch.from_numpy(oenv.positions().astype(np.float32)))
+    w = U.get_weights(env, p)
+    d = torch.cdist(pos, pos, 2)
+    ref = torch.exp(-(d.square()) / (p.pCommunicationRange ** 2))
+    ref[ref < 1.0 / np.e] = 0
+    ref.fill_diagonal_(0)
+    assert torch.allclose(w, ref)
