@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native CoverageControl grid hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], "C2"): 1024 x 1024 world, 32 robots, 32 Gaussian features,
+params/coverage_control_params.toml values, DecentralizedCVT + the LPAC observation (sensor 64,
+local 256, CNN 32 x 32) + the objective, i.e. per environment step
+    ComputeActions(); a = GetActions(); StepActions(a); GetObjectiveValue(); get_maps(C=32, comm)
+`--envs-per-gpu` independent environments are stepped together on every GPU (no data-path
+collective: environments are independent).  One bench "step" = one such pass over
+the whole batch; `value` = environment steps per second over all GPUs.
+
+Prints ONE JSON line (rank 0).  See the task contract for the keys.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_WORLD, N_ROBOTS, N_FEATURES = 1024, 32, 32
+SENSOR, LOCAL, CNN = 64, 256, 32
+
+
+def toml_params(cc):
+    """params/coverage_control_params.toml of the reference, set explicitly (the file is not on the GPU box)."""
+    p = cc.Parameters()
+    p.pNumRobots = N_ROBOTS
+    p.pNumGaussianFeatures = N_FEATURES
+    p.pWorldMapSize = p.pRobotMapSize = N_WORLD
+    p.pLocalMapSize = LOCAL
+    p.pSensorSize = SENSOR
+    p.pUpdateExplorationMap = False
+    p.pMinSigma, p.pMaxSigma = 40.0, 60.0
+    p.pMinPeak, p.pMaxPeak = 6.0, 10.0
+    p.pCommunicationRange = 128.0
+    p.pMaxRobotSpeed = 5.0
+    p.pRobotInitDist = 1024.0
+    p.pRobotPosHistorySize = 40
+    p.pTimeStep = 0.2
+    p.pEpisodeSteps = 2100
+    return p
+
+
+def synth_inputs(seed: int):
+    """SURVEY.md 8(d) synthetic inputs: circular Gaussians + robot start positions."""
+    rng = np.random.default_rng(seed)
+    bnd = np.zeros((N_FEATURES, 6))
+    bnd[:, 0:2] = rng.uniform(0, N_WORLD, (N_FEATURES, 2))
+    bnd[:, 2] = bnd[:, 3] = rng.uniform(40.0, 60.0, N_FEATURES)
+    bnd[:, 4] = rng.uniform(6.0, 10.0, N_FEATURES)
+    pos = rng.uniform(1e-4, 1024.0 - 1e-4, (N_ROBOTS, 2))
+    return bnd, pos
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's CPU path (the reference itself cannot be built here)
+# ------------------------------------------------------------------------------------------------
+def cpu_c2_step(orc, oenv, torchvision_resize):
+    """One C2 environment step as the reference's Python does it (controllers.py:67-88 +
+    coverage_env_utils.py:227-277), on the structure-faithful CPU environment."""
+    import torch
+
+    _, a, _ = oenv.compute_actions(2)
+    oenv.step_actions(a)
+    obj = oenv.objective()
+    R = oenv.R
+    local = torch.from_numpy(np.stack([oenv.local_map(r) for r in range(R)]))
+    obst = torch.from_numpy(np.stack([oenv.obstacle_map(r) for r in range(R)]))
+    rl, ro = torchvision_resize(local), torchvision_resize(obst)
+    comm = np.stack([np.stack(oenv.comm_maps(r, CNN, "py")) for r in range(R)])
+    maps = torch.cat([rl.unsqueeze(1), torch.from_numpy(comm), ro.unsqueeze(1)], 1)
+    return obj, maps
+
+
+def run_cpu(steps: int, warmup: int, budget_s: float):
+    import torch
+    import torchvision
+
+    from oracle import oracle as orc
+
+    class _P:
+        pass
+
+    import coveragecontrol_b200 as ccb
+
+    p = toml_params(ccb)
+    op = orc.params_from(p)
+    bnd, pos = synth_inputs(0)
+    wm, _ = orc.idf_generate(op, bnd, mode=1)
+    oenv = orc.Env(op, wm, pos)
+    rs = lambda t: torchvision.transforms.functional.resize(  # noqa: E731
+        t, (CNN, CNN), interpolation=torchvision.transforms.InterpolationMode.BILINEAR, antialias=True)
+    for _ in range(warmup):
+        cpu_c2_step(orc, oenv, rs)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        cpu_c2_step(orc, oenv, rs)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    orc.idf_generate(op, bnd, mode=0)
+    idf_ms = (time.perf_counter() - t1) * 1e3
+    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    return {"value": done / dt, "steps_done": done, "seconds": dt, "cores": cores, "idf_cpu_ms": idf_ms,
+            "torch_threads": torch.get_num_threads()}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=128)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    E = args.envs_per_gpu
+    workload = (f"C2: {N_WORLD}x{N_WORLD} world, {N_ROBOTS} robots, {N_FEATURES} Gaussian features, TOML params, "
+                f"DecentralizedCVT step + objective + LPAC observation (S={SENSOR}, L={LOCAL}, C={CNN})")
+    config = {"workload": workload, "envs_per_gpu": E, "world": N_WORLD, "robots": N_ROBOTS, "features": N_FEATURES,
+              "l2": "state per GPU (world+seen+sys = 9 MB x envs) is larger than the 126 MB L2",
+              "parallelism": f"independent environments sharded over {world} GPU(s), no data-path collective"}
+
+    if args.impl == "reference":
+        # the reference's own CPU path cannot be built here (no Eigen/CGAL/Boost):
+        # this arm times the oracle port of it on the host cores; rank 0 only.
+        if rank != 0:
+            return
+        r = run_cpu(10**6, args.warmup, 20.0)
+        sample = f"1 environment of the workload, {r['steps_done']} consecutive env steps in {r['seconds']:.1f} s"
+        line = {
+            "impl": "reference", "metric": "env steps/sec (1024^2 map, 32 robots)", "value": r["value"],
+            "unit": "env_steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / r["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 sums over f32 maps", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": r["value"], "unit": "env_steps/s", "cores": r["cores"], "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": r["value"], "unit": "env_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "idf_gen_ms": r["idf_cpu_ms"],
+        }
+        print(json.dumps(line))
+        return
+
+    import torch
+
+    import coveragecontrol_b200 as ccb
+    from coveragecontrol_b200 import BatchedCoverageSystem, BatchedCVT, _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.load()
+    dev = torch.device("cuda", local_rank)
+    p = toml_params(ccb)
+
+    # ---- build the batch: worlds generated on the GPU, one WorldIDF per environment ----------------
+    batch = BatchedCoverageSystem(p, E, N_ROBOTS, device=local_rank)
+    positions = np.zeros((E, N_ROBOTS, 2))
+    idf_evt = []
+    for e in range(E):
+        bnd, pos = synth_inputs(rank * E + e)
+        positions[e] = pos
+        idf = ccb.WorldIDF(p, device=local_rank)
+        for b in bnd:
+            idf.AddNormalDistribution(ccb.BivariateNormalDistribution(ccb.Point2(b[0], b[1]), float(b[2]), float(b[4])))
+        if e < 8:
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            idf.GenerateMap()
+            t.record()
+            idf_evt.append((s, t))
+        else:
+            idf.GenerateMap()
+        batch.set_world(e, idf)
+    batch.reset(positions)
+    ctrl = BatchedCVT(batch, 2)
+    obs = torch.empty((E, N_ROBOTS, 4, CNN, CNN), dtype=torch.float32, device=dev)
+    obj_dev = torch.empty((1, E), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    idf_ms = float(np.median([s.elapsed_time(t) for s, t in idf_evt[2:]])) if len(idf_evt) > 2 else None
+
+    def device_step():
+        ctrl.rollout(1, True, obj_dev.data_ptr())
+        _lib.check(lib.ccb_env_cnn_input_dev(batch._h, CNN, 1, obs.data_ptr()))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.ccb_kernel_launch_count()
+        s.record()
+        for _ in range(steps):
+            fn()
+        t.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(t)
+        launches = lib.ccb_kernel_launch_count() - l0
+        if dist is not None:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        barrier()
+        return ms, launches
+
+    # ---- device-resident number -------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches = timed(device_step, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * E * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the host-buffer API: actions D2H -> host -> H2D, objective D2H ----------
+    host_actions = np.empty((E, N_ROBOTS, 2))
+    host_obj = np.empty(E)
+
+    def e2e_step():
+        ctrl.compute_actions()
+        _lib.check(lib.ccb_ctrl_get_actions(ctrl._h, host_actions.ctypes.data_as(C.POINTER(C.c_double))))
+        bad = C.c_int(-1)
+        _lib.check(lib.ccb_env_step_actions(batch._h, host_actions.ctypes.data_as(C.POINTER(C.c_double)), C.byref(bad)))
+        _lib.check(lib.ccb_env_objective(batch._h, host_obj.ctypes.data_as(C.POINTER(C.c_double))))
+        _lib.check(lib.ccb_env_cnn_input_dev(batch._h, CNN, 1, obs.data_ptr()))
+
+    ms_e2e, _ = timed(e2e_step, args.steps, args.warmup)
+    e2e_value = world * E * args.steps / (ms_e2e * 1e-3)
+
+    # ---- per-kernel durations (same data, CUDA events on the launching stream) ----------------------
+    kernels = {}
+    cells = N_WORLD * N_WORLD
+    algo = {
+        "voronoi_window(decentralized)": (2, 4.0 * N_ROBOTS * LOCAL * LOCAL * E),
+        "voronoi_global(objective)": (0, 4.0 * cells * E),
+        "cnn_input": (4, (4.0 * N_ROBOTS * LOCAL * LOCAL + 16.0 * N_ROBOTS * CNN * CNN) * E),
+        "mark_windows": (3, 12.0 * N_ROBOTS * SENSOR * SENSOR * E),
+        "finalize_cells": (5, 32.0 * N_ROBOTS * E),
+    }
+    for name, (which, nbytes) in algo.items():
+        iters = 10
+        fn = lambda w=which: _lib.check(lib.ccb_bench_kernel(batch._h, w, 1, obs.data_ptr()))  # noqa: E731
+        ms, _ = timed(fn, iters, 3)
+        kernels[name] = {"ms": ms / iters, "algorithmic_bytes": nbytes, "gbs": nbytes / (ms / iters * 1e-3) / 1e9}
+    peak, peak_src = measured_peak_gbs()
+    dom = max(("voronoi_window(decentralized)", "voronoi_global(objective)", "cnn_input"), key=lambda k: kernels[k]["ms"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "kernels": kernels}
+
+    # ---- single-environment latency (API-faithful, E = 1) and the C1 variant, reported as extras -----
+    extras = {"idf_gen_ms_1024_32f_mode0": idf_ms}
+    try:
+        one = BatchedCoverageSystem(p, 1, N_ROBOTS, device=local_rank)
+        bnd, pos = synth_inputs(0)
+        idf = ccb.WorldIDF(p, device=local_rank)
+        for b in bnd:
+            idf.AddNormalDistribution(ccb.BivariateNormalDistribution(ccb.Point2(b[0], b[1]), float(b[2]), float(b[4])))
+        idf.GenerateMap()
+        one.set_world(0, idf)
+        one.reset(pos[None])
+        c1 = BatchedCVT(one, 0)
+        ha = np.empty((1, N_ROBOTS, 2))
+
+        def c1_api_step():
+            c1.compute_actions()
+            _lib.check(lib.ccb_ctrl_get_actions(c1._h, ha.ctypes.data_as(C.POINTER(C.c_double))))
+            bad = C.c_int(-1)
+            _lib.check(lib.ccb_env_step_actions(one._h, ha.ctypes.data_as(C.POINTER(C.c_double)), C.byref(bad)))
+
+        ms, _ = timed(c1_api_step, 200, 20)
+        extras["c1_single_env_api_steps_per_s"] = 200 / (ms * 1e-3)
+        ms, _ = timed(lambda: c1.rollout(1), 200, 20)
+        extras["c1_single_env_device_steps_per_s"] = 200 / (ms * 1e-3)
+        c1b = BatchedCVT(batch, 0)
+        ms, _ = timed(lambda: c1b.rollout(1), max(5, args.steps // 2), 3)
+        extras["c1_batched_device_steps_per_s"] = world * E * max(5, args.steps // 2) / (ms * 1e-3)
+    except Exception as exc:  # extras never invalidate the headline line
+        extras["extras_error"] = str(exc)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        r = run_cpu(10**6, 2, args.cpu_seconds)
+        cpu = {"value": r["value"], "unit": "env_steps/s", "cores": r["cores"], "kind": "port",
+               "sample": f"1 environment of the workload, {r['steps_done']} consecutive env steps in {r['seconds']:.1f} s",
+               "idf_gen_ms": r["idf_cpu_ms"]}
+
+    line = {
+        "metric": "env steps/sec (1024^2 map, 32 robots)", "value": value, "unit": "env_steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 sums over f32 maps (u32 seen masks)", "data": "synthetic", "config": config,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "env_steps/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(host_actions.nbytes),
+                "d2h_bytes_per_step": int(host_actions.nbytes + host_obj.nbytes)},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "extras": extras,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -336,6 +336,7 @@ struct ResizeTab {
   int C = 0, kmax = 0;
   int *d_xmin = nullptr, *d_xsize = nullptr;
   float *d_w = nullptr;
+  float *d_wfull8 = nullptr;  // [C][16] weights in the (8 o - 4) frame, only when L == 8 C == 256
 };
 
 struct ccb_env {
@@ -361,16 +362,28 @@ struct ccb_env {
 };
 
 static int pick_rpw(const ccb_env *env, int region_rows, int region_cols, int regions) {
-  if (env->vor_rpw_override > 0) return env->vor_rpw_override;
+  if (env->vor_rpw_override > 0) return std::min(env->vor_rpw_override, VOR_MAXROWS);
   const int tiles_y = (region_cols + VOR_TY - 1) / VOR_TY + 1;
-  for (int rpw = 16; rpw > 1; rpw >>= 1) {
+  for (int rpw = VOR_MAXROWS; rpw > 1; rpw >>= 1) {
     long tiles_x = (region_rows + VOR_WARPS * rpw - 1) / (VOR_WARPS * rpw);
     if ((long)regions * tiles_x * tiles_y >= 4L * 148) return rpw;
   }
   return 1;
 }
 
-static size_t vor_smem(int R) { return (size_t)R * (2 * sizeof(double) + 2 * sizeof(int)) + VOR_WARPS * 32 * sizeof(int); }
+// sites + candidate lists + per-warp staging (world tile, and a mask tile for the masked sources)
+static size_t vor_smem(int R, int rpw, bool masked) {
+  size_t base = ((size_t)R * 24 + VOR_WARPS * 32 * sizeof(int) + 15) & ~(size_t)15;
+  return base + (size_t)VOR_WARPS * rpw * 32 * 16 * (masked ? 2 : 1);
+}
+static int set_vor_smem(size_t bytes) {
+  static size_t current = 48 * 1024;
+  if (bytes > current) {
+    CCB_CUDA(cudaFuncSetAttribute(k_voronoi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    current = bytes;
+  }
+  return 0;
+}
 
 // Voronoi label + reduce over the full map of every environment; sums must be a [E][R][4] buffer.
 static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *labels = nullptr) {
@@ -382,7 +395,9 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
   a.tiles_y = (d.N + VOR_TY - 1) / VOR_TY;
   a.tiles_x = (d.N + VOR_WARPS * a.rpw - 1) / (VOR_WARPS * a.rpw);
   dim3 grid(a.tiles_x * a.tiles_y, 1, d.E);
-  k_voronoi<<<grid, VOR_THREADS, vor_smem(d.R), env->stream>>>(a);
+  const size_t smem = vor_smem(d.R, a.rpw, src != SRC_WORLD);
+  if (set_vor_smem(smem)) return 1;
+  k_voronoi<<<grid, VOR_THREADS, smem, env->stream>>>(a);
   CCB_LAUNCH_CHECK();
   return 0;
 }
@@ -393,11 +408,12 @@ static int launch_voronoi_single(ccb_env *env, double *sums) {
   CCB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * d.E * d.R, env->stream));
   VorArgs a;
   a.d = d, a.single = 1, a.src = SRC_ROBOT, a.sums = sums, a.labels = nullptr;
-  a.rpw = pick_rpw(env, d.L, d.L, d.E * d.R);
-  a.tiles_y = (d.L + VOR_TY - 1) / VOR_TY + 1;  // the window is not 128-aligned
-  a.tiles_x = (d.L + VOR_WARPS * a.rpw - 1) / (VOR_WARPS * a.rpw);
-  dim3 grid(a.tiles_x * a.tiles_y, d.R, d.E);
-  k_voronoi<<<grid, VOR_THREADS, vor_smem(d.R), env->stream>>>(a);
+  a.rpw = env->vor_rpw_override > 0 ? std::min(env->vor_rpw_override, VOR_MAXROWS) : 8;
+  a.tiles_x = a.tiles_y = 1;  // one CTA per robot window
+  dim3 grid(1, d.R, d.E);
+  const size_t smem = vor_smem(d.R, a.rpw, true);
+  if (set_vor_smem(smem)) return 1;
+  k_voronoi<<<grid, VOR_THREADS, smem, env->stream>>>(a);
   CCB_LAUNCH_CHECK();
   return 0;
 }
@@ -509,8 +525,6 @@ extern "C" ccb_env *ccb_env_create(const ccb_params *p, int num_envs, int num_ro
     ccb_env_destroy(env.release());
     return nullptr;
   }
-  size_t smem = vor_smem(num_robots);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(k_voronoi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   return env.release();
 }
 
@@ -527,7 +541,8 @@ extern "C" void ccb_env_destroy(ccb_env *env) {
   cudaFree(env->d_objective), cudaFree(env->d_stage), cudaFree(env->d_feat), cudaFree(env->d_ratio);
   cudaFree(env->d_scratch);
   cudaFreeHost(env->h_pin);
-  for (auto &kv : env->resize) cudaFree(kv.second.d_xmin), cudaFree(kv.second.d_xsize), cudaFree(kv.second.d_w);
+  for (auto &kv : env->resize)
+    cudaFree(kv.second.d_xmin), cudaFree(kv.second.d_xsize), cudaFree(kv.second.d_w), cudaFree(kv.second.d_wfull8);
   delete env;
 }
 
@@ -804,6 +819,16 @@ static int get_resize_table(ccb_env *env, int C, ResizeTab **out) {
   CCB_CUDA(cudaMemcpy(t.d_xmin, xmin.data(), sizeof(int) * C, cudaMemcpyHostToDevice));
   CCB_CUDA(cudaMemcpy(t.d_xsize, xsize.data(), sizeof(int) * C, cudaMemcpyHostToDevice));
   CCB_CUDA(cudaMemcpy(t.d_w, w.data(), sizeof(float) * C * kmax, cudaMemcpyHostToDevice));
+  if (L == 256 && C == 32) {
+    std::vector<float> wf((size_t)C * 16, 0.f);
+    for (int o = 0; o < C; ++o)
+      for (int k = 0; k < 16; ++k) {
+        int col = 8 * o - 4 + k;
+        if (col >= xmin[o] && col < xmin[o] + xsize[o]) wf[(size_t)o * 16 + k] = w[(size_t)o * kmax + (col - xmin[o])];
+      }
+    CCB_CUDA(cudaMalloc(&t.d_wfull8, sizeof(float) * C * 16));
+    CCB_CUDA(cudaMemcpy(t.d_wfull8, wf.data(), sizeof(float) * C * 16, cudaMemcpyHostToDevice));
+  }
   env->resize[C] = t;
   *out = &env->resize[C];
   return 0;
@@ -823,7 +848,11 @@ extern "C" int ccb_env_cnn_input_dev(ccb_env *env, int C, int use_comm, float *o
   if (smem > 48 * 1024)
     CCB_CUDA(cudaFuncSetAttribute(k_cnn_local_obstacle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // channel order of coverage_env_utils.py:264-276: [local, comm_x, comm_y, obstacle]
-  k_cnn_local_obstacle<<<dim3(C, d.R, d.E), 256, smem, env->stream>>>(d, C, tab, out_dev, stride, 0, cc * (nch - 1));
+  if (t->d_wfull8 && !getenv("CCB_CNN_GENERIC")) {
+    k_cnn_fused8<<<dim3(d.R, d.E), CNN8_THREADS, 0, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, cc * (nch - 1));
+  } else {
+    k_cnn_local_obstacle<<<dim3(C, d.R, d.E), 256, smem, env->stream>>>(d, C, tab, out_dev, stride, 0, cc * (nch - 1));
+  }
   CCB_LAUNCH_CHECK();
   if (use_comm) {
     k_comm_maps<<<dim3(d.R, d.E), 128, 0, env->stream>>>(d, C, out_dev, stride, cc);
@@ -1112,5 +1141,29 @@ extern "C" int ccb_ctrl_rollout(ccb_ctrl *c, int steps, int with_objective, doub
       if (objective_dev(env, dst)) return 1;
     }
   }
+  return 0;
+}
+
+// =================================================================================================
+// Profiling hook: launch one kernel of the step `iters` times back to back on the env stream,
+// bypassing the position-version cache.  bench.py brackets it with CUDA events for the per-kernel
+// roofline; it is not part of the reference-facing API.
+// =================================================================================================
+extern "C" int ccb_bench_kernel(ccb_env *env, int which, int iters, float *scratch_dev) {
+  if (!env->initialised) return fail("environment has no robot positions yet");
+  CCB_CUDA(cudaSetDevice(env->device));
+  const EnvDev &d = env->d;
+  for (int i = 0; i < iters; ++i) {
+    switch (which) {
+      case 0: if (launch_voronoi_global(env, SRC_WORLD, env->d_sums)) return 1; env->cells_version = 0; break;
+      case 1: if (launch_voronoi_global(env, SRC_EXPLORED, env->d_sums)) return 1; env->cells_version = 0; break;
+      case 2: if (launch_voronoi_single(env, env->d_sums)) return 1; env->cells_version = 0; break;
+      case 3: if (launch_mark(env, -1, -1, 1, 1)) return 1; break;
+      case 4: if (ccb_env_cnn_input_dev(env, 32, 1, scratch_dev)) return 1; break;
+      case 5: if (launch_finalize(env, env->d_sums, env->cells, 0)) return 1; env->cells_version = 0; break;
+      default: return fail("ccb_bench_kernel: unknown kernel id");
+    }
+  }
+  (void)d;
   return 0;
 }

@@ -121,4 +121,92 @@ __global__ void k_cnn_local_obstacle(EnvDev d, int C, ResizeTable tab, float *__
   }
 }
 
+
+// ---- specialised path for L = 8 C (LPAC: 256 -> 32) ----------------------------------------------
+// One CTA per (robot, env), 8 warps; warp w owns output rows ox = w, w+8, w+16, w+24 and lane = oy.
+// For each of the <= 16 input rows of an output row the warp reads the 256-cell row of the robot's
+// local window once (coalesced, seen mask first, world only where seen), stages it in a padded
+// shared-memory line (one pad word per 8 cells -> the 16-tap reads of the 32 lanes hit 32 different
+// banks) and runs the width pass; the height pass accumulates in a register in ascending row order,
+// the same order torchvision's separable antialias kernel uses.  The obstacle channel needs no map
+// at all: obstacle(a, b) = 1 - in_x(a) in_y(b), so its width pass has only two possible values per
+// output column.  wfull[o][k] = weight of input index 8 o - 4 + k (zero outside torch's tap range).
+constexpr int CNN8_THREADS = 256;
+constexpr int CNN8_LINE = 304;
+// window column b in [-4, 260) -> word of the padded line (one pad word per 8 cells)
+__device__ __forceinline__ int cnn8_pos(int b) { return (b + 8) + ((b + 8) >> 3); }
+
+__global__ void __launch_bounds__(CNN8_THREADS)
+k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__restrict__ out,
+             size_t robot_stride, size_t local_off, size_t obst_off) {
+  __shared__ float s_line[CNN8_THREADS / 32][CNN8_LINE];
+  __shared__ float s_w[32][16];
+  const int r = blockIdx.x, e = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t er = (size_t)e * d.R + r;
+  const size_t nn = cell_count(d);
+  for (int t = threadIdx.x; t < 32 * 16; t += CNN8_THREADS) s_w[t >> 4][t & 15] = wfull[t];
+  float *line = s_line[warp];
+  if (lane < 4) line[cnn8_pos(lane - 4)] = 0.f;   // taps left of the window
+  else if (lane < 8) line[cnn8_pos(252 + lane)] = 0.f;  // taps right of the window (b = 256..259)
+  __syncthreads();
+  const double *p = d.pos_g + er * 2;
+  const Window w = make_window(d.res, p[0], p[1], 256, d.N);
+  const float *world = d.world + (size_t)e * nn;
+  const uint32_t *seen = d.seen + ((size_t)e * d.W + (r >> 5)) * nn;
+  const uint32_t bit = 1u << (r & 31);
+
+  // width pass of the obstacle indicator for this lane's output column
+  float wc[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) wc[q] = s_w[lane][q];
+  float oy_out = 0.f, oy_all = 0.f;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int gy = w.oy + 8 * lane - 4 + q;
+    const bool in_y = gy >= 0 && gy < d.N;
+    oy_all = fmaf(wc[q], 1.f, oy_all);
+    oy_out = fmaf(wc[q], in_y ? 0.f : 1.f, oy_out);
+  }
+
+  for (int ox = warp; ox < 32; ox += CNN8_THREADS / 32) {
+    float acc = 0.f, acc_obs = 0.f;
+    for (int t = 0; t < 16; ++t) {
+      const float wr = s_w[ox][t];
+      if (wr == 0.f) continue;  // outside torch's tap range (warp-uniform)
+      const int gx = w.ox + 8 * ox - 4 + t;
+      const bool in_x = gx >= 0 && gx < d.N;
+      acc_obs = fmaf(wr, in_x ? oy_out : oy_all, acc_obs);
+      if (!in_x) continue;  // zero padding: the whole row contributes nothing (warp-uniform)
+      const size_t row_off = (size_t)gx * d.N;
+      bool any = false;
+      float vals[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int gy = w.oy + 32 * k + lane;
+        float v = 0.f;
+        if (gy >= 0 && gy < d.N) {
+          const uint32_t m = __ldg(seen + row_off + gy);
+          if (m & bit) v = d.use_sensor ? __ldg(world + row_off + gy) : 0.f;
+          else v = d.fill;
+        }
+        vals[k] = v;
+        any |= (v != 0.f);
+      }
+      if (!__any_sync(0xffffffffu, any)) continue;  // all-zero row (unseen): adds nothing
+#pragma unroll
+      for (int k = 0; k < 8; ++k) line[cnn8_pos(32 * k + lane)] = vals[k];
+      __syncwarp();
+      float tmp = 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) tmp = fmaf(wc[q], line[cnn8_pos(8 * lane - 4 + q)], tmp);
+      acc = fmaf(wr, tmp, acc);
+      __syncwarp();
+    }
+    float *dst = out + er * robot_stride + (size_t)ox * 32 + lane;
+    dst[local_off] = acc;
+    dst[obst_off] = acc_obs;
+  }
+}
+
 }  // namespace ccb

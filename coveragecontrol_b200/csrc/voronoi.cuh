@@ -67,67 +67,105 @@ struct StripCtx {
   int *labels;                // optional label plane of this environment
 };
 
-// load the 4 cells of this lane in one row, applying the map-source mask
-__device__ __forceinline__ void load_cells(const StripCtx &c, int row, int col, float v[4]) {
+// ---- staging: the whole strip goes global -> shared with cp.async ---------------------------------
+// Every lane copies exactly the 16 bytes per row it later consumes, so a per-thread
+// cp.async.wait_group is the only synchronisation.  All rows of the strip are in flight at once:
+// memory-level parallelism comes from shared memory, not from registers.
+constexpr int VOR_MAXROWS = 16;  // rows per strip kept in shared memory (rpw <= VOR_MAXROWS)
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled, no global read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// Stage the strip.  wbuf: [rows][32] float4 (this warp's slice), mbuf: same size, raw masks.
+// Returns per-row 4-bit visibility of this lane's cells packed into a 64-bit word (row u -> bits
+// 4u..4u+3): inside the region AND visible in the selected map.  Cells that are not visible are
+// never read from the world map.
+__device__ __forceinline__ unsigned long long stage_strip(const StripCtx &c, int col, int lane, float4 *wbuf,
+                                                          uint4 *mbuf) {
   const EnvDev &d = *c.d;
   const size_t nn = (size_t)d.N * d.N;
-  const size_t off = (size_t)row * d.N + col;
-  const bool full = (col >= c.c0) && (col + 3 < c.c1) && ((d.N & 3) == 0);
-  v[0] = v[1] = v[2] = v[3] = 0.f;
-  if (col + 3 < c.c0 || col >= c.c1) return;
+  const int rows = c.r1 - c.r0;
+  const bool aligned = (d.N & 3) == 0;
+  unsigned in4 = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (col + i >= c.c0 && col + i < c.c1) in4 |= 1u << i;
+  unsigned long long vis = 0;
   const float *world = d.world + (size_t)c.e * nn;
   if (c.src == SRC_WORLD) {
-    if (full) {
-      float4 w = __ldg(reinterpret_cast<const float4 *>(world + off));
-      v[0] = w.x, v[1] = w.y, v[2] = w.z, v[3] = w.w;
+    for (int u = 0; u < rows; ++u) vis |= (unsigned long long)in4 << (4 * u);
+  } else if (in4) {
+    // phase A: masks
+    if (c.src == SRC_EXPLORED) {
+      const uint8_t *sys = d.sys + (size_t)c.e * nn;
+      if (aligned && in4 == 0xfu) {
+        for (int u = 0; u < rows; ++u)
+          cp_async4(reinterpret_cast<uint32_t *>(mbuf) + u * 32 + lane, sys + (size_t)(c.r0 + u) * d.N + col, true);
+        cp_async_wait_all();
+        for (int u = 0; u < rows; ++u) {
+          const uint32_t q = reinterpret_cast<const uint32_t *>(mbuf)[u * 32 + lane];
+          const unsigned m = (q & 1u) | ((q >> 7) & 2u) | ((q >> 14) & 4u) | ((q >> 21) & 8u);
+          vis |= (unsigned long long)m << (4 * u);
+        }
+      } else {
+        for (int u = 0; u < rows; ++u) {
+          unsigned m = 0;
+          for (int i = 0; i < 4; ++i)
+            if (in4 & (1u << i)) m |= (unsigned)(__ldg(sys + (size_t)(c.r0 + u) * d.N + col + i) & 1u) << i;
+          vis |= (unsigned long long)m << (4 * u);
+        }
+      }
     } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (col + i >= c.c0 && col + i < c.c1) v[i] = __ldg(world + off + i);
+      const uint32_t *seen = d.seen + ((size_t)c.e * d.W + (c.robot >> 5)) * nn;
+      const int sh = c.robot & 31;
+      if (aligned && in4 == 0xfu) {
+        for (int u = 0; u < rows; ++u) cp_async16(mbuf + u * 32 + lane, seen + (size_t)(c.r0 + u) * d.N + col, true);
+        cp_async_wait_all();
+        for (int u = 0; u < rows; ++u) {
+          const uint4 q = mbuf[u * 32 + lane];
+          const unsigned m = ((q.x >> sh) & 1u) | (((q.y >> sh) & 1u) << 1) | (((q.z >> sh) & 1u) << 2) |
+                             (((q.w >> sh) & 1u) << 3);
+          vis |= (unsigned long long)m << (4 * u);
+        }
+      } else {
+        for (int u = 0; u < rows; ++u) {
+          unsigned m = 0;
+          for (int i = 0; i < 4; ++i)
+            if (in4 & (1u << i)) m |= ((__ldg(seen + (size_t)(c.r0 + u) * d.N + col + i) >> sh) & 1u) << i;
+          vis |= (unsigned long long)m << (4 * u);
+        }
+      }
     }
-    return;
   }
-  bool m[4] = {false, false, false, false};
-  if (c.src == SRC_EXPLORED) {
-    const uint8_t *sys = d.sys + (size_t)c.e * nn;
-    if (full) {
-      uchar4 s = __ldg(reinterpret_cast<const uchar4 *>(sys + off));
-      m[0] = s.x & 1, m[1] = s.y & 1, m[2] = s.z & 1, m[3] = s.w & 1;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (col + i >= c.c0 && col + i < c.c1) m[i] = __ldg(sys + off + i) & 1;
+  // phase B: world values, only where something is visible
+  if (!d.use_sensor) {
+    for (int u = 0; u < rows; ++u) wbuf[u * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else if (aligned && (in4 == 0xfu || in4 == 0)) {
+    for (int u = 0; u < rows; ++u) {
+      const bool need = ((vis >> (4 * u)) & 0xfull) != 0;
+      cp_async16(wbuf + u * 32 + lane, need ? world + (size_t)(c.r0 + u) * d.N + col : world, need);
     }
+    cp_async_wait_all();
   } else {
-    const uint32_t *seen = d.seen + ((size_t)c.e * d.W + (c.robot >> 5)) * nn;
-    const uint32_t bit = 1u << (c.robot & 31);
-    if (full) {
-      uint4 s = __ldg(reinterpret_cast<const uint4 *>(seen + off));
-      m[0] = s.x & bit, m[1] = s.y & bit, m[2] = s.z & bit, m[3] = s.w & bit;
-    } else {
-#pragma unroll
+    for (int u = 0; u < rows; ++u) {
+      float t[4] = {0.f, 0.f, 0.f, 0.f};
       for (int i = 0; i < 4; ++i)
-        if (col + i >= c.c0 && col + i < c.c1) m[i] = __ldg(seen + off + i) & bit;
+        if ((vis >> (4 * u + i)) & 1ull) t[i] = __ldg(world + (size_t)(c.r0 + u) * d.N + col + i);
+      wbuf[u * 32 + lane] = make_float4(t[0], t[1], t[2], t[3]);
     }
   }
-  const float fill = (c.src == SRC_ROBOT) ? d.fill : 0.f;
-  const bool any = m[0] | m[1] | m[2] | m[3];
-  float w[4] = {0.f, 0.f, 0.f, 0.f};
-  if (any && d.use_sensor) {
-    if (full) {
-      float4 t = __ldg(reinterpret_cast<const float4 *>(world + off));
-      w[0] = t.x, w[1] = t.y, w[2] = t.z, w[3] = t.w;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (m[i]) w[i] = __ldg(world + off + i);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    bool in = (col + i >= c.c0) && (col + i < c.c1);
-    v[i] = in ? (m[i] ? w[i] : fill) : 0.f;
-  }
+  return vis;
 }
 
 __device__ __forceinline__ void reduce_and_emit(const StripCtx &c, const Acc6 &a, int col, int lane,
@@ -162,14 +200,13 @@ __device__ __forceinline__ void emit(double *sums, int e, int R, int slot, const
 
 // exact rule among `n` candidates (ascending site order): returns the index of the winner
 template <int NC>
-__device__ __noinline__ int exact_label(const double (&px)[NC], const double (&py)[NC], int row, int col,
-                                        double res) {
+__device__ __noinline__ int exact_label(const StripCtx &c, const int (&site)[NC], int row, int col, double res) {
   double cx = cell_centre(row, res), cy = cell_centre(col, res);
   int best = 0;
-  double bd = d2_exact(cx, cy, px[0], py[0]);
+  double bd = d2_exact(cx, cy, c.s_px[site[0]], c.s_py[site[0]]);
 #pragma unroll
   for (int k = 1; k < NC; ++k) {
-    double dd = d2_exact(cx, cy, px[k], py[k]);
+    double dd = d2_exact(cx, cy, c.s_px[site[k]], c.s_py[site[k]]);
     if (dd < bd) bd = dd, best = k;
   }
   return best;
@@ -178,17 +215,16 @@ __device__ __noinline__ int exact_label(const double (&px)[NC], const double (&p
 // Fast path: NC (1..4) candidate sites can own cells of this strip.
 // SINGLE: accumulate only cells owned by candidate 0 (the robot itself).
 template <int NC, bool SINGLE>
-__device__ void strip_fast(const StripCtx &c, const int (&site)[NC], float margin, int lane) {
+__device__ void strip_fast(const StripCtx &c, const int (&site)[NC], float margin, int lane, float4 *wbuf,
+                           uint4 *mbuf) {
   const EnvDev &d = *c.d;
   const double res = d.res;
   const float resf = (float)res;
-  double px[NC], py[NC];
   float qx[NC], qy[NC];
 #pragma unroll
   for (int k = 0; k < NC; ++k) {
-    px[k] = c.s_px[site[k]], py[k] = c.s_py[site[k]];
-    qx[k] = (float)(px[k] - (double)c.r0 * res);
-    qy[k] = (float)(py[k] - (double)c.col_base * res);
+    qx[k] = (float)(c.s_px[site[k]] - (double)c.r0 * res);
+    qy[k] = (float)(c.s_py[site[k]] - (double)c.col_base * res);
   }
   constexpr int NSETS = SINGLE ? 1 : NC;
   Acc6 acc[NSETS];
@@ -199,78 +235,91 @@ __device__ void strip_fast(const StripCtx &c, const int (&site)[NC], float margi
 #pragma unroll
   for (int i = 0; i < 4; ++i) yl[i] = resf * ((float)(4 * lane + i) + 0.5f);
 
-  for (int row = c.r0; row < c.r1; ++row) {
-    float v[4];
-    load_cells(c, row, col, v);
-    int lab[4] = {0, 0, 0, 0};
-    if (NC > 1) {
-      const float xl = resf * ((float)(row - c.r0) + 0.5f);
-      float dx2[NC];
+  const unsigned long long vis = stage_strip(c, col, lane, wbuf, mbuf);
+  const float fill = (c.src == SRC_ROBOT) ? d.fill : 0.f;
+  {
+    for (int row = c.r0; row < c.r1; ++row) {
+      const int u = row - c.r0;
+      const float4 w4 = wbuf[u * 32 + lane];
+      const unsigned vb = (unsigned)(vis >> (4 * u)) & 0xfu;
+      float v[4];
+      v[0] = (vb & 1u) ? w4.x : 0.f, v[1] = (vb & 2u) ? w4.y : 0.f;
+      v[2] = (vb & 4u) ? w4.z : 0.f, v[3] = (vb & 8u) ? w4.w : 0.f;
+      if (fill != 0.f) {
 #pragma unroll
-      for (int k = 0; k < NC; ++k) {
-        float dx = xl - qx[k];
-        dx2[k] = dx * dx;
+        for (int i = 0; i < 4; ++i)
+          if (!(vb & (1u << i)) && col + i >= c.c0 && col + i < c.c1) v[i] = fill;
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float best, second;
-        int bl = 0;
-        {
-          float dy = yl[i] - qy[0];
-          best = fmaf(dy, dy, dx2[0]);
-          second = INFINITY;
+      int lab[4] = {0, 0, 0, 0};
+      if (NC > 1) {
+        const float xl = resf * ((float)(row - c.r0) + 0.5f);
+        float dx2[NC];
+  #pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          float dx = xl - qx[k];
+          dx2[k] = dx * dx;
         }
-#pragma unroll
-        for (int k = 1; k < NC; ++k) {
-          float dy = yl[i] - qy[k];
-          float dd = fmaf(dy, dy, dx2[k]);
-          if (dd < best) {
-            second = best;
-            best = dd;
-            bl = k;
-          } else {
-            second = fminf(second, dd);
+  #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float best, second;
+          int bl = 0;
+          {
+            float dy = yl[i] - qy[0];
+            best = fmaf(dy, dy, dx2[0]);
+            second = INFINITY;
           }
+  #pragma unroll
+          for (int k = 1; k < NC; ++k) {
+            float dy = yl[i] - qy[k];
+            float dd = fmaf(dy, dy, dx2[k]);
+            if (dd < best) {
+              second = best;
+              best = dd;
+              bl = k;
+            } else {
+              second = fminf(second, dd);
+            }
+          }
+          if (second - best < margin) bl = exact_label<NC>(c, site, row, col + i, res);
+          lab[i] = bl;
         }
-        if (second - best < margin) bl = exact_label<NC>(px, py, row, col + i, res);
-        lab[i] = bl;
       }
-    }
-    if (!SINGLE && c.labels) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (col + i >= c.c0 && col + i < c.c1) c.labels[(size_t)row * d.N + col + i] = c.s_out[site[lab[i]]];
-    }
-    const double dv0 = (double)v[0], dv1 = (double)v[1], dv2 = (double)v[2], dv3 = (double)v[3];
-    const double xd = (double)row + 0.5;
-    const double xd2 = xd * xd;
-    if (!SINGLE) {
-      // set 0: every cell of the strip
-      Acc6 &t = acc[0];
-      t.c0 += dv0, t.c1 += dv1, t.c2 += dv2, t.c3 += dv3;
-      double s = (dv0 + dv1) + (dv2 + dv3);
-      t.sx = fma(xd, s, t.sx);
-      t.sxx = fma(xd2, s, t.sxx);
-#pragma unroll
-      for (int k = 1; k < NC; ++k) {
-        Acc6 &a = acc[k];
+      if (!SINGLE && c.labels) {
+  #pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (col + i >= c.c0 && col + i < c.c1) c.labels[(size_t)row * d.N + col + i] = c.s_out[site[lab[i]]];
+      }
+      const double dv0 = (double)v[0], dv1 = (double)v[1], dv2 = (double)v[2], dv3 = (double)v[3];
+      const double xd = (double)row + 0.5;
+      const double xd2 = xd * xd;
+      if (!SINGLE) {
+        // set 0: every cell of the strip
+        Acc6 &t = acc[0];
+        t.c0 += dv0, t.c1 += dv1, t.c2 += dv2, t.c3 += dv3;
+        double s = (dv0 + dv1) + (dv2 + dv3);
+        t.sx = fma(xd, s, t.sx);
+        t.sxx = fma(xd2, s, t.sxx);
+  #pragma unroll
+        for (int k = 1; k < NC; ++k) {
+          Acc6 &a = acc[k];
+          double s_k = 0.0;
+          if (lab[0] == k) a.c0 += dv0, s_k += dv0;
+          if (lab[1] == k) a.c1 += dv1, s_k += dv1;
+          if (lab[2] == k) a.c2 += dv2, s_k += dv2;
+          if (lab[3] == k) a.c3 += dv3, s_k += dv3;
+          a.sx = fma(xd, s_k, a.sx);
+          a.sxx = fma(xd2, s_k, a.sxx);
+        }
+      } else {
+        Acc6 &a = acc[0];
         double s_k = 0.0;
-        if (lab[0] == k) a.c0 += dv0, s_k += dv0;
-        if (lab[1] == k) a.c1 += dv1, s_k += dv1;
-        if (lab[2] == k) a.c2 += dv2, s_k += dv2;
-        if (lab[3] == k) a.c3 += dv3, s_k += dv3;
+        if (lab[0] == 0) a.c0 += dv0, s_k += dv0;
+        if (lab[1] == 0) a.c1 += dv1, s_k += dv1;
+        if (lab[2] == 0) a.c2 += dv2, s_k += dv2;
+        if (lab[3] == 0) a.c3 += dv3, s_k += dv3;
         a.sx = fma(xd, s_k, a.sx);
         a.sxx = fma(xd2, s_k, a.sxx);
       }
-    } else {
-      Acc6 &a = acc[0];
-      double s_k = 0.0;
-      if (lab[0] == 0) a.c0 += dv0, s_k += dv0;
-      if (lab[1] == 0) a.c1 += dv1, s_k += dv1;
-      if (lab[2] == 0) a.c2 += dv2, s_k += dv2;
-      if (lab[3] == 0) a.c3 += dv3, s_k += dv3;
-      a.sx = fma(xd, s_k, a.sx);
-      a.sxx = fma(xd2, s_k, a.sxx);
     }
   }
 
@@ -292,6 +341,24 @@ __device__ void strip_fast(const StripCtx &c, const int (&site)[NC], float margi
   if (lane == 0) emit(c.sums, c.e, d.R, c.s_out[site[0]], rest);
 }
 
+// direct (unstaged) loader for the generic path
+__device__ inline void load_cells_direct(const StripCtx &c, int row, int col, float v[4]) {
+  const EnvDev &d = *c.d;
+  const size_t nn = (size_t)d.N * d.N;
+  const size_t off = (size_t)row * d.N + col;
+  const float fill = (c.src == SRC_ROBOT) ? d.fill : 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = 0.f;
+    if (col + i < c.c0 || col + i >= c.c1) continue;
+    bool visible = true;
+    if (c.src == SRC_EXPLORED) visible = __ldg(d.sys + (size_t)c.e * nn + off + i) & 1;
+    else if (c.src == SRC_ROBOT)
+      visible = (__ldg(d.seen + ((size_t)c.e * d.W + (c.robot >> 5)) * nn + off + i) >> (c.robot & 31)) & 1u;
+    v[i] = visible ? (d.use_sensor ? __ldg(d.world + (size_t)c.e * nn + off + i) : 0.f) : fill;
+  }
+}
+
 // Generic path: any number of candidates, fp64 rule per cell, per-lane label runs flushed with
 // global atomics.  Only strips that contain > 4 competing sites come here.
 __device__ void strip_slow(const StripCtx &c, const int *cand, int nc, bool single, int lane) {
@@ -302,7 +369,7 @@ __device__ void strip_slow(const StripCtx &c, const int *cand, int nc, bool sing
   double m = 0, sx = 0, sy = 0, s2 = 0;
   for (int row = c.r0; row < c.r1; ++row) {
     float v[4];
-    load_cells(c, row, col, v);
+    load_cells_direct(c, row, col, v);
     const double cx = cell_centre(row, res);
     const double xd = (double)row + 0.5;
 #pragma unroll 1
@@ -340,8 +407,96 @@ __device__ void strip_slow(const StripCtx &c, const int *cand, int nc, bool sing
   }
 }
 
+// One warp, one strip: cull the candidate list to the sites that can own a cell of the strip,
+// then stream it.  cand[0..nc) are site indices (ascending) valid for the whole CTA rectangle.
+__device__ void process_strip(StripCtx &c, const int *s_cand, int nc, bool single, int rpw, int *wcand, int lane,
+                              float4 *wbuf, uint4 *mbuf) {
+  const EnvDev &d = *c.d;
+  const double res = d.res;
+  if (nc > 32) {
+    strip_slow(c, s_cand, nc, single, lane);
+    return;
+  }
+  // warp-level cull: lane k < nc holds candidate k
+  const bool has = lane < nc;
+  const int my_site = has ? s_cand[lane] : 0;
+  const double kx = c.s_px[my_site], ky = c.s_py[my_site];
+  double fcen = INFINITY;
+  if (has) fcen = d2_exact(cell_centre((c.r0 + c.r1 - 1) >> 1, res), cell_centre((c.c0 + c.c1 - 1) >> 1, res), kx, ky);
+  double best = fcen;
+  int bl = lane;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+    if (ob < best || (ob == best && ol < bl)) best = ob, bl = ol;
+  }
+  const double jx = __shfl_sync(0xffffffffu, kx, bl), jy = __shfl_sync(0xffffffffu, ky, bl);
+  bool keep = false;
+  double dmax = 0.0;
+  if (has) {
+    const double ccx[2] = {cell_centre(c.r0, res), cell_centre(c.r1 - 1, res)};
+    const double ccy[2] = {cell_centre(c.c0, res), cell_centre(c.c1 - 1, res)};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double fk = d2_exact(ccx[q & 1], ccy[q >> 1], kx, ky);
+      double fj = d2_exact(ccx[q & 1], ccy[q >> 1], jx, jy);
+      if (fk - fj <= 1e-7 * (1.0 + fj)) keep = true;
+      dmax = fmax(dmax, fk);
+    }
+  }
+  const unsigned wmask = __ballot_sync(0xffffffffu, keep);
+  const int wnc = __popc(wmask);
+  if (single && !(wmask & 1u)) return;  // the robot owns no cell of this strip
+  if (!keep) dmax = 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  // fp32 error bound of (d2_a - d2_b) in strip-local coordinates: < 2^-19.6 (dmax + span^2), DESIGN.md
+  const double span = res * (double)(VOR_TY + rpw);
+  const float margin = (float)((dmax + span * span) * (1.0 / 131072.0));
+
+  // gather the kept candidates' site indices (ascending) into registers of every lane
+  int ksite[4] = {0, 0, 0, 0};
+  {
+    unsigned mm = wmask;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (mm) {
+        int src_lane = __ffs(mm) - 1;
+        mm &= mm - 1;
+        ksite[q] = __shfl_sync(0xffffffffu, my_site, src_lane);
+      }
+    }
+  }
+  if (wnc == 1) {
+    int s1[1] = {ksite[0]};
+    if (single) strip_fast<1, true>(c, s1, margin, lane, wbuf, mbuf);
+    else strip_fast<1, false>(c, s1, margin, lane, wbuf, mbuf);
+  } else if (wnc == 2) {
+    int s2[2] = {ksite[0], ksite[1]};
+    if (single) strip_fast<2, true>(c, s2, margin, lane, wbuf, mbuf);
+    else strip_fast<2, false>(c, s2, margin, lane, wbuf, mbuf);
+  } else if (wnc == 3) {
+    int s3[3] = {ksite[0], ksite[1], ksite[2]};
+    if (single) strip_fast<3, true>(c, s3, margin, lane, wbuf, mbuf);
+    else strip_fast<3, false>(c, s3, margin, lane, wbuf, mbuf);
+  } else if (wnc == 4) {
+    if (single) strip_fast<4, true>(c, ksite, margin, lane, wbuf, mbuf);
+    else strip_fast<4, false>(c, ksite, margin, lane, wbuf, mbuf);
+  } else {
+    if (keep) wcand[__popc(wmask & ((1u << lane) - 1u))] = my_site;
+    __syncwarp();
+    strip_slow(c, wcand, wnc, single, lane);
+    __syncwarp();
+  }
+}
+
 // dynamic shared memory: double px[ns_cap], py[ns_cap]; int out[ns_cap]; int cand[ns_cap];
 // int wcand[VOR_WARPS][32]
+//
+// Global mode: grid = (tiles_x * tiles_y, 1, E); a CTA owns a 128-column x (8 rpw)-row tile, one
+// strip per warp.  Window mode (single): grid = (1, R, E); a CTA owns the robot's whole clipped
+// L-window and its warps loop over the window's strips, so the neighbour list is built once.
 __global__ void __launch_bounds__(VOR_THREADS) k_voronoi(VorArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const EnvDev &d = a.d;
@@ -351,6 +506,10 @@ __global__ void __launch_bounds__(VOR_THREADS) k_voronoi(VorArgs a) {
   int *s_out = reinterpret_cast<int *>(s_py + ns_cap);
   int *s_cand = s_out + ns_cap;
   int *s_wcand = s_cand + ns_cap;
+  // per-warp staging buffers (16-byte aligned): world tile, then mask tile
+  size_t stage_off = ((size_t)ns_cap * 24 + VOR_WARPS * 32 * sizeof(int) + 15) & ~(size_t)15;
+  float4 *s_wbuf = reinterpret_cast<float4 *>(smem_raw + stage_off);
+  uint4 *s_mbuf = reinterpret_cast<uint4 *>(s_wbuf + (size_t)VOR_WARPS * a.rpw * 32);
   __shared__ int s_ns, s_nc;
   __shared__ double s_best[VOR_WARPS];
   __shared__ int s_besti[VOR_WARPS];
@@ -362,18 +521,20 @@ __global__ void __launch_bounds__(VOR_THREADS) k_voronoi(VorArgs a) {
   const double res = d.res;
   const double *pos = d.pos_g + (size_t)e * d.R * 2;
 
-  // ---- region and tile ---------------------------------------------------------------------
-  int rx0 = 0, rx1 = d.N, ry0 = 0, ry1 = d.N;
+  // ---- CTA rectangle: rows [tr0, tr1), columns [tc0, tc1), column tiles start at col_base0 -----
+  int tr0, tr1, tc0, tc1, col_base0;
   if (a.single) {
     // decentralized_cvt.h:89-95: clipped L-window around the robot
     Window w = make_window(res, pos[2 * robot], pos[2 * robot + 1], d.L, d.N);
-    rx0 = w.x0, rx1 = w.x1, ry0 = w.y0, ry1 = w.y1;
+    tr0 = w.x0, tr1 = w.x1, tc0 = w.y0, tc1 = w.y1;
+    col_base0 = (tc0 / VOR_TY) * VOR_TY;
+  } else {
+    const int th = VOR_WARPS * a.rpw;
+    const int tx = blockIdx.x / a.tiles_y, ty = blockIdx.x - tx * a.tiles_y;
+    tr0 = tx * th, tr1 = min(tr0 + th, d.N);
+    col_base0 = ty * VOR_TY;
+    tc0 = col_base0, tc1 = min(col_base0 + VOR_TY, d.N);
   }
-  const int th = VOR_WARPS * a.rpw;
-  const int tx = blockIdx.x / a.tiles_y, ty = blockIdx.x - tx * a.tiles_y;
-  const int tr0 = rx0 + tx * th, tr1 = min(tr0 + th, rx1);
-  const int col_base = (ry0 / VOR_TY) * VOR_TY + ty * VOR_TY;
-  const int tc0 = max(col_base, ry0), tc1 = min(col_base + VOR_TY, ry1);
   if (tr0 >= tr1 || tc0 >= tc1) return;
 
   // ---- site list ---------------------------------------------------------------------------
@@ -463,95 +624,26 @@ __global__ void __launch_bounds__(VOR_THREADS) k_voronoi(VorArgs a) {
     if (tid < ns) s_cand[tid] = tid;
     __syncthreads();
   }
+  if (a.single && s_cand[0] != 0) return;  // the robot itself was culled: it owns no cell here
 
-  if (a.single && s_cand[0] != 0) return;  // the robot itself was culled: it owns no cell of this tile
-
-  // ---- per-warp strip ----------------------------------------------------------------------
+  // ---- strips: (row chunk, column tile) pairs dealt round-robin to the warps -------------------
   StripCtx c;
   c.d = &d, c.e = e, c.robot = robot, c.src = a.src;
-  c.r0 = tr0 + warp * a.rpw;
-  c.r1 = min(c.r0 + a.rpw, tr1);
-  c.c0 = tc0, c.c1 = tc1, c.col_base = col_base;
   c.s_px = s_px, c.s_py = s_py, c.s_out = s_out, c.sums = a.sums;
   c.labels = (a.labels && !a.single) ? a.labels + (size_t)e * d.N * d.N : nullptr;
-  if (c.r0 >= c.r1) return;
-
-  if (nc > 32) {
-    strip_slow(c, s_cand, nc, a.single != 0, lane);
-    return;
-  }
-
-  // warp-level cull: lane k < nc holds candidate k
-  const bool has = lane < nc;
-  const int my_site = has ? s_cand[lane] : 0;
-  const double kx = s_px[my_site], ky = s_py[my_site];
-  double fcen = INFINITY;
-  if (has) fcen = d2_exact(cell_centre((c.r0 + c.r1 - 1) >> 1, res), cell_centre((c.c0 + c.c1 - 1) >> 1, res), kx, ky);
-  double best = fcen;
-  int bl = lane;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    double ob = __shfl_xor_sync(0xffffffffu, best, o);
-    int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-    if (ob < best || (ob == best && ol < bl)) best = ob, bl = ol;
-  }
-  const double jx = __shfl_sync(0xffffffffu, kx, bl), jy = __shfl_sync(0xffffffffu, ky, bl);
-  bool keep = false;
-  double dmax = 0.0;
-  if (has) {
-    const double ccx[2] = {cell_centre(c.r0, res), cell_centre(c.r1 - 1, res)};
-    const double ccy[2] = {cell_centre(c.c0, res), cell_centre(c.c1 - 1, res)};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      double fk = d2_exact(ccx[q & 1], ccy[q >> 1], kx, ky);
-      double fj = d2_exact(ccx[q & 1], ccy[q >> 1], jx, jy);
-      if (fk - fj <= 1e-7 * (1.0 + fj)) keep = true;
-      dmax = fmax(dmax, fk);
-    }
-  }
-  const unsigned wmask = __ballot_sync(0xffffffffu, keep);
-  const int wnc = __popc(wmask);
-  if (a.single && !(wmask & 1u)) return;  // the robot owns no cell of this strip
-  if (!keep) dmax = 0.0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-  // fp32 error bound of (d2_a - d2_b) in strip-local coordinates: < 2^-19.6 * dmax
-  const double span = res * (double)(VOR_TY + a.rpw);
-  const float margin = (float)((dmax + span * span) * (1.0 / 131072.0));
-
-  // gather the kept candidates' site indices (ascending) into registers of every lane
-  int ksite[4] = {0, 0, 0, 0};
-  {
-    unsigned mm = wmask;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (mm) {
-        int src_lane = __ffs(mm) - 1;
-        mm &= mm - 1;
-        ksite[q] = __shfl_sync(0xffffffffu, my_site, src_lane);
-      }
-    }
-  }
-  if (wnc == 1) {
-    int s1[1] = {ksite[0]};
-    if (a.single) strip_fast<1, true>(c, s1, margin, lane);
-    else strip_fast<1, false>(c, s1, margin, lane);
-  } else if (wnc == 2) {
-    int s2[2] = {ksite[0], ksite[1]};
-    if (a.single) strip_fast<2, true>(c, s2, margin, lane);
-    else strip_fast<2, false>(c, s2, margin, lane);
-  } else if (wnc == 3) {
-    int s3[3] = {ksite[0], ksite[1], ksite[2]};
-    if (a.single) strip_fast<3, true>(c, s3, margin, lane);
-    else strip_fast<3, false>(c, s3, margin, lane);
-  } else if (wnc == 4) {
-    if (a.single) strip_fast<4, true>(c, ksite, margin, lane);
-    else strip_fast<4, false>(c, ksite, margin, lane);
-  } else {
-    int *wc = s_wcand + warp * 32;
-    if (keep) wc[__popc(wmask & ((1u << lane) - 1u))] = my_site;
+  const int nrow = (tr1 - tr0 + a.rpw - 1) / a.rpw;
+  const int ncol = (tc1 - 1 - col_base0) / VOR_TY + 1;
+  for (int sidx = warp; sidx < nrow * ncol; sidx += VOR_WARPS) {
+    const int ri = sidx / ncol, ci = sidx - ri * ncol;
+    c.r0 = tr0 + ri * a.rpw;
+    c.r1 = min(c.r0 + a.rpw, tr1);
+    c.col_base = col_base0 + ci * VOR_TY;
+    c.c0 = max(c.col_base, tc0);
+    c.c1 = min(c.col_base + VOR_TY, tc1);
+    if (c.c0 >= c.c1) continue;
+    process_strip(c, s_cand, nc, a.single != 0, a.rpw, s_wcand + warp * 32, lane,
+                  s_wbuf + (size_t)warp * a.rpw * 32, s_mbuf + (size_t)warp * a.rpw * 32);
     __syncwarp();
-    strip_slow(c, wc, wnc, a.single != 0, lane);
   }
 }
 

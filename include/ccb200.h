@@ -181,7 +181,12 @@ int ccb_ctrl_is_converged(ccb_ctrl *c, int *out /* E */);
 int ccb_ctrl_rollout(ccb_ctrl *c, int steps, int with_objective, double *objective_dev);
 const double *ccb_ctrl_actions_dev(const ccb_ctrl *c);
 
-/* ---- counters (bench.py "gpu_launches") ---------------------------------- */
+/* ---- profiling hooks (bench.py) ------------------------------------------------- */
+/* launch one kernel of the step `iters` times back to back on the env stream, bypassing caches:
+ * which = 0 Voronoi label+reduce (world map), 1 same on the explored-IDF map, 2 per-robot window
+ * variant, 3 sensor-window marking, 4 CNN input (C = 32, scratch_dev = E x R x 4 x 32 x 32 floats),
+ * 5 cell finalisation */
+int ccb_bench_kernel(ccb_env *env, int which, int iters, float *scratch_dev);
 uint64_t ccb_kernel_launch_count(void);
 
 #ifdef __cplusplus
