@@ -361,25 +361,27 @@ struct ccb_env {
   int vor_rpw_override = 0;
 };
 
+// rows per warp region: as large as keeps >= ~3 CTAs per SM in flight over the whole launch
 static int pick_rpw(const ccb_env *env, int region_rows, int region_cols, int regions) {
-  if (env->vor_rpw_override > 0) return std::min(env->vor_rpw_override, VOR_MAXROWS);
-  const int tiles_y = (region_cols + VOR_TY - 1) / VOR_TY + 1;
-  for (int rpw = VOR_MAXROWS; rpw > 1; rpw >>= 1) {
-    long tiles_x = (region_rows + VOR_WARPS * rpw - 1) / (VOR_WARPS * rpw);
-    if ((long)regions * tiles_x * tiles_y >= 4L * 148) return rpw;
+  if (env->vor_rpw_override > 0) return std::max(2, std::min(env->vor_rpw_override, VOR_MAXRPW) & ~1);
+  const long tiles_y = (region_cols + VOR_WX * VOR_TW - 1) / (VOR_WX * VOR_TW);
+  for (int rpw = 64; rpw > 4; rpw >>= 1) {
+    long tiles_x = (region_rows + VOR_WY * rpw - 1) / (VOR_WY * rpw);
+    if ((long)regions * tiles_x * tiles_y >= 3L * 148) return rpw;
   }
-  return 1;
+  return 4;
 }
 
-// sites + candidate lists + per-warp staging (world tile, and a mask tile for the masked sources)
-static size_t vor_smem(int R, int rpw, bool masked) {
+// sites + candidate lists + per-warp staging (two world chunks and one mask chunk)
+static size_t vor_smem(int R) {
   size_t base = ((size_t)R * 24 + VOR_WARPS * 32 * sizeof(int) + 15) & ~(size_t)15;
-  return base + (size_t)VOR_WARPS * rpw * 32 * 16 * (masked ? 2 : 1);
+  return base + (size_t)VOR_WARPS * VOR_STAGE_BYTES_PER_WARP;
 }
+template <bool SINGLE>
 static int set_vor_smem(size_t bytes) {
   static size_t current = 48 * 1024;
   if (bytes > current) {
-    CCB_CUDA(cudaFuncSetAttribute(k_voronoi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    CCB_CUDA(cudaFuncSetAttribute(k_voronoi<SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     current = bytes;
   }
   return 0;
@@ -390,14 +392,14 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
   const EnvDev &d = env->d;
   CCB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * d.E * d.R, env->stream));
   VorArgs a;
-  a.d = d, a.single = 0, a.src = src, a.sums = sums, a.labels = labels;
+  a.d = d, a.src = src, a.sums = sums, a.labels = labels;
   a.rpw = pick_rpw(env, d.N, d.N, d.E);
-  a.tiles_y = (d.N + VOR_TY - 1) / VOR_TY;
-  a.tiles_x = (d.N + VOR_WARPS * a.rpw - 1) / (VOR_WARPS * a.rpw);
+  a.tiles_y = (d.N + VOR_WX * VOR_TW - 1) / (VOR_WX * VOR_TW);
+  a.tiles_x = (d.N + VOR_WY * a.rpw - 1) / (VOR_WY * a.rpw);
   dim3 grid(a.tiles_x * a.tiles_y, 1, d.E);
-  const size_t smem = vor_smem(d.R, a.rpw, src != SRC_WORLD);
-  if (set_vor_smem(smem)) return 1;
-  k_voronoi<<<grid, VOR_THREADS, smem, env->stream>>>(a);
+  const size_t smem = vor_smem(d.R);
+  if (set_vor_smem<false>(smem)) return 1;
+  k_voronoi<false><<<grid, VOR_THREADS, smem, env->stream>>>(a);
   CCB_LAUNCH_CHECK();
   return 0;
 }
@@ -407,13 +409,13 @@ static int launch_voronoi_single(ccb_env *env, double *sums) {
   const EnvDev &d = env->d;
   CCB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * d.E * d.R, env->stream));
   VorArgs a;
-  a.d = d, a.single = 1, a.src = SRC_ROBOT, a.sums = sums, a.labels = nullptr;
-  a.rpw = env->vor_rpw_override > 0 ? std::min(env->vor_rpw_override, VOR_MAXROWS) : 8;
+  a.d = d, a.src = SRC_ROBOT, a.sums = sums, a.labels = nullptr;
+  a.rpw = env->vor_rpw_override > 0 ? std::max(2, std::min(env->vor_rpw_override, VOR_MAXRPW) & ~1) : 64;
   a.tiles_x = a.tiles_y = 1;  // one CTA per robot window
   dim3 grid(1, d.R, d.E);
-  const size_t smem = vor_smem(d.R, a.rpw, true);
-  if (set_vor_smem(smem)) return 1;
-  k_voronoi<<<grid, VOR_THREADS, smem, env->stream>>>(a);
+  const size_t smem = vor_smem(d.R);
+  if (set_vor_smem<true>(smem)) return 1;
+  k_voronoi<true><<<grid, VOR_THREADS, smem, env->stream>>>(a);
   CCB_LAUNCH_CHECK();
   return 0;
 }
