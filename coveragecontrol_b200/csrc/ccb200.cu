@@ -377,11 +377,11 @@ static size_t vor_smem(int R) {
   size_t base = ((size_t)R * 24 + VOR_WARPS * 32 * sizeof(int) + 15) & ~(size_t)15;
   return base + (size_t)VOR_WARPS * VOR_STAGE_BYTES_PER_WARP;
 }
-template <bool SINGLE>
+template <bool SINGLE, bool LABELS>
 static int set_vor_smem(size_t bytes) {
   static size_t current = 48 * 1024;
   if (bytes > current) {
-    CCB_CUDA(cudaFuncSetAttribute(k_voronoi<SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    CCB_CUDA(cudaFuncSetAttribute(k_voronoi<SINGLE, LABELS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     current = bytes;
   }
   return 0;
@@ -398,8 +398,13 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
   a.tiles_x = (d.N + VOR_WY * a.rpw - 1) / (VOR_WY * a.rpw);
   dim3 grid(a.tiles_x * a.tiles_y, 1, d.E);
   const size_t smem = vor_smem(d.R);
-  if (set_vor_smem<false>(smem)) return 1;
-  k_voronoi<false><<<grid, VOR_THREADS, smem, env->stream>>>(a);
+  if (labels) {
+    if (set_vor_smem<false, true>(smem)) return 1;
+    k_voronoi<false, true><<<grid, VOR_THREADS, smem, env->stream>>>(a);
+  } else {
+    if (set_vor_smem<false, false>(smem)) return 1;
+    k_voronoi<false, false><<<grid, VOR_THREADS, smem, env->stream>>>(a);
+  }
   CCB_LAUNCH_CHECK();
   return 0;
 }
@@ -414,8 +419,8 @@ static int launch_voronoi_single(ccb_env *env, double *sums) {
   a.tiles_x = a.tiles_y = 1;  // one CTA per robot window
   dim3 grid(1, d.R, d.E);
   const size_t smem = vor_smem(d.R);
-  if (set_vor_smem<true>(smem)) return 1;
-  k_voronoi<true><<<grid, VOR_THREADS, smem, env->stream>>>(a);
+  if (set_vor_smem<true, false>(smem)) return 1;
+  k_voronoi<true, false><<<grid, VOR_THREADS, smem, env->stream>>>(a);
   CCB_LAUNCH_CHECK();
   return 0;
 }

@@ -123,9 +123,9 @@ __global__ void k_cnn_local_obstacle(EnvDev d, int C, ResizeTable tab, float *__
 
 
 // ---- specialised path for L = 8 C (LPAC: 256 -> 32) ----------------------------------------------
-// One CTA per (robot, env), 8 warps; warp w owns output rows ox = w, w+8, w+16, w+24 and lane = oy.
-// For each of the <= 16 input rows of an output row the warp reads the 256-cell row of the robot's
-// local window once (coalesced, seen mask first, world only where seen), stages it in a padded
+// One CTA per (robot, env), 8 warps; warp w owns output rows 4w .. 4w+3 (40 window rows, each read
+// once by the warp) and lane = oy.  Rows are loaded one ahead of their use (coalesced, seen word
+// and world value requested together), masked, staged in a padded
 // shared-memory line (one pad word per 8 cells -> the 16-tap reads of the 32 lanes hit 32 different
 // banks) and runs the width pass; the height pass accumulates in a register in ascending row order,
 // the same order torchvision's separable antialias kernel uses.  The obstacle channel needs no map
@@ -135,6 +135,26 @@ constexpr int CNN8_THREADS = 256;
 constexpr int CNN8_LINE = 304;
 // window column b in [-4, 260) -> word of the padded line (one pad word per 8 cells)
 __device__ __forceinline__ int cnn8_pos(int b) { return (b + 8) + ((b + 8) >> 3); }
+
+// Loads this lane's 8 cells (columns 32 k + lane) of window row gx: seen words and world values are
+// requested together (the world load does not wait for the mask), masked afterwards.
+struct Cnn8Row {
+  uint32_t m[8];
+  float w[8];
+  bool in_x;
+};
+__device__ __forceinline__ void cnn8_load(Cnn8Row &r, const uint32_t *__restrict__ seen, const float *__restrict__ world,
+                                          int N, int gx, int oy0, int lane) {
+  r.in_x = gx >= 0 && gx < N;
+  const size_t row_off = (size_t)(r.in_x ? gx : 0) * N;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int gy = oy0 + 32 * k + lane;
+    const bool in = r.in_x && gy >= 0 && gy < N;
+    r.m[k] = in ? __ldg(seen + row_off + gy) : 0u;
+    r.w[k] = in ? __ldg(world + row_off + gy) : 0.f;
+  }
+}
 
 __global__ void __launch_bounds__(CNN8_THREADS)
 k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__restrict__ out,
@@ -147,7 +167,7 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
   const size_t nn = cell_count(d);
   for (int t = threadIdx.x; t < 32 * 16; t += CNN8_THREADS) s_w[t >> 4][t & 15] = wfull[t];
   float *line = s_line[warp];
-  if (lane < 4) line[cnn8_pos(lane - 4)] = 0.f;   // taps left of the window
+  if (lane < 4) line[cnn8_pos(lane - 4)] = 0.f;         // taps left of the window
   else if (lane < 8) line[cnn8_pos(252 + lane)] = 0.f;  // taps right of the window (b = 256..259)
   __syncthreads();
   const double *p = d.pos_g + er * 2;
@@ -169,43 +189,54 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
     oy_out = fmaf(wc[q], in_y ? 0.f : 1.f, oy_out);
   }
 
-  for (int ox = warp; ox < 32; ox += CNN8_THREADS / 32) {
-    float acc = 0.f, acc_obs = 0.f;
-    for (int t = 0; t < 16; ++t) {
-      const float wr = s_w[ox][t];
-      if (wr == 0.f) continue;  // outside torch's tap range (warp-uniform)
-      const int gx = w.ox + 8 * ox - 4 + t;
-      const bool in_x = gx >= 0 && gx < d.N;
-      acc_obs = fmaf(wr, in_x ? oy_out : oy_all, acc_obs);
-      if (!in_x) continue;  // zero padding: the whole row contributes nothing (warp-uniform)
-      const size_t row_off = (size_t)gx * d.N;
-      bool any = false;
-      float vals[8];
+  // This warp owns output rows ox0 .. ox0+3; they need window rows a0 = 8 ox0 - 4 .. 8 ox0 + 35.
+  // Row a contributes to output row o = ox0 + i with weight s_w[o][a - (8 o - 4)] (two rows at most).
+  const int ox0 = warp * 4;
+  const int a0 = 8 * ox0 - 4;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc_obs[4] = {0.f, 0.f, 0.f, 0.f};
+  Cnn8Row cur, nxt;
+  cnn8_load(cur, seen, world, d.N, w.ox + a0, w.oy, lane);
+#pragma unroll 1
+  for (int t = 0; t < 40; ++t) {
+    if (t + 1 < 40) cnn8_load(nxt, seen, world, d.N, w.ox + a0 + t + 1, w.oy, lane);  // one row ahead
+    // weights of this row for the four output rows (zero outside torch's 16-tap range)
+    float wr[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int gy = w.oy + 32 * k + lane;
-        float v = 0.f;
-        if (gy >= 0 && gy < d.N) {
-          const uint32_t m = __ldg(seen + row_off + gy);
-          if (m & bit) v = d.use_sensor ? __ldg(world + row_off + gy) : 0.f;
-          else v = d.fill;
-        }
-        vals[k] = v;
-        any |= (v != 0.f);
-      }
-      if (!__any_sync(0xffffffffu, any)) continue;  // all-zero row (unseen): adds nothing
+    for (int i = 0; i < 4; ++i) {
+      const int k = t - 8 * i;  // tap index of row a0 + t in output row ox0 + i
+      wr[i] = (k >= 0 && k < 16) ? s_w[ox0 + i][k] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc_obs[i] = fmaf(wr[i], cur.in_x ? oy_out : oy_all, acc_obs[i]);
+    bool any = false;
+    float vals[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int gy = w.oy + 32 * k + lane;
+      const bool in = cur.in_x && gy >= 0 && gy < d.N;
+      float v = 0.f;
+      if (in) v = (cur.m[k] & bit) ? (d.use_sensor ? cur.w[k] : 0.f) : d.fill;
+      vals[k] = v;
+      any |= (v != 0.f);
+    }
+    if (__any_sync(0xffffffffu, any)) {  // all-zero rows (unseen / outside the world) add nothing
 #pragma unroll
       for (int k = 0; k < 8; ++k) line[cnn8_pos(32 * k + lane)] = vals[k];
       __syncwarp();
       float tmp = 0.f;
 #pragma unroll
       for (int q = 0; q < 16; ++q) tmp = fmaf(wc[q], line[cnn8_pos(8 * lane - 4 + q)], tmp);
-      acc = fmaf(wr, tmp, acc);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(wr[i], tmp, acc[i]);
       __syncwarp();
     }
-    float *dst = out + er * robot_stride + (size_t)ox * 32 + lane;
-    dst[local_off] = acc;
-    dst[obst_off] = acc_obs;
+    cur = nxt;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float *dst = out + er * robot_stride + (size_t)(ox0 + i) * 32 + lane;
+    dst[local_off] = acc[i];
+    dst[obst_off] = acc_obs[i];
   }
 }
 

@@ -42,7 +42,10 @@ constexpr int VOR_CH = 8;        // passes (2 rows each) per staging chunk: 8 x 
 constexpr int VOR_NBUF = 3;      // ring of staging chunks per warp (prefetch distance VOR_NBUF - 1)
 constexpr int VOR_MAXRPW = 128;  // rows per warp region
 constexpr int VOR_MAXFAST = 3;   // regions with more competing sites are split, then take the generic path
-constexpr int VOR_MINSPLIT = 4;  // do not split below this many rows
+constexpr int VOR_MINSPLIT = 4;
+// passes of the streaming loop interleaved for ILP (2 warps per scheduler cannot hide the
+// LDS -> F2F -> DADD chain of a single pass)
+constexpr int VOR_UNROLL = 1;  // do not split below this many rows
 
 enum { SRC_WORLD = 0, SRC_EXPLORED = 1, SRC_ROBOT = 2 };
 
@@ -101,6 +104,32 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// ---- bulk (TMA 1-D) copies completing on an mbarrier: one 256-byte row per lane, one warp
+//      instruction per chunk (SASS: UBLKCP + SYNCS) ------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned done = 0;
+  int spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1 << 22)) __trap();  // a lost copy must fail loudly, never hang the GPU
+  }
 }
 
 // ---- staging of one chunk ------------------------------------------------------------------------
@@ -290,9 +319,11 @@ __device__ __noinline__ int column_threshold(const double *s_px, const double *s
 
 // Fast path: NC (1..VOR_MAXFAST) candidate sites k0 < k1 < k2 can own cells of this region.
 // SINGLE: accumulate only the cells owned by candidate 0 (the robot itself).
-template <int NC, bool SINGLE>
+// LABELS: also store the label of every cell (parity tests only; a separate instantiation).
+// bars / phase: this warp's ring mbarriers (shared-memory addresses) and their parity bits.
+template <int NC, bool SINGLE, bool LABELS>
 __device__ __forceinline__ void region_fast(const StripCtx &c, int k0, int k1, int k2, int lane, float4 *wbuf,
-                                            unsigned *svis) {
+                                            unsigned *svis, unsigned bars, unsigned &phase) {
   const double res = c.res;
   const int hp = lane >> 4;
   const int col = c.col_base + 4 * (lane & 15);
@@ -345,32 +376,61 @@ __device__ __forceinline__ void region_fast(const StripCtx &c, int k0, int k1, i
   const float fill = (c.src == SRC_ROBOT) ? c.fill : 0.f;
 
   // ---- stream the region through a ring of VOR_NBUF chunks (prefetch distance VOR_NBUF - 1) ------
-  // Every iteration commits exactly one cp.async group (possibly empty), so "at most VOR_NBUF - 1
-  // groups pending" always means "chunk ch has landed".
+  // Interior regions of the world map (`bulk`): lanes 0-15 each copy one 256-byte row of the chunk
+  // with a bulk copy that completes on the slot's mbarrier -- one warp instruction per chunk.
+  // Otherwise (masked sources, map edges): per-lane cp.async; every iteration commits exactly one
+  // group (possibly empty), so "at most VOR_NBUF - 1 groups pending" means "chunk ch has landed".
   const int nch = (npass + VOR_CH - 1) / VOR_CH;
   float4 *wl = wbuf + lane;
+  const bool bulk = c.src == SRC_WORLD && (c.N & 3) == 0 && c.use_sensor && c.c0 == c.col_base &&
+                    c.c1 == c.col_base + VOR_TW && (rows & 1) == 0;
+  const float *brow = c.world + (size_t)(c.r0 + (lane & 15)) * c.N + c.col_base;  // this lane's row of chunk 0
+  const unsigned ring = (unsigned)__cvta_generic_to_shared(wbuf);
 #pragma unroll 1
   for (int b = 0; b < VOR_NBUF - 1; ++b) {
-    if (b < nch) svis[b * 32 + lane] = stage_chunk(c, b * VOR_CH, min(VOR_CH, npass - b * VOR_CH), lane, wl + b * (VOR_CH * 32));
-    else cp_async_commit();
+    if (bulk) {
+      if (b < nch) {
+        const int nr = min(2 * VOR_CH, rows - 2 * VOR_CH * b);
+        if (lane == 0) mbar_expect_tx(bars + 8 * b, nr * 256);
+        __syncwarp();
+        if (lane < nr) bulk_copy_g2s(ring + b * (VOR_CH * 512) + lane * 256, brow + (size_t)(2 * VOR_CH * b) * c.N, 256, bars + 8 * b);
+      }
+    } else if (b < nch) {
+      svis[b * 32 + lane] = stage_chunk(c, b * VOR_CH, min(VOR_CH, npass - b * VOR_CH), lane, wl + b * (VOR_CH * 32));
+    } else {
+      cp_async_commit();
+    }
   }
 #pragma unroll 1
   for (int ch = 0; ch < nch; ++ch) {
     const int t0 = ch * VOR_CH;
     const int np = min(VOR_CH, npass - t0);
+    const int cb = ch % VOR_NBUF;
+    unsigned vis_cur = 0xffffffffu;
     {
       const int nx = ch + VOR_NBUF - 1, nb = nx % VOR_NBUF;
-      if (nx < nch) svis[nb * 32 + lane] = stage_chunk(c, nx * VOR_CH, min(VOR_CH, npass - nx * VOR_CH), lane, wl + nb * (VOR_CH * 32));
-      else cp_async_commit();
+      if (bulk) {
+        if (nx < nch) {
+          const int nr = min(2 * VOR_CH, rows - 2 * VOR_CH * nx);
+          if (lane == 0) mbar_expect_tx(bars + 8 * nb, nr * 256);
+          __syncwarp();
+          if (lane < nr) bulk_copy_g2s(ring + nb * (VOR_CH * 512) + lane * 256, brow + (size_t)(2 * VOR_CH * nx) * c.N, 256, bars + 8 * nb);
+        }
+        mbar_wait(bars + 8 * cb, (phase >> cb) & 1u);
+        phase ^= 1u << cb;
+      } else {
+        if (nx < nch) svis[nb * 32 + lane] = stage_chunk(c, nx * VOR_CH, min(VOR_CH, npass - nx * VOR_CH), lane, wl + nb * (VOR_CH * 32));
+        else cp_async_commit();
+        cp_async_wait<VOR_NBUF - 1>();
+        vis_cur = svis[cb * 32 + lane];
+      }
     }
-    cp_async_wait<VOR_NBUF - 1>();
-    const int cb = ch % VOR_NBUF;
     const float4 *wp = wl + cb * (VOR_CH * 32);
-    const unsigned vis_cur = svis[cb * 32 + lane];
-    const bool plain_cur = __all_sync(0xffffffffu, vis_cur == 0xffffffffu);
-#pragma unroll 1
-    for (int j = 0; j < np; ++j) {
-      const int u = 2 * (t0 + j) + hp;  // row of this lane in this pass, relative to r0
+    const bool plain_cur = bulk || __all_sync(0xffffffffu, vis_cur == 0xffffffffu);
+    int u = 2 * t0 + hp;                         // row of this lane in this pass, relative to r0
+    double xd = (double)(c.r0 + u) + 0.5;
+#pragma unroll(VOR_UNROLL)
+    for (int j = 0; j < np; ++j, u += 2, xd += 2.0) {
       const float4 w4 = wp[j * 32];
       float v0 = w4.x, v1 = w4.y, v2 = w4.z, v3 = w4.w;
       if (!plain_cur) {
@@ -417,7 +477,7 @@ __device__ __forceinline__ void region_fast(const StripCtx &c, int k0, int k1, i
           l3 = exact_label(c.s_px, c.s_py, k0, k1, k2, 3, c.r0 + u, col + 3, res);
         }
       }
-      if (!SINGLE && c.labels && c.r0 + u < c.r1) {
+      if (LABELS && !SINGLE && c.labels && c.r0 + u < c.r1) {
         int *lp = c.labels + (size_t)(c.r0 + u) * c.N + col;
         if (col + 0 >= c.c0 && col + 0 < c.c1) lp[0] = c.s_out[ksel[l0]];
         if (col + 1 >= c.c0 && col + 1 < c.c1) lp[1] = c.s_out[ksel[l1]];
@@ -425,7 +485,6 @@ __device__ __forceinline__ void region_fast(const StripCtx &c, int k0, int k1, i
         if (col + 3 >= c.c0 && col + 3 < c.c1) lp[3] = c.s_out[ksel[l3]];
       }
       const double dv0 = (double)v0, dv1 = (double)v1, dv2 = (double)v2, dv3 = (double)v3;
-      const double xd = (double)(c.r0 + u) + 0.5;
       const double xd2 = xd * xd;
       if (!SINGLE) {
         Acc6 &t = acc[0];  // set 0: every cell of the region
@@ -455,6 +514,7 @@ __device__ __forceinline__ void region_fast(const StripCtx &c, int k0, int k1, i
         a.sxx = fma(xd2, s_k, a.sxx);
       }
     }
+    __syncwarp();  // every lane is done with this slot before it is refilled
   }
 
   Sum4 tot = fold_and_reduce(acc[0], col);
@@ -585,9 +645,10 @@ __device__ __noinline__ unsigned cull_rect(double res, int c0, int c1, int r0, i
 // One warp, one region.  cand[0..nc) are site indices (ascending) valid for the whole CTA rectangle.
 // The region is culled; if more than VOR_MAXFAST sites can own cells it is split in row halves and
 // each half is culled again (fewer rows, fewer owners) before falling back to the generic path.
-template <bool SINGLE>
+template <bool SINGLE, bool LABELS>
 __device__ __forceinline__ void process_region(StripCtx &c, const int *s_cand, int nc, int *wcand, int lane,
-                                               float4 *wbuf, unsigned *svis, StripCtx *sctx) {
+                                               float4 *wbuf, unsigned *svis, StripCtx *sctx, unsigned bars,
+                                               unsigned &phase) {
   if (nc > 32) {
     if (lane == 0) *sctx = c;
     __syncwarp();
@@ -625,11 +686,11 @@ __device__ __forceinline__ void process_region(StripCtx &c, const int *s_cand, i
       }
     }
     if (wnc == 1) {
-      region_fast<1, SINGLE>(c, ksite[0], ksite[0], ksite[0], lane, wbuf, svis);
+      region_fast<1, SINGLE, LABELS>(c, ksite[0], ksite[0], ksite[0], lane, wbuf, svis, bars, phase);
     } else if (wnc == 2) {
-      region_fast<2, SINGLE>(c, ksite[0], ksite[1], ksite[1], lane, wbuf, svis);
+      region_fast<2, SINGLE, LABELS>(c, ksite[0], ksite[1], ksite[1], lane, wbuf, svis, bars, phase);
     } else if (wnc == 3) {
-      region_fast<3, SINGLE>(c, ksite[0], ksite[1], ksite[2], lane, wbuf, svis);
+      region_fast<3, SINGLE, LABELS>(c, ksite[0], ksite[1], ksite[2], lane, wbuf, svis, bars, phase);
     } else {
       const bool keep = (wmask >> lane) & 1u;
       if (keep) wcand[__popc(wmask & ((1u << lane) - 1u))] = my_site;
@@ -651,10 +712,11 @@ __device__ __forceinline__ void process_region(StripCtx &c, const int *s_cand, i
 // SINGLE = true (window):  grid = (1, R, E); a CTA owns one robot's whole clipped L-window and its
 //   warps loop over the window's regions; sites = the robot + its neighbours within communication
 //   range (decentralized_cvt.h:100-120), only the robot's own cell is reduced.
-constexpr size_t VOR_STAGE_BYTES_PER_WARP = (size_t)VOR_NBUF * VOR_CH * 32 * 16 + VOR_NBUF * 32 * sizeof(unsigned) + 128;
+constexpr size_t VOR_STAGE_BYTES_PER_WARP =
+    (size_t)VOR_NBUF * VOR_CH * 32 * 16 + VOR_NBUF * 32 * sizeof(unsigned) + 128 + 32;  // ring, vis, ctx, mbarriers
 static_assert(sizeof(StripCtx) <= 128, "per-warp context slot too small");
 
-template <bool SINGLE>
+template <bool SINGLE, bool LABELS>
 __global__ void __launch_bounds__(VOR_THREADS) k_voronoi(VorArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const EnvDev &d = a.d;
@@ -674,6 +736,14 @@ __global__ void __launch_bounds__(VOR_THREADS) k_voronoi(VorArgs a) {
   float4 *wbuf = reinterpret_cast<float4 *>(smem_raw + stage_off + warp * VOR_STAGE_BYTES_PER_WARP);
   unsigned *svis = reinterpret_cast<unsigned *>(wbuf + VOR_NBUF * VOR_CH * 32);
   StripCtx *sctx = reinterpret_cast<StripCtx *>(svis + VOR_NBUF * 32);
+  const unsigned bars = (unsigned)__cvta_generic_to_shared(reinterpret_cast<unsigned char *>(sctx) + 128);
+  unsigned phase = 0;
+  if (lane == 0) {
+    for (int b = 0; b < VOR_NBUF; ++b) mbar_init(bars + 8 * b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncwarp();
   const int e = blockIdx.z;
   const int robot = SINGLE ? blockIdx.y : 0;
   const double res = d.res;
@@ -792,7 +862,7 @@ __global__ void __launch_bounds__(VOR_THREADS) k_voronoi(VorArgs a) {
   c.sys = d.sys + (size_t)e * nn;
   c.e = e, c.robot = robot, c.src = a.src;
   c.s_px = s_px, c.s_py = s_py, c.s_out = s_out, c.sums = a.sums;
-  c.labels = (a.labels && !SINGLE) ? a.labels + (size_t)e * nn : nullptr;
+  c.labels = (LABELS && a.labels && !SINGLE) ? a.labels + (size_t)e * nn : nullptr;
   const int nrow = (tr1 - tr0 + a.rpw - 1) / a.rpw;
   const int ncol = (tc1 - 1 - col_base0) / VOR_TW + 1;
   for (int sidx = warp; sidx < nrow * ncol; sidx += VOR_WARPS) {
@@ -803,7 +873,7 @@ __global__ void __launch_bounds__(VOR_THREADS) k_voronoi(VorArgs a) {
     c.c0 = max(c.col_base, tc0);
     c.c1 = min(c.col_base + VOR_TW, tc1);
     if (c.c0 >= c.c1) continue;
-    process_region<SINGLE>(c, s_cand, nc, s_wcand + warp * 32, lane, wbuf, svis, sctx);
+    process_region<SINGLE, LABELS>(c, s_cand, nc, s_wcand + warp * 32, lane, wbuf, svis, sctx, bars, phase);
     __syncwarp();
   }
 }
