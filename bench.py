@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=128)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the single-environment / C1 extras (ncu launch lists)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -337,6 +338,8 @@ def main():
     # ---- single-environment latency (API-faithful, E = 1) and the C1 variant, reported as extras -----
     extras = {"idf_gen_ms_1024_32f_mode0": idf_ms}
     try:
+        if args.no_extras:
+            raise RuntimeError("skipped (--no-extras)")
         one = BatchedCoverageSystem(p, 1, N_ROBOTS, device=local_rank)
         bnd, pos = synth_inputs(0)
         idf = ccb.WorldIDF(p, device=local_rank)

@@ -1,0 +1,24 @@
+#!/bin/bash
+# Round evidence on one B200 (run under gpurun): GPU parity tests, the bench line, the ncu launch
+# list of the same bench command and one `ncu --set full` capture per hot kernel.
+#   gpurun --timeout 1500 -- 'bash scripts/gpu_evidence.sh r01'
+set -u
+tag=${1:-r01}
+out=gpurun_out
+mkdir -p $out
+python -m pytest tests -m gpu -x -q > $out/pytest_$tag.log 2>&1
+echo "pytest rc=$?" | tee -a $out/pytest_$tag.log
+tail -3 $out/pytest_$tag.log
+python bench.py --steps 10 --warmup 3 > $out/bench_$tag.json 2> $out/bench_$tag.err
+echo "bench rc=$?"
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > $out/bench_short_$tag.json 2> $out/bench_short_$tag.err &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $out/launches_$tag.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > $out/ncu_launches_$tag.log 2>&1
+echo "launch list rc=$?"
+for which in 0 2 4; do
+  python scripts/prof_kernels.py --which $which --envs 64 --iters 3 > $out/prof_plain_${tag}_k$which.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'k_vor|k_cnn' -s 1 -c 1 -f \
+      -o $out/prof_${tag}_k$which python scripts/prof_kernels.py --which $which --envs 64 --iters 3 \
+      > $out/ncu_${tag}_k$which.log 2>&1
+  echo "ncu k$which rc=$?"
+done

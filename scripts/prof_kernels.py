@@ -42,8 +42,11 @@ obs = torch.empty((E, bench.N_ROBOTS, 4, 32, 32), device="cuda")
 torch.cuda.synchronize()
 s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 _lib.check(lib.ccb_bench_kernel(batch._h, args.which, 2, obs.data_ptr()))
+torch.cuda.synchronize()
+torch.cuda.profiler.start()  # ncu --profile-from-start off captures only the launches below
 s.record()
 _lib.check(lib.ccb_bench_kernel(batch._h, args.which, args.iters, obs.data_ptr()))
 t.record()
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print(f"kernel {args.which}: {s.elapsed_time(t) / args.iters:.4f} ms per launch, E={E}")
