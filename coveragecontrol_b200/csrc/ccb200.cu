@@ -365,25 +365,23 @@ struct ccb_env {
 static int pick_rpw(const ccb_env *env, int region_rows, int region_cols, int regions) {
   if (env->vor_rpw_override > 0) return std::max(2, std::min(env->vor_rpw_override, VOR_MAXRPW) & ~1);
   const long tiles_y = (region_cols + VOR_WX * VOR_TW - 1) / (VOR_WX * VOR_TW);
-  for (int rpw = 64; rpw > 4; rpw >>= 1) {
+  for (int rpw = VOR_MAXRPW; rpw > 4; rpw >>= 1) {
     long tiles_x = (region_rows + VOR_WY * rpw - 1) / (VOR_WY * rpw);
     if ((long)regions * tiles_x * tiles_y >= 3L * 148) return rpw;
   }
   return 4;
 }
 
-// sites + candidate lists + per-warp staging (two world chunks and one mask chunk)
-static size_t vor_smem(int R) {
-  size_t base = ((size_t)R * 24 + VOR_WARPS * 32 * sizeof(int) + 15) & ~(size_t)15;
-  return base + (size_t)VOR_WARPS * VOR_STAGE_BYTES_PER_WARP;
-}
-template <bool SINGLE, bool LABELS>
-static int set_vor_smem(size_t bytes) {
+template <int SRC, bool SINGLE, bool LABELS>
+static int run_voronoi(ccb_env *env, const VorArgs &a, dim3 grid) {
   static size_t current = 48 * 1024;
-  if (bytes > current) {
-    CCB_CUDA(cudaFuncSetAttribute(k_voronoi<SINGLE, LABELS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    current = bytes;
+  const size_t smem = vor_smem_bytes(env->d.R);
+  if (smem > current) {
+    CCB_CUDA(cudaFuncSetAttribute(k_voronoi<SRC, SINGLE, LABELS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    current = smem;
   }
+  k_voronoi<SRC, SINGLE, LABELS><<<grid, VOR_THREADS, smem, env->stream>>>(a);
+  CCB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -392,21 +390,13 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
   const EnvDev &d = env->d;
   CCB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * d.E * d.R, env->stream));
   VorArgs a;
-  a.d = d, a.src = src, a.sums = sums, a.labels = labels;
+  a.d = d, a.sums = sums, a.labels = labels;
   a.rpw = pick_rpw(env, d.N, d.N, d.E);
   a.tiles_y = (d.N + VOR_WX * VOR_TW - 1) / (VOR_WX * VOR_TW);
   a.tiles_x = (d.N + VOR_WY * a.rpw - 1) / (VOR_WY * a.rpw);
   dim3 grid(a.tiles_x * a.tiles_y, 1, d.E);
-  const size_t smem = vor_smem(d.R);
-  if (labels) {
-    if (set_vor_smem<false, true>(smem)) return 1;
-    k_voronoi<false, true><<<grid, VOR_THREADS, smem, env->stream>>>(a);
-  } else {
-    if (set_vor_smem<false, false>(smem)) return 1;
-    k_voronoi<false, false><<<grid, VOR_THREADS, smem, env->stream>>>(a);
-  }
-  CCB_LAUNCH_CHECK();
-  return 0;
+  if (src == SRC_WORLD) return labels ? run_voronoi<SRC_WORLD, false, true>(env, a, grid) : run_voronoi<SRC_WORLD, false, false>(env, a, grid);
+  return labels ? run_voronoi<SRC_EXPLORED, false, true>(env, a, grid) : run_voronoi<SRC_EXPLORED, false, false>(env, a, grid);
 }
 
 // per-robot L-window variant (DecentralizedCVT): only the robot's own cell is reduced
@@ -414,15 +404,10 @@ static int launch_voronoi_single(ccb_env *env, double *sums) {
   const EnvDev &d = env->d;
   CCB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * d.E * d.R, env->stream));
   VorArgs a;
-  a.d = d, a.src = SRC_ROBOT, a.sums = sums, a.labels = nullptr;
-  a.rpw = env->vor_rpw_override > 0 ? std::max(2, std::min(env->vor_rpw_override, VOR_MAXRPW) & ~1) : 64;
+  a.d = d, a.sums = sums, a.labels = nullptr;
+  a.rpw = env->vor_rpw_override > 0 ? std::max(2, std::min(env->vor_rpw_override, VOR_MAXRPW) & ~1) : 32;
   a.tiles_x = a.tiles_y = 1;  // one CTA per robot window
-  dim3 grid(1, d.R, d.E);
-  const size_t smem = vor_smem(d.R);
-  if (set_vor_smem<true, false>(smem)) return 1;
-  k_voronoi<true, false><<<grid, VOR_THREADS, smem, env->stream>>>(a);
-  CCB_LAUNCH_CHECK();
-  return 0;
+  return run_voronoi<SRC_ROBOT, true, false>(env, a, dim3(1, d.R, d.E));
 }
 
 static int launch_finalize(ccb_env *env, const double *sums, CellsOut out, int want_polys) {
@@ -468,9 +453,10 @@ static int env_alloc(ccb_env *env) {
   const ccb_params &p = env->p;
   const size_t nn = (size_t)d.N * d.N, er = (size_t)d.E * d.R;
   CCB_CUDA(cudaMalloc(&d.world, sizeof(float) * nn * d.E));
-  CCB_CUDA(cudaMalloc(&d.seen, sizeof(uint32_t) * nn * d.W * d.E));
-  if (p.pUpdateExplorationMap) CCB_CUDA(cudaMalloc(&d.xseen, sizeof(uint32_t) * nn * d.W * d.E));
-  CCB_CUDA(cudaMalloc(&d.sys, nn * d.E));
+  const size_t pw = plane_words(d);
+  CCB_CUDA(cudaMalloc(&d.seenb, sizeof(uint32_t) * pw * er));
+  if (p.pUpdateExplorationMap) CCB_CUDA(cudaMalloc(&d.xseenb, sizeof(uint32_t) * pw * er));
+  CCB_CUDA(cudaMalloc(&d.sysb, sizeof(uint32_t) * pw * 2 * d.E));
   CCB_CUDA(cudaMalloc(&d.pos_g, sizeof(double) * 2 * er));
   CCB_CUDA(cudaMalloc(&d.pos_s, sizeof(double) * 2 * er));
   CCB_CUDA(cudaMalloc(&d.pos_l, sizeof(double) * 2 * er));
@@ -488,9 +474,9 @@ static int env_alloc(ccb_env *env) {
   env->h_pin_bytes = sizeof(double) * std::max<size_t>(er * CCB_MAX_CELL_VERTS * 2, 64);
   CCB_CUDA(cudaMallocHost(&env->h_pin, env->h_pin_bytes));
   CCB_CUDA(cudaMemsetAsync(d.world, 0, sizeof(float) * nn * d.E, env->stream));
-  CCB_CUDA(cudaMemsetAsync(d.seen, 0, sizeof(uint32_t) * nn * d.W * d.E, env->stream));
-  if (d.xseen) CCB_CUDA(cudaMemsetAsync(d.xseen, 0, sizeof(uint32_t) * nn * d.W * d.E, env->stream));
-  CCB_CUDA(cudaMemsetAsync(d.sys, 0, nn * d.E, env->stream));
+  CCB_CUDA(cudaMemsetAsync(d.seenb, 0, sizeof(uint32_t) * pw * er, env->stream));
+  if (d.xseenb) CCB_CUDA(cudaMemsetAsync(d.xseenb, 0, sizeof(uint32_t) * pw * er, env->stream));
+  CCB_CUDA(cudaMemsetAsync(d.sysb, 0, sizeof(uint32_t) * pw * 2 * d.E, env->stream));
   CCB_CUDA(cudaMemsetAsync(d.status, 0, sizeof(int) * d.E, env->stream));
   return 0;
 }
@@ -520,7 +506,7 @@ extern "C" ccb_env *ccb_env_create(const ccb_params *p, int num_envs, int num_ro
   EnvDev &d = env->d;
   d.E = num_envs, d.R = num_robots, d.N = p->pWorldMapSize, d.S = p->pSensorSize, d.L = p->pLocalMapSize;
   d.H = std::max(1, p->pRobotPosHistorySize);
-  d.W = (num_robots + 31) / 32;
+  d.NW = (d.N + 31) / 32;
   d.res = p->pResolution;
   d.fill = p->pRobotMapUseUnknownImportance ? (float)(p->pUnknownImportance * p->pNorm) : 0.f;
   d.use_sensor = p->pUpdateSensorView, d.upd_robot = p->pUpdateRobotMap;
@@ -540,7 +526,7 @@ extern "C" void ccb_env_destroy(ccb_env *env) {
   cudaSetDevice(env->device);
   cudaStreamSynchronize(env->stream);
   EnvDev &d = env->d;
-  cudaFree(d.world), cudaFree(d.seen), cudaFree(d.xseen), cudaFree(d.sys);
+  cudaFree(d.world), cudaFree(d.seenb), cudaFree(d.xseenb), cudaFree(d.sysb);
   cudaFree(d.pos_g), cudaFree(d.pos_s), cudaFree(d.pos_l);
   cudaFree(d.hist), cudaFree(d.hist_start), cudaFree(d.hist_len), cudaFree(d.status);
   cudaFree(env->d_sums);
@@ -592,8 +578,8 @@ extern "C" int ccb_env_set_world_host(ccb_env *env, int e, const float *map) {
 
 static int launch_mark(ccb_env *env, int e, int robot, int mark_robot, int mark_sys) {
   const EnvDev &d = env->d;
-  int chunks = std::max(1, (d.S * d.S + 1023) / 1024);
-  dim3 grid(chunks, robot >= 0 ? 1 : d.R, e >= 0 ? 1 : d.E);
+  const int words = d.S * (d.S / 32 + 2);  // window rows x words a row can touch
+  dim3 grid(std::max(1, std::min(8, (words + 255) / 256)), robot >= 0 ? 1 : d.R, e >= 0 ? 1 : d.E);
   k_mark_windows<<<grid, 256, 0, env->stream>>>(d, e, robot, mark_robot, mark_sys);
   CCB_LAUNCH_CHECK();
   return 0;
@@ -611,11 +597,11 @@ static int stage_to_device(ccb_env *env, const double *host, size_t count, doubl
 extern "C" int ccb_env_reset(ccb_env *env, const double *positions) {
   CCB_CUDA(cudaSetDevice(env->device));
   const EnvDev &d = env->d;
-  const size_t nn = cell_count(d), er = (size_t)d.E * d.R;
+  const size_t pw = plane_words(d), er = (size_t)d.E * d.R;
   if (stage_to_device(env, positions, 2 * er, env->d_stage)) return 1;
-  CCB_CUDA(cudaMemsetAsync(d.seen, 0, sizeof(uint32_t) * nn * d.W * d.E, env->stream));
-  if (d.xseen) CCB_CUDA(cudaMemsetAsync(d.xseen, 0, sizeof(uint32_t) * nn * d.W * d.E, env->stream));
-  CCB_CUDA(cudaMemsetAsync(d.sys, 0, nn * d.E, env->stream));
+  CCB_CUDA(cudaMemsetAsync(d.seenb, 0, sizeof(uint32_t) * pw * er, env->stream));
+  if (d.xseenb) CCB_CUDA(cudaMemsetAsync(d.xseenb, 0, sizeof(uint32_t) * pw * er, env->stream));
+  CCB_CUDA(cudaMemsetAsync(d.sysb, 0, sizeof(uint32_t) * pw * 2 * d.E, env->stream));
   CCB_CUDA(cudaMemsetAsync(d.status, 0, sizeof(int) * d.E, env->stream));
   k_init_positions<<<(int)((er + 255) / 256), 256, 0, env->stream>>>(d, env->d_stage);
   CCB_LAUNCH_CHECK();
@@ -718,23 +704,18 @@ extern "C" int ccb_env_clear_robot_maps(ccb_env *env, int e) {
   if (check_env_index(env, e)) return 1;
   CCB_CUDA(cudaSetDevice(env->device));
   const EnvDev &d = env->d;
-  const size_t nn = cell_count(d);
-  CCB_CUDA(cudaMemsetAsync(d.seen + nn * d.W * e, 0, sizeof(uint32_t) * nn * d.W, env->stream));
+  const size_t pw = plane_words(d);
+  CCB_CUDA(cudaMemsetAsync(robot_plane(d, d.seenb, e, 0), 0, sizeof(uint32_t) * pw * d.R, env->stream));
   // the per-robot exploration maps are NOT cleared by the reference; only the robot-map bits are
   // re-marked here (mark_robot also ORs xseen bits that are already set)
   return launch_mark(env, e, -1, 1, 0);
 }
 
-__global__ void k_clear_explored(EnvDev d, int e) {
-  const size_t nn = cell_count(d);
-  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < nn; c += (size_t)gridDim.x * blockDim.x)
-    d.sys[(size_t)e * nn + c] &= (uint8_t)2;
-}
 extern "C" int ccb_env_clear_explored_idf(ccb_env *env, int e) {
+  // coverage_system.h:405-408: explored_idf_map_ back to zero, the exploration map is kept
   if (check_env_index(env, e)) return 1;
   CCB_CUDA(cudaSetDevice(env->device));
-  k_clear_explored<<<148 * 2, 256, 0, env->stream>>>(env->d, e);
-  CCB_LAUNCH_CHECK();
+  CCB_CUDA(cudaMemsetAsync(sys_plane(env->d, e, 0), 0, sizeof(uint32_t) * plane_words(env->d), env->stream));
   return 0;
 }
 

@@ -50,16 +50,18 @@ constexpr double kEps = 1e-10;      // reference constants.h:48
 constexpr double kLargeEps = 1e-4;  // reference constants.h:50
 
 // ---- device view of a batch of environments ----------------------------------
-// State layout in HBM (per environment e, N = world size, R robots, W = ceil(R/32)):
-//   world  f32 [E][N*N]      importance map, row-major [x][y]
-//   seen   u32 [E][W][N*N]   bit r of word w: robot 32w+r has had the cell in its sensor window
-//                            (robot_map_r = seen ? world : fill, robot_model.h:98-107,180-187)
-//   xseen  u32 [E][W][N*N]   same for the per-robot exploration map (only if pUpdateExplorationMap)
-//   sys    u8  [E][N*N]      bit0: cell is in explored_idf_map_, bit1: exploration_map_ cleared
-//                            (coverage_system.h:104-120)
-// instead of the reference's (3 + 2R) dense N*N float maps.
+// State layout in HBM (per environment e; N = world size, R robots, NW = ceil(N / 32)):
+//   world  f32 [E][N][N]        importance map, row-major [x][y]
+//   seenb  u32 [E][R][N][NW]    one BIT PLANE per robot: bit (y & 31) of word [x][y >> 5] is set once
+//                               the cell has been inside the robot's sensor window
+//                               (robot_map_r = seen ? world : fill, robot_model.h:98-107,180-187)
+//   xseenb u32 [E][R][N][NW]    same for the per-robot exploration map (only if pUpdateExplorationMap)
+//   sysb   u32 [E][2][N][NW]    plane 0: cell is in explored_idf_map_, plane 1: exploration_map_
+//                               cleared (coverage_system.h:104-120)
+// instead of the reference's (3 + 2R) dense N*N float maps: a robot's 256 x 256 local window is
+// 8 KB of mask instead of 256 KB of floats, and world values are only read where a bit is set.
 struct EnvDev {
-  int E, R, N, S, L, H, W;
+  int E, R, N, S, L, H, NW;
   double res;
   float fill;       // pUnknownImportance * pNorm, or 0
   int use_sensor;   // pUpdateSensorView
@@ -69,9 +71,9 @@ struct EnvDev {
   int check_osc;    // pCheckOscillations
   double comm_range, max_speed, dt;
   float *world;
-  uint32_t *seen;
-  uint32_t *xseen;
-  uint8_t *sys;
+  uint32_t *seenb;
+  uint32_t *xseenb;
+  uint32_t *sysb;
   double *pos_g;   // [E][R][2] global current position
   double *pos_s;   // [E][R][2] global start position
   double *pos_l;   // [E][R][2] local current position (robot_model.h:66)
@@ -82,6 +84,18 @@ struct EnvDev {
 };
 
 __host__ __device__ inline size_t cell_count(const EnvDev &d) { return (size_t)d.N * d.N; }
+__host__ __device__ inline size_t plane_words(const EnvDev &d) { return (size_t)d.N * d.NW; }
+__host__ __device__ inline uint32_t *robot_plane(const EnvDev &d, uint32_t *base, int e, int r) {
+  return base + ((size_t)e * d.R + r) * plane_words(d);
+}
+__host__ __device__ inline uint32_t *sys_plane(const EnvDev &d, int e, int which) {
+  return d.sysb + ((size_t)e * 2 + which) * plane_words(d);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t plane_bit(const uint32_t *plane, int NW, int row, int col) {
+  return (__ldg(plane + (size_t)row * NW + (col >> 5)) >> (col & 31)) & 1u;
+}
+#endif
 
 // map_utils.h:51-87 ComputeOffsets, reduced to the clipped window [x0,x1) x [y0,y1) and the
 // unclipped origin (ox, oy) = (index.left, index.bottom).

@@ -13,50 +13,53 @@
 namespace ccb {
 
 // ---- value of the derived maps at one cell -----------------------------------------------------
-__device__ __forceinline__ float robot_map_value(const EnvDev &d, int e, int r, size_t cell) {
-  const size_t nn = cell_count(d);
-  uint32_t w = d.seen[((size_t)e * d.W + (r >> 5)) * nn + cell];
-  if (w & (1u << (r & 31))) return d.use_sensor ? d.world[(size_t)e * nn + cell] : 0.f;
+__device__ __forceinline__ float robot_map_value(const EnvDev &d, int e, int r, int row, int col) {
+  if (plane_bit(robot_plane(d, d.seenb, e, r), d.NW, row, col))
+    return d.use_sensor ? d.world[(size_t)e * cell_count(d) + (size_t)row * d.N + col] : 0.f;
   return d.fill;
 }
-__device__ __forceinline__ float explored_value(const EnvDev &d, int e, size_t cell) {
-  const size_t nn = cell_count(d);
-  if (d.sys[(size_t)e * nn + cell] & 1) return d.use_sensor ? d.world[(size_t)e * nn + cell] : 0.f;
+__device__ __forceinline__ float explored_value(const EnvDev &d, int e, int row, int col) {
+  if (plane_bit(sys_plane(d, e, 0), d.NW, row, col))
+    return d.use_sensor ? d.world[(size_t)e * cell_count(d) + (size_t)row * d.N + col] : 0.f;
   return 0.f;
 }
-__device__ __forceinline__ float exploration_value(const EnvDev &d, int e, size_t cell) {
-  return (d.sys[(size_t)e * cell_count(d) + cell] & 2) ? 0.f : 1.f;
+__device__ __forceinline__ float exploration_value(const EnvDev &d, int e, int row, int col) {
+  return plane_bit(sys_plane(d, e, 1), d.NW, row, col) ? 0.f : 1.f;
 }
 // robot_model.h:137-148: per-robot exploration map (1 = unexplored), all zeros when disabled
-__device__ __forceinline__ float robot_exploration_value(const EnvDev &d, int e, int r, size_t cell) {
+__device__ __forceinline__ float robot_exploration_value(const EnvDev &d, int e, int r, int row, int col) {
   if (!d.upd_expl) return 0.f;
-  uint32_t w = d.xseen[((size_t)e * d.W + (r >> 5)) * cell_count(d) + cell];
-  return (w & (1u << (r & 31))) ? 0.f : 1.f;
+  return plane_bit(robot_plane(d, d.xseenb, e, r), d.NW, row, col) ? 0.f : 1.f;
 }
 
 // ---- sensor window marking ---------------------------------------------------------------------
 // robot_model.h:98-122 (UpdateRobotMap / UpdateExplorationMap) and coverage_system.h:104-118
-// (explored_idf / exploration windows).  grid = (chunks, R, E); env_sel/robot_sel < 0 means all.
+// (explored_idf / exploration windows).  grid = (1, R, E); env_sel/robot_sel >= 0 select one.
+// A thread ORs one word of one window row: S x S cells are S x ceil(S/32 + 1) word updates.
 __global__ void k_mark_windows(EnvDev d, int env_sel, int robot_sel, int mark_robot, int mark_sys) {
   const int e = env_sel >= 0 ? env_sel : blockIdx.z;
   const int r = robot_sel >= 0 ? robot_sel : blockIdx.y;
   const double *p = d.pos_g + ((size_t)e * d.R + r) * 2;
   const Window w = make_window(d.res, p[0], p[1], d.S, d.N);
-  const int wh = w.y1 - w.y0, ww = w.x1 - w.x0;
-  const int total = ww * wh;
-  const size_t nn = cell_count(d);
-  uint32_t *seen = d.seen + ((size_t)e * d.W + (r >> 5)) * nn;
-  uint32_t *xseen = d.xseen ? d.xseen + ((size_t)e * d.W + (r >> 5)) * nn : nullptr;
-  uint8_t *sys = d.sys + (size_t)e * nn;
-  const uint32_t bit = 1u << (r & 31);
+  if (w.x1 <= w.x0 || w.y1 <= w.y0) return;
+  const int w0 = w.y0 >> 5, nwords = ((w.y1 - 1) >> 5) - w0 + 1;
+  const int total = (w.x1 - w.x0) * nwords;
+  uint32_t *seen = robot_plane(d, d.seenb, e, r);
+  uint32_t *xseen = d.xseenb ? robot_plane(d, d.xseenb, e, r) : nullptr;
+  uint32_t *sys0 = sys_plane(d, e, 0), *sys1 = sys_plane(d, e, 1);
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-    int a = t / wh, b = t - a * wh;
-    size_t cell = (size_t)(w.x0 + a) * d.N + (w.y0 + b);
+    const int a = t / nwords, wd = w0 + (t - a * nwords);
+    const int lo = max(w.y0, wd * 32) - wd * 32, hi = min(w.y1, wd * 32 + 32) - wd * 32;  // bits [lo, hi)
+    const uint32_t m = (hi - lo >= 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+    const size_t idx = (size_t)(w.x0 + a) * d.NW + wd;
     if (mark_robot) {
-      if (d.upd_robot) atomicOr(seen + cell, bit);
-      if (d.upd_expl) atomicOr(xseen + cell, bit);
+      if (d.upd_robot) atomicOr(seen + idx, m);
+      if (d.upd_expl) atomicOr(xseen + idx, m);
     }
-    if (mark_sys && d.upd_sys) sys[cell] = 3;  // every writer stores the same value
+    if (mark_sys && d.upd_sys) {
+      atomicOr(sys0 + idx, m);
+      atomicOr(sys1 + idx, m);
+    }
   }
 }
 
@@ -344,13 +347,14 @@ __global__ void k_materialize(EnvDev d, int e, int kind, int robot, float *__res
   const size_t nn = cell_count(d);
   if (kind <= CCB_MAP_ROBOT) {
     for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < nn; c += (size_t)gridDim.x * blockDim.x) {
+      const int row = (int)(c / d.N), col = (int)(c - (size_t)row * d.N);
       float v;
       switch (kind) {
         case CCB_MAP_WORLD: v = d.world[(size_t)e * nn + c]; break;
-        case CCB_MAP_SYSTEM: v = explored_value(d, e, c) - exploration_value(d, e, c); break;  // coverage_system.h:119
-        case CCB_MAP_EXPLORED_IDF: v = explored_value(d, e, c); break;
-        case CCB_MAP_EXPLORATION: v = exploration_value(d, e, c); break;
-        default: v = robot_map_value(d, e, robot, c); break;
+        case CCB_MAP_SYSTEM: v = explored_value(d, e, row, col) - exploration_value(d, e, row, col); break;  // coverage_system.h:119
+        case CCB_MAP_EXPLORED_IDF: v = explored_value(d, e, row, col); break;
+        case CCB_MAP_EXPLORATION: v = exploration_value(d, e, row, col); break;
+        default: v = robot_map_value(d, e, robot, row, col); break;
       }
       out[c] = v;
     }
@@ -364,22 +368,23 @@ __global__ void k_materialize(EnvDev d, int e, int kind, int robot, float *__res
     int gx = w.ox + a, gy = w.oy + b;
     bool in = gx >= 0 && gx < d.N && gy >= 0 && gy < d.N;
     size_t c = in ? (size_t)gx * d.N + gy : 0;
+    if (!in) gx = gy = 0;
     float v;
     switch (kind) {
       case CCB_MAP_SENSOR_VIEW:  // robot_model.h:87-96: zero-padded world window
         v = (in && d.use_sensor) ? d.world[(size_t)e * nn + c] : 0.f;
         break;
       case CCB_MAP_LOCAL:  // robot_model.h:303-313
-        v = in ? robot_map_value(d, e, robot, c) : 0.f;
+        v = in ? robot_map_value(d, e, robot, gx, gy) : 0.f;
         break;
       case CCB_MAP_OBSTACLE:  // robot_model.h:336-345
         v = in ? 0.f : 1.f;
         break;
       case CCB_MAP_ROBOT_EXPLORATION:  // robot_model.h:321-334: -1 padded
-        v = in ? robot_exploration_value(d, e, robot, c) : -1.f;
+        v = in ? robot_exploration_value(d, e, robot, gx, gy) : -1.f;
         break;
       default:  // CCB_MAP_ROBOT_SYSTEM, robot_model.h:183-187: local - local_exploration
-        v = (in ? robot_map_value(d, e, robot, c) : 0.f) - (in ? robot_exploration_value(d, e, robot, c) : -1.f);
+        v = (in ? robot_map_value(d, e, robot, gx, gy) : 0.f) - (in ? robot_exploration_value(d, e, robot, gx, gy) : -1.f);
         break;
     }
     out[t] = v;
@@ -392,10 +397,10 @@ __global__ void k_ratio_sums(EnvDev d, double *__restrict__ out /* [E][3] */) {
   const size_t nn = cell_count(d);
   double cnt = 0, ex = 0, tot = 0;
   for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < nn; c += (size_t)gridDim.x * blockDim.x) {
-    uint8_t s = d.sys[(size_t)e * nn + c];
+    const int row = (int)(c / d.N), col = (int)(c - (size_t)row * d.N);
     float w = d.world[(size_t)e * nn + c];
-    cnt += (s & 2) ? 1.0 : 0.0;
-    ex += (s & 1) ? (d.use_sensor ? (double)w : 0.0) : 0.0;
+    cnt += plane_bit(sys_plane(d, e, 1), d.NW, row, col) ? 1.0 : 0.0;
+    ex += plane_bit(sys_plane(d, e, 0), d.NW, row, col) ? (d.use_sensor ? (double)w : 0.0) : 0.0;
     tot += (double)w;
   }
 #pragma unroll
@@ -425,7 +430,7 @@ __global__ void k_voronoi_features(EnvDev d, double *__restrict__ out) {
   double m = 0, cx = 0, cy = 0, sd = 0, sd2 = 0;
   for (int t = threadIdx.x; t < ww * wh; t += blockDim.x) {
     int a = t / wh, b = t - a * wh;
-    float vf = robot_map_value(d, e, r, (size_t)(w.x0 + a) * d.N + (w.y0 + b));
+    float vf = robot_map_value(d, e, r, w.x0 + a, w.y0 + b);
     if (vf == 0.f) continue;
     double v = vf;
     // voronoi.h:89-95 with origin_shift = -site0 (voronoi.h:171): pt is shifted, then (pt - site)

@@ -26,7 +26,7 @@ __global__ void k_raw_window_maps(EnvDev d, int kind, float *__restrict__ out) {
     const bool in = gx >= 0 && gx < d.N && gy >= 0 && gy < d.N;
     float v;
     if (kind == CCB_MAP_OBSTACLE) v = in ? 0.f : 1.f;
-    else v = in ? robot_map_value(d, e, r, (size_t)gx * d.N + gy) : 0.f;
+    else v = in ? robot_map_value(d, e, r, gx, gy) : 0.f;
     dst[b] = v;
   }
 }
@@ -97,7 +97,7 @@ __global__ void k_cnn_local_obstacle(EnvDev d, int C, ResizeTable tab, float *__
       const int gx = w.ox + a0 + a, gy = w.oy + b;
       const bool in = gx >= 0 && gx < d.N && gy >= 0 && gy < d.N;
       float v;
-      if (pass == 0) v = in ? robot_map_value(d, e, r, (size_t)gx * d.N + gy) : 0.f;
+      if (pass == 0) v = in ? robot_map_value(d, e, r, gx, gy) : 0.f;
       else v = in ? 0.f : 1.f;
       s_in[a * d.L + b] = v;
     }
@@ -123,58 +123,56 @@ __global__ void k_cnn_local_obstacle(EnvDev d, int C, ResizeTable tab, float *__
 
 
 // ---- specialised path for L = 8 C (LPAC: 256 -> 32) ----------------------------------------------
-// One CTA per (robot, env), 8 warps; warp w owns output rows 4w .. 4w+3 (40 window rows, each read
-// once by the warp) and lane = oy.  Rows are loaded one ahead of their use (coalesced, seen word
-// and world value requested together), masked, staged in a padded
-// shared-memory line (one pad word per 8 cells -> the 16-tap reads of the 32 lanes hit 32 different
-// banks) and runs the width pass; the height pass accumulates in a register in ascending row order,
-// the same order torchvision's separable antialias kernel uses.  The obstacle channel needs no map
-// at all: obstacle(a, b) = 1 - in_x(a) in_y(b), so its width pass has only two possible values per
-// output column.  wfull[o][k] = weight of input index 8 o - 4 + k (zero outside torch's tap range).
+// One CTA per (robot, env), 8 warps; warp w owns output rows 4w .. 4w+3, i.e. window rows
+// 32 w - 4 .. 32 w + 35 (40 rows, each used by at most two output rows), and lane = oy.
+// The robot's bit plane says where its local map is non-zero: the warp first stages the 40 x 9 mask
+// words of its rows in shared memory (1.4 KB instead of 40 KB of floats), then only rows with a set
+// bit load world values (8 predicated loads per lane), go through a padded shared-memory line (one
+// pad word per 8 cells -> the 16-tap reads of the 32 lanes hit 32 different banks) and the width
+// pass; the height pass accumulates in registers in ascending row order, the order torchvision's
+// separable antialias kernel uses.  The obstacle channel needs no map at all:
+// obstacle(a, b) = 1 - in_x(a) in_y(b), so its width pass has only two possible values per output
+// column.  wfull[o][k] = weight of input index 8 o - 4 + k (zero outside torch's tap range).
 constexpr int CNN8_THREADS = 256;
 constexpr int CNN8_LINE = 304;
+constexpr int CNN8_ROWS = 40;   // window rows per warp
+constexpr int CNN8_WORDS = 9;   // mask words a 256-cell window row can touch
 // window column b in [-4, 260) -> word of the padded line (one pad word per 8 cells)
 __device__ __forceinline__ int cnn8_pos(int b) { return (b + 8) + ((b + 8) >> 3); }
 
-// Loads this lane's 8 cells (columns 32 k + lane) of window row gx: seen words and world values are
-// requested together (the world load does not wait for the mask), masked afterwards.
-struct Cnn8Row {
-  uint32_t m[8];
-  float w[8];
-  bool in_x;
-};
-__device__ __forceinline__ void cnn8_load(Cnn8Row &r, const uint32_t *__restrict__ seen, const float *__restrict__ world,
-                                          int N, int gx, int oy0, int lane) {
-  r.in_x = gx >= 0 && gx < N;
-  const size_t row_off = (size_t)(r.in_x ? gx : 0) * N;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int gy = oy0 + 32 * k + lane;
-    const bool in = r.in_x && gy >= 0 && gy < N;
-    r.m[k] = in ? __ldg(seen + row_off + gy) : 0u;
-    r.w[k] = in ? __ldg(world + row_off + gy) : 0.f;
-  }
-}
-
-__global__ void __launch_bounds__(CNN8_THREADS)
+__global__ void __launch_bounds__(CNN8_THREADS, 3)
 k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__restrict__ out,
              size_t robot_stride, size_t local_off, size_t obst_off) {
   __shared__ float s_line[CNN8_THREADS / 32][CNN8_LINE];
   __shared__ float s_w[32][16];
+  __shared__ uint32_t s_mask[CNN8_THREADS / 32][CNN8_ROWS * CNN8_WORDS];
   const int r = blockIdx.x, e = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t er = (size_t)e * d.R + r;
   const size_t nn = cell_count(d);
   for (int t = threadIdx.x; t < 32 * 16; t += CNN8_THREADS) s_w[t >> 4][t & 15] = wfull[t];
   float *line = s_line[warp];
+  uint32_t *smask = s_mask[warp];
   if (lane < 4) line[cnn8_pos(lane - 4)] = 0.f;         // taps left of the window
   else if (lane < 8) line[cnn8_pos(252 + lane)] = 0.f;  // taps right of the window (b = 256..259)
-  __syncthreads();
   const double *p = d.pos_g + er * 2;
   const Window w = make_window(d.res, p[0], p[1], 256, d.N);
   const float *world = d.world + (size_t)e * nn;
-  const uint32_t *seen = d.seen + ((size_t)e * d.W + (r >> 5)) * nn;
-  const uint32_t bit = 1u << (r & 31);
+  const uint32_t *plane = robot_plane(d, d.seenb, e, r);
+
+  // This warp owns output rows ox0 .. ox0+3; they need window rows a0 = 8 ox0 - 4 .. 8 ox0 + 35.
+  const int ox0 = warp * 4;
+  const int a0 = 8 * ox0 - 4;
+  // mask words of the 40 rows: word j of a row covers map columns 32 (wbase + j) .. + 31
+  const int wbase = w.oy >> 5;  // arithmetic shift: floor for negative origins
+  for (int t = lane; t < CNN8_ROWS * CNN8_WORDS; t += 32) {
+    const int a = t / CNN8_WORDS, j = t - a * CNN8_WORDS;
+    const int gx = w.ox + a0 + a, wd = wbase + j;
+    uint32_t m = 0u;
+    if (gx >= 0 && gx < d.N && wd >= 0 && wd < d.NW) m = __ldg(plane + (size_t)gx * d.NW + wd);
+    smask[t] = m;
+  }
+  __syncthreads();
 
   // width pass of the obstacle indicator for this lane's output column
   float wc[16];
@@ -189,16 +187,13 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
     oy_out = fmaf(wc[q], in_y ? 0.f : 1.f, oy_out);
   }
 
-  // This warp owns output rows ox0 .. ox0+3; they need window rows a0 = 8 ox0 - 4 .. 8 ox0 + 35.
   // Row a contributes to output row o = ox0 + i with weight s_w[o][a - (8 o - 4)] (two rows at most).
-  const int ox0 = warp * 4;
-  const int a0 = 8 * ox0 - 4;
   float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc_obs[4] = {0.f, 0.f, 0.f, 0.f};
-  Cnn8Row cur, nxt;
-  cnn8_load(cur, seen, world, d.N, w.ox + a0, w.oy, lane);
+  const bool dense = d.fill != 0.f;  // unseen cells carry pUnknownImportance: nothing can be skipped
 #pragma unroll 1
-  for (int t = 0; t < 40; ++t) {
-    if (t + 1 < 40) cnn8_load(nxt, seen, world, d.N, w.ox + a0 + t + 1, w.oy, lane);  // one row ahead
+  for (int t = 0; t < CNN8_ROWS; ++t) {
+    const int gx = w.ox + a0 + t;
+    const bool in_x = gx >= 0 && gx < d.N;
     // weights of this row for the four output rows (zero outside torch's 16-tap range)
     float wr[4];
 #pragma unroll
@@ -207,19 +202,26 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
       wr[i] = (k >= 0 && k < 16) ? s_w[ox0 + i][k] : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc_obs[i] = fmaf(wr[i], cur.in_x ? oy_out : oy_all, acc_obs[i]);
-    bool any = false;
+    for (int i = 0; i < 4; ++i) acc_obs[i] = fmaf(wr[i], in_x ? oy_out : oy_all, acc_obs[i]);
+    if (!in_x) continue;  // zero padding (warp-uniform)
+    const uint32_t mine = lane < CNN8_WORDS ? smask[t * CNN8_WORDS + lane] : 0u;
+    if (!dense && !__any_sync(0xffffffffu, mine != 0u)) continue;  // nothing seen in this row
     float vals[8];
+    bool any = false;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int gy = w.oy + 32 * k + lane;
-      const bool in = cur.in_x && gy >= 0 && gy < d.N;
+      const bool in = gy >= 0 && gy < d.N;
+      const uint32_t word = smask[t * CNN8_WORDS + ((gy >> 5) - wbase)];
       float v = 0.f;
-      if (in) v = (cur.m[k] & bit) ? (d.use_sensor ? cur.w[k] : 0.f) : d.fill;
+      if (in) {
+        if ((word >> (gy & 31)) & 1u) v = d.use_sensor ? __ldg(world + (size_t)gx * d.N + gy) : 0.f;
+        else v = d.fill;
+      }
       vals[k] = v;
       any |= (v != 0.f);
     }
-    if (__any_sync(0xffffffffu, any)) {  // all-zero rows (unseen / outside the world) add nothing
+    if (__any_sync(0xffffffffu, any)) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) line[cnn8_pos(32 * k + lane)] = vals[k];
       __syncwarp();
@@ -230,7 +232,6 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
       for (int i = 0; i < 4; ++i) acc[i] = fmaf(wr[i], tmp, acc[i]);
       __syncwarp();
     }
-    cur = nxt;
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

@@ -7,7 +7,7 @@
 // Semantics: every cell centre ((i+.5)res, (j+.5)res) is labelled with its nearest site; the
 // distance is d2 = dx*dx + dy*dy evaluated in fp64 without FMA contraction and ties go to the
 // lowest site index (the build's stated rule).  The labels are never stored: each
-// warp streams a 64-column x rpw-row region of the map once and accumulates, per label,
+// warp streams a 64-column x <= 64-row region of the map once and accumulates, per label,
 //   S0 = sum v, Sx = sum (i+.5) v, Sy = sum (j+.5) v, S2 = sum ((i+.5)^2 + (j+.5)^2) v
 // in fp64 (cell units; a 24-bit v times a <= 15-bit half-integer is exact in fp64), from which
 // mass, centroid and the objective sum |c - p|^2 v follow in the finalize kernel.
@@ -24,10 +24,15 @@
 //   * three owners: h_k evaluated incrementally in fp32 per cell, with the fp64 rule only when
 //     the best two are closer than a rigorous bound of the fp32 error;
 //   * accumulation is predicated per surviving label: no per-cell atomics, no label runs; one
-//     warp reduction and one set of fp64 atomics per (region, label);
-//   * the region is staged global -> shared with cp.async in double-buffered 4 KB chunks (each lane
-//     copies the 16 bytes per row it later consumes, so a per-thread wait is the only sync):
-//     memory-level parallelism comes from shared memory, not from registers.
+//     warp reduction and one set of fp64 atomics per (region, label).
+//
+// Memory: a lane owns 4 consecutive columns (one 16-byte load per row), lanes 0-15 take one row and
+// lanes 16-31 the next, so one warp load is two full 256-byte row segments.  Loads are issued one
+// group of passes ahead of their use, straight into registers: with ~24 warps resident per SM that
+// keeps > 40 KB in flight per SM, more than HBM latency x bandwidth needs, without any shared-memory
+// staging.  Masked sources (a robot's own map, the explored map) are BIT PLANES (common.cuh): the
+// warp first loads the <= 128 mask words of its region; empty regions end there, empty row pairs
+// are skipped, and world values are only requested for row pairs with a visible cell.
 #pragma once
 
 #include "common.cuh"
@@ -38,21 +43,15 @@ constexpr int VOR_THREADS = 256;
 constexpr int VOR_WARPS = VOR_THREADS / 32;
 constexpr int VOR_WX = 2, VOR_WY = 4;  // warp grid of a CTA tile (global mode)
 constexpr int VOR_TW = 64;       // region width: 16 lanes x 4 cells; lanes 16-31 take the next row
-constexpr int VOR_CH = 8;        // passes (2 rows each) per staging chunk: 8 x 512 B = 4 KB
-constexpr int VOR_NBUF = 3;      // ring of staging chunks per warp (prefetch distance VOR_NBUF - 1)
-constexpr int VOR_MAXRPW = 128;  // rows per warp region
-constexpr int VOR_MAXFAST = 3;   // regions with more competing sites are split, then take the generic path
-constexpr int VOR_MINSPLIT = 4;
-// passes of the streaming loop interleaved for ILP (2 warps per scheduler cannot hide the
-// LDS -> F2F -> DADD chain of a single pass)
-constexpr int VOR_UNROLL = 1;  // do not split below this many rows
+constexpr int VOR_MAXRPW = 64;   // rows per warp region (4 mask words per lane cover 64 rows x 2 words)
+constexpr int VOR_MAXFAST = 2;   // regions with more competing sites are split, then take the generic path
+constexpr int VOR_MINSPLIT = 4;  // do not split below this many rows
 
 enum { SRC_WORLD = 0, SRC_EXPLORED = 1, SRC_ROBOT = 2 };
 
 struct VorArgs {
   EnvDev d;
-  int src;      // SRC_*
-  int rpw;      // rows per warp region (even)
+  int rpw;      // rows per warp region (even, <= VOR_MAXRPW)
   int tiles_x, tiles_y;
   double *sums; // [E][R][4]
   int *labels;  // optional [E][N*N] (global mode only): the label of every cell, for parity tests
@@ -71,174 +70,27 @@ struct Acc6 {
   __device__ __forceinline__ void zero() { c0 = c1 = c2 = c3 = sx = sxx = 0.0; }
 };
 
-// Everything a warp needs to stream one region, by value: nothing here points at the kernel
-// parameter block (taking its address would force a copy of it into local memory).
-struct StripCtx {
-  int N, R;            // map size, robots per environment
+// What every warp of a CTA needs to stream its regions: one copy per CTA in shared memory (fields are
+// read where they are used instead of living in registers across the whole kernel).
+struct VorCta {
+  int N, R, NW;        // map size, robots per environment, mask words per row
   double res;
   float fill;          // value of not-yet-seen cells of a robot map (0 unless pRobotMapUseUnknownImportance)
   int use_sensor;
   const float *world;     // this environment's world map
-  const uint32_t *seen;   // this environment's seen plane holding `robot`'s bit (SRC_ROBOT)
-  const uint8_t *sys;     // this environment's system mask (SRC_EXPLORED)
-  int e, robot;        // robot: mask bit for SRC_ROBOT / output slot in window mode
-  int src;
-  int r0, r1;          // region rows [r0, r1)
-  int c0, c1;          // valid columns [c0, c1)
-  int col_base;        // absolute column of lane 0's first cell (multiple of VOR_TW)
+  const uint32_t *mask;   // bit plane of the selected map (robot plane / explored plane); unused for SRC_WORLD
+  int e, robot;        // robot: output slot in window mode
   const double *s_px, *s_py;  // site coordinates (shared memory)
   const int *s_out;           // site -> output slot
   double *sums;
   int *labels;                // optional label plane of this environment
 };
-
-// ---- staging ----------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void *gmem, int src_bytes) {
-  // src_bytes 0: the 16 destination bytes are zero-filled and global memory is not read
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_addr), "l"(gmem), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async4(unsigned smem_addr, const void *gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_addr), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-
-// ---- bulk (TMA 1-D) copies completing on an mbarrier: one 256-byte row per lane, one warp
-//      instruction per chunk (SASS: UBLKCP + SYNCS) ------------------------------------------------
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  unsigned done = 0;
-  int spins = 0;
-  while (!done) {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!done && ++spins > (1 << 22)) __trap();  // a lost copy must fail loudly, never hang the GPU
-  }
-}
-
-// ---- staging of one chunk ------------------------------------------------------------------------
-// Pass t of a region covers rows r0 + 2t (lanes 0-15) and r0 + 2t + 1 (lanes 16-31); a chunk is up
-// to VOR_CH passes; a lane's slot for pass j of a chunk is wslot[j * 32] (16 bytes).
-// Masked sources (cold helper, scalars by value so that nothing is forced into local memory):
-// stage the visibility masks into the destination slots themselves (a lane only ever touches its own
-// 16 bytes per pass), wait, fold them into the per-pass 4-bit visibility word, then issue the world
-// copies for the passes where something is visible; cells that are not visible are never read.
-__device__ __noinline__ unsigned stage_masked(const uint8_t *sys, const uint32_t *seen, int sh, const float *world,
-                                             const float *any_valid, size_t rstride, unsigned in4, int np,
-                                             int np_lane, bool aligned, bool use_sensor, float4 *wslot) {
-  unsigned vis = 0;
-  const unsigned wsm = (unsigned)__cvta_generic_to_shared(wslot);
-  if (in4) {
-    if (sys) {
-      if (aligned && in4 == 0xfu) {
-#pragma unroll 1
-        for (int j = 0; j < np_lane; ++j) cp_async4(wsm + j * 512, sys + j * rstride);
-        cp_async_commit();
-        cp_async_wait<0>();
-#pragma unroll 1
-        for (int j = 0; j < np_lane; ++j) {
-          const uint32_t q = *reinterpret_cast<const uint32_t *>(wslot + j * 32);
-          vis |= ((q & 1u) | ((q >> 7) & 2u) | ((q >> 14) & 4u) | ((q >> 21) & 8u)) << (4 * j);
-        }
-      } else {
-#pragma unroll 1
-        for (int j = 0; j < np_lane; ++j)
-          for (int i = 0; i < 4; ++i)
-            if (in4 & (1u << i)) vis |= (unsigned)(__ldg(sys + j * rstride + i) & 1u) << (4 * j + i);
-      }
-    } else if (seen) {
-      if (aligned && in4 == 0xfu) {
-#pragma unroll 1
-        for (int j = 0; j < np_lane; ++j) cp_async16(wsm + j * 512, seen + j * rstride, 16);
-        cp_async_commit();
-        cp_async_wait<0>();
-#pragma unroll 1
-        for (int j = 0; j < np_lane; ++j) {
-          const uint4 q = *reinterpret_cast<const uint4 *>(wslot + j * 32);
-          vis |= (((q.x >> sh) & 1u) | (((q.y >> sh) & 1u) << 1) | (((q.z >> sh) & 1u) << 2) |
-                  (((q.w >> sh) & 1u) << 3)) << (4 * j);
-        }
-      } else {
-#pragma unroll 1
-        for (int j = 0; j < np_lane; ++j)
-          for (int i = 0; i < 4; ++i)
-            if (in4 & (1u << i)) vis |= ((__ldg(seen + j * rstride + i) >> sh) & 1u) << (4 * j + i);
-      }
-    } else {  // unmasked source, partially inside the region
-#pragma unroll 1
-      for (int j = 0; j < np_lane; ++j) vis |= in4 << (4 * j);
-    }
-  }
-  if (!use_sensor) {
-#pragma unroll 1
-    for (int j = 0; j < np; ++j) wslot[j * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
-  } else if (aligned && (in4 == 0xfu || in4 == 0)) {
-#pragma unroll 1
-    for (int j = 0; j < np; ++j) {
-      const bool need = ((vis >> (4 * j)) & 0xfu) != 0;
-      cp_async16(wsm + j * 512, need ? (const void *)(world + j * rstride) : (const void *)any_valid, need ? 16 : 0);
-    }
-  } else {
-#pragma unroll 1
-    for (int j = 0; j < np; ++j) {
-      float t[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int i = 0; i < 4; ++i)
-        if ((vis >> (4 * j + i)) & 1u) t[i] = __ldg(world + j * rstride + i);
-      wslot[j * 32] = make_float4(t[0], t[1], t[2], t[3]);
-    }
-  }
-  cp_async_commit();
-  return vis;
-}
-
-// Stage chunk [t0, t0 + np) of the region into this lane's slots and commit ONE cp.async group
-// (not waited for).  Returns the per-pass 4-bit visibility of this lane's cells (pass j -> bits
-// 4j..4j+3): inside the region AND visible in the selected map; 0xffffffff = everything visible.
-__device__ __forceinline__ unsigned stage_chunk(const StripCtx &c, int t0, int np, int lane, float4 *wslot) {
-  const bool aligned = (c.N & 3) == 0;
-  const int col = c.col_base + 4 * (lane & 15);
-  unsigned in4 = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    if (col + i >= c.c0 && col + i < c.c1) in4 |= 1u << i;
-  const int row0 = c.r0 + 2 * t0 + (lane >> 4);
-  const size_t off0 = (size_t)row0 * c.N + col;
-  const float *world = c.world + off0;
-  const size_t rstride = (size_t)2 * c.N;
-  int np_lane = np;  // rows beyond the region (odd row count): nothing visible
-  if (row0 + 2 * (np - 1) >= c.r1) np_lane = np - 1;
-  if (c.src == SRC_WORLD) {
-    const bool full = __all_sync(0xffffffffu, in4 == 0xfu && np_lane == np);
-    if (full && aligned && c.use_sensor) {  // hot path: one 16-byte cp.async per pass
-      const unsigned wsm = (unsigned)__cvta_generic_to_shared(wslot);
-#pragma unroll 1
-      for (int j = 0; j < np; ++j) cp_async16(wsm + j * 512, world + j * rstride, 16);
-      cp_async_commit();
-      return 0xffffffffu;
-    }
-    return stage_masked(nullptr, nullptr, 0, world, c.world, rstride, in4, np, np_lane, aligned, c.use_sensor, wslot);
-  }
-  if (c.src == SRC_EXPLORED)
-    return stage_masked(c.sys + off0, nullptr, 0, world, c.world, rstride, in4, np, np_lane, aligned, c.use_sensor, wslot);
-  return stage_masked(nullptr, c.seen + off0, c.robot & 31, world, c.world, rstride, in4, np, np_lane, aligned,
-                      c.use_sensor, wslot);
-}
+// One warp's region, by value (registers).
+struct StripCtx {
+  int r0, r1;          // region rows [r0, r1), r1 - r0 <= VOR_MAXRPW
+  int c0, c1;          // valid columns [c0, c1)
+  int col_base;        // absolute column of lane 0's first cell (multiple of VOR_TW)
+};
 
 // ---- reduction / emission ---------------------------------------------------------------------
 struct Sum4 {
@@ -264,7 +116,9 @@ __device__ __forceinline__ Sum4 fold_and_reduce(const Acc6 &a, int col) {
 
 __device__ __forceinline__ void emit(double *sums, int e, int R, int slot, double m, double sx, double sy, double s2) {
   if (m == 0.0 && sx == 0.0 && sy == 0.0 && s2 == 0.0) return;
-  double *dst = sums + ((size_t)e * R + slot) * 4;
+  // the pointer comes out of a shared-memory struct: tell the compiler it is global memory, otherwise
+  // every atomicAdd carries a shared-memory CAS-loop alternative
+  double *dst = reinterpret_cast<double *>(__cvta_generic_to_global(sums)) + ((size_t)e * R + slot) * 4;
   atomicAdd(dst + 0, m);
   atomicAdd(dst + 1, sx);
   atomicAdd(dst + 2, sy);
@@ -288,9 +142,9 @@ __device__ __noinline__ int exact_label(const double *s_px, const double *s_py, 
   return best;
 }
 
-// Two owners: returns T in [0, rows], packed with two flags: bit 30 = candidate 1 owns the rows
-// u < T (else the rows u >= T); bit 29 = every cell of the column needs the exact rule.
-// h(u) = hc + u HA is d2_1 - d2_0 at row r0 + u of column `col`.
+// Two owners, careful version (cold): returns T in [0, rows], packed with two flags: bit 30 =
+// candidate 1 owns the rows u < T (else the rows u >= T); bit 29 = every cell of the column needs
+// the exact rule.  h(u) = hc + u HA is d2_1 - d2_0 at row r0 + u of column `col`.
 __device__ __noinline__ int column_threshold(const double *s_px, const double *s_py, int k0, int k1, int r0, int col,
                                              int rows, double hc, double HA, double eps, double res) {
   if (fabs(HA) * rows <= eps) {
@@ -317,268 +171,386 @@ __device__ __noinline__ int column_threshold(const double *s_px, const double *s
   return T | (first1 ? (1 << 30) : 0);
 }
 
-// Fast path: NC (1..VOR_MAXFAST) candidate sites k0 < k1 < k2 can own cells of this region.
-// SINGLE: accumulate only the cells owned by candidate 0 (the robot itself).
-// LABELS: also store the label of every cell (parity tests only; a separate instantiation).
-// bars / phase: this warp's ring mbarriers (shared-memory addresses) and their parity bits.
-template <int NC, bool SINGLE, bool LABELS>
-__device__ __forceinline__ void region_fast(const StripCtx &c, int k0, int k1, int k2, int lane, float4 *wbuf,
-                                            unsigned *svis, unsigned bars, unsigned &phase) {
-  const double res = c.res;
-  const int hp = lane >> 4;
-  const int col = c.col_base + 4 * (lane & 15);
-  const int rows = c.r1 - c.r0;
-  const int npass = (rows + 1) >> 1;
-  const int ksel[3] = {k0, k1, k2};
+// ---- loads ---------------------------------------------------------------------------------------
+// this lane's four cells of one row; aligned = rows are 16-byte aligned (N % 4 == 0) and the four
+// columns are inside the map; otherwise element loads of the columns flagged in inmap
+__device__ __forceinline__ float4 load4(const float *p, bool vec, unsigned inmap) {
+  if (vec) return __ldg(reinterpret_cast<const float4 *>(p));
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (inmap & 1u) v.x = __ldg(p + 0);
+  if (inmap & 2u) v.y = __ldg(p + 1);
+  if (inmap & 4u) v.z = __ldg(p + 2);
+  if (inmap & 8u) v.w = __ldg(p + 3);
+  return v;
+}
 
-  // ---- label plan ---------------------------------------------------------------------------
-  // NC == 2: integer row threshold per column.  NC == 3: fp32 affine differences per cell.
-  int T0 = 0, T1 = 0, T2 = 0, T3 = 0;
-  bool first1 = true;
-  unsigned exact_cols = 0;
-  float h0a = 0.f, haa = 0.f, hba = 0.f, h0b = 0.f, hab = 0.f, hbb = 0.f, margin = 0.f;
-  if (NC >= 2) {
-    const double cx0 = cell_centre(c.r0, res), cy0 = cell_centre(col, res);
-    const double p0x = c.s_px[k0], p0y = c.s_py[k0];
-    const double f0 = d2_exact(cx0, cy0, p0x, p0y);
-    const double p1x = c.s_px[k1], p1y = c.s_py[k1];
-    const double H0 = d2_exact(cx0, cy0, p1x, p1y) - f0;
-    const double HA = 2.0 * res * (p0x - p1x), HB = 2.0 * res * (p0y - p1y);
-    double hmax = fabs(H0) + rows * fabs(HA) + 4.0 * fabs(HB);
-    if (NC == 2) {
-      const double eps = 1e-9 * (1.0 + f0 + hmax);  // >> the fp64 rounding of d2 and of the affine form
-      const int t0 = column_threshold(c.s_px, c.s_py, k0, k1, c.r0, col + 0, rows, H0, HA, eps, res);
-      const int t1 = column_threshold(c.s_px, c.s_py, k0, k1, c.r0, col + 1, rows, H0 + HB, HA, eps, res);
-      const int t2 = column_threshold(c.s_px, c.s_py, k0, k1, c.r0, col + 2, rows, H0 + 2.0 * HB, HA, eps, res);
-      const int t3 = column_threshold(c.s_px, c.s_py, k0, k1, c.r0, col + 3, rows, H0 + 3.0 * HB, HA, eps, res);
-      // the orientation flag depends on the sign of HA only, so it is the same for the 4 columns
-      first1 = (t0 >> 30) & 1;
-      T0 = t0 & 0xffff, T1 = t1 & 0xffff, T2 = t2 & 0xffff, T3 = t3 & 0xffff;
-      exact_cols = ((t0 >> 29) & 1u) | (((t1 >> 29) & 1u) << 1) | (((t2 >> 29) & 1u) << 2) | (((t3 >> 29) & 1u) << 3);
-    } else {
-      const double p2x = c.s_px[k2], p2y = c.s_py[k2];
-      const double G0 = d2_exact(cx0, cy0, p2x, p2y) - f0;
-      const double GA = 2.0 * res * (p0x - p2x), GB = 2.0 * res * (p0y - p2y);
-      hmax = fmax(hmax, fabs(G0) + rows * fabs(GA) + 4.0 * fabs(GB));
-      h0a = (float)H0, haa = (float)HA, hba = (float)HB;
-      h0b = (float)G0, hab = (float)GA, hbb = (float)GB;
-      // fp32 evaluation error of h_k is < 2^-22 hmax; differences of two h's double it
+// mask words of a region: lane l holds, for q = 0..3, the word of row r0 + 16 q + (l >> 1) and
+// half l & 1 (columns col_base + 32 half ..), already clipped to the valid columns [c0, c1).
+struct RegionMask {
+  uint32_t w[4];
+};
+__device__ __forceinline__ bool load_region_mask(const VorCta &g, const StripCtx &c, int lane, RegionMask &m) {
+  const int half = lane & 1;
+  const int wd = (c.col_base >> 5) + half;
+  const int cb = c.col_base + 32 * half;  // column of bit 0
+  // columns [c0, c1) -> bits [lo, hi) of this word
+  const int lo = min(max(c.c0 - cb, 0), 32), hi = min(max(c.c1 - cb, 0), 32);
+  uint32_t keep = 0u;
+  if (hi > lo) keep = ((hi - lo >= 32) ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) << lo;
+  uint32_t any = 0u;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) hmax = fmax(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
-      margin = (float)(hmax * (1.0 / 262144.0));
+  for (int q = 0; q < 4; ++q) {
+    const int row = c.r0 + 16 * q + (lane >> 1);
+    uint32_t v = 0u;
+    if (row < c.r1 && wd < g.NW && keep) v = __ldg(g.mask + (size_t)row * g.NW + wd) & keep;
+    m.w[q] = v;
+    any |= v;
+  }
+  return __any_sync(0xffffffffu, any != 0u);
+}
+
+// ---- label plan of a region (per lane) ---------------------------------------------------------
+// NC == 2: integer row threshold per column.  NC == 3: fp32 affine differences per cell.
+struct LabelPlan {
+  int T0, T1, T2, T3;   // NC == 2: cell (u, j) belongs to candidate 1 iff (first1 ? u : -u) < T_j
+  bool first1;
+  unsigned exact_cols;  // NC == 2: columns whose every cell takes the exact rule
+  float h0a, haa, hba, h0b, hab, hbb, margin;  // NC == 3
+};
+
+template <int NC>
+__device__ __forceinline__ void make_plan(const VorCta &g, int ra, int rows, int col, int k0, int k1, int k2,
+                                          LabelPlan &lp) {
+  lp.T0 = lp.T1 = lp.T2 = lp.T3 = 0, lp.first1 = true, lp.exact_cols = 0;
+  lp.h0a = lp.haa = lp.hba = lp.h0b = lp.hab = lp.hbb = lp.margin = 0.f;
+  if (NC < 2) return;
+  const double res = g.res;
+  const double cx0 = cell_centre(ra, res), cy0 = cell_centre(col, res);
+  const double p0x = g.s_px[k0], p0y = g.s_py[k0];
+  const double f0 = d2_exact(cx0, cy0, p0x, p0y);
+  const double p1x = g.s_px[k1], p1y = g.s_py[k1];
+  const double H0 = d2_exact(cx0, cy0, p1x, p1y) - f0;
+  const double HA = 2.0 * res * (p0x - p1x), HB = 2.0 * res * (p0y - p1y);
+  double hmax = fabs(H0) + rows * fabs(HA) + 4.0 * fabs(HB);
+  if (NC == 2) {
+    const double eps = 1e-9 * (1.0 + f0 + hmax);  // >> the fp64 rounding of d2 and of the affine form
+    int tt[4] = {0, 0, 0, 0};
+    bool careful = fabs(HA) * rows <= eps;
+    if (!careful) {
+      // h(u) = hc + u HA changes sign at x = -hc / HA: one reciprocal per lane, one multiply per
+      // column; a threshold whose neighbouring cells are within eps of the bisector is redone by
+      // the careful version (which applies the exact rule there)
+      lp.first1 = HA > 0.0;
+      const double ninv = -1.0 / HA;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double hc = fma((double)j, HB, H0);
+        const double x = hc * ninv;
+        double tf = lp.first1 ? ceil(x) : floor(x) + 1.0;
+        tf = fmin(fmax(tf, 0.0), (double)rows);
+        tt[j] = (int)tf;
+        const double hl = fma(tf - 1.0, HA, hc), hr = fma(tf, HA, hc);
+        careful |= (fabs(hl) <= eps) | (fabs(hr) <= eps);
+      }
+    }
+    if (careful) {  // rare, per lane
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const int t = column_threshold(g.s_px, g.s_py, k0, k1, ra, col + j, rows, fma((double)j, HB, H0), HA, eps, res);
+        lp.first1 = (t >> 30) & 1;  // depends on the sign of HA only (or is 1 for every flat column)
+        tt[j] = t & 0xffff;
+        lp.exact_cols |= ((t >> 29) & 1u) << j;
+      }
+    }
+    // consume_pass tests (first1 ? u : -u) < Ts_j: u < T_j, resp. u >= T_j <=> -u < 1 - T_j
+    if (!lp.first1) tt[0] = 1 - tt[0], tt[1] = 1 - tt[1], tt[2] = 1 - tt[2], tt[3] = 1 - tt[3];
+    lp.T0 = tt[0], lp.T1 = tt[1], lp.T2 = tt[2], lp.T3 = tt[3];
+  } else {
+    const double p2x = g.s_px[k2], p2y = g.s_py[k2];
+    const double G0 = d2_exact(cx0, cy0, p2x, p2y) - f0;
+    const double GA = 2.0 * res * (p0x - p2x), GB = 2.0 * res * (p0y - p2y);
+    hmax = fmax(hmax, fabs(G0) + rows * fabs(GA) + 4.0 * fabs(GB));
+    lp.h0a = (float)H0, lp.haa = (float)HA, lp.hba = (float)HB;
+    lp.h0b = (float)G0, lp.hab = (float)GA, lp.hbb = (float)GB;
+    // fp32 evaluation error of h_k is < 2^-22 hmax; differences of two h's double it
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) hmax = fmax(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
+    lp.margin = (float)(hmax * (1.0 / 262144.0));
+  }
+}
+
+// 1.0 where p, else 0.0: fma(v, one_if(p), acc) is a predicated fp64 add in one instruction (the
+// C++ `if (p) acc += v` compiles to an add plus two 32-bit selects)
+__device__ __forceinline__ double one_if(bool p) { return __hiloint2double(p ? 0x3ff00000 : 0, 0); }
+
+// One pass (this lane's four cells of row ra + u): labels, optional label store, accumulation.
+//   acc[0]: every cell of the region (SINGLE: every own cell); acc[k], k >= 1: cells of candidate k.
+// No calls in here: a call inside the streaming loop would push the load ring through local memory.
+template <int NC, bool SINGLE, bool LABELS, int NSETS>
+__device__ __forceinline__ void consume_pass(const VorCta &g, const LabelPlan &lp, Acc6 (&acc)[NSETS], float v0, float v1,
+                                             float v2, float v3, int u, double xd, int ra, int rb, int col, unsigned in4,
+                                             int k0, int k1, int k2) {
+  // q1_j / q2_j: cell j belongs to candidate 1 / 2
+  bool q10 = false, q11 = false, q12 = false, q13 = false, q20 = false, q21 = false, q22 = false, q23 = false;
+  if (NC == 2) {
+    // rows u < T_j belong to candidate (first1 ? 1 : 0): with us = +-u and Ts_j = first1 ? T_j : 1 - T_j
+    // (make_plan) that is the single compare us < Ts_j
+    const int us = lp.first1 ? u : -u;
+    q10 = us < lp.T0, q11 = us < lp.T1, q12 = us < lp.T2, q13 = us < lp.T3;
+  } else if (NC == 3) {
+    const float uf = (float)u;
+    const float hr0 = fmaf(uf, lp.haa, lp.h0a), hr1 = fmaf(uf, lp.hab, lp.h0b);
+    bool amb = false;
+    int lab[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float g1 = fmaf((float)i, lp.hba, hr0), g2 = fmaf((float)i, lp.hbb, hr1);
+      float best = 0.f, second;  // winner among {0: 0, 1: g1, 2: g2}
+      int bl = 0;
+      if (g1 < best) second = best, best = g1, bl = 1;
+      else second = g1;
+      if (g2 < best) second = best, best = g2, bl = 2;
+      else second = fminf(second, g2);
+      amb |= (second - best < lp.margin);
+      lab[i] = bl;
+    }
+    if (amb) {  // rare: a cell of this lane's four is within the fp32 error of a bisector -> exact rule
+      const double res = g.res;
+      const double cx = cell_centre(ra + u, res);
+      const double ax = g.s_px[k0], ay = g.s_py[k0], bx = g.s_px[k1], by = g.s_py[k1], ex = g.s_px[k2], ey = g.s_py[k2];
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) {
+        const double cy = cell_centre(col + i, res);
+        int best = 0;
+        double bd = d2_exact(cx, cy, ax, ay);
+        double dd = d2_exact(cx, cy, bx, by);
+        if (dd < bd) bd = dd, best = 1;
+        dd = d2_exact(cx, cy, ex, ey);
+        if (dd < bd) bd = dd, best = 2;
+        lab[0] = (i == 0) ? best : lab[0], lab[1] = (i == 1) ? best : lab[1];
+        lab[2] = (i == 2) ? best : lab[2], lab[3] = (i == 3) ? best : lab[3];
+      }
+    }
+    q10 = lab[0] == 1, q11 = lab[1] == 1, q12 = lab[2] == 1, q13 = lab[3] == 1;
+    q20 = lab[0] == 2, q21 = lab[1] == 2, q22 = lab[2] == 2, q23 = lab[3] == 2;
+  }
+  if (LABELS && !SINGLE) {
+    if (g.labels && ra + u < rb) {
+      int *lp_out = g.labels + (size_t)(ra + u) * g.N + col;
+      if (in4 & 1u) lp_out[0] = g.s_out[q10 ? k1 : (q20 ? k2 : k0)];
+      if (in4 & 2u) lp_out[1] = g.s_out[q11 ? k1 : (q21 ? k2 : k0)];
+      if (in4 & 4u) lp_out[2] = g.s_out[q12 ? k1 : (q22 ? k2 : k0)];
+      if (in4 & 8u) lp_out[3] = g.s_out[q13 ? k1 : (q23 ? k2 : k0)];
     }
   }
+  if (SINGLE && NC > 1) {  // only the robot's own cells (candidate 0) count
+    v0 = (q10 || q20) ? 0.f : v0, v1 = (q11 || q21) ? 0.f : v1;
+    v2 = (q12 || q22) ? 0.f : v2, v3 = (q13 || q23) ? 0.f : v3;
+  }
+  const double dv0 = (double)v0, dv1 = (double)v1, dv2 = (double)v2, dv3 = (double)v3;
+  const double xd2 = xd * xd;
+  {
+    Acc6 &t0 = acc[0];
+    t0.c0 += dv0, t0.c1 += dv1, t0.c2 += dv2, t0.c3 += dv3;
+    const double s = (dv0 + dv1) + (dv2 + dv3);
+    t0.sx = fma(xd, s, t0.sx);
+    t0.sxx = fma(xd2, s, t0.sxx);
+  }
+  if constexpr (!SINGLE && NC >= 2) {
+    Acc6 &a = acc[1];
+    const double b0 = one_if(q10), b1 = one_if(q11), b2 = one_if(q12), b3 = one_if(q13);
+    a.c0 = fma(dv0, b0, a.c0), a.c1 = fma(dv1, b1, a.c1), a.c2 = fma(dv2, b2, a.c2), a.c3 = fma(dv3, b3, a.c3);
+    const double s_k = fma(dv0, b0, dv1 * b1) + fma(dv2, b2, dv3 * b3);
+    a.sx = fma(xd, s_k, a.sx);
+    a.sxx = fma(xd2, s_k, a.sxx);
+  }
+  if constexpr (!SINGLE && NC >= 3) {
+    Acc6 &a = acc[2];
+    const double b0 = one_if(q20), b1 = one_if(q21), b2 = one_if(q22), b3 = one_if(q23);
+    a.c0 = fma(dv0, b0, a.c0), a.c1 = fma(dv1, b1, a.c1), a.c2 = fma(dv2, b2, a.c2), a.c3 = fma(dv3, b3, a.c3);
+    const double s_k = fma(dv0, b0, dv1 * b1) + fma(dv2, b2, dv3 * b3);
+    a.sx = fma(xd, s_k, a.sx);
+    a.sxx = fma(xd2, s_k, a.sxx);
+  }
+}
+
+// Fast path: NC (1..VOR_MAXFAST) candidate sites k0 < k1 < k2 can own cells of rows [ra, rb) of the
+// region (ra - c.r0 even).  SRC: which map is reduced.  SINGLE: accumulate only the cells owned by
+// candidate 0 (the robot itself).  LABELS: also store the label of every cell (parity tests only; a
+// separate instantiation).  Not inlined: every variant gets its own register allocation and the
+// caller's state stays out of the streaming loops.  Returns false without touching anything when the
+// region needs the exact rule for whole columns (a bisector that runs along a column through the
+// cell centres): the caller then takes the generic path.
+template <int NC, int SRC, bool SINGLE, bool LABELS>
+__device__ __noinline__ bool region_fast(const VorCta *gp, StripCtx c, int ra, int rb, int k0, int k1, int k2,
+                                         uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+  const VorCta &g = *gp;
+  constexpr int U = 4;  // load ring of the plain loop: U passes (2 KB per warp) always in flight
+  const int lane = threadIdx.x & 31;
+  const int hp = lane >> 4, c16 = lane & 15;
+  const int col = c.col_base + 4 * c16;
+  const int rows = rb - ra;
+  const int npass = (rows + 1) >> 1;
+  const int N = g.N;
+
+  LabelPlan lp;
+  make_plan<NC>(g, ra, rows, col, k0, k1, k2, lp);
+  if (NC == 2 && __any_sync(0xffffffffu, lp.exact_cols != 0u)) return false;
 
   constexpr int NSETS = SINGLE ? 1 : NC;
   Acc6 acc[NSETS];
 #pragma unroll
   for (int s = 0; s < NSETS; ++s) acc[s].zero();
-  const float fill = (c.src == SRC_ROBOT) ? c.fill : 0.f;
 
-  // ---- stream the region through a ring of VOR_NBUF chunks (prefetch distance VOR_NBUF - 1) ------
-  // Interior regions of the world map (`bulk`): lanes 0-15 each copy one 256-byte row of the chunk
-  // with a bulk copy that completes on the slot's mbarrier -- one warp instruction per chunk.
-  // Otherwise (masked sources, map edges): per-lane cp.async; every iteration commits exactly one
-  // group (possibly empty), so "at most VOR_NBUF - 1 groups pending" means "chunk ch has landed".
-  const int nch = (npass + VOR_CH - 1) / VOR_CH;
-  float4 *wl = wbuf + lane;
-  const bool bulk = c.src == SRC_WORLD && (c.N & 3) == 0 && c.use_sensor && c.c0 == c.col_base &&
-                    c.c1 == c.col_base + VOR_TW && (rows & 1) == 0;
-  const float *brow = c.world + (size_t)(c.r0 + (lane & 15)) * c.N + c.col_base;  // this lane's row of chunk 0
-  const unsigned ring = (unsigned)__cvta_generic_to_shared(wbuf);
+  // ---- which of this lane's cells exist ---------------------------------------------------------
+  unsigned in4 = 0;    // inside the valid columns of the region
+  unsigned inmap = 0;  // inside the map (loadable)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (col + i >= c.c0 && col + i < c.c1) in4 |= 1u << i;
+    if (col + i < N) inmap |= 1u << i;
+  }
+  const bool vec = ((N & 3) == 0) && inmap == 0xfu;
+  const float *wp = g.world + (size_t)(ra + hp) * N + col;  // this lane's row of pass 0
+  double xd = (double)(ra + hp) + 0.5;                      // its row coordinate (cell units)
+
+  // plain: unmasked source, every lane fully inside, even row count, 16-byte rows -> no per-cell
+  // selects, no bounds tests, vector loads one group ahead
+  const bool plain = (SRC == SRC_WORLD) && ((rows & 1) == 0) && __all_sync(0xffffffffu, in4 == 0xfu && vec);
+  if (plain) {
+    const float4 *p4 = reinterpret_cast<const float4 *>(wp);
+    const size_t s4 = (size_t)N >> 1;  // two rows, in float4 units
+    int t = 0;
+    if (npass >= U) {
+      float4 ring[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) ring[k] = __ldg(p4 + k * s4);
+      const float4 *pn = p4 + (size_t)U * s4;  // pass t + U
 #pragma unroll 1
-  for (int b = 0; b < VOR_NBUF - 1; ++b) {
-    if (bulk) {
-      if (b < nch) {
-        const int nr = min(2 * VOR_CH, rows - 2 * VOR_CH * b);
-        if (lane == 0) mbar_expect_tx(bars + 8 * b, nr * 256);
-        __syncwarp();
-        if (lane < nr) bulk_copy_g2s(ring + b * (VOR_CH * 512) + lane * 256, brow + (size_t)(2 * VOR_CH * b) * c.N, 256, bars + 8 * b);
+      for (; t + 2 * U <= npass; t += U) {  // steady state: consume pass t + k, refill its slot with pass t + U + k
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          consume_pass<NC, SINGLE, LABELS, NSETS>(g, lp, acc, ring[k].x, ring[k].y, ring[k].z, ring[k].w, 2 * (t + k) + hp,
+                                                  xd + (double)(2 * k), ra, rb, col, in4, k0, k1, k2);
+          ring[k] = __ldg(pn + k * s4);
+        }
+        xd += 2.0 * U;
+        pn += (size_t)U * s4;
       }
-    } else if (b < nch) {
-      svis[b * 32 + lane] = stage_chunk(c, b * VOR_CH, min(VOR_CH, npass - b * VOR_CH), lane, wl + b * (VOR_CH * 32));
-    } else {
-      cp_async_commit();
+#pragma unroll
+      for (int k = 0; k < U; ++k)  // drain: the ring holds passes t .. t + U - 1
+        consume_pass<NC, SINGLE, LABELS, NSETS>(g, lp, acc, ring[k].x, ring[k].y, ring[k].z, ring[k].w, 2 * (t + k) + hp,
+                                                xd + (double)(2 * k), ra, rb, col, in4, k0, k1, k2);
+      xd += 2.0 * U;
+      t += U;
+    }
+#pragma unroll 1
+    for (; t < npass; ++t) {  // fewer than U passes left
+      const float4 w = __ldg(p4 + (size_t)t * s4);
+      consume_pass<NC, SINGLE, LABELS, NSETS>(g, lp, acc, w.x, w.y, w.z, w.w, 2 * t + hp, xd, ra, rb, col, in4, k0, k1, k2);
+      xd += 2.0;
+    }
+  } else {
+    // general loop: map edges and masked sources.  Per pass: visibility nibble from the region's mask
+    // words (one shuffle), skip the row pair if nothing is visible, load, select, accumulate.
+    const float fill = (SRC == SRC_ROBOT) ? g.fill : 0.f;
+    const bool use_sensor = (SRC == SRC_WORLD) || g.use_sensor;
+    const size_t pstride = (size_t)2 * N;
+    const int um0 = ra - c.r0;  // even: pass t sits in mask word group (um0 + 2 t) >> 4
+#pragma unroll 1
+    for (int t = 0; t < npass; ++t, xd += 2.0) {
+      const int u = 2 * t + hp;
+      const unsigned inside = (ra + u < rb) ? in4 : 0u;
+      unsigned vis = inside;
+      if (SRC != SRC_WORLD) {
+        const int um = um0 + 2 * t;  // + hp stays inside the same 16-row word group
+        const int q = um >> 4;
+        const uint32_t sel = q == 0 ? m0 : (q == 1 ? m1 : (q == 2 ? m2 : m3));
+        const uint32_t word = __shfl_sync(0xffffffffu, sel, (((um + hp) & 15) << 1) | (c16 >> 3));
+        vis &= (word >> (4 * (c16 & 7))) & 0xfu;
+        if (!__any_sync(0xffffffffu, (fill != 0.f ? inside : vis) != 0u)) continue;  // nothing in this row pair
+      }
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vis != 0u && use_sensor) w = load4(wp + (size_t)t * pstride, vec, inmap);
+      float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+      if (SRC == SRC_ROBOT && fill != 0.f) {
+        f0 = (inside & 1u) ? fill : 0.f, f1 = (inside & 2u) ? fill : 0.f;
+        f2 = (inside & 4u) ? fill : 0.f, f3 = (inside & 8u) ? fill : 0.f;
+      }
+      const float v0 = (vis & 1u) ? w.x : f0, v1 = (vis & 2u) ? w.y : f1;
+      const float v2 = (vis & 4u) ? w.z : f2, v3 = (vis & 8u) ? w.w : f3;
+      consume_pass<NC, SINGLE, LABELS, NSETS>(g, lp, acc, v0, v1, v2, v3, u, xd, ra, rb, col, in4, k0, k1, k2);
     }
   }
-#pragma unroll 1
-  for (int ch = 0; ch < nch; ++ch) {
-    const int t0 = ch * VOR_CH;
-    const int np = min(VOR_CH, npass - t0);
-    const int cb = ch % VOR_NBUF;
-    unsigned vis_cur = 0xffffffffu;
-    {
-      const int nx = ch + VOR_NBUF - 1, nb = nx % VOR_NBUF;
-      if (bulk) {
-        if (nx < nch) {
-          const int nr = min(2 * VOR_CH, rows - 2 * VOR_CH * nx);
-          if (lane == 0) mbar_expect_tx(bars + 8 * nb, nr * 256);
-          __syncwarp();
-          if (lane < nr) bulk_copy_g2s(ring + nb * (VOR_CH * 512) + lane * 256, brow + (size_t)(2 * VOR_CH * nx) * c.N, 256, bars + 8 * nb);
-        }
-        mbar_wait(bars + 8 * cb, (phase >> cb) & 1u);
-        phase ^= 1u << cb;
-      } else {
-        if (nx < nch) svis[nb * 32 + lane] = stage_chunk(c, nx * VOR_CH, min(VOR_CH, npass - nx * VOR_CH), lane, wl + nb * (VOR_CH * 32));
-        else cp_async_commit();
-        cp_async_wait<VOR_NBUF - 1>();
-        vis_cur = svis[cb * 32 + lane];
-      }
-    }
-    const float4 *wp = wl + cb * (VOR_CH * 32);
-    const bool plain_cur = bulk || __all_sync(0xffffffffu, vis_cur == 0xffffffffu);
-    int u = 2 * t0 + hp;                         // row of this lane in this pass, relative to r0
-    double xd = (double)(c.r0 + u) + 0.5;
-#pragma unroll(VOR_UNROLL)
-    for (int j = 0; j < np; ++j, u += 2, xd += 2.0) {
-      const float4 w4 = wp[j * 32];
-      float v0 = w4.x, v1 = w4.y, v2 = w4.z, v3 = w4.w;
-      if (!plain_cur) {
-        const unsigned vb = (vis_cur >> (4 * j)) & 0xfu;
-        const bool row_in = c.r0 + u < c.r1;
-        const float f0 = (fill != 0.f && row_in && col + 0 >= c.c0 && col + 0 < c.c1) ? fill : 0.f;
-        const float f1 = (fill != 0.f && row_in && col + 1 >= c.c0 && col + 1 < c.c1) ? fill : 0.f;
-        const float f2 = (fill != 0.f && row_in && col + 2 >= c.c0 && col + 2 < c.c1) ? fill : 0.f;
-        const float f3 = (fill != 0.f && row_in && col + 3 >= c.c0 && col + 3 < c.c1) ? fill : 0.f;
-        v0 = (vb & 1u) ? v0 : f0, v1 = (vb & 2u) ? v1 : f1, v2 = (vb & 4u) ? v2 : f2, v3 = (vb & 8u) ? v3 : f3;
-      }
-      int l0 = 0, l1 = 0, l2 = 0, l3 = 0;
-      if (NC == 2) {
-        l0 = ((u < T0) == first1) ? 1 : 0, l1 = ((u < T1) == first1) ? 1 : 0;
-        l2 = ((u < T2) == first1) ? 1 : 0, l3 = ((u < T3) == first1) ? 1 : 0;
-        if (exact_cols) {
-          if (exact_cols & 1u) l0 = exact_label(c.s_px, c.s_py, k0, k1, k1, 2, c.r0 + u, col + 0, res);
-          if (exact_cols & 2u) l1 = exact_label(c.s_px, c.s_py, k0, k1, k1, 2, c.r0 + u, col + 1, res);
-          if (exact_cols & 4u) l2 = exact_label(c.s_px, c.s_py, k0, k1, k1, 2, c.r0 + u, col + 2, res);
-          if (exact_cols & 8u) l3 = exact_label(c.s_px, c.s_py, k0, k1, k1, 2, c.r0 + u, col + 3, res);
-        }
-      } else if (NC == 3) {
-        const float uf = (float)u;
-        const float hr0 = fmaf(uf, haa, h0a), hr1 = fmaf(uf, hab, h0b);
-        bool amb = false;
-        int lab[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float g1 = fmaf((float)i, hba, hr0), g2 = fmaf((float)i, hbb, hr1);
-          float best = 0.f, second;  // winner among {0: 0, 1: g1, 2: g2}
-          int bl = 0;
-          if (g1 < best) second = best, best = g1, bl = 1;
-          else second = g1;
-          if (g2 < best) second = best, best = g2, bl = 2;
-          else second = fminf(second, g2);
-          amb |= (second - best < margin);
-          lab[i] = bl;
-        }
-        l0 = lab[0], l1 = lab[1], l2 = lab[2], l3 = lab[3];
-        if (amb) {  // rare: a cell of this lane's four is within the fp32 error of a bisector
-          l0 = exact_label(c.s_px, c.s_py, k0, k1, k2, 3, c.r0 + u, col + 0, res);
-          l1 = exact_label(c.s_px, c.s_py, k0, k1, k2, 3, c.r0 + u, col + 1, res);
-          l2 = exact_label(c.s_px, c.s_py, k0, k1, k2, 3, c.r0 + u, col + 2, res);
-          l3 = exact_label(c.s_px, c.s_py, k0, k1, k2, 3, c.r0 + u, col + 3, res);
-        }
-      }
-      if (LABELS && !SINGLE && c.labels && c.r0 + u < c.r1) {
-        int *lp = c.labels + (size_t)(c.r0 + u) * c.N + col;
-        if (col + 0 >= c.c0 && col + 0 < c.c1) lp[0] = c.s_out[ksel[l0]];
-        if (col + 1 >= c.c0 && col + 1 < c.c1) lp[1] = c.s_out[ksel[l1]];
-        if (col + 2 >= c.c0 && col + 2 < c.c1) lp[2] = c.s_out[ksel[l2]];
-        if (col + 3 >= c.c0 && col + 3 < c.c1) lp[3] = c.s_out[ksel[l3]];
-      }
-      const double dv0 = (double)v0, dv1 = (double)v1, dv2 = (double)v2, dv3 = (double)v3;
-      const double xd2 = xd * xd;
-      if (!SINGLE) {
-        Acc6 &t = acc[0];  // set 0: every cell of the region
-        t.c0 += dv0, t.c1 += dv1, t.c2 += dv2, t.c3 += dv3;
-        const double s = (dv0 + dv1) + (dv2 + dv3);
-        t.sx = fma(xd, s, t.sx);
-        t.sxx = fma(xd2, s, t.sxx);
-#pragma unroll
-        for (int k = 1; k < NC; ++k) {
-          Acc6 &a = acc[k];
-          double s_k = 0.0;
-          if (l0 == k) a.c0 += dv0, s_k += dv0;
-          if (l1 == k) a.c1 += dv1, s_k += dv1;
-          if (l2 == k) a.c2 += dv2, s_k += dv2;
-          if (l3 == k) a.c3 += dv3, s_k += dv3;
-          a.sx = fma(xd, s_k, a.sx);
-          a.sxx = fma(xd2, s_k, a.sxx);
-        }
-      } else {
-        Acc6 &a = acc[0];
-        double s_k = 0.0;
-        if (l0 == 0) a.c0 += dv0, s_k += dv0;
-        if (l1 == 0) a.c1 += dv1, s_k += dv1;
-        if (l2 == 0) a.c2 += dv2, s_k += dv2;
-        if (l3 == 0) a.c3 += dv3, s_k += dv3;
-        a.sx = fma(xd, s_k, a.sx);
-        a.sxx = fma(xd2, s_k, a.sxx);
-      }
-    }
-    __syncwarp();  // every lane is done with this slot before it is refilled
-  }
 
+  double *sums = g.sums;
   Sum4 tot = fold_and_reduce(acc[0], col);
   if (SINGLE) {
-    if (lane == 0) emit(c.sums, c.e, c.R, c.robot, tot.m, tot.sx, tot.sy, tot.s2);
-    return;
+    if (lane == 0) emit(sums, g.e, g.R, g.robot, tot.m, tot.sx, tot.sy, tot.s2);
+    return true;
   }
+  const int ksel[3] = {k0, k1, k2};
 #pragma unroll
   for (int k = 1; k < NSETS; ++k) {
     const Sum4 part = fold_and_reduce(acc[k], col);
-    if (lane == 0) emit(c.sums, c.e, c.R, c.s_out[ksel[k]], part.m, part.sx, part.sy, part.s2);
+    if (lane == 0) emit(sums, g.e, g.R, g.s_out[ksel[k]], part.m, part.sx, part.sy, part.s2);
     tot.m -= part.m, tot.sx -= part.sx, tot.sy -= part.sy, tot.s2 -= part.s2;
   }
-  if (lane == 0) emit(c.sums, c.e, c.R, c.s_out[k0], tot.m, tot.sx, tot.sy, tot.s2);
+  if (lane == 0) emit(sums, g.e, g.R, g.s_out[k0], tot.m, tot.sx, tot.sy, tot.s2);
+  return true;
 }
 
-// direct (unstaged) loader for the generic path
-__device__ __forceinline__ void load_cells_direct(const StripCtx &c, int row, int col, float v[4]) {
-  const size_t off = (size_t)row * c.N + col;
-  const float fill = (c.src == SRC_ROBOT) ? c.fill : 0.f;
+// direct loader for the generic path
+template <int SRC>
+__device__ __forceinline__ void load_cells_direct(const VorCta &g, const StripCtx &c, int row, int col, float v[4]) {
+  const size_t off = (size_t)row * g.N + col;
+  const float fill = (SRC == SRC_ROBOT) ? g.fill : 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     v[i] = 0.f;
     if (col + i < c.c0 || col + i >= c.c1) continue;
     bool visible = true;
-    if (c.src == SRC_EXPLORED) visible = __ldg(c.sys + off + i) & 1;
-    else if (c.src == SRC_ROBOT) visible = (__ldg(c.seen + off + i) >> (c.robot & 31)) & 1u;
-    v[i] = visible ? (c.use_sensor ? __ldg(c.world + off + i) : 0.f) : fill;
+    if (SRC != SRC_WORLD) visible = plane_bit(g.mask, g.NW, row, col + i);
+    if (visible) v[i] = (SRC == SRC_WORLD || g.use_sensor) ? __ldg(g.world + off + i) : 0.f;
+    else v[i] = fill;
   }
 }
 
 // Generic path: any number of candidates, fp64 rule per cell, per-lane label runs flushed with
 // global atomics.  Only small regions that still contain more than VOR_MAXFAST owners come here.
-// The context is handed over through shared memory so that its address never escapes in the caller
-// (which would force the hot path's copy into local memory).
-__device__ __noinline__ void region_slow(const StripCtx *cs, const int *cand, int nc, bool single, int lane) {
-  const StripCtx c = *cs;
-  const double res = c.res;
-  const int col = c.col_base + 4 * (lane & 15);
+template <int SRC>
+__device__ __noinline__ void region_slow(const VorCta *gp, int c0, int c1, int col_base, int ra, int rb,
+                                         const int *cand, int nc, bool single, int lane) {
+  const VorCta &g = *gp;
+  StripCtx c;
+  c.r0 = ra, c.r1 = rb, c.c0 = c0, c.c1 = c1, c.col_base = col_base;
+  const double res = g.res;
+  const int col = col_base + 4 * (lane & 15);
   int cur = -1;
   double m = 0, sx = 0, sy = 0, s2 = 0;
-  for (int row = c.r0 + (lane >> 4); row < c.r1; row += 2) {
+  for (int row = ra + (lane >> 4); row < rb; row += 2) {
     float v[4];
-    load_cells_direct(c, row, col, v);
+    load_cells_direct<SRC>(g, c, row, col, v);
     const double cx = cell_centre(row, res);
     const double xd = (double)row + 0.5;
 #pragma unroll 1
     for (int i = 0; i < 4; ++i) {
-      if (v[i] == 0.f && !c.labels) continue;
-      if (col + i < c.c0 || col + i >= c.c1) continue;
+      if (v[i] == 0.f && !g.labels) continue;
+      if (col + i < c0 || col + i >= c1) continue;
       const double cy = cell_centre(col + i, res);
       int best = 0;
-      double bd = d2_exact(cx, cy, c.s_px[cand[0]], c.s_py[cand[0]]);
+      double bd = d2_exact(cx, cy, g.s_px[cand[0]], g.s_py[cand[0]]);
       for (int k = 1; k < nc; ++k) {
-        double dd = d2_exact(cx, cy, c.s_px[cand[k]], c.s_py[cand[k]]);
+        double dd = d2_exact(cx, cy, g.s_px[cand[k]], g.s_py[cand[k]]);
         if (dd < bd) bd = dd, best = k;
       }
       if (single && best != 0) continue;
-      const int slot = single ? c.robot : c.s_out[cand[best]];
-      if (!single && c.labels) c.labels[(size_t)row * c.N + col + i] = slot;
+      const int slot = single ? g.robot : g.s_out[cand[best]];
+      if (!single && g.labels) g.labels[(size_t)row * g.N + col + i] = slot;
       if (v[i] == 0.f) continue;
       if (slot != cur) {
         if (cur >= 0) {
-          emit(c.sums, c.e, c.R, cur, m, sx, sy, s2);
+          emit(g.sums, g.e, g.R, cur, m, sx, sy, s2);
         }
         cur = slot, m = sx = sy = s2 = 0;
       }
@@ -590,12 +562,12 @@ __device__ __noinline__ void region_slow(const StripCtx *cs, const int *cand, in
     }
   }
   if (cur >= 0) {
-    emit(c.sums, c.e, c.R, cur, m, sx, sy, s2);
+    emit(g.sums, g.e, g.R, cur, m, sx, sy, s2);
   }
 }
 
 // Warp-level cull of the candidate list (lane k < nc holds candidate k) for the rectangle
-// rows [r0, r1) x columns [c.c0, c.c1).  Two exact steps, both resting on h_k - h_j being affine:
+// rows [r0, r1) x columns [c0, c1).  Two exact steps, both resting on h_k - h_j being affine:
 //   1. j* = winner at the rectangle's centre cell; drop every k that loses to j* at all 4 corners;
 //   2. among the survivors drop every k that loses to one and the same survivor j at all 4 corners.
 // Returns the ballot of surviving lanes.
@@ -611,11 +583,14 @@ __device__ __noinline__ unsigned cull_rect(double res, int c0, int c1, int r0, i
     int ol = __shfl_xor_sync(0xffffffffu, bl, o);
     if (ob < best || (ob == best && ol < bl)) best = ob, bl = ol;
   }
-  const double cx0 = cell_centre(r0, res), cx1 = cell_centre(r1 - 1, res);
-  const double cy0 = cell_centre(c0, res), cy1 = cell_centre(c1 - 1, res);
+  // corner distances share their one-dimensional squares
+  const double dx0 = __dsub_rn(cell_centre(r0, res), kx), dx1 = __dsub_rn(cell_centre(r1 - 1, res), kx);
+  const double dy0 = __dsub_rn(cell_centre(c0, res), ky), dy1 = __dsub_rn(cell_centre(c1 - 1, res), ky);
+  const double qx0 = __dmul_rn(dx0, dx0), qx1 = __dmul_rn(dx1, dx1);
+  const double qy0 = __dmul_rn(dy0, dy0), qy1 = __dmul_rn(dy1, dy1);
   double f[4];
-  f[0] = d2_exact(cx0, cy0, kx, ky), f[1] = d2_exact(cx1, cy0, kx, ky);
-  f[2] = d2_exact(cx0, cy1, kx, ky), f[3] = d2_exact(cx1, cy1, kx, ky);
+  f[0] = __dadd_rn(qx0, qy0), f[1] = __dadd_rn(qx1, qy0);
+  f[2] = __dadd_rn(qx0, qy1), f[3] = __dadd_rn(qx1, qy1);
   bool keep = false;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -643,33 +618,36 @@ __device__ __noinline__ unsigned cull_rect(double res, int c0, int c1, int r0, i
 }
 
 // One warp, one region.  cand[0..nc) are site indices (ascending) valid for the whole CTA rectangle.
-// The region is culled; if more than VOR_MAXFAST sites can own cells it is split in row halves and
-// each half is culled again (fewer rows, fewer owners) before falling back to the generic path.
-template <bool SINGLE, bool LABELS>
-__device__ __forceinline__ void process_region(StripCtx &c, const int *s_cand, int nc, int *wcand, int lane,
-                                               float4 *wbuf, unsigned *svis, StripCtx *sctx, unsigned bars,
-                                               unsigned &phase) {
+// Masked sources first load the region's mask words: an empty region ends there.  The region is
+// culled; if more than VOR_MAXFAST sites can own cells it is split in row halves and each half is
+// culled again (fewer rows, fewer owners) before falling back to the generic path.
+template <int SRC, bool SINGLE, bool LABELS>
+__device__ __forceinline__ void process_region(const VorCta &g, const StripCtx &c, const int *s_cand, int nc, int *wcand,
+                                               int lane) {
+  RegionMask rm;
+  rm.w[0] = rm.w[1] = rm.w[2] = rm.w[3] = 0u;
+  if (SRC != SRC_WORLD) {
+    const bool any = load_region_mask(g, c, lane, rm);
+    if (!any && !(SRC == SRC_ROBOT && g.fill != 0.f)) return;  // nothing visible: all values are zero
+  }
   if (nc > 32) {
-    if (lane == 0) *sctx = c;
-    __syncwarp();
-    region_slow(sctx, s_cand, nc, SINGLE, lane);
+    region_slow<SRC>(&g, c.c0, c.c1, c.col_base, c.r0, c.r1, s_cand, nc, SINGLE, lane);
     return;
   }
   const bool has = lane < nc;
   const int my_site = has ? s_cand[lane] : 0;
-  const double kx = c.s_px[my_site], ky = c.s_py[my_site];
-  const int region_r1 = c.r1;
+  const double kx = g.s_px[my_site], ky = g.s_py[my_site];
   int r = c.r0;
-  int len = region_r1 - r;
-  while (r < region_r1) {
-    if (len > region_r1 - r) len = region_r1 - r;
-    const unsigned wmask = cull_rect(c.res, c.c0, c.c1, r, r + len, has, kx, ky, lane);
+  int len = c.r1 - r;
+  while (r < c.r1) {
+    if (len > c.r1 - r) len = c.r1 - r;
+    const unsigned wmask = cull_rect(g.res, c.c0, c.c1, r, r + len, has, kx, ky, lane);
     const int wnc = __popc(wmask);
     if (wnc > VOR_MAXFAST && len > VOR_MINSPLIT) {
       len = ((len >> 1) + 1) & ~1;  // split (keep it even): retry the first half
       continue;
     }
-    c.r0 = r, c.r1 = r + len;
+    const int ra = r, rb = r + len;
     r += len;
     if (SINGLE && !(wmask & 1u)) continue;  // the robot owns no cell of these rows
     int ksite[VOR_MAXFAST];
@@ -685,39 +663,39 @@ __device__ __forceinline__ void process_region(StripCtx &c, const int *s_cand, i
         }
       }
     }
+    bool done = false;
     if (wnc == 1) {
-      region_fast<1, SINGLE, LABELS>(c, ksite[0], ksite[0], ksite[0], lane, wbuf, svis, bars, phase);
+      done = region_fast<1, SRC, SINGLE, LABELS>(&g, c, ra, rb, ksite[0], ksite[0], ksite[0], rm.w[0], rm.w[1], rm.w[2], rm.w[3]);
     } else if (wnc == 2) {
-      region_fast<2, SINGLE, LABELS>(c, ksite[0], ksite[1], ksite[1], lane, wbuf, svis, bars, phase);
-    } else if (wnc == 3) {
-      region_fast<3, SINGLE, LABELS>(c, ksite[0], ksite[1], ksite[2], lane, wbuf, svis, bars, phase);
-    } else {
+      done = region_fast<2, SRC, SINGLE, LABELS>(&g, c, ra, rb, ksite[0], ksite[1], ksite[1], rm.w[0], rm.w[1], rm.w[2], rm.w[3]);
+    } else if (VOR_MAXFAST >= 3 && wnc == 3) {
+      if constexpr (VOR_MAXFAST >= 3)
+        done = region_fast<3, SRC, SINGLE, LABELS>(&g, c, ra, rb, ksite[0], ksite[1], ksite[VOR_MAXFAST - 1], rm.w[0], rm.w[1], rm.w[2], rm.w[3]);
+    }
+    if (!done) {
       const bool keep = (wmask >> lane) & 1u;
       if (keep) wcand[__popc(wmask & ((1u << lane) - 1u))] = my_site;
-      if (lane == 0) *sctx = c;
       __syncwarp();
-      region_slow(sctx, wcand, wnc, SINGLE, lane);
+      region_slow<SRC>(&g, c.c0, c.c1, c.col_base, ra, rb, wcand, wnc, SINGLE, lane);
     }
     __syncwarp();
   }
 }
 
-// dynamic shared memory: double px[R], py[R]; int out[R]; int cand[R]; int wcand[VOR_WARPS][32];
-// then (16-byte aligned) per warp: a ring of VOR_NBUF world chunks [VOR_CH][32] float4 and the
-// per-lane visibility word of each ring slot.
+// dynamic shared memory: double px[R], py[R]; int out[R]; int cand[R]; int wcand[VOR_WARPS][32].
 //
 // SINGLE = false (global): grid = (tiles_x * tiles_y, 1, E); a CTA owns a (2 x 64)-column x
 //   (4 x rpw)-row tile of the map, one region per warp; every robot is a site and every site's sums
-//   are produced.
+//   are produced.  SRC = SRC_WORLD or SRC_EXPLORED.
 // SINGLE = true (window):  grid = (1, R, E); a CTA owns one robot's whole clipped L-window and its
 //   warps loop over the window's regions; sites = the robot + its neighbours within communication
-//   range (decentralized_cvt.h:100-120), only the robot's own cell is reduced.
-constexpr size_t VOR_STAGE_BYTES_PER_WARP =
-    (size_t)VOR_NBUF * VOR_CH * 32 * 16 + VOR_NBUF * 32 * sizeof(unsigned) + 128 + 32;  // ring, vis, ctx, mbarriers
-static_assert(sizeof(StripCtx) <= 128, "per-warp context slot too small");
+//   range (decentralized_cvt.h:100-120), only the robot's own cell is reduced.  SRC = SRC_ROBOT.
+__host__ __device__ inline size_t vor_smem_bytes(int R) {
+  return ((size_t)R * 24 + VOR_WARPS * 32 * sizeof(int) + 15) & ~(size_t)15;
+}
 
-template <bool SINGLE, bool LABELS>
-__global__ void __launch_bounds__(VOR_THREADS) k_voronoi(VorArgs a) {
+template <int SRC, bool SINGLE, bool LABELS>
+__global__ void __launch_bounds__(VOR_THREADS, 3) k_voronoi(VorArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const EnvDev &d = a.d;
   const int ns_cap = d.R;
@@ -726,24 +704,13 @@ __global__ void __launch_bounds__(VOR_THREADS) k_voronoi(VorArgs a) {
   int *s_out = reinterpret_cast<int *>(s_py + ns_cap);
   int *s_cand = s_out + ns_cap;
   int *s_wcand = s_cand + ns_cap;
-  const size_t stage_off = ((size_t)ns_cap * 24 + VOR_WARPS * 32 * sizeof(int) + 15) & ~(size_t)15;
+  __shared__ VorCta s_cta;
   __shared__ int s_ns, s_nc;
   __shared__ double s_best[VOR_WARPS];
   __shared__ int s_besti[VOR_WARPS];
   __shared__ int s_woff[VOR_WARPS + 1];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float4 *wbuf = reinterpret_cast<float4 *>(smem_raw + stage_off + warp * VOR_STAGE_BYTES_PER_WARP);
-  unsigned *svis = reinterpret_cast<unsigned *>(wbuf + VOR_NBUF * VOR_CH * 32);
-  StripCtx *sctx = reinterpret_cast<StripCtx *>(svis + VOR_NBUF * 32);
-  const unsigned bars = (unsigned)__cvta_generic_to_shared(reinterpret_cast<unsigned char *>(sctx) + 128);
-  unsigned phase = 0;
-  if (lane == 0) {
-    for (int b = 0; b < VOR_NBUF; ++b) mbar_init(bars + 8 * b, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-  }
-  __syncwarp();
   const int e = blockIdx.z;
   const int robot = SINGLE ? blockIdx.y : 0;
   const double res = d.res;
@@ -854,26 +821,32 @@ __global__ void __launch_bounds__(VOR_THREADS) k_voronoi(VorArgs a) {
   if (SINGLE && s_cand[0] != 0) return;  // the robot itself was culled: it owns no cell here
 
   // ---- regions: (row chunk, 64-column tile) pairs dealt round-robin to the warps ---------------
-  StripCtx c;
-  const size_t nn = (size_t)d.N * d.N;
-  c.N = d.N, c.R = d.R, c.res = d.res, c.fill = d.fill, c.use_sensor = d.use_sensor;
-  c.world = d.world + (size_t)e * nn;
-  c.seen = d.seen + ((size_t)e * d.W + (robot >> 5)) * nn;
-  c.sys = d.sys + (size_t)e * nn;
-  c.e = e, c.robot = robot, c.src = a.src;
-  c.s_px = s_px, c.s_py = s_py, c.s_out = s_out, c.sums = a.sums;
-  c.labels = (LABELS && a.labels && !SINGLE) ? a.labels + (size_t)e * nn : nullptr;
-  const int nrow = (tr1 - tr0 + a.rpw - 1) / a.rpw;
+  if (tid == 0) {
+    const size_t nn = (size_t)d.N * d.N, pw = (size_t)d.N * d.NW;
+    VorCta &g = s_cta;
+    g.N = d.N, g.R = d.R, g.NW = d.NW, g.res = d.res, g.fill = d.fill, g.use_sensor = d.use_sensor;
+    g.world = d.world + (size_t)e * nn;
+    g.mask = nullptr;
+    if (SRC == SRC_ROBOT) g.mask = d.seenb + ((size_t)e * d.R + robot) * pw;
+    if (SRC == SRC_EXPLORED) g.mask = d.sysb + ((size_t)e * 2) * pw;
+    g.e = e, g.robot = robot;
+    g.s_px = s_px, g.s_py = s_py, g.s_out = s_out, g.sums = a.sums;
+    g.labels = (LABELS && a.labels && !SINGLE) ? a.labels + (size_t)e * nn : nullptr;
+  }
+  __syncthreads();
+  const int rpw = a.rpw;
+  const int nrow = (tr1 - tr0 + rpw - 1) / rpw;
   const int ncol = (tc1 - 1 - col_base0) / VOR_TW + 1;
   for (int sidx = warp; sidx < nrow * ncol; sidx += VOR_WARPS) {
     const int ri = sidx / ncol, ci = sidx - ri * ncol;
-    c.r0 = tr0 + ri * a.rpw;
-    c.r1 = min(c.r0 + a.rpw, tr1);
+    StripCtx c;
+    c.r0 = tr0 + ri * rpw;
+    c.r1 = min(c.r0 + rpw, tr1);
     c.col_base = col_base0 + ci * VOR_TW;
     c.c0 = max(c.col_base, tc0);
     c.c1 = min(c.col_base + VOR_TW, tc1);
     if (c.c0 >= c.c1) continue;
-    process_region<SINGLE, LABELS>(c, s_cand, nc, s_wcand + warp * 32, lane, wbuf, svis, sctx, bars, phase);
+    process_region<SRC, SINGLE, LABELS>(s_cta, c, s_cand, nc, s_wcand + warp * 32, lane);
     __syncwarp();
   }
 }
