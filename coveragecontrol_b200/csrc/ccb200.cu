@@ -452,7 +452,8 @@ static int env_alloc(ccb_env *env) {
   EnvDev &d = env->d;
   const ccb_params &p = env->p;
   const size_t nn = (size_t)d.N * d.N, er = (size_t)d.E * d.R;
-  CCB_CUDA(cudaMalloc(&d.world, sizeof(float) * nn * d.E));
+  // VOR_PAD_ROWS rows of padding: the Voronoi load ring prefetches past the last region of the last map
+  CCB_CUDA(cudaMalloc(&d.world, sizeof(float) * (nn * d.E + (size_t)VOR_PAD_ROWS * d.N)));
   const size_t pw = plane_words(d);
   CCB_CUDA(cudaMalloc(&d.seenb, sizeof(uint32_t) * pw * er));
   if (p.pUpdateExplorationMap) CCB_CUDA(cudaMalloc(&d.xseenb, sizeof(uint32_t) * pw * er));
@@ -473,7 +474,7 @@ static int env_alloc(ccb_env *env) {
   CCB_CUDA(cudaMalloc(&env->d_scratch, sizeof(float) * std::max(nn, (size_t)d.L * d.L)));
   env->h_pin_bytes = sizeof(double) * std::max<size_t>(er * CCB_MAX_CELL_VERTS * 2, 64);
   CCB_CUDA(cudaMallocHost(&env->h_pin, env->h_pin_bytes));
-  CCB_CUDA(cudaMemsetAsync(d.world, 0, sizeof(float) * nn * d.E, env->stream));
+  CCB_CUDA(cudaMemsetAsync(d.world, 0, sizeof(float) * (nn * d.E + (size_t)VOR_PAD_ROWS * d.N), env->stream));
   CCB_CUDA(cudaMemsetAsync(d.seenb, 0, sizeof(uint32_t) * pw * er, env->stream));
   if (d.xseenb) CCB_CUDA(cudaMemsetAsync(d.xseenb, 0, sizeof(uint32_t) * pw * er, env->stream));
   CCB_CUDA(cudaMemsetAsync(d.sysb, 0, sizeof(uint32_t) * pw * 2 * d.E, env->stream));

@@ -44,8 +44,9 @@ constexpr int VOR_WARPS = VOR_THREADS / 32;
 constexpr int VOR_WX = 2, VOR_WY = 4;  // warp grid of a CTA tile (global mode)
 constexpr int VOR_TW = 64;       // region width: 16 lanes x 4 cells; lanes 16-31 take the next row
 constexpr int VOR_MAXRPW = 64;   // rows per warp region (4 mask words per lane cover 64 rows x 2 words)
-constexpr int VOR_MAXFAST = 2;   // regions with more competing sites are split, then take the generic path
+constexpr int VOR_MAXFAST = 4;   // regions with more competing sites are split, then take the generic path
 constexpr int VOR_MINSPLIT = 4;  // do not split below this many rows
+constexpr int VOR_PAD_ROWS = 8;  // rows the streaming loop may read past a region (see stream_region)
 
 enum { SRC_WORLD = 0, SRC_EXPLORED = 1, SRC_ROBOT = 2 };
 
@@ -125,52 +126,6 @@ __device__ __forceinline__ void emit(double *sums, int e, int R, int slot, doubl
   atomicAdd(dst + 3, s2);
 }
 
-// the stated rule among nc <= 3 candidates k0 < k1 < k2 (site indices): index 0..nc-1 of the winner
-__device__ __noinline__ int exact_label(const double *s_px, const double *s_py, int k0, int k1, int k2, int nc, int row,
-                                        int col, double res) {
-  const double cx = cell_centre(row, res), cy = cell_centre(col, res);
-  int best = 0;
-  double bd = d2_exact(cx, cy, s_px[k0], s_py[k0]);
-  if (nc > 1) {
-    double dd = d2_exact(cx, cy, s_px[k1], s_py[k1]);
-    if (dd < bd) bd = dd, best = 1;
-  }
-  if (nc > 2) {
-    double dd = d2_exact(cx, cy, s_px[k2], s_py[k2]);
-    if (dd < bd) bd = dd, best = 2;
-  }
-  return best;
-}
-
-// Two owners, careful version (cold): returns T in [0, rows], packed with two flags: bit 30 =
-// candidate 1 owns the rows u < T (else the rows u >= T); bit 29 = every cell of the column needs
-// the exact rule.  h(u) = hc + u HA is d2_1 - d2_0 at row r0 + u of column `col`.
-__device__ __noinline__ int column_threshold(const double *s_px, const double *s_py, int k0, int k1, int r0, int col,
-                                             int rows, double hc, double HA, double eps, double res) {
-  if (fabs(HA) * rows <= eps) {
-    // the bisector runs (numerically) along this column: one label for all rows, unless it is
-    // within rounding of the cell centres, in which case every cell takes the exact rule
-    int T = (hc < 0.0) ? rows : 0;
-    return T | (1 << 30) | ((fabs(hc) <= eps) ? (1 << 29) : 0);
-  }
-  const double x = -hc / HA;       // h(x) = 0
-  const bool first1 = HA > 0.0;    // h increasing: candidate 1 (h < 0) owns the rows below x
-  double tf = first1 ? ceil(x) : floor(x) + 1.0;
-  tf = fmin(fmax(tf, 0.0), (double)rows);
-  int T = (int)tf;
-  // re-check the two cells next to the threshold with the exact rule when they are within
-  // rounding of the bisector (|h| <= eps there)
-  if (T - 1 >= 0 && T - 1 < rows && fabs(hc + (T - 1) * HA) <= eps) {
-    const int lab = exact_label(s_px, s_py, k0, k1, k1, 2, r0 + T - 1, col, res);
-    if ((lab == 1) != first1) T -= 1;
-  }
-  if (T >= 0 && T < rows && fabs(hc + T * HA) <= eps) {
-    const int lab = exact_label(s_px, s_py, k0, k1, k1, 2, r0 + T, col, res);
-    if ((lab == 1) == first1) T += 1;
-  }
-  return T | (first1 ? (1 << 30) : 0);
-}
-
 // ---- loads ---------------------------------------------------------------------------------------
 // this lane's four cells of one row; aligned = rows are 16-byte aligned (N % 4 == 0) and the four
 // columns are inside the map; otherwise element loads of the columns flagged in inmap
@@ -209,200 +164,184 @@ __device__ __forceinline__ bool load_region_mask(const VorCta &g, const StripCtx
   return __any_sync(0xffffffffu, any != 0u);
 }
 
-// ---- label plan of a region (per lane) ---------------------------------------------------------
-// NC == 2: integer row threshold per column.  NC == 3: fp32 affine differences per cell.
-struct LabelPlan {
-  int T0, T1, T2, T3;   // NC == 2: cell (u, j) belongs to candidate 1 iff (first1 ? u : -u) < T_j
-  bool first1;
-  unsigned exact_cols;  // NC == 2: columns whose every cell takes the exact rule
-  float h0a, haa, hba, h0b, hab, hbb, margin;  // NC == 3
+// ---- consumers: what a warp does with the four cells a lane holds in one pass ----------------------
+// One owner: every cell of the region belongs to site k0.  Column sums c0..c3 plus the row-weighted
+// sums of the lane's row total: 11 fp64 operations per pass.
+template <bool LABELS>
+struct ConsOne {
+  Acc6 a;
+  int k0_slot;  // output slot written as label
+  __device__ __forceinline__ void init() { a.zero(); }
+  __device__ __forceinline__ void pass(const VorCta &g, float v0, float v1, float v2, float v3, int u, double xd, int ra,
+                                       int rb, int col, unsigned in4) {
+    if (LABELS) {
+      if (g.labels && ra + u < rb) {
+        int *lp_out = g.labels + (size_t)(ra + u) * g.N + col;
+        if (in4 & 1u) lp_out[0] = k0_slot;
+        if (in4 & 2u) lp_out[1] = k0_slot;
+        if (in4 & 4u) lp_out[2] = k0_slot;
+        if (in4 & 8u) lp_out[3] = k0_slot;
+      }
+    }
+    const double dv0 = (double)v0, dv1 = (double)v1, dv2 = (double)v2, dv3 = (double)v3;
+    a.c0 += dv0, a.c1 += dv1, a.c2 += dv2, a.c3 += dv3;
+    const double s = (dv0 + dv1) + (dv2 + dv3);
+    a.sx = fma(xd, s, a.sx);
+    a.sxx = fma(xd * xd, s, a.sxx);
+  }
 };
 
-template <int NC>
-__device__ __forceinline__ void make_plan(const VorCta &g, int ra, int rows, int col, int k0, int k1, int k2,
-                                          LabelPlan &lp) {
-  lp.T0 = lp.T1 = lp.T2 = lp.T3 = 0, lp.first1 = true, lp.exact_cols = 0;
-  lp.h0a = lp.haa = lp.hba = lp.h0b = lp.hab = lp.hbb = lp.margin = 0.f;
-  if (NC < 2) return;
-  const double res = g.res;
-  const double cx0 = cell_centre(ra, res), cy0 = cell_centre(col, res);
-  const double p0x = g.s_px[k0], p0y = g.s_py[k0];
-  const double f0 = d2_exact(cx0, cy0, p0x, p0y);
-  const double p1x = g.s_px[k1], p1y = g.s_py[k1];
-  const double H0 = d2_exact(cx0, cy0, p1x, p1y) - f0;
-  const double HA = 2.0 * res * (p0x - p1x), HB = 2.0 * res * (p0y - p1y);
-  double hmax = fabs(H0) + rows * fabs(HA) + 4.0 * fabs(HB);
-  if (NC == 2) {
-    const double eps = 1e-9 * (1.0 + f0 + hmax);  // >> the fp64 rounding of d2 and of the affine form
-    int tt[4] = {0, 0, 0, 0};
-    bool careful = fabs(HA) * rows <= eps;
-    if (!careful) {
-      // h(u) = hc + u HA changes sign at x = -hc / HA: one reciprocal per lane, one multiply per
-      // column; a threshold whose neighbouring cells are within eps of the bisector is redone by
-      // the careful version (which applies the exact rule there)
-      lp.first1 = HA > 0.0;
-      const double ninv = -1.0 / HA;
+// NCAND (2..4) owners: per-cell labels from the fp32 affine differences h_i = d2_i - d2_0 (the exact
+// fp64 rule for a lane's four cells whenever the best two are within a rigorous bound of the fp32
+// error), and per-COLUMN running sums (v, x v, x^2 v) that are flushed into the lane's per-owner
+// accumulators (shared memory, private to the lane) whenever the column's label changes -- a Voronoi
+// cell is convex, so a column changes owner at most NCAND - 1 times per region.  14 fp64 operations
+// per pass whatever the number of owners; no thresholds, no per-owner predicated sets.  The cold part
+// (exact labels, flushes) runs through a shared-memory scratch copy of the running sums with rolled
+// loops, so that it costs little code and no registers in the streaming loop.
+constexpr int RUNS_LANE_DOUBLES = VOR_MAXFAST * 4 + 12;  // per lane: owner accumulators + scratch
+
+template <int NCAND, bool SINGLE, bool LABELS>
+struct ConsRuns {
+  float h0[NCAND - 1], ha[NCAND - 1], hb[NCAND - 1];  // h_i at (row ra, this lane's first column); per row; per column
+  float margin;
+  unsigned cur;                    // owner (candidate index) of each column's running sums, one per byte; 0xff: none yet
+  double c[4], cx[4], cxx[4];
+  double *lacc;                    // this lane's shared memory: lacc[(owner * 4 + v) * 32], v = m, sx, sy, s2;
+                                   // scratch at lacc[(VOR_MAXFAST * 4 + k) * 32], k = 0..11
+  const int *cand;                 // NCAND site indices, ascending (shared memory)
+
+  __device__ __forceinline__ void init(const VorCta &g, int ra, int rows, int col, const int *cand_, double *lacc_) {
+    cand = cand_, lacc = lacc_;
+    const double res = g.res;
+    const double cx0 = cell_centre(ra, res), cy0 = cell_centre(col, res);
+    const int k0 = cand[0];
+    const double p0x = g.s_px[k0], p0y = g.s_py[k0];
+    const double f0 = d2_exact(cx0, cy0, p0x, p0y);
+    double hmax = 0.0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double hc = fma((double)j, HB, H0);
-        const double x = hc * ninv;
-        double tf = lp.first1 ? ceil(x) : floor(x) + 1.0;
-        tf = fmin(fmax(tf, 0.0), (double)rows);
-        tt[j] = (int)tf;
-        const double hl = fma(tf - 1.0, HA, hc), hr = fma(tf, HA, hc);
-        careful |= (fabs(hl) <= eps) | (fabs(hr) <= eps);
-      }
+    for (int i = 1; i < NCAND; ++i) {
+      const int k = cand[i];
+      const double px = g.s_px[k], py = g.s_py[k];
+      const double H0 = d2_exact(cx0, cy0, px, py) - f0;
+      const double HA = 2.0 * res * (p0x - px), HB = 2.0 * res * (p0y - py);
+      hmax = fmax(hmax, fabs(H0) + rows * fabs(HA) + 4.0 * fabs(HB));
+      h0[i - 1] = (float)H0, ha[i - 1] = (float)HA, hb[i - 1] = (float)HB;
     }
-    if (careful) {  // rare, per lane
-#pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        const int t = column_threshold(g.s_px, g.s_py, k0, k1, ra, col + j, rows, fma((double)j, HB, H0), HA, eps, res);
-        lp.first1 = (t >> 30) & 1;  // depends on the sign of HA only (or is 1 for every flat column)
-        tt[j] = t & 0xffff;
-        lp.exact_cols |= ((t >> 29) & 1u) << j;
-      }
-    }
-    // consume_pass tests (first1 ? u : -u) < Ts_j: u < T_j, resp. u >= T_j <=> -u < 1 - T_j
-    if (!lp.first1) tt[0] = 1 - tt[0], tt[1] = 1 - tt[1], tt[2] = 1 - tt[2], tt[3] = 1 - tt[3];
-    lp.T0 = tt[0], lp.T1 = tt[1], lp.T2 = tt[2], lp.T3 = tt[3];
-  } else {
-    const double p2x = g.s_px[k2], p2y = g.s_py[k2];
-    const double G0 = d2_exact(cx0, cy0, p2x, p2y) - f0;
-    const double GA = 2.0 * res * (p0x - p2x), GB = 2.0 * res * (p0y - p2y);
-    hmax = fmax(hmax, fabs(G0) + rows * fabs(GA) + 4.0 * fabs(GB));
-    lp.h0a = (float)H0, lp.haa = (float)HA, lp.hba = (float)HB;
-    lp.h0b = (float)G0, lp.hab = (float)GA, lp.hbb = (float)GB;
-    // fp32 evaluation error of h_k is < 2^-22 hmax; differences of two h's double it
+    // fp32 evaluation error of h_i is < 2^-21 hmax; differences of two h's double it
+    margin = (float)(hmax * (1.0 / 262144.0));
+    cur = 0xffffffffu;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) hmax = fmax(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
-    lp.margin = (float)(hmax * (1.0 / 262144.0));
+    for (int j = 0; j < 4; ++j) c[j] = cx[j] = cxx[j] = 0.0;
+#pragma unroll
+    for (int t = 0; t < NCAND * 4; ++t) lacc[t * 32] = 0.0;
   }
-}
 
-// 1.0 where p, else 0.0: fma(v, one_if(p), acc) is a predicated fp64 add in one instruction (the
-// C++ `if (p) acc += v` compiles to an add plus two 32-bit selects)
-__device__ __forceinline__ double one_if(bool p) { return __hiloint2double(p ? 0x3ff00000 : 0, 0); }
-
-// One pass (this lane's four cells of row ra + u): labels, optional label store, accumulation.
-//   acc[0]: every cell of the region (SINGLE: every own cell); acc[k], k >= 1: cells of candidate k.
-// No calls in here: a call inside the streaming loop would push the load ring through local memory.
-template <int NC, bool SINGLE, bool LABELS, int NSETS>
-__device__ __forceinline__ void consume_pass(const VorCta &g, const LabelPlan &lp, Acc6 (&acc)[NSETS], float v0, float v1,
-                                             float v2, float v3, int u, double xd, int ra, int rb, int col, unsigned in4,
-                                             int k0, int k1, int k2) {
-  // q1_j / q2_j: cell j belongs to candidate 1 / 2
-  bool q10 = false, q11 = false, q12 = false, q13 = false, q20 = false, q21 = false, q22 = false, q23 = false;
-  if (NC == 2) {
-    // rows u < T_j belong to candidate (first1 ? 1 : 0): with us = +-u and Ts_j = first1 ? T_j : 1 - T_j
-    // (make_plan) that is the single compare us < Ts_j
-    const int us = lp.first1 ? u : -u;
-    q10 = us < lp.T0, q11 = us < lp.T1, q12 = us < lp.T2, q13 = us < lp.T3;
-  } else if (NC == 3) {
-    const float uf = (float)u;
-    const float hr0 = fmaf(uf, lp.haa, lp.h0a), hr1 = fmaf(uf, lp.hab, lp.h0b);
-    bool amb = false;
-    int lab[4];
+  // Cold: exact labels where the fp32 ones are in doubt, then every column whose label changed moves
+  // its running sums to the previous owner's accumulators.  Returns the final labels.
+  __device__ __forceinline__ unsigned change(const VorCta &g, unsigned labs, bool amb, int row, int col) {
+    double *scr = lacc + VOR_MAXFAST * 4 * 32;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float g1 = fmaf((float)i, lp.hba, hr0), g2 = fmaf((float)i, lp.hbb, hr1);
-      float best = 0.f, second;  // winner among {0: 0, 1: g1, 2: g2}
-      int bl = 0;
-      if (g1 < best) second = best, best = g1, bl = 1;
-      else second = g1;
-      if (g2 < best) second = best, best = g2, bl = 2;
-      else second = fminf(second, g2);
-      amb |= (second - best < lp.margin);
-      lab[i] = bl;
-    }
-    if (amb) {  // rare: a cell of this lane's four is within the fp32 error of a bisector -> exact rule
+    for (int j = 0; j < 4; ++j) scr[j * 32] = c[j], scr[(4 + j) * 32] = cx[j], scr[(8 + j) * 32] = cxx[j];
+    if (amb) {
       const double res = g.res;
-      const double cx = cell_centre(ra + u, res);
-      const double ax = g.s_px[k0], ay = g.s_py[k0], bx = g.s_px[k1], by = g.s_py[k1], ex = g.s_px[k2], ey = g.s_py[k2];
+      const double cxr = cell_centre(row, res);
+      labs = 0;
 #pragma unroll 1
-      for (int i = 0; i < 4; ++i) {
-        const double cy = cell_centre(col + i, res);
+      for (int j = 0; j < 4; ++j) {
+        const double cy = cell_centre(col + j, res);
         int best = 0;
-        double bd = d2_exact(cx, cy, ax, ay);
-        double dd = d2_exact(cx, cy, bx, by);
-        if (dd < bd) bd = dd, best = 1;
-        dd = d2_exact(cx, cy, ex, ey);
-        if (dd < bd) bd = dd, best = 2;
-        lab[0] = (i == 0) ? best : lab[0], lab[1] = (i == 1) ? best : lab[1];
-        lab[2] = (i == 2) ? best : lab[2], lab[3] = (i == 3) ? best : lab[3];
+        double bd = d2_exact(cxr, cy, g.s_px[cand[0]], g.s_py[cand[0]]);
+#pragma unroll 1
+        for (int i = 1; i < NCAND; ++i) {
+          const double dd = d2_exact(cxr, cy, g.s_px[cand[i]], g.s_py[cand[i]]);
+          if (dd < bd) bd = dd, best = i;
+        }
+        labs |= (unsigned)best << (8 * j);
       }
     }
-    q10 = lab[0] == 1, q11 = lab[1] == 1, q12 = lab[2] == 1, q13 = lab[3] == 1;
-    q20 = lab[0] == 2, q21 = lab[1] == 2, q22 = lab[2] == 2, q23 = lab[3] == 2;
-  }
-  if (LABELS && !SINGLE) {
-    if (g.labels && ra + u < rb) {
-      int *lp_out = g.labels + (size_t)(ra + u) * g.N + col;
-      if (in4 & 1u) lp_out[0] = g.s_out[q10 ? k1 : (q20 ? k2 : k0)];
-      if (in4 & 2u) lp_out[1] = g.s_out[q11 ? k1 : (q21 ? k2 : k0)];
-      if (in4 & 4u) lp_out[2] = g.s_out[q12 ? k1 : (q22 ? k2 : k0)];
-      if (in4 & 8u) lp_out[3] = g.s_out[q13 ? k1 : (q23 ? k2 : k0)];
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const unsigned lj = (labs >> (8 * j)) & 0xffu, cj = (cur >> (8 * j)) & 0xffu;
+      if (lj == cj) continue;
+      if (cj != 0xffu && (!SINGLE || cj == 0u)) {
+        const double y = (double)(col + j) + 0.5;
+        const double cc = scr[j * 32];
+        double *dst = lacc + cj * 128;
+        dst[0] += cc;
+        dst[32] += scr[(4 + j) * 32];
+        dst[64] = fma(y, cc, dst[64]);
+        dst[96] += fma(y * y, cc, scr[(8 + j) * 32]);
+      }
+      scr[j * 32] = 0.0, scr[(4 + j) * 32] = 0.0, scr[(8 + j) * 32] = 0.0;
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] = scr[j * 32], cx[j] = scr[(4 + j) * 32], cxx[j] = scr[(8 + j) * 32];
+    cur = labs;
+    return labs;
   }
-  if (SINGLE && NC > 1) {  // only the robot's own cells (candidate 0) count
-    v0 = (q10 || q20) ? 0.f : v0, v1 = (q11 || q21) ? 0.f : v1;
-    v2 = (q12 || q22) ? 0.f : v2, v3 = (q13 || q23) ? 0.f : v3;
-  }
-  const double dv0 = (double)v0, dv1 = (double)v1, dv2 = (double)v2, dv3 = (double)v3;
-  const double xd2 = xd * xd;
-  {
-    Acc6 &t0 = acc[0];
-    t0.c0 += dv0, t0.c1 += dv1, t0.c2 += dv2, t0.c3 += dv3;
-    const double s = (dv0 + dv1) + (dv2 + dv3);
-    t0.sx = fma(xd, s, t0.sx);
-    t0.sxx = fma(xd2, s, t0.sxx);
-  }
-  if constexpr (!SINGLE && NC >= 2) {
-    Acc6 &a = acc[1];
-    const double b0 = one_if(q10), b1 = one_if(q11), b2 = one_if(q12), b3 = one_if(q13);
-    a.c0 = fma(dv0, b0, a.c0), a.c1 = fma(dv1, b1, a.c1), a.c2 = fma(dv2, b2, a.c2), a.c3 = fma(dv3, b3, a.c3);
-    const double s_k = fma(dv0, b0, dv1 * b1) + fma(dv2, b2, dv3 * b3);
-    a.sx = fma(xd, s_k, a.sx);
-    a.sxx = fma(xd2, s_k, a.sxx);
-  }
-  if constexpr (!SINGLE && NC >= 3) {
-    Acc6 &a = acc[2];
-    const double b0 = one_if(q20), b1 = one_if(q21), b2 = one_if(q22), b3 = one_if(q23);
-    a.c0 = fma(dv0, b0, a.c0), a.c1 = fma(dv1, b1, a.c1), a.c2 = fma(dv2, b2, a.c2), a.c3 = fma(dv3, b3, a.c3);
-    const double s_k = fma(dv0, b0, dv1 * b1) + fma(dv2, b2, dv3 * b3);
-    a.sx = fma(xd, s_k, a.sx);
-    a.sxx = fma(xd2, s_k, a.sxx);
-  }
-}
 
-// Fast path: NC (1..VOR_MAXFAST) candidate sites k0 < k1 < k2 can own cells of rows [ra, rb) of the
-// region (ra - c.r0 even).  SRC: which map is reduced.  SINGLE: accumulate only the cells owned by
-// candidate 0 (the robot itself).  LABELS: also store the label of every cell (parity tests only; a
-// separate instantiation).  Not inlined: every variant gets its own register allocation and the
-// caller's state stays out of the streaming loops.  Returns false without touching anything when the
-// region needs the exact rule for whole columns (a bisector that runs along a column through the
-// cell centres): the caller then takes the generic path.
-template <int NC, int SRC, bool SINGLE, bool LABELS>
-__device__ __noinline__ bool region_fast(const VorCta *gp, StripCtx c, int ra, int rb, int k0, int k1, int k2,
-                                         uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
-  const VorCta &g = *gp;
-  constexpr int U = 4;  // load ring of the plain loop: U passes (2 KB per warp) always in flight
+  __device__ __forceinline__ void pass(const VorCta &g, float v0, float v1, float v2, float v3, int u, double xd, int ra,
+                                       int rb, int col, unsigned in4) {
+    unsigned labs = 0;
+    bool amb = false;
+    {
+      const float uf = (float)u;
+      float hr[NCAND - 1];
+#pragma unroll
+      for (int i = 0; i < NCAND - 1; ++i) hr[i] = fmaf(uf, ha[i], h0[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float best = 0.f, second = 3.0e38f;  // candidate 0 has h = 0
+        unsigned bl = 0;
+#pragma unroll
+        for (int i = 0; i < NCAND - 1; ++i) {
+          const float gi = fmaf((float)j, hb[i], hr[i]);
+          if (gi < best) second = best, best = gi, bl = (unsigned)(i + 1) << (8 * j);
+          else second = fminf(second, gi);
+        }
+        amb |= (second - best < margin);
+        labs |= bl;
+      }
+    }
+    if (amb | (labs != cur)) labs = change(g, labs, amb, ra + u, col);
+    if (LABELS && !SINGLE) {
+      if (g.labels && ra + u < rb) {
+        int *lp_out = g.labels + (size_t)(ra + u) * g.N + col;
+        if (in4 & 1u) lp_out[0] = g.s_out[cand[labs & 0xffu]];
+        if (in4 & 2u) lp_out[1] = g.s_out[cand[(labs >> 8) & 0xffu]];
+        if (in4 & 4u) lp_out[2] = g.s_out[cand[(labs >> 16) & 0xffu]];
+        if (in4 & 8u) lp_out[3] = g.s_out[cand[labs >> 24]];
+      }
+    }
+    const double dv0 = (double)v0, dv1 = (double)v1, dv2 = (double)v2, dv3 = (double)v3;
+    const double xd2 = xd * xd;
+    c[0] += dv0, c[1] += dv1, c[2] += dv2, c[3] += dv3;
+    cx[0] = fma(xd, dv0, cx[0]), cx[1] = fma(xd, dv1, cx[1]), cx[2] = fma(xd, dv2, cx[2]), cx[3] = fma(xd, dv3, cx[3]);
+    cxx[0] = fma(xd2, dv0, cxx[0]), cxx[1] = fma(xd2, dv1, cxx[1]);
+    cxx[2] = fma(xd2, dv2, cxx[2]), cxx[3] = fma(xd2, dv3, cxx[3]);
+  }
+
+  __device__ __forceinline__ void finish(const VorCta &g, int col) { change(g, 0xfefefefeu, false, 0, col); }
+};
+
+// ---- the streaming skeleton ------------------------------------------------------------------------
+// Rows [ra, rb) of region c (ra - c.r0 even) go through cons.pass() once, a lane holding four
+// consecutive cells of one row per pass (lanes 16-31: the next row).
+//   plain (unmasked source, every lane inside the map and the region, even row count, 16-byte rows):
+//     vector loads through a register ring that keeps U passes (2 KB per warp) in flight;
+//   otherwise: per pass the visibility nibble comes from the region's mask words (one shuffle), row
+//     pairs with nothing visible are skipped, cells are selected against the mask.
+template <int SRC, class Cons>
+__device__ __forceinline__ void stream_region(const VorCta &g, const StripCtx &c, int ra, int rb, uint32_t m0, uint32_t m1,
+                                              uint32_t m2, uint32_t m3, Cons &cons) {
+  constexpr int U = 4;
   const int lane = threadIdx.x & 31;
   const int hp = lane >> 4, c16 = lane & 15;
   const int col = c.col_base + 4 * c16;
   const int rows = rb - ra;
   const int npass = (rows + 1) >> 1;
   const int N = g.N;
-
-  LabelPlan lp;
-  make_plan<NC>(g, ra, rows, col, k0, k1, k2, lp);
-  if (NC == 2 && __any_sync(0xffffffffu, lp.exact_cols != 0u)) return false;
-
-  constexpr int NSETS = SINGLE ? 1 : NC;
-  Acc6 acc[NSETS];
-#pragma unroll
-  for (int s = 0; s < NSETS; ++s) acc[s].zero();
-
-  // ---- which of this lane's cells exist ---------------------------------------------------------
   unsigned in4 = 0;    // inside the valid columns of the region
   unsigned inmap = 0;  // inside the map (loadable)
 #pragma unroll
@@ -413,9 +352,6 @@ __device__ __noinline__ bool region_fast(const VorCta *gp, StripCtx c, int ra, i
   const bool vec = ((N & 3) == 0) && inmap == 0xfu;
   const float *wp = g.world + (size_t)(ra + hp) * N + col;  // this lane's row of pass 0
   double xd = (double)(ra + hp) + 0.5;                      // its row coordinate (cell units)
-
-  // plain: unmasked source, every lane fully inside, even row count, 16-byte rows -> no per-cell
-  // selects, no bounds tests, vector loads one group ahead
   const bool plain = (SRC == SRC_WORLD) && ((rows & 1) == 0) && __all_sync(0xffffffffu, in4 == 0xfu && vec);
   if (plain) {
     const float4 *p4 = reinterpret_cast<const float4 *>(wp);
@@ -426,33 +362,26 @@ __device__ __noinline__ bool region_fast(const VorCta *gp, StripCtx c, int ra, i
 #pragma unroll
       for (int k = 0; k < U; ++k) ring[k] = __ldg(p4 + k * s4);
       const float4 *pn = p4 + (size_t)U * s4;  // pass t + U
+      // consume pass t + k, refill its slot with pass t + U + k.  The last iteration refills with rows
+      // past the region (never used): the world buffer is padded by VOR_PAD_ROWS rows for that.
 #pragma unroll 1
-      for (; t + 2 * U <= npass; t += U) {  // steady state: consume pass t + k, refill its slot with pass t + U + k
+      for (; t + U <= npass; t += U) {
 #pragma unroll
         for (int k = 0; k < U; ++k) {
-          consume_pass<NC, SINGLE, LABELS, NSETS>(g, lp, acc, ring[k].x, ring[k].y, ring[k].z, ring[k].w, 2 * (t + k) + hp,
-                                                  xd + (double)(2 * k), ra, rb, col, in4, k0, k1, k2);
+          cons.pass(g, ring[k].x, ring[k].y, ring[k].z, ring[k].w, 2 * (t + k) + hp, xd + (double)(2 * k), ra, rb, col, in4);
           ring[k] = __ldg(pn + k * s4);
         }
         xd += 2.0 * U;
         pn += (size_t)U * s4;
       }
-#pragma unroll
-      for (int k = 0; k < U; ++k)  // drain: the ring holds passes t .. t + U - 1
-        consume_pass<NC, SINGLE, LABELS, NSETS>(g, lp, acc, ring[k].x, ring[k].y, ring[k].z, ring[k].w, 2 * (t + k) + hp,
-                                                xd + (double)(2 * k), ra, rb, col, in4, k0, k1, k2);
-      xd += 2.0 * U;
-      t += U;
     }
 #pragma unroll 1
     for (; t < npass; ++t) {  // fewer than U passes left
       const float4 w = __ldg(p4 + (size_t)t * s4);
-      consume_pass<NC, SINGLE, LABELS, NSETS>(g, lp, acc, w.x, w.y, w.z, w.w, 2 * t + hp, xd, ra, rb, col, in4, k0, k1, k2);
+      cons.pass(g, w.x, w.y, w.z, w.w, 2 * t + hp, xd, ra, rb, col, in4);
       xd += 2.0;
     }
   } else {
-    // general loop: map edges and masked sources.  Per pass: visibility nibble from the region's mask
-    // words (one shuffle), skip the row pair if nothing is visible, load, select, accumulate.
     const float fill = (SRC == SRC_ROBOT) ? g.fill : 0.f;
     const bool use_sensor = (SRC == SRC_WORLD) || g.use_sensor;
     const size_t pstride = (size_t)2 * N;
@@ -479,25 +408,52 @@ __device__ __noinline__ bool region_fast(const VorCta *gp, StripCtx c, int ra, i
       }
       const float v0 = (vis & 1u) ? w.x : f0, v1 = (vis & 2u) ? w.y : f1;
       const float v2 = (vis & 4u) ? w.z : f2, v3 = (vis & 8u) ? w.w : f3;
-      consume_pass<NC, SINGLE, LABELS, NSETS>(g, lp, acc, v0, v1, v2, v3, u, xd, ra, rb, col, in4, k0, k1, k2);
+      cons.pass(g, v0, v1, v2, v3, u, xd, ra, rb, col, in4);
     }
   }
+}
 
-  double *sums = g.sums;
-  Sum4 tot = fold_and_reduce(acc[0], col);
-  if (SINGLE) {
-    if (lane == 0) emit(sums, g.e, g.R, g.robot, tot.m, tot.sx, tot.sy, tot.s2);
-    return true;
-  }
-  const int ksel[3] = {k0, k1, k2};
+// One owner (site index k0).  Not inlined: every streaming variant gets its own register allocation and
+// the caller's state stays out of the streaming loops.
+template <int SRC, bool SINGLE, bool LABELS>
+__device__ __noinline__ void region_one(const VorCta *gp, StripCtx c, int ra, int rb, int k0, uint32_t m0, uint32_t m1,
+                                        uint32_t m2, uint32_t m3) {
+  const VorCta &g = *gp;
+  const int lane = threadIdx.x & 31;
+  ConsOne<LABELS && !SINGLE> cons;
+  cons.init();
+  cons.k0_slot = g.s_out[k0];
+  stream_region<SRC>(g, c, ra, rb, m0, m1, m2, m3, cons);
+  const Sum4 tot = fold_and_reduce(cons.a, c.col_base + 4 * (lane & 15));
+  if (lane == 0) emit(g.sums, g.e, g.R, SINGLE ? g.robot : g.s_out[k0], tot.m, tot.sx, tot.sy, tot.s2);
+}
+
+// NCAND owners; cand (shared memory) holds their site indices, ascending.  lacc: this warp's per-lane
+// owner accumulators (shared memory, [4][4][32] doubles).
+template <int NCAND, int SRC, bool SINGLE, bool LABELS>
+__device__ __noinline__ void region_runs(const VorCta *gp, StripCtx c, int ra, int rb, const int *cand, double *lacc,
+                                         uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+  const VorCta &g = *gp;
+  const int lane = threadIdx.x & 31;
+  const int col = c.col_base + 4 * (lane & 15);
+  ConsRuns<NCAND, SINGLE, LABELS> cons;
+  cons.init(g, ra, rb - ra, col, cand, lacc + lane);
+  stream_region<SRC>(g, c, ra, rb, m0, m1, m2, m3, cons);
+  cons.finish(g, col);
+  // per owner: reduce the lanes' accumulators and emit
+#pragma unroll 1
+  for (int s = 0; s < (SINGLE ? 1 : NCAND); ++s) {
+    const double *src = lacc + lane + s * 128;
+    double m = src[0], sx = src[32], sy = src[64], s2 = src[96];
 #pragma unroll
-  for (int k = 1; k < NSETS; ++k) {
-    const Sum4 part = fold_and_reduce(acc[k], col);
-    if (lane == 0) emit(sums, g.e, g.R, g.s_out[ksel[k]], part.m, part.sx, part.sy, part.s2);
-    tot.m -= part.m, tot.sx -= part.sx, tot.sy -= part.sy, tot.s2 -= part.s2;
+    for (int o = 16; o > 0; o >>= 1) {
+      m += __shfl_xor_sync(0xffffffffu, m, o);
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) emit(g.sums, g.e, g.R, SINGLE ? g.robot : g.s_out[cand[s]], m, sx, sy, s2);
   }
-  if (lane == 0) emit(sums, g.e, g.R, g.s_out[k0], tot.m, tot.sx, tot.sy, tot.s2);
-  return true;
 }
 
 // direct loader for the generic path
@@ -623,7 +579,7 @@ __device__ __noinline__ unsigned cull_rect(double res, int c0, int c1, int r0, i
 // culled again (fewer rows, fewer owners) before falling back to the generic path.
 template <int SRC, bool SINGLE, bool LABELS>
 __device__ __forceinline__ void process_region(const VorCta &g, const StripCtx &c, const int *s_cand, int nc, int *wcand,
-                                               int lane) {
+                                               double *lacc, int lane) {
   RegionMask rm;
   rm.w[0] = rm.w[1] = rm.w[2] = rm.w[3] = 0u;
   if (SRC != SRC_WORLD) {
@@ -650,39 +606,29 @@ __device__ __forceinline__ void process_region(const VorCta &g, const StripCtx &
     const int ra = r, rb = r + len;
     r += len;
     if (SINGLE && !(wmask & 1u)) continue;  // the robot owns no cell of these rows
-    int ksite[VOR_MAXFAST];
+    // the surviving candidates, ascending, into this warp's list
     {
-      unsigned mm = wmask;
-#pragma unroll
-      for (int q = 0; q < VOR_MAXFAST; ++q) {
-        ksite[q] = 0;
-        if (mm) {
-          int src_lane = __ffs(mm) - 1;
-          mm &= mm - 1;
-          ksite[q] = __shfl_sync(0xffffffffu, my_site, src_lane);
-        }
-      }
-    }
-    bool done = false;
-    if (wnc == 1) {
-      done = region_fast<1, SRC, SINGLE, LABELS>(&g, c, ra, rb, ksite[0], ksite[0], ksite[0], rm.w[0], rm.w[1], rm.w[2], rm.w[3]);
-    } else if (wnc == 2) {
-      done = region_fast<2, SRC, SINGLE, LABELS>(&g, c, ra, rb, ksite[0], ksite[1], ksite[1], rm.w[0], rm.w[1], rm.w[2], rm.w[3]);
-    } else if (VOR_MAXFAST >= 3 && wnc == 3) {
-      if constexpr (VOR_MAXFAST >= 3)
-        done = region_fast<3, SRC, SINGLE, LABELS>(&g, c, ra, rb, ksite[0], ksite[1], ksite[VOR_MAXFAST - 1], rm.w[0], rm.w[1], rm.w[2], rm.w[3]);
-    }
-    if (!done) {
       const bool keep = (wmask >> lane) & 1u;
       if (keep) wcand[__popc(wmask & ((1u << lane) - 1u))] = my_site;
       __syncwarp();
+    }
+    if (wnc == 1) {
+      region_one<SRC, SINGLE, LABELS>(&g, c, ra, rb, wcand[0], rm.w[0], rm.w[1], rm.w[2], rm.w[3]);
+    } else if (wnc == 2) {
+      region_runs<2, SRC, SINGLE, LABELS>(&g, c, ra, rb, wcand, lacc, rm.w[0], rm.w[1], rm.w[2], rm.w[3]);
+    } else if (wnc == 3) {
+      region_runs<3, SRC, SINGLE, LABELS>(&g, c, ra, rb, wcand, lacc, rm.w[0], rm.w[1], rm.w[2], rm.w[3]);
+    } else if (wnc == 4) {
+      region_runs<4, SRC, SINGLE, LABELS>(&g, c, ra, rb, wcand, lacc, rm.w[0], rm.w[1], rm.w[2], rm.w[3]);
+    } else {
       region_slow<SRC>(&g, c.c0, c.c1, c.col_base, ra, rb, wcand, wnc, SINGLE, lane);
     }
     __syncwarp();
   }
 }
 
-// dynamic shared memory: double px[R], py[R]; int out[R]; int cand[R]; int wcand[VOR_WARPS][32].
+// dynamic shared memory: double px[R], py[R]; int out[R]; int cand[R]; int wcand[VOR_WARPS][32];
+// then (16-byte aligned) per warp the lanes' owner accumulators and scratch, double [RUNS_LANE_DOUBLES][32 lanes].
 //
 // SINGLE = false (global): grid = (tiles_x * tiles_y, 1, E); a CTA owns a (2 x 64)-column x
 //   (4 x rpw)-row tile of the map, one region per warp; every robot is a site and every site's sums
@@ -691,7 +637,7 @@ __device__ __forceinline__ void process_region(const VorCta &g, const StripCtx &
 //   warps loop over the window's regions; sites = the robot + its neighbours within communication
 //   range (decentralized_cvt.h:100-120), only the robot's own cell is reduced.  SRC = SRC_ROBOT.
 __host__ __device__ inline size_t vor_smem_bytes(int R) {
-  return ((size_t)R * 24 + VOR_WARPS * 32 * sizeof(int) + 15) & ~(size_t)15;
+  return (((size_t)R * 24 + VOR_WARPS * 32 * sizeof(int) + 15) & ~(size_t)15) + (size_t)VOR_WARPS * RUNS_LANE_DOUBLES * 32 * 8;
 }
 
 template <int SRC, bool SINGLE, bool LABELS>
@@ -704,6 +650,7 @@ __global__ void __launch_bounds__(VOR_THREADS, 3) k_voronoi(VorArgs a) {
   int *s_out = reinterpret_cast<int *>(s_py + ns_cap);
   int *s_cand = s_out + ns_cap;
   int *s_wcand = s_cand + ns_cap;
+  const size_t acc_off = ((size_t)ns_cap * 24 + VOR_WARPS * 32 * sizeof(int) + 15) & ~(size_t)15;
   __shared__ VorCta s_cta;
   __shared__ int s_ns, s_nc;
   __shared__ double s_best[VOR_WARPS];
@@ -846,7 +793,8 @@ __global__ void __launch_bounds__(VOR_THREADS, 3) k_voronoi(VorArgs a) {
     c.c0 = max(c.col_base, tc0);
     c.c1 = min(c.col_base + VOR_TW, tc1);
     if (c.c0 >= c.c1) continue;
-    process_region<SRC, SINGLE, LABELS>(s_cta, c, s_cand, nc, s_wcand + warp * 32, lane);
+    process_region<SRC, SINGLE, LABELS>(s_cta, c, s_cand, nc, s_wcand + warp * 32,
+                                        reinterpret_cast<double *>(smem_raw + acc_off) + warp * (RUNS_LANE_DOUBLES * 32), lane);
     __syncwarp();
   }
 }
