@@ -44,7 +44,7 @@ constexpr int VOR_WARPS = VOR_THREADS / 32;
 constexpr int VOR_WX = 2, VOR_WY = 4;  // warp grid of a CTA tile (global mode)
 constexpr int VOR_TW = 64;       // region width: 16 lanes x 4 cells; lanes 16-31 take the next row
 constexpr int VOR_MAXRPW = 64;   // rows per warp region (4 mask words per lane cover 64 rows x 2 words)
-constexpr int VOR_MAXFAST = 4;   // regions with more competing sites are split, then take the generic path
+constexpr int VOR_MAXFAST = 3;   // regions with more competing sites are split, then take the generic path
 constexpr int VOR_MINSPLIT = 4;  // do not split below this many rows
 constexpr int VOR_PAD_ROWS = 8;  // rows the streaming loop may read past a region (see stream_region)
 
@@ -97,22 +97,40 @@ struct StripCtx {
 struct Sum4 {
   double m, sx, sy, s2;
 };
+__device__ __forceinline__ double shfl_xor_d(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+// Warp sum of four values per lane with 6 shuffles instead of 20: the first two butterfly steps halve
+// the number of values a lane carries (lanes with the bit set keep the upper half), the remaining
+// three steps reduce one value.  Lane l ends up with the total of value ((l >> 4) & 1) * 2 + ((l >> 3) & 1);
+// the result is returned to lane 0 .. through shared exchange of the four holders.
+__device__ __forceinline__ Sum4 reduce4(double m, double sx, double sy, double s2) {
+  const int lane = threadIdx.x & 31;
+  // step 1 (xor 16): lanes 0-15 keep (m, sx), lanes 16-31 keep (sy, s2)
+  const bool up1 = lane & 16;
+  double a0 = up1 ? sy : m, a1 = up1 ? s2 : sx;      // kept
+  double b0 = up1 ? m : sy, b1 = up1 ? sx : s2;      // sent
+  a0 += shfl_xor_d(b0, 16), a1 += shfl_xor_d(b1, 16);
+  // step 2 (xor 8): lanes with bit 3 clear keep a0, the others a1
+  const bool up2 = lane & 8;
+  double c0 = up2 ? a1 : a0, d0 = up2 ? a0 : a1;
+  c0 += shfl_xor_d(d0, 8);
+  c0 += shfl_xor_d(c0, 4);
+  c0 += shfl_xor_d(c0, 2);
+  c0 += shfl_xor_d(c0, 1);
+  // holders: lane 0 -> m, lane 8 -> sx, lane 16 -> sy, lane 24 -> s2
+  Sum4 r;
+  r.m = __shfl_sync(0xffffffffu, c0, 0);
+  r.sx = __shfl_sync(0xffffffffu, c0, 8);
+  r.sy = __shfl_sync(0xffffffffu, c0, 16);
+  r.s2 = __shfl_sync(0xffffffffu, c0, 24);
+  return r;
+}
 __device__ __forceinline__ Sum4 fold_and_reduce(const Acc6 &a, int col) {
   // fold the per-column sums with this lane's column coordinates (cell units), then warp-reduce
   const double y0 = (double)col + 0.5, y1 = y0 + 1.0, y2 = y0 + 2.0, y3 = y0 + 3.0;
-  Sum4 r;
-  r.m = (a.c0 + a.c1) + (a.c2 + a.c3);
-  r.sy = fma(y0, a.c0, fma(y1, a.c1, fma(y2, a.c2, y3 * a.c3)));
-  r.s2 = a.sxx + fma(y0 * y0, a.c0, fma(y1 * y1, a.c1, fma(y2 * y2, a.c2, (y3 * y3) * a.c3)));
-  r.sx = a.sx;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    r.m += __shfl_xor_sync(0xffffffffu, r.m, o);
-    r.sx += __shfl_xor_sync(0xffffffffu, r.sx, o);
-    r.sy += __shfl_xor_sync(0xffffffffu, r.sy, o);
-    r.s2 += __shfl_xor_sync(0xffffffffu, r.s2, o);
-  }
-  return r;
+  const double m = (a.c0 + a.c1) + (a.c2 + a.c3);
+  const double sy = fma(y0, a.c0, fma(y1, a.c1, fma(y2, a.c2, y3 * a.c3)));
+  const double s2 = a.sxx + fma(y0 * y0, a.c0, fma(y1 * y1, a.c1, fma(y2 * y2, a.c2, (y3 * y3) * a.c3)));
+  return reduce4(m, a.sx, sy, s2);
 }
 
 __device__ __forceinline__ void emit(double *sums, int e, int R, int slot, double m, double sx, double sy, double s2) {
@@ -191,138 +209,209 @@ struct ConsOne {
   }
 };
 
-// NCAND (2..4) owners: per-cell labels from the fp32 affine differences h_i = d2_i - d2_0 (the exact
-// fp64 rule for a lane's four cells whenever the best two are within a rigorous bound of the fp32
-// error), and per-COLUMN running sums (v, x v, x^2 v) that are flushed into the lane's per-owner
-// accumulators (shared memory, private to the lane) whenever the column's label changes -- a Voronoi
-// cell is convex, so a column changes owner at most NCAND - 1 times per region.  14 fp64 operations
-// per pass whatever the number of owners; no thresholds, no per-owner predicated sets.  The cold part
-// (exact labels, flushes) runs through a shared-memory scratch copy of the running sums with rolled
-// loops, so that it costs little code and no registers in the streaming loop.
-constexpr int RUNS_LANE_DOUBLES = VOR_MAXFAST * 4 + 12;  // per lane: owner accumulators + scratch
+// the stated rule between two candidates k0 < k1 (site indices) at one cell: 1 if k1 is strictly nearer
+__device__ __noinline__ int exact_label2(const double *s_px, const double *s_py, int k0, int k1, int row, int col,
+                                         double res) {
+  const double cx = cell_centre(row, res), cy = cell_centre(col, res);
+  return d2_exact(cx, cy, s_px[k1], s_py[k1]) < d2_exact(cx, cy, s_px[k0], s_py[k0]) ? 1 : 0;
+}
 
-template <int NCAND, bool SINGLE, bool LABELS>
-struct ConsRuns {
-  float h0[NCAND - 1], ha[NCAND - 1], hb[NCAND - 1];  // h_i at (row ra, this lane's first column); per row; per column
-  float margin;
-  unsigned cur;                    // owner (candidate index) of each column's running sums, one per byte; 0xff: none yet
-  double c[4], cx[4], cxx[4];
-  double *lacc;                    // this lane's shared memory: lacc[(owner * 4 + v) * 32], v = m, sx, sy, s2;
-                                   // scratch at lacc[(VOR_MAXFAST * 4 + k) * 32], k = 0..11
-  const int *cand;                 // NCAND site indices, ascending (shared memory)
+// Two owners, careful version (cold): returns T in [0, rows], packed with two flags: bit 30 =
+// candidate 1 owns the rows u < T (else the rows u >= T); bit 29 = every cell of the column needs
+// the exact rule.  h(u) = hc + u HA is d2_1 - d2_0 at row r0 + u of column `col`.
+__device__ __noinline__ int column_threshold(const double *s_px, const double *s_py, int k0, int k1, int r0, int col,
+                                             int rows, double hc, double HA, double eps, double res) {
+  if (fabs(HA) * rows <= eps) {
+    // the bisector runs (numerically) along this column: one label for all rows, unless it is
+    // within rounding of the cell centres, in which case every cell takes the exact rule
+    int T = (hc < 0.0) ? rows : 0;
+    return T | (1 << 30) | ((fabs(hc) <= eps) ? (1 << 29) : 0);
+  }
+  const double x = -hc / HA;       // h(x) = 0
+  const bool first1 = HA > 0.0;    // h increasing: candidate 1 (h < 0) owns the rows below x
+  double tf = first1 ? ceil(x) : floor(x) + 1.0;
+  tf = fmin(fmax(tf, 0.0), (double)rows);
+  int T = (int)tf;
+  // re-check the two cells next to the threshold with the exact rule when they are within
+  // rounding of the bisector (|h| <= eps there)
+  if (T - 1 >= 0 && T - 1 < rows && fabs(hc + (T - 1) * HA) <= eps) {
+    const int lab = exact_label2(s_px, s_py, k0, k1, r0 + T - 1, col, res);
+    if ((lab == 1) != first1) T -= 1;
+  }
+  if (T >= 0 && T < rows && fabs(hc + T * HA) <= eps) {
+    const int lab = exact_label2(s_px, s_py, k0, k1, r0 + T, col, res);
+    if ((lab == 1) == first1) T += 1;
+  }
+  return T | (first1 ? (1 << 30) : 0);
+}
 
-  __device__ __forceinline__ void init(const VorCta &g, int ra, int rows, int col, const int *cand_, double *lacc_) {
-    cand = cand_, lacc = lacc_;
+// 1.0 where p, else 0.0: fma(v, one_if(p), acc) is a predicated fp64 add in one instruction (the
+// C++ `if (p) acc += v` compiles to an add plus two 32-bit selects)
+__device__ __forceinline__ double one_if(bool p) { return __hiloint2double(p ? 0x3ff00000 : 0, 0); }
+
+// Two or three owners k0 < k1 (< k2), branch-free: set 0 takes every cell, set i the cells of owner i
+// through 0/1 masks, owner 0 gets the difference at the end.  A region's boundary crosses a different
+// column in almost every pass, so anything that branches per label change diverges on every pass.
+//   NC == 2: along a column h = d2_1 - d2_0 is affine and changes sign once: an integer row threshold
+//            per column (fp64, once per region; the cells next to it re-checked with the exact rule
+//            when they are within rounding of the bisector), one integer compare per cell;
+//   NC == 3: fp32 affine differences per cell, the exact rule when the best two are closer than a
+//            rigorous bound of the fp32 error.
+template <int NC, bool SINGLE, bool LABELS>
+struct ConsMask {
+  static constexpr int NSETS = SINGLE ? 1 : NC;
+  Acc6 acc[NSETS];
+  int T0, T1, T2, T3;   // NC == 2: cell (u, j) belongs to candidate 1 iff (first1 ? u : -u) < T_j
+  bool first1;
+  float h0a, haa, hba, h0b, hab, hbb, margin;  // NC == 3
+  int k0, k1, k2;
+
+  // returns false when whole columns need the exact rule (a bisector along a column through the cell
+  // centres): the caller takes the generic path
+  __device__ __forceinline__ bool init(const VorCta &g, int ra, int rows, int col, int k0_, int k1_, int k2_) {
+    k0 = k0_, k1 = k1_, k2 = k2_;
+#pragma unroll
+    for (int s = 0; s < NSETS; ++s) acc[s].zero();
+    T0 = T1 = T2 = T3 = 0, first1 = true;
+    h0a = haa = hba = h0b = hab = hbb = margin = 0.f;
     const double res = g.res;
     const double cx0 = cell_centre(ra, res), cy0 = cell_centre(col, res);
-    const int k0 = cand[0];
     const double p0x = g.s_px[k0], p0y = g.s_py[k0];
     const double f0 = d2_exact(cx0, cy0, p0x, p0y);
-    double hmax = 0.0;
+    const double p1x = g.s_px[k1], p1y = g.s_py[k1];
+    const double H0 = d2_exact(cx0, cy0, p1x, p1y) - f0;
+    const double HA = 2.0 * res * (p0x - p1x), HB = 2.0 * res * (p0y - p1y);
+    double hmax = fabs(H0) + rows * fabs(HA) + 4.0 * fabs(HB);
+    unsigned exact_cols = 0;
+    if (NC == 2) {
+      const double eps = 1e-9 * (1.0 + f0 + hmax);  // >> the fp64 rounding of d2 and of the affine form
+      int tt[4] = {0, 0, 0, 0};
+      bool careful = fabs(HA) * rows <= eps;
+      if (!careful) {
+        // h(u) = hc + u HA changes sign at x = -hc / HA: one reciprocal per lane, one multiply per
+        // column; a threshold whose neighbouring cells are within eps of the bisector is redone by
+        // the careful version (which applies the exact rule there)
+        first1 = HA > 0.0;
+        const double ninv = -1.0 / HA;
 #pragma unroll
-    for (int i = 1; i < NCAND; ++i) {
-      const int k = cand[i];
-      const double px = g.s_px[k], py = g.s_py[k];
-      const double H0 = d2_exact(cx0, cy0, px, py) - f0;
-      const double HA = 2.0 * res * (p0x - px), HB = 2.0 * res * (p0y - py);
-      hmax = fmax(hmax, fabs(H0) + rows * fabs(HA) + 4.0 * fabs(HB));
-      h0[i - 1] = (float)H0, ha[i - 1] = (float)HA, hb[i - 1] = (float)HB;
-    }
-    // fp32 evaluation error of h_i is < 2^-21 hmax; differences of two h's double it
-    margin = (float)(hmax * (1.0 / 262144.0));
-    cur = 0xffffffffu;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) c[j] = cx[j] = cxx[j] = 0.0;
-#pragma unroll
-    for (int t = 0; t < NCAND * 4; ++t) lacc[t * 32] = 0.0;
-  }
-
-  // Cold: exact labels where the fp32 ones are in doubt, then every column whose label changed moves
-  // its running sums to the previous owner's accumulators.  Returns the final labels.
-  __device__ __forceinline__ unsigned change(const VorCta &g, unsigned labs, bool amb, int row, int col) {
-    double *scr = lacc + VOR_MAXFAST * 4 * 32;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) scr[j * 32] = c[j], scr[(4 + j) * 32] = cx[j], scr[(8 + j) * 32] = cxx[j];
-    if (amb) {
-      const double res = g.res;
-      const double cxr = cell_centre(row, res);
-      labs = 0;
-#pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        const double cy = cell_centre(col + j, res);
-        int best = 0;
-        double bd = d2_exact(cxr, cy, g.s_px[cand[0]], g.s_py[cand[0]]);
-#pragma unroll 1
-        for (int i = 1; i < NCAND; ++i) {
-          const double dd = d2_exact(cxr, cy, g.s_px[cand[i]], g.s_py[cand[i]]);
-          if (dd < bd) bd = dd, best = i;
+        for (int j = 0; j < 4; ++j) {
+          const double hc = fma((double)j, HB, H0);
+          const double x = hc * ninv;
+          double tf = first1 ? ceil(x) : floor(x) + 1.0;
+          tf = fmin(fmax(tf, 0.0), (double)rows);
+          tt[j] = (int)tf;
+          const double hl = fma(tf - 1.0, HA, hc), hr = fma(tf, HA, hc);
+          careful |= (fabs(hl) <= eps) | (fabs(hr) <= eps);
         }
-        labs |= (unsigned)best << (8 * j);
       }
-    }
+      if (careful) {  // rare, per lane
 #pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-      const unsigned lj = (labs >> (8 * j)) & 0xffu, cj = (cur >> (8 * j)) & 0xffu;
-      if (lj == cj) continue;
-      if (cj != 0xffu && (!SINGLE || cj == 0u)) {
-        const double y = (double)(col + j) + 0.5;
-        const double cc = scr[j * 32];
-        double *dst = lacc + cj * 128;
-        dst[0] += cc;
-        dst[32] += scr[(4 + j) * 32];
-        dst[64] = fma(y, cc, dst[64]);
-        dst[96] += fma(y * y, cc, scr[(8 + j) * 32]);
+        for (int j = 0; j < 4; ++j) {
+          const int t = column_threshold(g.s_px, g.s_py, k0, k1, ra, col + j, rows, fma((double)j, HB, H0), HA, eps, res);
+          first1 = (t >> 30) & 1;  // depends on the sign of HA only (or is 1 for every flat column)
+          tt[j] = t & 0xffff;
+          exact_cols |= ((t >> 29) & 1u) << j;
+        }
       }
-      scr[j * 32] = 0.0, scr[(4 + j) * 32] = 0.0, scr[(8 + j) * 32] = 0.0;
+      // pass() tests (first1 ? u : -u) < Ts_j: u < T_j, resp. u >= T_j <=> -u < 1 - T_j
+      if (!first1) tt[0] = 1 - tt[0], tt[1] = 1 - tt[1], tt[2] = 1 - tt[2], tt[3] = 1 - tt[3];
+      T0 = tt[0], T1 = tt[1], T2 = tt[2], T3 = tt[3];
+    } else {
+      const double p2x = g.s_px[k2], p2y = g.s_py[k2];
+      const double G0 = d2_exact(cx0, cy0, p2x, p2y) - f0;
+      const double GA = 2.0 * res * (p0x - p2x), GB = 2.0 * res * (p0y - p2y);
+      hmax = fmax(hmax, fabs(G0) + rows * fabs(GA) + 4.0 * fabs(GB));
+      h0a = (float)H0, haa = (float)HA, hba = (float)HB;
+      h0b = (float)G0, hab = (float)GA, hbb = (float)GB;
+      // fp32 evaluation error of h_k is < 2^-21 hmax; differences of two h's double it
+      margin = (float)(hmax * (1.0 / 262144.0));
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) c[j] = scr[j * 32], cx[j] = scr[(4 + j) * 32], cxx[j] = scr[(8 + j) * 32];
-    cur = labs;
-    return labs;
+    return !__any_sync(0xffffffffu, exact_cols != 0u);
   }
 
   __device__ __forceinline__ void pass(const VorCta &g, float v0, float v1, float v2, float v3, int u, double xd, int ra,
                                        int rb, int col, unsigned in4) {
-    unsigned labs = 0;
-    bool amb = false;
-    {
+    // q1_j / q2_j: cell j belongs to candidate 1 / 2
+    bool q10 = false, q11 = false, q12 = false, q13 = false, q20 = false, q21 = false, q22 = false, q23 = false;
+    if (NC == 2) {
+      const int us = first1 ? u : -u;
+      q10 = us < T0, q11 = us < T1, q12 = us < T2, q13 = us < T3;
+    } else {
       const float uf = (float)u;
-      float hr[NCAND - 1];
+      const float hr0 = fmaf(uf, haa, h0a), hr1 = fmaf(uf, hab, h0b);
+      bool amb = false;
+      unsigned labs = 0;  // one label per byte
 #pragma unroll
-      for (int i = 0; i < NCAND - 1; ++i) hr[i] = fmaf(uf, ha[i], h0[i]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float best = 0.f, second = 3.0e38f;  // candidate 0 has h = 0
+      for (int i = 0; i < 4; ++i) {
+        const float g1 = fmaf((float)i, hba, hr0), g2 = fmaf((float)i, hbb, hr1);
+        float best = 0.f, second;  // winner among {0: 0, 1: g1, 2: g2}
         unsigned bl = 0;
-#pragma unroll
-        for (int i = 0; i < NCAND - 1; ++i) {
-          const float gi = fmaf((float)j, hb[i], hr[i]);
-          if (gi < best) second = best, best = gi, bl = (unsigned)(i + 1) << (8 * j);
-          else second = fminf(second, gi);
-        }
+        if (g1 < best) second = best, best = g1, bl = 1u << (8 * i);
+        else second = g1;
+        if (g2 < best) second = best, best = g2, bl = 2u << (8 * i);
+        else second = fminf(second, g2);
         amb |= (second - best < margin);
         labs |= bl;
       }
+      if (amb) {  // rare: a cell of this lane's four is within the fp32 error of a bisector -> exact rule
+        const double res = g.res;
+        const double cxr = cell_centre(ra + u, res);
+        const double ax = g.s_px[k0], ay = g.s_py[k0], bx = g.s_px[k1], by = g.s_py[k1], ex = g.s_px[k2], ey = g.s_py[k2];
+        labs = 0;
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+          const double cy = cell_centre(col + i, res);
+          unsigned best = 0;
+          double bd = d2_exact(cxr, cy, ax, ay);
+          double dd = d2_exact(cxr, cy, bx, by);
+          if (dd < bd) bd = dd, best = 1;
+          dd = d2_exact(cxr, cy, ex, ey);
+          if (dd < bd) bd = dd, best = 2;
+          labs |= best << (8 * i);
+        }
+      }
+      q10 = (labs & 0xffu) == 1u, q11 = ((labs >> 8) & 0xffu) == 1u, q12 = ((labs >> 16) & 0xffu) == 1u, q13 = (labs >> 24) == 1u;
+      q20 = (labs & 0xffu) == 2u, q21 = ((labs >> 8) & 0xffu) == 2u, q22 = ((labs >> 16) & 0xffu) == 2u, q23 = (labs >> 24) == 2u;
     }
-    if (amb | (labs != cur)) labs = change(g, labs, amb, ra + u, col);
     if (LABELS && !SINGLE) {
       if (g.labels && ra + u < rb) {
         int *lp_out = g.labels + (size_t)(ra + u) * g.N + col;
-        if (in4 & 1u) lp_out[0] = g.s_out[cand[labs & 0xffu]];
-        if (in4 & 2u) lp_out[1] = g.s_out[cand[(labs >> 8) & 0xffu]];
-        if (in4 & 4u) lp_out[2] = g.s_out[cand[(labs >> 16) & 0xffu]];
-        if (in4 & 8u) lp_out[3] = g.s_out[cand[labs >> 24]];
+        if (in4 & 1u) lp_out[0] = g.s_out[q10 ? k1 : (q20 ? k2 : k0)];
+        if (in4 & 2u) lp_out[1] = g.s_out[q11 ? k1 : (q21 ? k2 : k0)];
+        if (in4 & 4u) lp_out[2] = g.s_out[q12 ? k1 : (q22 ? k2 : k0)];
+        if (in4 & 8u) lp_out[3] = g.s_out[q13 ? k1 : (q23 ? k2 : k0)];
       }
+    }
+    if (SINGLE) {  // only the robot's own cells (candidate 0) count
+      v0 = (q10 || q20) ? 0.f : v0, v1 = (q11 || q21) ? 0.f : v1;
+      v2 = (q12 || q22) ? 0.f : v2, v3 = (q13 || q23) ? 0.f : v3;
     }
     const double dv0 = (double)v0, dv1 = (double)v1, dv2 = (double)v2, dv3 = (double)v3;
     const double xd2 = xd * xd;
-    c[0] += dv0, c[1] += dv1, c[2] += dv2, c[3] += dv3;
-    cx[0] = fma(xd, dv0, cx[0]), cx[1] = fma(xd, dv1, cx[1]), cx[2] = fma(xd, dv2, cx[2]), cx[3] = fma(xd, dv3, cx[3]);
-    cxx[0] = fma(xd2, dv0, cxx[0]), cxx[1] = fma(xd2, dv1, cxx[1]);
-    cxx[2] = fma(xd2, dv2, cxx[2]), cxx[3] = fma(xd2, dv3, cxx[3]);
+    {
+      Acc6 &t0 = acc[0];
+      t0.c0 += dv0, t0.c1 += dv1, t0.c2 += dv2, t0.c3 += dv3;
+      const double s = (dv0 + dv1) + (dv2 + dv3);
+      t0.sx = fma(xd, s, t0.sx);
+      t0.sxx = fma(xd2, s, t0.sxx);
+    }
+    if constexpr (!SINGLE) {
+      Acc6 &a = acc[1];
+      const double b0 = one_if(q10), b1 = one_if(q11), b2 = one_if(q12), b3 = one_if(q13);
+      a.c0 = fma(dv0, b0, a.c0), a.c1 = fma(dv1, b1, a.c1), a.c2 = fma(dv2, b2, a.c2), a.c3 = fma(dv3, b3, a.c3);
+      const double s_k = fma(dv0, b0, dv1 * b1) + fma(dv2, b2, dv3 * b3);
+      a.sx = fma(xd, s_k, a.sx);
+      a.sxx = fma(xd2, s_k, a.sxx);
+    }
+    if constexpr (!SINGLE && NC >= 3) {
+      Acc6 &a = acc[2];
+      const double b0 = one_if(q20), b1 = one_if(q21), b2 = one_if(q22), b3 = one_if(q23);
+      a.c0 = fma(dv0, b0, a.c0), a.c1 = fma(dv1, b1, a.c1), a.c2 = fma(dv2, b2, a.c2), a.c3 = fma(dv3, b3, a.c3);
+      const double s_k = fma(dv0, b0, dv1 * b1) + fma(dv2, b2, dv3 * b3);
+      a.sx = fma(xd, s_k, a.sx);
+      a.sxx = fma(xd2, s_k, a.sxx);
+    }
   }
-
-  __device__ __forceinline__ void finish(const VorCta &g, int col) { change(g, 0xfefefefeu, false, 0, col); }
 };
 
 // ---- the streaming skeleton ------------------------------------------------------------------------
@@ -332,10 +421,9 @@ struct ConsRuns {
 //     vector loads through a register ring that keeps U passes (2 KB per warp) in flight;
 //   otherwise: per pass the visibility nibble comes from the region's mask words (one shuffle), row
 //     pairs with nothing visible are skipped, cells are selected against the mask.
-template <int SRC, class Cons>
+template <int SRC, int U, class Cons>
 __device__ __forceinline__ void stream_region(const VorCta &g, const StripCtx &c, int ra, int rb, uint32_t m0, uint32_t m1,
                                               uint32_t m2, uint32_t m3, Cons &cons) {
-  constexpr int U = 4;
   const int lane = threadIdx.x & 31;
   const int hp = lane >> 4, c16 = lane & 15;
   const int col = c.col_base + 4 * c16;
@@ -423,37 +511,35 @@ __device__ __noinline__ void region_one(const VorCta *gp, StripCtx c, int ra, in
   ConsOne<LABELS && !SINGLE> cons;
   cons.init();
   cons.k0_slot = g.s_out[k0];
-  stream_region<SRC>(g, c, ra, rb, m0, m1, m2, m3, cons);
+  stream_region<SRC, 4>(g, c, ra, rb, m0, m1, m2, m3, cons);
   const Sum4 tot = fold_and_reduce(cons.a, c.col_base + 4 * (lane & 15));
   if (lane == 0) emit(g.sums, g.e, g.R, SINGLE ? g.robot : g.s_out[k0], tot.m, tot.sx, tot.sy, tot.s2);
 }
 
-// NCAND owners; cand (shared memory) holds their site indices, ascending.  lacc: this warp's per-lane
-// owner accumulators (shared memory, [4][4][32] doubles).
-template <int NCAND, int SRC, bool SINGLE, bool LABELS>
-__device__ __noinline__ void region_runs(const VorCta *gp, StripCtx c, int ra, int rb, const int *cand, double *lacc,
-                                         uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+// Two or three owners.  Returns false (nothing accumulated) when the caller has to take the generic path.
+template <int NC, int SRC, bool SINGLE, bool LABELS>
+__device__ __noinline__ bool region_mask(const VorCta *gp, StripCtx c, int ra, int rb, int k0, int k1, int k2, uint32_t m0,
+                                         uint32_t m1, uint32_t m2, uint32_t m3) {
   const VorCta &g = *gp;
   const int lane = threadIdx.x & 31;
   const int col = c.col_base + 4 * (lane & 15);
-  ConsRuns<NCAND, SINGLE, LABELS> cons;
-  cons.init(g, ra, rb - ra, col, cand, lacc + lane);
-  stream_region<SRC>(g, c, ra, rb, m0, m1, m2, m3, cons);
-  cons.finish(g, col);
-  // per owner: reduce the lanes' accumulators and emit
-#pragma unroll 1
-  for (int s = 0; s < (SINGLE ? 1 : NCAND); ++s) {
-    const double *src = lacc + lane + s * 128;
-    double m = src[0], sx = src[32], sy = src[64], s2 = src[96];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      m += __shfl_xor_sync(0xffffffffu, m, o);
-      sx += __shfl_xor_sync(0xffffffffu, sx, o);
-      sy += __shfl_xor_sync(0xffffffffu, sy, o);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    if (lane == 0) emit(g.sums, g.e, g.R, SINGLE ? g.robot : g.s_out[cand[s]], m, sx, sy, s2);
+  ConsMask<NC, SINGLE, LABELS> cons;
+  if (!cons.init(g, ra, rb - ra, col, k0, k1, k2)) return false;
+  stream_region<SRC, (NC == 2 ? 4 : 2)>(g, c, ra, rb, m0, m1, m2, m3, cons);
+  Sum4 tot = fold_and_reduce(cons.acc[0], col);
+  if (SINGLE) {
+    if (lane == 0) emit(g.sums, g.e, g.R, g.robot, tot.m, tot.sx, tot.sy, tot.s2);
+    return true;
   }
+  const int ksel[3] = {k0, k1, k2};
+#pragma unroll
+  for (int k = 1; k < ConsMask<NC, SINGLE, LABELS>::NSETS; ++k) {
+    const Sum4 part = fold_and_reduce(cons.acc[k], col);
+    if (lane == 0) emit(g.sums, g.e, g.R, g.s_out[ksel[k]], part.m, part.sx, part.sy, part.s2);
+    tot.m -= part.m, tot.sx -= part.sx, tot.sy -= part.sy, tot.s2 -= part.s2;
+  }
+  if (lane == 0) emit(g.sums, g.e, g.R, g.s_out[k0], tot.m, tot.sx, tot.sy, tot.s2);
+  return true;
 }
 
 // direct loader for the generic path
@@ -529,16 +615,12 @@ __device__ __noinline__ void region_slow(const VorCta *gp, int c0, int c1, int c
 // Returns the ballot of surviving lanes.
 __device__ __noinline__ unsigned cull_rect(double res, int c0, int c1, int r0, int r1, bool has, double kx, double ky,
                                           int lane) {
-  double fcen = INFINITY;
-  if (has) fcen = d2_exact(cell_centre((r0 + r1 - 1) >> 1, res), cell_centre((c0 + c1 - 1) >> 1, res), kx, ky);
-  double best = fcen;
-  int bl = lane;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    double ob = __shfl_xor_sync(0xffffffffu, best, o);
-    int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-    if (ob < best || (ob == best && ol < bl)) best = ob, bl = ol;
-  }
+  // reference site j*: the winner at the centre cell, found on fp32 keys (any site is a valid
+  // reference for the domination test below; a near-tie at the centre only changes how much is culled)
+  float fcen = 3.0e38f;
+  if (has) fcen = (float)d2_exact(cell_centre((r0 + r1 - 1) >> 1, res), cell_centre((c0 + c1 - 1) >> 1, res), kx, ky);
+  const unsigned kmin = __reduce_min_sync(0xffffffffu, __float_as_uint(fcen));  // non-negative floats order as integers
+  const int bl = __ffs(__ballot_sync(0xffffffffu, __float_as_uint(fcen) == kmin)) - 1;
   // corner distances share their one-dimensional squares
   const double dx0 = __dsub_rn(cell_centre(r0, res), kx), dx1 = __dsub_rn(cell_centre(r1 - 1, res), kx);
   const double dy0 = __dsub_rn(cell_centre(c0, res), ky), dy1 = __dsub_rn(cell_centre(c1 - 1, res), ky);
@@ -554,7 +636,7 @@ __device__ __noinline__ unsigned cull_rect(double res, int c0, int c1, int r0, i
     if (has && f[q] - fj <= 1e-7 * (1.0 + fj)) keep = true;
   }
   unsigned mask = __ballot_sync(0xffffffffu, keep);
-  if (__popc(mask) > 1) {
+  if (__popc(mask) > 2) {  // (with two survivors the other one is j* itself: nothing to gain)
     // pairwise domination among the survivors (a dominated site may still be used as dominator)
     unsigned todo = mask;
     while (todo) {
@@ -579,10 +661,22 @@ __device__ __noinline__ unsigned cull_rect(double res, int c0, int c1, int r0, i
 // culled again (fewer rows, fewer owners) before falling back to the generic path.
 template <int SRC, bool SINGLE, bool LABELS>
 __device__ __forceinline__ void process_region(const VorCta &g, const StripCtx &c, const int *s_cand, int nc, int *wcand,
-                                               double *lacc, int lane) {
+                                               int lane) {
   RegionMask rm;
   rm.w[0] = rm.w[1] = rm.w[2] = rm.w[3] = 0u;
-  if (SRC != SRC_WORLD) {
+  if (SRC == SRC_WORLD) {
+    // Ask for the whole region (<= 64 rows x 256 bytes = 128 lines, four per lane) to be brought into
+    // L2 now: the requests are all in flight while the warp culls and plans, and the streaming loop's
+    // loads then see L2 latency instead of HBM latency.
+    const int pcol = c.col_base + 32 * (lane & 1);
+    if (pcol < g.N) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int row = c.r0 + 16 * q + (lane >> 1);
+        if (row < c.r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.world + (size_t)row * g.N + pcol));
+      }
+    }
+  } else {
     const bool any = load_region_mask(g, c, lane, rm);
     if (!any && !(SRC == SRC_ROBOT && g.fill != 0.f)) return;  // nothing visible: all values are zero
   }
@@ -612,23 +706,21 @@ __device__ __forceinline__ void process_region(const VorCta &g, const StripCtx &
       if (keep) wcand[__popc(wmask & ((1u << lane) - 1u))] = my_site;
       __syncwarp();
     }
+    bool done = false;
     if (wnc == 1) {
       region_one<SRC, SINGLE, LABELS>(&g, c, ra, rb, wcand[0], rm.w[0], rm.w[1], rm.w[2], rm.w[3]);
+      done = true;
     } else if (wnc == 2) {
-      region_runs<2, SRC, SINGLE, LABELS>(&g, c, ra, rb, wcand, lacc, rm.w[0], rm.w[1], rm.w[2], rm.w[3]);
+      done = region_mask<2, SRC, SINGLE, LABELS>(&g, c, ra, rb, wcand[0], wcand[1], wcand[1], rm.w[0], rm.w[1], rm.w[2], rm.w[3]);
     } else if (wnc == 3) {
-      region_runs<3, SRC, SINGLE, LABELS>(&g, c, ra, rb, wcand, lacc, rm.w[0], rm.w[1], rm.w[2], rm.w[3]);
-    } else if (wnc == 4) {
-      region_runs<4, SRC, SINGLE, LABELS>(&g, c, ra, rb, wcand, lacc, rm.w[0], rm.w[1], rm.w[2], rm.w[3]);
-    } else {
-      region_slow<SRC>(&g, c.c0, c.c1, c.col_base, ra, rb, wcand, wnc, SINGLE, lane);
+      done = region_mask<3, SRC, SINGLE, LABELS>(&g, c, ra, rb, wcand[0], wcand[1], wcand[2], rm.w[0], rm.w[1], rm.w[2], rm.w[3]);
     }
+    if (!done) region_slow<SRC>(&g, c.c0, c.c1, c.col_base, ra, rb, wcand, wnc, SINGLE, lane);
     __syncwarp();
   }
 }
 
-// dynamic shared memory: double px[R], py[R]; int out[R]; int cand[R]; int wcand[VOR_WARPS][32];
-// then (16-byte aligned) per warp the lanes' owner accumulators and scratch, double [RUNS_LANE_DOUBLES][32 lanes].
+// dynamic shared memory: double px[R], py[R]; int out[R]; int cand[R]; int wcand[VOR_WARPS][32].
 //
 // SINGLE = false (global): grid = (tiles_x * tiles_y, 1, E); a CTA owns a (2 x 64)-column x
 //   (4 x rpw)-row tile of the map, one region per warp; every robot is a site and every site's sums
@@ -637,7 +729,7 @@ __device__ __forceinline__ void process_region(const VorCta &g, const StripCtx &
 //   warps loop over the window's regions; sites = the robot + its neighbours within communication
 //   range (decentralized_cvt.h:100-120), only the robot's own cell is reduced.  SRC = SRC_ROBOT.
 __host__ __device__ inline size_t vor_smem_bytes(int R) {
-  return (((size_t)R * 24 + VOR_WARPS * 32 * sizeof(int) + 15) & ~(size_t)15) + (size_t)VOR_WARPS * RUNS_LANE_DOUBLES * 32 * 8;
+  return ((size_t)R * 24 + VOR_WARPS * 32 * sizeof(int) + 15) & ~(size_t)15;
 }
 
 template <int SRC, bool SINGLE, bool LABELS>
@@ -650,7 +742,6 @@ __global__ void __launch_bounds__(VOR_THREADS, 3) k_voronoi(VorArgs a) {
   int *s_out = reinterpret_cast<int *>(s_py + ns_cap);
   int *s_cand = s_out + ns_cap;
   int *s_wcand = s_cand + ns_cap;
-  const size_t acc_off = ((size_t)ns_cap * 24 + VOR_WARPS * 32 * sizeof(int) + 15) & ~(size_t)15;
   __shared__ VorCta s_cta;
   __shared__ int s_ns, s_nc;
   __shared__ double s_best[VOR_WARPS];
@@ -793,8 +884,7 @@ __global__ void __launch_bounds__(VOR_THREADS, 3) k_voronoi(VorArgs a) {
     c.c0 = max(c.col_base, tc0);
     c.c1 = min(c.col_base + VOR_TW, tc1);
     if (c.c0 >= c.c1) continue;
-    process_region<SRC, SINGLE, LABELS>(s_cta, c, s_cand, nc, s_wcand + warp * 32,
-                                        reinterpret_cast<double *>(smem_raw + acc_off) + warp * (RUNS_LANE_DOUBLES * 32), lane);
+    process_region<SRC, SINGLE, LABELS>(s_cta, c, s_cand, nc, s_wcand + warp * 32, lane);
     __syncwarp();
   }
 }
