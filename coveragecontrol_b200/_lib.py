@@ -59,6 +59,10 @@ SIGNATURES = {
     "ccb_idf_set_map": (C.c_int, [C.c_void_p, c_float_p]),
     "ccb_idf_map_dev": (C.c_void_p, [C.c_void_p]),
     "ccb_idf_norm_factor": (C.c_int, [C.c_void_p, c_float_p]),
+    "ccb_idf_generate_band": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "ccb_idf_band_max_dev": (C.c_void_p, [C.c_void_p]),
+    "ccb_idf_normalize_band": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "ccb_idf_map_dev_mut": (C.c_void_p, [C.c_void_p]),
     "ccb_idf_get_bnds": (C.c_int, [C.c_void_p, c_double_p, C.c_int]),
     "ccb_idf_num_bnds": (C.c_int, [C.c_void_p]),
     "ccb_idf_num_polygons": (C.c_int, [C.c_void_p]),
@@ -96,6 +100,10 @@ SIGNATURES = {
     "ccb_env_sync": (C.c_int, [C.c_void_p]),
     "ccb_env_world_dev": (C.c_void_p, [C.c_void_p]),
     "ccb_env_positions_dev": (C.c_void_p, [C.c_void_p]),
+    "ccb_env_set_band_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "ccb_env_voronoi_partials_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ccb_env_finalize_from_partials_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ccb_env_step_actions_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ccb_ctrl_create": (C.c_void_p, [C.c_void_p, C.c_int]),
     "ccb_ctrl_destroy": (None, [C.c_void_p]),
     "ccb_ctrl_compute_actions": (C.c_int, [C.c_void_p]),

@@ -209,11 +209,27 @@ extern "C" int ccb_idf_get_polygon(const ccb_idf *idf, int k, double *xy, int ca
   return n;
 }
 
-extern "C" int ccb_idf_generate(ccb_idf *idf, int mode) {
+static int idf_finish(ccb_idf *idf, int row0, int row1) {
+  const int N = idf->p.pWorldMapSize;
+  cudaStream_t st = idf->stream;
+  k_idf_factor<<<1, 1, 0, st>>>(idf->d_max, (float)idf->p.pNorm, idf->d_factor);
+  CCB_LAUNCH_CHECK();
+  size_t nn = (size_t)(row1 - row0) * N;
+  if (nn > 0) {
+    k_idf_normalize<<<148 * 4, 256, 0, st>>>(idf->d_map + (size_t)row0 * N, ((size_t)row0 * N) % 4 == 0 ? nn / 4 : 0, nn, idf->d_factor);
+    CCB_LAUNCH_CHECK();
+  }
+  idf->factor_valid = false;
+  return 0;
+}
+
+// rows [row0, row1) of the map; finish = compute the factor from the map maximum and normalise
+static int idf_generate_rows(ccb_idf *idf, int mode, int row0, int row1, bool finish) {
   if (mode != 0 && mode != 1) return fail("ccb_idf_generate: mode must be 0 or 1");
   CCB_CUDA(cudaSetDevice(idf->device));
   const ccb_params &p = idf->p;
   const int N = p.pWorldMapSize;
+  if (row0 < 0 || row1 > N || row0 > row1) return fail("ccb_idf_generate: bad row band");
   const int F = (int)idf->bnds.size();
   cudaStream_t st = idf->stream;
 
@@ -276,18 +292,15 @@ extern "C" int ccb_idf_generate(ccb_idf *idf, int mode) {
   const float trun = (float)p.pTruncationBND;
   const float trun_sq = trun * trun;                       // generate_world_map.cu:188-189
   const float one_by_sqrt2 = (float)(1. / std::sqrt(2.));  // generate_world_map.cu:190-192
-  dim3 grid((N + IDF_TY - 1) / IDF_TY, (N + IDF_TX - 1) / IDF_TX);
-  if (mode == 0)
-    k_idf_generate<0><<<grid, IDF_THREADS, 0, st>>>(d_b, F, pd, N, res, trun_sq, one_by_sqrt2, idf->d_map, idf->d_max);
-  else
-    k_idf_generate<1><<<grid, IDF_THREADS, 0, st>>>(d_b, F, pd, N, res, trun_sq, one_by_sqrt2, idf->d_map, idf->d_max);
-  CCB_LAUNCH_CHECK();
-  k_idf_factor<<<1, 1, 0, st>>>(idf->d_max, (float)p.pNorm, idf->d_factor);
-  CCB_LAUNCH_CHECK();
-  size_t nn = (size_t)N * N;
-  k_idf_normalize<<<148 * 4, 256, 0, st>>>(idf->d_map, nn / 4, nn, idf->d_factor);
-  CCB_LAUNCH_CHECK();
-  idf->factor_valid = false;
+  if (row1 > row0) {
+    dim3 grid((N + IDF_TY - 1) / IDF_TY, (row1 - row0 + IDF_TX - 1) / IDF_TX);
+    if (mode == 0)
+      k_idf_generate<0><<<grid, IDF_THREADS, 0, st>>>(d_b, F, pd, N, row0, row1, res, trun_sq, one_by_sqrt2, idf->d_map, idf->d_max);
+    else
+      k_idf_generate<1><<<grid, IDF_THREADS, 0, st>>>(d_b, F, pd, N, row0, row1, res, trun_sq, one_by_sqrt2, idf->d_map, idf->d_max);
+    CCB_LAUNCH_CHECK();
+  }
+  if (finish && idf_finish(idf, row0, row1)) return 1;
   CCB_CUDA(cudaFreeAsync(d_b, st));
   if (NP > 0) {
     CCB_CUDA(cudaFreeAsync(d_px, st));
@@ -299,6 +312,20 @@ extern "C" int ccb_idf_generate(ccb_idf *idf, int mode) {
   }
   return 0;
 }
+
+extern "C" int ccb_idf_generate(ccb_idf *idf, int mode) {
+  return idf_generate_rows(idf, mode, 0, idf->p.pWorldMapSize, true);
+}
+extern "C" int ccb_idf_generate_band(ccb_idf *idf, int mode, int row0, int row1) {
+  return idf_generate_rows(idf, mode, row0, row1, false);
+}
+extern "C" int *ccb_idf_band_max_dev(ccb_idf *idf) { return idf->d_max; }
+extern "C" int ccb_idf_normalize_band(ccb_idf *idf, int row0, int row1) {
+  CCB_CUDA(cudaSetDevice(idf->device));
+  if (row0 < 0 || row1 > idf->p.pWorldMapSize || row0 > row1) return fail("ccb_idf_normalize_band: bad row band");
+  return idf_finish(idf, row0, row1);
+}
+extern "C" float *ccb_idf_map_dev_mut(ccb_idf *idf) { return idf->d_map; }
 
 extern "C" int ccb_idf_get_map(ccb_idf *idf, float *out) {
   CCB_CUDA(cudaSetDevice(idf->device));
@@ -359,6 +386,7 @@ struct ccb_env {
   bool initialised = false;
   std::map<int, ResizeTab> resize;
   int vor_rpw_override = 0;
+  bool band_mode = false;       // this env holds one row band of a world tiled over several GPUs
 };
 
 // rows per warp region: as large as keeps >= ~3 CTAs per SM in flight over the whole launch
@@ -386,14 +414,18 @@ static int run_voronoi(ccb_env *env, const VorArgs &a, dim3 grid) {
 }
 
 // Voronoi label + reduce over the full map of every environment; sums must be a [E][R][4] buffer.
-static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *labels = nullptr) {
+// row0/row1 restrict the pass to a row band (row1 < 0: the whole map).
+static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *labels = nullptr, int row0 = 0, int row1 = -1) {
   const EnvDev &d = env->d;
+  if (row1 < 0) row1 = d.N;
   CCB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * d.E * d.R, env->stream));
+  if (row1 <= row0) return 0;
   VorArgs a;
   a.d = d, a.sums = sums, a.labels = labels;
-  a.rpw = pick_rpw(env, d.N, d.N, d.E);
+  a.row0 = row0, a.row1 = row1;
+  a.rpw = pick_rpw(env, row1 - row0, d.N, d.E);
   a.tiles_y = (d.N + VOR_WX * VOR_TW - 1) / (VOR_WX * VOR_TW);
-  a.tiles_x = (d.N + VOR_WY * a.rpw - 1) / (VOR_WY * a.rpw);
+  a.tiles_x = (row1 - row0 + VOR_WY * a.rpw - 1) / (VOR_WY * a.rpw);
   dim3 grid(a.tiles_x * a.tiles_y, 1, d.E);
   if (src == SRC_WORLD) return labels ? run_voronoi<SRC_WORLD, false, true>(env, a, grid) : run_voronoi<SRC_WORLD, false, false>(env, a, grid);
   return labels ? run_voronoi<SRC_EXPLORED, false, true>(env, a, grid) : run_voronoi<SRC_EXPLORED, false, false>(env, a, grid);
@@ -407,6 +439,7 @@ static int launch_voronoi_single(ccb_env *env, double *sums) {
   a.d = d, a.sums = sums, a.labels = nullptr;
   a.rpw = env->vor_rpw_override > 0 ? std::max(2, std::min(env->vor_rpw_override, VOR_MAXRPW) & ~1) : 32;
   a.tiles_x = a.tiles_y = 1;  // one CTA per robot window
+  a.row0 = 0, a.row1 = d.N;
   return run_voronoi<SRC_ROBOT, true, false>(env, a, dim3(1, d.R, d.E));
 }
 
@@ -421,6 +454,8 @@ static int launch_finalize(ccb_env *env, const double *sums, CellsOut out, int w
 static int ensure_cells(ccb_env *env, bool want_polys) {
   if (!env->initialised) return fail("environment has no robot positions yet (call ccb_env_reset)");
   if (env->cells_version != env->pos_version) {
+    if (env->band_mode)
+      return fail("row-band mode: all-reduce the partials and call ccb_env_finalize_from_partials_dev first");
     if (launch_voronoi_global(env, SRC_WORLD, env->d_sums)) return 1;
     if (launch_finalize(env, env->d_sums, env->cells, want_polys ? 1 : 0)) return 1;
     env->cells_version = env->pos_version;
@@ -927,6 +962,38 @@ extern "C" int ccb_env_voronoi_labels(ccb_env *env, int src, int32_t *out /* E x
   return st;
 }
 
+// ---- row bands (multi-GPU tiling of one large world) ---------------------------------
+extern "C" int ccb_env_voronoi_partials_dev(ccb_env *env, int src, int row0, int row1, double *sums_dev) {
+  if (!env->initialised) return fail("environment has no robot positions yet");
+  if (src != SRC_WORLD && src != SRC_EXPLORED) return fail("partials: src must be 0 (world) or 1 (explored)");
+  if (row0 < 0 || row1 > env->d.N || row0 > row1) return fail("partials: bad row band");
+  CCB_CUDA(cudaSetDevice(env->device));
+  return launch_voronoi_global(env, src, sums_dev, nullptr, row0, row1);
+}
+
+extern "C" int ccb_env_finalize_from_partials_dev(ccb_env *env, const double *sums_dev) {
+  if (!env->initialised) return fail("environment has no robot positions yet");
+  CCB_CUDA(cudaSetDevice(env->device));
+  if (sums_dev != env->d_sums)
+    CCB_CUDA(cudaMemcpyAsync(env->d_sums, sums_dev, sizeof(double) * 4 * env->E * env->R, cudaMemcpyDeviceToDevice, env->stream));
+  if (launch_finalize(env, env->d_sums, env->cells, 0)) return 1;
+  env->cells_version = env->pos_version;
+  env->cells_have_polys = false;
+  return 0;
+}
+
+extern "C" int ccb_env_set_band_mode(ccb_env *env, int on) {
+  env->band_mode = on != 0;
+  env->cells_version = 0;
+  return 0;
+}
+
+extern "C" int ccb_env_step_actions_dev(ccb_env *env, const double *actions_dev) {
+  if (!env->initialised) return fail("environment has no robot positions yet");
+  CCB_CUDA(cudaSetDevice(env->device));
+  return step_actions_dev(env, actions_dev);
+}
+
 static int objective_dev(ccb_env *env, double *out_dev) {
   if (ensure_cells(env, false)) return 1;
   k_objective<<<env->E, 32, 0, env->stream>>>(env->d, env->cells.obj, out_dev);
@@ -1010,6 +1077,10 @@ static int ctrl_compute_goals(ccb_ctrl *c) {
   const size_t er = (size_t)d.E * d.R;
   if (c->kind == CCB_CLAIRVOYANT) {
     // clairvoyant_cvt.h:89-98: Voronoi on the world map == the env-level cells
+    if (ensure_cells(env, false)) return 1;
+    CCB_CUDA(cudaMemcpyAsync(c->d_goals, env->cells.centroid, sizeof(double) * 2 * er, cudaMemcpyDeviceToDevice, env->stream));
+  } else if (c->kind == CCB_CENTRALIZED && env->band_mode) {
+    // row-band mode: the caller all-reduced the explored-IDF partials into the env-level cells
     if (ensure_cells(env, false)) return 1;
     CCB_CUDA(cudaMemcpyAsync(c->d_goals, env->cells.centroid, sizeof(double) * 2 * er, cudaMemcpyDeviceToDevice, env->stream));
   } else if (c->kind == CCB_CENTRALIZED) {

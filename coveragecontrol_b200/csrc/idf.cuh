@@ -81,7 +81,7 @@ __device__ __forceinline__ float ordered_to_float(int i) {
 // differences tabulated in fp64 (more accurate than the reference, same truncation support).
 template <int MODE>
 __global__ void __launch_bounds__(IDF_THREADS)
-k_idf_generate(const BndF *__restrict__ bnd, int F, PolyDev poly, int N, float res, float trun_sq,
+k_idf_generate(const BndF *__restrict__ bnd, int F, PolyDev poly, int N, int row0, int row1, float res, float trun_sq,
                float one_by_sqrt2, float *__restrict__ out, int *__restrict__ max_ordered) {
   __shared__ int s_list[IDF_FC];
   __shared__ int s_nlist;
@@ -97,12 +97,12 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, PolyDev poly, int N, float r
   __shared__ float s_red[IDF_THREADS / 32];
 
   const int tid = threadIdx.x;
-  const int x0 = blockIdx.y * IDF_TX, y0 = blockIdx.x * IDF_TY;
+  const int x0 = row0 + blockIdx.y * IDF_TX, y0 = blockIdx.x * IDF_TY;  // rows [row0, row1): the whole map or a row band
   const int lrow = tid >> 3, lcol = (tid & 7) * 4;
   const int gx = x0 + lrow, gy = y0 + lcol;
 
   // tile extent of the cell mid points, used for conservative culling
-  const float tile_xlo = x0 * res, tile_xhi = (min(x0 + IDF_TX, N)) * res;
+  const float tile_xlo = x0 * res, tile_xhi = (min(x0 + IDF_TX, row1)) * res;
   const float tile_ylo = y0 * res, tile_yhi = (min(y0 + IDF_TY, N)) * res;
 
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -232,7 +232,7 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, PolyDev poly, int N, float r
     }
     __syncthreads();
     const int np = s_npoly;
-    if (np > 0 && gx < N) {
+    if (np > 0 && gx < row1) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (gy + c >= N) continue;
@@ -256,7 +256,7 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, PolyDev poly, int N, float r
 
   // ---- store + tile max ------------------------------------------------------------------------
   float vmax = -INFINITY;
-  if (gx < N) {
+  if (gx < row1) {
     float *row = out + (size_t)gx * N;
     if ((N & 3) == 0 && gy + 3 < N) {
       *reinterpret_cast<float4 *>(row + gy) = make_float4(acc[0], acc[1], acc[2], acc[3]);

@@ -54,6 +54,7 @@ struct VorArgs {
   EnvDev d;
   int rpw;      // rows per warp region (even, <= VOR_MAXRPW)
   int tiles_x, tiles_y;
+  int row0, row1;  // global mode: only rows [row0, row1) are labelled and reduced (row band of a multi-GPU world)
   double *sums; // [E][R][4]
   int *labels;  // optional [E][N*N] (global mode only): the label of every cell, for parity tests
 };
@@ -764,7 +765,7 @@ __global__ void __launch_bounds__(VOR_THREADS, 3) k_voronoi(VorArgs a) {
   } else {
     const int th = VOR_WY * a.rpw, tw = VOR_WX * VOR_TW;
     const int tx = blockIdx.x / a.tiles_y, ty = blockIdx.x - tx * a.tiles_y;
-    tr0 = tx * th, tr1 = min(tr0 + th, d.N);
+    tr0 = a.row0 + tx * th, tr1 = min(tr0 + th, a.row1);
     col_base0 = ty * tw;
     tc0 = col_base0, tc1 = min(col_base0 + tw, d.N);
   }

@@ -1,0 +1,177 @@
+"""Multi-GPU use of the grid hot path: one process per GPU, ``torch.distributed`` for the plumbing.
+
+The path shards two ways:
+
+* **independent environments** (BASELINE config 3): :func:`shard_envs` deals environment indices to
+  ranks; there is no data-path collective, only the final gather of whatever the caller collects;
+* **row bands of one large world** (BASELINE config 4): every rank holds the replicated robot state
+  and labels / reduces rows ``band_rows(N, world_size, rank)`` of the map only.  Per step the
+  per-robot moment partials ``[E][R][4]`` float64 are combined with ONE ``all_reduce(SUM)`` (NCCL over
+  NVLink on the GPU box, gloo in the CPU tests); IDF generation is per band with one scalar
+  ``all_reduce(MAX)`` for the normalisation factor and one ``all_gather`` of the bands (once, at
+  set-up) so that window crops near a band edge need no halo exchange.
+
+The reference has no multi-process form of this path (its Voronoi, voronoi.cpp:55-327, and its
+data generation, python/scripts/data_generation/data_generation.py:217-259, are single-process loops).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["band_rows", "shard_envs", "float_to_ordered", "ordered_to_float", "allreduce_sum_", "allreduce_max_",
+           "BandedWorldIDF", "BandedCoverageSystem"]
+
+
+def band_rows(n_rows: int, world_size: int, rank: int, align: int = 64) -> tuple[int, int]:
+    """Rows ``[row0, row1)`` of rank ``rank``: contiguous, disjoint, covering ``[0, n_rows)``; band edges are
+    multiples of ``align`` (the Voronoi kernel's region height) whenever ``n_rows`` allows it."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError("bad rank / world size")
+    units = (n_rows + align - 1) // align
+    if units < world_size:  # fewer aligned chunks than ranks: fall back to single rows
+        align, units = 1, n_rows
+    lo = (units * rank) // world_size
+    hi = (units * (rank + 1)) // world_size
+    return min(lo * align, n_rows), min(hi * align, n_rows)
+
+
+def shard_envs(total_envs: int, world_size: int, rank: int) -> range:
+    """Environment indices of rank ``rank`` (contiguous blocks, sizes differ by at most one)."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError("bad rank / world size")
+    lo = (total_envs * rank) // world_size
+    hi = (total_envs * (rank + 1)) // world_size
+    return range(lo, hi)
+
+
+def float_to_ordered(x):
+    """Order-preserving int32 image of float32 (the encoding the IDF kernel's atomicMax uses)."""
+    i = np.asarray(x, np.float32).view(np.int32)
+    return np.where(i >= 0, i, i ^ np.int32(0x7FFFFFFF)).astype(np.int32)
+
+
+def ordered_to_float(i):
+    i = np.asarray(i, np.int32)
+    return np.where(i >= 0, i, i ^ np.int32(0x7FFFFFFF)).astype(np.int32).view(np.float32)
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+def allreduce_sum_(t):
+    """In-place SUM over ranks (no-op in a single process).  ``t``: torch tensor on the backend's device."""
+    dist = _dist()
+    if dist is not None and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def allreduce_max_(t):
+    dist = _dist()
+    if dist is not None and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t
+
+
+def _rank_world():
+    dist = _dist()
+    return (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
+
+
+class BandedWorldIDF:
+    """WorldIDF generation tiled in row bands over the ranks of the default process group.
+
+    Each rank integrates the features over its rows only (generate_world_map.cu:76-164 per cell),
+    the map maximum is all-reduced (one int32), every band is normalised with the global factor
+    (generate_world_map.cu:252-259) and the bands are all-gathered so that every rank ends up with
+    the full, bit-identical map."""
+
+    def __init__(self, idf, mode: int = 0):
+        import torch
+
+        self.idf = idf
+        rank, world = _rank_world()
+        n = idf._params.pWorldMapSize
+        self.rows = band_rows(n, world, rank)
+        lib = _lib.load()
+        r0, r1 = self.rows
+        _lib.check(lib.ccb_idf_generate_band(idf._h, int(mode), r0, r1))
+        dev = torch.device("cuda", idf._device)
+        mx = _wrap_dev(lib.ccb_idf_band_max_dev(idf._h), (1,), torch.int32, dev)
+        allreduce_max_(mx)
+        _lib.check(lib.ccb_idf_normalize_band(idf._h, r0, r1))
+        if world > 1:
+            import torch.distributed as dist
+
+            full = _wrap_dev(lib.ccb_idf_map_dev_mut(idf._h), (n, n), torch.float32, dev)
+            bounds = [band_rows(n, world, g) for g in range(world)]
+            if len({b[1] - b[0] for b in bounds}) == 1:
+                dist.all_gather_into_tensor(full, full[r0:r1].clone())
+            else:  # ragged bands: one broadcast per band
+                for g, (a, b) in enumerate(bounds):
+                    if b > a:
+                        dist.broadcast(full[a:b], src=g)
+        idf._mutable = None
+
+
+def _wrap_dev(ptr: int, shape, dtype, device):
+    """Zero-copy torch view of library-owned device memory (``__cuda_array_interface__``)."""
+    import torch
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4"}[dtype]
+    h.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3,
+                                  "strides": None}
+    return torch.as_tensor(h, device=device)
+
+
+class BandedCoverageSystem:
+    """One large world tiled in row bands over the ranks (BASELINE config 4).
+
+    Every rank constructs the same :class:`BatchedCoverageSystem` (replicated positions; controllers
+    are deterministic, so the replicas stay bit-identical) and calls :meth:`compute_cells` instead of
+    relying on the env-level lazy Voronoi: partials over the rank's rows -> all-reduce -> finalise.
+    """
+
+    def __init__(self, env, src: int = 0):
+        import torch
+
+        self.env = env
+        self.src = int(src)
+        rank, world = _rank_world()
+        self.rank, self.world = rank, world
+        self.rows = band_rows(env._params.pWorldMapSize, world, rank)
+        self._sums = torch.zeros((env._E, env._R, 4), dtype=torch.float64, device=torch.device("cuda", env._device))
+        _lib.check(_lib.load().ccb_env_set_band_mode(env._h, 1))
+
+    def compute_cells(self, src: int | None = None):
+        """voronoi.cpp:55-327 over the whole world: band partials, one all-reduce, finalisation.
+        ``src`` 0: world map (ClairvoyantCVT, objective), 1: explored-IDF map (CentralizedCVT)."""
+        lib = _lib.load()
+        r0, r1 = self.rows
+        src = self.src if src is None else int(src)
+        _lib.check(lib.ccb_env_voronoi_partials_dev(self.env._h, src, r0, r1, self._sums.data_ptr()))
+        allreduce_sum_(self._sums)
+        _lib.check(lib.ccb_env_finalize_from_partials_dev(self.env._h, self._sums.data_ptr()))
+        return self._sums
+
+    def step(self, ctrl, with_objective: bool = False):
+        """``ComputeActions(); StepActions(GetActions())`` of a Clairvoyant/Centralized controller on the
+        banded world, device-resident.  Returns the objective (E,) at the new positions if asked."""
+        lib = _lib.load()
+        self.compute_cells()
+        _lib.check(lib.ccb_ctrl_compute_actions(ctrl._h))
+        _lib.check(lib.ccb_env_step_actions_dev(self.env._h, lib.ccb_ctrl_actions_dev(ctrl._h)))
+        self.env._invalidate()
+        if with_objective:  # coverage_system.h:598-601: always on the world map
+            self.compute_cells(0)
+            return self.env.objective()
+        return None

@@ -79,6 +79,13 @@ int ccb_idf_num_features(const ccb_idf *idf); /* world_idf.h:262-264 */
  * mode 0: arithmetic of the reference CUDA kernel (generate_world_map.cu:76-164), bit for bit
  * mode 1: fast separable form (erfc x1 - erfc x2)(erfc y1 - erfc y2), same truncation */
 int ccb_idf_generate(ccb_idf *idf, int mode);
+/* row-band variant for a world tiled over several GPUs: generate rows [row0,row1)
+ * un-normalised; *ccb_idf_band_max_dev = the band maximum as an order-preserving int32 (all-reduce
+ * it with MAX), then ccb_idf_normalize_band applies generate_world_map.cu:252-259 to the band. */
+int ccb_idf_generate_band(ccb_idf *idf, int mode, int row0, int row1);
+int *ccb_idf_band_max_dev(ccb_idf *idf);
+int ccb_idf_normalize_band(ccb_idf *idf, int row0, int row1);
+float *ccb_idf_map_dev_mut(ccb_idf *idf);
 int ccb_idf_get_map(ccb_idf *idf, float *out);       /* world_idf.h:258  GetWorldMap (D2H copy) */
 int ccb_idf_set_map(ccb_idf *idf, const float *in);  /* world_idf.h:115-127 / GetWorldMapMutable */
 const float *ccb_idf_map_dev(const ccb_idf *idf);
@@ -163,6 +170,20 @@ int ccb_env_sync(ccb_env *env);
 /* raw device state for zero-copy consumers (world: E x N x N floats) */
 const float *ccb_env_world_dev(const ccb_env *env);
 const double *ccb_env_positions_dev(const ccb_env *env);
+
+/* ---- row bands: one large world tiled over the GPUs of a box ------------------------
+ * Every rank holds the full-size buffers and the replicated robot state but labels/reduces only
+ * its rows.  Per step: partials (each rank, its band) -> all-reduce(SUM) of E x R x 4 doubles by the
+ * caller (NCCL) -> finalize (each rank) -> controllers / objective read the finalised cells.
+ * No reference equivalent: the reference's Voronoi (voronoi.cpp:55-327) is single-process. */
+int ccb_env_set_band_mode(ccb_env *env, int on);
+/* moments (sum v, sum x v, sum y v, sum (x^2+y^2) v; cell units) of rows [row0,row1) per site;
+ * src 0: world map, 1: explored-IDF map; sums_dev = E x R x 4 doubles on the device */
+int ccb_env_voronoi_partials_dev(ccb_env *env, int src, int row0, int row1, double *sums_dev);
+/* voronoi.cpp:41-53 + voronoi.h:89-95 from all-reduced moments; the env-level cells become current */
+int ccb_env_finalize_from_partials_dev(ccb_env *env, const double *sums_dev);
+/* coverage_system.h:279-291 StepActions with the actions already on the device (E x R x 2) */
+int ccb_env_step_actions_dev(ccb_env *env, const double *actions_dev);
 
 /* ---- CVT controllers ---------------------------------------------------- */
 enum ccb_ctrl_kind { CCB_CLAIRVOYANT = 0, CCB_CENTRALIZED = 1, CCB_DECENTRALIZED = 2 };

@@ -1,0 +1,106 @@
+"""Row-band tiling on the GPU (BASELINE config 4 mechanics), single process: the band entry points of
+the C ABI give, band by band, exactly what the whole-map calls give."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import random_world
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(N, R, F, seed):
+    import coverage_control as cc
+    from coveragecontrol_b200 import BatchedCoverageSystem
+
+    p = cc.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    p.pNumRobots = R
+    bnd, pos = random_world(seed, N, F, R)
+    idf = cc.WorldIDF(p)
+    for b in bnd:
+        idf.AddNormalDistribution(cc.BivariateNormalDistribution(cc.Point2(b[0], b[1]), float(b[2]), float(b[4])))
+    return cc, p, idf, pos, BatchedCoverageSystem
+
+
+@pytest.mark.parametrize("N,bands", [(512, [(0, 192), (192, 448), (448, 512)]), (300, [(0, 77), (77, 300)])])
+def test_idf_bands_equal_whole_map_bit_for_bit(N, bands):
+    import torch
+
+    from coveragecontrol_b200 import _lib
+    from coveragecontrol_b200.parallel import _wrap_dev
+
+    cc, p, idf, _, _ = _setup(N, 4, 9, 11)
+    idf.GenerateMap()
+    whole = np.array(idf.GetWorldMap())
+    cc2, p2, idf2, _, _ = _setup(N, 4, 9, 11)
+    lib = _lib.load()
+    # every "rank" generates its band into its own map; the maxima are combined as the all-reduce would
+    mx = []
+    for r0, r1 in bands:
+        _lib.check(lib.ccb_idf_generate_band(idf2._h, 0, r0, r1))
+        t = _wrap_dev(lib.ccb_idf_band_max_dev(idf2._h), (1,), torch.int32, torch.device("cuda", 0))
+        mx.append(int(t.item()))
+    t.fill_(max(mx))
+    for r0, r1 in bands:
+        _lib.check(lib.ccb_idf_normalize_band(idf2._h, r0, r1))
+    idf2._host = None
+    banded = np.array(idf2.GetWorldMap())
+    assert np.array_equal(whole.view(np.int32), banded.view(np.int32))
+    assert idf2.GetNormalizationFactor() == idf.GetNormalizationFactor()
+
+
+@pytest.mark.parametrize("N,R,nb", [(1024, 32, 4), (512, 64, 3), (300, 7, 2)])
+def test_band_partials_sum_to_whole_map_moments(N, R, nb):
+    import torch
+
+    from coveragecontrol_b200 import _lib
+    from coveragecontrol_b200.parallel import band_rows
+
+    cc, p, idf, pos, Batched = _setup(N, R, 12, 3)
+    idf.GenerateMap()
+    env = Batched(p, 1, R)
+    env.set_world(0, idf)
+    env.reset(pos[None])
+    mass, cen, _, obj = env.cells(0)
+    lib = _lib.load()
+    tot = torch.zeros((1, R, 4), dtype=torch.float64, device="cuda")
+    part = torch.zeros_like(tot)
+    for g in range(nb):
+        r0, r1 = band_rows(N, nb, g)
+        _lib.check(lib.ccb_env_voronoi_partials_dev(env._h, 0, r0, r1, part.data_ptr()))
+        tot += part
+    _lib.check(lib.ccb_env_set_band_mode(env._h, 1))
+    with pytest.raises(RuntimeError):
+        env.cells(0)  # band mode refuses to label the whole map behind the caller's back
+    _lib.check(lib.ccb_env_finalize_from_partials_dev(env._h, tot.data_ptr()))
+    mass2, cen2, _, obj2 = env.cells(0)
+    assert np.allclose(mass2, mass, rtol=1e-12, atol=1e-12)
+    assert np.allclose(cen2, cen, rtol=1e-10, atol=1e-9)
+    assert np.allclose(obj2, obj, rtol=1e-10, atol=1e-6)
+
+
+def test_banded_system_step_equals_plain_rollout():
+    from coveragecontrol_b200 import BatchedCVT
+    from coveragecontrol_b200.parallel import BandedCoverageSystem
+
+    N, R = 512, 12
+    cc, p, idf, pos, Batched = _setup(N, R, 10, 7)
+    idf.GenerateMap()
+    envs = []
+    for _ in range(2):
+        e = Batched(p, 1, R)
+        e.set_world(0, idf)
+        e.reset(pos[None])
+        envs.append(e)
+    plain, banded_env = envs
+    c0 = BatchedCVT(plain, 0)
+    banded = BandedCoverageSystem(banded_env, 0)
+    banded.compute_cells()
+    c1 = BatchedCVT(banded_env, 0)
+    for _ in range(5):
+        c0.rollout(1)
+        obj = banded.step(c1, with_objective=True)
+        assert np.allclose(plain.positions(), banded_env.positions(), rtol=0, atol=1e-9)
+        assert obj[0] == pytest.approx(plain.objective()[0], rel=1e-10)
