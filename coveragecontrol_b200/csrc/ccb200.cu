@@ -15,6 +15,7 @@
 #include "maps.cuh"
 #include "obs.cuh"
 #include "voronoi.cuh"
+#include "vwindow.cuh"
 
 namespace ccb {
 thread_local std::string g_last_error;
@@ -386,6 +387,7 @@ struct ccb_env {
   bool initialised = false;
   std::map<int, ResizeTab> resize;
   int vor_rpw_override = 0;
+  bool vw_generic = false;      // CCB_VW_GENERIC: force the generic window kernel (tests)
   bool band_mode = false;       // this env holds one row band of a world tiled over several GPUs
 };
 
@@ -434,6 +436,17 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
 // per-robot L-window variant (DecentralizedCVT): only the robot's own cell is reduced
 static int launch_voronoi_single(ccb_env *env, double *sums) {
   const EnvDev &d = env->d;
+  if (d.L <= VW_MAXL && (d.N & 3) == 0 && !env->vw_generic) {
+    static size_t current = 48 * 1024;
+    const size_t smem = vw_smem_bytes(d.R);
+    if (smem > current) {
+      CCB_CUDA(cudaFuncSetAttribute(k_voronoi_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      current = smem;
+    }
+    k_voronoi_window<<<dim3(d.R, d.E), VW_THREADS, smem, env->stream>>>(d, sums);
+    CCB_LAUNCH_CHECK();
+    return 0;
+  }
   CCB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * d.E * d.R, env->stream));
   VorArgs a;
   a.d = d, a.sums = sums, a.labels = nullptr;
@@ -550,6 +563,7 @@ extern "C" ccb_env *ccb_env_create(const ccb_params *p, int num_envs, int num_ro
   d.check_osc = p->pCheckOscillations;
   d.comm_range = p->pCommunicationRange, d.max_speed = p->pMaxRobotSpeed, d.dt = p->pTimeStep;
   if (const char *s = getenv("CCB_VOR_RPW")) env->vor_rpw_override = atoi(s);
+  if (const char *s = getenv("CCB_VW_GENERIC")) env->vw_generic = atoi(s) != 0;
   if (env_alloc(env.get())) {
     ccb_env_destroy(env.release());
     return nullptr;
@@ -872,8 +886,13 @@ extern "C" int ccb_env_cnn_input_dev(ccb_env *env, int C, int use_comm, float *o
   if (smem > 48 * 1024)
     CCB_CUDA(cudaFuncSetAttribute(k_cnn_local_obstacle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // channel order of coverage_env_utils.py:264-276: [local, comm_x, comm_y, obstacle]
-  if (t->d_wfull8 && !getenv("CCB_CNN_GENERIC")) {
-    k_cnn_fused8<<<dim3(d.R, d.E), CNN8_THREADS, 0, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, cc * (nch - 1));
+  if (t->d_wfull8 && (d.N & 3) == 0 && !getenv("CCB_CNN_GENERIC")) {
+    static bool cnn8_attr = false;
+    if (!cnn8_attr) {
+      CCB_CUDA(cudaFuncSetAttribute(k_cnn_fused8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CNN8_SMEM_BYTES));
+      cnn8_attr = true;
+    }
+    k_cnn_fused8<<<dim3(d.R, d.E), CNN8_THREADS, CNN8_SMEM_BYTES, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, cc * (nch - 1));
   } else {
     k_cnn_local_obstacle<<<dim3(C, d.R, d.E), 256, smem, env->stream>>>(d, C, tab, out_dev, stride, 0, cc * (nch - 1));
   }

@@ -122,62 +122,185 @@ __global__ void k_cnn_local_obstacle(EnvDev d, int C, ResizeTable tab, float *__
 }
 
 
-// ---- specialised path for L = 8 C (LPAC: 256 -> 32) ----------------------------------------------
-// One CTA per (robot, env), 8 warps; warp w owns output rows 4w .. 4w+3, i.e. window rows
-// 32 w - 4 .. 32 w + 35 (40 rows, each used by at most two output rows), and lane = oy.
-// The robot's bit plane says where its local map is non-zero: the warp first stages the 40 x 9 mask
-// words of its rows in shared memory (1.4 KB instead of 40 KB of floats), then only rows with a set
-// bit load world values (8 predicated loads per lane), go through a padded shared-memory line (one
-// pad word per 8 cells -> the 16-tap reads of the 32 lanes hit 32 different banks) and the width
-// pass; the height pass accumulates in registers in ascending row order, the order torchvision's
-// separable antialias kernel uses.  The obstacle channel needs no map at all:
-// obstacle(a, b) = 1 - in_x(a) in_y(b), so its width pass has only two possible values per output
-// column.  wfull[o][k] = weight of input index 8 o - 4 + k (zero outside torch's tap range).
+// ---- specialised path for L = 8 C (LPAC: 256 -> 32), N % 4 == 0 -----------------------------------
+// One CTA per (robot, env), 8 warps, lane = output column oy.  The robot's bit plane says where its
+// local map is non-zero, and after a few hundred steps that is still a small part of the 256 x 256
+// window, so the kernel is organised around the rows that have a seen cell:
+//   1. the 264 x 9 mask words of the window rows a in [-4, 260) are staged in shared memory, clipped to
+//      the window's columns (2.4 KB of global reads instead of 270 KB of floats), and the rows with a
+//      set bit are compacted into a list;
+//   2. width pass: the warps deal the listed rows between them in batches of CNN8_BATCH rows whose
+//      world values are all requested before the first is used (one HBM latency per batch instead of
+//      one per row).  A lane owns the 8 window columns 8 oy .. 8 oy + 7 of its output column: one byte
+//      of the row's mask says which are seen, the values arrive as 16-byte loads (the window origin is
+//      arbitrary, so the loads start at the aligned column below it and the misalignment S, uniform
+//      over the CTA, is a template parameter), the 4 + 4 neighbour taps come from the adjacent lanes by
+//      shuffle, and the 16-tap sum goes to s_tmp[a][oy];
+//   3. height pass: warp w owns output rows 4w .. 4w+3 and sums its 16 taps in ascending row order,
+//      the order torchvision's separable antialias kernel uses.
+// The obstacle channel needs no map at all: obstacle(a, b) = 1 - in_x(a) in_y(b), so its width pass
+// has only two possible values per output column.  wfull[o][k] = weight of input index 8 o - 4 + k
+// (zero outside torch's tap range).
 constexpr int CNN8_THREADS = 256;
-constexpr int CNN8_LINE = 304;
-constexpr int CNN8_ROWS = 40;   // window rows per warp
+constexpr int CNN8_WARPS = CNN8_THREADS / 32;
+constexpr int CNN8_ROWS = 264;  // window rows -4 .. 259
 constexpr int CNN8_WORDS = 9;   // mask words a 256-cell window row can touch
-// window column b in [-4, 260) -> word of the padded line (one pad word per 8 cells)
-__device__ __forceinline__ int cnn8_pos(int b) { return (b + 8) + ((b + 8) >> 3); }
+constexpr int CNN8_BATCH = 3;   // rows whose loads are in flight together
+
+struct Cnn8Shared {
+  float tmp[CNN8_ROWS][32];
+  uint32_t mask[CNN8_ROWS * CNN8_WORDS + 1];
+  float w[32][16];
+  uint32_t flags[(CNN8_ROWS + 31) / 32 + 1];  // bit a + 4: window row a has a non-zero cell
+  int act[CNN8_ROWS];
+  int nact;
+};
+constexpr size_t CNN8_SMEM_BYTES = sizeof(Cnn8Shared);
+
+// width pass over the listed rows; S = (window origin column) & 3
+template <int S>
+__device__ __forceinline__ void cnn8_width_pass(const EnvDev &d, Cnn8Shared &sh, const float *__restrict__ world, int ox_map,
+                                                int oy_map, int wbase, const float (&wc)[16]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nact = sh.nact;
+  const int gy0 = oy_map + 8 * lane;  // map column of this lane's first cell
+  const int gyb = gy0 - S;            // 16-byte aligned (N % 4 == 0)
+  constexpr int NV = S == 0 ? 2 : 3;  // aligned 4-cell groups covering the 8 cells
+  bool grp_in[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) grp_in[j] = gyb + 4 * j >= 0 && gyb + 4 * j + 3 < d.N;
+  unsigned inmap = 0u;  // bit i: column gy0 + i is inside the map
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (gy0 + i >= 0 && gy0 + i < d.N) inmap |= 1u << i;
+  // the lane's 8 mask bits start at bit `off` of the row's 9 words
+  const int off = gy0 - 32 * wbase;
+  const int wi = off >> 5, shf = off & 31;
+  const float fill = d.fill;
+  const bool dense = fill != 0.f;
+#pragma unroll 1
+  for (int base = warp * CNN8_BATCH; base < nact; base += CNN8_WARPS * CNN8_BATCH) {
+    float4 v[CNN8_BATCH][NV];
+    unsigned vis[CNN8_BATCH];
+#pragma unroll
+    for (int b = 0; b < CNN8_BATCH; ++b) {
+      vis[b] = 0u;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[b][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (base + b < nact) {  // warp-uniform
+        const int ai = sh.act[base + b];
+        const uint32_t lo = sh.mask[ai * CNN8_WORDS + wi], hi = sh.mask[ai * CNN8_WORDS + wi + 1];
+        vis[b] = __funnelshift_r(lo, hi, shf) & 0xffu;
+        if (vis[b] != 0u && d.use_sensor) {
+          const float4 *src = reinterpret_cast<const float4 *>(world + (size_t)(ox_map + ai - 4) * d.N + gyb);
+#pragma unroll
+          for (int j = 0; j < NV; ++j)
+            if (grp_in[j]) v[b][j] = __ldg(src + j);
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < CNN8_BATCH; ++b) {
+      if (base + b >= nact) break;  // warp-uniform
+      float x[4 * NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) x[4 * j] = v[b][j].x, x[4 * j + 1] = v[b][j].y, x[4 * j + 2] = v[b][j].z, x[4 * j + 3] = v[b][j].w;
+      float c[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float unseen = (dense && ((inmap >> i) & 1u)) ? fill : 0.f;
+        c[i] = ((vis[b] >> i) & 1u) ? x[S + i] : unseen;
+      }
+      // taps q = 0..15 are window columns 8 lane - 4 + q: the left neighbour's c[4..7], c[0..7], the
+      // right neighbour's c[0..3]; beyond the window (lanes 0 / 31) the padding is zero
+      float tmp = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float l = __shfl_up_sync(0xffffffffu, c[4 + q], 1);
+        if (lane == 0) l = 0.f;
+        tmp = fmaf(wc[q], l, tmp);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) tmp = fmaf(wc[4 + q], c[q], tmp);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float r = __shfl_down_sync(0xffffffffu, c[q], 1);
+        if (lane == 31) r = 0.f;
+        tmp = fmaf(wc[12 + q], r, tmp);
+      }
+      sh.tmp[sh.act[base + b]][lane] = tmp;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(CNN8_THREADS, 3)
 k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__restrict__ out,
              size_t robot_stride, size_t local_off, size_t obst_off) {
-  __shared__ float s_line[CNN8_THREADS / 32][CNN8_LINE];
-  __shared__ float s_w[32][16];
-  __shared__ uint32_t s_mask[CNN8_THREADS / 32][CNN8_ROWS * CNN8_WORDS];
+  extern __shared__ __align__(16) unsigned char cnn8_smem[];  // CNN8_SMEM_BYTES (opt-in: above 48 KB)
+  Cnn8Shared &sh = *reinterpret_cast<Cnn8Shared *>(cnn8_smem);
   const int r = blockIdx.x, e = blockIdx.y;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t er = (size_t)e * d.R + r;
   const size_t nn = cell_count(d);
-  for (int t = threadIdx.x; t < 32 * 16; t += CNN8_THREADS) s_w[t >> 4][t & 15] = wfull[t];
-  float *line = s_line[warp];
-  uint32_t *smask = s_mask[warp];
-  if (lane < 4) line[cnn8_pos(lane - 4)] = 0.f;         // taps left of the window
-  else if (lane < 8) line[cnn8_pos(252 + lane)] = 0.f;  // taps right of the window (b = 256..259)
+  for (int t = tid; t < 32 * 16; t += CNN8_THREADS) sh.w[t >> 4][t & 15] = wfull[t];
+  if (tid < (CNN8_ROWS + 31) / 32 + 1) sh.flags[tid] = 0u;
+  if (tid == 0) sh.nact = 0, sh.mask[CNN8_ROWS * CNN8_WORDS] = 0u;
   const double *p = d.pos_g + er * 2;
   const Window w = make_window(d.res, p[0], p[1], 256, d.N);
   const float *world = d.world + (size_t)e * nn;
   const uint32_t *plane = robot_plane(d, d.seenb, e, r);
-
-  // This warp owns output rows ox0 .. ox0+3; they need window rows a0 = 8 ox0 - 4 .. 8 ox0 + 35.
-  const int ox0 = warp * 4;
-  const int a0 = 8 * ox0 - 4;
-  // mask words of the 40 rows: word j of a row covers map columns 32 (wbase + j) .. + 31
-  const int wbase = w.oy >> 5;  // arithmetic shift: floor for negative origins
-  for (int t = lane; t < CNN8_ROWS * CNN8_WORDS; t += 32) {
-    const int a = t / CNN8_WORDS, j = t - a * CNN8_WORDS;
-    const int gx = w.ox + a0 + a, wd = wbase + j;
-    uint32_t m = 0u;
-    if (gx >= 0 && gx < d.N && wd >= 0 && wd < d.NW) m = __ldg(plane + (size_t)gx * d.NW + wd);
-    smask[t] = m;
-  }
+  const bool dense = d.fill != 0.f;  // unseen cells carry pUnknownImportance: every in-map row counts
   __syncthreads();
 
-  // width pass of the obstacle indicator for this lane's output column
+  // ---- 1. mask words, clipped to the window's map columns [cy0, cy1); all loads issued first ------
+  const int wbase = w.oy >> 5;  // arithmetic shift: floor for negative origins
+  const int cy0 = max(w.oy, 0), cy1 = min(w.oy + 256, d.N);
+  constexpr int NMW = (CNN8_ROWS * CNN8_WORDS + CNN8_THREADS - 1) / CNN8_THREADS;
+  uint32_t mw[NMW];
+#pragma unroll
+  for (int it = 0; it < NMW; ++it) {
+    const int t = tid + it * CNN8_THREADS;
+    const int ai = t / CNN8_WORDS, j = t - ai * CNN8_WORDS;  // ai = a + 4
+    const int a = ai - 4;
+    const int gx = w.ox + a, wd = wbase + j;
+    uint32_t m = 0u;
+    if (t < CNN8_ROWS * CNN8_WORDS && a >= 0 && a < 256 && gx >= 0 && gx < d.N && wd >= 0 && wd < d.NW) {
+      const int cb = wd << 5;  // map column of bit 0
+      const int lo = min(max(cy0 - cb, 0), 32), hi = min(max(cy1 - cb, 0), 32);
+      if (hi > lo) {
+        const uint32_t keep = ((hi - lo >= 32) ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) << lo;
+        m = __ldg(plane + (size_t)gx * d.NW + wd) & keep;
+        if (dense) atomicOr(&sh.flags[ai >> 5], 1u << (ai & 31));
+      }
+    }
+    mw[it] = m;
+  }
+#pragma unroll
+  for (int it = 0; it < NMW; ++it) {
+    const int t = tid + it * CNN8_THREADS;
+    if (t < CNN8_ROWS * CNN8_WORDS) {
+      sh.mask[t] = mw[it];
+      const int ai = t / CNN8_WORDS;
+      if (mw[it]) atomicOr(&sh.flags[ai >> 5], 1u << (ai & 31));
+    }
+  }
+  __syncthreads();
+  for (int ai = tid; ai < CNN8_ROWS; ai += CNN8_THREADS)
+    if ((sh.flags[ai >> 5] >> (ai & 31)) & 1u) sh.act[atomicAdd(&sh.nact, 1)] = ai;
+  __syncthreads();
+
+  // ---- 2. width pass over the listed rows ----------------------------------------------------------
   float wc[16];
 #pragma unroll
-  for (int q = 0; q < 16; ++q) wc[q] = s_w[lane][q];
+  for (int q = 0; q < 16; ++q) wc[q] = sh.w[lane][q];
+  switch (w.oy & 3) {
+    case 0: cnn8_width_pass<0>(d, sh, world, w.ox, w.oy, wbase, wc); break;
+    case 1: cnn8_width_pass<1>(d, sh, world, w.ox, w.oy, wbase, wc); break;
+    case 2: cnn8_width_pass<2>(d, sh, world, w.ox, w.oy, wbase, wc); break;
+    default: cnn8_width_pass<3>(d, sh, world, w.ox, w.oy, wbase, wc); break;
+  }
+
+  // width pass of the obstacle indicator for this lane's output column
   float oy_out = 0.f, oy_all = 0.f;
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
@@ -186,58 +309,28 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
     oy_all = fmaf(wc[q], 1.f, oy_all);
     oy_out = fmaf(wc[q], in_y ? 0.f : 1.f, oy_out);
   }
+  __syncthreads();
 
-  // Row a contributes to output row o = ox0 + i with weight s_w[o][a - (8 o - 4)] (two rows at most).
-  float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc_obs[4] = {0.f, 0.f, 0.f, 0.f};
-  const bool dense = d.fill != 0.f;  // unseen cells carry pUnknownImportance: nothing can be skipped
-#pragma unroll 1
-  for (int t = 0; t < CNN8_ROWS; ++t) {
-    const int gx = w.ox + a0 + t;
-    const bool in_x = gx >= 0 && gx < d.N;
-    // weights of this row for the four output rows (zero outside torch's 16-tap range)
-    float wr[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = t - 8 * i;  // tap index of row a0 + t in output row ox0 + i
-      wr[i] = (k >= 0 && k < 16) ? s_w[ox0 + i][k] : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc_obs[i] = fmaf(wr[i], in_x ? oy_out : oy_all, acc_obs[i]);
-    if (!in_x) continue;  // zero padding (warp-uniform)
-    const uint32_t mine = lane < CNN8_WORDS ? smask[t * CNN8_WORDS + lane] : 0u;
-    if (!dense && !__any_sync(0xffffffffu, mine != 0u)) continue;  // nothing seen in this row
-    float vals[8];
-    bool any = false;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int gy = w.oy + 32 * k + lane;
-      const bool in = gy >= 0 && gy < d.N;
-      const uint32_t word = smask[t * CNN8_WORDS + ((gy >> 5) - wbase)];
-      float v = 0.f;
-      if (in) {
-        if ((word >> (gy & 31)) & 1u) v = d.use_sensor ? __ldg(world + (size_t)gx * d.N + gy) : 0.f;
-        else v = d.fill;
-      }
-      vals[k] = v;
-      any |= (v != 0.f);
-    }
-    if (__any_sync(0xffffffffu, any)) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) line[cnn8_pos(32 * k + lane)] = vals[k];
-      __syncwarp();
-      float tmp = 0.f;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) tmp = fmaf(wc[q], line[cnn8_pos(8 * lane - 4 + q)], tmp);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] = fmaf(wr[i], tmp, acc[i]);
-      __syncwarp();
-    }
-  }
+  // ---- 3. height pass: output rows 4 warp .. 4 warp + 3, taps in ascending row order --------------
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float *dst = out + er * robot_stride + (size_t)(ox0 + i) * 32 + lane;
-    dst[local_off] = acc[i];
-    dst[obst_off] = acc_obs[i];
+    const int ox = warp * 4 + i;
+    float acc = 0.f, acc_obs = 0.f;
+    const int ai0 = 8 * ox;  // a + 4 of tap 0
+    // the 16 row flags of this output row: bits ai0 .. ai0 + 15
+    const uint32_t fl = __funnelshift_r(sh.flags[ai0 >> 5], sh.flags[(ai0 >> 5) + 1], ai0 & 31) & 0xffffu;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int a = ai0 - 4 + k;
+      const float wr = sh.w[ox][k];  // zero outside torch's tap range
+      const int gx = w.ox + a;
+      const bool in_x = a >= 0 && a < 256 && gx >= 0 && gx < d.N;
+      acc_obs = fmaf(wr, in_x ? oy_out : oy_all, acc_obs);
+      if ((fl >> k) & 1u) acc = fmaf(wr, sh.tmp[ai0 + k][lane], acc);
+    }
+    float *dst = out + er * robot_stride + (size_t)ox * 32 + lane;
+    dst[local_off] = acc;
+    dst[obst_off] = acc_obs;
   }
 }
 

@@ -475,29 +475,54 @@ __device__ __forceinline__ void stream_region(const VorCta &g, const StripCtx &c
     const bool use_sensor = (SRC == SRC_WORLD) || g.use_sensor;
     const size_t pstride = (size_t)2 * N;
     const int um0 = ra - c.r0;  // even: pass t sits in mask word group (um0 + 2 t) >> 4
-#pragma unroll 1
-    for (int t = 0; t < npass; ++t, xd += 2.0) {
+    // visibility nibble of pass t for this lane (0 past the last pass) and, where something is visible,
+    // the request for its world values.  t is warp-uniform, so the shuffle is executed by every lane.
+    auto fetch = [&](int t, float4 &w, unsigned &vis) {
+      vis = 0u;
+      w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t >= npass) return;
       const int u = 2 * t + hp;
-      const unsigned inside = (ra + u < rb) ? in4 : 0u;
-      unsigned vis = inside;
+      vis = (ra + u < rb) ? in4 : 0u;
       if (SRC != SRC_WORLD) {
         const int um = um0 + 2 * t;  // + hp stays inside the same 16-row word group
         const int q = um >> 4;
         const uint32_t sel = q == 0 ? m0 : (q == 1 ? m1 : (q == 2 ? m2 : m3));
         const uint32_t word = __shfl_sync(0xffffffffu, sel, (((um + hp) & 15) << 1) | (c16 >> 3));
         vis &= (word >> (4 * (c16 & 7))) & 0xfu;
-        if (!__any_sync(0xffffffffu, (fill != 0.f ? inside : vis) != 0u)) continue;  // nothing in this row pair
       }
-      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
       if (vis != 0u && use_sensor) w = load4(wp + (size_t)t * pstride, vec, inmap);
-      float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
-      if (SRC == SRC_ROBOT && fill != 0.f) {
-        f0 = (inside & 1u) ? fill : 0.f, f1 = (inside & 2u) ? fill : 0.f;
-        f2 = (inside & 4u) ? fill : 0.f, f3 = (inside & 8u) ? fill : 0.f;
+    };
+    // a ring of UM passes in flight: the loads of pass t + UM are issued before pass t is consumed
+    constexpr int UM = 4;
+    float4 ring[UM];
+    unsigned visr[UM];
+#pragma unroll
+    for (int k = 0; k < UM; ++k) fetch(k, ring[k], visr[k]);
+#pragma unroll 1
+    for (int t0 = 0; t0 < npass; t0 += UM) {
+#pragma unroll
+      for (int k = 0; k < UM; ++k) {
+        const int t = t0 + k;
+        if (t < npass) {  // warp-uniform
+          const int u = 2 * t + hp;
+          const unsigned inside = (ra + u < rb) ? in4 : 0u;
+          const unsigned vis = visr[k];
+          const float4 w = ring[k];
+          // row pairs with nothing visible contribute nothing (unless unseen cells carry a fill value)
+          const bool live = (SRC == SRC_WORLD) || __any_sync(0xffffffffu, (fill != 0.f ? inside : vis) != 0u);
+          if (live) {
+            float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+            if (SRC == SRC_ROBOT && fill != 0.f) {
+              f0 = (inside & 1u) ? fill : 0.f, f1 = (inside & 2u) ? fill : 0.f;
+              f2 = (inside & 4u) ? fill : 0.f, f3 = (inside & 8u) ? fill : 0.f;
+            }
+            const float v0 = (vis & 1u) ? w.x : f0, v1 = (vis & 2u) ? w.y : f1;
+            const float v2 = (vis & 4u) ? w.z : f2, v3 = (vis & 8u) ? w.w : f3;
+            cons.pass(g, v0, v1, v2, v3, u, xd + (double)(2 * t), ra, rb, col, in4);
+          }
+        }
+        fetch(t + UM, ring[k], visr[k]);
       }
-      const float v0 = (vis & 1u) ? w.x : f0, v1 = (vis & 2u) ? w.y : f1;
-      const float v2 = (vis & 4u) ? w.z : f2, v3 = (vis & 8u) ? w.w : f3;
-      cons.pass(g, v0, v1, v2, v3, u, xd, ra, rb, col, in4);
     }
   }
 }

@@ -103,3 +103,36 @@ def test_weights_and_positions():
     ref[ref < 1.0 / np.e] = 0
     ref.fill_diagonal_(0)
     assert torch.allclose(w, ref)
+
+
+@pytest.mark.parametrize("N,fill", [(1000, False), (1024, True), (600, False)])
+def test_cnn_input_every_window_alignment(N, fill):
+    """Window origins with every column misalignment (oy & 3), windows overhanging all four map edges,
+    optional unknown-importance fill of unseen cells (robot_model.h:180-187)."""
+    import torch
+    import torchvision
+
+    import coverage_control as cc
+    from oracle import oracle as orc
+
+    R = 12
+    p = cc.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    p.pNumRobots = R
+    p.pRobotMapUseUnknownImportance = fill
+    bnd, pos = random_world(33, N, 10, R)
+    for k in range(8):  # columns 8 apart cover every oy & 3 and oy & 31 phase, near and across the edges
+        pos[k] = [40.0 + 97.0 * k, 3.0 + 1.0 * k + (N - 20.0 if k % 2 else 0.0)]
+    pos[8] = [N - 5.0, N / 2 + 1.0]
+    pos[9] = [4.0, N / 2 + 2.0]
+    op = orc.params_from(p)
+    wm, _ = orc.idf_generate(op, bnd, mode=1)
+    oenv = orc.Env(op, wm, pos)
+    env = cc.CoverageSystem(p, cc.WorldIDF(p, wm), cc.PointVector(pos))
+    maps = cc.CoverageEnvUtils.get_maps(env, p, 32, True).cpu()
+    raw_local = torch.from_numpy(np.stack([oenv.local_map(r) for r in range(R)]))
+    raw_obst = torch.from_numpy(np.stack([oenv.obstacle_map(r) for r in range(R)]))
+    rs = lambda t: torchvision.transforms.functional.resize(  # noqa: E731
+        t, (32, 32), interpolation=torchvision.transforms.InterpolationMode.BILINEAR, antialias=True)
+    assert torch.allclose(maps[:, 0], rs(raw_local), rtol=1e-5, atol=1e-8)
+    assert torch.allclose(maps[:, 3], rs(raw_obst), rtol=1e-5, atol=1e-8)

@@ -1,0 +1,79 @@
+"""DecentralizedCVT's per-robot window Voronoi (csrc/vwindow.cuh): the row-interval kernel against the
+generic region kernel and against the oracle, on geometry chosen to hit the exact-rule branches
+(bisectors through cell centres, along rows, along columns), clipped windows and the unknown-fill mode."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import random_world
+
+pytestmark = pytest.mark.gpu
+
+
+def _goals(p, wm, pos, steps, generic):
+    from coveragecontrol_b200 import BatchedCoverageSystem, BatchedCVT
+
+    old = os.environ.get("CCB_VW_GENERIC")
+    os.environ["CCB_VW_GENERIC"] = "1" if generic else "0"
+    try:
+        env = BatchedCoverageSystem(p, 1, len(pos))
+    finally:
+        if old is None:
+            os.environ.pop("CCB_VW_GENERIC", None)
+        else:
+            os.environ["CCB_VW_GENERIC"] = old
+    env.set_world(0, wm)
+    env.reset(pos[None])
+    ctrl = BatchedCVT(env, 2)
+    out = []
+    for _ in range(steps):
+        ctrl.compute_actions()
+        out.append((ctrl.goals()[0].copy(), ctrl.actions()[0].copy()))
+        env.step_actions(ctrl.actions())
+    return out
+
+
+@pytest.mark.parametrize("N,L,S,fill,ties", [(512, 256, 64, False, True), (512, 128, 32, True, True),
+                                              (512, 128, 32, True, False), (256, 64, 16, False, False)])
+def test_window_kernel_matches_generic_kernel_and_oracle(N, L, S, fill, ties):
+    """ties=True puts bisectors exactly through cell centres: there the build's stated rule (ties to the
+    lowest site index = the robot itself in its own list) and the reference's scan-line rule
+    (voronoi.cpp:137-141, ties to the geometrically lower cell) differ, so only the two kernels are
+    compared; ties=False shifts the sites off the lattice and also compares with the oracle."""
+    import coverage_control as cc
+    from oracle import oracle as orc
+
+    R = 14
+    p = cc.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    p.pNumRobots = R
+    p.pLocalMapSize = L
+    p.pSensorSize = S
+    p.pCommunicationRange = L / 2.0
+    p.pRobotMapUseUnknownImportance = fill
+    p.pTimeStep = 0.2
+    bnd, pos = random_world(77, N, 14, R, sigma=(60.0, 90.0))
+    c = N / 2.0
+    q = 0.0 if ties else 0.3
+    pos[0] = [c, c]                # bisector with robot 1 along a row, through cell centres (x = c + 5.5)
+    pos[1] = [c + 11.0 + q, c]
+    pos[2] = [c, c + 11.0 + q]     # bisector with robot 0 along a column, through cell centres
+    pos[3] = [c + 7.0 + q, c + 7.0]  # diagonal bisector through cell centres
+    pos[4] = [c + 1e-9, c - 13.0 - q]  # nearly flat bisector slope
+    pos[5] = [2.5, 3.5]        # clipped windows
+    pos[6] = [N - 1.5, N - 9.0]
+    pos[7] = [N - 30.0, 12.0]
+    op = orc.params_from(p)
+    wm, _ = orc.idf_generate(op, bnd, mode=1)
+    steps = 8
+    new = _goals(p, wm, pos, steps, generic=False)
+    gen = _goals(p, wm, pos, steps, generic=True)
+    oenv = orc.Env(op, wm, pos)
+    for s in range(steps):
+        _, oa, og = oenv.compute_actions(2)
+        assert np.allclose(new[s][0], gen[s][0], rtol=1e-11, atol=1e-9), f"goals: window kernel vs generic, step {s}"
+        if not ties:
+            assert np.allclose(new[s][0], og, rtol=1e-4, atol=1e-6), f"goals vs oracle, step {s}"
+            assert np.allclose(new[s][1], oa, rtol=1e-4, atol=1e-6), f"actions vs oracle, step {s}"
+            oenv.step_actions(oa)
