@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libccb200.so")
 SOURCES = ["ccb200.cu"]
-HEADERS = ["common.cuh", "idf.cuh", "voronoi.cuh", "vwindow.cuh", "maps.cuh", "obs.cuh"]
+HEADERS = ["common.cuh", "idf.cuh", "voronoi.cuh", "vglobal.cuh", "vwindow.cuh", "maps.cuh", "obs.cuh"]
 
 NVCC_FLAGS = [
     "-std=c++17",

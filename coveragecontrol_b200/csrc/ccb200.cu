@@ -15,6 +15,7 @@
 #include "maps.cuh"
 #include "obs.cuh"
 #include "voronoi.cuh"
+#include "vglobal.cuh"
 #include "vwindow.cuh"
 
 namespace ccb {
@@ -387,6 +388,10 @@ struct ccb_env {
   bool initialised = false;
   std::map<int, ResizeTab> resize;
   int vor_rpw_override = 0;
+  uint32_t *d_vg_table = nullptr;  // [E][R][N] row intervals of the site-ordered global Voronoi (vglobal.cuh)
+  int *d_vg_flag = nullptr;     // [1 + E*N]: count, then the flagged rows
+  int *d_vg_span = nullptr;     // [E][R][2] row span of every site
+  bool vg_generic = false;      // CCB_VG_GENERIC: force the tile-ordered kernel (tests)
   bool vw_generic = false;      // CCB_VW_GENERIC: force the generic window kernel (tests)
   bool band_mode = false;       // this env holds one row band of a world tiled over several GPUs
 };
@@ -422,6 +427,40 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
   if (row1 < 0) row1 = d.N;
   CCB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * d.E * d.R, env->stream));
   if (row1 <= row0) return 0;
+  if (d.R <= VG_MAXR && (d.N & 3) == 0 && d.N < 65536 && !env->vg_generic) {
+    // site-ordered path: row partition -> per-site interval streaming -> exact rule on flagged rows
+    if (!env->d_vg_table) {
+      CCB_CUDA(cudaMalloc(&env->d_vg_table, sizeof(uint32_t) * (size_t)d.E * d.R * d.N));
+      CCB_CUDA(cudaMalloc(&env->d_vg_flag, sizeof(int) * ((size_t)d.E * d.N + 1)));
+      CCB_CUDA(cudaMalloc(&env->d_vg_span, sizeof(int) * 2 * (size_t)d.E * d.R));
+    }
+    k_vg_init_span<<<(d.E * d.R + 255) / 256, 256, 0, env->stream>>>(env->d_vg_span, d.E * d.R);
+    CCB_LAUNCH_CHECK();
+    CCB_CUDA(cudaMemsetAsync(env->d_vg_flag, 0, sizeof(int), env->stream));
+    VgArgs g;
+    g.d = d, g.row0 = row0, g.row1 = row1, g.table = env->d_vg_table, g.nflag = env->d_vg_flag, g.flag_list = env->d_vg_flag + 1, g.span = env->d_vg_span, g.sums = sums, g.labels = labels;
+    const int rows = row1 - row0;
+    k_vg_partition<<<dim3((rows + VG_PART_THREADS - 1) / VG_PART_THREADS, d.E), VG_PART_THREADS,
+                     sizeof(double) * d.R * d.R, env->stream>>>(g);
+    CCB_LAUNCH_CHECK();
+    const int chunks = (rows + VG_CHUNK - 1) / VG_CHUNK;
+    dim3 rgrid((chunks * d.R + VG_RED_WARPS - 1) / VG_RED_WARPS, d.E), fgrid(148 * 2);
+    if (src == SRC_WORLD) {
+      if (labels) k_vg_reduce<SRC_WORLD, true><<<rgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g);
+      else k_vg_reduce<SRC_WORLD, false><<<rgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g);
+      CCB_LAUNCH_CHECK();
+      if (labels) k_vg_fixup<SRC_WORLD, true><<<fgrid, 256, 0, env->stream>>>(g);
+      else k_vg_fixup<SRC_WORLD, false><<<fgrid, 256, 0, env->stream>>>(g);
+    } else {
+      if (labels) k_vg_reduce<SRC_EXPLORED, true><<<rgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g);
+      else k_vg_reduce<SRC_EXPLORED, false><<<rgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g);
+      CCB_LAUNCH_CHECK();
+      if (labels) k_vg_fixup<SRC_EXPLORED, true><<<fgrid, 256, 0, env->stream>>>(g);
+      else k_vg_fixup<SRC_EXPLORED, false><<<fgrid, 256, 0, env->stream>>>(g);
+    }
+    CCB_LAUNCH_CHECK();
+    return 0;
+  }
   VorArgs a;
   a.d = d, a.sums = sums, a.labels = labels;
   a.row0 = row0, a.row1 = row1;
@@ -564,6 +603,7 @@ extern "C" ccb_env *ccb_env_create(const ccb_params *p, int num_envs, int num_ro
   d.comm_range = p->pCommunicationRange, d.max_speed = p->pMaxRobotSpeed, d.dt = p->pTimeStep;
   if (const char *s = getenv("CCB_VOR_RPW")) env->vor_rpw_override = atoi(s);
   if (const char *s = getenv("CCB_VW_GENERIC")) env->vw_generic = atoi(s) != 0;
+  if (const char *s = getenv("CCB_VG_GENERIC")) env->vg_generic = atoi(s) != 0;
   if (env_alloc(env.get())) {
     ccb_env_destroy(env.release());
     return nullptr;
@@ -583,6 +623,7 @@ extern "C" void ccb_env_destroy(ccb_env *env) {
   free_cells(env->cells);
   cudaFree(env->d_objective), cudaFree(env->d_stage), cudaFree(env->d_feat), cudaFree(env->d_ratio);
   cudaFree(env->d_scratch);
+  cudaFree(env->d_vg_table), cudaFree(env->d_vg_flag), cudaFree(env->d_vg_span);
   cudaFreeHost(env->h_pin);
   for (auto &kv : env->resize)
     cudaFree(kv.second.d_xmin), cudaFree(kv.second.d_xsize), cudaFree(kv.second.d_w), cudaFree(kv.second.d_wfull8);

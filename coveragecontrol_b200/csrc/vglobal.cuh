@@ -1,0 +1,353 @@
+// vglobal.cuh -- whole-map Voronoi assignment + moment reduction organised by SITE instead of by tile.
+//
+// Replaces reference voronoi.cpp:55-327 for the global cells (ClairvoyantCVT, CentralizedCVT,
+// CoverageSystem::ComputeVoronoiCells / GetObjectiveValue).  A Voronoi cell is convex, so on every map
+// row it is ONE column interval.  Three kernels:
+//
+//   k_vg_partition  one thread per map row.  On row x the squared distances to the sites are parabolas
+//                   in y of equal curvature, F_q(y) = (y - py_q)^2 + (x - px_q)^2; their lower envelope
+//                   (the row's partition into owners) comes from the classic stack sweep over the sites
+//                   sorted by py.  Every decision carries a rigorous bound of its fp64 rounding error:
+//                   a hidden/visible decision, a breakpoint next to a cell centre, or a pair of parabolas
+//                   that cannot be separated within that bound FLAGS the row instead of guessing.
+//                   Output: table[e][site][row] = lo | hi << 16 (the site's cells on that row).
+//   k_vg_reduce     one warp per (site, 32-row chunk): streams the site's intervals with 16-byte loads
+//                   (4 rows x 32 columns per pass, the next pass requested before this one is used),
+//                   no labels, no per-cell distance, one owner per warp: fp64 sums in cell units as in
+//                   voronoi.cuh, one set of fp64 atomics per (site, chunk).  Every map cell is read
+//                   once, by its owner.  SRC_EXPLORED ANDs the intervals with the explored bit plane.
+//   k_vg_fixup      flagged rows only: the stated rule per cell (d2 in fp64 without FMA contraction,
+//                   strict <, ascending site index), label runs flushed with atomics.
+//
+// A cell's label is therefore either decided by an envelope whose every comparison was outside its
+// error bound (then it equals the stated rule's label) or by the stated rule itself.
+// Restrictions (the caller falls back to k_voronoi otherwise): R <= VG_MAXR, N % 4 == 0, N < 65536.
+#pragma once
+
+#include "common.cuh"
+#include "voronoi.cuh"
+
+namespace ccb {
+
+constexpr int VG_MAXR = 64;
+constexpr int VG_PART_THREADS = 128;
+constexpr int VG_RED_WARPS = 4;
+constexpr int VG_CHUNK = 32;  // rows per warp item: lane <-> row when the intervals are fetched
+constexpr int VG_U = 8;       // passes requested together
+
+struct VgArgs {
+  EnvDev d;
+  int row0, row1;       // rows [row0, row1): the whole map or a row band
+  uint32_t *table;      // [E][R][N]
+  int *flag_list;       // flagged rows as e * N + row, *nflag entries (zeroed before k_vg_partition)
+  int *nflag;
+  int *span;            // [E][R][2]: first row / last row + 1 on which the site owns a cell (within the band)
+  double *sums;         // [E][R][4]
+  int *labels;          // optional [E][N*N]
+};
+
+__device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row, const int *s_ord, const double *s_x,
+                                                 const double *s_y, const double *s_inv, int *s_rmin, int *s_rmax);
+
+__global__ void k_vg_init_span(int *span, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) span[2 * i] = 0x7fffffff, span[2 * i + 1] = 0;
+}
+
+__global__ void __launch_bounds__(VG_PART_THREADS) k_vg_partition(VgArgs a) {
+  __shared__ int s_ord[VG_MAXR];
+  __shared__ double s_x[VG_MAXR], s_y[VG_MAXR];
+  __shared__ int s_rmin[VG_MAXR], s_rmax[VG_MAXR];
+  extern __shared__ double s_inv[];  // [R][R]: 1 / (2 (y_q - y_p)) of the sorted sites, shared by the CTA's rows
+  const EnvDev &d = a.d;
+  const int e = blockIdx.y, tid = threadIdx.x, R = d.R, N = d.N;
+  const double *pos = d.pos_g + (size_t)e * R * 2;
+  // sites sorted by (py, index): rank by counting
+  for (int k = tid; k < R; k += VG_PART_THREADS) {
+    const double yk = pos[2 * k + 1];
+    int rank = 0;
+    for (int j = 0; j < R; ++j) {
+      const double yj = pos[2 * j + 1];
+      rank += (yj < yk || (yj == yk && j < k)) ? 1 : 0;
+    }
+    s_ord[rank] = k, s_x[rank] = pos[2 * k], s_y[rank] = yk;
+    s_rmin[k] = 0x7fffffff, s_rmax[k] = 0;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < R * R; idx += VG_PART_THREADS) {
+    const int p = idx / R, q = idx - p * R;
+    const double dy = s_y[q] - s_y[p];
+    s_inv[idx] = dy > 0.0 ? 1.0 / (2.0 * dy) : 0.0;
+  }
+  __syncthreads();
+  const int row = a.row0 + blockIdx.x * VG_PART_THREADS + tid;
+  if (row < a.row1) vg_partition_row(a, e, row, s_ord, s_x, s_y, s_inv, s_rmin, s_rmax);
+  __syncthreads();
+  // the CTA's rows extend every site's row span
+  for (int k = tid; k < R; k += VG_PART_THREADS)
+    if (s_rmax[k] > s_rmin[k]) {
+      atomicMin(a.span + ((size_t)e * R + k) * 2, s_rmin[k]);
+      atomicMax(a.span + ((size_t)e * R + k) * 2 + 1, s_rmax[k]);
+    }
+}
+
+__device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row, const int *s_ord, const double *s_x,
+                                                 const double *s_y, const double *s_inv, int *s_rmin, int *s_rmax) {
+  const EnvDev &d = a.d;
+  const int R = d.R, N = d.N;
+  const double res = d.res;
+  const double cx = cell_centre(row, res);
+  const double y_first = cell_centre(0, res), y_last = cell_centre(N - 1, res);
+
+  int v[VG_MAXR];          // envelope: sorted positions of the owners, left to right
+  double z[VG_MAXR];       // z[m]: boundary between v[m-1] and v[m]
+  double zerr[VG_MAXR];    // bound of its rounding error
+  bool flagged = false;
+  int top = 0;
+  v[0] = 0, z[0] = -INFINITY, zerr[0] = 0.0;
+  for (int q = 1; q < R; ++q) {
+    const double yq = s_y[q], dxq = cx - s_x[q];
+    while (true) {
+      const int p = v[top];
+      const double yp = s_y[p], dxp = cx - s_x[p];
+      const double dy = yq - yp;                     // >= 0 (sorted)
+      const double num = (dxq - dxp) * (dxq + dxp);  // dxq^2 - dxp^2
+      const double ysum = yq + yp;
+      // F_q(y) - F_p(y) = num + dy (ysum - 2 y): decreasing in y
+      const double scale = 1.0 + fabs(num) + (fabs(ysum) + 2.0 * y_last) * dy + dxq * dxq + dxp * dxp;
+      const double eps_h = 1e-12 * scale;
+      if (2.0 * dy * (y_last - y_first) <= eps_h) {
+        // the two parabolas differ by a constant within rounding on this row
+        const double d0 = num + dy * (ysum - 2.0 * y_first), d1 = num + dy * (ysum - 2.0 * y_last);
+        if (d0 > eps_h && d1 > eps_h) break;  // q is above p everywhere: q owns nothing
+        if (d0 < -eps_h && d1 < -eps_h) {     // p is above q everywhere: drop p
+          if (top == 0) {
+            v[0] = q;
+            break;
+          }
+          --top;
+          continue;
+        }
+        flagged = true;
+        break;
+      }
+      const double inv = s_inv[p * R + q];
+      const double s = fma(num, inv, 0.5 * ysum);  // q is nearer than p for y > s
+      // bound of the rounding error of s, plus the distance (in y) within which the rounded d2 of the
+      // stated rule may order p and q differently from exact arithmetic: 1e-14 is ~45 ulp
+      const double fsum = dxp * dxp + dxq * dxq + (s - yp) * (s - yp) + (s - yq) * (s - yq);
+      const double serr = 1e-14 * (fabs(0.5 * ysum) + res + (fabs(num) + fsum) * inv);
+      const double slack = serr + zerr[top];
+      if (s <= z[top] - slack) {  // p never owns anything: hidden between v[top-1] and q
+        --top;                    // (top >= 1 here: z[0] = -inf)
+        continue;
+      }
+      if (s < z[top] + slack) {   // cannot tell hidden from visible within rounding
+        flagged = true;
+        --top;
+        continue;
+      }
+      ++top;
+      v[top] = q, z[top] = s, zerr[top] = serr;
+      break;
+    }
+  }
+
+  // integer breakpoints: v[m] owns columns [T[m], T[m+1]); a cell centre within the error bound of a
+  // boundary flags the row
+  uint32_t iv[VG_MAXR];
+  for (int k = 0; k < R; ++k) iv[k] = 0u;
+  int lo = 0;
+  for (int m = 0; m <= top && !flagged; ++m) {
+    int hi = N;
+    if (m < top) {
+      const double b = z[m + 1], berr = zerr[m + 1] + 1e-13 * (fabs(b) + res);
+      const double t = ceil(b / res - 0.5);  // first column whose centre is >= b
+      const double tc = fmin(fmax(t, 0.0), (double)N);
+      hi = (int)tc;
+      // centres of the cells next to the boundary
+      if (t >= 1.0 && t <= (double)N && fabs(cell_centre((int)t - 1, res) - b) <= berr) flagged = true;
+      if (t >= 0.0 && t < (double)N && fabs(cell_centre((int)t, res) - b) <= berr) flagged = true;
+    }
+    if (hi < lo) hi = lo;
+    iv[s_ord[v[m]]] = (uint32_t)lo | ((uint32_t)hi << 16);
+    if (hi > lo) atomicMin(&s_rmin[s_ord[v[m]]], row), atomicMax(&s_rmax[s_ord[v[m]]], row + 1);
+    lo = hi;
+  }
+  if (flagged) a.flag_list[atomicAdd(a.nflag, 1)] = e * N + row;
+  uint32_t *t = a.table + (size_t)e * R * N + row;
+  for (int k = 0; k < R; ++k) t[(size_t)k * N] = flagged ? 0u : iv[k];
+}
+
+// ---- reduce ----------------------------------------------------------------------------------------
+// keep bits of a lane's four cells col .. col + 3 against [lo, hi): bit i set iff lo <= col + i < hi
+__device__ __forceinline__ unsigned vg_keep4(int col, int lo, int hi) {
+  const int a = min(max(lo - col, 0), 4), b = min(max(hi - col, 0), 4);
+  return ((1u << b) - 1u) & ~((1u << a) - 1u);
+}
+
+template <int SRC, bool LABELS>
+__global__ void __launch_bounds__(VG_RED_WARPS * 32) k_vg_reduce(VgArgs a) {
+  const EnvDev &d = a.d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.y;
+  const int N = d.N, R = d.R;
+  // Items = (site, 32-row chunk) pairs on which the site owns cells, numbered site by site from the row
+  // spans k_vg_partition left: the first warps of the grid get all the work, the rest exit at once.
+  const int item = blockIdx.x * VG_RED_WARPS + warp;
+  int k = -1, chunk = 0;
+  {
+    int before = 0;  // items of the sites below the ones this round looks at
+    for (int kb = 0; kb < R && k < 0; kb += 32) {
+      const int kk = kb + lane;
+      int first = 0, cnt = 0;
+      if (kk < R) {
+        const int2 sp = __ldg(reinterpret_cast<const int2 *>(a.span) + (size_t)e * R + kk);
+        if (sp.y > sp.x) first = (sp.x - a.row0) / VG_CHUNK, cnt = (sp.y - 1 - a.row0) / VG_CHUNK - first + 1;
+      }
+      int incl = cnt;  // inclusive prefix sum over the lanes
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      const unsigned hit = __ballot_sync(0xffffffffu, item < before + incl);
+      if (hit) {
+        const int src = __ffs(hit) - 1;
+        k = kb + src;
+        chunk = __shfl_sync(0xffffffffu, first, src) + (item - before - (__shfl_sync(0xffffffffu, incl, src) - __shfl_sync(0xffffffffu, cnt, src)));
+      }
+      before += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+  if (k < 0) return;
+  const int rbase = a.row0 + chunk * VG_CHUNK;
+  const int myrow = rbase + lane;
+  const uint32_t iv = myrow < a.row1 ? __ldg(a.table + ((size_t)e * R + k) * N + myrow) : 0u;
+  const int lo_l = (int)(iv & 0xffffu), hi_l = (int)(iv >> 16);
+  const float *world = d.world + (size_t)e * N * N;
+  // ask for this lane's row interval to be brought into L2 now (a line per 32 columns): the whole
+  // chunk is in flight while the warp streams it, and the loads below see L2 latency
+  if (SRC == SRC_WORLD) {
+    const float *prow = world + (size_t)myrow * N;
+    for (int c = lo_l & ~31; c < hi_l; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + c));
+  }
+  const uint32_t *plane = SRC == SRC_EXPLORED ? d.sysb + ((size_t)e * 2) * plane_words(d) : nullptr;
+  int *labels = (LABELS && a.labels) ? a.labels + (size_t)e * N * N : nullptr;
+  const int g = lane >> 3, c8 = lane & 7;
+  double M = 0.0, SX = 0.0, SY = 0.0, S2 = 0.0;
+#pragma unroll 1
+  for (int q = 0; q < VG_CHUNK / 4; ++q) {
+    const int lo = __shfl_sync(0xffffffffu, lo_l, 4 * q + g), hi = __shfl_sync(0xffffffffu, hi_l, 4 * q + g);
+    int qlo = hi > lo ? lo : 0x7fffffff, qhi = hi > lo ? hi : 0;
+    qlo = min(qlo, __shfl_xor_sync(0xffffffffu, qlo, 8)), qhi = max(qhi, __shfl_xor_sync(0xffffffffu, qhi, 8));
+    qlo = min(qlo, __shfl_xor_sync(0xffffffffu, qlo, 16)), qhi = max(qhi, __shfl_xor_sync(0xffffffffu, qhi, 16));
+    if (qhi <= qlo) continue;  // warp-uniform
+    const int row = rbase + 4 * q + g;
+    // pass j covers columns cb0 + 32 j ..; this lane's cells: col0 + 32 j .. + 3
+    const int cb0 = qlo & ~31, npass = (qhi - cb0 + 31) >> 5;
+    const int col0 = cb0 + 4 * c8;
+    const float4 *p4 = reinterpret_cast<const float4 *>(world + (size_t)row * N + col0);
+    const uint32_t *pw = SRC == SRC_EXPLORED ? plane + (size_t)row * d.NW + (cb0 >> 5) : nullptr;
+    int *lrow = LABELS && labels ? labels + (size_t)row * N + col0 : nullptr;
+    const int A = lo - col0, B = hi - col0;  // the interval relative to the lane's first cell
+    // passes jf0 .. jf1 lie fully inside [A, B); at most the passes holding A and B are partial
+    const int jf0 = A > 0 ? (A + 31) >> 5 : 0, jf1 = (B - 4) >> 5;
+    const int ja = A >> 5, jb = B >> 5;
+    const unsigned na = (A > 0 && hi > lo) ? vg_keep4(32 * ja, A, B) : 0u, nb = (B > 0 && hi > lo) ? vg_keep4(32 * jb, A, B) : 0u;
+    double y0 = (double)col0 + 0.5;
+    double rs = 0.0, rsy = 0.0, rsyy = 0.0;
+#pragma unroll 1
+    for (int base = 0; base < npass; base += VG_U) {
+      // request the whole batch, then consume it: VG_U x 512 bytes in flight per warp
+      float4 w[VG_U];
+      // 4 keep bits per pass of the batch: nibbles [jf0 - base, jf1 - base] full, plus the partial ones
+      unsigned kl;
+      {
+        const int l4 = 4 * min(max(jf0 - base, 0), VG_U), h4 = 4 * min(max(jf1 - base + 1, 0), VG_U);
+        kl = h4 > l4 ? (unsigned)(((1ull << h4) - 1ull) & ~((1ull << l4) - 1ull)) : 0u;
+        if (ja >= base && ja < base + VG_U) kl |= na << (4 * (ja - base));
+        if (jb >= base && jb < base + VG_U) kl |= nb << (4 * (jb - base));
+      }
+      unsigned kp = kl;  // cells to add (kl: cells inside the interval, for the labels)
+      if (SRC == SRC_EXPLORED) {
+        uint32_t pwv[VG_U];
+#pragma unroll
+        for (int j = 0; j < VG_U; ++j) pwv[j] = ((kl >> (4 * j)) & 0xfu) ? __ldg(pw + base + j) : 0u;
+#pragma unroll
+        for (int j = 0; j < VG_U; ++j) kp &= ~(0xfu << (4 * j)) | (((pwv[j] >> (col0 & 31)) & 0xfu) << (4 * j));
+      }
+#pragma unroll
+      for (int j = 0; j < VG_U; ++j) {
+        if ((kp >> (4 * j)) & 0xfu) w[j] = __ldg(p4 + 8 * (base + j));
+      }
+#pragma unroll
+      for (int j = 0; j < VG_U; ++j) {
+        if (base + j >= npass) break;  // warp-uniform
+        const unsigned keep = (kp >> (4 * j)) & 0xfu;
+        if (LABELS) {
+          if (lrow) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if ((kl >> (4 * j + i)) & 1u) lrow[32 * (base + j) + i] = k;
+          }
+        }
+        float4 x;  // (w[j] is only defined where keep has a bit)
+        x.x = (keep & 1u) ? w[j].x : 0.f, x.y = (keep & 2u) ? w[j].y : 0.f;
+        x.z = (keep & 4u) ? w[j].z : 0.f, x.w = (keep & 8u) ? w[j].w : 0.f;
+        const double v0 = (double)x.x, v1 = (double)x.y, v2 = (double)x.z, v3 = (double)x.w;
+        // sums over the four cells with y = y0 + i
+        const double s = (v0 + v1) + (v2 + v3);
+        const double t = fma(3.0, v3, fma(2.0, v2, v1));   // sum i v_i
+        const double u = fma(9.0, v3, fma(4.0, v2, v1));   // sum i^2 v_i
+        rs += s;
+        rsy += fma(y0, s, t);
+        rsyy += fma(y0 * y0, s, fma(y0 + y0, t, u));
+        y0 += 32.0;
+      }
+    }
+    const double x = (double)row + 0.5;
+    M += rs;
+    SX = fma(x, rs, SX);
+    SY += rsy;
+    S2 += fma(x * x, rs, rsyy);
+  }
+  const Sum4 tot = reduce4(M, SX, SY, S2);
+  if (lane == 0) emit(a.sums, e, d.R, k, tot.m, tot.sx, tot.sy, tot.s2);
+}
+
+// ---- flagged rows: the stated rule per cell --------------------------------------------------------
+// items = flagged (environment, row) pairs listed by k_vg_partition, each split in 256-column pieces;
+// a fixed grid strides over them.  One cell per thread per piece: 32 x R exact distances per warp.
+template <int SRC, bool LABELS>
+__global__ void __launch_bounds__(256) k_vg_fixup(VgArgs a) {
+  const EnvDev &d = a.d;
+  const int N = d.N, R = d.R;
+  const int nflag = *a.nflag;
+  const int pieces = (N + 255) / 256;
+  for (int item = blockIdx.x; item < nflag * pieces; item += gridDim.x) {
+    const int entry = a.flag_list[item / pieces], piece = item - (item / pieces) * pieces;
+    const int e = entry / N, row = entry - e * N;
+    const int col = piece * 256 + threadIdx.x;
+    const double *pos = d.pos_g + (size_t)e * R * 2;
+    const float *world = d.world + (size_t)e * N * N;
+    const uint32_t *plane = SRC == SRC_EXPLORED ? d.sysb + ((size_t)e * 2) * plane_words(d) : nullptr;
+    int *labels = (LABELS && a.labels) ? a.labels + (size_t)e * N * N : nullptr;
+    if (col >= N) continue;
+    const double res = d.res, cx = cell_centre(row, res), cy = cell_centre(col, res);
+    int best = 0;
+    double bd = d2_exact(cx, cy, pos[0], pos[1]);
+    for (int k = 1; k < R; ++k) {
+      const double dd = d2_exact(cx, cy, pos[2 * k], pos[2 * k + 1]);
+      if (dd < bd) bd = dd, best = k;
+    }
+    if (labels) labels[(size_t)row * N + col] = best;
+    float v = 0.f;
+    if (SRC == SRC_WORLD || plane_bit(plane, d.NW, row, col)) v = __ldg(world + (size_t)row * N + col);
+    if (v == 0.f) continue;
+    const double dv = (double)v, xd = (double)row + 0.5, yd = (double)col + 0.5;
+    emit(a.sums, e, R, best, dv, xd * dv, yd * dv, (xd * xd + yd * yd) * dv);
+  }
+}
+
+}  // namespace ccb

@@ -1,0 +1,90 @@
+"""Site-ordered global Voronoi (csrc/vglobal.cuh: row partition -> interval streaming -> exact rule on
+flagged rows) against the brute-force oracle and against the tile-ordered kernel (csrc/voronoi.cuh),
+on random, clustered and lattice site sets (the latter put bisectors through cell centres and along
+rows/columns: every such row must be flagged and resolved by the stated rule)."""
+import numpy as np
+import pytest
+
+from conftest import random_world
+
+pytestmark = pytest.mark.gpu
+
+
+def _sites(kind, N, R, rng):
+    if kind == "random":
+        return rng.uniform(1e-4, N - 1e-4, (R, 2))
+    if kind == "cluster":  # many near-degenerate vertices, tiny py differences
+        return np.concatenate([rng.uniform(1, N - 1, (R // 2, 2)), rng.normal(N / 2, 3.0, (R - R // 2, 2)).clip(1, N - 1)])
+    if kind == "lattice":  # integer lattice: bisectors on cell centres, along rows and columns, 4-way vertices
+        g = int(np.ceil(np.sqrt(R)))
+        xs = (np.arange(g) + 0.5) * (N // g)
+        pts = np.array([[x, y] for x in xs for y in xs], np.float64)[:R]
+        return pts
+    if kind == "halfint":  # sites on cell centres with duplicates
+        pts = np.floor(rng.uniform(2, N - 2, (R, 2))) + 0.5
+        pts[1] = pts[0]
+        pts[3, 1] = pts[2, 1]  # equal py, different px
+        pts[5, 0] = pts[4, 0]  # equal px, different py
+        return pts
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("generic", [0, 1])
+@pytest.mark.parametrize("kind,N,R,seed", [("random", 1024, 32, 0), ("random", 512, 64, 1), ("cluster", 256, 48, 2),
+                                           ("lattice", 256, 36, 3), ("halfint", 512, 24, 4), ("random", 300, 2, 5),
+                                           ("cluster", 1024, 64, 6)])
+def test_labels_bit_exact_and_moments(monkeypatch, generic, kind, N, R, seed):
+    import coverage_control as cc
+    from oracle import oracle as orc
+
+    monkeypatch.setenv("CCB_VG_GENERIC", str(generic))
+    rng = np.random.default_rng(seed)
+    pos = _sites(kind, N, R, rng)
+    p = cc.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    p.pNumRobots = R
+    wm = rng.random((N, N)).astype(np.float32)
+    env = cc.CoverageSystem(p, cc.WorldIDF(p, wm), cc.PointVector(pos))
+    labels = env.voronoi_labels(0)[0]
+    ref_labels, ref_sums = orc.voronoi_bruteforce(pos, wm)
+    bad = np.argwhere(labels != ref_labels)
+    assert len(bad) == 0, f"{len(bad)} labels differ, first at {bad[:5].tolist()}"
+    cells = env.GetVoronoiCells()
+    assert np.allclose([c.mass for c in cells], ref_sums[:, 0], rtol=1e-9, atol=1e-9)
+    assert env.GetObjectiveValue() == pytest.approx(ref_sums[:, 3].sum(), rel=1e-9)
+
+
+def test_explored_source_matches_tile_kernel(monkeypatch):
+    """CentralizedCVT (explored-IDF map): both kernels, same goals, step after step."""
+    import coverage_control as cc
+    from coveragecontrol_b200 import BatchedCoverageSystem, BatchedCVT
+
+    N, R, E = 512, 20, 3
+    p = cc.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    p.pNumRobots = R
+    p.pSensorSize = 48
+    rng = np.random.default_rng(9)
+    worlds = [rng.random((N, N)).astype(np.float32) for _ in range(E)]
+    pos = rng.uniform(1, N - 1, (E, R, 2))
+    runs = []
+    for generic in (0, 1):
+        monkeypatch.setenv("CCB_VG_GENERIC", str(generic))
+        env = BatchedCoverageSystem(p, E, R)
+        for e in range(E):
+            env.set_world(e, worlds[e])
+        env.reset(pos)
+        ctrl = BatchedCVT(env, 1)
+        trace = []
+        for _ in range(6):
+            ctrl.compute_actions()
+            trace.append(ctrl.goals().copy())
+            env.step_actions(ctrl.actions())
+        trace.append(env.voronoi_labels(1))
+        runs.append(trace)
+    for a, b in zip(runs[0][:-1], runs[1][:-1]):
+        assert np.allclose(a, b, rtol=1e-11, atol=1e-9)
+    la, lb = runs[0][-1], runs[1][-1]
+    assert (la >= 0).all()  # the site-ordered kernel labels every cell
+    seen = lb >= 0          # the tile-ordered kernel skips regions without an explored cell
+    assert seen.any() and np.array_equal(la[seen], lb[seen])
