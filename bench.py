@@ -263,8 +263,8 @@ def main():
     idf_ms = float(np.median([s.elapsed_time(t) for s, t in idf_evt[2:]])) if len(idf_evt) > 2 else None
 
     def device_step():
-        ctrl.rollout(1, True, obj_dev.data_ptr())
-        _lib.check(lib.ccb_env_cnn_input_dev(batch._h, CNN, 1, obs.data_ptr()))
+        # one call: ComputeActions, StepActions, then GetObjectiveValue and get_maps side by side (two streams)
+        ctrl.rollout_obs(1, True, obj_dev.data_ptr(), CNN, True, obs.data_ptr())
 
     def barrier():
         if dist is not None:
@@ -308,8 +308,9 @@ def main():
         _lib.check(lib.ccb_ctrl_get_actions(ctrl._h, host_actions.ctypes.data_as(C.POINTER(C.c_double))))
         bad = C.c_int(-1)
         _lib.check(lib.ccb_env_step_actions(batch._h, host_actions.ctypes.data_as(C.POINTER(C.c_double)), C.byref(bad)))
-        _lib.check(lib.ccb_env_objective(batch._h, host_obj.ctypes.data_as(C.POINTER(C.c_double))))
+        # the observation is launched first: the objective chain runs beside it on the library's second stream
         _lib.check(lib.ccb_env_cnn_input_dev(batch._h, CNN, 1, obs.data_ptr()))
+        _lib.check(lib.ccb_env_objective(batch._h, host_obj.ctypes.data_as(C.POINTER(C.c_double))))
 
     ms_e2e, _ = timed(e2e_step, args.steps, args.warmup)
     e2e_value = world * E * args.steps / (ms_e2e * 1e-3)

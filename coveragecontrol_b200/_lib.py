@@ -111,6 +111,7 @@ SIGNATURES = {
     "ccb_ctrl_get_goals": (C.c_int, [C.c_void_p, c_double_p]),
     "ccb_ctrl_is_converged": (C.c_int, [C.c_void_p, c_int_p]),
     "ccb_ctrl_rollout": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ccb_ctrl_rollout_obs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "ccb_ctrl_actions_dev": (C.c_void_p, [C.c_void_p]),
     "ccb_bench_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ccb_kernel_launch_count": (C.c_uint64, []),

@@ -1179,5 +1179,13 @@ class BatchedCVT(_CVT):
         _lib.check(_lib.load().ccb_ctrl_rollout(self._h, int(steps), int(with_objective), objective_dev_ptr or None))
         self._env._invalidate()
 
+    def rollout_obs(self, steps: int, with_objective: bool, objective_dev_ptr: int, cnn_size: int, use_comm: bool,
+                    obs_dev_ptr: int, obs_step_stride: int = 0) -> None:
+        """``rollout`` that also writes the LPAC observation (coverage_env_utils.py:227-277 get_maps) of every step
+        to ``obs_dev_ptr + s * obs_step_stride`` floats; objective chain and observation kernels overlap."""
+        _lib.check(_lib.load().ccb_ctrl_rollout_obs(self._h, int(steps), int(with_objective), objective_dev_ptr or None,
+                                                    int(cnn_size), int(use_comm), obs_dev_ptr or None, int(obs_step_stride)))
+        self._env._invalidate()
+
     def actions_device_ptr(self) -> int:
         return int(_lib.load().ccb_ctrl_actions_dev(self._h))

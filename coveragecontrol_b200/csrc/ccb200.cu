@@ -388,12 +388,41 @@ struct ccb_env {
   bool initialised = false;
   std::map<int, ResizeTab> resize;
   int vor_rpw_override = 0;
+  // second stream: the objective chain (global Voronoi -> finalise -> sum) reads only positions and the
+  // world map, so it runs beside the observation kernels and the next step's window Voronoi.
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_state = nullptr;  // recorded on `stream` after every change of positions / maps
+  cudaEvent_t ev_aux = nullptr;    // recorded on `aux` after the last chain launched there
+  cudaEvent_t ev_cells = nullptr;  // recorded on `stream` after cells were (re)computed there
+  bool no_aux = false;             // CCB_NO_AUX: keep everything on `stream` (debugging)
+  bool aux_pending = false;        // `stream` has not yet waited for ev_aux
   uint32_t *d_vg_table = nullptr;  // [E][R][N] row intervals of the site-ordered global Voronoi (vglobal.cuh)
   int *d_vg_flag = nullptr;     // [1 + E*N]: count, then the flagged rows
   int *d_vg_span = nullptr;     // [E][R][2] row span of every site
   bool vg_generic = false;      // CCB_VG_GENERIC: force the tile-ordered kernel (tests)
   bool vw_generic = false;      // CCB_VW_GENERIC: force the generic window kernel (tests)
   bool band_mode = false;       // this env holds one row band of a world tiled over several GPUs
+};
+
+// every change of the robot state or the maps goes through here: new version + fork point for `aux`
+static int state_changed(ccb_env *env) {
+  env->pos_version++;
+  CCB_CUDA(cudaEventRecord(env->ev_state, env->stream));
+  return 0;
+}
+// make `stream` wait for whatever was launched on `aux` (no-op when nothing is pending)
+static int join_aux(ccb_env *env) {
+  if (env->aux_pending) {
+    CCB_CUDA(cudaStreamWaitEvent(env->stream, env->ev_aux, 0));
+    env->aux_pending = false;
+  }
+  return 0;
+}
+struct AuxScope {  // launches issued through env->stream go to `aux` while this is alive
+  ccb_env *env;
+  cudaStream_t saved;
+  explicit AuxScope(ccb_env *e) : env(e), saved(e->stream) { e->stream = e->aux; }
+  ~AuxScope() { env->stream = saved; }
 };
 
 // rows per warp region: as large as keeps >= ~3 CTAs per SM in flight over the whole launch
@@ -425,6 +454,7 @@ static int run_voronoi(ccb_env *env, const VorArgs &a, dim3 grid) {
 static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *labels = nullptr, int row0 = 0, int row1 = -1) {
   const EnvDev &d = env->d;
   if (row1 < 0) row1 = d.N;
+  if (env->stream != env->aux && join_aux(env)) return 1;  // the partition tables are shared with `aux`
   CCB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * d.E * d.R, env->stream));
   if (row1 <= row0) return 0;
   if (d.R <= VG_MAXR && (d.N & 3) == 0 && d.N < 65536 && !env->vg_generic) {
@@ -505,6 +535,7 @@ static int launch_finalize(ccb_env *env, const double *sums, CellsOut out, int w
 
 static int ensure_cells(ccb_env *env, bool want_polys) {
   if (!env->initialised) return fail("environment has no robot positions yet (call ccb_env_reset)");
+  if (env->stream != env->aux && join_aux(env)) return 1;  // the cells may still be in the making on `aux`
   if (env->cells_version != env->pos_version) {
     if (env->band_mode)
       return fail("row-band mode: all-reduce the partials and call ccb_env_finalize_from_partials_dev first");
@@ -516,6 +547,7 @@ static int ensure_cells(ccb_env *env, bool want_polys) {
     if (launch_finalize(env, env->d_sums, env->cells, 1)) return 1;
     env->cells_have_polys = true;
   }
+  if (env->stream != env->aux) CCB_CUDA(cudaEventRecord(env->ev_cells, env->stream));
   return 0;
 }
 
@@ -566,6 +598,12 @@ static int env_alloc(ccb_env *env) {
   if (d.xseenb) CCB_CUDA(cudaMemsetAsync(d.xseenb, 0, sizeof(uint32_t) * pw * er, env->stream));
   CCB_CUDA(cudaMemsetAsync(d.sysb, 0, sizeof(uint32_t) * pw * 2 * d.E, env->stream));
   CCB_CUDA(cudaMemsetAsync(d.status, 0, sizeof(int) * d.E, env->stream));
+  CCB_CUDA(cudaStreamCreateWithFlags(&env->aux, cudaStreamNonBlocking));
+  CCB_CUDA(cudaEventCreateWithFlags(&env->ev_state, cudaEventDisableTiming));
+  CCB_CUDA(cudaEventCreateWithFlags(&env->ev_aux, cudaEventDisableTiming));
+  CCB_CUDA(cudaEventCreateWithFlags(&env->ev_cells, cudaEventDisableTiming));
+  CCB_CUDA(cudaEventRecord(env->ev_state, env->stream));
+  CCB_CUDA(cudaEventRecord(env->ev_cells, env->stream));
   return 0;
 }
 
@@ -604,6 +642,7 @@ extern "C" ccb_env *ccb_env_create(const ccb_params *p, int num_envs, int num_ro
   if (const char *s = getenv("CCB_VOR_RPW")) env->vor_rpw_override = atoi(s);
   if (const char *s = getenv("CCB_VW_GENERIC")) env->vw_generic = atoi(s) != 0;
   if (const char *s = getenv("CCB_VG_GENERIC")) env->vg_generic = atoi(s) != 0;
+  if (const char *s = getenv("CCB_NO_AUX")) env->no_aux = atoi(s) != 0;
   if (env_alloc(env.get())) {
     ccb_env_destroy(env.release());
     return nullptr;
@@ -615,6 +654,10 @@ extern "C" void ccb_env_destroy(ccb_env *env) {
   if (!env) return;
   cudaSetDevice(env->device);
   cudaStreamSynchronize(env->stream);
+  if (env->aux) cudaStreamSynchronize(env->aux), cudaStreamDestroy(env->aux);
+  if (env->ev_state) cudaEventDestroy(env->ev_state);
+  if (env->ev_aux) cudaEventDestroy(env->ev_aux);
+  if (env->ev_cells) cudaEventDestroy(env->ev_cells);
   EnvDev &d = env->d;
   cudaFree(d.world), cudaFree(d.seenb), cudaFree(d.xseenb), cudaFree(d.sysb);
   cudaFree(d.pos_g), cudaFree(d.pos_s), cudaFree(d.pos_l);
@@ -647,9 +690,10 @@ static int check_robot(const ccb_env *env, int r) {
 extern "C" int ccb_env_set_world_dev(ccb_env *env, int e, const float *map_dev) {
   if (check_env_index(env, e)) return 1;
   CCB_CUDA(cudaSetDevice(env->device));
+  if (join_aux(env)) return 1;
   size_t nn = cell_count(env->d);
   CCB_CUDA(cudaMemcpyAsync(env->d.world + nn * e, map_dev, nn * sizeof(float), cudaMemcpyDeviceToDevice, env->stream));
-  env->pos_version++;
+  if (state_changed(env)) return 1;
   return 0;
 }
 extern "C" int ccb_env_set_world_idf(ccb_env *env, int e, const ccb_idf *idf) {
@@ -660,10 +704,11 @@ extern "C" int ccb_env_set_world_idf(ccb_env *env, int e, const ccb_idf *idf) {
 extern "C" int ccb_env_set_world_host(ccb_env *env, int e, const float *map) {
   if (check_env_index(env, e)) return 1;
   CCB_CUDA(cudaSetDevice(env->device));
+  if (join_aux(env)) return 1;
   size_t nn = cell_count(env->d);
   CCB_CUDA(cudaMemcpyAsync(env->d.world + nn * e, map, nn * sizeof(float), cudaMemcpyHostToDevice, env->stream));
   CCB_CUDA(cudaStreamSynchronize(env->stream));
-  env->pos_version++;
+  if (state_changed(env)) return 1;
   return 0;
 }
 
@@ -687,6 +732,7 @@ static int stage_to_device(ccb_env *env, const double *host, size_t count, doubl
 
 extern "C" int ccb_env_reset(ccb_env *env, const double *positions) {
   CCB_CUDA(cudaSetDevice(env->device));
+  if (join_aux(env)) return 1;
   const EnvDev &d = env->d;
   const size_t pw = plane_words(d), er = (size_t)d.E * d.R;
   if (stage_to_device(env, positions, 2 * er, env->d_stage)) return 1;
@@ -698,12 +744,13 @@ extern "C" int ccb_env_reset(ccb_env *env, const double *positions) {
   CCB_LAUNCH_CHECK();
   if (launch_mark(env, -1, -1, 1, 1)) return 1;
   env->initialised = true;
-  env->pos_version++;
+  if (state_changed(env)) return 1;
   return 0;
 }
 
 extern "C" int ccb_env_step_actions(ccb_env *env, const double *actions, int *bad_env) {
   CCB_CUDA(cudaSetDevice(env->device));
+  if (join_aux(env)) return 1;
   const EnvDev &d = env->d;
   const size_t er = (size_t)d.E * d.R;
   if (bad_env) *bad_env = -1;
@@ -711,18 +758,19 @@ extern "C" int ccb_env_step_actions(ccb_env *env, const double *actions, int *ba
   k_move<<<(int)((er + 255) / 256), 256, 0, env->stream>>>(d, env->d_stage, nullptr);
   CCB_LAUNCH_CHECK();
   if (launch_mark(env, -1, -1, 1, 1)) return 1;
-  env->pos_version++;
+  if (state_changed(env)) return 1;
   return 0;
 }
 
 // device-resident variant used by the roll-out (actions already on the device)
 static int step_actions_dev(ccb_env *env, const double *actions_dev) {
+  if (join_aux(env)) return 1;
   const EnvDev &d = env->d;
   const size_t er = (size_t)d.E * d.R;
   k_move<<<(int)((er + 255) / 256), 256, 0, env->stream>>>(d, actions_dev, nullptr);
   CCB_LAUNCH_CHECK();
   if (launch_mark(env, -1, -1, 1, 1)) return 1;
-  env->pos_version++;
+  if (state_changed(env)) return 1;
   return 0;
 }
 
@@ -749,6 +797,7 @@ __global__ void k_post_history(EnvDev d, int e, int robot) {
 extern "C" int ccb_env_step_control(ccb_env *env, int e, int robot, double dir_x, double dir_y, double speed) {
   if (check_env_index(env, e) || check_robot(env, robot)) return 1;
   CCB_CUDA(cudaSetDevice(env->device));
+  if (join_aux(env)) return 1;
   const EnvDev &d = env->d;
   double sp = speed;
   if (sp > d.max_speed) sp = d.max_speed;
@@ -762,7 +811,7 @@ extern "C" int ccb_env_step_control(ccb_env *env, int e, int robot, double dir_x
   if (launch_mark(env, e, -1, 0, 1)) return 1;
   k_post_history<<<(d.R + 127) / 128, 128, 0, env->stream>>>(d, e, -1);
   CCB_LAUNCH_CHECK();
-  env->pos_version++;
+  if (state_changed(env)) return 1;
   return 0;
 }
 
@@ -770,6 +819,7 @@ extern "C" int ccb_env_set_positions(ccb_env *env, int e, int robot, int local, 
   if (check_env_index(env, e)) return 1;
   if (robot >= 0 && check_robot(env, robot)) return 1;
   CCB_CUDA(cudaSetDevice(env->device));
+  if (join_aux(env)) return 1;
   const EnvDev &d = env->d;
   const int count = robot < 0 ? d.R : 1;
   if (stage_to_device(env, positions, 2 * (size_t)count, env->d_stage)) return 1;
@@ -777,7 +827,7 @@ extern "C" int ccb_env_set_positions(ccb_env *env, int e, int robot, int local, 
   k_set_positions<<<(count + 127) / 128, 128, 0, env->stream>>>(d, e, robot, local, env->d_stage, 1);
   CCB_LAUNCH_CHECK();
   if (launch_mark(env, e, robot, 1, 1)) return 1;
-  env->pos_version++;
+  if (state_changed(env)) return 1;
   return 0;
 }
 
@@ -794,6 +844,7 @@ extern "C" int ccb_env_clear_robot_maps(ccb_env *env, int e) {
   // coverage_system.h:399-403 -> robot_model.h:180-196: refill, then re-sense at the current position
   if (check_env_index(env, e)) return 1;
   CCB_CUDA(cudaSetDevice(env->device));
+  if (join_aux(env)) return 1;
   const EnvDev &d = env->d;
   const size_t pw = plane_words(d);
   CCB_CUDA(cudaMemsetAsync(robot_plane(d, d.seenb, e, 0), 0, sizeof(uint32_t) * pw * d.R, env->stream));
@@ -806,6 +857,7 @@ extern "C" int ccb_env_clear_explored_idf(ccb_env *env, int e) {
   // coverage_system.h:405-408: explored_idf_map_ back to zero, the exploration map is kept
   if (check_env_index(env, e)) return 1;
   CCB_CUDA(cudaSetDevice(env->device));
+  if (join_aux(env)) return 1;
   CCB_CUDA(cudaMemsetAsync(sys_plane(env->d, e, 0), 0, sizeof(uint32_t) * plane_words(env->d), env->stream));
   return 0;
 }
@@ -1034,11 +1086,13 @@ extern "C" int ccb_env_voronoi_partials_dev(ccb_env *env, int src, int row0, int
 extern "C" int ccb_env_finalize_from_partials_dev(ccb_env *env, const double *sums_dev) {
   if (!env->initialised) return fail("environment has no robot positions yet");
   CCB_CUDA(cudaSetDevice(env->device));
+  if (join_aux(env)) return 1;
   if (sums_dev != env->d_sums)
     CCB_CUDA(cudaMemcpyAsync(env->d_sums, sums_dev, sizeof(double) * 4 * env->E * env->R, cudaMemcpyDeviceToDevice, env->stream));
   if (launch_finalize(env, env->d_sums, env->cells, 0)) return 1;
   env->cells_version = env->pos_version;
   env->cells_have_polys = false;
+  CCB_CUDA(cudaEventRecord(env->ev_cells, env->stream));
   return 0;
 }
 
@@ -1061,11 +1115,29 @@ static int objective_dev(ccb_env *env, double *out_dev) {
   return 0;
 }
 
+// The objective chain on `aux`: it starts as soon as the last state change is done and runs beside
+// whatever `stream` does next (observation kernels, the next step's window Voronoi).
+static int objective_aux(ccb_env *env, double *out_dev) {
+  if (env->no_aux) return objective_dev(env, out_dev);
+  CCB_CUDA(cudaStreamWaitEvent(env->aux, env->ev_state, 0));
+  CCB_CUDA(cudaStreamWaitEvent(env->aux, env->ev_cells, 0));
+  int rc;
+  {
+    AuxScope scope(env);
+    rc = objective_dev(env, out_dev);
+  }
+  if (rc) return rc;
+  CCB_CUDA(cudaEventRecord(env->ev_aux, env->aux));
+  env->aux_pending = true;
+  return 0;
+}
+
 extern "C" int ccb_env_objective(ccb_env *env, double *out) {
   CCB_CUDA(cudaSetDevice(env->device));
-  if (objective_dev(env, env->d_objective)) return 1;
-  CCB_CUDA(cudaMemcpyAsync(env->h_pin, env->d_objective, sizeof(double) * env->E, cudaMemcpyDeviceToHost, env->stream));
-  CCB_CUDA(cudaStreamSynchronize(env->stream));
+  if (objective_aux(env, env->d_objective)) return 1;
+  cudaStream_t st = env->no_aux ? env->stream : env->aux;
+  CCB_CUDA(cudaMemcpyAsync(env->h_pin, env->d_objective, sizeof(double) * env->E, cudaMemcpyDeviceToHost, st));
+  CCB_CUDA(cudaStreamSynchronize(st));
   memcpy(out, env->h_pin, sizeof(double) * env->E);
   return 0;
 }
@@ -1114,6 +1186,7 @@ extern "C" int ccb_env_check_oscillation(ccb_env *env, int e, int robot, int *ou
 
 extern "C" int ccb_env_sync(ccb_env *env) {
   CCB_CUDA(cudaSetDevice(env->device));
+  CCB_CUDA(cudaStreamSynchronize(env->aux));
   CCB_CUDA(cudaStreamSynchronize(env->stream));
   return 0;
 }
@@ -1250,18 +1323,24 @@ extern "C" int ccb_ctrl_is_converged(ccb_ctrl *c, int *out) {
 }
 extern "C" const double *ccb_ctrl_actions_dev(const ccb_ctrl *c) { return c->d_actions; }
 
-extern "C" int ccb_ctrl_rollout(ccb_ctrl *c, int steps, int with_objective, double *objective_dev_out) {
+extern "C" int ccb_ctrl_rollout_obs(ccb_ctrl *c, int steps, int with_objective, double *objective_dev_out, int C,
+                                    int use_comm, float *obs_dev, size_t obs_step_stride) {
   CCB_CUDA(cudaSetDevice(c->env->device));
   ccb_env *env = c->env;
   for (int s = 0; s < steps; ++s) {
     if (ctrl_compute_actions_async(c)) return 1;
     if (step_actions_dev(env, c->d_actions)) return 1;
-    if (with_objective) {
+    if (with_objective) {  // on `aux`, beside the observation below and the next step's controller
       double *dst = objective_dev_out ? objective_dev_out + (size_t)s * env->E : env->d_objective;
-      if (objective_dev(env, dst)) return 1;
+      if (objective_aux(env, dst)) return 1;
     }
+    if (obs_dev && ccb_env_cnn_input_dev(env, C, use_comm, obs_dev + (size_t)s * obs_step_stride)) return 1;
   }
-  return 0;
+  return join_aux(env);  // everything this call produced is ordered on the env stream when it returns
+}
+
+extern "C" int ccb_ctrl_rollout(ccb_ctrl *c, int steps, int with_objective, double *objective_dev_out) {
+  return ccb_ctrl_rollout_obs(c, steps, with_objective, objective_dev_out, 0, 0, nullptr, 0);
 }
 
 // =================================================================================================

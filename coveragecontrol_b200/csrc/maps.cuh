@@ -195,6 +195,10 @@ __device__ inline int clip_cell(const double *sx, const double *sy, int n, int k
     const double nx = jx - kx, ny = jy - ky;
     if (nx == 0 && ny == 0) continue;
     const double c = ((jx * jx + jy * jy) - (kx * kx + ky * ky)) / 2.;
+    // most bisectors do not reach the cell: when every vertex is inside, the polygon stays as it is
+    bool cuts = false;
+    for (int v = 0; v < na; ++v) cuts = cuts || (nx * poly[v][0] + ny * poly[v][1] - c > 0);
+    if (!cuts) continue;
     int nb = 0;
     for (int v = 0; v < na; ++v) {
       int u = (v + 1 == na) ? 0 : v + 1;

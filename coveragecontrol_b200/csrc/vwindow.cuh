@@ -260,8 +260,16 @@ __global__ void __launch_bounds__(VW_THREADS, 3) k_voronoi_window(EnvDev d, doub
   }
   __syncthreads();
   {
+    // rows with work, in ascending order (a fixed order makes the fp64 sums reproducible run to run)
     const int a = tid;
-    if ((sh.flags[a >> 5] >> (a & 31)) & 1u) sh.act[atomicAdd(&sh.nact, 1)] = a;
+    int before = 0;
+#pragma unroll
+    for (int wq = 0; wq < VW_MAXL / 32; ++wq) {
+      const uint32_t f = sh.flags[wq];
+      before += wq < (a >> 5) ? __popc(f) : (wq == (a >> 5) ? __popc(f & ((1u << (a & 31)) - 1u)) : 0);
+    }
+    if ((sh.flags[a >> 5] >> (a & 31)) & 1u) sh.act[before] = a;
+    if (a == VW_MAXL - 1) sh.nact = before + ((sh.flags[a >> 5] >> (a & 31)) & 1u);
   }
   __syncthreads();
 

@@ -200,6 +200,12 @@ int ccb_ctrl_is_converged(ccb_ctrl *c, int *out /* E */);
  * environment with no host round trip; with_objective != 0 adds GetObjectiveValue per step and
  * writes steps x E doubles to objective_dev (may be NULL). */
 int ccb_ctrl_rollout(ccb_ctrl *c, int steps, int with_objective, double *objective_dev);
+/* the same roll-out that also produces the LPAC observation (ccb_env_cnn_input_dev) after every step:
+ * obs_dev + s * obs_step_stride floats receives step s (stride 0: only the last step is kept).  The
+ * objective chain and the observation kernels of a step run on two streams side by side; everything is
+ * ordered on the env stream when the call returns. */
+int ccb_ctrl_rollout_obs(ccb_ctrl *c, int steps, int with_objective, double *objective_dev, int C, int use_comm,
+                         float *obs_dev, size_t obs_step_stride);
 const double *ccb_ctrl_actions_dev(const ccb_ctrl *c);
 
 /* ---- profiling hooks (bench.py) ------------------------------------------------- */
