@@ -316,14 +316,17 @@ def main():
     e2e_value = world * E * args.steps / (ms_e2e * 1e-3)
 
     # ---- per-kernel durations (same data, CUDA events on the launching stream) ----------------------
+    # algorithmic bytes per launch: SURVEY.md 8(d) per-environment figure x E
     kernels = {}
     cells = N_WORLD * N_WORLD
     algo = {
-        "voronoi_window(decentralized)": (2, 4.0 * N_ROBOTS * LOCAL * LOCAL * E),
-        "voronoi_global(objective)": (0, 4.0 * cells * E),
-        "cnn_input": (4, (4.0 * N_ROBOTS * LOCAL * LOCAL + 16.0 * N_ROBOTS * CNN * CNN) * E),
-        "mark_windows": (3, 12.0 * N_ROBOTS * SENSOR * SENSOR * E),
-        "finalize_cells": (5, 32.0 * N_ROBOTS * E),
+        "voronoi_global(partition+reduce+fixup)": (0, 4.0 * cells * E),
+        "k_vg_reduce": (6, 4.0 * cells * E),
+        "k_vg_partition": (7, 4.0 * N_ROBOTS * N_WORLD * E),
+        "k_voronoi_window": (2, 4.0 * N_ROBOTS * LOCAL * LOCAL * E),
+        "k_cnn_fused8(+k_comm_maps)": (4, (4.0 * N_ROBOTS * LOCAL * LOCAL + 16.0 * N_ROBOTS * CNN * CNN) * E),
+        "k_mark_windows": (3, 12.0 * N_ROBOTS * SENSOR * SENSOR * E),
+        "k_finalize_cells": (5, 32.0 * N_ROBOTS * E),
     }
     for name, (which, nbytes) in algo.items():
         iters = 10
@@ -331,10 +334,19 @@ def main():
         ms, _ = timed(fn, iters, 3)
         kernels[name] = {"ms": ms / iters, "algorithmic_bytes": nbytes, "gbs": nbytes / (ms / iters * 1e-3) / 1e9}
     peak, peak_src = measured_peak_gbs()
-    dom = max(("voronoi_window(decentralized)", "voronoi_global(objective)", "cnn_input"), key=lambda k: kernels[k]["ms"])
+    # the dominant single kernel of the step
+    dom = max(("k_vg_reduce", "k_voronoi_window", "k_cnn_fused8(+k_comm_maps)"), key=lambda k: kernels[k]["ms"])
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture
+        with open(tpath) as f:
+            t = json.load(f)
+        if dom in t["kernels"]:
+            traffic = t["kernels"][dom]["dram_bytes_per_env"] * E
+            traffic_src = t["source"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
-                "kernels": kernels}
+                "frac": kernels[dom]["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src, "kernels": kernels}
 
     # ---- single-environment latency (API-faithful, E = 1) and the C1 variant, reported as extras -----
     extras = {"idf_gen_ms_1024_32f_mode0": idf_ms}

@@ -399,7 +399,7 @@ struct ccb_env {
   uint32_t *d_vg_table = nullptr;  // [E][R][N] row intervals of the site-ordered global Voronoi (vglobal.cuh)
   int *d_vg_flag = nullptr;     // [1 + E*N]: count, then the flagged rows
   int *d_vg_span = nullptr;     // [E][R][2] row span of every site
-  bool vg_generic = false;      // CCB_VG_GENERIC: force the tile-ordered kernel (tests)
+  int vg_mode = -1;             // CCB_VG_GENERIC: 1 forces the tile-ordered kernel, 0 the site-ordered one (tests)
   bool vw_generic = false;      // CCB_VW_GENERIC: force the generic window kernel (tests)
   bool band_mode = false;       // this env holds one row band of a world tiled over several GPUs
 };
@@ -451,44 +451,60 @@ static int run_voronoi(ccb_env *env, const VorArgs &a, dim3 grid) {
 
 // Voronoi label + reduce over the full map of every environment; sums must be a [E][R][4] buffer.
 // row0/row1 restrict the pass to a row band (row1 < 0: the whole map).
-static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *labels = nullptr, int row0 = 0, int row1 = -1) {
+// stages: bit 0 row partition, bit 1 per-site reduce, bit 2 flagged-row fix-up (site-ordered path; the
+// profiling hook times the reduce alone on the tables of a previous full call)
+static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *labels = nullptr, int row0 = 0, int row1 = -1,
+                                 int stages = 7) {
   const EnvDev &d = env->d;
   if (row1 < 0) row1 = d.N;
   if (env->stream != env->aux && join_aux(env)) return 1;  // the partition tables are shared with `aux`
   CCB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * d.E * d.R, env->stream));
   if (row1 <= row0) return 0;
-  if (d.R <= VG_MAXR && (d.N & 3) == 0 && d.N < 65536 && !env->vg_generic) {
+  // The row partition is one sequential sweep per map row (~30 us whatever the batch): it pays once
+  // there are enough rows in the launch to fill the machine; small batches keep the tile-ordered kernel.
+  const bool site_ordered = env->vg_mode == 0 || (env->vg_mode < 0 && (long)d.E * (row1 - row0) >= 32L * 1024);
+  if (d.R <= VG_MAXR && (d.N & 3) == 0 && d.N < 65536 && site_ordered) {
     // site-ordered path: row partition -> per-site interval streaming -> exact rule on flagged rows
     if (!env->d_vg_table) {
       CCB_CUDA(cudaMalloc(&env->d_vg_table, sizeof(uint32_t) * (size_t)d.E * d.R * d.N));
       CCB_CUDA(cudaMalloc(&env->d_vg_flag, sizeof(int) * ((size_t)d.E * d.N + 1)));
       CCB_CUDA(cudaMalloc(&env->d_vg_span, sizeof(int) * 2 * (size_t)d.E * d.R));
     }
-    k_vg_init_span<<<(d.E * d.R + 255) / 256, 256, 0, env->stream>>>(env->d_vg_span, d.E * d.R);
-    CCB_LAUNCH_CHECK();
-    CCB_CUDA(cudaMemsetAsync(env->d_vg_flag, 0, sizeof(int), env->stream));
+    if (stages & 1) {
+      k_vg_init_span<<<(d.E * d.R + 255) / 256, 256, 0, env->stream>>>(env->d_vg_span, d.E * d.R);
+      CCB_LAUNCH_CHECK();
+    }
+    if (stages & 1) CCB_CUDA(cudaMemsetAsync(env->d_vg_flag, 0, sizeof(int), env->stream));
     VgArgs g;
     g.d = d, g.row0 = row0, g.row1 = row1, g.table = env->d_vg_table, g.nflag = env->d_vg_flag, g.flag_list = env->d_vg_flag + 1, g.span = env->d_vg_span, g.sums = sums, g.labels = labels;
     const int rows = row1 - row0;
-    k_vg_partition<<<dim3((rows + VG_PART_THREADS - 1) / VG_PART_THREADS, d.E), VG_PART_THREADS,
-                     sizeof(double) * d.R * d.R, env->stream>>>(g);
-    CCB_LAUNCH_CHECK();
+    if (stages & 1) {
+      k_vg_partition<<<dim3((rows + VG_PART_THREADS - 1) / VG_PART_THREADS, d.E), VG_PART_THREADS,
+                       sizeof(double) * d.R * d.R, env->stream>>>(g);
+      CCB_LAUNCH_CHECK();
+    }
     const int chunks = (rows + VG_CHUNK - 1) / VG_CHUNK;
     dim3 rgrid((chunks * d.R + VG_RED_WARPS - 1) / VG_RED_WARPS, d.E), fgrid(148 * 2);
-    if (src == SRC_WORLD) {
-      if (labels) k_vg_reduce<SRC_WORLD, true><<<rgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g);
-      else k_vg_reduce<SRC_WORLD, false><<<rgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g);
+    if (stages & 2) {
+      if (src == SRC_WORLD) {
+        if (labels) k_vg_reduce<SRC_WORLD, true><<<rgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g);
+        else k_vg_reduce<SRC_WORLD, false><<<rgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g);
+      } else {
+        if (labels) k_vg_reduce<SRC_EXPLORED, true><<<rgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g);
+        else k_vg_reduce<SRC_EXPLORED, false><<<rgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g);
+      }
       CCB_LAUNCH_CHECK();
-      if (labels) k_vg_fixup<SRC_WORLD, true><<<fgrid, 256, 0, env->stream>>>(g);
-      else k_vg_fixup<SRC_WORLD, false><<<fgrid, 256, 0, env->stream>>>(g);
-    } else {
-      if (labels) k_vg_reduce<SRC_EXPLORED, true><<<rgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g);
-      else k_vg_reduce<SRC_EXPLORED, false><<<rgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g);
-      CCB_LAUNCH_CHECK();
-      if (labels) k_vg_fixup<SRC_EXPLORED, true><<<fgrid, 256, 0, env->stream>>>(g);
-      else k_vg_fixup<SRC_EXPLORED, false><<<fgrid, 256, 0, env->stream>>>(g);
     }
-    CCB_LAUNCH_CHECK();
+    if (stages & 4) {
+      if (src == SRC_WORLD) {
+        if (labels) k_vg_fixup<SRC_WORLD, true><<<fgrid, 256, 0, env->stream>>>(g);
+        else k_vg_fixup<SRC_WORLD, false><<<fgrid, 256, 0, env->stream>>>(g);
+      } else {
+        if (labels) k_vg_fixup<SRC_EXPLORED, true><<<fgrid, 256, 0, env->stream>>>(g);
+        else k_vg_fixup<SRC_EXPLORED, false><<<fgrid, 256, 0, env->stream>>>(g);
+      }
+      CCB_LAUNCH_CHECK();
+    }
     return 0;
   }
   VorArgs a;
@@ -641,7 +657,7 @@ extern "C" ccb_env *ccb_env_create(const ccb_params *p, int num_envs, int num_ro
   d.comm_range = p->pCommunicationRange, d.max_speed = p->pMaxRobotSpeed, d.dt = p->pTimeStep;
   if (const char *s = getenv("CCB_VOR_RPW")) env->vor_rpw_override = atoi(s);
   if (const char *s = getenv("CCB_VW_GENERIC")) env->vw_generic = atoi(s) != 0;
-  if (const char *s = getenv("CCB_VG_GENERIC")) env->vg_generic = atoi(s) != 0;
+  if (const char *s = getenv("CCB_VG_GENERIC")) env->vg_mode = atoi(s) != 0 ? 1 : 0;
   if (const char *s = getenv("CCB_NO_AUX")) env->no_aux = atoi(s) != 0;
   if (env_alloc(env.get())) {
     ccb_env_destroy(env.release());
@@ -1360,6 +1376,8 @@ extern "C" int ccb_bench_kernel(ccb_env *env, int which, int iters, float *scrat
       case 3: if (launch_mark(env, -1, -1, 1, 1)) return 1; break;
       case 4: if (ccb_env_cnn_input_dev(env, 32, 1, scratch_dev)) return 1; break;
       case 5: if (launch_finalize(env, env->d_sums, env->cells, 0)) return 1; env->cells_version = 0; break;
+      case 6: if (launch_voronoi_global(env, SRC_WORLD, env->d_sums, nullptr, 0, -1, 2)) return 1; env->cells_version = 0; break;
+      case 7: if (launch_voronoi_global(env, SRC_WORLD, env->d_sums, nullptr, 0, -1, 1)) return 1; env->cells_version = 0; break;
       default: return fail("ccb_bench_kernel: unknown kernel id");
     }
   }

@@ -73,6 +73,20 @@ KEYS = [
     "sm__pipe_xu_cycles_active.avg.pct_of_peak_sustained_active",
     "smsp__thread_inst_executed_per_inst_executed.ratio",
 ]
+traffic = {}
+TRAFFIC_KEYS = {"k_vg_reduce": "k_vg_reduce", "k_vg_partition": "k_vg_partition", "k_voronoi_window": "k_voronoi_window",
+                "k_cnn_fused8": "k_cnn_fused8(+k_comm_maps)"}
+PROFILE_ENVS = 128  # scripts/gpu_evidence.sh profiles at the bench's batch size
+
+
+def _num(x):
+    return float(x.replace(",", "") or 0)
+
+
+def _bytes(value, unit):
+    return _num(value) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+
+
 for fn in sorted(os.listdir(G)):
     if not (fn.startswith(f"prof_{tag}_") and fn.endswith(".ncu-rep")):
         continue
@@ -84,6 +98,12 @@ for fn in sorted(os.listdir(G)):
     hdr, units = rws[0], rws[1]
     for r in rws[2:]:
         out.append(f"## ncu --set full: `{r[hdr.index('Kernel Name')][:80]}` ({fn})\n")
+        for short, key in TRAFFIC_KEYS.items():
+            if short in r[hdr.index("Kernel Name")]:
+                ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+                total = _bytes(r[ir], units[ir]) + _bytes(r[iw], units[iw])
+                traffic[key] = {"dram_bytes_per_launch": total, "envs": PROFILE_ENVS, "dram_bytes_per_env": total / PROFILE_ENVS,
+                                "duration_us_under_ncu": _num(r[hdr.index("gpu__time_duration.sum")]), "report": fn}
         out.append("| metric | value | unit |\n|---|---:|---|")
         for k in KEYS:
             if k in hdr:
@@ -97,6 +117,10 @@ for fn in sorted(os.listdir(G)):
                          capture_output=True, text=True).stdout
     out.append("```\n" + "\n".join(l[:170] for l in top.splitlines()) + "\n```\n")
 
+if traffic:
+    with open(os.path.join(P, "traffic.json"), "w") as f:
+        json.dump({"source": f"ncu --set full captures of scripts/gpu_evidence.sh {tag} (profiles/{tag}_summary.md)",
+                   "kernels": traffic}, f, indent=1)
 with open(os.path.join(P, f"{tag}_summary.md"), "w") as f:
     f.write("\n".join(out) + "\n")
 print("wrote", os.path.join(P, f"{tag}_summary.md"))

@@ -51,9 +51,12 @@ def test_idf_bands_equal_whole_map_bit_for_bit(N, bands):
     assert idf2.GetNormalizationFactor() == idf.GetNormalizationFactor()
 
 
+@pytest.mark.parametrize("vg", ["0", "1"])  # site-ordered / tile-ordered global Voronoi kernel
 @pytest.mark.parametrize("N,R,nb", [(1024, 32, 4), (512, 64, 3), (300, 7, 2)])
-def test_band_partials_sum_to_whole_map_moments(N, R, nb):
+def test_band_partials_sum_to_whole_map_moments(monkeypatch, N, R, nb, vg):
     import torch
+
+    monkeypatch.setenv("CCB_VG_GENERIC", vg)
 
     from coveragecontrol_b200 import _lib
     from coveragecontrol_b200.parallel import band_rows
