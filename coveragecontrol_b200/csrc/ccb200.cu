@@ -543,8 +543,8 @@ static int launch_voronoi_single(ccb_env *env, double *sums) {
 
 static int launch_finalize(ccb_env *env, const double *sums, CellsOut out, int want_polys) {
   const EnvDev &d = env->d;
-  int threads = std::min(256, ((d.R + 31) / 32) * 32);
-  k_finalize_cells<<<d.E, threads, 2 * d.R * sizeof(double), env->stream>>>(d, sums, out, want_polys);
+  const int warps = d.E * d.R;
+  k_finalize_cells<<<(warps + FIN_WARPS - 1) / FIN_WARPS, FIN_WARPS * 32, 0, env->stream>>>(d, sums, out, want_polys);
   CCB_LAUNCH_CHECK();
   return 0;
 }
@@ -1239,8 +1239,8 @@ static int ctrl_compute_goals(ccb_ctrl *c) {
     CCB_CUDA(cudaMemcpyAsync(c->d_goals, c->cells.centroid, sizeof(double) * 2 * er, cudaMemcpyDeviceToDevice, env->stream));
   } else {
     if (launch_voronoi_single(env, c->d_sums)) return 1;
-    int threads = std::min(256, ((d.R + 31) / 32) * 32);
-    k_finalize_single<<<d.E, threads, 0, env->stream>>>(d, c->d_sums, c->d_goals);
+    const int warps = d.E * d.R;
+    k_finalize_single<<<(warps + FIN_WARPS - 1) / FIN_WARPS, FIN_WARPS * 32, 0, env->stream>>>(d, c->d_sums, c->d_goals);
     CCB_LAUNCH_CHECK();
   }
   return 0;

@@ -183,15 +183,16 @@ __global__ void k_init_positions(EnvDev d, const double *__restrict__ pos) {
 
 // ---- convex cell polygon: rectangle clipped by the bisector half-planes --------------------------
 // Stands in for the CGAL arrangement face of voronoi.cpp:184-326; same vertex set.
-__device__ inline int clip_cell(const double *sx, const double *sy, int n, int k, double w, double h,
+// sites: x_j = sx[j * stride], y_j = sy[j * stride]
+__device__ inline int clip_cell(const double *sx, const double *sy, int stride, int n, int k, double w, double h,
                                 double (*poly)[2], double (*tmp)[2]) {
   int na = 4;
   poly[0][0] = 0, poly[0][1] = 0, poly[1][0] = w, poly[1][1] = 0;
   poly[2][0] = w, poly[2][1] = h, poly[3][0] = 0, poly[3][1] = h;
-  const double kx = sx[k], ky = sy[k];
+  const double kx = sx[k * stride], ky = sy[k * stride];
   for (int j = 0; j < n && na > 0; ++j) {
     if (j == k) continue;
-    const double jx = sx[j], jy = sy[j];
+    const double jx = sx[j * stride], jy = sy[j * stride];
     const double nx = jx - kx, ny = jy - ky;
     if (nx == 0 && ny == 0) continue;
     const double c = ((jx * jx + jy * jy) - (kx * kx + ky * ky)) / 2.;
@@ -230,40 +231,123 @@ struct CellsOut {
   double *verts;     // [E][R][CCB_MAX_CELL_VERTS][2]
 };
 
+// The same clipping with one WARP per cell: lane v holds vertex v, a half-plane is tested by all lanes at
+// once (most bisectors do not reach the cell and cost a dozen instructions), a cutting half-plane
+// is one prefix sum + one pass through the warp's shared-memory scratch.  Same expressions in the same
+// order as clip_cell, hence the same vertices bit for bit.  sx/sy: n sites (any address space, read by
+// all lanes alike); buf: this warp's scratch, 2 x 32 x 2 doubles; returns the vertex count with the
+// polygon in buf[0..na), or -1 if a polygon outgrew 32 vertices (the caller then uses clip_cell).
+constexpr int CLIPW_MAX = 32;
+__device__ inline int clip_cell_warp(const double *sx, const double *sy, int stride, int n, int k, double w, double h,
+                                     double (*buf)[2]) {
+  const int lane = threadIdx.x & 31;
+  double (*poly)[2] = buf, (*tmp)[2] = buf + CLIPW_MAX;
+  int na = 4;
+  double vx = (lane == 1 || lane == 2) ? w : 0.0, vy = (lane == 2 || lane == 3) ? h : 0.0;
+  const double kx = sx[k * stride], ky = sy[k * stride];
+  for (int j = 0; j < n && na > 0; ++j) {
+    if (j == k) continue;
+    const double jx = sx[j * stride], jy = sy[j * stride];
+    const double nx = jx - kx, ny = jy - ky;
+    if (nx == 0 && ny == 0) continue;
+    const double c = ((jx * jx + jy * jy) - (kx * kx + ky * ky)) / 2.;
+    const double dv = nx * vx + ny * vy - c;
+    const bool act = lane < na;
+    if (!__any_sync(0xffffffffu, act && dv > 0)) continue;  // the bisector does not reach the cell
+    const int u = (lane + 1 == na) ? 0 : lane + 1;
+    const double ux = __shfl_sync(0xffffffffu, vx, u & 31), uy = __shfl_sync(0xffffffffu, vy, u & 31);
+    const double du = __shfl_sync(0xffffffffu, dv, u & 31);
+    const bool vin = act && dv <= 0, uin = du <= 0;
+    const bool cross = act && ((dv <= 0) != uin);
+    const int cnt = (vin ? 1 : 0) + (cross ? 1 : 0);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    const int nb = __shfl_sync(0xffffffffu, incl, 31);
+    if (nb > CLIPW_MAX) return -1;
+    int off = incl - cnt;
+    if (vin) tmp[off][0] = vx, tmp[off][1] = vy, ++off;
+    if (cross) {
+      const double t = dv / (dv - du);
+      tmp[off][0] = vx + t * (ux - vx), tmp[off][1] = vy + t * (uy - vy);
+    }
+    __syncwarp();
+    // drop a vertex equal to its predecessor (cyclically), keep the order
+    bool keep = false;
+    double tx = 0, ty = 0;
+    if (lane < nb) {
+      tx = tmp[lane][0], ty = tmp[lane][1];
+      const int pv = lane == 0 ? nb - 1 : lane - 1;
+      keep = !(nb > 1 && tx == tmp[pv][0] && ty == tmp[pv][1]);
+    }
+    const unsigned km = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int pos = __popc(km & ((1u << lane) - 1u));
+      poly[pos][0] = tx, poly[pos][1] = ty;
+    }
+    na = __popc(km);
+    __syncwarp();
+    vx = lane < na ? poly[lane][0] : 0.0, vy = lane < na ? poly[lane][1] : 0.0;
+    __syncwarp();
+  }
+  if (lane < na) poly[lane][0] = vx, poly[lane][1] = vy;
+  __syncwarp();
+  return na;
+}
+
+constexpr int FIN_WARPS = 8;
+
 // Finalise the global Voronoi cells of every environment from the reduced moments
 // (voronoi.cpp:41-53 ComputeFinalCentroid incl. the vertex-mean fallback; voronoi.h:89-95 sums).
-// One CTA per environment, robots strided over threads.  Dynamic smem: 2 * R doubles.
-__global__ void k_finalize_cells(EnvDev d, const double *__restrict__ sums, CellsOut out, int want_polys) {
-  extern __shared__ double s_sites[];
-  double *s_x = s_sites, *s_y = s_sites + d.R;
-  const int e = blockIdx.x;
+// One warp per cell; the polygon is only built for cells without mass (or when the caller wants the
+// vertex lists).  grid = ceil(E R / FIN_WARPS), block = 32 FIN_WARPS.
+__global__ void __launch_bounds__(FIN_WARPS * 32) k_finalize_cells(EnvDev d, const double *__restrict__ sums, CellsOut out,
+                                                                   int want_polys) {
+  __shared__ double s_buf[FIN_WARPS][2 * CLIPW_MAX][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t er = (size_t)blockIdx.x * FIN_WARPS + warp;
+  if (er >= (size_t)d.E * d.R) return;
+  const int e = (int)(er / d.R), r = (int)(er - (size_t)e * d.R);
   const double *pos = d.pos_g + (size_t)e * d.R * 2;
-  for (int k = threadIdx.x; k < d.R; k += blockDim.x) s_x[k] = pos[2 * k], s_y[k] = pos[2 * k + 1];
-  __syncthreads();
-  for (int r = threadIdx.x; r < d.R; r += blockDim.x) {
-    const size_t er = (size_t)e * d.R + r;
-    const double *s = sums + er * 4;
-    const double m = s[0];
-    const double px = s_x[r], py = s_y[r];
-    const double res = d.res;
-    const double mx = res * s[1], my = res * s[2];
-    out.mass[er] = m;
-    out.obj[er] = res * res * s[3] - 2. * (px * mx + py * my) + (px * px + py * py) * m;
-    double cx, cy;
-    int nv = 0;
-    if (m < kEps || want_polys) {
-      double poly[CCB_MAX_CELL_VERTS][2], tmp[CCB_MAX_CELL_VERTS][2];
-      // box = (pWorldMapSize, pWorldMapSize), not scaled by the resolution (coverage_system.h:373-375)
-      nv = clip_cell(s_x, s_y, d.R, r, (double)d.N, (double)d.N, poly, tmp);
+  const double *s = sums + er * 4;
+  const double m = s[0];
+  const double px = pos[2 * r], py = pos[2 * r + 1];
+  const double res = d.res;
+  const double mx = res * s[1], my = res * s[2];
+  double cx = 0, cy = 0;
+  int nv = 0;
+  if (m < kEps || want_polys) {  // warp-uniform
+    // box = (pWorldMapSize, pWorldMapSize), not scaled by the resolution (coverage_system.h:373-375)
+    double (*poly)[2] = s_buf[warp];
+    nv = clip_cell_warp(pos, pos + 1, 2, d.R, r, (double)d.N, (double)d.N, poly);
+    if (nv >= 0) {
       double ax = 0, ay = 0;
       for (int v = 0; v < nv; ++v) ax += poly[v][0], ay += poly[v][1];
       cx = nv > 0 ? ax / nv : px;
       cy = nv > 0 ? ay / nv : py;
+      if (want_polys && lane < nv) {
+        double *dst = out.verts + er * CCB_MAX_CELL_VERTS * 2;
+        dst[2 * lane] = poly[lane][0], dst[2 * lane + 1] = poly[lane][1];
+      }
+    } else if (lane == 0) {  // more than 32 vertices: the sequential version
+      double big[CCB_MAX_CELL_VERTS][2], tmp[CCB_MAX_CELL_VERTS][2];
+      nv = clip_cell(pos, pos + 1, 2, d.R, r, (double)d.N, (double)d.N, big, tmp);
+      double ax = 0, ay = 0;
+      for (int v = 0; v < nv; ++v) ax += big[v][0], ay += big[v][1];
+      cx = nv > 0 ? ax / nv : px;
+      cy = nv > 0 ? ay / nv : py;
       if (want_polys) {
         double *dst = out.verts + er * CCB_MAX_CELL_VERTS * 2;
-        for (int v = 0; v < nv; ++v) dst[2 * v] = poly[v][0], dst[2 * v + 1] = poly[v][1];
+        for (int v = 0; v < nv; ++v) dst[2 * v] = big[v][0], dst[2 * v + 1] = big[v][1];
       }
     }
+  }
+  if (lane == 0) {
+    out.mass[er] = m;
+    out.obj[er] = res * res * s[3] - 2. * (px * mx + py * my) + (px * px + py * py) * m;
     if (!(m < kEps)) cx = mx / m, cy = my / m;
     out.centroid[2 * er] = cx, out.centroid[2 * er + 1] = cy;
     if (want_polys) out.nverts[er] = nv;
@@ -271,42 +355,66 @@ __global__ void k_finalize_cells(EnvDev d, const double *__restrict__ sums, Cell
 }
 
 // Goals of DecentralizedCVT (decentralized_cvt.h:85-143) from the per-robot window moments.
-// One CTA per environment.  Dynamic smem: 2 * R doubles per thread-independent scratch is avoided
-// by rebuilding the (small) neighbour list per robot in local memory.
-__global__ void k_finalize_single(EnvDev d, const double *__restrict__ sums, double *__restrict__ goals) {
-  const int e = blockIdx.x;
+// One warp per robot; the clipped cell is only built when the robot's own cell has no mass.
+// grid = ceil(E R / FIN_WARPS), block = 32 FIN_WARPS.
+__global__ void __launch_bounds__(FIN_WARPS * 32) k_finalize_single(EnvDev d, const double *__restrict__ sums,
+                                                                    double *__restrict__ goals) {
+  __shared__ double s_buf[FIN_WARPS][2 * CLIPW_MAX][2];
+  __shared__ double s_lx[FIN_WARPS][CCB_MAX_CELL_VERTS], s_ly[FIN_WARPS][CCB_MAX_CELL_VERTS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t er = (size_t)blockIdx.x * FIN_WARPS + warp;
+  if (er >= (size_t)d.E * d.R) return;
+  const int e = (int)(er / d.R), r = (int)(er - (size_t)e * d.R);
   const double *pos = d.pos_g + (size_t)e * d.R * 2;
-  for (int r = threadIdx.x; r < d.R; r += blockDim.x) {
-    const size_t er = (size_t)e * d.R + r;
-    const double *s = sums + er * 4;
-    const double m = s[0], res = d.res;
-    double gx, gy;
-    if (m < kEps) {
-      // vertex mean of (window rectangle ∩ bisector half-planes), in window coordinates
-      const double sxr = pos[2 * r], syr = pos[2 * r + 1];
-      const Window w = make_window(res, sxr, syr, d.L, d.N);
-      const double tx = w.x0 * res, ty = w.y0 * res;
-      double lx[CCB_MAX_CELL_VERTS], ly[CCB_MAX_CELL_VERTS];
-      int n = 1;
-      lx[0] = sxr - tx, ly[0] = syr - ty;
-      for (int j = 0; j < d.R && n < CCB_MAX_CELL_VERTS; ++j) {
-        if (j == r) continue;
-        double dx = pos[2 * j] - sxr, dy = pos[2 * j + 1] - syr;
-        if (sqrt(dx * dx + dy * dy) < d.comm_range) lx[n] = pos[2 * j] - tx, ly[n] = pos[2 * j + 1] - ty, ++n;
+  const double *s = sums + er * 4;
+  const double m = s[0], res = d.res;
+  double gx, gy;
+  if (m < kEps) {  // warp-uniform
+    // vertex mean of (window rectangle ∩ bisector half-planes), in window coordinates
+    const double sxr = pos[2 * r], syr = pos[2 * r + 1];
+    const Window w = make_window(res, sxr, syr, d.L, d.N);
+    const double tx = w.x0 * res, ty = w.y0 * res;
+    double *lx = s_lx[warp], *ly = s_ly[warp];
+    if (lane == 0) lx[0] = sxr - tx, ly[0] = syr - ty;
+    int n = 1;
+    // the robot, then its neighbours within communication range in ascending index (at most
+    // CCB_MAX_CELL_VERTS sites, as the sequential version)
+    for (int base = 0; base < d.R && n < CCB_MAX_CELL_VERTS; base += 32) {
+      const int j = base + lane;
+      bool keep = false;
+      double jx = 0, jy = 0;
+      if (j < d.R && j != r) {
+        jx = pos[2 * j], jy = pos[2 * j + 1];
+        const double dx = jx - sxr, dy = jy - syr;
+        keep = sqrt(dx * dx + dy * dy) < d.comm_range;
       }
-      double poly[CCB_MAX_CELL_VERTS][2], tmp[CCB_MAX_CELL_VERTS][2];
-      int nv = clip_cell(lx, ly, n, 0, (double)(w.x1 - w.x0), (double)(w.y1 - w.y0), poly, tmp);
-      double ax = 0, ay = 0;
-      for (int v = 0; v < nv; ++v) ax += poly[v][0], ay += poly[v][1];
-      // voronoi.cpp:49: centroid_ += origin_shift (= -site0); decentralized_cvt.h:126 adds it back
-      double cxs = (nv > 0 ? ax / nv : lx[0]) + (-lx[0]);
-      double cys = (nv > 0 ? ay / nv : ly[0]) + (-ly[0]);
-      gx = cxs + lx[0] + tx;
-      gy = cys + ly[0] + ty;
-    } else {
-      gx = res * s[1] / m;
-      gy = res * s[2] / m;
+      const unsigned km = __ballot_sync(0xffffffffu, keep);
+      const int slot = n + __popc(km & ((1u << lane) - 1u));
+      if (keep && slot < CCB_MAX_CELL_VERTS) lx[slot] = jx - tx, ly[slot] = jy - ty;
+      n = min(n + __popc(km), CCB_MAX_CELL_VERTS);
     }
+    __syncwarp();
+    double (*poly)[2] = s_buf[warp];
+    int nv = clip_cell_warp(lx, ly, 1, n, 0, (double)(w.x1 - w.x0), (double)(w.y1 - w.y0), poly);
+    double ax = 0, ay = 0;
+    if (nv >= 0) {
+      for (int v = 0; v < nv; ++v) ax += poly[v][0], ay += poly[v][1];
+    } else {
+      double big[CCB_MAX_CELL_VERTS][2], tmp[CCB_MAX_CELL_VERTS][2];
+      nv = clip_cell(lx, ly, 1, n, 0, (double)(w.x1 - w.x0), (double)(w.y1 - w.y0), big, tmp);
+      for (int v = 0; v < nv; ++v) ax += big[v][0], ay += big[v][1];
+    }
+    // voronoi.cpp:49: centroid_ += origin_shift (= -site0); decentralized_cvt.h:126 adds it back
+    const double l0x = sxr - tx, l0y = syr - ty;
+    const double cxs = (nv > 0 ? ax / nv : l0x) + (-l0x);
+    const double cys = (nv > 0 ? ay / nv : l0y) + (-l0y);
+    gx = cxs + l0x + tx;
+    gy = cys + l0y + ty;
+  } else {
+    gx = res * s[1] / m;
+    gy = res * s[2] / m;
+  }
+  if (lane == 0) {
     goals[2 * er] = gx, goals[2 * er + 1] = gy;
     if (gx < 0 || gx > d.N || gy < 0 || gy > d.N) atomicOr(d.status + e, 1);  // decentralized_cvt.h:127-141
   }
