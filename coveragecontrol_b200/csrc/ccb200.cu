@@ -395,6 +395,13 @@ struct ccb_env {
   cudaEvent_t ev_aux = nullptr;    // recorded on `aux` after the last chain launched there
   cudaEvent_t ev_cells = nullptr;  // recorded on `stream` after cells were (re)computed there
   bool no_aux = false;             // CCB_NO_AUX: keep everything on `stream` (debugging)
+  bool no_graph = false;           // CCB_NO_GRAPH: never replay roll-outs from a CUDA graph
+  // roll-out graphs are captured on and launched into `cap` (the caller's stream may be the legacy
+  // default stream, which cannot be captured); every replay is bracketed by ev_fork / ev_join so that
+  // it stays ordered with the work on `stream` before and after it
+  cudaStream_t cap = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool cells_recomputed = false;   // set whenever ensure_cells launches (read by the roll-out graph capture)
   bool aux_pending = false;        // `stream` has not yet waited for ev_aux
   uint32_t *d_vg_table = nullptr;  // [E][R][N] row intervals of the site-ordered global Voronoi (vglobal.cuh)
   int *d_vg_flag = nullptr;     // [1 + E*N]: count, then the flagged rows
@@ -557,6 +564,7 @@ static int ensure_cells(ccb_env *env, bool want_polys) {
       return fail("row-band mode: all-reduce the partials and call ccb_env_finalize_from_partials_dev first");
     if (launch_voronoi_global(env, SRC_WORLD, env->d_sums)) return 1;
     if (launch_finalize(env, env->d_sums, env->cells, want_polys ? 1 : 0)) return 1;
+    env->cells_recomputed = true;
     env->cells_version = env->pos_version;
     env->cells_have_polys = want_polys;
   } else if (want_polys && !env->cells_have_polys) {
@@ -618,6 +626,9 @@ static int env_alloc(ccb_env *env) {
   CCB_CUDA(cudaEventCreateWithFlags(&env->ev_state, cudaEventDisableTiming));
   CCB_CUDA(cudaEventCreateWithFlags(&env->ev_aux, cudaEventDisableTiming));
   CCB_CUDA(cudaEventCreateWithFlags(&env->ev_cells, cudaEventDisableTiming));
+  CCB_CUDA(cudaStreamCreateWithFlags(&env->cap, cudaStreamNonBlocking));
+  CCB_CUDA(cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming));
+  CCB_CUDA(cudaEventCreateWithFlags(&env->ev_join, cudaEventDisableTiming));
   CCB_CUDA(cudaEventRecord(env->ev_state, env->stream));
   CCB_CUDA(cudaEventRecord(env->ev_cells, env->stream));
   return 0;
@@ -659,6 +670,7 @@ extern "C" ccb_env *ccb_env_create(const ccb_params *p, int num_envs, int num_ro
   if (const char *s = getenv("CCB_VW_GENERIC")) env->vw_generic = atoi(s) != 0;
   if (const char *s = getenv("CCB_VG_GENERIC")) env->vg_mode = atoi(s) != 0 ? 1 : 0;
   if (const char *s = getenv("CCB_NO_AUX")) env->no_aux = atoi(s) != 0;
+  if (const char *s = getenv("CCB_NO_GRAPH")) env->no_graph = atoi(s) != 0;
   if (env_alloc(env.get())) {
     ccb_env_destroy(env.release());
     return nullptr;
@@ -674,6 +686,9 @@ extern "C" void ccb_env_destroy(ccb_env *env) {
   if (env->ev_state) cudaEventDestroy(env->ev_state);
   if (env->ev_aux) cudaEventDestroy(env->ev_aux);
   if (env->ev_cells) cudaEventDestroy(env->ev_cells);
+  if (env->cap) cudaStreamSynchronize(env->cap), cudaStreamDestroy(env->cap);
+  if (env->ev_fork) cudaEventDestroy(env->ev_fork);
+  if (env->ev_join) cudaEventDestroy(env->ev_join);
   EnvDev &d = env->d;
   cudaFree(d.world), cudaFree(d.seenb), cudaFree(d.xseenb), cudaFree(d.sysb);
   cudaFree(d.pos_g), cudaFree(d.pos_s), cudaFree(d.pos_l);
@@ -1218,6 +1233,20 @@ struct ccb_ctrl {
   int *d_conv = nullptr;        // [E]
   double *d_sums = nullptr;     // [E][R][4] (centralized / decentralized)
   CellsOut cells{};             // centralized
+  // A roll-out call is a fixed sequence of launches on two streams: the second identical call is
+  // captured into a CUDA graph and later ones replay it (one launch per call instead of ~15 per step).
+  struct RolloutGraph {
+    int steps = 0, with_objective = 0, C = 0, use_comm = 0, entry_valid = 0;
+    double *obj = nullptr;
+    float *obs = nullptr;
+    size_t stride = 0;
+    int seen = 0;                 // eager calls with this signature so far
+    cudaGraphExec_t exec = nullptr;
+    uint64_t launches = 0;        // kernel launches inside the graph
+    uint64_t pos_delta = 0;       // host bookkeeping the replay must reproduce
+    bool cells_recomputed = false;
+    uint64_t cells_lag = 0;
+  } rg;
 };
 
 static int ctrl_compute_goals(ccb_ctrl *c) {
@@ -1282,6 +1311,7 @@ extern "C" void ccb_ctrl_destroy(ccb_ctrl *c) {
   if (!c) return;
   cudaSetDevice(c->env->device);
   cudaStreamSynchronize(c->env->stream);
+  if (c->rg.exec) cudaGraphExecDestroy(c->rg.exec);
   cudaFree(c->d_goals), cudaFree(c->d_actions), cudaFree(c->d_conv), cudaFree(c->d_sums);
   free_cells(c->cells);
   delete c;
@@ -1339,10 +1369,12 @@ extern "C" int ccb_ctrl_is_converged(ccb_ctrl *c, int *out) {
 }
 extern "C" const double *ccb_ctrl_actions_dev(const ccb_ctrl *c) { return c->d_actions; }
 
-extern "C" int ccb_ctrl_rollout_obs(ccb_ctrl *c, int steps, int with_objective, double *objective_dev_out, int C,
-                                    int use_comm, float *obs_dev, size_t obs_step_stride) {
-  CCB_CUDA(cudaSetDevice(c->env->device));
+static int rollout_obs_eager(ccb_ctrl *c, int steps, int with_objective, double *objective_dev_out, int C, int use_comm,
+                             float *obs_dev, size_t obs_step_stride) {
   ccb_env *env = c->env;
+  // fork points of this call (inside a graph capture they must belong to the capture)
+  CCB_CUDA(cudaEventRecord(env->ev_state, env->stream));
+  CCB_CUDA(cudaEventRecord(env->ev_cells, env->stream));
   for (int s = 0; s < steps; ++s) {
     if (ctrl_compute_actions_async(c)) return 1;
     if (step_actions_dev(env, c->d_actions)) return 1;
@@ -1353,6 +1385,88 @@ extern "C" int ccb_ctrl_rollout_obs(ccb_ctrl *c, int steps, int with_objective, 
     if (obs_dev && ccb_env_cnn_input_dev(env, C, use_comm, obs_dev + (size_t)s * obs_step_stride)) return 1;
   }
   return join_aux(env);  // everything this call produced is ordered on the env stream when it returns
+}
+
+extern "C" int ccb_ctrl_rollout_obs(ccb_ctrl *c, int steps, int with_objective, double *objective_dev_out, int C,
+                                    int use_comm, float *obs_dev, size_t obs_step_stride) {
+  CCB_CUDA(cudaSetDevice(c->env->device));
+  ccb_env *env = c->env;
+  ccb_ctrl::RolloutGraph &g = c->rg;
+  const int entry_valid = env->cells_version == env->pos_version ? 1 : 0;
+  const bool same = g.steps == steps && g.with_objective == with_objective && g.C == C && g.use_comm == use_comm &&
+                    g.obj == objective_dev_out && g.obs == obs_dev && g.stride == obs_step_stride &&
+                    g.entry_valid == entry_valid;
+  if (env->no_graph || env->no_aux || env->band_mode || steps < 1 || steps > 64)
+    return rollout_obs_eager(c, steps, with_objective, objective_dev_out, C, use_comm, obs_dev, obs_step_stride);
+  if (!same) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g = ccb_ctrl::RolloutGraph{};
+    g.steps = steps, g.with_objective = with_objective, g.C = C, g.use_comm = use_comm, g.obj = objective_dev_out;
+    g.obs = obs_dev, g.stride = obs_step_stride, g.entry_valid = entry_valid;
+  }
+  if (join_aux(env)) return 1;
+  auto launch_graph = [&]() -> int {
+    CCB_CUDA(cudaEventRecord(env->ev_fork, env->stream));
+    CCB_CUDA(cudaStreamWaitEvent(env->cap, env->ev_fork, 0));
+    CCB_CUDA(cudaGraphLaunch(g.exec, env->cap));
+    CCB_CUDA(cudaEventRecord(env->ev_join, env->cap));
+    CCB_CUDA(cudaStreamWaitEvent(env->stream, env->ev_join, 0));
+    // the events were last recorded inside the captured region: make them real again
+    CCB_CUDA(cudaEventRecord(env->ev_state, env->stream));
+    CCB_CUDA(cudaEventRecord(env->ev_cells, env->stream));
+    env->aux_pending = false;
+    return 0;
+  };
+  if (g.exec) {  // replay
+    if (launch_graph()) return 1;
+    g_launches.fetch_add(g.launches);
+    env->pos_version += g.pos_delta;
+    if (g.cells_recomputed) env->cells_version = env->pos_version - g.cells_lag, env->cells_have_polys = false;
+    return 0;
+  }
+  if (g.seen < 1) {  // first call: eager (also allocates and caches whatever the kernels need)
+    g.seen++;
+    return rollout_obs_eager(c, steps, with_objective, objective_dev_out, C, use_comm, obs_dev, obs_step_stride);
+  }
+  // second identical call: capture it
+  const uint64_t pos0 = env->pos_version, launches0 = g_launches.load();
+  env->cells_recomputed = false;
+  cudaGraph_t graph = nullptr;
+  int rc;
+  cudaError_t ce;
+  {
+    cudaStream_t user = env->stream;
+    env->stream = env->cap;  // every launch of the captured pass goes to `cap` (and, forked from it, `aux`)
+    ce = cudaStreamBeginCapture(env->cap, cudaStreamCaptureModeRelaxed);
+    if (ce != cudaSuccess) {
+      env->stream = user;
+      env->no_graph = true;
+      cudaGetLastError();
+      return rollout_obs_eager(c, steps, with_objective, objective_dev_out, C, use_comm, obs_dev, obs_step_stride);
+    }
+    rc = rollout_obs_eager(c, steps, with_objective, objective_dev_out, C, use_comm, obs_dev, obs_step_stride);
+    ce = cudaStreamEndCapture(env->cap, &graph);
+    env->stream = user;
+  }
+  if (rc || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    env->no_graph = true;  // do not try again; the state may be inconsistent with the (unexecuted) capture
+    return fail("roll-out graph capture failed", rc ? ccb_last_error() : cudaGetErrorString(ce));
+  }
+  g.launches = g_launches.load() - launches0;
+  g.pos_delta = env->pos_version - pos0;
+  g.cells_recomputed = env->cells_recomputed;
+  g.cells_lag = env->pos_version - env->cells_version;
+  cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) {
+    g.exec = nullptr;
+    env->no_graph = true;
+    return fail("cudaGraphInstantiate failed", cudaGetErrorString(ie));
+  }
+  // nothing ran during the capture: launch the graph for this call (host bookkeeping is already done)
+  return launch_graph();
 }
 
 extern "C" int ccb_ctrl_rollout(ccb_ctrl *c, int steps, int with_objective, double *objective_dev_out) {

@@ -373,3 +373,52 @@ def test_fused_rollout_with_observation_equals_separate_calls():
     assert np.allclose(out[0][2], out[1][2], rtol=1e-6, atol=1e-9)
     assert np.allclose(out[0][3], out[1][3], rtol=1e-12)
     assert np.allclose(out[1][1][-1], out[1][3], rtol=1e-12)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_rollout_graph_replay_equals_eager(monkeypatch, kind):
+    """Identical roll-out calls are captured into a CUDA graph on the second call and replayed afterwards
+    (csrc/ccb200.cu ccb_ctrl_rollout_obs); the trajectory, objective and observation must be those of the
+    eager launches, and the host-side bookkeeping must stay consistent with calls made in between."""
+    import torch
+
+    cc, orc = _cc(), _orc()
+    from coveragecontrol_b200 import BatchedCoverageSystem, BatchedCVT, _lib
+
+    N, R, E, C = 512, 9, 3, 32
+    p = cc.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    p.pNumRobots = R
+    rng = np.random.default_rng(17)
+    worlds = [rng.random((N, N)).astype(np.float32) for _ in range(E)]
+    pos = rng.uniform(1, N - 1, (E, R, 2))
+    res = []
+    for nograph in ("1", "0"):
+        monkeypatch.setenv("CCB_NO_GRAPH", nograph)
+        env = BatchedCoverageSystem(p, E, R)
+        for e in range(E):
+            env.set_world(e, worlds[e])
+        env.reset(pos)
+        ctrl = BatchedCVT(env, kind)
+        obj = torch.zeros((2, E), dtype=torch.float64, device="cuda")
+        obs = torch.zeros((E, R, 4, C, C), dtype=torch.float32, device="cuda")
+        launches0 = _lib.load().ccb_kernel_launch_count()
+        trace = []
+        for it in range(6):
+            ctrl.rollout_obs(2, True, obj.data_ptr(), C, True, obs.data_ptr(), 0)
+            torch.cuda.synchronize()
+            trace.append((env.positions(), obj.cpu().numpy().copy(), obs.cpu().numpy().copy()))
+            if it == 3:  # calls in between: host-returning getters and a plain step through the host API
+                trace.append((env.objective(), np.array(env.cells(0)[0])))
+                ctrl.compute_actions()
+                env.step_actions(ctrl.actions())
+        trace.append(env.objective())
+        res.append((trace, _lib.load().ccb_kernel_launch_count() - launches0))
+    (eager, n_eager), (graph, n_graph) = res
+    assert n_graph == n_eager > 0  # replays are counted like the launches they stand for
+    for a, b in zip(eager, graph):
+        if isinstance(a, tuple):
+            for x, y in zip(a, b):
+                assert np.allclose(x, y, rtol=1e-9, atol=1e-9)
+        else:
+            assert np.allclose(a, b, rtol=1e-9)
