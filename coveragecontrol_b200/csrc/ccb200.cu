@@ -402,6 +402,13 @@ struct ccb_env {
   cudaStream_t cap = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool cells_recomputed = false;   // set whenever ensure_cells launches (read by the roll-out graph capture)
+  // DecentralizedCVT's window moments as a by-product of the observation kernel (obs.cuh, VOR variant):
+  // valid for the positions of wsums_version; the next ComputeGoals picks them up instead of launching
+  // k_voronoi_window over the same windows
+  double *d_wsums = nullptr;       // [E][R][4]
+  uint64_t wsums_version = 0;
+  int n_decentralized = 0;         // live DecentralizedCVT controllers on this environment
+  bool no_wfuse = false;           // CCB_NO_WFUSE: keep the two kernels apart (tests)
   bool aux_pending = false;        // `stream` has not yet waited for ev_aux
   uint32_t *d_vg_table = nullptr;  // [E][R][N] row intervals of the site-ordered global Voronoi (vglobal.cuh)
   int *d_vg_flag = nullptr;     // [1 + E*N]: count, then the flagged rows
@@ -528,6 +535,10 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
 // per-robot L-window variant (DecentralizedCVT): only the robot's own cell is reduced
 static int launch_voronoi_single(ccb_env *env, double *sums) {
   const EnvDev &d = env->d;
+  if (env->wsums_version == env->pos_version) {  // the observation kernel already reduced these windows
+    CCB_CUDA(cudaMemcpyAsync(sums, env->d_wsums, sizeof(double) * 4 * d.E * d.R, cudaMemcpyDeviceToDevice, env->stream));
+    return 0;
+  }
   if (d.L <= VW_MAXL && (d.N & 3) == 0 && !env->vw_generic) {
     static size_t current = 48 * 1024;
     const size_t smem = vw_smem_bytes(d.R);
@@ -609,6 +620,7 @@ static int env_alloc(ccb_env *env) {
   CCB_CUDA(cudaMalloc(&d.hist_len, sizeof(int) * er));
   CCB_CUDA(cudaMalloc(&d.status, sizeof(int) * d.E));
   CCB_CUDA(cudaMalloc(&env->d_sums, sizeof(double) * 4 * er));
+  CCB_CUDA(cudaMalloc(&env->d_wsums, sizeof(double) * 4 * er));
   if (alloc_cells(env->cells, d.E, d.R, true)) return 1;
   CCB_CUDA(cudaMalloc(&env->d_objective, sizeof(double) * d.E));
   CCB_CUDA(cudaMalloc(&env->d_stage, sizeof(double) * 2 * er));
@@ -671,6 +683,7 @@ extern "C" ccb_env *ccb_env_create(const ccb_params *p, int num_envs, int num_ro
   if (const char *s = getenv("CCB_VG_GENERIC")) env->vg_mode = atoi(s) != 0 ? 1 : 0;
   if (const char *s = getenv("CCB_NO_AUX")) env->no_aux = atoi(s) != 0;
   if (const char *s = getenv("CCB_NO_GRAPH")) env->no_graph = atoi(s) != 0;
+  if (const char *s = getenv("CCB_NO_WFUSE")) env->no_wfuse = atoi(s) != 0;
   if (env_alloc(env.get())) {
     ccb_env_destroy(env.release());
     return nullptr;
@@ -693,7 +706,7 @@ extern "C" void ccb_env_destroy(ccb_env *env) {
   cudaFree(d.world), cudaFree(d.seenb), cudaFree(d.xseenb), cudaFree(d.sysb);
   cudaFree(d.pos_g), cudaFree(d.pos_s), cudaFree(d.pos_l);
   cudaFree(d.hist), cudaFree(d.hist_start), cudaFree(d.hist_len), cudaFree(d.status);
-  cudaFree(env->d_sums);
+  cudaFree(env->d_sums), cudaFree(env->d_wsums);
   free_cells(env->cells);
   cudaFree(env->d_objective), cudaFree(env->d_stage), cudaFree(env->d_feat), cudaFree(env->d_ratio);
   cudaFree(env->d_scratch);
@@ -1011,12 +1024,22 @@ extern "C" int ccb_env_cnn_input_dev(ccb_env *env, int C, int use_comm, float *o
     CCB_CUDA(cudaFuncSetAttribute(k_cnn_local_obstacle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // channel order of coverage_env_utils.py:264-276: [local, comm_x, comm_y, obstacle]
   if (t->d_wfull8 && (d.N & 3) == 0 && !getenv("CCB_CNN_GENERIC")) {
-    static bool cnn8_attr = false;
-    if (!cnn8_attr) {
-      CCB_CUDA(cudaFuncSetAttribute(k_cnn_fused8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CNN8_SMEM_BYTES));
-      cnn8_attr = true;
+    static size_t cnn8_attr = 0;
+    const bool vor = env->n_decentralized > 0 && !env->no_wfuse && d.L == 256 && env->wsums_version != env->pos_version;
+    const size_t smem8 = vor ? cnn8_vor_smem_bytes(d.R) : CNN8_SMEM_BYTES;
+    if (smem8 > cnn8_attr) {
+      CCB_CUDA(cudaFuncSetAttribute(k_cnn_fused8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+      CCB_CUDA(cudaFuncSetAttribute(k_cnn_fused8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+      cnn8_attr = smem8;
     }
-    k_cnn_fused8<<<dim3(d.R, d.E), CNN8_THREADS, CNN8_SMEM_BYTES, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, cc * (nch - 1));
+    if (vor) {
+      k_cnn_fused8<true><<<dim3(d.R, d.E), CNN8_THREADS, smem8, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, cc * (nch - 1),
+                                                                                env->d_wsums);
+      env->wsums_version = env->pos_version;
+    } else {
+      k_cnn_fused8<false><<<dim3(d.R, d.E), CNN8_THREADS, smem8, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, cc * (nch - 1),
+                                                                                 nullptr);
+    }
   } else {
     k_cnn_local_obstacle<<<dim3(C, d.R, d.E), 256, smem, env->stream>>>(d, C, tab, out_dev, stride, 0, cc * (nch - 1));
   }
@@ -1246,6 +1269,7 @@ struct ccb_ctrl {
     uint64_t pos_delta = 0;       // host bookkeeping the replay must reproduce
     bool cells_recomputed = false;
     uint64_t cells_lag = 0;
+    bool wsums_valid_after = false;
   } rg;
 };
 
@@ -1298,6 +1322,7 @@ extern "C" ccb_ctrl *ccb_ctrl_create(ccb_env *env, int kind) {
     ccb_ctrl_destroy(c.release());
     return nullptr;
   }
+  if (kind == CCB_DECENTRALIZED) env->n_decentralized++;
   cudaMemsetAsync(c->d_actions, 0, sizeof(double) * 2 * er, env->stream);
   cudaMemsetAsync(c->d_conv, 0, sizeof(int) * env->E, env->stream);
   if (ctrl_compute_goals(c.get())) {  // the reference constructors call ComputeGoals()
@@ -1312,6 +1337,7 @@ extern "C" void ccb_ctrl_destroy(ccb_ctrl *c) {
   cudaSetDevice(c->env->device);
   cudaStreamSynchronize(c->env->stream);
   if (c->rg.exec) cudaGraphExecDestroy(c->rg.exec);
+  if (c->kind == CCB_DECENTRALIZED && c->env->n_decentralized > 0) c->env->n_decentralized--;
   cudaFree(c->d_goals), cudaFree(c->d_actions), cudaFree(c->d_conv), cudaFree(c->d_sums);
   free_cells(c->cells);
   delete c;
@@ -1392,7 +1418,7 @@ extern "C" int ccb_ctrl_rollout_obs(ccb_ctrl *c, int steps, int with_objective, 
   CCB_CUDA(cudaSetDevice(c->env->device));
   ccb_env *env = c->env;
   ccb_ctrl::RolloutGraph &g = c->rg;
-  const int entry_valid = env->cells_version == env->pos_version ? 1 : 0;
+  const int entry_valid = (env->cells_version == env->pos_version ? 1 : 0) | (env->wsums_version == env->pos_version ? 2 : 0);
   const bool same = g.steps == steps && g.with_objective == with_objective && g.C == C && g.use_comm == use_comm &&
                     g.obj == objective_dev_out && g.obs == obs_dev && g.stride == obs_step_stride &&
                     g.entry_valid == entry_valid;
@@ -1422,6 +1448,7 @@ extern "C" int ccb_ctrl_rollout_obs(ccb_ctrl *c, int steps, int with_objective, 
     g_launches.fetch_add(g.launches);
     env->pos_version += g.pos_delta;
     if (g.cells_recomputed) env->cells_version = env->pos_version - g.cells_lag, env->cells_have_polys = false;
+    if (g.wsums_valid_after) env->wsums_version = env->pos_version;
     return 0;
   }
   if (g.seen < 1) {  // first call: eager (also allocates and caches whatever the kernels need)
@@ -1458,6 +1485,7 @@ extern "C" int ccb_ctrl_rollout_obs(ccb_ctrl *c, int steps, int with_objective, 
   g.pos_delta = env->pos_version - pos0;
   g.cells_recomputed = env->cells_recomputed;
   g.cells_lag = env->pos_version - env->cells_version;
+  g.wsums_valid_after = env->wsums_version == env->pos_version;
   cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
   cudaGraphDestroy(graph);
   if (ie != cudaSuccess) {
@@ -1486,9 +1514,17 @@ extern "C" int ccb_bench_kernel(ccb_env *env, int which, int iters, float *scrat
     switch (which) {
       case 0: if (launch_voronoi_global(env, SRC_WORLD, env->d_sums)) return 1; env->cells_version = 0; break;
       case 1: if (launch_voronoi_global(env, SRC_EXPLORED, env->d_sums)) return 1; env->cells_version = 0; break;
-      case 2: if (launch_voronoi_single(env, env->d_sums)) return 1; env->cells_version = 0; break;
+      case 2: env->wsums_version = 0; if (launch_voronoi_single(env, env->d_sums)) return 1; env->cells_version = 0; break;
       case 3: if (launch_mark(env, -1, -1, 1, 1)) return 1; break;
-      case 4: if (ccb_env_cnn_input_dev(env, 32, 1, scratch_dev)) return 1; break;
+      case 4: env->wsums_version = env->pos_version; if (ccb_env_cnn_input_dev(env, 32, 1, scratch_dev)) return 1; break;
+      case 8: {  // the fused observation + window-Voronoi variant
+        env->wsums_version = 0;
+        env->n_decentralized++;
+        const int rc = ccb_env_cnn_input_dev(env, 32, 1, scratch_dev);
+        env->n_decentralized--;
+        if (rc) return 1;
+        break;
+      }
       case 5: if (launch_finalize(env, env->d_sums, env->cells, 0)) return 1; env->cells_version = 0; break;
       case 6: if (launch_voronoi_global(env, SRC_WORLD, env->d_sums, nullptr, 0, -1, 2)) return 1; env->cells_version = 0; break;
       case 7: if (launch_voronoi_global(env, SRC_WORLD, env->d_sums, nullptr, 0, -1, 1)) return 1; env->cells_version = 0; break;

@@ -8,6 +8,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "vwindow.cuh"
 #include "maps.cuh"
 
 namespace ccb {
@@ -156,11 +157,26 @@ struct Cnn8Shared {
   int nact;
 };
 constexpr size_t CNN8_SMEM_BYTES = sizeof(Cnn8Shared);
+// The fused variant (VOR) also reduces DecentralizedCVT's window Voronoi (vwindow.cuh) over the same
+// window: same bit plane, same seen rows, same world values -- the controller of the NEXT step finds
+// its moments ready.  Extra state: the robot's own-cell interval of every window row as bits.
+struct Cnn8Vor {
+  uint32_t own[CNN8_ROWS * CNN8_WORDS + 1];  // cells of the robot's own Voronoi cell (indexed like Cnn8Shared::mask)
+  int lo[256], hi[256];                      // the same as map-column intervals, per window row
+  uint32_t exact[8];                         // rows that need the per-cell rule
+  float wt[16][32];                          // tap weights transposed (conflict-free): frees 16 registers
+  int K;
+  double red[CNN8_WARPS][4];
+};
+// dynamic shared memory of the fused variant: Cnn8Shared, Cnn8Vor, px[R], py[R]
+__host__ __device__ inline size_t cnn8_vor_smem_bytes(int R) {
+  return sizeof(Cnn8Shared) + sizeof(Cnn8Vor) + sizeof(double) * 2 * (size_t)R;
+}
 
 // width pass over the listed rows; S = (window origin column) & 3
-template <int S>
+template <int S, bool VOR>
 __device__ __forceinline__ void cnn8_width_pass(const EnvDev &d, Cnn8Shared &sh, const float *__restrict__ world, int ox_map,
-                                                int oy_map, int wbase, const float (&wc)[16]) {
+                                                int oy_map, int wbase, const float (&wc)[16], const Cnn8Vor *vor, VwAcc &acc) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nact = sh.nact;
   const int gy0 = oy_map + 8 * lane;  // map column of this lane's first cell
@@ -178,12 +194,13 @@ __device__ __forceinline__ void cnn8_width_pass(const EnvDev &d, Cnn8Shared &sh,
   const int wi = off >> 5, shf = off & 31;
   const float fill = d.fill;
   const bool dense = fill != 0.f;
+  constexpr int BATCH = VOR ? 2 : CNN8_BATCH;  // the fused variant also carries the fp64 moments in registers
 #pragma unroll 1
-  for (int base = warp * CNN8_BATCH; base < nact; base += CNN8_WARPS * CNN8_BATCH) {
-    float4 v[CNN8_BATCH][NV];
-    unsigned vis[CNN8_BATCH];
+  for (int base = warp * BATCH; base < nact; base += CNN8_WARPS * BATCH) {
+    float4 v[BATCH][NV];
+    unsigned vis[BATCH];
 #pragma unroll
-    for (int b = 0; b < CNN8_BATCH; ++b) {
+    for (int b = 0; b < BATCH; ++b) {
       vis[b] = 0u;
 #pragma unroll
       for (int j = 0; j < NV; ++j) v[b][j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -200,7 +217,7 @@ __device__ __forceinline__ void cnn8_width_pass(const EnvDev &d, Cnn8Shared &sh,
       }
     }
 #pragma unroll
-    for (int b = 0; b < CNN8_BATCH; ++b) {
+    for (int b = 0; b < BATCH; ++b) {
       if (base + b >= nact) break;  // warp-uniform
       float x[4 * NV];
 #pragma unroll
@@ -211,6 +228,23 @@ __device__ __forceinline__ void cnn8_width_pass(const EnvDev &d, Cnn8Shared &sh,
         const float unseen = (dense && ((inmap >> i) & 1u)) ? fill : 0.f;
         c[i] = ((vis[b] >> i) & 1u) ? x[S + i] : unseen;
       }
+      if (VOR) {
+        // the robot's own Voronoi cell on this row: fp64 moments in cell units, as vwindow.cuh
+        const int ai = sh.act[base + b];
+        const unsigned ob = __funnelshift_r(vor->own[ai * CNN8_WORDS + wi], vor->own[ai * CNN8_WORDS + wi + 1], shf) & 0xffu;
+        if (__any_sync(0xffffffffu, ob != 0u)) {
+          const double xd = (double)(ox_map + ai - 4) + 0.5;
+          double s = 0.0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const double dv = (double)(((ob >> i) & 1u) ? c[i] : 0.f);
+            acc.cs[i] += dv;
+            s += dv;
+          }
+          acc.sx = fma(xd, s, acc.sx);
+          acc.sxx = fma(xd * xd, s, acc.sxx);
+        }
+      }
       // taps q = 0..15 are window columns 8 lane - 4 + q: the left neighbour's c[4..7], c[0..7], the
       // right neighbour's c[0..3]; beyond the window (lanes 0 / 31) the padding is zero
       float tmp = 0.f;
@@ -218,31 +252,39 @@ __device__ __forceinline__ void cnn8_width_pass(const EnvDev &d, Cnn8Shared &sh,
       for (int q = 0; q < 4; ++q) {
         float l = __shfl_up_sync(0xffffffffu, c[4 + q], 1);
         if (lane == 0) l = 0.f;
-        tmp = fmaf(wc[q], l, tmp);
+        tmp = fmaf(VOR ? vor->wt[q][lane] : wc[q], l, tmp);
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) tmp = fmaf(wc[4 + q], c[q], tmp);
+      for (int q = 0; q < 8; ++q) tmp = fmaf(VOR ? vor->wt[4 + q][lane] : wc[4 + q], c[q], tmp);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float r = __shfl_down_sync(0xffffffffu, c[q], 1);
         if (lane == 31) r = 0.f;
-        tmp = fmaf(wc[12 + q], r, tmp);
+        tmp = fmaf(VOR ? vor->wt[12 + q][lane] : wc[12 + q], r, tmp);
       }
       sh.tmp[sh.act[base + b]][lane] = tmp;
     }
   }
 }
 
+template <bool VOR>
 __global__ void __launch_bounds__(CNN8_THREADS, 3)
 k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__restrict__ out,
-             size_t robot_stride, size_t local_off, size_t obst_off) {
+             size_t robot_stride, size_t local_off, size_t obst_off, double *__restrict__ wsums /* VOR: [E][R][4] */) {
   extern __shared__ __align__(16) unsigned char cnn8_smem[];  // CNN8_SMEM_BYTES (opt-in: above 48 KB)
   Cnn8Shared &sh = *reinterpret_cast<Cnn8Shared *>(cnn8_smem);
+  Cnn8Vor *vor = VOR ? reinterpret_cast<Cnn8Vor *>(cnn8_smem + sizeof(Cnn8Shared)) : nullptr;
+  double *s_px = reinterpret_cast<double *>(cnn8_smem + sizeof(Cnn8Shared) + sizeof(Cnn8Vor));
+  double *s_py = s_px + d.R;
   const int r = blockIdx.x, e = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t er = (size_t)e * d.R + r;
   const size_t nn = cell_count(d);
-  for (int t = tid; t < 32 * 16; t += CNN8_THREADS) sh.w[t >> 4][t & 15] = wfull[t];
+  for (int t = tid; t < 32 * 16; t += CNN8_THREADS) {
+    const float wv = wfull[t];
+    sh.w[t >> 4][t & 15] = wv;
+    if (VOR) vor->wt[t & 15][t >> 4] = wv;
+  }
   if (tid < (CNN8_ROWS + 31) / 32 + 1) sh.flags[tid] = 0u;
   if (tid == 0) sh.nact = 0, sh.mask[CNN8_ROWS * CNN8_WORDS] = 0u;
   const double *p = d.pos_g + er * 2;
@@ -250,20 +292,60 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
   const float *world = d.world + (size_t)e * nn;
   const uint32_t *plane = robot_plane(d, d.seenb, e, r);
   const bool dense = d.fill != 0.f;  // unseen cells carry pUnknownImportance: every in-map row counts
+  if (VOR) {
+    if (tid < 8) vor->exact[tid] = 0u;
+    if (tid == 0) vor->own[CNN8_ROWS * CNN8_WORDS] = 0u;
+    if (warp == 0) {
+      // sites: self, then the neighbours within communication range in ascending index
+      // (decentralized_cvt.h:100-120), exactly as k_voronoi_window
+      const double *pos = d.pos_g + (size_t)e * d.R * 2;
+      const double sx = p[0], sy = p[1];
+      if (lane == 0) s_px[0] = sx, s_py[0] = sy;
+      int n = 1;
+      for (int base = 0; base < d.R; base += 32) {
+        const int j = base + lane;
+        bool keep = false;
+        double jx = 0, jy = 0;
+        if (j < d.R && j != r) {
+          jx = pos[2 * j], jy = pos[2 * j + 1];
+          const double dx = __dsub_rn(jx, sx), dy = __dsub_rn(jy, sy);
+          keep = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) < d.comm_range;
+        }
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+          const int slot = n + __popc(km & ((1u << lane) - 1u));
+          s_px[slot] = jx, s_py[slot] = jy;
+        }
+        n += __popc(km);
+      }
+      if (lane == 0) vor->K = n - 1;
+    }
+  }
   __syncthreads();
+  if (VOR) {
+    // own-cell interval of every window row (thread a <-> window row a), as k_voronoi_window
+    const int a = tid, row = w.ox + a, ncols = w.y1 - w.y0;
+    int lo = 0, hi = 0;
+    if (row >= w.x0 && row < w.x1 && ncols > 0) {
+      if (vor->K == 0) lo = 0, hi = ncols;
+      else if (vw_row_interval(d.res, row, w.y0, ncols, vor->K, s_px, s_py, lo, hi)) atomicOr(&vor->exact[a >> 5], 1u << (a & 31));
+    }
+    vor->lo[a] = w.y0 + lo, vor->hi[a] = w.y0 + max(hi, lo);
+    __syncthreads();
+  }
 
   // ---- 1. mask words, clipped to the window's map columns [cy0, cy1); all loads issued first ------
   const int wbase = w.oy >> 5;  // arithmetic shift: floor for negative origins
   const int cy0 = max(w.oy, 0), cy1 = min(w.oy + 256, d.N);
   constexpr int NMW = (CNN8_ROWS * CNN8_WORDS + CNN8_THREADS - 1) / CNN8_THREADS;
-  uint32_t mw[NMW];
+  uint32_t mw[NMW], ow[VOR ? NMW : 1];
 #pragma unroll
   for (int it = 0; it < NMW; ++it) {
     const int t = tid + it * CNN8_THREADS;
     const int ai = t / CNN8_WORDS, j = t - ai * CNN8_WORDS;  // ai = a + 4
     const int a = ai - 4;
     const int gx = w.ox + a, wd = wbase + j;
-    uint32_t m = 0u;
+    uint32_t m = 0u, o = 0u;
     if (t < CNN8_ROWS * CNN8_WORDS && a >= 0 && a < 256 && gx >= 0 && gx < d.N && wd >= 0 && wd < d.NW) {
       const int cb = wd << 5;  // map column of bit 0
       const int lo = min(max(cy0 - cb, 0), 32), hi = min(max(cy1 - cb, 0), 32);
@@ -271,9 +353,11 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
         const uint32_t keep = ((hi - lo >= 32) ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) << lo;
         m = __ldg(plane + (size_t)gx * d.NW + wd) & keep;
         if (dense) atomicOr(&sh.flags[ai >> 5], 1u << (ai & 31));
+        if (VOR) o = vw_range_bits(vor->lo[a], vor->hi[a], cb);
       }
     }
     mw[it] = m;
+    if (VOR) ow[it] = o;
   }
 #pragma unroll
   for (int it = 0; it < NMW; ++it) {
@@ -282,22 +366,66 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
       sh.mask[t] = mw[it];
       const int ai = t / CNN8_WORDS;
       if (mw[it]) atomicOr(&sh.flags[ai >> 5], 1u << (ai & 31));
+      if (VOR) {
+        uint32_t o = ow[it];
+        const int a = ai - 4, j = t - ai * CNN8_WORDS;
+        uint32_t todo = dense ? o : (o & mw[it]);
+        if (todo && a >= 0 && a < 256 && ((vor->exact[a >> 5] >> (a & 31)) & 1u)) {
+          // per-cell rule on this row: drop the cells where some neighbour is strictly nearer
+          while (todo) {
+            const int bit = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int col = ((wbase + j) << 5) + bit;
+            bool lost = false;
+            for (int k = 1; k <= vor->K && !lost; ++k) lost = vw_beats(d.res, w.ox + a, col, s_px[k], s_py[k], s_px[0], s_py[0]);
+            if (lost) o &= ~(1u << bit);
+          }
+        }
+        vor->own[t] = o;
+      }
     }
   }
   __syncthreads();
-  for (int ai = tid; ai < CNN8_ROWS; ai += CNN8_THREADS)
-    if ((sh.flags[ai >> 5] >> (ai & 31)) & 1u) sh.act[atomicAdd(&sh.nact, 1)] = ai;
+  // rows with work, in ascending order (a fixed order keeps the fp64 sums reproducible run to run)
+  for (int ai = tid; ai < CNN8_ROWS; ai += CNN8_THREADS) {
+    int before = 0;
+#pragma unroll
+    for (int wq = 0; wq < (CNN8_ROWS + 31) / 32; ++wq) {
+      const uint32_t f = sh.flags[wq];
+      before += wq < (ai >> 5) ? __popc(f) : (wq == (ai >> 5) ? __popc(f & ((1u << (ai & 31)) - 1u)) : 0);
+    }
+    const bool on = (sh.flags[ai >> 5] >> (ai & 31)) & 1u;
+    if (on) sh.act[before] = ai;
+    if (ai == CNN8_ROWS - 1) sh.nact = before + (on ? 1 : 0);
+  }
   __syncthreads();
 
   // ---- 2. width pass over the listed rows ----------------------------------------------------------
   float wc[16];
 #pragma unroll
   for (int q = 0; q < 16; ++q) wc[q] = sh.w[lane][q];
+  VwAcc acc;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc.cs[i] = 0.0;
+  acc.sx = acc.sxx = 0.0;
   switch (w.oy & 3) {
-    case 0: cnn8_width_pass<0>(d, sh, world, w.ox, w.oy, wbase, wc); break;
-    case 1: cnn8_width_pass<1>(d, sh, world, w.ox, w.oy, wbase, wc); break;
-    case 2: cnn8_width_pass<2>(d, sh, world, w.ox, w.oy, wbase, wc); break;
-    default: cnn8_width_pass<3>(d, sh, world, w.ox, w.oy, wbase, wc); break;
+    case 0: cnn8_width_pass<0, VOR>(d, sh, world, w.ox, w.oy, wbase, wc, vor, acc); break;
+    case 1: cnn8_width_pass<1, VOR>(d, sh, world, w.ox, w.oy, wbase, wc, vor, acc); break;
+    case 2: cnn8_width_pass<2, VOR>(d, sh, world, w.ox, w.oy, wbase, wc, vor, acc); break;
+    default: cnn8_width_pass<3, VOR>(d, sh, world, w.ox, w.oy, wbase, wc, vor, acc); break;
+  }
+  if (VOR) {
+    // fold with the column coordinates; one deterministic CTA reduction below
+    double m = 0.0, smy = 0.0, s2 = acc.sxx;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double y = (double)(w.oy + 8 * lane + i) + 0.5;
+      m += acc.cs[i];
+      smy = fma(y, acc.cs[i], smy);
+      s2 = fma(y * y, acc.cs[i], s2);
+    }
+    const Sum4 tot = reduce4(m, acc.sx, smy, s2);
+    if (lane == 0) vor->red[warp][0] = tot.m, vor->red[warp][1] = tot.sx, vor->red[warp][2] = tot.sy, vor->red[warp][3] = tot.s2;
   }
 
   // width pass of the obstacle indicator for this lane's output column
@@ -310,6 +438,12 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
     oy_out = fmaf(wc[q], in_y ? 0.f : 1.f, oy_out);
   }
   __syncthreads();
+  if (VOR && tid < 4) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < CNN8_WARPS; ++k) t += vor->red[k][tid];
+    wsums[er * 4 + tid] = t;
+  }
 
   // ---- 3. height pass: output rows 4 warp .. 4 warp + 3, taps in ascending row order --------------
 #pragma unroll

@@ -213,7 +213,7 @@ const double *ccb_ctrl_actions_dev(const ccb_ctrl *c);
  * which = 0 Voronoi label+reduce (world map), 1 same on the explored-IDF map, 2 per-robot window
  * variant, 3 sensor-window marking, 4 CNN input (C = 32, scratch_dev = E x R x 4 x 32 x 32 floats),
  * 5 cell finalisation, 6 the per-site reduce of the whole-map Voronoi alone (on the row partition a
- * previous which = 0 left), 7 its row partition alone */
+ * previous which = 0 left), 7 its row partition alone, 8 the CNN input fused with the window Voronoi */
 int ccb_bench_kernel(ccb_env *env, int which, int iters, float *scratch_dev);
 uint64_t ccb_kernel_launch_count(void);
 

@@ -77,3 +77,50 @@ def test_window_kernel_matches_generic_kernel_and_oracle(N, L, S, fill, ties):
             assert np.allclose(new[s][0], og, rtol=1e-4, atol=1e-6), f"goals vs oracle, step {s}"
             assert np.allclose(new[s][1], oa, rtol=1e-4, atol=1e-6), f"actions vs oracle, step {s}"
             oenv.step_actions(oa)
+
+
+@pytest.mark.parametrize("fill", [False, True])
+def test_observation_kernel_supplies_the_next_window_moments(monkeypatch, fill):
+    """With a DecentralizedCVT attached, the CNN-input kernel also reduces the robots' window Voronoi
+    (obs.cuh, VOR variant) and the next ComputeActions uses those moments: same goals / trajectory as with
+    the two kernels kept apart (CCB_NO_WFUSE), observation bit-identical."""
+    import torch
+
+    import coverage_control as cc
+    from coveragecontrol_b200 import BatchedCoverageSystem, BatchedCVT, _lib
+
+    N, R, E, C = 512, 14, 3, 32
+    p = cc.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    p.pNumRobots = R
+    p.pRobotMapUseUnknownImportance = fill
+    p.pTimeStep = 0.2
+    rng = np.random.default_rng(23)
+    worlds = [rng.random((N, N)).astype(np.float32) for _ in range(E)]
+    pos = rng.uniform(1, N - 1, (E, R, 2))
+    c = N / 2.0
+    pos[0, 0], pos[0, 1], pos[0, 2] = [c, c], [c + 11.0, c], [c, c + 11.0]   # exact ties (rows / columns)
+    pos[1, 0], pos[1, 1] = [2.5, 3.5], [N - 1.5, N - 9.0]                     # clipped windows
+    runs = []
+    for nofuse in ("1", "0"):
+        monkeypatch.setenv("CCB_NO_WFUSE", nofuse)
+        monkeypatch.setenv("CCB_NO_GRAPH", "1")
+        env = BatchedCoverageSystem(p, E, R)
+        for e in range(E):
+            env.set_world(e, worlds[e])
+        env.reset(pos)
+        ctrl = BatchedCVT(env, 2)
+        obs = torch.zeros((E, R, 4, C, C), dtype=torch.float32, device="cuda")
+        trace = []
+        for s in range(6):
+            ctrl.compute_actions()
+            trace.append(ctrl.goals().copy())
+            env.step_actions(ctrl.actions())
+            _lib.check(_lib.load().ccb_env_cnn_input_dev(env._h, C, 1, obs.data_ptr()))
+            trace.append(obs.cpu().numpy().copy())
+        runs.append(trace)
+    for s, (a, b) in enumerate(zip(*runs)):
+        if s % 2 == 0:
+            assert np.allclose(a, b, rtol=1e-11, atol=1e-9), f"goals differ at step {s // 2}"
+        else:
+            assert np.array_equal(a, b), f"observation differs at step {s // 2}"
