@@ -323,6 +323,7 @@ def main():
         "voronoi_global(partition+reduce+fixup)": (0, 4.0 * cells * E),
         "k_vg_reduce": (6, 4.0 * cells * E),
         "k_vg_partition": (7, 4.0 * N_ROBOTS * N_WORLD * E),
+        "k_vg_fixup": (9, 0.0),
         "k_voronoi_window": (2, 4.0 * N_ROBOTS * LOCAL * LOCAL * E),
         "k_cnn_fused8(+k_comm_maps)": (4, (4.0 * N_ROBOTS * LOCAL * LOCAL + 16.0 * N_ROBOTS * CNN * CNN) * E),
         "k_cnn_fused8<window Voronoi>(+k_comm_maps)": (8, (4.0 * N_ROBOTS * LOCAL * LOCAL + 16.0 * N_ROBOTS * CNN * CNN) * E),

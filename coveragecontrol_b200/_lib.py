@@ -98,6 +98,7 @@ SIGNATURES = {
     "ccb_env_exploration_ratios": (C.c_int, [C.c_void_p, c_double_p]),
     "ccb_env_check_oscillation": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int_p]),
     "ccb_env_sync": (C.c_int, [C.c_void_p]),
+    "ccb_env_flagged_rows": (C.c_int, [C.c_void_p, c_int_p, c_int_p, C.c_int]),
     "ccb_env_world_dev": (C.c_void_p, [C.c_void_p]),
     "ccb_env_positions_dev": (C.c_void_p, [C.c_void_p]),
     "ccb_env_set_band_mode": (C.c_int, [C.c_void_p, C.c_int]),

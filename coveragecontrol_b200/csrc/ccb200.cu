@@ -1238,6 +1238,19 @@ extern "C" int ccb_env_check_oscillation(ccb_env *env, int e, int robot, int *ou
   return 0;
 }
 
+// diagnostics: rows the last site-ordered whole-map Voronoi handed to the exact per-cell rule
+extern "C" int ccb_env_flagged_rows(ccb_env *env, int *count, int *rows, int cap) {
+  CCB_CUDA(cudaSetDevice(env->device));
+  *count = 0;
+  if (!env->d_vg_flag) return 0;
+  CCB_CUDA(cudaStreamSynchronize(env->aux));
+  CCB_CUDA(cudaStreamSynchronize(env->stream));
+  CCB_CUDA(cudaMemcpy(count, env->d_vg_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  const int n = std::min(*count, cap);
+  if (rows && n > 0) CCB_CUDA(cudaMemcpy(rows, env->d_vg_flag + 1, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 extern "C" int ccb_env_sync(ccb_env *env) {
   CCB_CUDA(cudaSetDevice(env->device));
   CCB_CUDA(cudaStreamSynchronize(env->aux));
@@ -1528,6 +1541,7 @@ extern "C" int ccb_bench_kernel(ccb_env *env, int which, int iters, float *scrat
       case 5: if (launch_finalize(env, env->d_sums, env->cells, 0)) return 1; env->cells_version = 0; break;
       case 6: if (launch_voronoi_global(env, SRC_WORLD, env->d_sums, nullptr, 0, -1, 2)) return 1; env->cells_version = 0; break;
       case 7: if (launch_voronoi_global(env, SRC_WORLD, env->d_sums, nullptr, 0, -1, 1)) return 1; env->cells_version = 0; break;
+      case 9: if (launch_voronoi_global(env, SRC_WORLD, env->d_sums, nullptr, 0, -1, 4)) return 1; env->cells_version = 0; break;
       default: return fail("ccb_bench_kernel: unknown kernel id");
     }
   }

@@ -46,7 +46,7 @@ struct VgArgs {
   int *labels;          // optional [E][N*N]
 };
 
-__device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row, const int *s_ord, const double *s_x,
+__device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row, int Rs, const int *s_ord, const double *s_x,
                                                  const double *s_y, const double *s_inv, int *s_rmin, int *s_rmax);
 
 __global__ void k_vg_init_span(int *span, int n) {
@@ -63,6 +63,10 @@ __global__ void __launch_bounds__(VG_PART_THREADS) k_vg_partition(VgArgs a) {
   const int e = blockIdx.y, tid = threadIdx.x, R = d.R, N = d.N;
   const double *pos = d.pos_g + (size_t)e * R * 2;
   // sites sorted by (py, index): rank by counting
+  __shared__ int t_ord[VG_MAXR];
+  __shared__ double t_x[VG_MAXR], t_y[VG_MAXR];
+  __shared__ unsigned char t_keep[VG_MAXR];
+  __shared__ int s_nkeep;
   for (int k = tid; k < R; k += VG_PART_THREADS) {
     const double yk = pos[2 * k + 1];
     int rank = 0;
@@ -70,18 +74,64 @@ __global__ void __launch_bounds__(VG_PART_THREADS) k_vg_partition(VgArgs a) {
       const double yj = pos[2 * j + 1];
       rank += (yj < yk || (yj == yk && j < k)) ? 1 : 0;
     }
-    s_ord[rank] = k, s_x[rank] = pos[2 * k], s_y[rank] = yk;
+    t_ord[rank] = k, t_x[rank] = pos[2 * k], t_y[rank] = yk;
     s_rmin[k] = 0x7fffffff, s_rmax[k] = 0;
   }
   __syncthreads();
-  for (int idx = tid; idx < R * R; idx += VG_PART_THREADS) {
-    const int p = idx / R, q = idx - p * R;
+  // Band cull: d2_q - d2_p is affine in the cell centre, so a site q that is farther than one and the
+  // same site p at the four corner cells of this CTA's row band owns no cell of the band: the sweeps
+  // below run over the ~10 sites whose cells reach the band instead of all R.
+  {
+    const double res = d.res;
+    const int rlo = a.row0 + blockIdx.x * VG_PART_THREADS, rhi = min(rlo + VG_PART_THREADS, a.row1) - 1;
+    const double cxs[2] = {cell_centre(rlo, res), cell_centre(rhi, res)};
+    const double cys[2] = {cell_centre(0, res), cell_centre(N - 1, res)};
+    // thread (q, part): site q against every parts-th site p
+    const int parts = max(1, VG_PART_THREADS / R);
+    // a site that coincides with a lower-indexed one never wins under the stated rule (equal d2, strict <):
+    // dropped here, otherwise every row the pair reaches would be flagged as inseparable
+    for (int q = tid; q < R; q += VG_PART_THREADS) {
+      bool dup = false;
+      for (int p = 0; p < R; ++p) dup = dup || (t_ord[p] < t_ord[q] && t_x[p] == t_x[q] && t_y[p] == t_y[q]);
+      t_keep[q] = dup ? 0 : 1;
+    }
+    __syncthreads();
+    for (int t = tid; t < R * parts; t += VG_PART_THREADS) {
+      const int q = t % R, part = t / R;
+      double fq[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) fq[c] = d2_exact(cxs[c & 1], cys[c >> 1], t_x[q], t_y[q]);
+      bool dominated = false;
+      for (int p = part; p < R && !dominated; p += parts) {
+        if (p == q || (t_x[p] == t_x[q] && t_y[p] == t_y[q])) continue;  // a twin dominates nothing
+        bool all = true;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double fp = d2_exact(cxs[c & 1], cys[c >> 1], t_x[p], t_y[p]);
+          all = all && (fq[c] - fp > 1e-7 * (1.0 + fp));
+        }
+        dominated = all;
+      }
+      if (dominated) t_keep[q] = 0;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {  // compact, keeping the sorted order
+    int n = 0;
+    for (int q = 0; q < R; ++q)
+      if (t_keep[q]) s_ord[n] = t_ord[q], s_x[n] = t_x[q], s_y[n] = t_y[q], ++n;
+    s_nkeep = n;
+  }
+  __syncthreads();
+  const int Rs = s_nkeep;
+  for (int idx = tid; idx < Rs * Rs; idx += VG_PART_THREADS) {
+    const int p = idx / Rs, q = idx - p * Rs;
     const double dy = s_y[q] - s_y[p];
     s_inv[idx] = dy > 0.0 ? 1.0 / (2.0 * dy) : 0.0;
   }
   __syncthreads();
   const int row = a.row0 + blockIdx.x * VG_PART_THREADS + tid;
-  if (row < a.row1) vg_partition_row(a, e, row, s_ord, s_x, s_y, s_inv, s_rmin, s_rmax);
+  if (row < a.row1) vg_partition_row(a, e, row, Rs, s_ord, s_x, s_y, s_inv, s_rmin, s_rmax);
   __syncthreads();
   // the CTA's rows extend every site's row span
   for (int k = tid; k < R; k += VG_PART_THREADS)
@@ -91,7 +141,8 @@ __global__ void __launch_bounds__(VG_PART_THREADS) k_vg_partition(VgArgs a) {
     }
 }
 
-__device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row, const int *s_ord, const double *s_x,
+// Rs sorted sites survive the band cull (s_ord: their site indices); the table is written for all R
+__device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row, int Rs, const int *s_ord, const double *s_x,
                                                  const double *s_y, const double *s_inv, int *s_rmin, int *s_rmax) {
   const EnvDev &d = a.d;
   const int R = d.R, N = d.N;
@@ -105,7 +156,7 @@ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row
   bool flagged = false;
   int top = 0;
   v[0] = 0, z[0] = -INFINITY, zerr[0] = 0.0;
-  for (int q = 1; q < R; ++q) {
+  for (int q = 1; q < Rs; ++q) {
     const double yq = s_y[q], dxq = cx - s_x[q];
     while (true) {
       const int p = v[top];
@@ -131,7 +182,7 @@ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row
         flagged = true;
         break;
       }
-      const double inv = s_inv[p * R + q];
+      const double inv = s_inv[p * Rs + q];
       const double s = fma(num, inv, 0.5 * ysum);  // q is nearer than p for y > s
       // bound of the rounding error of s, plus the distance (in y) within which the rounded d2 of the
       // stated rule may order p and q differently from exact arithmetic: 1e-14 is ~45 ulp
@@ -333,20 +384,32 @@ __global__ void __launch_bounds__(256) k_vg_fixup(VgArgs a) {
     const float *world = d.world + (size_t)e * N * N;
     const uint32_t *plane = SRC == SRC_EXPLORED ? d.sysb + ((size_t)e * 2) * plane_words(d) : nullptr;
     int *labels = (LABELS && a.labels) ? a.labels + (size_t)e * N * N : nullptr;
-    if (col >= N) continue;
-    const double res = d.res, cx = cell_centre(row, res), cy = cell_centre(col, res);
+    const double res = d.res, cx = cell_centre(row, res), cy = cell_centre(min(col, N - 1), res);
     int best = 0;
-    double bd = d2_exact(cx, cy, pos[0], pos[1]);
+    double bd = d2_exact(cx, cy, __ldg(pos), __ldg(pos + 1));
     for (int k = 1; k < R; ++k) {
-      const double dd = d2_exact(cx, cy, pos[2 * k], pos[2 * k + 1]);
+      const double dd = d2_exact(cx, cy, __ldg(pos + 2 * k), __ldg(pos + 2 * k + 1));
       if (dd < bd) bd = dd, best = k;
     }
-    if (labels) labels[(size_t)row * N + col] = best;
     float v = 0.f;
-    if (SRC == SRC_WORLD || plane_bit(plane, d.NW, row, col)) v = __ldg(world + (size_t)row * N + col);
-    if (v == 0.f) continue;
+    if (col < N) {
+      if (labels) labels[(size_t)row * N + col] = best;
+      if (SRC == SRC_WORLD || plane_bit(plane, d.NW, row, col)) v = __ldg(world + (size_t)row * N + col);
+    }
+    // one set of atomics per (warp, label) instead of per cell: 32 consecutive cells rarely have more
+    // than two owners
     const double dv = (double)v, xd = (double)row + 0.5, yd = (double)col + 0.5;
-    emit(a.sums, e, R, best, dv, xd * dv, yd * dv, (xd * xd + yd * yd) * dv);
+    const int lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(0xffffffffu, v != 0.f);
+    while (todo) {
+      const int leader = __ffs(todo) - 1;
+      const int lab = __shfl_sync(0xffffffffu, best, leader);
+      const bool mine = v != 0.f && best == lab;
+      const double w = mine ? dv : 0.0;
+      const Sum4 tot = reduce4(w, xd * w, yd * w, (xd * xd + yd * yd) * w);
+      if (lane == leader) emit(a.sums, e, R, lab, tot.m, tot.sx, tot.sy, tot.s2);
+      todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
   }
 }
 

@@ -167,6 +167,9 @@ int ccb_env_voronoi_features(ccb_env *env, double *out);
 int ccb_env_exploration_ratios(ccb_env *env, double *out /* E x 2 */);
 int ccb_env_check_oscillation(ccb_env *env, int e, int robot, int *out); /* coverage_system.h:341-363 */
 int ccb_env_sync(ccb_env *env);
+/* diagnostics: how many map rows the last whole-map Voronoi pass resolved with the exact per-cell rule
+ * (csrc/vglobal.cuh k_vg_fixup) and which (entries e * N + row, at most cap) */
+int ccb_env_flagged_rows(ccb_env *env, int *count, int *rows, int cap);
 /* raw device state for zero-copy consumers (world: E x N x N floats) */
 const float *ccb_env_world_dev(const ccb_env *env);
 const double *ccb_env_positions_dev(const ccb_env *env);
