@@ -1028,17 +1028,22 @@ extern "C" int ccb_env_cnn_input_dev(ccb_env *env, int C, int use_comm, float *o
     const bool vor = env->n_decentralized > 0 && !env->no_wfuse && d.L == 256 && env->wsums_version != env->pos_version;
     const size_t smem8 = vor ? cnn8_vor_smem_bytes(d.R) : CNN8_SMEM_BYTES;
     if (smem8 > cnn8_attr) {
-      CCB_CUDA(cudaFuncSetAttribute(k_cnn_fused8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-      CCB_CUDA(cudaFuncSetAttribute(k_cnn_fused8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+      CCB_CUDA(cudaFuncSetAttribute(k_cnn_fused8<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+      CCB_CUDA(cudaFuncSetAttribute(k_cnn_fused8<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+      CCB_CUDA(cudaFuncSetAttribute(k_cnn_fused8<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+      CCB_CUDA(cudaFuncSetAttribute(k_cnn_fused8<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
       cnn8_attr = smem8;
     }
+    const dim3 g8(d.R, d.E);
+    const size_t oo = cc * (nch - 1);
+    const bool dense = d.fill != 0.f;
     if (vor) {
-      k_cnn_fused8<true><<<dim3(d.R, d.E), CNN8_THREADS, smem8, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, cc * (nch - 1),
-                                                                                env->d_wsums);
+      if (dense) k_cnn_fused8<true, true><<<g8, CNN8_THREADS, smem8, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, oo, env->d_wsums);
+      else k_cnn_fused8<true, false><<<g8, CNN8_THREADS, smem8, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, oo, env->d_wsums);
       env->wsums_version = env->pos_version;
     } else {
-      k_cnn_fused8<false><<<dim3(d.R, d.E), CNN8_THREADS, smem8, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, cc * (nch - 1),
-                                                                                 nullptr);
+      if (dense) k_cnn_fused8<false, true><<<g8, CNN8_THREADS, smem8, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, oo, nullptr);
+      else k_cnn_fused8<false, false><<<g8, CNN8_THREADS, smem8, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, oo, nullptr);
     }
   } else {
     k_cnn_local_obstacle<<<dim3(C, d.R, d.E), 256, smem, env->stream>>>(d, C, tab, out_dev, stride, 0, cc * (nch - 1));

@@ -174,7 +174,7 @@ __host__ __device__ inline size_t cnn8_vor_smem_bytes(int R) {
 }
 
 // width pass over the listed rows; S = (window origin column) & 3
-template <int S, bool VOR>
+template <int S, bool VOR, bool DENSE>
 __device__ __forceinline__ void cnn8_width_pass(const EnvDev &d, Cnn8Shared &sh, const float *__restrict__ world, int ox_map,
                                                 int oy_map, int wbase, const float (&wc)[16], const Cnn8Vor *vor, VwAcc &acc) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -193,7 +193,7 @@ __device__ __forceinline__ void cnn8_width_pass(const EnvDev &d, Cnn8Shared &sh,
   const int off = gy0 - 32 * wbase;
   const int wi = off >> 5, shf = off & 31;
   const float fill = d.fill;
-  const bool dense = fill != 0.f;
+  constexpr bool dense = DENSE;  // unseen cells carry pUnknownImportance (fill != 0): rare, compiled apart
   constexpr int BATCH = VOR ? 2 : CNN8_BATCH;  // the fused variant also carries the fp64 moments in registers
 #pragma unroll 1
   for (int base = warp * BATCH; base < nact; base += CNN8_WARPS * BATCH) {
@@ -267,7 +267,7 @@ __device__ __forceinline__ void cnn8_width_pass(const EnvDev &d, Cnn8Shared &sh,
   }
 }
 
-template <bool VOR>
+template <bool VOR, bool DENSE>
 __global__ void __launch_bounds__(CNN8_THREADS, 3)
 k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__restrict__ out,
              size_t robot_stride, size_t local_off, size_t obst_off, double *__restrict__ wsums /* VOR: [E][R][4] */) {
@@ -291,7 +291,7 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
   const Window w = make_window(d.res, p[0], p[1], 256, d.N);
   const float *world = d.world + (size_t)e * nn;
   const uint32_t *plane = robot_plane(d, d.seenb, e, r);
-  const bool dense = d.fill != 0.f;  // unseen cells carry pUnknownImportance: every in-map row counts
+  constexpr bool dense = DENSE;  // unseen cells carry pUnknownImportance: every in-map row counts
   if (VOR) {
     if (tid < 8) vor->exact[tid] = 0u;
     if (tid == 0) vor->own[CNN8_ROWS * CNN8_WORDS] = 0u;
@@ -409,10 +409,10 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
   for (int i = 0; i < 8; ++i) acc.cs[i] = 0.0;
   acc.sx = acc.sxx = 0.0;
   switch (w.oy & 3) {
-    case 0: cnn8_width_pass<0, VOR>(d, sh, world, w.ox, w.oy, wbase, wc, vor, acc); break;
-    case 1: cnn8_width_pass<1, VOR>(d, sh, world, w.ox, w.oy, wbase, wc, vor, acc); break;
-    case 2: cnn8_width_pass<2, VOR>(d, sh, world, w.ox, w.oy, wbase, wc, vor, acc); break;
-    default: cnn8_width_pass<3, VOR>(d, sh, world, w.ox, w.oy, wbase, wc, vor, acc); break;
+    case 0: cnn8_width_pass<0, VOR, DENSE>(d, sh, world, w.ox, w.oy, wbase, wc, vor, acc); break;
+    case 1: cnn8_width_pass<1, VOR, DENSE>(d, sh, world, w.ox, w.oy, wbase, wc, vor, acc); break;
+    case 2: cnn8_width_pass<2, VOR, DENSE>(d, sh, world, w.ox, w.oy, wbase, wc, vor, acc); break;
+    default: cnn8_width_pass<3, VOR, DENSE>(d, sh, world, w.ox, w.oy, wbase, wc, vor, acc); break;
   }
   if (VOR) {
     // fold with the column coordinates; one deterministic CTA reduction below
@@ -453,13 +453,15 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
     const int ai0 = 8 * ox;  // a + 4 of tap 0
     // the 16 row flags of this output row: bits ai0 .. ai0 + 15
     const uint32_t fl = __funnelshift_r(sh.flags[ai0 >> 5], sh.flags[(ai0 >> 5) + 1], ai0 & 31) & 0xffffu;
+    // taps whose window row is inside the window and the map: a in [alo, ahi)
+    const int a0 = ai0 - 4;
+    const int alo = max(0, -w.ox), ahi = min(256, d.N - w.ox);
+    const int tl = min(max(alo - a0, 0), 16), th = min(max(ahi - a0, 0), 16);
+    const uint32_t inx = th > tl ? (((1u << th) - 1u) & ~((1u << tl) - 1u)) : 0u;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      const int a = ai0 - 4 + k;
       const float wr = sh.w[ox][k];  // zero outside torch's tap range
-      const int gx = w.ox + a;
-      const bool in_x = a >= 0 && a < 256 && gx >= 0 && gx < d.N;
-      acc_obs = fmaf(wr, in_x ? oy_out : oy_all, acc_obs);
+      acc_obs = fmaf(wr, ((inx >> k) & 1u) ? oy_out : oy_all, acc_obs);
       if ((fl >> k) & 1u) acc = fmaf(wr, sh.tmp[ai0 + k][lane], acc);
     }
     float *dst = out + er * robot_stride + (size_t)ox * 32 + lane;

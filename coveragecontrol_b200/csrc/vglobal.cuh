@@ -237,8 +237,9 @@ __device__ __forceinline__ unsigned vg_keep4(int col, int lo, int hi) {
   return ((1u << b) - 1u) & ~((1u << a) - 1u);
 }
 
+constexpr int VG_RED_MINB = 7;  // resident CTAs per SM the register allocation aims for
 template <int SRC, bool LABELS>
-__global__ void __launch_bounds__(VG_RED_WARPS * 32) k_vg_reduce(VgArgs a) {
+__global__ void __launch_bounds__(VG_RED_WARPS * 32, VG_RED_MINB) k_vg_reduce(VgArgs a) {
   const EnvDev &d = a.d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.y;
@@ -343,9 +344,11 @@ __global__ void __launch_bounds__(VG_RED_WARPS * 32) k_vg_reduce(VgArgs a) {
               if ((kl >> (4 * j + i)) & 1u) lrow[32 * (base + j) + i] = k;
           }
         }
-        float4 x;  // (w[j] is only defined where keep has a bit)
-        x.x = (keep & 1u) ? w[j].x : 0.f, x.y = (keep & 2u) ? w[j].y : 0.f;
-        x.z = (keep & 4u) ? w[j].z : 0.f, x.w = (keep & 8u) ? w[j].w : 0.f;
+        float4 x = w[j];  // only defined where keep has a bit
+        if (keep != 0xfu) {  // an end of the interval, outside it, or unexplored cells
+          x.x = (keep & 1u) ? x.x : 0.f, x.y = (keep & 2u) ? x.y : 0.f;
+          x.z = (keep & 4u) ? x.z : 0.f, x.w = (keep & 8u) ? x.w : 0.f;
+        }
         const double v0 = (double)x.x, v1 = (double)x.y, v2 = (double)x.z, v3 = (double)x.w;
         // sums over the four cells with y = y0 + i
         const double s = (v0 + v1) + (v2 + v3);
