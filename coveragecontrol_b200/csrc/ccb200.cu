@@ -474,9 +474,12 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
   if (env->stream != env->aux && join_aux(env)) return 1;  // the partition tables are shared with `aux`
   CCB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * d.E * d.R, env->stream));
   if (row1 <= row0) return 0;
-  // The row partition is one sequential sweep per map row (~30 us whatever the batch): it pays once
-  // there are enough rows in the launch to fill the machine; small batches keep the tile-ordered kernel.
-  const bool site_ordered = env->vg_mode == 0 || (env->vg_mode < 0 && (long)d.E * (row1 - row0) >= 32L * 1024);
+  // Which kernel (measured: profiles/r01_sweep_c5.md).  The site-ordered path pays one sequential sweep
+  // per map row (~30 us whatever the batch) and streams every cell at the same cost; the tile-ordered
+  // kernel is faster where most 64 x 64 regions have a single owner (cells of more than ~128 K map cells:
+  // 4.7 TB/s at N = 16384, R = 64) and slower where they do not (1.5 TB/s at N = 1024, R = 32).
+  const bool site_ordered = env->vg_mode == 0 || (env->vg_mode < 0 && (long)d.E * (row1 - row0) >= 32L * 1024 &&
+                                                  (long)d.N * d.N / d.R <= 128L * 1024);
   if (d.R <= VG_MAXR && (d.N & 3) == 0 && d.N < 65536 && site_ordered) {
     // site-ordered path: row partition -> per-site interval streaming -> exact rule on flagged rows
     if (!env->d_vg_table) {

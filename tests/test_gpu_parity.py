@@ -422,3 +422,55 @@ def test_rollout_graph_replay_equals_eager(monkeypatch, kind):
                 assert np.allclose(x, y, rtol=1e-9, atol=1e-9)
         else:
             assert np.allclose(a, b, rtol=1e-9)
+
+
+def test_bench_configuration_against_oracle():
+    """The configuration bench.py measures (C2: 1024^2 world, 32 robots, TOML parameters, DecentralizedCVT,
+    objective + LPAC observation), batched wide enough that every default fast path is taken -- site-ordered
+    whole-map Voronoi, observation kernel fused with the window Voronoi, roll-outs replayed from a CUDA
+    graph -- against the CPU oracle stepping single environments."""
+    import torch
+    import torchvision
+
+    import bench
+    cc, orc = _cc(), _orc()
+    from coveragecontrol_b200 import BatchedCoverageSystem, BatchedCVT
+
+    E, C, calls, per_call = 36, 32, 4, 2
+    p = bench.toml_params(cc)
+    op = orc.params_from(p)
+    env = BatchedCoverageSystem(p, E, bench.N_ROBOTS)
+    pos = np.zeros((E, bench.N_ROBOTS, 2))
+    worlds = {}
+    for e in range(E):
+        bnd, pos[e] = bench.synth_inputs(1000 + e)
+        idf = cc.WorldIDF(p)
+        for b in bnd:
+            idf.AddNormalDistribution(cc.BivariateNormalDistribution(cc.Point2(b[0], b[1]), float(b[2]), float(b[4])))
+        idf.GenerateMap()
+        env.set_world(e, idf)
+        if e in (0, 17, 35):
+            worlds[e] = np.array(idf.GetWorldMap())
+    env.reset(pos)
+    ctrl = BatchedCVT(env, 2)
+    obj = torch.zeros((per_call, E), dtype=torch.float64, device="cuda")
+    obs = torch.zeros((E, bench.N_ROBOTS, 4, C, C), dtype=torch.float32, device="cuda")
+    for _ in range(calls):
+        ctrl.rollout_obs(per_call, True, obj.data_ptr(), C, True, obs.data_ptr(), 0)
+    torch.cuda.synchronize()
+    got_pos, got_obj, got_obs = env.positions(), obj.cpu().numpy()[-1], obs.cpu()
+    rs = lambda t: torchvision.transforms.functional.resize(  # noqa: E731
+        t, (C, C), interpolation=torchvision.transforms.InterpolationMode.BILINEAR, antialias=True)
+    for e, wm in worlds.items():
+        oenv = orc.Env(op, wm, pos[e])
+        for _ in range(calls * per_call):
+            _, a, _ = oenv.compute_actions(2)
+            oenv.step_actions(a)
+        assert np.allclose(got_pos[e], oenv.positions(), rtol=0, atol=1e-6), f"env {e}"
+        assert got_obj[e] == pytest.approx(oenv.objective(), rel=1e-4)
+        local = torch.from_numpy(np.stack([oenv.local_map(r) for r in range(bench.N_ROBOTS)]))
+        obst = torch.from_numpy(np.stack([oenv.obstacle_map(r) for r in range(bench.N_ROBOTS)]))
+        assert torch.allclose(got_obs[e, :, 0], rs(local), rtol=1e-5, atol=1e-8)
+        assert torch.allclose(got_obs[e, :, 3], rs(obst), rtol=1e-5, atol=1e-8)
+        comm = np.stack([np.stack(oenv.comm_maps(r, C, "py")) for r in range(bench.N_ROBOTS)])
+        assert np.array_equal(got_obs[e, :, 1:3].numpy(), comm)
