@@ -8,8 +8,8 @@ Workload (BASELINE.json configs[1], "C2"): 1024 x 1024 world, 32 robots, 32 Gaus
 params/coverage_control_params.toml values, DecentralizedCVT + the LPAC observation (sensor 64,
 local 256, CNN 32 x 32) + the objective, i.e. per environment step
     ComputeActions(); a = GetActions(); StepActions(a); GetObjectiveValue(); get_maps(C=32, comm)
-`--envs-per-gpu` independent environments are stepped together on every GPU (no data-path
-collective: environments are independent).  One bench "step" = one such pass over
+`--envs-per-gpu` independent environments (default 1024, the batch of BASELINE config 3) are stepped
+together on every GPU (no data-path collective: environments are independent).  One bench "step" = one such pass over
 the whole batch; `value` = environment steps per second over all GPUs.
 
 Prints ONE JSON line (rank 0).  See the task contract for the keys.
@@ -181,10 +181,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=128)
+    ap.add_argument("--envs-per-gpu", type=int, default=1024,
+                    help="independent environments stepped together on every GPU (BASELINE config 3 batches 1024)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the single-environment / C1 extras (ncu launch lists)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the single-environment / C1 extras")
+    ap.add_argument("--step-only", action="store_true",
+                    help="only the device-resident step loop (the ncu launch list of the step: no e2e arm, no per-kernel timing)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -298,6 +301,15 @@ def main():
     ms_total, launches = timed(device_step, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     value = world * E * args.steps / (ms_total * 1e-3)
+
+    if args.step_only:
+        if rank == 0:
+            print(json.dumps({"metric": "env steps/sec (1024^2 map, 32 robots)", "value": value, "unit": "env_steps/s",
+                              "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+                              "config": config, "gpu_launches": int(launches), "note": "--step-only: step loop alone"}))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the host-buffer API: actions D2H -> host -> H2D, objective D2H ----------
     host_actions = np.empty((E, N_ROBOTS, 2))

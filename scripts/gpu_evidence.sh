@@ -11,12 +11,13 @@ echo "pytest rc=$?" | tee -a $out/pytest_$tag.log
 tail -3 $out/pytest_$tag.log
 python bench.py --steps 10 --warmup 3 > $out/bench_$tag.json 2> $out/bench_$tag.err
 echo "bench rc=$?"
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > $out/bench_short_$tag.json 2> $out/bench_short_$tag.err &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $out/launches_$tag.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > $out/ncu_launches_$tag.log 2>&1
+# the step loop alone (no e2e arm, no per-kernel timing loops), IDF set-up launches filtered out
+python bench.py --steps 4 --warmup 3 --step-only > $out/bench_short_$tag.json 2> $out/bench_short_$tag.err &&
+ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(?!k_idf).*' -c 600 --csv --log-file $out/launches_$tag.csv \
+    python bench.py --steps 4 --warmup 3 --step-only > $out/ncu_launches_$tag.log 2>&1
 echo "launch list rc=$?"
 # one `ncu --set full` capture per hot kernel, at the bench's batch size (E = 128)
-for spec in 0:k_vg_reduce 7:k_vg_partition 2:k_voronoi_window 4:k_cnn_fused8; do
+for spec in 0:k_vg_reduce 7:k_vg_partition 2:k_voronoi_window 8:k_cnn_fused8; do
   which=${spec%%:*}; kern=${spec##*:}
   python scripts/prof_kernels.py --which $which --envs 128 --iters 3 > $out/prof_plain_${tag}_$kern.log 2>&1 &&
   ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"$kern" -s 1 -c 1 -f \

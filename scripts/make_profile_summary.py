@@ -52,7 +52,7 @@ if os.path.exists(lpath):
         agg[name][0] += 1
         agg[name][1] += float(r[vi].replace(",", ""))
     tot = sum(v[1] for v in agg.values()) or 1.0
-    out.append("## ncu launch list of `bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras`\n")
+    out.append("## ncu launch list of `bench.py --steps 4 --warmup 3 --step-only` (the bench's step loop alone)\n")
     out.append("Per-launch times under ncu are cold-cache and serialised: compare shares, not absolutes. "
                "IDF generation launches (environment set-up) are left out of the shares.\n")
     out.append("| kernel | launches | total us | share |\n|---|---:|---:|---:|")
@@ -75,7 +75,8 @@ KEYS = [
 ]
 traffic = {}
 TRAFFIC_KEYS = {"k_vg_reduce": "k_vg_reduce", "k_vg_partition": "k_vg_partition", "k_voronoi_window": "k_voronoi_window",
-                "k_cnn_fused8": "k_cnn_fused8(+k_comm_maps)"}
+                "k_cnn_fused8<1": "k_cnn_fused8<window Voronoi>(+k_comm_maps)", "k_cnn_fused8<(bool)1": "k_cnn_fused8<window Voronoi>(+k_comm_maps)",
+                "k_cnn_fused8<0": "k_cnn_fused8(+k_comm_maps)", "k_cnn_fused8<(bool)0": "k_cnn_fused8(+k_comm_maps)"}
 PROFILE_ENVS = 128  # scripts/gpu_evidence.sh profiles at the bench's batch size
 
 
