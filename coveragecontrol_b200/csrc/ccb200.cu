@@ -380,6 +380,9 @@ struct ccb_env {
   double *d_feat = nullptr;     // [E][R][7]
   double *d_ratio = nullptr;    // [E][3]
   float *d_scratch = nullptr;   // max(N*N, L*L) floats for host getters
+  double *h_stage[2] = {nullptr, nullptr};  // pinned host -> device staging (actions / positions), used in turn
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};  // recorded after the copy out of the slot
+  int stage_next = 0;
   double *h_pin = nullptr;      // pinned host staging, E*R*CCB_MAX_CELL_VERTS*2 doubles
   size_t h_pin_bytes = 0;
   uint64_t pos_version = 1;     // bumped whenever positions or the world map change
@@ -387,6 +390,7 @@ struct ccb_env {
   bool cells_have_polys = false;
   bool initialised = false;
   std::map<int, ResizeTab> resize;
+  std::map<const void *, size_t> func_smem;  // opt-in dynamic shared memory already granted, per kernel (on this device)
   int vor_rpw_override = 0;
   // second stream: the objective chain (global Voronoi -> finalise -> sum) reads only positions and the
   // world map, so it runs beside the observation kernels and the next step's window Voronoi.
@@ -417,6 +421,18 @@ struct ccb_env {
   bool vw_generic = false;      // CCB_VW_GENERIC: force the generic window kernel (tests)
   bool band_mode = false;       // this env holds one row band of a world tiled over several GPUs
 };
+
+// kernels that need more than 48 KB of dynamic shared memory: raise the limit once per (device, kernel)
+template <class K>
+static int ensure_smem(ccb_env *env, K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return 0;
+  size_t &have = env->func_smem[reinterpret_cast<const void *>(kernel)];
+  if (bytes > have) {
+    CCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+  }
+  return 0;
+}
 
 // every change of the robot state or the maps goes through here: new version + fork point for `aux`
 static int state_changed(ccb_env *env) {
@@ -452,12 +468,8 @@ static int pick_rpw(const ccb_env *env, int region_rows, int region_cols, int re
 
 template <int SRC, bool SINGLE, bool LABELS>
 static int run_voronoi(ccb_env *env, const VorArgs &a, dim3 grid) {
-  static size_t current = 48 * 1024;
   const size_t smem = vor_smem_bytes(env->d.R);
-  if (smem > current) {
-    CCB_CUDA(cudaFuncSetAttribute(k_voronoi<SRC, SINGLE, LABELS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    current = smem;
-  }
+  if (ensure_smem(env, k_voronoi<SRC, SINGLE, LABELS>, smem)) return 1;
   k_voronoi<SRC, SINGLE, LABELS><<<grid, VOR_THREADS, smem, env->stream>>>(a);
   CCB_LAUNCH_CHECK();
   return 0;
@@ -543,12 +555,8 @@ static int launch_voronoi_single(ccb_env *env, double *sums) {
     return 0;
   }
   if (d.L <= VW_MAXL && (d.N & 3) == 0 && !env->vw_generic) {
-    static size_t current = 48 * 1024;
     const size_t smem = vw_smem_bytes(d.R);
-    if (smem > current) {
-      CCB_CUDA(cudaFuncSetAttribute(k_voronoi_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      current = smem;
-    }
+    if (ensure_smem(env, k_voronoi_window, smem)) return 1;
     k_voronoi_window<<<dim3(d.R, d.E), VW_THREADS, smem, env->stream>>>(d, sums);
     CCB_LAUNCH_CHECK();
     return 0;
@@ -632,6 +640,10 @@ static int env_alloc(ccb_env *env) {
   CCB_CUDA(cudaMalloc(&env->d_scratch, sizeof(float) * std::max(nn, (size_t)d.L * d.L)));
   env->h_pin_bytes = sizeof(double) * std::max<size_t>(er * CCB_MAX_CELL_VERTS * 2, 64);
   CCB_CUDA(cudaMallocHost(&env->h_pin, env->h_pin_bytes));
+  for (int k = 0; k < 2; ++k) {
+    CCB_CUDA(cudaMallocHost(&env->h_stage[k], sizeof(double) * 2 * er));
+    CCB_CUDA(cudaEventCreateWithFlags(&env->ev_stage[k], cudaEventDisableTiming));
+  }
   CCB_CUDA(cudaMemsetAsync(d.world, 0, sizeof(float) * (nn * d.E + (size_t)VOR_PAD_ROWS * d.N), env->stream));
   CCB_CUDA(cudaMemsetAsync(d.seenb, 0, sizeof(uint32_t) * pw * er, env->stream));
   if (d.xseenb) CCB_CUDA(cudaMemsetAsync(d.xseenb, 0, sizeof(uint32_t) * pw * er, env->stream));
@@ -715,6 +727,10 @@ extern "C" void ccb_env_destroy(ccb_env *env) {
   cudaFree(env->d_scratch);
   cudaFree(env->d_vg_table), cudaFree(env->d_vg_flag), cudaFree(env->d_vg_span);
   cudaFreeHost(env->h_pin);
+  for (int k = 0; k < 2; ++k) {
+    cudaFreeHost(env->h_stage[k]);
+    if (env->ev_stage[k]) cudaEventDestroy(env->ev_stage[k]);
+  }
   for (auto &kv : env->resize)
     cudaFree(kv.second.d_xmin), cudaFree(kv.second.d_xsize), cudaFree(kv.second.d_w), cudaFree(kv.second.d_wfull8);
   delete env;
@@ -769,11 +785,15 @@ static int launch_mark(ccb_env *env, int e, int robot, int mark_robot, int mark_
 }
 
 static int stage_to_device(ccb_env *env, const double *host, size_t count, double *dev) {
-  // host -> pinned -> device on the env stream; the pinned buffer is reused, so wait for the copy
-  if (count * sizeof(double) > env->h_pin_bytes) return fail("staging buffer too small");
-  memcpy(env->h_pin, host, count * sizeof(double));
-  CCB_CUDA(cudaMemcpyAsync(dev, env->h_pin, count * sizeof(double), cudaMemcpyHostToDevice, env->stream));
-  CCB_CUDA(cudaStreamSynchronize(env->stream));
+  // host -> pinned slot -> device on the env stream, without waiting for the copy: two slots are used in
+  // turn and a slot is only rewritten once the copy that last read it has finished
+  if (count > 2 * (size_t)env->E * env->R) return fail("staging buffer too small");
+  const int k = env->stage_next;
+  env->stage_next ^= 1;
+  CCB_CUDA(cudaEventSynchronize(env->ev_stage[k]));
+  memcpy(env->h_stage[k], host, count * sizeof(double));
+  CCB_CUDA(cudaMemcpyAsync(dev, env->h_stage[k], count * sizeof(double), cudaMemcpyHostToDevice, env->stream));
+  CCB_CUDA(cudaEventRecord(env->ev_stage[k], env->stream));
   return 0;
 }
 
@@ -1023,20 +1043,14 @@ extern "C" int ccb_env_cnn_input_dev(ccb_env *env, int C, int use_comm, float *o
   const size_t cc = (size_t)C * C, stride = cc * nch;
   ResizeTable tab{t->d_xmin, t->d_xsize, t->d_w, t->kmax};
   size_t smem = sizeof(float) * ((size_t)t->kmax * d.L + (size_t)t->kmax * C);
-  if (smem > 48 * 1024)
-    CCB_CUDA(cudaFuncSetAttribute(k_cnn_local_obstacle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (ensure_smem(env, k_cnn_local_obstacle, smem)) return 1;
   // channel order of coverage_env_utils.py:264-276: [local, comm_x, comm_y, obstacle]
   if (t->d_wfull8 && (d.N & 3) == 0 && !getenv("CCB_CNN_GENERIC")) {
-    static size_t cnn8_attr = 0;
     const bool vor = env->n_decentralized > 0 && !env->no_wfuse && d.L == 256 && env->wsums_version != env->pos_version;
     const size_t smem8 = vor ? cnn8_vor_smem_bytes(d.R) : CNN8_SMEM_BYTES;
-    if (smem8 > cnn8_attr) {
-      CCB_CUDA(cudaFuncSetAttribute(k_cnn_fused8<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-      CCB_CUDA(cudaFuncSetAttribute(k_cnn_fused8<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-      CCB_CUDA(cudaFuncSetAttribute(k_cnn_fused8<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-      CCB_CUDA(cudaFuncSetAttribute(k_cnn_fused8<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-      cnn8_attr = smem8;
-    }
+    if (ensure_smem(env, k_cnn_fused8<false, false>, smem8) || ensure_smem(env, k_cnn_fused8<false, true>, smem8) ||
+        ensure_smem(env, k_cnn_fused8<true, false>, smem8) || ensure_smem(env, k_cnn_fused8<true, true>, smem8))
+      return 1;
     const dim3 g8(d.R, d.E);
     const size_t oo = cc * (nch - 1);
     const bool dense = d.fill != 0.f;
