@@ -266,27 +266,56 @@ static int idf_generate_rows(ccb_idf *idf, int mode, int row0, int row1, bool fi
   }
   const int NP = (int)sz.size();
 
-  BndF *d_b = nullptr;
-  float *d_px = nullptr, *d_py = nullptr, *d_imp = nullptr;
-  int *d_start = nullptr, *d_sz = nullptr;
-  float4 *d_bounds = nullptr;
-  CCB_CUDA(cudaMallocAsync(&d_b, sizeof(BndF) * hb.size(), st));
-  CCB_CUDA(cudaMemcpyAsync(d_b, hb.data(), sizeof(BndF) * hb.size(), cudaMemcpyHostToDevice, st));
-  if (NP > 0) {
-    CCB_CUDA(cudaMallocAsync(&d_px, sizeof(float) * px.size(), st));
-    CCB_CUDA(cudaMallocAsync(&d_py, sizeof(float) * py.size(), st));
-    CCB_CUDA(cudaMallocAsync(&d_imp, sizeof(float) * NP, st));
-    CCB_CUDA(cudaMallocAsync(&d_start, sizeof(int) * NP, st));
-    CCB_CUDA(cudaMallocAsync(&d_sz, sizeof(int) * NP, st));
-    CCB_CUDA(cudaMallocAsync(&d_bounds, sizeof(float4) * NP, st));
-    CCB_CUDA(cudaMemcpyAsync(d_px, px.data(), sizeof(float) * px.size(), cudaMemcpyHostToDevice, st));
-    CCB_CUDA(cudaMemcpyAsync(d_py, py.data(), sizeof(float) * py.size(), cudaMemcpyHostToDevice, st));
-    CCB_CUDA(cudaMemcpyAsync(d_imp, imp.data(), sizeof(float) * NP, cudaMemcpyHostToDevice, st));
-    CCB_CUDA(cudaMemcpyAsync(d_start, start.data(), sizeof(int) * NP, cudaMemcpyHostToDevice, st));
-    CCB_CUDA(cudaMemcpyAsync(d_sz, sz.data(), sizeof(int) * NP, cudaMemcpyHostToDevice, st));
-    CCB_CUDA(cudaMemcpyAsync(d_bounds, bounds.data(), sizeof(float4) * NP, cudaMemcpyHostToDevice, st));
+  // coarse bucket grid over the features: bucket (bx, by) lists, in ascending order, the features whose
+  // truncation box (a little larger than the one the kernel tests per tile) touches it
+  const int bk_size = 256;
+  const int bk_nb = (N + bk_size - 1) / bk_size;
+  std::vector<int> bk_start((size_t)bk_nb * bk_nb + 1, 0), bk_items;
+  {
+    const double T = std::sqrt((double)p.pTruncationBND * p.pTruncationBND) * 1.001 + 1e-2;
+    const double cell = p.pResolution * bk_size;
+    std::vector<std::array<int, 4>> span(F);
+    for (int i = 0; i < F; ++i) {
+      const auto &b = idf->bnds[i];
+      const double rx = T * std::fabs(b[2]) + 2 * p.pResolution, ry = T * std::fabs(b[3]) + 2 * p.pResolution;
+      int x0 = (int)std::floor((b[0] - rx) / cell), x1 = (int)std::floor((b[0] + rx) / cell);
+      int y0 = (int)std::floor((b[1] - ry) / cell), y1 = (int)std::floor((b[1] + ry) / cell);
+      x0 = std::max(x0, 0), y0 = std::max(y0, 0), x1 = std::min(x1, bk_nb - 1), y1 = std::min(y1, bk_nb - 1);
+      span[i] = {x0, x1, y0, y1};
+      for (int bx = x0; bx <= x1; ++bx)
+        for (int by = y0; by <= y1; ++by) bk_start[(size_t)bx * bk_nb + by + 1]++;
+    }
+    for (size_t k = 1; k < bk_start.size(); ++k) bk_start[k] += bk_start[k - 1];
+    bk_items.resize(std::max<size_t>(bk_start.back(), 1));
+    std::vector<int> fill(bk_start.begin(), bk_start.end() - 1);
+    for (int i = 0; i < F; ++i)
+      for (int bx = span[i][0]; bx <= span[i][1]; ++bx)
+        for (int by = span[i][2]; by <= span[i][3]; ++by) bk_items[fill[(size_t)bx * bk_nb + by]++] = i;
   }
-  PolyDev pd{d_px, d_py, d_start, d_sz, d_imp, d_bounds, NP};
+  // everything the kernel reads goes up in ONE blob (one allocation, one copy): the order counter for the
+  // maximum, the feature records, the bucket grid and the polygon pieces, each section 16-byte aligned
+  std::vector<unsigned char> blob;
+  auto put = [&blob](const void *src, size_t bytes) -> size_t {
+    const size_t off = (blob.size() + 15) & ~(size_t)15;
+    blob.resize(off + bytes);
+    if (bytes) memcpy(blob.data() + off, src, bytes);
+    return off;
+  };
+  const size_t o_b = put(hb.data(), sizeof(BndF) * hb.size());
+  const size_t o_bs = put(bk_start.data(), sizeof(int) * bk_start.size());
+  const size_t o_bi = put(bk_items.data(), sizeof(int) * bk_items.size());
+  const size_t o_px = put(px.data(), sizeof(float) * px.size()), o_py = put(py.data(), sizeof(float) * py.size());
+  const size_t o_imp = put(imp.data(), sizeof(float) * imp.size());
+  const size_t o_start = put(start.data(), sizeof(int) * start.size()), o_sz = put(sz.data(), sizeof(int) * sz.size());
+  const size_t o_bounds = put(bounds.data(), sizeof(float4) * bounds.size());
+  unsigned char *d_blob = nullptr;
+  CCB_CUDA(cudaMallocAsync(&d_blob, blob.size(), st));
+  CCB_CUDA(cudaMemcpyAsync(d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
+  const BndF *d_b = reinterpret_cast<const BndF *>(d_blob + o_b);
+  const int *d_bk_start = reinterpret_cast<const int *>(d_blob + o_bs), *d_bk_items = reinterpret_cast<const int *>(d_blob + o_bi);
+  PolyDev pd{reinterpret_cast<const float *>(d_blob + o_px), reinterpret_cast<const float *>(d_blob + o_py),
+             reinterpret_cast<const int *>(d_blob + o_start), reinterpret_cast<const int *>(d_blob + o_sz),
+             reinterpret_cast<const float *>(d_blob + o_imp), reinterpret_cast<const float4 *>(d_blob + o_bounds), NP};
 
   const int init = (int)0x80000000;
   CCB_CUDA(cudaMemcpyAsync(idf->d_max, &init, sizeof(int), cudaMemcpyHostToDevice, st));
@@ -297,21 +326,15 @@ static int idf_generate_rows(ccb_idf *idf, int mode, int row0, int row1, bool fi
   if (row1 > row0) {
     dim3 grid((N + IDF_TY - 1) / IDF_TY, (row1 - row0 + IDF_TX - 1) / IDF_TX);
     if (mode == 0)
-      k_idf_generate<0><<<grid, IDF_THREADS, 0, st>>>(d_b, F, pd, N, row0, row1, res, trun_sq, one_by_sqrt2, idf->d_map, idf->d_max);
+      k_idf_generate<0><<<grid, IDF_THREADS, 0, st>>>(d_b, F, d_bk_start, d_bk_items, bk_nb, bk_size, pd, N, row0, row1, res, trun_sq,
+                                                     one_by_sqrt2, idf->d_map, idf->d_max);
     else
-      k_idf_generate<1><<<grid, IDF_THREADS, 0, st>>>(d_b, F, pd, N, row0, row1, res, trun_sq, one_by_sqrt2, idf->d_map, idf->d_max);
+      k_idf_generate<1><<<grid, IDF_THREADS, 0, st>>>(d_b, F, d_bk_start, d_bk_items, bk_nb, bk_size, pd, N, row0, row1, res, trun_sq,
+                                                     one_by_sqrt2, idf->d_map, idf->d_max);
     CCB_LAUNCH_CHECK();
   }
   if (finish && idf_finish(idf, row0, row1)) return 1;
-  CCB_CUDA(cudaFreeAsync(d_b, st));
-  if (NP > 0) {
-    CCB_CUDA(cudaFreeAsync(d_px, st));
-    CCB_CUDA(cudaFreeAsync(d_py, st));
-    CCB_CUDA(cudaFreeAsync(d_imp, st));
-    CCB_CUDA(cudaFreeAsync(d_start, st));
-    CCB_CUDA(cudaFreeAsync(d_sz, st));
-    CCB_CUDA(cudaFreeAsync(d_bounds, st));
-  }
+  CCB_CUDA(cudaFreeAsync(d_blob, st));
   return 0;
 }
 

@@ -81,8 +81,9 @@ __device__ __forceinline__ float ordered_to_float(int i) {
 // differences tabulated in fp64 (more accurate than the reference, same truncation support).
 template <int MODE>
 __global__ void __launch_bounds__(IDF_THREADS)
-k_idf_generate(const BndF *__restrict__ bnd, int F, PolyDev poly, int N, int row0, int row1, float res, float trun_sq,
-               float one_by_sqrt2, float *__restrict__ out, int *__restrict__ max_ordered) {
+k_idf_generate(const BndF *__restrict__ bnd, int F, const int *__restrict__ bk_start, const int *__restrict__ bk_items, int bk_nb,
+               int bk_size, PolyDev poly, int N, int row0, int row1, float res, float trun_sq, float one_by_sqrt2,
+               float *__restrict__ out, int *__restrict__ max_ordered) {
   __shared__ int s_list[IDF_FC];
   __shared__ int s_nlist;
   __shared__ int s_scan_base;
@@ -107,6 +108,13 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, PolyDev poly, int N, int row
 
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
 
+  // The host sorted the features into a coarse grid of bk_size x bk_size-cell buckets (ascending feature
+  // index inside a bucket): the tile only scans the features whose truncation box touches its bucket.
+  const int bucket = (x0 / bk_size) * bk_nb + (y0 / bk_size);
+  const int *items = bk_items + bk_start[bucket];
+  const int Fb = bk_start[bucket + 1] - bk_start[bucket];
+  (void)F;
+
   if (tid == 0) s_scan_base = 0;
   __syncthreads();
   while (true) {
@@ -114,15 +122,15 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, PolyDev poly, int N, int row
     //      feature index, so the accumulation order is the reference's loop order) -------------
     const int base = s_scan_base;
     __syncthreads();  // everyone has read the cursor before warp 0 advances it
-    if (base >= F) break;
+    if (base >= Fb) break;
     if (tid < 32) {
       const float T = sqrtf(trun_sq) * 1.0001f + 1e-3f;
       int n = 0;
       int f = base;
-      while (f < F && n < IDF_FC) {
-        const int ff = f + tid;
+      while (f < Fb && n < IDF_FC) {
+        const int ff = f + tid < Fb ? items[f + tid] : -1;
         bool keep = false;
-        if (ff < F) {
+        if (ff >= 0) {
           BndF b = bnd[ff];
           float rx = T * b.sx + res, ry = T * b.sy + res;
           keep = !(b.mx + rx < tile_xlo || b.mx - rx > tile_xhi || b.my + ry < tile_ylo || b.my - ry > tile_yhi);
@@ -146,7 +154,7 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, PolyDev poly, int N, int row
       }
       if (tid == 0) {
         s_nlist = n;
-        s_scan_base = (n == IDF_FC) ? min(f, F) : F;
+        s_scan_base = (n == IDF_FC) ? min(f, Fb) : Fb;
       }
     }
     __syncthreads();
