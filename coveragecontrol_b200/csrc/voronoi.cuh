@@ -1,4 +1,8 @@
-// voronoi.cuh -- discrete Voronoi assignment fused with the per-cell mass / moment reductions.
+// voronoi.cuh -- discrete Voronoi assignment fused with the per-cell mass / moment reductions: the
+// TILE-ORDERED, fully general kernel (any number of sites, any map size, masked sources, robot windows).
+// The batched product path uses the site-ordered kernels of vglobal.cuh (whole map) and vwindow.cuh (robot
+// windows) where they apply; this kernel covers the rest and large single worlds, where it is the faster
+// one.  It also provides the shared helpers (cell_centre, d2_exact, reduce4, emit).
 //
 // Replaces reference cppsrc/core/src/voronoi.cpp:55-327 (CGAL arrangement + scan-line
 // rasterisation + fp64 accumulation, one OpenMP thread per site) and the per-robot windowed
