@@ -88,3 +88,28 @@ def test_explored_source_matches_tile_kernel(monkeypatch):
     assert (la >= 0).all()  # the site-ordered kernel labels every cell
     seen = lb >= 0          # the tile-ordered kernel skips regions without an explored cell
     assert seen.any() and np.array_equal(la[seen], lb[seen])
+
+
+def test_cell_polygon_with_more_vertices_than_a_warp():
+    """40 sites on a circle around a central one: its cell has 40 edges, more than the 32 lanes of the
+    warp-parallel clipping (csrc/maps.cuh clip_cell_warp) -> the sequential fallback; same vertex set as the
+    oracle's half-plane clipping, and every ring cell (a wedge cut by the map rectangle) as well."""
+    import coverage_control as cc
+    from oracle import oracle as orc
+
+    N, K = 512, 40
+    ang = 2 * np.pi * (np.arange(K) + 0.37) / K
+    pos = np.concatenate([[[256.3, 255.6]], np.stack([256.3 + 120 * np.cos(ang), 255.6 + 120 * np.sin(ang)], 1)])
+    p = cc.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    p.pNumRobots = len(pos)
+    wm = np.random.default_rng(3).random((N, N)).astype(np.float32)
+    env = cc.CoverageSystem(p, cc.WorldIDF(p, wm), cc.PointVector(pos))
+    cells = env.GetVoronoiCells()
+    ocells = orc.voronoi(pos, wm)
+    assert len(np.array(cells[0].cell)) == K
+    for c, o in zip(cells, ocells):
+        a = np.array(sorted(map(tuple, np.round(np.array(c.cell), 6))))
+        b = np.array(sorted(map(tuple, np.round(o.polygon(), 6))))
+        assert a.shape == b.shape and np.allclose(a, b, atol=1e-5)
+        assert c.mass == pytest.approx(o.mass, rel=1e-9)
