@@ -75,6 +75,7 @@ SIGNATURES = {
     "ccb_env_set_world_host": (C.c_int, [C.c_void_p, C.c_int, c_float_p]),
     "ccb_env_set_world_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ccb_env_reset": (C.c_int, [C.c_void_p, c_double_p]),
+    "ccb_env_reset_env": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "ccb_env_step_actions": (C.c_int, [C.c_void_p, c_double_p, c_int_p]),
     "ccb_env_step_control": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
     "ccb_env_set_positions": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
@@ -95,6 +96,7 @@ SIGNATURES = {
     "ccb_env_objective": (C.c_int, [C.c_void_p, c_double_p]),
     "ccb_env_voronoi_labels": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]),
     "ccb_env_voronoi_features": (C.c_int, [C.c_void_p, c_double_p]),
+    "ccb_env_voronoi_features_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ccb_env_exploration_ratios": (C.c_int, [C.c_void_p, c_double_p]),
     "ccb_env_check_oscillation": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int_p]),
     "ccb_env_sync": (C.c_int, [C.c_void_p]),

@@ -387,7 +387,7 @@ class WorldIDF:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and _lib is not None and getattr(_lib, "load", None):  # (module globals are gone at interpreter exit)
             _lib.load().ccb_idf_destroy(h)
 
     # world_idf.h:130-171
@@ -601,7 +601,7 @@ class _EnvBase:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and _lib is not None and getattr(_lib, "load", None):
             _lib.load().ccb_env_destroy(h)
 
     def _invalidate(self):
@@ -986,7 +986,7 @@ class _CVT:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h and getattr(self._env, "_h", None):
+        if h and getattr(self._env, "_h", None) and _lib is not None and getattr(_lib, "load", None):
             _lib.load().ccb_ctrl_destroy(h)
 
     def ComputeActions(self) -> int:
@@ -1111,6 +1111,19 @@ class BatchedCoverageSystem(_EnvBase):
         if p.shape != (self._E, self._R, 2):
             raise ValueError(f"positions must have shape ({self._E}, {self._R}, 2)")
         _lib.check(_lib.load().ccb_env_reset(self._h, _dp(p)))
+        self._invalidate()
+
+    def reset_env(self, e: int, positions) -> None:
+        """A fresh episode in slot ``e`` (set its world first with :meth:`set_world`): positions ``[R, 2]``."""
+        p = np.ascontiguousarray(positions, np.float64)
+        if p.shape != (self._R, 2):
+            raise ValueError(f"positions must have shape ({self._R}, 2)")
+        _lib.check(_lib.load().ccb_env_reset_env(self._h, int(e), _dp(p)))
+        self._invalidate()
+
+    def step_actions_device(self, actions_dev_ptr: int) -> None:
+        """StepActions with the actions already on the device (``E x R x 2`` float64)."""
+        _lib.check(_lib.load().ccb_env_step_actions_dev(self._h, actions_dev_ptr))
         self._invalidate()
 
     def step_actions(self, actions) -> None:

@@ -838,6 +838,27 @@ extern "C" int ccb_env_reset(ccb_env *env, const double *positions) {
   return 0;
 }
 
+// RobotModel::Initialize + InitSetup for ONE environment of the batch (a fresh episode in that slot:
+// the world map is set separately with ccb_env_set_world_*); positions = R x 2
+extern "C" int ccb_env_reset_env(ccb_env *env, int e, const double *positions) {
+  if (check_env_index(env, e)) return 1;
+  if (!env->initialised) return fail("environment has no robot positions yet (call ccb_env_reset first)");
+  CCB_CUDA(cudaSetDevice(env->device));
+  if (join_aux(env)) return 1;
+  const EnvDev &d = env->d;
+  const size_t pw = plane_words(d);
+  if (stage_to_device(env, positions, 2 * (size_t)d.R, env->d_stage)) return 1;
+  CCB_CUDA(cudaMemsetAsync(robot_plane(d, d.seenb, e, 0), 0, sizeof(uint32_t) * pw * d.R, env->stream));
+  if (d.xseenb) CCB_CUDA(cudaMemsetAsync(robot_plane(d, d.xseenb, e, 0), 0, sizeof(uint32_t) * pw * d.R, env->stream));
+  CCB_CUDA(cudaMemsetAsync(sys_plane(d, e, 0), 0, sizeof(uint32_t) * pw * 2, env->stream));
+  CCB_CUDA(cudaMemsetAsync(d.status + e, 0, sizeof(int), env->stream));
+  k_init_positions<<<(d.R + 255) / 256, 256, 0, env->stream>>>(d, env->d_stage, e);
+  CCB_LAUNCH_CHECK();
+  if (launch_mark(env, e, -1, 1, 1)) return 1;
+  if (state_changed(env)) return 1;
+  return 0;
+}
+
 extern "C" int ccb_env_step_actions(ccb_env *env, const double *actions, int *bad_env) {
   CCB_CUDA(cudaSetDevice(env->device));
   if (join_aux(env)) return 1;
@@ -1250,6 +1271,14 @@ extern "C" int ccb_env_voronoi_features(ccb_env *env, double *out) {
   CCB_CUDA(cudaMemcpyAsync(env->h_pin, env->d_feat, sizeof(double) * n, cudaMemcpyDeviceToHost, env->stream));
   CCB_CUDA(cudaStreamSynchronize(env->stream));
   memcpy(out, env->h_pin, sizeof(double) * n);
+  return 0;
+}
+
+extern "C" int ccb_env_voronoi_features_dev(ccb_env *env, double *out_dev) {
+  if (!env->initialised) return fail("environment has no robot positions yet");
+  CCB_CUDA(cudaSetDevice(env->device));
+  k_voronoi_features<<<dim3(env->R, env->E), 256, 0, env->stream>>>(env->d, out_dev);
+  CCB_LAUNCH_CHECK();
   return 0;
 }
 

@@ -169,11 +169,14 @@ __global__ void k_set_positions(EnvDev d, int e, int robot, int local, const dou
 }
 
 // RobotModel::Initialize (robot_model.h:124-153) positions part + InitSetup history push
-__global__ void k_init_positions(EnvDev d, const double *__restrict__ pos) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= d.E * d.R) return;
+// env_sel >= 0: only that environment, pos = its R x 2 positions; otherwise all, pos = E x R x 2
+__global__ void k_init_positions(EnvDev d, const double *__restrict__ pos, int env_sel = -1) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (env_sel >= 0 ? d.R : d.E * d.R)) return;
+  const double *src = pos + 2 * (size_t)idx;
+  if (env_sel >= 0) idx += env_sel * d.R;
   const size_t er = (size_t)idx;
-  double gx = pos[2 * er], gy = pos[2 * er + 1];
+  double gx = src[0], gy = src[1];
   d.pos_s[2 * er] = gx, d.pos_s[2 * er + 1] = gy;
   d.pos_g[2 * er] = gx, d.pos_g[2 * er + 1] = gy;
   d.pos_l[2 * er] = 0, d.pos_l[2 * er + 1] = 0;

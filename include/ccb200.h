@@ -109,6 +109,8 @@ int ccb_env_set_world_dev(ccb_env *env, int e, const float *map_dev);
 /* RobotModel::Initialize (robot_model.h:124-153) + CoverageSystem::InitSetup
  * (coverage_system.cpp:201-226) for every environment; positions = E x R x 2 */
 int ccb_env_reset(ccb_env *env, const double *positions);
+/* the same for ONE environment of the batch (a fresh episode in slot e; set its world map first) */
+int ccb_env_reset_env(ccb_env *env, int e, const double *positions /* R x 2 */);
 /* coverage_system.h:279-291 StepActions; actions = E x R x 2.  Returns 0, or 1 when a
  * control is invalid (the reference's `true`): bad_env receives the first such env. */
 int ccb_env_step_actions(ccb_env *env, const double *actions, int *bad_env);
@@ -163,6 +165,7 @@ int ccb_env_objective(ccb_env *env, double *out /* E */); /* coverage_system.h:5
 int ccb_env_voronoi_labels(ccb_env *env, int src, int32_t *out);
 /* coverage_system.h:612-619 GetRobotVoronoiFeatures: E x R x 7 */
 int ccb_env_voronoi_features(ccb_env *env, double *out);
+int ccb_env_voronoi_features_dev(ccb_env *env, double *out_dev); /* the same, left on the device */
 /* coverage_system.h:557-571 (ratio of explored cells / IDF-weighted): 2 doubles per env */
 int ccb_env_exploration_ratios(ccb_env *env, double *out /* E x 2 */);
 int ccb_env_check_oscillation(ccb_env *env, int e, int robot, int *out); /* coverage_system.h:341-363 */
