@@ -106,7 +106,7 @@ class BatchedDataGenerator:
         shapes = {"actions": (n, R, 2), "robot_positions": (n, R, 2), "local_maps": (n, R, C, C), "obstacle_maps": (n, R, C, C),
                   "comm_maps": (n, R, 2, C, C), "coverage_features": (n, R, 7), "edge_weights": (n, R, R)}
         # (pageable output: page-locking gigabytes costs more than it saves -- measured)
-        out = {k: torch.zeros(s) for k, s in shapes.items()}
+        out = {k: torch.empty(s) for k, s in shapes.items()}  # every row is written before generate() returns
         if self.save_objective:
             out["objectives"] = torch.zeros(n)
         num_conv = math.ceil(self.ratio * n)          # data_generation.py:104-107
