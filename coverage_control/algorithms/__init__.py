@@ -1,5 +1,5 @@
-"""reference python/coverage_control/algorithms/__init__.py (CVT trio; NearOptimalCVT is out of scope)."""
-from .._core import CentralizedCVT, ClairvoyantCVT, DecentralizedCVT
+"""reference python/coverage_control/algorithms/__init__.py (the four CVT controllers; ControllerNN needs the LPAC network, out of scope)."""
+from .._core import CentralizedCVT, ClairvoyantCVT, DecentralizedCVT, NearOptimalCVT
 from .controllers import ControllerCVT
 
-__all__ = ["ClairvoyantCVT", "CentralizedCVT", "DecentralizedCVT", "ControllerCVT"]
+__all__ = ["NearOptimalCVT", "ClairvoyantCVT", "CentralizedCVT", "DecentralizedCVT", "ControllerCVT"]

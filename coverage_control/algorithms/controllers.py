@@ -1,7 +1,7 @@
 """ControllerCVT with the interface of reference python/coverage_control/algorithms/controllers.py:40-88."""
 from __future__ import annotations
 
-from .._core import CentralizedCVT, ClairvoyantCVT, CoverageSystem, DecentralizedCVT, Parameters
+from .._core import CentralizedCVT, ClairvoyantCVT, CoverageSystem, DecentralizedCVT, NearOptimalCVT, Parameters
 
 
 class ControllerCVT:
@@ -9,7 +9,7 @@ class ControllerCVT:
         self.name = config["Name"]
         self.params = params
         algs = {"DecentralizedCVT": DecentralizedCVT, "ClairvoyantCVT": ClairvoyantCVT,
-                "CentralizedCVT": CentralizedCVT}
+                "CentralizedCVT": CentralizedCVT, "NearOptimalCVT": NearOptimalCVT}
         if config["Algorithm"] not in algs:
             raise ValueError(f"Unknown controller type: {config['Algorithm']}")
         self.alg = algs[config["Algorithm"]](params, env)

@@ -93,6 +93,7 @@ SIGNATURES = {
     "ccb_env_compute_voronoi": (C.c_int, [C.c_void_p]),
     "ccb_env_get_cells": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p,
                                     c_int_p, c_double_p]),
+    "ccb_env_get_cells_all": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
     "ccb_env_objective": (C.c_int, [C.c_void_p, c_double_p]),
     "ccb_env_voronoi_labels": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]),
     "ccb_env_voronoi_features": (C.c_int, [C.c_void_p, c_double_p]),

@@ -22,10 +22,11 @@ __all__ = [
     "Point2", "Point2f", "PointVector", "Point3Vector", "DblVector", "DblVectorVector", "intVector",
     "MapTypeVector", "PolygonFeature", "PolygonVector", "VoronoiCell", "VoronoiCells",
     "BivariateNormalDistribution", "BNDVector", "WorldIDF", "RobotModel", "CoverageSystem",
-    "Parameters", "CudaUtils", "ClairvoyantCVT", "CentralizedCVT", "DecentralizedCVT",
+    "Parameters", "CudaUtils", "ClairvoyantCVT", "CentralizedCVT", "DecentralizedCVT", "NearOptimalCVT",
     "BatchedCoverageSystem", "BatchedCVT",
 ]
 
+kEps = 1e-10       # reference constants.h:48
 kLargeEps = 1e-4  # reference constants.h:50
 _MAX_PRECISION = 19  # reference constants.h:57 kMaxPrecision (long double digits10 + 1)
 
@@ -1025,6 +1026,122 @@ class CentralizedCVT(_CVT):
 
 class DecentralizedCVT(_CVT):
     _KIND = 2
+
+
+class NearOptimalCVT:
+    """Drop-in for the reference ``NearOptimalCVT`` (algorithms/near_optimal_cvt.h:60-118,
+    near_optimal_cvt_algorithm.h:57-146): ``pLloydNumTries`` random site sets are relaxed with Lloyd's
+    algorithm on the world map (a site moves to its cell's centroid while it is at least one resolution
+    away, at most ``pLloydMaxIterations`` rounds), one relaxed set is chosen and the robots are assigned to
+    its centroids with the Hungarian method (here: scipy's ``linear_sum_assignment``, same optimum).
+
+    All tries advance together: they are the environments of one scratch batch over the same world map, so
+    a Lloyd round is one batched whole-map Voronoi pass.  The reference chooses the try with the smallest
+    ``GetSumIDFGoalDistSqr()``; that sum is never accumulated there (``GoalObjFunctional`` is commented out,
+    voronoi.cpp:162), so every try scores 0 and the first one wins -- ``select="reference"`` (default)
+    reproduces that, ``select="objective"`` takes the try with the smallest coverage objective instead.
+    """
+
+    def __init__(self, params: Parameters, a, b=None, *, select: str = "reference", initial_sites=None):
+        env = b if b is not None else a  # (params, env) or (params, num_robots, env)
+        if not isinstance(env, CoverageSystem):
+            raise TypeError("expected a CoverageSystem")
+        if select not in ("reference", "objective"):
+            raise ValueError("select must be 'reference' or 'objective'")
+        self._params = params.copy()
+        self._env = env
+        self._R = env._R if b is None else int(a)
+        self._select = select
+        self._initial_sites = None if initial_sites is None else np.ascontiguousarray(initial_sites, np.float64)
+        self._positions = env._positions()[0].copy()
+        self._actions = np.zeros((self._R, 2))
+        self._goals = self._positions.copy()
+        self._converged = False
+        self._scratch = None
+        self.lloyd_iterations = 0
+        self.ComputeGoals()
+
+    def _lloyd(self, sites: np.ndarray):
+        """near_optimal_cvt_algorithm.h:75-101 for all tries at once; returns the centroids [tries, R, 2]
+        of the relaxed sites and the coverage objective of every try."""
+        p, lib = self._params, _lib.load()
+        tries, R = sites.shape[0], sites.shape[1]
+        if self._scratch is None or self._scratch._E != tries:
+            sp = p.copy()
+            sp.pNumRobots = R
+            sp.pUpdateExplorationMap = False
+            self._scratch = BatchedCoverageSystem(sp, tries, R, device=self._env._device)
+        sc = self._scratch
+        self._env._sync_world()
+        for t in range(tries):
+            _lib.check(lib.ccb_env_set_world_dev(sc._h, t, lib.ccb_env_world_dev(self._env._h)))
+        active = np.ones(tries, bool)
+        cen = np.empty((tries, R, 2))
+        obj = np.empty((tries, R))
+        sites = sites.copy()
+        it = 0
+        while True:
+            sc.reset(sites)
+            _lib.check(lib.ccb_env_get_cells_all(sc._h, None, _dp(cen), _dp(obj)))
+            if it >= p.pLloydMaxIterations or not active.any():
+                break
+            far = np.linalg.norm(cen - sites, axis=2) >= p.pResolution   # sites that still move
+            far &= active[:, None]
+            active = far.any(axis=1)
+            if not active.any():
+                break
+            sites[far] = cen[far]
+            it += 1
+        self.lloyd_iterations = it
+        return cen, obj.sum(axis=1)
+
+    def ComputeGoals(self) -> None:
+        p = self._params
+        R = self._R
+        if self._initial_sites is not None:
+            sites = self._initial_sites.reshape(-1, R, 2)
+        else:
+            hi = p.pWorldMapSize * p.pResolution - 0.001   # near_optimal_cvt_algorithm.h:72
+            sites = _rng.uniform(0.001, hi, size=(max(1, p.pLloydNumTries), R, 2))
+        cen, objective = self._lloyd(sites)
+        best = 0 if self._select == "reference" else int(np.argmin(objective))
+        self.best_try, self.try_objectives = best, objective
+        centroids = cen[best]
+        from scipy.optimize import linear_sum_assignment
+
+        cost = np.linalg.norm(self._positions[:, None, :] - centroids[None, :, :], axis=2)  # :121-127
+        rows, cols = linear_sum_assignment(cost)
+        goals = np.empty((R, 2))
+        goals[rows] = centroids[cols]
+        self._goals = goals
+
+    def ComputeActions(self) -> int:
+        """near_optimal_cvt.h:93-113."""
+        p = self._params
+        self._converged = True
+        self._positions = self._env._positions()[0].copy()
+        for i in range(self._R):
+            self._actions[i] = 0.0
+            diff = self._goals[i] - self._positions[i]
+            dist = float(np.sqrt(diff[0] * diff[0] + diff[1] * diff[1]))
+            if dist < kEps:
+                continue
+            speed = min(p.pMaxRobotSpeed, dist / p.pTimeStep)
+            self._actions[i] = speed * (diff / dist)
+            self._converged = False
+        return 0
+
+    def GetActions(self) -> PointVector:
+        return PointVector(self._actions)
+
+    def GetGoals(self) -> PointVector:
+        return PointVector(self._goals)
+
+    def IsConverged(self) -> bool:
+        return self._converged
+
+    def GetVoronoi(self):
+        raise NotImplementedError("the Voronoi class itself is not bound in the reference either (core_binds.h:187)")
 
 
 # --------------------------------------------------------------------------------------------

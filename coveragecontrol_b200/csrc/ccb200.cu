@@ -1171,6 +1171,20 @@ extern "C" int ccb_env_get_cells(ccb_env *env, int e, double *mass, double *cent
   return 0;
 }
 
+// mass, centroid and sum |c - site|^2 v of every cell of every environment in one go (the Lloyd
+// iterations of NearOptimalCVT read all tries at once); any of the outputs may be null
+extern "C" int ccb_env_get_cells_all(ccb_env *env, double *mass, double *centroid, double *sum_dist_sqr) {
+  CCB_CUDA(cudaSetDevice(env->device));
+  if (ensure_cells(env, false)) return 1;
+  const size_t er = (size_t)env->E * env->R;
+  cudaStream_t st = env->stream;
+  if (mass) CCB_CUDA(cudaMemcpyAsync(mass, env->cells.mass, sizeof(double) * er, cudaMemcpyDeviceToHost, st));
+  if (centroid) CCB_CUDA(cudaMemcpyAsync(centroid, env->cells.centroid, sizeof(double) * 2 * er, cudaMemcpyDeviceToHost, st));
+  if (sum_dist_sqr) CCB_CUDA(cudaMemcpyAsync(sum_dist_sqr, env->cells.obj, sizeof(double) * er, cudaMemcpyDeviceToHost, st));
+  CCB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 extern "C" int ccb_env_voronoi_labels(ccb_env *env, int src, int32_t *out /* E x N x N, host */) {
   // parity-test accessor: the label the fused kernel assigns to every cell (never stored otherwise)
   if (!env->initialised) return fail("environment has no robot positions yet");

@@ -158,6 +158,8 @@ int ccb_env_compute_voronoi(ccb_env *env);
  * verts = R x CCB_MAX_CELL_VERTS x 2. */
 int ccb_env_get_cells(ccb_env *env, int e, double *mass, double *centroid, double *site,
                       double *sum_dist_sqr, int *nverts, double *verts);
+/* the same for every environment at once: mass E x R, centroid E x R x 2, sum_dist_sqr E x R (any may be NULL) */
+int ccb_env_get_cells_all(ccb_env *env, double *mass, double *centroid, double *sum_dist_sqr);
 int ccb_env_objective(ccb_env *env, double *out /* E */); /* coverage_system.h:598-601 */
 /* parity-test accessor: the site index the fused label+reduce kernel assigns to every cell
  * (src 0: world map, 1: explored-IDF map); out = E x N x N int32 on the host.  The product path
