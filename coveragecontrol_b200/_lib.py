@@ -98,6 +98,7 @@ SIGNATURES = {
     "ccb_env_voronoi_labels": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]),
     "ccb_env_voronoi_features": (C.c_int, [C.c_void_p, c_double_p]),
     "ccb_env_voronoi_features_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ccb_env_local_voronoi_features": (C.c_int, [C.c_void_p, c_double_p]),
     "ccb_env_exploration_ratios": (C.c_int, [C.c_void_p, c_double_p]),
     "ccb_env_check_oscillation": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int_p]),
     "ccb_env_sync": (C.c_int, [C.c_void_p]),

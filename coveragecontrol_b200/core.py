@@ -916,7 +916,13 @@ class CoverageSystem(_EnvBase):
         return DblVectorVector(DblVector(row) for row in out[0])
 
     def GetLocalVoronoiFeatures(self, robot_id=None):
-        raise NotImplementedError("GetLocalVoronoiFeatures is outside the hot-path scope (SURVEY.md 8f rank 4)")
+        """coverage_system.cpp:648-676 / coverage_system.h:624-633: one robot (DblVector) or all of them."""
+        out = np.empty((1, self._R, 7))
+        _lib.check(_lib.load().ccb_env_local_voronoi_features(self._h, _dp(out)))
+        if robot_id is None:
+            return DblVectorVector(DblVector(row) for row in out[0])
+        self._check_robot(robot_id)
+        return DblVector(out[0, robot_id])
 
     def GetRobotExplorationFeatures(self):
         raise NotImplementedError("GetRobotExplorationFeatures is outside the hot-path scope (SURVEY.md 8a row 4)")

@@ -1279,7 +1279,7 @@ extern "C" int ccb_env_objective(ccb_env *env, double *out) {
 extern "C" int ccb_env_voronoi_features(ccb_env *env, double *out) {
   if (!env->initialised) return fail("environment has no robot positions yet");
   CCB_CUDA(cudaSetDevice(env->device));
-  k_voronoi_features<<<dim3(env->R, env->E), 256, 0, env->stream>>>(env->d, env->d_feat);
+  k_voronoi_features<<<dim3(env->R, env->E), 256, sizeof(double) * 2 * env->R, env->stream>>>(env->d, env->d_feat, 0);
   CCB_LAUNCH_CHECK();
   const size_t n = (size_t)env->E * env->R * 7;
   CCB_CUDA(cudaMemcpyAsync(env->h_pin, env->d_feat, sizeof(double) * n, cudaMemcpyDeviceToHost, env->stream));
@@ -1291,8 +1291,21 @@ extern "C" int ccb_env_voronoi_features(ccb_env *env, double *out) {
 extern "C" int ccb_env_voronoi_features_dev(ccb_env *env, double *out_dev) {
   if (!env->initialised) return fail("environment has no robot positions yet");
   CCB_CUDA(cudaSetDevice(env->device));
-  k_voronoi_features<<<dim3(env->R, env->E), 256, 0, env->stream>>>(env->d, out_dev);
+  k_voronoi_features<<<dim3(env->R, env->E), 256, sizeof(double) * 2 * env->R, env->stream>>>(env->d, out_dev, 0);
   CCB_LAUNCH_CHECK();
+  return 0;
+}
+
+// coverage_system.cpp:648-676 GetLocalVoronoiFeatures for every robot: E x R x 7, host
+extern "C" int ccb_env_local_voronoi_features(ccb_env *env, double *out) {
+  if (!env->initialised) return fail("environment has no robot positions yet");
+  CCB_CUDA(cudaSetDevice(env->device));
+  k_voronoi_features<<<dim3(env->R, env->E), 256, sizeof(double) * 2 * env->R, env->stream>>>(env->d, env->d_feat, 1);
+  CCB_LAUNCH_CHECK();
+  const size_t n = (size_t)env->E * env->R * 7;
+  CCB_CUDA(cudaMemcpyAsync(env->h_pin, env->d_feat, sizeof(double) * n, cudaMemcpyDeviceToHost, env->stream));
+  CCB_CUDA(cudaStreamSynchronize(env->stream));
+  memcpy(out, env->h_pin, sizeof(double) * n);
   return 0;
 }
 

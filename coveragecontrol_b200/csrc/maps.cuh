@@ -533,7 +533,12 @@ __global__ void k_ratio_sums(EnvDev d, double *__restrict__ out /* [E][3] */) {
 
 // robot_model.h:408-430 GetVoronoiFeatures: single-site "Voronoi" over the robot's clipped
 // L-window of its own map.  One CTA per (robot, env).  out: [E][R][7].
-__global__ void k_voronoi_features(EnvDev d, double *__restrict__ out) {
+// local != 0: CoverageSystem::GetLocalVoronoiFeatures (coverage_system.cpp:648-676): the same window and
+// map, but only the robot's own cell among itself and its neighbours within communication range (the
+// stated rule: a cell is lost when some neighbour is strictly nearer); dynamic smem: 2 R doubles.
+__global__ void k_voronoi_features(EnvDev d, double *__restrict__ out, int local) {
+  extern __shared__ double s_nb[];  // neighbour coordinates (local mode)
+  __shared__ int s_nnb;
   const int r = blockIdx.x, e = blockIdx.y;
   const size_t er = (size_t)e * d.R + r;
   const double *p = d.pos_g + er * 2;
@@ -542,11 +547,36 @@ __global__ void k_voronoi_features(EnvDev d, double *__restrict__ out) {
   const double tx = w.x0 * res, ty = w.y0 * res;
   const double s0x = p[0] - tx, s0y = p[1] - ty;  // site in window coordinates
   const int ww = w.x1 - w.x0, wh = w.y1 - w.y0;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    if (local) {
+      const double *pos = d.pos_g + (size_t)e * d.R * 2;
+      for (int j = 0; j < d.R; ++j) {
+        if (j == r) continue;
+        const double dx = pos[2 * j] - p[0], dy = pos[2 * j + 1] - p[1];
+        if (sqrt(dx * dx + dy * dy) < d.comm_range) s_nb[2 * n] = pos[2 * j], s_nb[2 * n + 1] = pos[2 * j + 1], ++n;
+      }
+    }
+    s_nnb = n;
+  }
+  __syncthreads();
+  const int nnb = s_nnb;
   double m = 0, cx = 0, cy = 0, sd = 0, sd2 = 0;
   for (int t = threadIdx.x; t < ww * wh; t += blockDim.x) {
     int a = t / wh, b = t - a * wh;
     float vf = robot_map_value(d, e, r, w.x0 + a, w.y0 + b);
     if (vf == 0.f) continue;
+    if (nnb > 0) {
+      const double ccx = __dmul_rn(__dadd_rn((double)(w.x0 + a), 0.5), res), ccy = __dmul_rn(__dadd_rn((double)(w.y0 + b), 0.5), res);
+      const double ex = __dsub_rn(ccx, p[0]), ey = __dsub_rn(ccy, p[1]);
+      const double own = __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
+      bool lost = false;
+      for (int k = 0; k < nnb && !lost; ++k) {
+        const double fx = __dsub_rn(ccx, s_nb[2 * k]), fy = __dsub_rn(ccy, s_nb[2 * k + 1]);
+        lost = __dadd_rn(__dmul_rn(fx, fx), __dmul_rn(fy, fy)) < own;
+      }
+      if (lost) continue;
+    }
     double v = vf;
     // voronoi.h:89-95 with origin_shift = -site0 (voronoi.h:171): pt is shifted, then (pt - site)
     // shifts a second time -- the reference's quirk, kept.
@@ -574,8 +604,21 @@ __global__ void k_voronoi_features(EnvDev d, double *__restrict__ out) {
     }
     double *o = out + er * 7;
     if (vals[0] < kEps) {
-      // vertex mean of the window rectangle + origin_shift (voronoi.cpp:41-50)
-      o[0] = (0 + ww + ww + 0) / 4. - s0x, o[1] = (0 + 0 + wh + wh) / 4. - s0y;
+      if (nnb > 0) {
+        // vertex mean of (window rectangle cut by the bisectors) + origin_shift (voronoi.cpp:41-50)
+        double lx[CCB_MAX_CELL_VERTS], ly[CCB_MAX_CELL_VERTS];
+        int n = 1;
+        lx[0] = s0x, ly[0] = s0y;
+        for (int k = 0; k < nnb && n < CCB_MAX_CELL_VERTS; ++k) lx[n] = s_nb[2 * k] - tx, ly[n] = s_nb[2 * k + 1] - ty, ++n;
+        double poly[CCB_MAX_CELL_VERTS][2], tmp[CCB_MAX_CELL_VERTS][2];
+        const int nv = clip_cell(lx, ly, 1, n, 0, (double)ww, (double)wh, poly, tmp);
+        double ax = 0, ay = 0;
+        for (int v = 0; v < nv; ++v) ax += poly[v][0], ay += poly[v][1];
+        o[0] = (nv > 0 ? ax / nv : s0x) - s0x, o[1] = (nv > 0 ? ay / nv : s0y) - s0y;
+      } else {
+        // vertex mean of the window rectangle + origin_shift (voronoi.cpp:41-50)
+        o[0] = (0 + ww + ww + 0) / 4. - s0x, o[1] = (0 + 0 + wh + wh) / 4. - s0y;
+      }
     } else {
       o[0] = vals[1] / vals[0], o[1] = vals[2] / vals[0];
     }

@@ -168,6 +168,8 @@ int ccb_env_voronoi_labels(ccb_env *env, int src, int32_t *out);
 /* coverage_system.h:612-619 GetRobotVoronoiFeatures: E x R x 7 */
 int ccb_env_voronoi_features(ccb_env *env, double *out);
 int ccb_env_voronoi_features_dev(ccb_env *env, double *out_dev); /* the same, left on the device */
+/* coverage_system.cpp:648-676 GetLocalVoronoiFeatures (own cell among the robot and its neighbours): E x R x 7 */
+int ccb_env_local_voronoi_features(ccb_env *env, double *out);
 /* coverage_system.h:557-571 (ratio of explored cells / IDF-weighted): 2 doubles per env */
 int ccb_env_exploration_ratios(ccb_env *env, double *out /* E x 2 */);
 int ccb_env_check_oscillation(ccb_env *env, int e, int robot, int *out); /* coverage_system.h:341-363 */

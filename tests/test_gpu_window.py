@@ -124,3 +124,45 @@ def test_observation_kernel_supplies_the_next_window_moments(monkeypatch, fill):
             assert np.allclose(a, b, rtol=1e-11, atol=1e-9), f"goals differ at step {s // 2}"
         else:
             assert np.array_equal(a, b), f"observation differs at step {s // 2}"
+
+
+def test_local_voronoi_features_match_oracle():
+    """CoverageSystem::GetLocalVoronoiFeatures (coverage_system.cpp:648-676): the robot's own cell among itself and
+    its neighbours over the clipped local window of its own map -> [cx, cy, mass, sum d^2 v, 0, sum d v, 0]."""
+    import coverage_control as cc
+    from coverage_control.algorithms import DecentralizedCVT
+    from oracle import oracle as orc
+
+    N, R, L = 512, 10, 128
+    p = cc.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    p.pNumRobots = R
+    p.pLocalMapSize = L
+    p.pSensorSize = 48
+    p.pCommunicationRange = 100
+    bnd, pos = random_world(91, N, 14, R, sigma=(60.0, 90.0))
+    pos[0], pos[1] = [3.2, 5.7], [N - 2.3, N - 7.9]  # clipped windows
+    pos[2] = pos[3] + [20.3, -11.2]                   # close neighbours
+    op = orc.params_from(p)
+    wm, _ = orc.idf_generate(op, bnd, mode=1)
+    env = cc.CoverageSystem(p, cc.WorldIDF(p, wm), cc.PointVector(pos))
+    oenv = orc.Env(op, wm, pos)
+    ctrl = DecentralizedCVT(p, env)
+    for _ in range(5):
+        ctrl.ComputeActions()
+        a = ctrl.GetActions()
+        env.StepActions(a)
+        oenv.step_actions(np.array(a))
+    feats = np.array([list(f) for f in env.GetLocalVoronoiFeatures()])
+    P = oenv.positions()
+    for r in range(R):
+        ix, of = orc.compute_offsets(p.pResolution, P[r, 0], P[r, 1], L, N)
+        x0, y0 = ix.left + of.left, ix.bottom + of.bottom
+        trimmed = np.ascontiguousarray(oenv.robot_map(r)[x0:x0 + of.width, y0:y0 + of.height])
+        shift = np.array([x0, y0]) * p.pResolution
+        nb = oenv.neighbors(r).reshape(-1, 2) + P[r]          # neighbours' global positions
+        sites = np.concatenate([[P[r] - shift], nb - shift]) if len(nb) else np.array([P[r] - shift])
+        cell = orc.voronoi(sites, trimmed, p.pResolution, single=True, robot_id=0, map_size=(of.width, of.height))[0]
+        want = [cell.centroid[0], cell.centroid[1], cell.mass, cell.sum_idf_site_dist_sqr, 0.0, cell.sum_idf_site_dist, 0.0]
+        assert np.allclose(feats[r], want, rtol=1e-6, atol=1e-6), (r, feats[r], want)
+        assert np.allclose(list(env.GetLocalVoronoiFeatures(r)), feats[r])
