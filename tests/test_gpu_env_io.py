@@ -56,3 +56,26 @@ def test_feature_file_formats_round_trip():
         env2 = cc.CoverageSystem(p, back, d + "/r.pos")
         assert np.array_equal(np.array(env2.GetRobotPositions()), pos)
         assert np.array_equal(env2.GetSystemMap(), env.GetSystemMap())
+
+
+def test_parity():
+    """python/tests/test_parity.py:31-58, statement for statement (GenerateMapCPU is served by the same kernel
+    here, so the two maps are identical; the reference only asks for atol 1e-2)."""
+    import coverage_control
+
+    params = coverage_control.Parameters()
+    assert coverage_control.CudaUtils.IsCudaAvailable()
+    env_cuda = coverage_control.CoverageSystem(params)
+    world_idf_obj_cuda = env_cuda.GetWorldIDFObject()
+    world_idf_obj_cuda.GenerateMapCuda()
+    world_map_cuda = world_idf_obj_cuda.GetWorldMap()
+    init_robots = env_cuda.GetRobotPositions()
+    env_cpu = coverage_control.CoverageSystem(params, world_idf_obj_cuda, init_robots)
+    world_idf_obj_cpu = env_cpu.GetWorldIDFObject()
+    world_idf_obj_cpu.GenerateMapCPU()
+    world_map_cpu = world_idf_obj_cpu.GetWorldMap()
+    assert np.allclose(world_map_cuda, world_map_cpu, atol=1e-2)
+    assert np.array_equal(world_map_cuda, world_map_cpu)
+    # the plot switches of the evaluators must not crash (python/evaluators/eval_single_env.py:85-151)
+    assert env_cuda.PlotInitMap("/tmp", "InitMap") is None
+    assert env_cuda.RecordPlotData() is None
