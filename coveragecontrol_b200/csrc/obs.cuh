@@ -292,6 +292,10 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
   const float *world = d.world + (size_t)e * nn;
   const uint32_t *plane = robot_plane(d, d.seenb, e, r);
   constexpr bool dense = DENSE;  // unseen cells carry pUnknownImportance: every in-map row counts
+  // window rows that can hold a non-zero cell: inside the map and (unless unseen cells carry a value) inside
+  // the robot's seen-row span
+  int alo = max(0, -w.ox), ahi = min(256, d.N - w.ox);
+  if (!dense) alo = max(alo, d.seen_rows[2 * er] - w.ox), ahi = min(ahi, d.seen_rows[2 * er + 1] - w.ox);
   if (VOR) {
     if (tid < 8) vor->exact[tid] = 0u;
     if (tid == 0) vor->own[CNN8_ROWS * CNN8_WORDS] = 0u;
@@ -326,7 +330,7 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
     // own-cell interval of every window row (thread a <-> window row a), as k_voronoi_window
     const int a = tid, row = w.ox + a, ncols = w.y1 - w.y0;
     int lo = 0, hi = 0;
-    if (row >= w.x0 && row < w.x1 && ncols > 0) {
+    if (row >= w.x0 && row < w.x1 && ncols > 0 && a >= alo && a < ahi) {
       if (vor->K == 0) lo = 0, hi = ncols;
       else if (vw_row_interval(d.res, row, w.y0, ncols, vor->K, s_px, s_py, lo, hi)) atomicOr(&vor->exact[a >> 5], 1u << (a & 31));
     }
@@ -334,43 +338,40 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
     __syncthreads();
   }
 
-  // ---- 1. mask words, clipped to the window's map columns [cy0, cy1); all loads issued first ------
+  // ---- 1. mask words, clipped to the window's map columns [cy0, cy1).  Only the window rows inside the
+  //         robot's seen-row span can hold a bit (EnvDev::seen_rows, kept by k_mark_windows): a few steps into
+  //         an episode that is a third of the window.  Batches of CNN8_STAGE loads are issued before use.
   const int wbase = w.oy >> 5;  // arithmetic shift: floor for negative origins
   const int cy0 = max(w.oy, 0), cy1 = min(w.oy + 256, d.N);
-  constexpr int NMW = (CNN8_ROWS * CNN8_WORDS + CNN8_THREADS - 1) / CNN8_THREADS;
-  uint32_t mw[NMW], ow[VOR ? NMW : 1];
+  const int nstage = max(ahi - alo, 0) * CNN8_WORDS;
+  constexpr int CNN8_STAGE = 4;
+#pragma unroll 1
+  for (int t0 = 0; t0 < nstage; t0 += CNN8_STAGE * CNN8_THREADS) {
+    uint32_t mw[CNN8_STAGE], kw[CNN8_STAGE];
 #pragma unroll
-  for (int it = 0; it < NMW; ++it) {
-    const int t = tid + it * CNN8_THREADS;
-    const int ai = t / CNN8_WORDS, j = t - ai * CNN8_WORDS;  // ai = a + 4
-    const int a = ai - 4;
-    const int gx = w.ox + a, wd = wbase + j;
-    uint32_t m = 0u, o = 0u;
-    if (t < CNN8_ROWS * CNN8_WORDS && a >= 0 && a < 256 && gx >= 0 && gx < d.N && wd >= 0 && wd < d.NW) {
-      const int cb = wd << 5;  // map column of bit 0
-      const int lo = min(max(cy0 - cb, 0), 32), hi = min(max(cy1 - cb, 0), 32);
-      if (hi > lo) {
-        const uint32_t keep = ((hi - lo >= 32) ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) << lo;
-        m = __ldg(plane + (size_t)gx * d.NW + wd) & keep;
-        if (dense) atomicOr(&sh.flags[ai >> 5], 1u << (ai & 31));
-        if (VOR) o = vw_range_bits(vor->lo[a], vor->hi[a], cb);
+    for (int it = 0; it < CNN8_STAGE; ++it) {
+      const int t = t0 + tid + it * CNN8_THREADS;
+      const int ar = t / CNN8_WORDS, j = t - ar * CNN8_WORDS;
+      const int a = alo + ar, wd = wbase + j;
+      uint32_t m = 0u, keep = 0u;
+      if (t < nstage && wd >= 0 && wd < d.NW) {
+        keep = vw_range_bits(cy0, cy1, wd << 5);
+        if (keep) m = __ldg(plane + (size_t)(w.ox + a) * d.NW + wd) & keep;
       }
+      mw[it] = m, kw[it] = keep;
     }
-    mw[it] = m;
-    if (VOR) ow[it] = o;
-  }
 #pragma unroll
-  for (int it = 0; it < NMW; ++it) {
-    const int t = tid + it * CNN8_THREADS;
-    if (t < CNN8_ROWS * CNN8_WORDS) {
-      sh.mask[t] = mw[it];
-      const int ai = t / CNN8_WORDS;
-      if (mw[it]) atomicOr(&sh.flags[ai >> 5], 1u << (ai & 31));
+    for (int it = 0; it < CNN8_STAGE; ++it) {
+      const int t = t0 + tid + it * CNN8_THREADS;
+      if (t >= nstage) continue;
+      const int ar = t / CNN8_WORDS, j = t - ar * CNN8_WORDS;
+      const int a = alo + ar, ai = a + 4;
+      sh.mask[ai * CNN8_WORDS + j] = mw[it];
+      if (mw[it] || (dense && kw[it])) atomicOr(&sh.flags[ai >> 5], 1u << (ai & 31));
       if (VOR) {
-        uint32_t o = ow[it];
-        const int a = ai - 4, j = t - ai * CNN8_WORDS;
+        uint32_t o = kw[it] ? vw_range_bits(vor->lo[a], vor->hi[a], (wbase + j) << 5) : 0u;
         uint32_t todo = dense ? o : (o & mw[it]);
-        if (todo && a >= 0 && a < 256 && ((vor->exact[a >> 5] >> (a & 31)) & 1u)) {
+        if (todo && ((vor->exact[a >> 5] >> (a & 31)) & 1u)) {
           // per-cell rule on this row: drop the cells where some neighbour is strictly nearer
           while (todo) {
             const int bit = __ffs(todo) - 1;
@@ -381,7 +382,7 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
             if (lost) o &= ~(1u << bit);
           }
         }
-        vor->own[t] = o;
+        vor->own[ai * CNN8_WORDS + j] = o;
       }
     }
   }
