@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(VW_THREADS, 3) k_voronoi_window(EnvDev d, doub
   const double sx = pos[2 * r], sy = pos[2 * r + 1];
   // decentralized_cvt.h:89-95: clipped L-window around the robot
   const Window w = make_window(res, sx, sy, d.L, d.N);
-  const int nrows = w.x1 - w.x0, ncols = w.y1 - w.y0;
+  const int ncols = w.y1 - w.y0;
   if (tid < VW_MAXL / 32) sh.flags[tid] = 0u, sh.exact[tid] = 0u;
   if (tid == 0) sh.nact = 0, sh.mask[VW_MAXL * VW_WORDS] = 0u, sh.own[VW_MAXL * VW_WORDS] = 0u;
 
@@ -205,12 +205,19 @@ __global__ void __launch_bounds__(VW_THREADS, 3) k_voronoi_window(EnvDev d, doub
   __syncthreads();
   const int K = sh.K;
 
-  // ---- 1. own-cell interval of every window row (thread a <-> window row a = map row w.ox + a) ----
+  // window rows that can hold a cell to add: inside the clipped window and (unless unseen cells carry a value)
+  // inside the robot's seen-row span (EnvDev::seen_rows, kept by k_mark_windows)
+  const bool dense = d.fill != 0.f;
+  int alo = w.x0 - w.ox, ahi = w.x1 - w.ox;
+  if (!dense) alo = max(alo, d.seen_rows[2 * er] - w.ox), ahi = min(ahi, d.seen_rows[2 * er + 1] - w.ox);
+  ahi = min(ahi, VW_MAXL);
+
+  // ---- 1. own-cell interval of every such row (thread a <-> window row a = map row w.ox + a) ----
   {
     const int a = tid;  // VW_THREADS == VW_MAXL
     const int row = w.ox + a;
     int lo = 0, hi = 0;
-    if (a < d.L && row >= w.x0 && row < w.x1 && ncols > 0) {
+    if (a >= alo && a < ahi && ncols > 0) {
       if (K == 0) lo = 0, hi = ncols;
       else if (vw_row_interval(res, row, w.y0, ncols, K, s_px, s_py, lo, hi)) atomicOr(&sh.exact[a >> 5], 1u << (a & 31));
     }
@@ -218,29 +225,32 @@ __global__ void __launch_bounds__(VW_THREADS, 3) k_voronoi_window(EnvDev d, doub
   }
   __syncthreads();
 
-  // ---- 2. mask words: seen & window & own interval; all loads issued first -----------------------
+  // ---- 2. mask words: seen & window & own interval, batches of VW_STAGE loads issued before use ------
   const uint32_t *plane = robot_plane(d, d.seenb, e, r);
   const int wbase = w.oy >> 5;  // arithmetic shift: floor for negative origins
-  const bool dense = d.fill != 0.f;
-  constexpr int NMW = (VW_MAXL * VW_WORDS + VW_THREADS - 1) / VW_THREADS;
-  uint32_t mw[NMW], ow[NMW];
+  const int nstage = max(ahi - alo, 0) * VW_WORDS;
+  constexpr int VW_STAGE = 4;
+#pragma unroll 1
+  for (int t0 = 0; t0 < nstage; t0 += VW_STAGE * VW_THREADS) {
+    uint32_t mw[VW_STAGE], ow[VW_STAGE];
 #pragma unroll
-  for (int it = 0; it < NMW; ++it) {
-    const int t = tid + it * VW_THREADS;
-    const int a = t / VW_WORDS, j = t - a * VW_WORDS;
-    const int wd = wbase + j;
-    uint32_t m = 0u, o = 0u;
-    if (a < nrows + (w.x0 - w.ox) && a < VW_MAXL && wd >= 0 && wd < d.NW) {
-      o = vw_range_bits(sh.lo[a], sh.hi[a], wd << 5);
-      if (o) m = __ldg(plane + (size_t)(w.ox + a) * d.NW + wd) & o;
+    for (int it = 0; it < VW_STAGE; ++it) {
+      const int t = t0 + tid + it * VW_THREADS;
+      const int ar = t / VW_WORDS, j = t - ar * VW_WORDS;
+      const int a = alo + ar, wd = wbase + j;
+      uint32_t m = 0u, o = 0u;
+      if (t < nstage && wd >= 0 && wd < d.NW) {
+        o = vw_range_bits(sh.lo[a], sh.hi[a], wd << 5);
+        if (o) m = __ldg(plane + (size_t)(w.ox + a) * d.NW + wd) & o;
+      }
+      mw[it] = m, ow[it] = o;
     }
-    mw[it] = m, ow[it] = o;
-  }
 #pragma unroll
-  for (int it = 0; it < NMW; ++it) {
-    const int t = tid + it * VW_THREADS;
-    if (t < VW_MAXL * VW_WORDS) {
-      const int a = t / VW_WORDS, j = t - a * VW_WORDS;
+    for (int it = 0; it < VW_STAGE; ++it) {
+      const int t = t0 + tid + it * VW_THREADS;
+      if (t >= nstage) continue;
+      const int ar = t / VW_WORDS, j = t - ar * VW_WORDS;
+      const int a = alo + ar;
       uint32_t m = mw[it], o = ow[it];
       if ((dense ? o : m) && ((sh.exact[a >> 5] >> (a & 31)) & 1u)) {
         // per-cell rule on this row: drop the cells where some neighbour is strictly nearer
@@ -254,7 +264,7 @@ __global__ void __launch_bounds__(VW_THREADS, 3) k_voronoi_window(EnvDev d, doub
           if (lost) m &= ~(1u << bit), o &= ~(1u << bit);
         }
       }
-      sh.mask[t] = m, sh.own[t] = o;
+      sh.mask[a * VW_WORDS + j] = m, sh.own[a * VW_WORDS + j] = o;
       if (dense ? o : m) atomicOr(&sh.flags[a >> 5], 1u << (a & 31));
     }
   }
