@@ -646,8 +646,8 @@ static int env_alloc(ccb_env *env) {
   CCB_CUDA(cudaMalloc(&d.seenb, sizeof(uint32_t) * pw * er));
   if (p.pUpdateExplorationMap) CCB_CUDA(cudaMalloc(&d.xseenb, sizeof(uint32_t) * pw * er));
   CCB_CUDA(cudaMalloc(&d.sysb, sizeof(uint32_t) * pw * 2 * d.E));
-  CCB_CUDA(cudaMalloc(&d.seen_rows, sizeof(int) * 2 * er));
-  CCB_CUDA(cudaMemsetAsync(d.seen_rows, 0, sizeof(int) * 2 * er, env->stream));
+  CCB_CUDA(cudaMalloc(&d.seen_box, sizeof(int) * 4 * er));
+  CCB_CUDA(cudaMemsetAsync(d.seen_box, 0, sizeof(int) * 4 * er, env->stream));
   CCB_CUDA(cudaMalloc(&d.pos_g, sizeof(double) * 2 * er));
   CCB_CUDA(cudaMalloc(&d.pos_s, sizeof(double) * 2 * er));
   CCB_CUDA(cudaMalloc(&d.pos_l, sizeof(double) * 2 * er));
@@ -743,7 +743,7 @@ extern "C" void ccb_env_destroy(ccb_env *env) {
   if (env->ev_fork) cudaEventDestroy(env->ev_fork);
   if (env->ev_join) cudaEventDestroy(env->ev_join);
   EnvDev &d = env->d;
-  cudaFree(d.world), cudaFree(d.seenb), cudaFree(d.xseenb), cudaFree(d.sysb), cudaFree(d.seen_rows);
+  cudaFree(d.world), cudaFree(d.seenb), cudaFree(d.xseenb), cudaFree(d.sysb), cudaFree(d.seen_box);
   cudaFree(d.pos_g), cudaFree(d.pos_s), cudaFree(d.pos_l);
   cudaFree(d.hist), cudaFree(d.hist_start), cudaFree(d.hist_len), cudaFree(d.status);
   cudaFree(env->d_sums), cudaFree(env->d_wsums);
@@ -889,7 +889,9 @@ static int step_actions_dev(ccb_env *env, const double *actions_dev) {
 
 __global__ void k_reset_seen_rows(EnvDev d, int e) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < d.R) d.seen_rows[2 * ((size_t)e * d.R + r)] = 0x7fffffff, d.seen_rows[2 * ((size_t)e * d.R + r) + 1] = 0;
+  if (r >= d.R) return;
+  int *box = d.seen_box + ((size_t)e * d.R + r) * 4;
+  box[0] = box[2] = 0x7fffffff, box[1] = box[3] = 0;
 }
 __global__ void k_step_control(EnvDev d, int e, int r, double dx, double dy, double sp) {
   // robot_model.h:200-226 after the validity test, then SetRobotPosition

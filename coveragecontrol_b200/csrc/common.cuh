@@ -74,8 +74,8 @@ struct EnvDev {
   uint32_t *seenb;
   uint32_t *xseenb;
   uint32_t *sysb;
-  int *seen_rows;  // [E][R][2]: first row / last row + 1 a robot-map bit has ever been set in (a bound, kept by
-                   // k_mark_windows; the window kernels only stage the mask rows inside it)
+  int *seen_box;   // [E][R][4]: row_min, row_max + 1, col_min, col_max + 1 of the robot-map bits ever set (a bound,
+                   // kept by k_mark_windows; the window kernels only stage the mask words inside it)
   double *pos_g;   // [E][R][2] global current position
   double *pos_s;   // [E][R][2] global start position
   double *pos_l;   // [E][R][2] local current position (robot_model.h:66)

@@ -48,8 +48,8 @@ __global__ void k_mark_windows(EnvDev d, int env_sel, int robot_sel, int mark_ro
   uint32_t *xseen = d.xseenb ? robot_plane(d, d.xseenb, e, r) : nullptr;
   uint32_t *sys0 = sys_plane(d, e, 0), *sys1 = sys_plane(d, e, 1);
   if (mark_robot && d.upd_robot && blockIdx.x == 0 && threadIdx.x == 0) {
-    int *span = d.seen_rows + ((size_t)e * d.R + r) * 2;
-    atomicMin(span, w.x0), atomicMax(span + 1, w.x1);
+    int *box = d.seen_box + ((size_t)e * d.R + r) * 4;
+    atomicMin(box, w.x0), atomicMax(box + 1, w.x1), atomicMin(box + 2, w.y0), atomicMax(box + 3, w.y1);
   }
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const int a = t / nwords, wd = w0 + (t - a * nwords);
@@ -185,7 +185,7 @@ __global__ void k_init_positions(EnvDev d, const double *__restrict__ pos, int e
   d.pos_g[2 * er] = gx, d.pos_g[2 * er + 1] = gy;
   d.pos_l[2 * er] = 0, d.pos_l[2 * er + 1] = 0;
   d.hist_start[er] = 0, d.hist_len[er] = 0;
-  d.seen_rows[2 * er] = 0x7fffffff, d.seen_rows[2 * er + 1] = 0;  // nothing seen yet (the caller marks next)
+  d.seen_box[4 * er] = d.seen_box[4 * er + 2] = 0x7fffffff, d.seen_box[4 * er + 1] = d.seen_box[4 * er + 3] = 0;  // nothing seen yet
   history_post_step(d, idx / d.R, idx % d.R, gx, gy);
 }
 

@@ -292,10 +292,15 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
   const float *world = d.world + (size_t)e * nn;
   const uint32_t *plane = robot_plane(d, d.seenb, e, r);
   constexpr bool dense = DENSE;  // unseen cells carry pUnknownImportance: every in-map row counts
-  // window rows that can hold a non-zero cell: inside the map and (unless unseen cells carry a value) inside
-  // the robot's seen-row span
+  // window rows / mask words that can hold a non-zero cell: inside the map and (unless unseen cells carry a
+  // value) inside the robot's seen box
   int alo = max(0, -w.ox), ahi = min(256, d.N - w.ox);
-  if (!dense) alo = max(alo, d.seen_rows[2 * er] - w.ox), ahi = min(ahi, d.seen_rows[2 * er + 1] - w.ox);
+  int wlo = 0, whi = CNN8_WORDS;
+  if (!dense) {
+    const int *box = d.seen_box + 4 * er;
+    alo = max(alo, box[0] - w.ox), ahi = min(ahi, box[1] - w.ox);
+    wlo = max(0, (box[2] >> 5) - (w.oy >> 5)), whi = min(CNN8_WORDS, ((box[3] - 1) >> 5) - (w.oy >> 5) + 1);
+  }
   if (VOR) {
     if (tid < 8) vor->exact[tid] = 0u;
     if (tid == 0) vor->own[CNN8_ROWS * CNN8_WORDS] = 0u;
@@ -338,12 +343,20 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
     __syncthreads();
   }
 
-  // ---- 1. mask words, clipped to the window's map columns [cy0, cy1).  Only the window rows inside the
-  //         robot's seen-row span can hold a bit (EnvDev::seen_rows, kept by k_mark_windows): a few steps into
-  //         an episode that is a third of the window.  Batches of CNN8_STAGE loads are issued before use.
+  // ---- 1. mask words, clipped to the window's map columns [cy0, cy1).  Only the words inside the robot's
+  //         seen box can hold a bit (EnvDev::seen_box, kept by k_mark_windows): a few steps into an episode
+  //         that is a sixth of the window's words.  Batches of CNN8_STAGE loads are issued before use.
   const int wbase = w.oy >> 5;  // arithmetic shift: floor for negative origins
   const int cy0 = max(w.oy, 0), cy1 = min(w.oy + 256, d.N);
-  const int nstage = max(ahi - alo, 0) * CNN8_WORDS;
+  const int nrow_s = max(ahi - alo, 0), nw_s = max(whi - wlo, 0);
+  const int nstage = nrow_s * nw_s;
+  // the words of those rows outside the box hold nothing: zeros without a load
+  for (int t = tid; t < nrow_s * CNN8_WORDS; t += CNN8_THREADS) {
+    const int ar = t / CNN8_WORDS, j = t - ar * CNN8_WORDS;
+    if (j >= wlo && j < whi) continue;
+    sh.mask[(alo + ar + 4) * CNN8_WORDS + j] = 0u;
+    if (VOR) vor->own[(alo + ar + 4) * CNN8_WORDS + j] = 0u;
+  }
   constexpr int CNN8_STAGE = 4;
 #pragma unroll 1
   for (int t0 = 0; t0 < nstage; t0 += CNN8_STAGE * CNN8_THREADS) {
@@ -351,7 +364,7 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
 #pragma unroll
     for (int it = 0; it < CNN8_STAGE; ++it) {
       const int t = t0 + tid + it * CNN8_THREADS;
-      const int ar = t / CNN8_WORDS, j = t - ar * CNN8_WORDS;
+      const int ar = t / nw_s, j = wlo + t - ar * nw_s;
       const int a = alo + ar, wd = wbase + j;
       uint32_t m = 0u, keep = 0u;
       if (t < nstage && wd >= 0 && wd < d.NW) {
@@ -364,7 +377,7 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
     for (int it = 0; it < CNN8_STAGE; ++it) {
       const int t = t0 + tid + it * CNN8_THREADS;
       if (t >= nstage) continue;
-      const int ar = t / CNN8_WORDS, j = t - ar * CNN8_WORDS;
+      const int ar = t / nw_s, j = wlo + t - ar * nw_s;
       const int a = alo + ar, ai = a + 4;
       sh.mask[ai * CNN8_WORDS + j] = mw[it];
       if (mw[it] || (dense && kw[it])) atomicOr(&sh.flags[ai >> 5], 1u << (ai & 31));

@@ -206,10 +206,10 @@ __global__ void __launch_bounds__(VW_THREADS, 3) k_voronoi_window(EnvDev d, doub
   const int K = sh.K;
 
   // window rows that can hold a cell to add: inside the clipped window and (unless unseen cells carry a value)
-  // inside the robot's seen-row span (EnvDev::seen_rows, kept by k_mark_windows)
+  // inside the rows of the robot's seen box (EnvDev::seen_box, kept by k_mark_windows)
   const bool dense = d.fill != 0.f;
   int alo = w.x0 - w.ox, ahi = w.x1 - w.ox;
-  if (!dense) alo = max(alo, d.seen_rows[2 * er] - w.ox), ahi = min(ahi, d.seen_rows[2 * er + 1] - w.ox);
+  if (!dense) alo = max(alo, d.seen_box[4 * er] - w.ox), ahi = min(ahi, d.seen_box[4 * er + 1] - w.ox);
   ahi = min(ahi, VW_MAXL);
 
   // ---- 1. own-cell interval of every such row (thread a <-> window row a = map row w.ox + a) ----
