@@ -440,6 +440,10 @@ struct ccb_env {
   uint32_t *d_vg_table = nullptr;  // [E][R][N] row intervals of the site-ordered global Voronoi (vglobal.cuh)
   int *d_vg_flag = nullptr;     // [1 + E*N]: count, then the flagged rows
   int *d_vg_span = nullptr;     // [E][R][2] row span of every site
+  int *d_vg_items = nullptr;    // [E][R + 1] first (site, chunk) item of every site, then their total
+  int vg_warps = VG_RED_WARPS;  // CCB_VG_WARPS: warps per CTA of k_vg_reduce (<= VG_RED_WARPS)
+  int vg_griddiv = 4;           // CCB_VG_GRIDDIV: grid = largest possible item count / this
+  int vg_lean = 0;              // CCB_VG_LEAN: k_vg_reduce's unmasked interior run: 0 none, 1 4 passes / 72 regs, 2 8 passes / 80 regs
   int vg_mode = -1;             // CCB_VG_GENERIC: 1 forces the tile-ordered kernel, 0 the site-ordered one (tests)
   bool vw_generic = false;      // CCB_VW_GENERIC: force the generic window kernel (tests)
   bool band_mode = false;       // this env holds one row band of a world tiled over several GPUs
@@ -521,6 +525,7 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
       CCB_CUDA(cudaMalloc(&env->d_vg_table, sizeof(uint32_t) * (size_t)d.E * d.R * d.N));
       CCB_CUDA(cudaMalloc(&env->d_vg_flag, sizeof(int) * ((size_t)d.E * d.N + 1)));
       CCB_CUDA(cudaMalloc(&env->d_vg_span, sizeof(int) * 2 * (size_t)d.E * d.R));
+      CCB_CUDA(cudaMalloc(&env->d_vg_items, sizeof(int) * (size_t)d.E * (d.R + 1)));
     }
     if (stages & 1) {
       k_vg_init_span<<<(d.E * d.R + 255) / 256, 256, 0, env->stream>>>(env->d_vg_span, d.E * d.R);
@@ -529,21 +534,30 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
     if (stages & 1) CCB_CUDA(cudaMemsetAsync(env->d_vg_flag, 0, sizeof(int), env->stream));
     VgArgs g;
     g.d = d, g.row0 = row0, g.row1 = row1, g.table = env->d_vg_table, g.nflag = env->d_vg_flag, g.flag_list = env->d_vg_flag + 1, g.span = env->d_vg_span, g.sums = sums, g.labels = labels;
+    g.items = env->d_vg_items;
     const int rows = row1 - row0;
     if (stages & 1) {
       k_vg_partition<<<dim3((rows + VG_PART_THREADS - 1) / VG_PART_THREADS, d.E), VG_PART_THREADS,
                        sizeof(double) * d.R * d.R, env->stream>>>(g);
       CCB_LAUNCH_CHECK();
+      k_vg_items<<<(d.E + 3) / 4, 128, 0, env->stream>>>(env->d_vg_span, env->d_vg_items, d.E, d.R, row0);
+      CCB_LAUNCH_CHECK();
     }
+    // A site of a typical partition spans a fraction of the rows: a quarter of the largest possible item
+    // count (every site on every chunk) covers it with about one item per warp; the warps stride beyond it.
     const int chunks = (rows + VG_CHUNK - 1) / VG_CHUNK;
-    dim3 rgrid((chunks * d.R + VG_RED_WARPS - 1) / VG_RED_WARPS, d.E), fgrid(148 * 2);
+    const int max_ctas = (chunks * d.R + env->vg_warps - 1) / env->vg_warps;
+    dim3 rgrid(std::max(1, (max_ctas + env->vg_griddiv - 1) / env->vg_griddiv), d.E), fgrid(148 * 2);
     if (stages & 2) {
+      const int nt = env->vg_warps * 32;
       if (src == SRC_WORLD) {
-        if (labels) k_vg_reduce<SRC_WORLD, true><<<rgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g);
-        else k_vg_reduce<SRC_WORLD, false><<<rgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g);
+        if (labels) k_vg_reduce<SRC_WORLD, true, 0, 7><<<rgrid, nt, 0, env->stream>>>(g);
+        else if (env->vg_lean == 1) k_vg_reduce<SRC_WORLD, false, 4, 7><<<rgrid, nt, 0, env->stream>>>(g);
+        else if (env->vg_lean == 2) k_vg_reduce<SRC_WORLD, false, 8, 6><<<rgrid, nt, 0, env->stream>>>(g);
+        else k_vg_reduce<SRC_WORLD, false, 0, 7><<<rgrid, nt, 0, env->stream>>>(g);
       } else {
-        if (labels) k_vg_reduce<SRC_EXPLORED, true><<<rgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g);
-        else k_vg_reduce<SRC_EXPLORED, false><<<rgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g);
+        if (labels) k_vg_reduce<SRC_EXPLORED, true, 0, 7><<<rgrid, nt, 0, env->stream>>>(g);
+        else k_vg_reduce<SRC_EXPLORED, false, 0, 7><<<rgrid, nt, 0, env->stream>>>(g);
       }
       CCB_LAUNCH_CHECK();
     }
@@ -721,6 +735,9 @@ extern "C" ccb_env *ccb_env_create(const ccb_params *p, int num_envs, int num_ro
   if (const char *s = getenv("CCB_VOR_RPW")) env->vor_rpw_override = atoi(s);
   if (const char *s = getenv("CCB_VW_GENERIC")) env->vw_generic = atoi(s) != 0;
   if (const char *s = getenv("CCB_VG_GENERIC")) env->vg_mode = atoi(s) != 0 ? 1 : 0;
+  if (const char *s = getenv("CCB_VG_LEAN")) env->vg_lean = atoi(s);
+  if (const char *s = getenv("CCB_VG_WARPS")) env->vg_warps = std::min(std::max(atoi(s), 1), VG_RED_WARPS);
+  if (const char *s = getenv("CCB_VG_GRIDDIV")) env->vg_griddiv = std::max(atoi(s), 1);
   if (const char *s = getenv("CCB_NO_AUX")) env->no_aux = atoi(s) != 0;
   if (const char *s = getenv("CCB_NO_GRAPH")) env->no_graph = atoi(s) != 0;
   if (const char *s = getenv("CCB_NO_WFUSE")) env->no_wfuse = atoi(s) != 0;
@@ -750,7 +767,7 @@ extern "C" void ccb_env_destroy(ccb_env *env) {
   free_cells(env->cells);
   cudaFree(env->d_objective), cudaFree(env->d_stage), cudaFree(env->d_feat), cudaFree(env->d_ratio);
   cudaFree(env->d_scratch);
-  cudaFree(env->d_vg_table), cudaFree(env->d_vg_flag), cudaFree(env->d_vg_span);
+  cudaFree(env->d_vg_table), cudaFree(env->d_vg_flag), cudaFree(env->d_vg_span), cudaFree(env->d_vg_items);
   cudaFreeHost(env->h_pin);
   for (int k = 0; k < 2; ++k) {
     cudaFreeHost(env->h_stage[k]);

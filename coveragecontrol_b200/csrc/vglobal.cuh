@@ -42,6 +42,7 @@ struct VgArgs {
   int *flag_list;       // flagged rows as e * N + row, *nflag entries (zeroed before k_vg_partition)
   int *nflag;
   int *span;            // [E][R][2]: first row / last row + 1 on which the site owns a cell (within the band)
+  int *items;           // [E][R + 1]: first (site, 32-row chunk) item of every site, then the total (k_vg_items)
   double *sums;         // [E][R][4]
   int *labels;          // optional [E][N*N]
 };
@@ -231,143 +232,202 @@ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row
 }
 
 // ---- reduce ----------------------------------------------------------------------------------------
+// Items = (site, 32-row chunk) pairs on which the site owns cells, numbered site by site from the row
+// spans k_vg_partition left.  items[e][k] = number of the first item of site k, items[e][R] = their total:
+// one warp per environment (an exclusive prefix sum over <= VG_MAXR sites).
+__global__ void k_vg_items(const int *__restrict__ span, int *__restrict__ items, int E, int R, int row0) {
+  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (e >= E) return;
+  int before = 0;
+  for (int kb = 0; kb < R; kb += 32) {
+    const int kk = kb + lane;
+    int cnt = 0;
+    if (kk < R) {
+      const int2 sp = __ldg(reinterpret_cast<const int2 *>(span) + (size_t)e * R + kk);
+      if (sp.y > sp.x) cnt = (sp.y - 1 - row0) / VG_CHUNK - (sp.x - row0) / VG_CHUNK + 1;
+    }
+    int incl = cnt;  // inclusive prefix sum over the lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (kk < R) items[(size_t)e * (R + 1) + kk] = before + incl - cnt;
+    before += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) items[(size_t)e * (R + 1) + R] = before;
+}
+
 // keep bits of a lane's four cells col .. col + 3 against [lo, hi): bit i set iff lo <= col + i < hi
 __device__ __forceinline__ unsigned vg_keep4(int col, int lo, int hi) {
   const int a = min(max(lo - col, 0), 4), b = min(max(hi - col, 0), 4);
   return ((1u << b) - 1u) & ~((1u << a) - 1u);
 }
 
-constexpr int VG_RED_MINB = 7;  // resident CTAs per SM the register allocation aims for
-template <int SRC, bool LABELS>
-__global__ void __launch_bounds__(VG_RED_WARPS * 32, VG_RED_MINB) k_vg_reduce(VgArgs a) {
+// four cells y0 .. y0 + 3 (cell units) of one row into the row's sums
+__device__ __forceinline__ void vg_add4(const float4 x, const double y0, double &rs, double &rsy, double &rsyy) {
+  const double v0 = (double)x.x, v1 = (double)x.y, v2 = (double)x.z, v3 = (double)x.w;
+  const double s = (v0 + v1) + (v2 + v3);
+  const double t = fma(3.0, v3, fma(2.0, v2, v1));   // sum i v_i
+  const double u = fma(9.0, v3, fma(4.0, v2, v1));   // sum i^2 v_i
+  rs += s;
+  rsy += fma(y0, s, t);
+  rsyy += fma(y0 * y0, s, fma(y0 + y0, t, u));
+}
+
+// U passes base .. base + U - 1 of a row without masks: all requested, then all added
+template <int U>
+__device__ __forceinline__ void vg_lean_batch(const float4 *p4, int col0, int base, double &rs, double &rsy, double &rsyy) {
+  const float4 *pp = p4 + 8 * base;
+  float4 w[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) w[j] = __ldg(pp + 8 * j);
+  double y0 = (double)(col0 + 32 * base) + 0.5;
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    vg_add4(w[j], y0, rs, rsy, rsyy);
+    y0 += 32.0;
+  }
+}
+
+// LU = passes requested together in the unmasked interior run (0: no such run), MINB = resident CTAs per
+// SM the register allocation aims for (7 -> 72 registers, 6 -> 80)
+template <int SRC, bool LABELS, int LU, int MINB>
+__global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a) {
   const EnvDev &d = a.d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.y;
   const int N = d.N, R = d.R;
-  // Items = (site, 32-row chunk) pairs on which the site owns cells, numbered site by site from the row
-  // spans k_vg_partition left: the first warps of the grid get all the work, the rest exit at once.
-  const int item = blockIdx.x * VG_RED_WARPS + warp;
-  int k = -1, chunk = 0;
-  {
-    int before = 0;  // items of the sites below the ones this round looks at
-    for (int kb = 0; kb < R && k < 0; kb += 32) {
-      const int kk = kb + lane;
-      int first = 0, cnt = 0;
-      if (kk < R) {
-        const int2 sp = __ldg(reinterpret_cast<const int2 *>(a.span) + (size_t)e * R + kk);
-        if (sp.y > sp.x) first = (sp.x - a.row0) / VG_CHUNK, cnt = (sp.y - 1 - a.row0) / VG_CHUNK - first + 1;
-      }
-      int incl = cnt;  // inclusive prefix sum over the lanes
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += up;
-      }
-      const unsigned hit = __ballot_sync(0xffffffffu, item < before + incl);
-      if (hit) {
-        const int src = __ffs(hit) - 1;
-        k = kb + src;
-        chunk = __shfl_sync(0xffffffffu, first, src) + (item - before - (__shfl_sync(0xffffffffu, incl, src) - __shfl_sync(0xffffffffu, cnt, src)));
-      }
-      before += __shfl_sync(0xffffffffu, incl, 31);
-    }
-  }
-  if (k < 0) return;
-  const int rbase = a.row0 + chunk * VG_CHUNK;
-  const int myrow = rbase + lane;
-  const uint32_t iv = myrow < a.row1 ? __ldg(a.table + ((size_t)e * R + k) * N + myrow) : 0u;
-  const int lo_l = (int)(iv & 0xffffu), hi_l = (int)(iv >> 16);
+  const int *its = a.items + (size_t)e * (R + 1);
+  const int total = __ldg(its + R);
   const float *world = d.world + (size_t)e * N * N;
-  // ask for this lane's row interval to be brought into L2 now (a line per 32 columns): the whole
-  // chunk is in flight while the warp streams it, and the loads below see L2 latency
-  if (SRC == SRC_WORLD) {
-    const float *prow = world + (size_t)myrow * N;
-    for (int c = lo_l & ~31; c < hi_l; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + c));
-  }
   const uint32_t *plane = SRC == SRC_EXPLORED ? d.sysb + ((size_t)e * 2) * plane_words(d) : nullptr;
   int *labels = (LABELS && a.labels) ? a.labels + (size_t)e * N * N : nullptr;
   const int g = lane >> 3, c8 = lane & 7;
-  double M = 0.0, SX = 0.0, SY = 0.0, S2 = 0.0;
+  // the grid is a fraction of the largest possible item count: a warp strides over the items
 #pragma unroll 1
-  for (int q = 0; q < VG_CHUNK / 4; ++q) {
-    const int lo = __shfl_sync(0xffffffffu, lo_l, 4 * q + g), hi = __shfl_sync(0xffffffffu, hi_l, 4 * q + g);
-    int qlo = hi > lo ? lo : 0x7fffffff, qhi = hi > lo ? hi : 0;
-    qlo = min(qlo, __shfl_xor_sync(0xffffffffu, qlo, 8)), qhi = max(qhi, __shfl_xor_sync(0xffffffffu, qhi, 8));
-    qlo = min(qlo, __shfl_xor_sync(0xffffffffu, qlo, 16)), qhi = max(qhi, __shfl_xor_sync(0xffffffffu, qhi, 16));
-    if (qhi <= qlo) continue;  // warp-uniform
-    const int row = rbase + 4 * q + g;
-    // pass j covers columns cb0 + 32 j ..; this lane's cells: col0 + 32 j .. + 3
-    const int cb0 = qlo & ~31, npass = (qhi - cb0 + 31) >> 5;
-    const int col0 = cb0 + 4 * c8;
-    const float4 *p4 = reinterpret_cast<const float4 *>(world + (size_t)row * N + col0);
-    const uint32_t *pw = SRC == SRC_EXPLORED ? plane + (size_t)row * d.NW + (cb0 >> 5) : nullptr;
-    int *lrow = LABELS && labels ? labels + (size_t)row * N + col0 : nullptr;
-    const int A = lo - col0, B = hi - col0;  // the interval relative to the lane's first cell
-    // passes jf0 .. jf1 lie fully inside [A, B); at most the passes holding A and B are partial
-    const int jf0 = A > 0 ? (A + 31) >> 5 : 0, jf1 = (B - 4) >> 5;
-    const int ja = A >> 5, jb = B >> 5;
-    const unsigned na = (A > 0 && hi > lo) ? vg_keep4(32 * ja, A, B) : 0u, nb = (B > 0 && hi > lo) ? vg_keep4(32 * jb, A, B) : 0u;
-    double y0 = (double)col0 + 0.5;
-    double rs = 0.0, rsy = 0.0, rsyy = 0.0;
-#pragma unroll 1
-    for (int base = 0; base < npass; base += VG_U) {
-      // request the whole batch, then consume it: VG_U x 512 bytes in flight per warp
-      float4 w[VG_U];
-      // 4 keep bits per pass of the batch: nibbles [jf0 - base, jf1 - base] full, plus the partial ones
-      unsigned kl;
-      {
-        const int l4 = 4 * min(max(jf0 - base, 0), VG_U), h4 = 4 * min(max(jf1 - base + 1, 0), VG_U);
-        kl = h4 > l4 ? (unsigned)(((1ull << h4) - 1ull) & ~((1ull << l4) - 1ull)) : 0u;
-        if (ja >= base && ja < base + VG_U) kl |= na << (4 * (ja - base));
-        if (jb >= base && jb < base + VG_U) kl |= nb << (4 * (jb - base));
-      }
-      unsigned kp = kl;  // cells to add (kl: cells inside the interval, for the labels)
-      if (SRC == SRC_EXPLORED) {
-        uint32_t pwv[VG_U];
-#pragma unroll
-        for (int j = 0; j < VG_U; ++j) pwv[j] = ((kl >> (4 * j)) & 0xfu) ? __ldg(pw + base + j) : 0u;
-#pragma unroll
-        for (int j = 0; j < VG_U; ++j) kp &= ~(0xfu << (4 * j)) | (((pwv[j] >> (col0 & 31)) & 0xfu) << (4 * j));
-      }
-#pragma unroll
-      for (int j = 0; j < VG_U; ++j) {
-        if ((kp >> (4 * j)) & 0xfu) w[j] = __ldg(p4 + 8 * (base + j));
-      }
-#pragma unroll
-      for (int j = 0; j < VG_U; ++j) {
-        if (base + j >= npass) break;  // warp-uniform
-        const unsigned keep = (kp >> (4 * j)) & 0xfu;
-        if (LABELS) {
-          if (lrow) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if ((kl >> (4 * j + i)) & 1u) lrow[32 * (base + j) + i] = k;
-          }
-        }
-        float4 x = w[j];  // only defined where keep has a bit
-        if (keep != 0xfu) {  // an end of the interval, outside it, or unexplored cells
-          x.x = (keep & 1u) ? x.x : 0.f, x.y = (keep & 2u) ? x.y : 0.f;
-          x.z = (keep & 4u) ? x.z : 0.f, x.w = (keep & 8u) ? x.w : 0.f;
-        }
-        const double v0 = (double)x.x, v1 = (double)x.y, v2 = (double)x.z, v3 = (double)x.w;
-        // sums over the four cells with y = y0 + i
-        const double s = (v0 + v1) + (v2 + v3);
-        const double t = fma(3.0, v3, fma(2.0, v2, v1));   // sum i v_i
-        const double u = fma(9.0, v3, fma(4.0, v2, v1));   // sum i^2 v_i
-        rs += s;
-        rsy += fma(y0, s, t);
-        rsyy += fma(y0 * y0, s, fma(y0 + y0, t, u));
-        y0 += 32.0;
+  for (int item = blockIdx.x * (blockDim.x >> 5) + warp; item < total; item += gridDim.x * (blockDim.x >> 5)) {
+    // the item's site: the first one whose items end beyond `item` (sites without cells have none)
+    int k;
+    {
+      const int end0 = lane < R ? __ldg(its + lane + 1) : 0x7fffffff;
+      unsigned hit = __ballot_sync(0xffffffffu, item < end0);
+      if (hit) {
+        k = __ffs(hit) - 1;
+      } else {
+        const int end1 = lane + 32 < R ? __ldg(its + lane + 33) : 0x7fffffff;
+        hit = __ballot_sync(0xffffffffu, item < end1);
+        k = 32 + __ffs(hit) - 1;
       }
     }
-    const double x = (double)row + 0.5;
-    M += rs;
-    SX = fma(x, rs, SX);
-    SY += rsy;
-    S2 += fma(x * x, rs, rsyy);
+    const int chunk = (__ldg(a.span + ((size_t)e * R + k) * 2) - a.row0) / VG_CHUNK + (item - __ldg(its + k));
+    const int rbase = a.row0 + chunk * VG_CHUNK;
+    const int myrow = rbase + lane;
+    const uint32_t iv = myrow < a.row1 ? __ldg(a.table + ((size_t)e * R + k) * N + myrow) : 0u;
+    const int lo_l = (int)(iv & 0xffffu), hi_l = (int)(iv >> 16);
+    // ask for this lane's row interval to be brought into L2 now (a line per 32 columns): the whole
+    // chunk is in flight while the warp streams it, and the loads below see L2 latency
+    if (SRC == SRC_WORLD) {
+      const float *prow = world + (size_t)myrow * N;
+      for (int c = lo_l & ~31; c < hi_l; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + c));
+    }
+    double M = 0.0, SX = 0.0, SY = 0.0, S2 = 0.0;
+#pragma unroll 1
+    for (int q = 0; q < VG_CHUNK / 4; ++q) {
+      const int lo = __shfl_sync(0xffffffffu, lo_l, 4 * q + g), hi = __shfl_sync(0xffffffffu, hi_l, 4 * q + g);
+      const bool has = hi > lo;
+      const int qlo = __reduce_min_sync(0xffffffffu, has ? lo : 0x7fffffff), qhi = __reduce_max_sync(0xffffffffu, has ? hi : 0);
+      if (qhi <= qlo) continue;  // warp-uniform
+      const int row = rbase + 4 * q + g;
+      // pass j covers columns cb0 + 32 j ..; this lane's cells: col0 + 32 j .. + 3
+      const int cb0 = qlo & ~31, npass = (qhi - cb0 + 31) >> 5;
+      const int col0 = cb0 + 4 * c8;
+      const float4 *p4 = reinterpret_cast<const float4 *>(world + (size_t)row * N + col0);
+      const uint32_t *pw = SRC == SRC_EXPLORED ? plane + (size_t)row * d.NW + (cb0 >> 5) : nullptr;
+      int *lrow = LABELS && labels ? labels + (size_t)row * N + col0 : nullptr;
+      const int A = lo - col0, B = hi - col0;  // the interval relative to the lane's first cell
+      // passes jf0 .. jf1 lie fully inside [A, B); at most the passes holding A and B are partial
+      const int jf0 = A > 0 ? (A + 31) >> 5 : 0, jf1 = (B - 4) >> 5;
+      double rs = 0.0, rsy = 0.0, rsyy = 0.0;
+      // Passes [L0, L1) lie inside the interval of every one of the four rows (all 32 lanes keep all
+      // four cells): they run without keep masks, selects or per-pass tests.  Voronoi cells are convex,
+      // so these are most of the passes away from a cell's top and bottom rows.
+      int L0 = npass, L1 = npass;
+      if constexpr (LU > 0) {
+        const int f0 = __reduce_max_sync(0xffffffffu, has ? jf0 : 0x7fff), f1 = __reduce_min_sync(0xffffffffu, has ? jf1 : -1);
+        if (f1 >= f0) L0 = f0, L1 = f1 + 1;
+        int base = L0;
+#pragma unroll 1
+        for (; base + LU <= L1; base += LU) vg_lean_batch<LU>(p4, col0, base, rs, rsy, rsyy);
+        if constexpr (LU > 4)
+          if (base + 4 <= L1) vg_lean_batch<4>(p4, col0, base, rs, rsy, rsyy), base += 4;
+        if constexpr (LU > 2)
+          if (base + 2 <= L1) vg_lean_batch<2>(p4, col0, base, rs, rsy, rsyy), base += 2;
+        if constexpr (LU > 1)
+          if (base < L1) vg_lean_batch<1>(p4, col0, base, rs, rsy, rsyy);
+      }
+      const int ja = A >> 5, jb = B >> 5;
+      const unsigned na = (A > 0 && has) ? vg_keep4(32 * ja, A, B) : 0u, nb = (B > 0 && has) ? vg_keep4(32 * jb, A, B) : 0u;
+      // the other passes: [0, L0) and [L1, npass) (everything when there is no such run)
+#pragma unroll 1
+      for (int seg = 0; seg < 2; ++seg) {
+        const int b0 = seg ? L1 : 0, b1 = seg ? npass : L0;
+#pragma unroll 1
+        for (int base = b0; base < b1; base += VG_U) {
+          // request the whole batch, then consume it: VG_U x 512 bytes in flight per warp
+          float4 w[VG_U];
+          // 4 keep bits per pass of the batch: nibbles [jf0 - base, jf1 - base] full, plus the partial ones
+          unsigned kl;
+          {
+            const int l4 = 4 * min(max(jf0 - base, 0), VG_U), h4 = 4 * min(max(jf1 - base + 1, 0), VG_U);
+            kl = h4 > l4 ? (unsigned)(((1ull << h4) - 1ull) & ~((1ull << l4) - 1ull)) : 0u;
+            if (ja >= base && ja < base + VG_U) kl |= na << (4 * (ja - base));
+            if (jb >= base && jb < base + VG_U) kl |= nb << (4 * (jb - base));
+            if (b1 - base < VG_U) kl &= (1u << (4 * (b1 - base))) - 1u;  // nothing beyond the segment
+          }
+          unsigned kp = kl;  // cells to add (kl: cells inside the interval, for the labels)
+          if (SRC == SRC_EXPLORED) {
+            uint32_t pwv[VG_U];
+#pragma unroll
+            for (int j = 0; j < VG_U; ++j) pwv[j] = ((kl >> (4 * j)) & 0xfu) ? __ldg(pw + base + j) : 0u;
+#pragma unroll
+            for (int j = 0; j < VG_U; ++j) kp &= ~(0xfu << (4 * j)) | (((pwv[j] >> (col0 & 31)) & 0xfu) << (4 * j));
+          }
+#pragma unroll
+          for (int j = 0; j < VG_U; ++j) {
+            if ((kp >> (4 * j)) & 0xfu) w[j] = __ldg(p4 + 8 * (base + j));
+          }
+          double y0 = (double)(col0 + 32 * base) + 0.5;
+#pragma unroll
+          for (int j = 0; j < VG_U; ++j) {
+            if (base + j >= b1) break;  // warp-uniform
+            const unsigned keep = (kp >> (4 * j)) & 0xfu;
+            if (LABELS) {
+              if (lrow) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if ((kl >> (4 * j + i)) & 1u) lrow[32 * (base + j) + i] = k;
+              }
+            }
+            float4 x = w[j];  // only defined where keep has a bit
+            if (keep != 0xfu) {  // an end of the interval, outside it, or unexplored cells
+              x.x = (keep & 1u) ? x.x : 0.f, x.y = (keep & 2u) ? x.y : 0.f;
+              x.z = (keep & 4u) ? x.z : 0.f, x.w = (keep & 8u) ? x.w : 0.f;
+            }
+            vg_add4(x, y0, rs, rsy, rsyy);
+            y0 += 32.0;
+          }
+        }
+      }
+      const double x = (double)row + 0.5;
+      M += rs;
+      SX = fma(x, rs, SX);
+      SY += rsy;
+      S2 += fma(x * x, rs, rsyy);
+    }
+    const Sum4 tot = reduce4(M, SX, SY, S2);
+    if (lane == 0) emit(a.sums, e, d.R, k, tot.m, tot.sx, tot.sy, tot.s2);
   }
-  const Sum4 tot = reduce4(M, SX, SY, S2);
-  if (lane == 0) emit(a.sums, e, d.R, k, tot.m, tot.sx, tot.sy, tot.s2);
 }
 
 // ---- flagged rows: the stated rule per cell --------------------------------------------------------
