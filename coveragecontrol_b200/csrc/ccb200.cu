@@ -441,9 +441,8 @@ struct ccb_env {
   int *d_vg_flag = nullptr;     // [1 + E*N]: count, then the flagged rows
   int *d_vg_span = nullptr;     // [E][R][2] row span of every site
   int *d_vg_items = nullptr;    // [E][R + 1] first (site, chunk) item of every site, then their total
-  int vg_warps = VG_RED_WARPS;  // CCB_VG_WARPS: warps per CTA of k_vg_reduce (<= VG_RED_WARPS)
+  int vg_warps = 1;             // CCB_VG_WARPS: warps per CTA of k_vg_reduce (<= VG_RED_WARPS)
   int vg_griddiv = 4;           // CCB_VG_GRIDDIV: grid = largest possible item count / this
-  int vg_lean = 0;              // CCB_VG_LEAN: k_vg_reduce's unmasked interior run: 0 none, 1 4 passes / 72 regs, 2 8 passes / 80 regs
   int vg_mode = -1;             // CCB_VG_GENERIC: 1 forces the tile-ordered kernel, 0 the site-ordered one (tests)
   bool vw_generic = false;      // CCB_VW_GENERIC: force the generic window kernel (tests)
   bool band_mode = false;       // this env holds one row band of a world tiled over several GPUs
@@ -551,13 +550,11 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
     if (stages & 2) {
       const int nt = env->vg_warps * 32;
       if (src == SRC_WORLD) {
-        if (labels) k_vg_reduce<SRC_WORLD, true, 0, 7><<<rgrid, nt, 0, env->stream>>>(g);
-        else if (env->vg_lean == 1) k_vg_reduce<SRC_WORLD, false, 4, 7><<<rgrid, nt, 0, env->stream>>>(g);
-        else if (env->vg_lean == 2) k_vg_reduce<SRC_WORLD, false, 8, 6><<<rgrid, nt, 0, env->stream>>>(g);
-        else k_vg_reduce<SRC_WORLD, false, 0, 7><<<rgrid, nt, 0, env->stream>>>(g);
+        if (labels) k_vg_reduce<SRC_WORLD, true><<<rgrid, nt, 0, env->stream>>>(g);
+        else k_vg_reduce<SRC_WORLD, false><<<rgrid, nt, 0, env->stream>>>(g);
       } else {
-        if (labels) k_vg_reduce<SRC_EXPLORED, true, 0, 7><<<rgrid, nt, 0, env->stream>>>(g);
-        else k_vg_reduce<SRC_EXPLORED, false, 0, 7><<<rgrid, nt, 0, env->stream>>>(g);
+        if (labels) k_vg_reduce<SRC_EXPLORED, true><<<rgrid, nt, 0, env->stream>>>(g);
+        else k_vg_reduce<SRC_EXPLORED, false><<<rgrid, nt, 0, env->stream>>>(g);
       }
       CCB_LAUNCH_CHECK();
     }
@@ -735,7 +732,6 @@ extern "C" ccb_env *ccb_env_create(const ccb_params *p, int num_envs, int num_ro
   if (const char *s = getenv("CCB_VOR_RPW")) env->vor_rpw_override = atoi(s);
   if (const char *s = getenv("CCB_VW_GENERIC")) env->vw_generic = atoi(s) != 0;
   if (const char *s = getenv("CCB_VG_GENERIC")) env->vg_mode = atoi(s) != 0 ? 1 : 0;
-  if (const char *s = getenv("CCB_VG_LEAN")) env->vg_lean = atoi(s);
   if (const char *s = getenv("CCB_VG_WARPS")) env->vg_warps = std::min(std::max(atoi(s), 1), VG_RED_WARPS);
   if (const char *s = getenv("CCB_VG_GRIDDIV")) env->vg_griddiv = std::max(atoi(s), 1);
   if (const char *s = getenv("CCB_NO_AUX")) env->no_aux = atoi(s) != 0;

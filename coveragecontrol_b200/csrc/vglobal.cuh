@@ -275,25 +275,9 @@ __device__ __forceinline__ void vg_add4(const float4 x, const double y0, double 
   rsyy += fma(y0 * y0, s, fma(y0 + y0, t, u));
 }
 
-// U passes base .. base + U - 1 of a row without masks: all requested, then all added
-template <int U>
-__device__ __forceinline__ void vg_lean_batch(const float4 *p4, int col0, int base, double &rs, double &rsy, double &rsyy) {
-  const float4 *pp = p4 + 8 * base;
-  float4 w[U];
-#pragma unroll
-  for (int j = 0; j < U; ++j) w[j] = __ldg(pp + 8 * j);
-  double y0 = (double)(col0 + 32 * base) + 0.5;
-#pragma unroll
-  for (int j = 0; j < U; ++j) {
-    vg_add4(w[j], y0, rs, rsy, rsyy);
-    y0 += 32.0;
-  }
-}
-
-// LU = passes requested together in the unmasked interior run (0: no such run), MINB = resident CTAs per
-// SM the register allocation aims for (7 -> 72 registers, 6 -> 80)
-template <int SRC, bool LABELS, int LU, int MINB>
-__global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a) {
+constexpr int VG_RED_MINB = 7;  // resident CTAs of VG_RED_WARPS warps per SM the register allocation aims for (72 registers)
+template <int SRC, bool LABELS>
+__global__ void __launch_bounds__(VG_RED_WARPS * 32, VG_RED_MINB) k_vg_reduce(VgArgs a) {
   const EnvDev &d = a.d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.y;
@@ -345,78 +329,58 @@ __global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a)
       const float4 *p4 = reinterpret_cast<const float4 *>(world + (size_t)row * N + col0);
       const uint32_t *pw = SRC == SRC_EXPLORED ? plane + (size_t)row * d.NW + (cb0 >> 5) : nullptr;
       int *lrow = LABELS && labels ? labels + (size_t)row * N + col0 : nullptr;
-      const int A = lo - col0, B = hi - col0;  // the interval relative to the lane's first cell
-      // passes jf0 .. jf1 lie fully inside [A, B); at most the passes holding A and B are partial
+      // the interval relative to the lane's first cell (an empty one for a row without cells of the site)
+      const int A = has ? lo - col0 : 0, B = has ? hi - col0 : 0;
+      // Pass j holds the lane's cells 32 j .. 32 j + 3.  They touch [A, B) for jl0 <= j <= jl1 (the passes
+      // the lane requests) and lie inside it for jf0 <= j <= jf1 (added without a mask); only the passes
+      // holding A or B in between need one.
+      const int jl0 = (A + 28) >> 5, jl1 = (B - 1) >> 5;
       const int jf0 = A > 0 ? (A + 31) >> 5 : 0, jf1 = (B - 4) >> 5;
       double rs = 0.0, rsy = 0.0, rsyy = 0.0;
-      // Passes [L0, L1) lie inside the interval of every one of the four rows (all 32 lanes keep all
-      // four cells): they run without keep masks, selects or per-pass tests.  Voronoi cells are convex,
-      // so these are most of the passes away from a cell's top and bottom rows.
-      int L0 = npass, L1 = npass;
-      if constexpr (LU > 0) {
-        const int f0 = __reduce_max_sync(0xffffffffu, has ? jf0 : 0x7fff), f1 = __reduce_min_sync(0xffffffffu, has ? jf1 : -1);
-        if (f1 >= f0) L0 = f0, L1 = f1 + 1;
-        int base = L0;
 #pragma unroll 1
-        for (; base + LU <= L1; base += LU) vg_lean_batch<LU>(p4, col0, base, rs, rsy, rsyy);
-        if constexpr (LU > 4)
-          if (base + 4 <= L1) vg_lean_batch<4>(p4, col0, base, rs, rsy, rsyy), base += 4;
-        if constexpr (LU > 2)
-          if (base + 2 <= L1) vg_lean_batch<2>(p4, col0, base, rs, rsy, rsyy), base += 2;
-        if constexpr (LU > 1)
-          if (base < L1) vg_lean_batch<1>(p4, col0, base, rs, rsy, rsyy);
-      }
-      const int ja = A >> 5, jb = B >> 5;
-      const unsigned na = (A > 0 && has) ? vg_keep4(32 * ja, A, B) : 0u, nb = (B > 0 && has) ? vg_keep4(32 * jb, A, B) : 0u;
-      // the other passes: [0, L0) and [L1, npass) (everything when there is no such run)
-#pragma unroll 1
-      for (int seg = 0; seg < 2; ++seg) {
-        const int b0 = seg ? L1 : 0, b1 = seg ? npass : L0;
-#pragma unroll 1
-        for (int base = b0; base < b1; base += VG_U) {
-          // request the whole batch, then consume it: VG_U x 512 bytes in flight per warp
-          float4 w[VG_U];
-          // 4 keep bits per pass of the batch: nibbles [jf0 - base, jf1 - base] full, plus the partial ones
-          unsigned kl;
-          {
-            const int l4 = 4 * min(max(jf0 - base, 0), VG_U), h4 = 4 * min(max(jf1 - base + 1, 0), VG_U);
-            kl = h4 > l4 ? (unsigned)(((1ull << h4) - 1ull) & ~((1ull << l4) - 1ull)) : 0u;
-            if (ja >= base && ja < base + VG_U) kl |= na << (4 * (ja - base));
-            if (jb >= base && jb < base + VG_U) kl |= nb << (4 * (jb - base));
-            if (b1 - base < VG_U) kl &= (1u << (4 * (b1 - base))) - 1u;  // nothing beyond the segment
-          }
-          unsigned kp = kl;  // cells to add (kl: cells inside the interval, for the labels)
+      for (int base = 0; base < npass; base += VG_U) {
+        // request the whole batch, then consume it: VG_U x 512 bytes in flight per warp
+        float4 w[VG_U];
+        const int Ab = A - 32 * base, Bb = B - 32 * base;  // the interval relative to the batch's first pass
+        const int l0 = jl0 - base, l1 = jl1 - base, f0 = jf0 - base, f1 = jf1 - base;
+        unsigned kl = 0u, kp = 0u;  // LABELS / SRC_EXPLORED: 4 keep bits per pass (kl: inside the interval, kp: to add)
+        if (LABELS || SRC == SRC_EXPLORED) {
+#pragma unroll
+          for (int j = 0; j < VG_U; ++j) kl |= vg_keep4(32 * j, Ab, Bb) << (4 * j);
+          kp = kl;
           if (SRC == SRC_EXPLORED) {
             uint32_t pwv[VG_U];
 #pragma unroll
-            for (int j = 0; j < VG_U; ++j) pwv[j] = ((kl >> (4 * j)) & 0xfu) ? __ldg(pw + base + j) : 0u;
+            for (int j = 0; j < VG_U; ++j) pwv[j] = (((kl >> (4 * j)) & 0xfu) && base + j < npass) ? __ldg(pw + base + j) : 0u;
 #pragma unroll
             for (int j = 0; j < VG_U; ++j) kp &= ~(0xfu << (4 * j)) | (((pwv[j] >> (col0 & 31)) & 0xfu) << (4 * j));
           }
+        }
 #pragma unroll
-          for (int j = 0; j < VG_U; ++j) {
-            if ((kp >> (4 * j)) & 0xfu) w[j] = __ldg(p4 + 8 * (base + j));
-          }
-          double y0 = (double)(col0 + 32 * base) + 0.5;
+        for (int j = 0; j < VG_U; ++j) {
+          // (jl1 < npass: no pass beyond the row group's last one is asked for)
+          const bool want = (LABELS || SRC == SRC_EXPLORED) ? ((kp >> (4 * j)) & 0xfu) != 0u && base + j < npass : (j >= l0 && j <= l1);
+          if (want) w[j] = __ldg(p4 + 8 * (base + j));
+        }
+        double y0 = (double)(col0 + 32 * base) + 0.5;
 #pragma unroll
-          for (int j = 0; j < VG_U; ++j) {
-            if (base + j >= b1) break;  // warp-uniform
-            const unsigned keep = (kp >> (4 * j)) & 0xfu;
-            if (LABELS) {
-              if (lrow) {
+        for (int j = 0; j < VG_U; ++j) {
+          if (base + j >= npass) break;  // warp-uniform
+          if (LABELS) {
+            if (lrow) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  if ((kl >> (4 * j + i)) & 1u) lrow[32 * (base + j) + i] = k;
-              }
+              for (int i = 0; i < 4; ++i)
+                if ((kl >> (4 * j + i)) & 1u) lrow[32 * (base + j) + i] = k;
             }
-            float4 x = w[j];  // only defined where keep has a bit
-            if (keep != 0xfu) {  // an end of the interval, outside it, or unexplored cells
-              x.x = (keep & 1u) ? x.x : 0.f, x.y = (keep & 2u) ? x.y : 0.f;
-              x.z = (keep & 4u) ? x.z : 0.f, x.w = (keep & 8u) ? x.w : 0.f;
-            }
-            vg_add4(x, y0, rs, rsy, rsyy);
-            y0 += 32.0;
           }
+          // w[j] is only defined where the lane asked for it
+          if ((LABELS || SRC == SRC_EXPLORED) || j < f0 || j > f1) {  // an end of the interval, outside it, unexplored cells
+            const unsigned keep = (LABELS || SRC == SRC_EXPLORED) ? (kp >> (4 * j)) & 0xfu : vg_keep4(32 * j, Ab, Bb);
+            w[j].x = (keep & 1u) ? w[j].x : 0.f, w[j].y = (keep & 2u) ? w[j].y : 0.f;
+            w[j].z = (keep & 4u) ? w[j].z : 0.f, w[j].w = (keep & 8u) ? w[j].w : 0.f;
+          }
+          vg_add4(w[j], y0, rs, rsy, rsyy);
+          y0 += 32.0;
         }
       }
       const double x = (double)row + 0.5;
