@@ -11,11 +11,14 @@
 //                   a hidden/visible decision, a breakpoint next to a cell centre, or a pair of parabolas
 //                   that cannot be separated within that bound FLAGS the row instead of guessing.
 //                   Output: table[e][site][row] = lo | hi << 16 (the site's cells on that row).
+//   k_vg_items      one warp per environment: numbers the (site, 32-row chunk) pairs that hold cells.
 //   k_vg_reduce     one warp per (site, 32-row chunk): streams the site's intervals with 16-byte loads
-//                   (4 rows x 32 columns per pass, the next pass requested before this one is used),
-//                   no labels, no per-cell distance, one owner per warp: fp64 sums in cell units as in
-//                   voronoi.cuh, one set of fp64 atomics per (site, chunk).  Every map cell is read
-//                   once, by its owner.  SRC_EXPLORED ANDs the intervals with the explored bit plane.
+//                   (4 rows x 32 columns per pass, a batch of passes requested before the first is used;
+//                   a lane asks for a pass iff its four cells touch its row's interval and masks only
+//                   the passes that hold an end of it), no labels, no per-cell distance, one owner per
+//                   warp: fp64 sums in cell units as in voronoi.cuh, one set of fp64 atomics per
+//                   (site, chunk).  Every map cell is read once, by its owner.  SRC_EXPLORED ANDs the
+//                   intervals with the explored bit plane.
 //   k_vg_fixup      flagged rows only: the stated rule per cell (d2 in fp64 without FMA contraction,
 //                   strict <, ascending site index), label runs flushed with atomics.
 //
@@ -33,7 +36,7 @@ constexpr int VG_MAXR = 64;
 constexpr int VG_PART_THREADS = 128;
 constexpr int VG_RED_WARPS = 4;
 constexpr int VG_CHUNK = 32;  // rows per warp item: lane <-> row when the intervals are fetched
-constexpr int VG_U = 8;       // passes requested together
+constexpr int VG_U = 6;       // passes requested together (measured: 6 passes / 64 registers beats 8 / 72 and 4 / 48)
 
 struct VgArgs {
   EnvDev d;
@@ -275,9 +278,9 @@ __device__ __forceinline__ void vg_add4(const float4 x, const double y0, double 
   rsyy += fma(y0 * y0, s, fma(y0 + y0, t, u));
 }
 
-constexpr int VG_RED_MINB = 7;  // resident CTAs of VG_RED_WARPS warps per SM the register allocation aims for (72 registers)
-template <int SRC, bool LABELS>
-__global__ void __launch_bounds__(VG_RED_WARPS * 32, VG_RED_MINB) k_vg_reduce(VgArgs a) {
+constexpr int VG_RED_MINB = 8;  // resident CTAs of VG_RED_WARPS warps per SM the register allocation aims for (64 registers)
+template <int SRC, bool LABELS, int U = VG_U, int MINB = VG_RED_MINB>
+__global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a) {
   const EnvDev &d = a.d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.y;
@@ -338,33 +341,33 @@ __global__ void __launch_bounds__(VG_RED_WARPS * 32, VG_RED_MINB) k_vg_reduce(Vg
       const int jf0 = A > 0 ? (A + 31) >> 5 : 0, jf1 = (B - 4) >> 5;
       double rs = 0.0, rsy = 0.0, rsyy = 0.0;
 #pragma unroll 1
-      for (int base = 0; base < npass; base += VG_U) {
-        // request the whole batch, then consume it: VG_U x 512 bytes in flight per warp
-        float4 w[VG_U];
+      for (int base = 0; base < npass; base += U) {
+        // request the whole batch, then consume it: U x 512 bytes in flight per warp
+        float4 w[U];
         const int Ab = A - 32 * base, Bb = B - 32 * base;  // the interval relative to the batch's first pass
         const int l0 = jl0 - base, l1 = jl1 - base, f0 = jf0 - base, f1 = jf1 - base;
         unsigned kl = 0u, kp = 0u;  // LABELS / SRC_EXPLORED: 4 keep bits per pass (kl: inside the interval, kp: to add)
         if (LABELS || SRC == SRC_EXPLORED) {
 #pragma unroll
-          for (int j = 0; j < VG_U; ++j) kl |= vg_keep4(32 * j, Ab, Bb) << (4 * j);
+          for (int j = 0; j < U; ++j) kl |= vg_keep4(32 * j, Ab, Bb) << (4 * j);
           kp = kl;
           if (SRC == SRC_EXPLORED) {
-            uint32_t pwv[VG_U];
+            uint32_t pwv[U];
 #pragma unroll
-            for (int j = 0; j < VG_U; ++j) pwv[j] = (((kl >> (4 * j)) & 0xfu) && base + j < npass) ? __ldg(pw + base + j) : 0u;
+            for (int j = 0; j < U; ++j) pwv[j] = (((kl >> (4 * j)) & 0xfu) && base + j < npass) ? __ldg(pw + base + j) : 0u;
 #pragma unroll
-            for (int j = 0; j < VG_U; ++j) kp &= ~(0xfu << (4 * j)) | (((pwv[j] >> (col0 & 31)) & 0xfu) << (4 * j));
+            for (int j = 0; j < U; ++j) kp &= ~(0xfu << (4 * j)) | (((pwv[j] >> (col0 & 31)) & 0xfu) << (4 * j));
           }
         }
 #pragma unroll
-        for (int j = 0; j < VG_U; ++j) {
+        for (int j = 0; j < U; ++j) {
           // (jl1 < npass: no pass beyond the row group's last one is asked for)
           const bool want = (LABELS || SRC == SRC_EXPLORED) ? ((kp >> (4 * j)) & 0xfu) != 0u && base + j < npass : (j >= l0 && j <= l1);
           if (want) w[j] = __ldg(p4 + 8 * (base + j));
         }
         double y0 = (double)(col0 + 32 * base) + 0.5;
 #pragma unroll
-        for (int j = 0; j < VG_U; ++j) {
+        for (int j = 0; j < U; ++j) {
           if (base + j >= npass) break;  // warp-uniform
           if (LABELS) {
             if (lrow) {
