@@ -928,8 +928,13 @@ class CoverageSystem(_EnvBase):
         self._check_robot(robot_id)
         return DblVector(out[0, robot_id])
 
-    def GetRobotExplorationFeatures(self):
-        raise NotImplementedError("GetRobotExplorationFeatures is outside the hot-path scope (SURVEY.md 8a row 4)")
+    def GetRobotExplorationFeatures(self) -> DblVectorVector:
+        """coverage_system.h:603-610 -> robot_model.h:347-403: per robot the pNumFrontiers best frontier
+        points (worst first) as [dx, dy, dx, dy, ...] relative to the robot, zero-padded."""
+        K = int(self._params.pNumFrontiers)
+        out = np.zeros((1, self._R, 2 * K))
+        _lib.check(_lib.load().ccb_env_exploration_features(self._h, K, _dp(out)))
+        return DblVectorVector(DblVector(row) for row in out[0])
 
     def CheckOscillation(self, robot_id: int) -> bool:
         self._check_robot(robot_id)
@@ -1288,6 +1293,13 @@ class BatchedCoverageSystem(_EnvBase):
     def voronoi_features(self) -> np.ndarray:
         out = np.empty((self._E, self._R, 7))
         _lib.check(_lib.load().ccb_env_voronoi_features(self._h, _dp(out)))
+        return out
+
+    def exploration_features(self, num_frontiers: int | None = None) -> np.ndarray:
+        """GetRobotExplorationFeatures of every environment: [E, R, 2 * num_frontiers]."""
+        K = int(self._params.pNumFrontiers if num_frontiers is None else num_frontiers)
+        out = np.zeros((self._E, self._R, 2 * K))
+        _lib.check(_lib.load().ccb_env_exploration_features(self._h, K, _dp(out)))
         return out
 
     def sync(self) -> None:

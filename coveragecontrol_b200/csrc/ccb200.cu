@@ -440,6 +440,8 @@ struct ccb_env {
   uint32_t *d_vg_table = nullptr;  // [E][R][N] row intervals of the site-ordered global Voronoi (vglobal.cuh)
   int *d_vg_flag = nullptr;     // [1 + E*N]: count, then the flagged rows
   int *d_vg_span = nullptr;     // [E][R][2] row span of every site
+  double *d_xfeat = nullptr;    // [E][R][2 K] exploration features (ccb_env_exploration_features)
+  size_t feat_cap = 0;
   int *d_vg_items = nullptr;    // [E][R + 1] first (site, chunk) item of every site, then their total
   int vg_warps = 1;             // CCB_VG_WARPS: warps per CTA of k_vg_reduce (<= VG_RED_WARPS)
   int vg_griddiv = 4;           // CCB_VG_GRIDDIV: grid = largest possible item count / this
@@ -763,7 +765,7 @@ extern "C" void ccb_env_destroy(ccb_env *env) {
   free_cells(env->cells);
   cudaFree(env->d_objective), cudaFree(env->d_stage), cudaFree(env->d_feat), cudaFree(env->d_ratio);
   cudaFree(env->d_scratch);
-  cudaFree(env->d_vg_table), cudaFree(env->d_vg_flag), cudaFree(env->d_vg_span), cudaFree(env->d_vg_items);
+  cudaFree(env->d_vg_table), cudaFree(env->d_vg_flag), cudaFree(env->d_vg_span), cudaFree(env->d_vg_items), cudaFree(env->d_xfeat);
   cudaFreeHost(env->h_pin);
   for (int k = 0; k < 2; ++k) {
     cudaFreeHost(env->h_stage[k]);
@@ -1329,6 +1331,50 @@ extern "C" int ccb_env_local_voronoi_features(ccb_env *env, double *out) {
   CCB_CUDA(cudaMemcpyAsync(env->h_pin, env->d_feat, sizeof(double) * n, cudaMemcpyDeviceToHost, env->stream));
   CCB_CUDA(cudaStreamSynchronize(env->stream));
   memcpy(out, env->h_pin, sizeof(double) * n);
+  return 0;
+}
+
+// Host run of the kernel's frontier queue (the same expl_* code, compiled for the host): lets the CPU
+// tests check it against std::priority_queue without a GPU.  Not a compute path: no map is touched.
+extern "C" int ccb_selftest_frontier_select(const double *values, int n, int num_frontiers, int *order_out) {
+  if (num_frontiers < 1 || num_frontiers > EXPL_MAXK) return -1;
+  ExplHeap h;
+  expl_select(h, values, n, num_frontiers);
+  int count = 0;
+  while (h.n > 0) {
+    order_out[count++] = h.id[0];
+    expl_pop(h);
+  }
+  return count;
+}
+
+// coverage_system.h:603-610 GetRobotExplorationFeatures for every robot: E x R x 2 K, host
+extern "C" int ccb_env_exploration_features(ccb_env *env, int num_frontiers, double *out) {
+  if (!env->initialised) return fail("environment has no robot positions yet");
+  const EnvDev &d = env->d;
+  const int K = num_frontiers;
+  if (K < 1 || K > EXPL_MAXK) return fail("exploration features: pNumFrontiers must be in [1, 64]");
+  // the kernel's bounds, from the same quantities: candidates per axis, union of their sensor windows
+  const double tsd = d.max_speed * d.dt * d.res;
+  const double per_axis = 8.0 * tsd / d.res + 2.0;
+  if (!(per_axis <= (double)EXPL_MAXC)) return fail("exploration features: more than 96 candidate points per axis (4 x pMaxRobotSpeed x pTimeStep too large)");
+  const size_t side = (size_t)per_axis + (size_t)d.S + 2;
+  const size_t words = (2 * side * side + 1) & ~(size_t)1;
+  const size_t smem = sizeof(int) * words + sizeof(double) * (size_t)per_axis * (size_t)per_axis;
+  if (smem > 200 * 1024) return fail("exploration features: candidate windows do not fit in shared memory (pSensorSize too large)");
+  CCB_CUDA(cudaSetDevice(env->device));
+  const size_t n = (size_t)d.E * d.R * 2 * K;
+  if (n > env->feat_cap) {
+    if (env->d_xfeat) cudaFree(env->d_xfeat);
+    env->d_xfeat = nullptr;
+    CCB_CUDA(cudaMalloc(&env->d_xfeat, sizeof(double) * n));
+    env->feat_cap = n;
+  }
+  CCB_CUDA(cudaFuncSetAttribute(k_exploration_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_exploration_features<<<dim3(d.R, d.E), 256, smem, env->stream>>>(d, K, env->d_xfeat);
+  CCB_LAUNCH_CHECK();
+  CCB_CUDA(cudaMemcpyAsync(out, env->d_xfeat, sizeof(double) * n, cudaMemcpyDeviceToHost, env->stream));
+  CCB_CUDA(cudaStreamSynchronize(env->stream));
   return 0;
 }
 

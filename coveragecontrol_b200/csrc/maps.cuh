@@ -32,6 +32,170 @@ __device__ __forceinline__ float robot_exploration_value(const EnvDev &d, int e,
   return plane_bit(robot_plane(d, d.xseenb, e, r), d.NW, row, col) ? 0.f : 1.f;
 }
 
+// ---- exploration (frontier) features --------------------------------------------------------------
+// robot_model.h:347-403 GetExplorationFeatures.  Candidate points q on a res-spaced lattice within
+// 4 time-step distances of the robot; for each, over the sensor window centred at q:
+//   unexplored = sum of the robot's exploration map, benefit = unexplored (+ 2 x the number of non-zero
+//   robot-map cells if unexplored > 0.1 S^2), value = benefit / max(|q - p|, time-step distance);
+// the pNumFrontiers best candidates are kept in a std::priority_queue (worst on top) and popped worst
+// first into [dx, dy] pairs.  One CTA per (robot, environment): both indicator maps over the union of
+// the candidate windows become integral images in shared memory (a window sum = four look-ups), the
+// candidates are scored in parallel, and one thread replays the queue in the reference's order with
+// libstdc++'s heap algorithms (bits/stl_heap.h __push_heap / __adjust_heap), so ties resolve as there.
+// Dynamic smem: 2 (nxr + 1)(nyr + 1) ints + nc doubles, sized by the host from the same bounds.
+constexpr int EXPL_MAXC = 96;   // candidates per axis
+constexpr int EXPL_MAXK = 64;   // pNumFrontiers
+
+struct ExplHeap {
+  double v[EXPL_MAXK];
+  int id[EXPL_MAXK];
+  int n;
+};
+// comp(a, b) of FrontierCompare (typedefs.h:79-83): a.value > b.value
+__host__ __device__ __forceinline__ void expl_push_heap(ExplHeap &h, int hole, int top, double val, int id) {
+  int parent = (hole - 1) / 2;
+  while (hole > top && h.v[parent] > val) {
+    h.v[hole] = h.v[parent], h.id[hole] = h.id[parent];
+    hole = parent, parent = (hole - 1) / 2;
+  }
+  h.v[hole] = val, h.id[hole] = id;
+}
+__host__ __device__ __forceinline__ void expl_adjust_heap(ExplHeap &h, int hole, int len, double val, int id) {
+  const int top = hole;
+  int child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (h.v[child] > h.v[child - 1]) --child;
+    h.v[hole] = h.v[child], h.id[hole] = h.id[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    h.v[hole] = h.v[child - 1], h.id[hole] = h.id[child - 1];
+    hole = child - 1;
+  }
+  expl_push_heap(h, hole, top, val, id);
+}
+// priority_queue::pop: the top leaves, the last element is sifted in from the root
+__host__ __device__ __forceinline__ void expl_pop(ExplHeap &h) {
+  if (h.n > 1) {
+    const double val = h.v[h.n - 1];
+    const int id = h.id[h.n - 1];
+    h.v[h.n - 1] = h.v[0], h.id[h.n - 1] = h.id[0];
+    expl_adjust_heap(h, 0, h.n - 1, val, id);
+  }
+  --h.n;
+}
+
+// robot_model.h:383-391: keep the K best of val[0 .. n), the worst on top
+__host__ __device__ __forceinline__ void expl_select(ExplHeap &h, const double *val, int n, int K) {
+  h.n = 0;
+  for (int t = 0; t < n; ++t) {
+    const double bcr = val[t];
+    if (h.n < K) {
+      ++h.n;  // push_back + push_heap
+      expl_push_heap(h, h.n - 1, 0, bcr, t);
+    } else if (h.v[0] < bcr) {
+      expl_pop(h);
+      ++h.n;
+      expl_push_heap(h, h.n - 1, 0, bcr, t);
+    }
+  }
+}
+
+// the reference's candidate loop along one axis: for (q = max(p - reach, kLargeEps); q < min(p + reach, size); q += res)
+__device__ __forceinline__ int expl_axis(double p, double reach, double size, double res, double *q) {
+  const double lim = fmin(p + reach, size);
+  int n = 0;
+  for (double v = fmax(p - reach, kLargeEps); v < lim && n < EXPL_MAXC; v += res) q[n++] = v;
+  return n;
+}
+
+__global__ void __launch_bounds__(256) k_exploration_features(EnvDev d, int K, double *__restrict__ out) {
+  extern __shared__ int s_dyn[];
+  __shared__ double s_qx[EXPL_MAXC], s_qy[EXPL_MAXC];
+  __shared__ int s_cx[EXPL_MAXC], s_cy[EXPL_MAXC];
+  __shared__ int s_nx, s_ny;
+  __shared__ ExplHeap s_heap;
+  const int r = blockIdx.x, e = blockIdx.y, tid = threadIdx.x;
+  const size_t er = (size_t)e * d.R + r;
+  const double px = d.pos_g[er * 2], py = d.pos_g[er * 2 + 1];
+  const double res = d.res;
+  const double tsd = d.max_speed * d.dt * res;  // time_step_dist_ (robot_model.h:150-151)
+  const double reach = 4.0 * tsd, size = (double)d.N;  // (the reference compares with pWorldMapSize, not its extent)
+  const int S = d.S, half = S / 2;
+  if (tid == 0) {
+    s_nx = expl_axis(px, reach, size, res, s_qx);
+    for (int k = 0; k < s_nx; ++k) s_cx[k] = (int)round(s_qx[k] / res);
+  }
+  if (tid == 32) {
+    s_ny = expl_axis(py, reach, size, res, s_qy);
+    for (int k = 0; k < s_ny; ++k) s_cy[k] = (int)round(s_qy[k] / res);
+  }
+  __syncthreads();
+  const int nx = s_nx, ny = s_ny;
+  double *o = out + er * 2 * K;
+  if (nx == 0 || ny == 0) {
+    for (int t = tid; t < 2 * K; t += blockDim.x) o[t] = 0.0;
+    return;
+  }
+  // union of the candidate windows (the centres are monotone along an axis), clipped to the map
+  const int x0 = max(s_cx[0] - half, 0), x1 = min(s_cx[nx - 1] + half, d.N);
+  const int y0 = max(s_cy[0] - half, 0), y1 = min(s_cy[ny - 1] + half, d.N);
+  const int nxr = max(x1 - x0, 0), nyr = max(y1 - y0, 0), ld = nyr + 1;
+  int *s_un = s_dyn, *s_nz = s_dyn + (size_t)(nxr + 1) * ld;
+  double *s_val = reinterpret_cast<double *>(s_dyn + (((size_t)2 * (nxr + 1) * ld + 1) & ~(size_t)1));
+  // indicators, shifted by one row and one column; row 0 and column 0 stay zero
+  for (int t = tid; t < (nxr + 1) * ld; t += blockDim.x) {
+    const int a = t / ld, b = t - a * ld;
+    int un = 0, nz = 0;
+    if (a > 0 && b > 0) {
+      un = robot_exploration_value(d, e, r, x0 + a - 1, y0 + b - 1) != 0.f;
+      nz = robot_map_value(d, e, r, x0 + a - 1, y0 + b - 1) != 0.f;
+    }
+    s_un[t] = un, s_nz[t] = nz;
+  }
+  __syncthreads();
+  for (int a = 1 + tid; a <= nxr; a += blockDim.x) {  // prefix along a row
+    int su = 0, sn = 0;
+    for (int b = 1; b <= nyr; ++b) su += s_un[a * ld + b], sn += s_nz[a * ld + b], s_un[a * ld + b] = su, s_nz[a * ld + b] = sn;
+  }
+  __syncthreads();
+  for (int b = 1 + tid; b <= nyr; b += blockDim.x) {  // then down the columns
+    int su = 0, sn = 0;
+    for (int a = 1; a <= nxr; ++a) su += s_un[a * ld + b], sn += s_nz[a * ld + b], s_un[a * ld + b] = su, s_nz[a * ld + b] = sn;
+  }
+  __syncthreads();
+  const double area = (double)(S * S);
+  for (int t = tid; t < nx * ny; t += blockDim.x) {
+    const int kx = t / ny, ky = t - kx * ny;
+    const double dx = s_qx[kx] - px, dy = s_qy[ky] - py;
+    const double dist = fmax(sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))), tsd);
+    // map_utils.h:51-87 window of q, clipped, in integral-image coordinates
+    const int a0 = max(s_cx[kx] - half, 0) - x0, a1 = min(s_cx[kx] + half, d.N) - x0;
+    const int b0 = max(s_cy[ky] - half, 0) - y0, b1 = min(s_cy[ky] + half, d.N) - y0;
+    const int un = s_un[a1 * ld + b1] - s_un[a0 * ld + b1] - s_un[a1 * ld + b0] + s_un[a0 * ld + b0];
+    double benefit = (double)un;
+    if ((double)un > 0.1 * area) {
+      const int nz = s_nz[a1 * ld + b1] - s_nz[a0 * ld + b1] - s_nz[a1 * ld + b0] + s_nz[a0 * ld + b0];
+      benefit += 2.0 * (double)nz;
+    }
+    s_val[t] = benefit / dist;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    ExplHeap &h = s_heap;
+    expl_select(h, s_val, nx * ny, K);  // kx outer, ky inner: the reference's order
+    int count = 0;
+    while (h.n > 0) {
+      const int t = h.id[0], kx = t / ny, ky = t - kx * ny;
+      o[count++] = s_qx[kx] - px, o[count++] = s_qy[ky] - py;
+      expl_pop(h);
+    }
+    while (count < 2 * K) o[count++] = 0.0;
+  }
+}
+
 // ---- sensor window marking ---------------------------------------------------------------------
 // robot_model.h:98-122 (UpdateRobotMap / UpdateExplorationMap) and coverage_system.h:104-118
 // (explored_idf / exploration windows).  grid = (1, R, E); env_sel/robot_sel >= 0 select one.

@@ -170,6 +170,14 @@ int ccb_env_voronoi_features(ccb_env *env, double *out);
 int ccb_env_voronoi_features_dev(ccb_env *env, double *out_dev); /* the same, left on the device */
 /* coverage_system.cpp:648-676 GetLocalVoronoiFeatures (own cell among the robot and its neighbours): E x R x 7 */
 int ccb_env_local_voronoi_features(ccb_env *env, double *out);
+/* coverage_system.h:603-610 GetRobotExplorationFeatures -> robot_model.h:347-403 GetExplorationFeatures:
+ * the num_frontiers (pNumFrontiers) best candidate points around every robot, worst first, as
+ * [dx, dy] pairs relative to the robot, zero-padded: E x R x (2 num_frontiers) */
+int ccb_env_exploration_features(ccb_env *env, int num_frontiers, double *out);
+/* Test hook, host only: the frontier queue of ccb_env_exploration_features (the kernel's own heap code
+ * compiled for the host) over values[n]; candidate numbers as popped, worst first; returns their count
+ * or -1.  Touches no map and no device. */
+int ccb_selftest_frontier_select(const double *values, int n, int num_frontiers, int *order_out);
 /* coverage_system.h:557-571 (ratio of explored cells / IDF-weighted): 2 doubles per env */
 int ccb_env_exploration_ratios(ccb_env *env, double *out /* E x 2 */);
 int ccb_env_check_oscillation(ccb_env *env, int e, int robot, int *out); /* coverage_system.h:341-363 */

@@ -875,6 +875,61 @@ void orc_env_voronoi_features(orc_env *e, int r, double *out7) {
   out7[3] = c.sum_idf_site_dist_sqr, out7[4] = 0, out7[5] = c.sum_idf_site_dist, out7[6] = 0;
 }
 
+/* frontier_pq.cpp: the real std::priority_queue of robot_model.h:383-401 */
+int orc_frontier_select(const double *values, int n, int num_frontiers, int *order_out);
+
+void orc_env_exploration_features(orc_env *e, int r, int num_frontiers, double *out) {
+  /* robot_model.h:347-403 GetExplorationFeatures */
+  const orc_params *p = &e->p;
+  const double posx = e->gcur[2 * r], posy = e->gcur[2 * r + 1];
+  const double tsd = p->pMaxRobotSpeed * p->pTimeStep * p->pResolution; /* :150-151 */
+  const double sensor_area = (double)(p->pSensorSize * p->pSensorSize);  /* :152 */
+  const double factor = 4;
+  const double pos_x_lim = fmin(posx + factor * tsd, (double)p->pWorldMapSize);
+  const double pos_y_lim = fmin(posy + factor * tsd, (double)p->pWorldMapSize);
+  const float *rm = e->robot_map + (size_t)r * e->N * e->N;
+  const float *ex = e->robot_expl ? e->robot_expl + (size_t)r * e->N * e->N : NULL;
+  int cap = 1024, n = 0;
+  double *val = (double *)malloc(sizeof(double) * cap), *qx = (double *)malloc(sizeof(double) * cap),
+         *qy = (double *)malloc(sizeof(double) * cap);
+  for (double px = fmax(posx - factor * tsd, 1e-4); px < pos_x_lim; px += 1 * p->pResolution) {
+    for (double py = fmax(posy - factor * tsd, 1e-4); py < pos_y_lim; py += 1 * p->pResolution) {
+      double dx = px - posx, dy = py - posy;
+      double dist = sqrt(dx * dx + dy * dy);
+      dist = fmax(dist, tsd);
+      orc_bounds ix, of;
+      orc_compute_offsets(p->pResolution, px, py, p->pSensorSize, p->pWorldMapSize, &ix, &of);
+      float unexplored_f = 0.f; /* Eigen block().sum() over floats 0/1: exact */
+      if (ex)
+        for (int a = 0; a < of.width; ++a)
+          for (int b = 0; b < of.height; ++b)
+            unexplored_f += ex[(size_t)(ix.left + of.left + a) * e->N + ix.bottom + of.bottom + b];
+      double unexplored = unexplored_f;
+      double benefit = unexplored;
+      if (unexplored > 0.1 * sensor_area) {
+        long cnt = 0; /* block().count(): non-zero coefficients */
+        for (int a = 0; a < of.width; ++a)
+          for (int b = 0; b < of.height; ++b)
+            cnt += rm[(size_t)(ix.left + of.left + a) * e->N + ix.bottom + of.bottom + b] != 0.f;
+        double idf_value = (double)cnt;
+        benefit += 2 * idf_value;
+      }
+      if (n == cap) {
+        cap *= 2;
+        val = (double *)realloc(val, sizeof(double) * cap);
+        qx = (double *)realloc(qx, sizeof(double) * cap);
+        qy = (double *)realloc(qy, sizeof(double) * cap);
+      }
+      val[n] = benefit / dist, qx[n] = px, qy[n] = py, ++n;
+    }
+  }
+  int *order = (int *)malloc(sizeof(int) * (num_frontiers > 0 ? num_frontiers : 1));
+  int got = orc_frontier_select(val, n, num_frontiers, order);
+  for (int k = 0; k < 2 * num_frontiers; ++k) out[k] = 0.0;
+  for (int k = 0; k < got; ++k) out[2 * k] = qx[order[k]] - posx, out[2 * k + 1] = qy[order[k]] - posy;
+  free(order), free(val), free(qx), free(qy);
+}
+
 /* ========================================================================== */
 /* Controllers                                                                 */
 /* ========================================================================== */

@@ -126,6 +126,9 @@ void orc_env_comm_maps_py(orc_env *e, int r, int map_size, float *out_x,
                           float *out_y);
 int orc_env_neighbors(const orc_env *e, int r, double *rel /* R x 2 */);
 void orc_env_voronoi_features(orc_env *e, int r, double *out7);
+/* robot_model.h:347-403: 2 * num_frontiers doubles [dx, dy, ...], worst frontier first, zero-padded;
+ * the frontier queue is the real std::priority_queue (frontier_pq.cpp) */
+void orc_env_exploration_features(orc_env *e, int r, int num_frontiers, double *out);
 int orc_env_check_oscillation(const orc_env *e, int r);
 
 /* ---- controllers -------------------------------------------------------- */

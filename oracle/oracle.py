@@ -116,6 +116,10 @@ def lib():
         L.orc_env_comm_maps_py.argtypes = [C.c_void_p, C.c_int, C.c_int, fp, fp]
         L.orc_env_neighbors.argtypes = [C.c_void_p, C.c_int, dp]
         L.orc_env_voronoi_features.argtypes = [C.c_void_p, C.c_int, dp]
+        L.orc_env_exploration_features.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
+        L.orc_env_exploration_features.restype = None
+        L.orc_frontier_select.argtypes = [dp, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.orc_frontier_select.restype = C.c_int
         L.orc_env_check_oscillation.argtypes = [C.c_void_p, C.c_int]
         L.orc_ctrl_compute_actions.argtypes = [C.c_void_p, C.c_int, dp, dp]
     return _lib
@@ -302,6 +306,11 @@ class Env:
         rel = np.zeros((self.R, 2), np.float64)
         n = lib().orc_env_neighbors(self._h, r, _dp(rel))
         return rel[:n].copy()
+
+    def exploration_features(self, r, num_frontiers):
+        out = np.zeros(2 * num_frontiers)
+        lib().orc_env_exploration_features(self._h, r, num_frontiers, _dp(out))
+        return out
 
     def voronoi_features(self, r):
         out = np.zeros(7, np.float64)
