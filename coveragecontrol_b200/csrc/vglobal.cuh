@@ -279,7 +279,10 @@ __device__ __forceinline__ void vg_add4(const float4 x, const double y0, double 
 }
 
 constexpr int VG_RED_MINB = 8;  // resident CTAs of VG_RED_WARPS warps per SM the register allocation aims for (64 registers)
-template <int SRC, bool LABELS, int U = VG_U, int MINB = VG_RED_MINB>
+// LPR lanes share a row: a pass is 32 / LPR rows x 4 LPR columns (512 bytes either way).  The map-only
+// instantiation runs with LPR = 4 (8 rows x 16 columns): half as many row groups per item and less of a
+// pass lost at the ends of an interval than with 4 rows x 32 columns (0.93 -> 0.85 ms).
+template <int SRC, bool LABELS, int U = VG_U, int MINB = VG_RED_MINB, int LPR = 8>
 __global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a) {
   const EnvDev &d = a.d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -290,7 +293,10 @@ __global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a)
   const float *world = d.world + (size_t)e * N * N;
   const uint32_t *plane = SRC == SRC_EXPLORED ? d.sysb + ((size_t)e * 2) * plane_words(d) : nullptr;
   int *labels = (LABELS && a.labels) ? a.labels + (size_t)e * N * N : nullptr;
-  const int g = lane >> 3, c8 = lane & 7;
+  static_assert(LPR == 8 || (SRC == SRC_WORLD && !LABELS), "bit-plane words and label rows assume 32-column passes");
+  constexpr int P = 4 * LPR, RQ = 32 / LPR, SH = LPR == 8 ? 5 : (LPR == 4 ? 4 : 3);
+  static_assert((1 << SH) == P, "pass width");
+  const int g = lane / LPR, c8 = lane % LPR;
   // the grid is a fraction of the largest possible item count: a warp strides over the items
 #pragma unroll 1
   for (int item = blockIdx.x * (blockDim.x >> 5) + warp; item < total; item += gridDim.x * (blockDim.x >> 5)) {
@@ -320,14 +326,14 @@ __global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a)
     }
     double M = 0.0, SX = 0.0, SY = 0.0, S2 = 0.0;
 #pragma unroll 1
-    for (int q = 0; q < VG_CHUNK / 4; ++q) {
-      const int lo = __shfl_sync(0xffffffffu, lo_l, 4 * q + g), hi = __shfl_sync(0xffffffffu, hi_l, 4 * q + g);
+    for (int q = 0; q < VG_CHUNK / RQ; ++q) {
+      const int lo = __shfl_sync(0xffffffffu, lo_l, RQ * q + g), hi = __shfl_sync(0xffffffffu, hi_l, RQ * q + g);
       const bool has = hi > lo;
       const int qlo = __reduce_min_sync(0xffffffffu, has ? lo : 0x7fffffff), qhi = __reduce_max_sync(0xffffffffu, has ? hi : 0);
       if (qhi <= qlo) continue;  // warp-uniform
-      const int row = rbase + 4 * q + g;
+      const int row = rbase + RQ * q + g;
       // pass j covers columns cb0 + 32 j ..; this lane's cells: col0 + 32 j .. + 3
-      const int cb0 = qlo & ~31, npass = (qhi - cb0 + 31) >> 5;
+      const int cb0 = qlo & ~(P - 1), npass = (qhi - cb0 + P - 1) >> SH;
       const int col0 = cb0 + 4 * c8;
       const float4 *p4 = reinterpret_cast<const float4 *>(world + (size_t)row * N + col0);
       const uint32_t *pw = SRC == SRC_EXPLORED ? plane + (size_t)row * d.NW + (cb0 >> 5) : nullptr;
@@ -337,19 +343,19 @@ __global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a)
       // Pass j holds the lane's cells 32 j .. 32 j + 3.  They touch [A, B) for jl0 <= j <= jl1 (the passes
       // the lane requests) and lie inside it for jf0 <= j <= jf1 (added without a mask); only the passes
       // holding A or B in between need one.
-      const int jl0 = (A + 28) >> 5, jl1 = (B - 1) >> 5;
-      const int jf0 = A > 0 ? (A + 31) >> 5 : 0, jf1 = (B - 4) >> 5;
+      const int jl0 = (A + P - 4) >> SH, jl1 = (B - 1) >> SH;
+      const int jf0 = A > 0 ? (A + P - 1) >> SH : 0, jf1 = (B - 4) >> SH;
       double rs = 0.0, rsy = 0.0, rsyy = 0.0;
 #pragma unroll 1
       for (int base = 0; base < npass; base += U) {
         // request the whole batch, then consume it: U x 512 bytes in flight per warp
         float4 w[U];
-        const int Ab = A - 32 * base, Bb = B - 32 * base;  // the interval relative to the batch's first pass
+        const int Ab = A - P * base, Bb = B - P * base;  // the interval relative to the batch's first pass
         const int l0 = jl0 - base, l1 = jl1 - base, f0 = jf0 - base, f1 = jf1 - base;
         unsigned kl = 0u, kp = 0u;  // LABELS / SRC_EXPLORED: 4 keep bits per pass (kl: inside the interval, kp: to add)
         if (LABELS || SRC == SRC_EXPLORED) {
 #pragma unroll
-          for (int j = 0; j < U; ++j) kl |= vg_keep4(32 * j, Ab, Bb) << (4 * j);
+          for (int j = 0; j < U; ++j) kl |= vg_keep4(P * j, Ab, Bb) << (4 * j);
           kp = kl;
           if (SRC == SRC_EXPLORED) {
             uint32_t pwv[U];
@@ -363,9 +369,9 @@ __global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a)
         for (int j = 0; j < U; ++j) {
           // (jl1 < npass: no pass beyond the row group's last one is asked for)
           const bool want = (LABELS || SRC == SRC_EXPLORED) ? ((kp >> (4 * j)) & 0xfu) != 0u && base + j < npass : (j >= l0 && j <= l1);
-          if (want) w[j] = __ldg(p4 + 8 * (base + j));
+          if (want) w[j] = __ldg(p4 + LPR * (base + j));
         }
-        double y0 = (double)(col0 + 32 * base) + 0.5;
+        double y0 = (double)(col0 + P * base) + 0.5;
 #pragma unroll
         for (int j = 0; j < U; ++j) {
           if (base + j >= npass) break;  // warp-uniform
@@ -378,12 +384,12 @@ __global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a)
           }
           // w[j] is only defined where the lane asked for it
           if ((LABELS || SRC == SRC_EXPLORED) || j < f0 || j > f1) {  // an end of the interval, outside it, unexplored cells
-            const unsigned keep = (LABELS || SRC == SRC_EXPLORED) ? (kp >> (4 * j)) & 0xfu : vg_keep4(32 * j, Ab, Bb);
+            const unsigned keep = (LABELS || SRC == SRC_EXPLORED) ? (kp >> (4 * j)) & 0xfu : vg_keep4(P * j, Ab, Bb);
             w[j].x = (keep & 1u) ? w[j].x : 0.f, w[j].y = (keep & 2u) ? w[j].y : 0.f;
             w[j].z = (keep & 4u) ? w[j].z : 0.f, w[j].w = (keep & 8u) ? w[j].w : 0.f;
           }
           vg_add4(w[j], y0, rs, rsy, rsyy);
-          y0 += 32.0;
+          y0 += (double)P;
         }
       }
       const double x = (double)row + 0.5;
