@@ -89,6 +89,7 @@ SIGNATURES = {
     "ccb_env_obstacle_maps_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ccb_env_comm_maps_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ccb_env_cnn_input_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ccb_env_graph_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ccb_env_comm_maps_cpp": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
     "ccb_env_compute_voronoi": (C.c_int, [C.c_void_p]),
     "ccb_env_get_cells": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p,

@@ -109,8 +109,15 @@ class CoverageEnvUtils:
         return CoverageEnvUtils.to_tensor(env.GetRobotPositions())
 
     @staticmethod
-    def get_weights(env, params: Parameters) -> torch.Tensor:
-        """reference :313-335."""
+    def get_weights(env, params: Parameters, device=None) -> torch.Tensor:
+        """reference :313-335 -> [R, R] ([E, R, R] batched).  ``device=None``: host tensor computed with the
+        reference's own torch expressions; any ``device``: the ``k_graph`` kernel, no host round trip."""
+        if device is not None:
+            if float(params.pCommunicationRange) != float(env._params.pCommunicationRange):
+                raise ValueError("get_weights(device=...): params.pCommunicationRange differs from the environment's")
+            out = torch.empty((env._E, env._R, env._R), dtype=torch.float32, device=_cuda_device(env))
+            _lib.check(_lib.load().ccb_env_graph_dev(env._h, out.data_ptr(), None))
+            return _finish(out, env, device)
         onebyexp = 1.0 / math.exp(1.0)
         robot_positions = CoverageEnvUtils.get_robot_positions(env)
         pairwise_distances = torch.cdist(robot_positions, robot_positions, 2)
@@ -123,20 +130,50 @@ class CoverageEnvUtils:
         return edge_weights
 
     @staticmethod
-    def get_torch_geometric_data(env, params: Parameters, use_cnn: bool, use_comm_map: bool, map_size: int):
-        """reference :337-377 (needs torch_geometric, which this image does not ship)."""
-        try:
-            import torch_geometric
-        except ImportError as exc:  # pragma: no cover
-            raise ImportError("get_torch_geometric_data needs torch_geometric") from exc
+    def get_torch_geometric_data(env, params: Parameters, use_cnn: bool, use_comm_map: bool, map_size: int, device=None):
+        """reference :337-377 for one CoverageSystem.  Everything is produced on the GPU (node features by
+        ``get_maps`` / ``k_voronoi_features``, edge weights and normalised positions by ``k_graph``) and stays
+        there unless ``device`` says otherwise: no host round trip between the simulator and the GNN.
+        Returns ``torch_geometric.data.Data`` when torch_geometric is importable, else a ``GraphData`` with
+        the same four fields (this image does not ship torch_geometric)."""
+        if isinstance(env, BatchedCoverageSystem):
+            raise ValueError("get_torch_geometric_data takes one CoverageSystem, as the reference; "
+                             "use get_maps / get_weights(device=...) for a batch")
+        if float(params.pCommunicationRange) != float(env._params.pCommunicationRange) or \
+                int(params.pWorldMapSize) != int(env._params.pWorldMapSize):
+            raise ValueError("get_torch_geometric_data: params differ from the environment's")
+        dev = _cuda_device(env)
         if use_cnn:
             features = CoverageEnvUtils.get_maps(env, params, map_size, use_comm_map)
         else:
-            features = CoverageEnvUtils.get_voronoi_features(env)
-        edge_weights = CoverageEnvUtils.get_weights(env, params).to_sparse().coalesce()
-        edge_index = edge_weights.indices().long()
-        weights = edge_weights.values().float()
-        pos = CoverageEnvUtils.get_robot_positions(env)
-        pos = (pos + params.pWorldMapSize / 2.0) / params.pWorldMapSize
-        return torch_geometric.data.Data(x=features, edge_index=edge_index.clone().detach(),
-                                         edge_weight=weights.clone().detach(), pos=pos.clone().detach())
+            feats = torch.empty((env._E, env._R, 7), dtype=torch.float64, device=dev)
+            _lib.check(_lib.load().ccb_env_voronoi_features_dev(env._h, feats.data_ptr()))
+            features = _finish(feats, env, None).to(torch.float32)
+        w = torch.empty((1, env._R, env._R), dtype=torch.float32, device=dev)
+        pos = torch.empty((1, env._R, 2), dtype=torch.float32, device=dev)
+        _lib.check(_lib.load().ccb_env_graph_dev(env._h, w.data_ptr(), pos.data_ptr()))
+        w, pos = _finish(w, env, None), _finish(pos, env, None)
+        edge_index = w.nonzero().t().contiguous()          # row-major order, as to_sparse().coalesce().indices()
+        edge_weight = w[edge_index[0], edge_index[1]]
+        if device is not None:
+            features, edge_index, edge_weight, pos = (t.to(device) for t in (features, edge_index, edge_weight, pos))
+        try:
+            import torch_geometric
+        except ImportError:
+            return GraphData(x=features, edge_index=edge_index, edge_weight=edge_weight, pos=pos)
+        return torch_geometric.data.Data(x=features, edge_index=edge_index, edge_weight=edge_weight, pos=pos)
+
+
+class GraphData:
+    """The four fields of the ``torch_geometric.data.Data`` object the reference builds
+    (coverage_env_utils.py:370-375), for installations without torch_geometric."""
+
+    def __init__(self, x, edge_index, edge_weight, pos):
+        self.x, self.edge_index, self.edge_weight, self.pos = x, edge_index, edge_weight, pos
+
+    @property
+    def num_nodes(self) -> int:
+        return int(self.pos.shape[0])
+
+    def to(self, device):
+        return GraphData(self.x.to(device), self.edge_index.to(device), self.edge_weight.to(device), self.pos.to(device))

@@ -1039,6 +1039,14 @@ extern "C" int ccb_env_obstacle_maps_dev(ccb_env *env, float *out_dev) {
   CCB_LAUNCH_CHECK();
   return 0;
 }
+// coverage_env_utils.py:313-335 get_weights + the normalised positions of :368-369, left on the device
+extern "C" int ccb_env_graph_dev(ccb_env *env, float *weights_dev, float *pos_norm_dev) {
+  if (!env->initialised) return fail("environment has no robot positions yet");
+  CCB_CUDA(cudaSetDevice(env->device));
+  k_graph<<<env->d.E, 256, 0, env->stream>>>(env->d, weights_dev, pos_norm_dev);
+  CCB_LAUNCH_CHECK();
+  return 0;
+}
 extern "C" int ccb_env_comm_maps_dev(ccb_env *env, int C, float *out_dev) {
   CCB_CUDA(cudaSetDevice(env->device));
   const EnvDev &d = env->d;

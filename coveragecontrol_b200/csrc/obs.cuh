@@ -32,6 +32,32 @@ __global__ void k_raw_window_maps(EnvDev d, int kind, float *__restrict__ out) {
   }
 }
 
+// ---- communication graph of LPAC's GNN -----------------------------------------------------------------
+// coverage_env_utils.py:313-335 get_weights and :368-369 of get_torch_geometric_data, float32 as there:
+//   w[i][j] = exp(-|p_i - p_j|^2 / Rc^2), set to 0 below 1/e (i.e. beyond the communication range) and on
+//   the diagonal;  pos_norm = (p + N/2) / N.
+// One CTA per environment; weights [E][R][R], pos_norm [E][R][2] (either may be null).
+__global__ void k_graph(EnvDev d, float *__restrict__ weights, float *__restrict__ pos_norm) {
+  const int e = blockIdx.x, R = d.R;
+  const double *pos = d.pos_g + (size_t)e * R * 2;
+  const float rc2 = (float)(d.comm_range * d.comm_range);
+  const float onebyexp = (float)(1.0 / exp(1.0));
+  if (weights) {
+    for (int t = threadIdx.x; t < R * R; t += blockDim.x) {
+      const int i = t / R, j = t - i * R;
+      const float dx = __fsub_rn((float)pos[2 * i], (float)pos[2 * j]), dy = __fsub_rn((float)pos[2 * i + 1], (float)pos[2 * j + 1]);
+      const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+      float w = expf(-d2 / rc2);
+      if (w < onebyexp || i == j) w = 0.f;
+      weights[(size_t)e * R * R + t] = w;
+    }
+  }
+  if (pos_norm) {
+    const float half = (float)d.N / 2.f, size = (float)d.N;
+    for (int t = threadIdx.x; t < 2 * R; t += blockDim.x) pos_norm[(size_t)e * 2 * R + t] = __fadd_rn((float)pos[t], half) / size;
+  }
+}
+
 // Communication maps with the semantics LPAC consumes (coverage_env_utils.py:143-191): float32
 // arithmetic, torch.round = round-half-even, duplicates summed.  out: E x R x 2 x C x C, or a
 // channel slice of a wider tensor (chan_stride = floats between robots, chan_off = first channel).

@@ -149,6 +149,10 @@ int ccb_env_local_maps_dev(ccb_env *env, float *out_dev);
 int ccb_env_obstacle_maps_dev(ccb_env *env, float *out_dev);
 int ccb_env_comm_maps_dev(ccb_env *env, int C, float *out_dev);
 int ccb_env_cnn_input_dev(ccb_env *env, int C, int use_comm, float *out_dev);
+/* LPAC's communication graph (coverage_env_utils.py:313-335 get_weights, :368-369 normalised positions),
+ * float32 on the device: weights E x R x R (exp(-d^2 / Rc^2), 0 below 1/e and on the diagonal),
+ * pos_norm E x R x 2 ((p + N/2) / N); either pointer may be NULL */
+int ccb_env_graph_dev(ccb_env *env, float *weights_dev, float *pos_norm_dev);
 /* coverage_system.cpp:177-199 GetCommunicationMaps (C++ float64 semantics), host, env e: R x 2 x C x C */
 int ccb_env_comm_maps_cpp(ccb_env *env, int e, int C, float *out);
 

@@ -105,6 +105,43 @@ def test_weights_and_positions():
     assert torch.allclose(w, ref)
 
 
+def test_graph_data_on_device():
+    """get_weights(device=...) and get_torch_geometric_data (reference coverage_env_utils.py:313-377): the k_graph
+    kernel against the reference's own torch expressions on the host; tolerance 1e-5 on float32 weights (torch's
+    cdist goes through a matrix product for more than 25 points), edges compared away from the 1/e threshold."""
+    import torch
+
+    cc, orc, p, env, oenv = _setup(steps=3)
+    U = cc.CoverageEnvUtils
+    host = U.get_weights(env, p)
+    dev = U.get_weights(env, p, device="cuda")
+    assert dev.is_cuda and dev.shape == host.shape and dev.dtype == torch.float32
+    pos = U.get_robot_positions(env).double()
+    d2 = torch.cdist(pos, pos, 2).square()
+    exact = torch.exp(-d2 / p.pCommunicationRange ** 2)
+    sure = (exact - 1.0 / np.e).abs() > 1e-4  # pairs whose side of the threshold does not hang on float32 rounding
+    assert torch.allclose(dev.cpu()[sure], host[sure], rtol=0, atol=1e-5)
+    assert torch.all(dev.cpu().diagonal() == 0)
+    for use_cnn in (True, False):
+        g = U.get_torch_geometric_data(env, p, use_cnn, True, 32)
+        assert g.x.is_cuda and g.edge_index.is_cuda and g.edge_weight.is_cuda and g.pos.is_cuda
+        want_x = U.get_maps(env, p, 32, True) if use_cnn else U.get_voronoi_features(env)
+        assert torch.allclose(g.x.cpu(), want_x.cpu())
+        ref_pos = (U.get_robot_positions(env) + p.pWorldMapSize / 2.0) / p.pWorldMapSize
+        assert torch.allclose(g.pos.cpu(), ref_pos, rtol=0, atol=1e-6)
+        sp = host.to_sparse().coalesce()
+        if bool(sure.all()):
+            assert torch.equal(g.edge_index.cpu(), sp.indices().long())
+            assert torch.allclose(g.edge_weight.cpu(), sp.values().float(), rtol=0, atol=1e-5)
+        assert g.edge_index.dtype == torch.long and g.edge_index.shape[0] == 2
+        assert g.edge_weight.shape[0] == g.edge_index.shape[1] and torch.all(g.edge_weight >= 1.0 / np.e - 1e-6)
+        assert g.num_nodes == p.pNumRobots
+    with pytest.raises(ValueError):
+        q = p.copy() if hasattr(p, "copy") else p
+        q.pCommunicationRange = p.pCommunicationRange + 1.0
+        U.get_weights(env, q, device="cuda")
+
+
 @pytest.mark.parametrize("N,fill", [(1000, False), (1024, True), (600, False)])
 def test_cnn_input_every_window_alignment(N, fill):
     """Window origins with every column misalignment (oy & 3), windows overhanging all four map edges,
