@@ -1,0 +1,168 @@
+"""Host side of the drop-in boundary that needs no GPU: the Parameters mirror (reference parameters.h:49-175,
+parameters.cpp:36-261; the reference's own python/tests/test_parameters.py logic), the value types and opaque
+vectors of core_binds.h:63-112, and the import names the reference package exposes.  Expected values come from
+tests/golden/params_golden.json, derived from the reference tree by tests/golden/make_params_golden.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "params_golden.json")))
+
+
+def test_parameter_defaults_match_the_reference_header():
+    import coverage_control as cc
+
+    p = cc.Parameters()
+    assert set(cc.Parameters._DEFAULTS) == set(GOLD["defaults"])
+    for name, want in GOLD["defaults"].items():
+        got = getattr(p, name)
+        assert type(got) is type(want) and got == want, (name, got, want)
+
+
+def test_every_parameter_is_a_toml_key_as_in_the_reference_test():
+    """python/tests/test_parameters.py:34-67: every p* attribute, minus the p, is a leaf of the TOML file (the only
+    exception is NumGaussianFeatures, which parameters.cpp:125 reads but the shipped TOML spells NumFeatures)."""
+    import coverage_control as cc
+
+    names = [a[1:] for a in dir(cc.Parameters()) if a.startswith("p") and a[1].isupper()]
+    assert len(names) == len(GOLD["defaults"])
+    missing = [n for n in names if n not in GOLD["toml_keys"]]
+    assert missing == ["NumGaussianFeatures"]
+    # and the paths the mirror reads end in exactly those keys
+    assert sorted(path[-1] for path in cc.Parameters._TOML) == sorted(names)
+
+
+def _toml_text(values):
+    import coverage_control as cc
+
+    tree = {}
+    for path, attr in cc.Parameters._TOML.items():
+        node = tree
+        for key in path[:-1]:
+            node = node.setdefault(key, {})
+        node[path[-1]] = values[attr]
+
+    def emit(node, prefix):
+        out = []
+        for k, v in node.items():
+            if not isinstance(v, dict):
+                out.append(f"{k} = {str(v).lower() if isinstance(v, bool) else repr(v)}")
+        for k, v in node.items():
+            if isinstance(v, dict):
+                name = ".".join(prefix + [f'"{k}"' if "-" in k else k])
+                out.append(f"[{name}]")
+                out.extend(emit(v, prefix + [f'"{k}"' if "-" in k else k]))
+        return out
+
+    return "\n".join(emit(tree, [])) + "\n"
+
+
+def test_parameters_load_a_config_file(tmp_path):
+    import coverage_control as cc
+
+    # the reference's shipped values, then every value changed
+    for bump in (False, True):
+        values = dict(GOLD["defaults"])
+        values.update(GOLD["toml"])
+        if bump:
+            values = {k: (not v if isinstance(v, bool) else v + 3 if isinstance(v, int) else v * 1.5 + 0.25) for k, v in values.items()}
+        f = tmp_path / f"params_{int(bump)}.toml"
+        f.write_text(_toml_text(values))
+        p = cc.Parameters(str(f))
+        for name, want in values.items():
+            assert getattr(p, name) == want, (name, getattr(p, name), want)
+        q = cc.Parameters()
+        q.SetConfig(str(f))
+        assert all(getattr(q, n) == getattr(p, n) for n in values)
+        c = p.copy()
+        c.pNumRobots += 1
+        assert p.pNumRobots == values["pNumRobots"]
+
+
+def test_parameters_errors(tmp_path):
+    import coverage_control as cc
+
+    with pytest.raises(RuntimeError):
+        cc.Parameters(str(tmp_path / "absent.toml"))
+    bad = tmp_path / "bad.toml"
+    bad.write_text("NumRobots = = 3\n")
+    with pytest.raises(RuntimeError):
+        cc.Parameters(str(bad))
+    zero = tmp_path / "zero.toml"
+    zero.write_text("NumRobots = 0\n")
+    with pytest.raises(RuntimeError):
+        cc.Parameters(str(zero))
+    partial = tmp_path / "partial.toml"
+    partial.write_text("NumRobots = 7\n[RobotModel]\nSensorSize = 32\n")
+    p = cc.Parameters(str(partial))
+    assert p.pNumRobots == 7 and p.pSensorSize == 32 and p.pWorldMapSize == GOLD["defaults"]["pWorldMapSize"]
+
+
+def test_value_types_and_vectors():
+    """core_binds.h:63-112; the usages of python/tests/test_coverage.py:40-43 and controllers.py:150."""
+    import coverage_control as cc
+
+    assert cc.Point2().dtype == np.float64 and np.array_equal(cc.Point2(), [0, 0])
+    assert np.array_equal(cc.Point2(3, 4.5), [3.0, 4.5])
+    src = np.array([1.0, 2.0])
+    cp = cc.Point2(src)
+    cp[0] = 9
+    assert src[0] == 1.0
+    with pytest.raises(TypeError):
+        cc.Point2([1, 2, 3])
+    from coverage_control import _core  # Point2f / intVector are bound (core_binds.h:71,80) but not re-exported
+
+    assert _core.Point2f(1, 2).dtype == np.float32
+
+    pv = cc.PointVector(np.array([[1.0, 2.0], [3.0, 4.0]]))
+    pv.append(np.array([5.0, 6.0]))
+    pv.append(cc.Point2(7, 8))
+    assert len(pv) == 4 and isinstance(pv, cc.PointVector)
+    assert np.array_equal(pv.to_numpy(), [[1, 2], [3, 4], [5, 6], [7, 8]])
+    assert np.array_equal(np.array(pv), pv.to_numpy())
+    with pytest.raises(TypeError):
+        pv.append([1.0, 2.0, 3.0])
+    assert len(cc.PointVector(3)) == 3 and np.array_equal(cc.PointVector(3).to_numpy(), np.zeros((3, 2)))
+
+    dv = cc.DblVector([1, 2.5])
+    dv.append(3)
+    assert list(dv) == [1.0, 2.5, 3.0] and all(isinstance(v, float) for v in dv)
+    dvv = cc.DblVectorVector([[1, 2], [3]])
+    assert isinstance(dvv[0], cc.DblVector) and list(dvv[1]) == [3.0]
+    assert list(_core.intVector([1.0, 2.0])) == [1, 2]
+
+    b = cc.BivariateNormalDistribution()
+    assert np.array_equal(b.GetMean(), [0, 0]) and np.array_equal(b.GetSigma(), [1, 1]) and b.GetScale() == 1.0 and b.GetRho() == 0.0
+    b = cc.BivariateNormalDistribution(cc.Point2(10, 20), 5.0, 8.0)
+    assert np.array_equal(b.GetMean(), [10, 20]) and np.array_equal(b.GetSigma(), [5, 5]) and b.GetScale() == 8.0
+    b = cc.BivariateNormalDistribution(cc.Point2(1, 2), cc.Point2(3, 4), 0.5, 6.0)
+    assert np.array_equal(b.GetSigma(), [3, 4]) and b.GetScale() == 6.0
+    assert b.GetRho() == 0.0  # bivariate_normal_distribution.h:103-116 tests its member rho_, not the argument
+
+    f = cc.PolygonFeature(cc.PointVector([[0, 0], [4, 0], [0, 4]]), 0.25)
+    assert f.size == 3 and f.imp == 0.25 and isinstance(f.poly, cc.PointVector)
+    assert cc.PolygonFeature().size == 0
+
+
+def test_import_names_of_the_reference_package():
+    """python/coverage_control/__init__.py:11-14, core/__init__.py:7-22, algorithms/__init__.py."""
+    import coverage_control as cc
+    import coverage_control.algorithms as alg
+    import coverage_control.core as core
+    from coverage_control import CoverageEnvUtils, IOUtils  # noqa: F401
+
+    for name in ("Point2", "PointVector", "DblVector", "DblVectorVector", "Parameters", "BivariateNormalDistribution",
+                 "BNDVector", "WorldIDF", "RobotModel", "CoverageSystem", "PolygonFeature", "VoronoiCell", "VoronoiCells",
+                 "CudaUtils"):
+        assert hasattr(core, name) or name == "RobotModel", name
+        assert hasattr(cc, name) or name == "RobotModel", name
+    for name in ("ClairvoyantCVT", "CentralizedCVT", "DecentralizedCVT", "NearOptimalCVT"):
+        assert hasattr(alg, name), name
+    assert isinstance(cc.__version__, str)
+    assert cc.CudaUtils.UseCuda() in (True, False)
+    with pytest.raises(RuntimeError):
+        cc.CudaUtils.SetUseCuda(False)  # there is no CPU path to switch to
