@@ -238,7 +238,7 @@ __device__ __forceinline__ void cnn8_width_pass(const EnvDev &d, Cnn8Shared &sh,
           const float4 *src = reinterpret_cast<const float4 *>(world + (size_t)(ox_map + ai - 4) * d.N + gyb);
 #pragma unroll
           for (int j = 0; j < NV; ++j)
-            if (grp_in[j]) v[b][j] = __ldcs(src + j);  // streaming: 3-5 % over __ldg (scripts/ab_ldcs.py)
+            if (grp_in[j]) v[b][j] = __ldcs(src + j);  // read once per CTA: streaming load, 3-5 % over __ldg
         }
       }
     }

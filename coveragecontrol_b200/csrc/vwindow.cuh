@@ -136,7 +136,7 @@ __device__ __forceinline__ void vw_accumulate(const EnvDev &d, VwShared &sh, con
           const float4 *src = reinterpret_cast<const float4 *>(world + (size_t)(w.ox + a) * d.N + gyb);
 #pragma unroll
           for (int j = 0; j < NV; ++j)
-            if (grp_in[j]) v[b][j] = __ldcs(src + j);  // streaming: 3-5 % over __ldg (scripts/ab_ldcs.py)
+            if (grp_in[j]) v[b][j] = __ldcs(src + j);  // read once per CTA: streaming load, 3-5 % over __ldg
         }
       }
     }
