@@ -1,8 +1,9 @@
-"""A/B of k_vg_reduce's unmasked interior run (CCB_VG_LEAN = 0 none, 1 = 4 passes / 72 registers,
-2 = 8 passes / 80 registers) on the bench workload: reduce alone and the whole partition + reduce +
-fix-up chain, CUDA events, plus the spread of the objectives between the variants.
+"""A/B timing of the site-ordered whole-map Voronoi chain on the bench workload: k_vg_reduce alone, k_vg_partition
+alone and the whole partition + items + reduce + fix-up chain (CUDA events, ccb_bench_kernel), for a list of
+CCB_VG_* settings (CCB_VG_WARPS = warps per CTA, CCB_VG_GRIDDIV = grid divisor, CCB_VG_GENERIC = tile-ordered
+kernel), plus the spread of the objectives between the settings.
 
-    python scripts/ab_vg_lean.py [--envs 1024] [--iters 20] [--steps 20]
+    python scripts/ab_vg_reduce.py [--envs 1024] [--iters 20] [--steps 20] [--configs "WARPS=1;WARPS=4;GENERIC=1"]
 """
 import argparse
 import json
@@ -22,7 +23,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--envs", type=int, default=1024)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--steps", type=int, default=20, help="decentralized roll-out steps before timing")
-ap.add_argument("--configs", default="LEAN=0;LEAN=1;LEAN=2", help="';'-separated CCB_VG_* settings, e.g. 'LEAN=0,WARPS=1'")
+ap.add_argument("--configs", default="WARPS=1;WARPS=4", help="';'-separated CCB_VG_* settings, e.g. 'WARPS=1,GRIDDIV=4'")
 args = ap.parse_args()
 
 lib = _lib.load()
