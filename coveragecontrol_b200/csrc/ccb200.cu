@@ -556,7 +556,7 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
         else k_vg_reduce<SRC_WORLD, false, VG_U, VG_RED_MINB, 4><<<rgrid, nt, 0, env->stream>>>(g);  // 8 rows x 16 columns per pass
       } else {
         if (labels) k_vg_reduce<SRC_EXPLORED, true><<<rgrid, nt, 0, env->stream>>>(g);
-        else k_vg_reduce<SRC_EXPLORED, false><<<rgrid, nt, 0, env->stream>>>(g);
+        else k_vg_reduce<SRC_EXPLORED, false, VG_U, VG_RED_MINB, 4><<<rgrid, nt, 0, env->stream>>>(g);
       }
       CCB_LAUNCH_CHECK();
     }

@@ -279,9 +279,9 @@ __device__ __forceinline__ void vg_add4(const float4 x, const double y0, double 
 }
 
 constexpr int VG_RED_MINB = 8;  // resident CTAs of VG_RED_WARPS warps per SM the register allocation aims for (64 registers)
-// LPR lanes share a row: a pass is 32 / LPR rows x 4 LPR columns (512 bytes either way).  The map-only
-// instantiation runs with LPR = 4 (8 rows x 16 columns): half as many row groups per item and less of a
-// pass lost at the ends of an interval than with 4 rows x 32 columns (0.93 -> 0.85 ms).
+// LPR lanes share a row: a pass is 32 / LPR rows x 4 LPR columns (512 bytes either way).  The instantiations
+// without labels run with LPR = 4 (8 rows x 16 columns): half as many row groups per item and less of a pass
+// lost at the ends of an interval than with 4 rows x 32 columns (map: 0.93 -> 0.85 ms, explored map: -16 %).
 template <int SRC, bool LABELS, int U = VG_U, int MINB = VG_RED_MINB, int LPR = 8>
 __global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a) {
   const EnvDev &d = a.d;
@@ -293,7 +293,6 @@ __global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a)
   const float *world = d.world + (size_t)e * N * N;
   const uint32_t *plane = SRC == SRC_EXPLORED ? d.sysb + ((size_t)e * 2) * plane_words(d) : nullptr;
   int *labels = (LABELS && a.labels) ? a.labels + (size_t)e * N * N : nullptr;
-  static_assert(LPR == 8 || (SRC == SRC_WORLD && !LABELS), "bit-plane words and label rows assume 32-column passes");
   constexpr int P = 4 * LPR, RQ = 32 / LPR, SH = LPR == 8 ? 5 : (LPR == 4 ? 4 : 3);
   static_assert((1 << SH) == P, "pass width");
   const int g = lane / LPR, c8 = lane % LPR;
@@ -336,7 +335,7 @@ __global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a)
       const int cb0 = qlo & ~(P - 1), npass = (qhi - cb0 + P - 1) >> SH;
       const int col0 = cb0 + 4 * c8;
       const float4 *p4 = reinterpret_cast<const float4 *>(world + (size_t)row * N + col0);
-      const uint32_t *pw = SRC == SRC_EXPLORED ? plane + (size_t)row * d.NW + (cb0 >> 5) : nullptr;
+      const uint32_t *pw = SRC == SRC_EXPLORED ? plane + (size_t)row * d.NW : nullptr;  // the row's explored bits
       int *lrow = LABELS && labels ? labels + (size_t)row * N + col0 : nullptr;
       // the interval relative to the lane's first cell (an empty one for a row without cells of the site)
       const int A = has ? lo - col0 : 0, B = has ? hi - col0 : 0;
@@ -360,9 +359,9 @@ __global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a)
           if (SRC == SRC_EXPLORED) {
             uint32_t pwv[U];
 #pragma unroll
-            for (int j = 0; j < U; ++j) pwv[j] = (((kl >> (4 * j)) & 0xfu) && base + j < npass) ? __ldg(pw + base + j) : 0u;
+            for (int j = 0; j < U; ++j) pwv[j] = (((kl >> (4 * j)) & 0xfu) && base + j < npass) ? __ldg(pw + ((col0 + P * (base + j)) >> 5)) : 0u;
 #pragma unroll
-            for (int j = 0; j < U; ++j) kp &= ~(0xfu << (4 * j)) | (((pwv[j] >> (col0 & 31)) & 0xfu) << (4 * j));
+            for (int j = 0; j < U; ++j) kp &= ~(0xfu << (4 * j)) | (((pwv[j] >> ((col0 + P * (base + j)) & 31)) & 0xfu) << (4 * j));
           }
         }
 #pragma unroll
@@ -379,7 +378,7 @@ __global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a)
             if (lrow) {
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                if ((kl >> (4 * j + i)) & 1u) lrow[32 * (base + j) + i] = k;
+                if ((kl >> (4 * j + i)) & 1u) lrow[P * (base + j) + i] = k;
             }
           }
           // w[j] is only defined where the lane asked for it

@@ -67,7 +67,7 @@ for mode in args.configs.split(";"):
     torch.cuda.synchronize()
     _lib.check(lib.ccb_bench_kernel(batch._h, 0, 1, obs.data_ptr()))
     r = {"reduce_ms": timed(batch, 6, args.iters, obs), "partition_ms": timed(batch, 7, args.iters, obs),
-         "chain_ms": timed(batch, 0, args.iters, obs)}
+         "chain_ms": timed(batch, 0, args.iters, obs), "explored_chain_ms": timed(batch, 1, args.iters, obs)}
     r["reduce_gbs"] = 4.0 * 1024 * 1024 * E / (r["reduce_ms"] * 1e-3) / 1e9
     objs[mode] = np.array(batch.objective())
     out[mode] = r
