@@ -19,6 +19,7 @@ from __future__ import annotations
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import subprocess
 import sys
@@ -373,6 +374,19 @@ def main():
 
     # ---- single-environment latency (API-faithful, E = 1) and the C1 variant, reported as extras -----
     extras = {"idf_gen_ms_1024_32f_mode0": idf_ms}
+    if idf_ms:
+        # flops_idf = 8 N^2 F + 16 N^2 F p_in + 2 N^2, p_in = share of (cell, feature) pairs inside
+        # the truncation radius (pi (T sigma)^2 / N^2 at the mean sigma); the FP32 peak is nominal
+        # (148 SMs x 128 lanes x 2 x the maximum SM clock): there is no measured FP32 figure in MEASURED_PEAKS.json.
+        # At this size the three launches of GenerateMap (integrate, maximum, normalise) dominate: the kernel
+        # itself runs 8 us (profiles/*_summary.md).
+        sig = 0.5 * (p.pMinSigma + p.pMaxSigma)
+        p_in = min(1.0, math.pi * (p.pTruncationBND * sig) ** 2 / (N_WORLD * N_WORLD))
+        flops = N_WORLD * N_WORLD * (8.0 * N_FEATURES + 16.0 * N_FEATURES * p_in + 2.0)
+        fp32_peak = 148 * 128 * 2 * (clocks or {}).get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+        extras["idf_fp32_roofline"] = {"flops": flops, "achieved_tflops": flops / (idf_ms * 1e-3) / 1e12,
+                                       "peak_tflops_nominal": fp32_peak,
+                                       "frac": flops / (idf_ms * 1e-3) / 1e12 / fp32_peak}
     try:
         if args.no_extras:
             raise RuntimeError("skipped (--no-extras)")
