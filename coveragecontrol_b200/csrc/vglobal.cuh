@@ -154,7 +154,8 @@ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row
   const double cx = cell_centre(row, res);
   const double y_first = cell_centre(0, res), y_last = cell_centre(N - 1, res);
 
-  int v[VG_MAXR];          // envelope: sorted positions of the owners, left to right
+  unsigned char v[VG_MAXR];  // envelope: sorted positions of the owners, left to right (bytes: the stacks live in
+                             // local memory and every resident warp's share of L1 counts)
   double z[VG_MAXR];       // z[m]: boundary between v[m-1] and v[m]
   double zerr[VG_MAXR];    // bound of its rounding error
   bool flagged = false;
@@ -210,8 +211,8 @@ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row
 
   // integer breakpoints: v[m] owns columns [T[m], T[m+1]); a cell centre within the error bound of a
   // boundary flags the row
-  uint32_t iv[VG_MAXR];
-  for (int k = 0; k < R; ++k) iv[k] = 0u;
+  uint32_t *t = a.table + (size_t)e * R * N + row;
+  unsigned long long owned = 0ull;  // sites whose interval has been written (R <= VG_MAXR = 64)
   int lo = 0;
   for (int m = 0; m <= top && !flagged; ++m) {
     int hi = N;
@@ -225,13 +226,16 @@ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row
       if (t >= 0.0 && t < (double)N && fabs(cell_centre((int)t, res) - b) <= berr) flagged = true;
     }
     if (hi < lo) hi = lo;
-    iv[s_ord[v[m]]] = (uint32_t)lo | ((uint32_t)hi << 16);
-    if (hi > lo) atomicMin(&s_rmin[s_ord[v[m]]], row), atomicMax(&s_rmax[s_ord[v[m]]], row + 1);
+    const int site = s_ord[v[m]];
+    t[(size_t)site * N] = (uint32_t)lo | ((uint32_t)hi << 16);
+    owned |= 1ull << site;
+    if (hi > lo) atomicMin(&s_rmin[site], row), atomicMax(&s_rmax[site], row + 1);
     lo = hi;
   }
-  if (flagged) a.flag_list[atomicAdd(a.nflag, 1)] = e * N + row;
-  uint32_t *t = a.table + (size_t)e * R * N + row;
-  for (int k = 0; k < R; ++k) t[(size_t)k * N] = flagged ? 0u : iv[k];
+  // everyone else owns nothing on this row; a flagged row is left to k_vg_fixup entirely
+  if (flagged) a.flag_list[atomicAdd(a.nflag, 1)] = e * N + row, owned = 0ull;
+  for (int k = 0; k < R; ++k)
+    if (!((owned >> k) & 1ull)) t[(size_t)k * N] = 0u;
 }
 
 // ---- reduce ----------------------------------------------------------------------------------------
