@@ -20,6 +20,17 @@ class IOUtils:
             return tomllib.load(f)
 
     @staticmethod
+    def load_yaml(path: str) -> dict:
+        """reference io_utils.py:93-117."""
+        import yaml
+
+        path = IOUtils.sanitize_path(path)
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"IOUtils::load_yaml File not found: {path}")
+        with open(path, "rb") as f:
+            return yaml.load(f, Loader=yaml.FullLoader)
+
+    @staticmethod
     def load_tensor(path: str):
         import torch
 

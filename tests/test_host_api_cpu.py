@@ -166,3 +166,23 @@ def test_import_names_of_the_reference_package():
     assert cc.CudaUtils.UseCuda() in (True, False)
     with pytest.raises(RuntimeError):
         cc.CudaUtils.SetUseCuda(False)  # there is no CPU path to switch to
+
+
+def test_io_utils(tmp_path, monkeypatch):
+    """python/coverage_control/io_utils.py:50-132: sanitize_path, load_toml, load_yaml, load_tensor."""
+    import torch
+
+    from coverage_control import IOUtils
+
+    monkeypatch.setenv("CCB_TEST_DIR", str(tmp_path))
+    assert IOUtils.sanitize_path("$CCB_TEST_DIR/a/../b.toml") == os.path.join(str(tmp_path), "b.toml")
+    (tmp_path / "b.toml").write_text("NumRobots = 5\n[RobotModel]\nSensorSize = 32\n")
+    assert IOUtils.load_toml("$CCB_TEST_DIR/b.toml") == {"NumRobots": 5, "RobotModel": {"SensorSize": 32}}
+    (tmp_path / "c.yaml").write_text("a: 1\nb: [2, 3]\n")
+    assert IOUtils.load_yaml(str(tmp_path / "c.yaml")) == {"a": 1, "b": [2, 3]}
+    t = torch.arange(6, dtype=torch.float32).reshape(2, 3)
+    torch.save(t, tmp_path / "t.pt")
+    assert torch.equal(IOUtils.load_tensor(tmp_path / "t.pt"), t)
+    for fn in (IOUtils.load_toml, IOUtils.load_yaml, IOUtils.load_tensor):
+        with pytest.raises(FileNotFoundError):
+            fn(str(tmp_path / "absent"))
