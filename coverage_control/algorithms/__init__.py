@@ -1,5 +1,5 @@
-"""reference python/coverage_control/algorithms/__init__.py (the four CVT controllers; ControllerNN needs the LPAC network, out of scope)."""
+"""reference python/coverage_control/algorithms/__init__.py."""
 from .._core import CentralizedCVT, ClairvoyantCVT, DecentralizedCVT, NearOptimalCVT
-from .controllers import ControllerCVT
+from .controllers import ControllerCVT, ControllerNN
 
-__all__ = ["NearOptimalCVT", "ClairvoyantCVT", "CentralizedCVT", "DecentralizedCVT", "ControllerCVT"]
+__all__ = ["NearOptimalCVT", "ClairvoyantCVT", "CentralizedCVT", "DecentralizedCVT", "ControllerCVT", "ControllerNN"]

@@ -173,3 +173,49 @@ def test_cnn_input_every_window_alignment(N, fill):
         t, (32, 32), interpolation=torchvision.transforms.InterpolationMode.BILINEAR, antialias=True)
     assert torch.allclose(maps[:, 0], rs(raw_local), rtol=1e-5, atol=1e-8)
     assert torch.allclose(maps[:, 3], rs(raw_obst), rtol=1e-5, atol=1e-8)
+
+
+def _net():
+    import torch
+
+    class Net(torch.nn.Module):
+        """Stand-in for the LPAC network: any function of the graph data with the fields ControllerNN reads."""
+
+        def __init__(self):
+            super().__init__()
+            self.register_buffer("actions_mean", torch.tensor([0.25, -0.5]))
+            self.register_buffer("actions_std", torch.tensor([2.0, 1.5]))
+
+        def forward(self, data):
+            R = data.pos.shape[0]
+            deg = torch.zeros(R, device=data.pos.device).index_add_(0, data.edge_index[0], data.edge_weight)
+            feat = data.x.reshape(R, -1).mean(dim=1)
+            return torch.stack([0.5 - data.pos[:, 0] + 0.1 * deg, 0.5 - data.pos[:, 1] + feat], dim=1)
+
+    return Net()
+
+
+def test_controller_nn_steps_on_the_device():
+    """reference algorithms/controllers.py:91-160: ControllerNN.step with the observation, the graph and the actions left
+    on the GPU against the reference's own sequence (actions.cpu() -> PointVector -> StepActions) on a twin environment."""
+    import torch
+
+    from coverage_control.algorithms import ControllerNN
+
+    cc, orc, p, env, _ = _setup(steps=2)
+    _, _, _, twin, _ = _setup(steps=2)
+    U = cc.CoverageEnvUtils
+    cfg = {"Name": "nn", "UseCNN": True, "UseCommMap": True, "CNNMapSize": 32}
+    ctrl = ControllerNN(cfg, p, env, model=_net())
+    assert ctrl.name == "nn" and next(ctrl.model.buffers()).is_cuda
+    for _ in range(3):
+        obj, converged = ctrl.step(env)
+        data = U.get_torch_geometric_data(twin, p, True, True, 32)
+        with torch.no_grad():
+            a = ctrl.model(data) * ctrl.actions_std + ctrl.actions_mean
+        assert not twin.StepActions(cc.PointVector(a.cpu().numpy()))
+        assert np.array_equal(np.array(env.GetRobotPositions()), np.array(twin.GetRobotPositions()))
+        assert obj == pytest.approx(twin.GetObjectiveValue(), rel=1e-12)
+        assert converged is False
+    with pytest.raises(ImportError):
+        ControllerNN(cfg, p, env)
