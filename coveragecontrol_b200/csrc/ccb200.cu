@@ -1356,6 +1356,78 @@ extern "C" int ccb_selftest_frontier_select(const double *values, int n, int num
   return count;
 }
 
+// Host run of k_vg_partition for one environment: the row sweep is the kernel's own vg_partition_row compiled
+// for the host; the CTA preamble (sort by (py, index), twins, band cull, 1 / (2 dy) table) is restated
+// sequentially with the kernel's expressions, band by band of VG_PART_THREADS rows.  Lets the CPU tests hold the
+// envelope intervals of every unflagged row against the stated rule without a GPU.  Not a compute path: no map
+// is read.  table[R][N] = lo | hi << 16, flag_rows[<= N], span[R][2]; returns the number of flagged rows.
+extern "C" int ccb_selftest_vg_partition(const double *pos, int R, int N, double res, int row0, int row1, uint32_t *table,
+                                         int *flag_rows, int *span) {
+  if (R < 1 || R > VG_MAXR || N < 1 || N >= 65536 || row0 < 0 || row1 > N || row0 > row1 || !(res > 0.0)) return -1;
+  VgArgs a{};
+  a.d.E = 1, a.d.R = R, a.d.N = N, a.d.res = res;
+  a.row0 = row0, a.row1 = row1;
+  a.table = table;
+  int nflag = 0;
+  a.flag_list = flag_rows, a.nflag = &nflag;
+  for (int k = 0; k < R; ++k) span[2 * k] = 0x7fffffff, span[2 * k + 1] = 0;
+  std::vector<int> t_ord(R), s_ord(R), s_rmin(R), s_rmax(R);
+  std::vector<double> t_x(R), t_y(R), s_x(R), s_y(R), s_inv((size_t)R * R);
+  std::vector<unsigned char> keep(R);
+  for (int k = 0; k < R; ++k) {
+    const double yk = pos[2 * k + 1];
+    int rank = 0;
+    for (int j = 0; j < R; ++j) {
+      const double yj = pos[2 * j + 1];
+      rank += (yj < yk || (yj == yk && j < k)) ? 1 : 0;
+    }
+    t_ord[rank] = k, t_x[rank] = pos[2 * k], t_y[rank] = yk;
+  }
+  for (int rlo = row0; rlo < row1; rlo += VG_PART_THREADS) {
+    const int rhi = std::min(rlo + VG_PART_THREADS, row1) - 1;
+    const double cxs[2] = {cell_centre(rlo, res), cell_centre(rhi, res)};
+    const double cys[2] = {cell_centre(0, res), cell_centre(N - 1, res)};
+    for (int q = 0; q < R; ++q) {
+      bool dup = false;
+      for (int p = 0; p < R; ++p) dup = dup || (t_ord[p] < t_ord[q] && t_x[p] == t_x[q] && t_y[p] == t_y[q]);
+      keep[q] = dup ? 0 : 1;
+    }
+    for (int q = 0; q < R; ++q) {
+      double fq[4];
+      for (int c = 0; c < 4; ++c) fq[c] = d2_exact(cxs[c & 1], cys[c >> 1], t_x[q], t_y[q]);
+      for (int p = 0; p < R; ++p) {
+        if (p == q || (t_x[p] == t_x[q] && t_y[p] == t_y[q])) continue;
+        bool all = true;
+        for (int c = 0; c < 4; ++c) {
+          const double fp = d2_exact(cxs[c & 1], cys[c >> 1], t_x[p], t_y[p]);
+          all = all && (fq[c] - fp > 1e-7 * (1.0 + fp));
+        }
+        if (all) {
+          keep[q] = 0;
+          break;
+        }
+      }
+    }
+    int Rs = 0;
+    for (int q = 0; q < R; ++q)
+      if (keep[q]) s_ord[Rs] = t_ord[q], s_x[Rs] = t_x[q], s_y[Rs] = t_y[q], ++Rs;
+    for (int idx = 0; idx < Rs * Rs; ++idx) {
+      const int p = idx / Rs, q = idx - p * Rs;
+      const double dy = s_y[q] - s_y[p];
+      s_inv[idx] = dy > 0.0 ? 1.0 / (2.0 * dy) : 0.0;
+    }
+    for (int k = 0; k < R; ++k) s_rmin[k] = 0x7fffffff, s_rmax[k] = 0;
+    for (int row = rlo; row <= rhi; ++row)
+      vg_partition_row(a, 0, row, Rs, s_ord.data(), s_x.data(), s_y.data(), s_inv.data(), s_rmin.data(), s_rmax.data());
+    for (int k = 0; k < R; ++k)
+      if (s_rmax[k] > s_rmin[k]) {
+        span[2 * k] = std::min(span[2 * k], s_rmin[k]);
+        span[2 * k + 1] = std::max(span[2 * k + 1], s_rmax[k]);
+      }
+  }
+  return nflag;
+}
+
 // coverage_system.h:603-610 GetRobotExplorationFeatures for every robot: E x R x 2 K, host
 extern "C" int ccb_env_exploration_features(ccb_env *env, int num_frontiers, double *out) {
   if (!env->initialised) return fail("environment has no robot positions yet");

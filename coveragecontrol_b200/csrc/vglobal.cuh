@@ -50,8 +50,32 @@ struct VgArgs {
   int *labels;          // optional [E][N*N]
 };
 
-__device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row, int Rs, const int *s_ord, const double *s_x,
-                                                 const double *s_y, const double *s_inv, int *s_rmin, int *s_rmax);
+__host__ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row, int Rs, const int *s_ord,
+                                                          const double *s_x, const double *s_y, const double *s_inv,
+                                                          int *s_rmin, int *s_rmax);
+
+// The row sweep also runs on the host (ccb_selftest_vg_partition, CPU tests): one thread, plain updates there.
+__host__ __device__ __forceinline__ void vg_min(int *p, int v) {
+#ifdef __CUDA_ARCH__
+  atomicMin(p, v);
+#else
+  if (v < *p) *p = v;
+#endif
+}
+__host__ __device__ __forceinline__ void vg_max(int *p, int v) {
+#ifdef __CUDA_ARCH__
+  atomicMax(p, v);
+#else
+  if (v > *p) *p = v;
+#endif
+}
+__host__ __device__ __forceinline__ int vg_next(int *p) {
+#ifdef __CUDA_ARCH__
+  return atomicAdd(p, 1);
+#else
+  return (*p)++;
+#endif
+}
 
 __global__ void k_vg_init_span(int *span, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -146,8 +170,9 @@ __global__ void __launch_bounds__(VG_PART_THREADS) k_vg_partition(VgArgs a) {
 }
 
 // Rs sorted sites survive the band cull (s_ord: their site indices); the table is written for all R
-__device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row, int Rs, const int *s_ord, const double *s_x,
-                                                 const double *s_y, const double *s_inv, int *s_rmin, int *s_rmax) {
+__host__ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row, int Rs, const int *s_ord,
+                                                          const double *s_x, const double *s_y, const double *s_inv,
+                                                          int *s_rmin, int *s_rmax) {
   const EnvDev &d = a.d;
   const int R = d.R, N = d.N;
   const double res = d.res;
@@ -229,11 +254,11 @@ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row
     const int site = s_ord[v[m]];
     t[(size_t)site * N] = (uint32_t)lo | ((uint32_t)hi << 16);
     owned |= 1ull << site;
-    if (hi > lo) atomicMin(&s_rmin[site], row), atomicMax(&s_rmax[site], row + 1);
+    if (hi > lo) vg_min(&s_rmin[site], row), vg_max(&s_rmax[site], row + 1);
     lo = hi;
   }
   // everyone else owns nothing on this row; a flagged row is left to k_vg_fixup entirely
-  if (flagged) a.flag_list[atomicAdd(a.nflag, 1)] = e * N + row, owned = 0ull;
+  if (flagged) a.flag_list[vg_next(a.nflag)] = e * N + row, owned = 0ull;
   for (int k = 0; k < R; ++k)
     if (!((owned >> k) & 1ull)) t[(size_t)k * N] = 0u;
 }

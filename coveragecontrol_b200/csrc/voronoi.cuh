@@ -63,12 +63,25 @@ struct VorArgs {
   int *labels;  // optional [E][N*N] (global mode only): the label of every cell, for parity tests
 };
 
-__device__ __forceinline__ double cell_centre(int i, double res) {
+// (the host bodies serve the CPU self-test of the partition sweep, ccb_selftest_vg_partition: x86-64 without
+// -mfma rounds every operation separately, like the __d*_rn intrinsics)
+__host__ __device__ __forceinline__ double cell_centre(int i, double res) {
+#ifdef __CUDA_ARCH__
   return __dmul_rn(__dadd_rn((double)i, 0.5), res);
+#else
+  volatile double c = (double)i + 0.5;
+  return c * res;
+#endif
 }
-__device__ __forceinline__ double d2_exact(double cx, double cy, double px, double py) {
+__host__ __device__ __forceinline__ double d2_exact(double cx, double cy, double px, double py) {
+#ifdef __CUDA_ARCH__
   double dx = __dsub_rn(cx, px), dy = __dsub_rn(cy, py);
   return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+#else
+  volatile double dx = cx - px, dy = cy - py;
+  volatile double xx = dx * dx, yy = dy * dy;
+  return xx + yy;
+#endif
 }
 
 struct Acc6 {

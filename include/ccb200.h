@@ -182,6 +182,14 @@ int ccb_env_exploration_features(ccb_env *env, int num_frontiers, double *out);
  * compiled for the host) over values[n]; candidate numbers as popped, worst first; returns their count
  * or -1.  Touches no map and no device. */
 int ccb_selftest_frontier_select(const double *values, int n, int num_frontiers, int *order_out);
+/* Test hook, host only: k_vg_partition (the whole-map Voronoi's row partition, replacing voronoi.cpp:55-165
+ * for the global cells) for ONE environment, its row sweep being the kernel's own code compiled for the
+ * host.  pos[R][2] sites, rows [row0, row1) of an N x N map; table[R][N] = lo | hi << 16 (columns [lo, hi)
+ * of the row belong to the site), flag_rows[<= N] = rows left to the per-cell rule, span[R][2] = first row /
+ * last row + 1 on which the site owns a cell.  Returns the number of flagged rows or -1.  Touches no map
+ * and no device. */
+int ccb_selftest_vg_partition(const double *pos, int R, int N, double res, int row0, int row1, uint32_t *table,
+                              int *flag_rows, int *span);
 /* coverage_system.h:557-571 (ratio of explored cells / IDF-weighted): 2 doubles per env */
 int ccb_env_exploration_ratios(ccb_env *env, double *out /* E x 2 */);
 int ccb_env_check_oscillation(ccb_env *env, int e, int robot, int *out); /* coverage_system.h:341-363 */
