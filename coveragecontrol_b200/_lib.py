@@ -104,6 +104,8 @@ SIGNATURES = {
     "ccb_selftest_frontier_select": (C.c_int, [c_double_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "ccb_selftest_vg_partition": (C.c_int, [c_double_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                             C.POINTER(C.c_uint32), c_int_p, c_int_p]),
+    "ccb_selftest_vw_row_interval": (C.c_int, [C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p,
+                                               c_int_p, c_int_p, c_int_p, C.c_int, C.POINTER(C.c_uint32)]),
     "ccb_env_exploration_ratios": (C.c_int, [C.c_void_p, c_double_p]),
     "ccb_env_check_oscillation": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int_p]),
     "ccb_env_sync": (C.c_int, [C.c_void_p]),

@@ -1428,6 +1428,25 @@ extern "C" int ccb_selftest_vg_partition(const double *pos, int R, int N, double
   return nflag;
 }
 
+// Host run of the window kernels' own-cell row interval (vw_row_interval of k_voronoi_window / k_cnn_fused8<VOR>,
+// the same code compiled for the host): px / py = the robot first, then its K neighbours.  For every row of
+// [row0, row1): lo[], hi[] (columns y0 + lo .. y0 + hi - 1) and exact[] = 1 when the kernel applies the per-cell
+// rule inside that interval.  Also returns the kernel's mask words for the interval of the first row through
+// vw_range_bits when words_out is given (9 words from column word `wbase`).  Not a compute path.
+extern "C" int ccb_selftest_vw_row_interval(double res, int row0, int row1, int y0, int ncols, int K, const double *px,
+                                            const double *py, int *lo, int *hi, int *exact, int wbase, uint32_t *words_out) {
+  if (K < 0 || ncols < 0 || row1 < row0 || !(res > 0.0)) return -1;
+  for (int row = row0; row < row1; ++row) {
+    int l = 0, h = ncols;
+    bool ex = false;
+    if (K > 0) ex = vw_row_interval(res, row, y0, ncols, K, px, py, l, h);
+    lo[row - row0] = l, hi[row - row0] = h > l ? h : l, exact[row - row0] = ex ? 1 : 0;
+  }
+  if (words_out && row1 > row0)
+    for (int j = 0; j < VW_WORDS; ++j) words_out[j] = vw_range_bits(y0 + lo[0], y0 + hi[0], (wbase + j) << 5);
+  return 0;
+}
+
 // coverage_system.h:603-610 GetRobotExplorationFeatures for every robot: E x R x 2 K, host
 extern "C" int ccb_env_exploration_features(ccb_env *env, int num_frontiers, double *out) {
   if (!env->initialised) return fail("environment has no robot positions yet");

@@ -48,15 +48,16 @@ struct VwShared {
 __host__ __device__ inline size_t vw_smem_bytes(int R) { return sizeof(VwShared) + sizeof(double) * 2 * (size_t)R; }
 
 // 1 if neighbour (kx, ky) is strictly nearer to cell (row, col) than the robot (sx, sy)
-__device__ __forceinline__ bool vw_beats(double res, int row, int col, double kx, double ky, double sx, double sy) {
+// (vw_beats / vw_row_interval / vw_range_bits also compile for the host: ccb_selftest_vw_row_interval, CPU tests)
+__host__ __device__ __forceinline__ bool vw_beats(double res, int row, int col, double kx, double ky, double sx, double sy) {
   const double cx = cell_centre(row, res), cy = cell_centre(col, res);
   return d2_exact(cx, cy, kx, ky) < d2_exact(cx, cy, sx, sy);
 }
 
 // own-cell interval of one window row (columns y0 + lo .. y0 + hi - 1); returns true when the row needs
 // the per-cell rule (then [lo, hi) only holds the unambiguous constraints)
-__device__ __noinline__ bool vw_row_interval(double res, int row, int y0, int ncols, int K, const double *px, const double *py,
-                                             int &lo_out, int &hi_out) {
+__host__ __device__ __noinline__ bool vw_row_interval(double res, int row, int y0, int ncols, int K, const double *px,
+                                                      const double *py, int &lo_out, int &hi_out) {
   const double cx = cell_centre(row, res), cy0 = cell_centre(y0, res);
   const double sx = px[0], sy = py[0];
   const double f0 = d2_exact(cx, cy0, sx, sy);
@@ -93,7 +94,7 @@ __device__ __noinline__ bool vw_row_interval(double res, int row, int y0, int nc
 }
 
 // bits [a, b) of a 32-bit word whose bit 0 is column cb
-__device__ __forceinline__ uint32_t vw_range_bits(int a, int b, int cb) {
+__host__ __device__ __forceinline__ uint32_t vw_range_bits(int a, int b, int cb) {
   const int lo = min(max(a - cb, 0), 32), hi = min(max(b - cb, 0), 32);
   if (hi <= lo) return 0u;
   return ((hi - lo >= 32) ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) << lo;

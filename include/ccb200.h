@@ -190,6 +190,14 @@ int ccb_selftest_frontier_select(const double *values, int n, int num_frontiers,
  * and no device. */
 int ccb_selftest_vg_partition(const double *pos, int R, int N, double res, int row0, int row1, uint32_t *table,
                               int *flag_rows, int *span);
+/* Test hook, host only: the own-cell column interval of window rows [row0, row1) as the DecentralizedCVT
+ * window kernels compute it (replacing voronoi.cpp:55-150 for decentralized_cvt.h:85-143), their own code
+ * compiled for the host.  px / py[K + 1]: the robot, then its K neighbours; window columns y0 .. y0 + ncols - 1.
+ * lo / hi / exact[row1 - row0]; exact = the kernel applies the per-cell rule inside [lo, hi) on that row.
+ * words_out (optional, 9 words): the first row's interval as mask words from column word wbase.
+ * Touches no map and no device. */
+int ccb_selftest_vw_row_interval(double res, int row0, int row1, int y0, int ncols, int K, const double *px,
+                                 const double *py, int *lo, int *hi, int *exact, int wbase, uint32_t *words_out);
 /* coverage_system.h:557-571 (ratio of explored cells / IDF-weighted): 2 doubles per env */
 int ccb_env_exploration_ratios(ccb_env *env, double *out /* E x 2 */);
 int ccb_env_check_oscillation(ccb_env *env, int e, int robot, int *out); /* coverage_system.h:341-363 */
