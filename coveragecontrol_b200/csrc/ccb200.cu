@@ -162,6 +162,8 @@ extern "C" ccb_idf *ccb_idf_create(const ccb_params *p, int device, void *stream
       cudaMalloc(&idf->d_max, sizeof(int)) != cudaSuccess ||
       cudaMalloc(&idf->d_factor, sizeof(float)) != cudaSuccess) {
     fail("cudaMalloc failed (WorldIDF map)");
+    cudaGetLastError();
+    ccb_idf_destroy(idf.release());  // frees whatever was allocated before the failure
     return nullptr;
   }
   cudaMemsetAsync(idf->d_map, 0, nn * sizeof(float), idf->stream);
