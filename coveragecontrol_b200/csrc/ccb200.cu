@@ -1358,6 +1358,13 @@ extern "C" int ccb_selftest_frontier_select(const double *values, int n, int num
   return count;
 }
 
+// Host run of make_window (common.cuh; map_utils.h:51-87 as every window kernel uses it): out6 = ox, oy, x0, x1, y0, y1
+extern "C" int ccb_selftest_make_window(double res, double px, double py, int sub, int map_size, int *out6) {
+  const Window w = make_window(res, px, py, sub, map_size);
+  out6[0] = w.ox, out6[1] = w.oy, out6[2] = w.x0, out6[3] = w.x1, out6[4] = w.y0, out6[5] = w.y1;
+  return 0;
+}
+
 // Host run of k_vg_partition for one environment: the row sweep is the kernel's own vg_partition_row compiled
 // for the host; the CTA preamble (sort by (py, index), twins, band cull, 1 / (2 dy) table) is restated
 // sequentially with the kernel's expressions, band by band of VG_PART_THREADS rows.  Lets the CPU tests hold the

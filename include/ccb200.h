@@ -182,6 +182,9 @@ int ccb_env_exploration_features(ccb_env *env, int num_frontiers, double *out);
  * compiled for the host) over values[n]; candidate numbers as popped, worst first; returns their count
  * or -1.  Touches no map and no device. */
 int ccb_selftest_frontier_select(const double *values, int n, int num_frontiers, int *order_out);
+/* Test hook, host only: the window of size `sub` around a position as every window kernel derives it
+ * (map_utils.h:51-87 ComputeOffsets): out6 = unclipped origin (ox, oy), clipped rows [x0, x1), columns [y0, y1). */
+int ccb_selftest_make_window(double res, double px, double py, int sub, int map_size, int *out6);
 /* Test hook, host only: k_vg_partition (the whole-map Voronoi's row partition, replacing voronoi.cpp:55-165
  * for the global cells) for ONE environment, its row sweep being the kernel's own code compiled for the
  * host.  pos[R][2] sites, rows [row0, row1) of an N x N map; table[R][N] = lo | hi << 16 (columns [lo, hi)

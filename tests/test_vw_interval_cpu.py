@@ -160,3 +160,33 @@ def test_interval_mask_words():
         bits[max(a, 0):max(b, 0)] = True
         got = ((words[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).astype(bool).reshape(-1)
         assert np.array_equal(got, bits)
+
+
+def test_make_window_matches_the_oracle_offsets():
+    """common.cuh make_window (host run) against the oracle's ComputeOffsets (map_utils.h:51-87): half-way
+    positions round away from zero, windows clipped on every side, windows that miss the map"""
+    from coveragecontrol_b200 import _lib
+    from oracle import oracle as orc
+
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    out = np.zeros(6, np.int32)
+    cases = [(1.0, 10.5, 11.5, 64, 1024), (1.0, 0.5, 1023.5, 64, 1024), (0.5, 3.25, 3.75, 8, 64), (1.0, 1e-4, 1023.9999, 256, 1024),
+             (2.0, 31.0, 33.0, 16, 32), (1.0, 2.5, 3.5, 7, 50)]
+    for _ in range(2000):
+        res = float(rng.choice([1.0, 0.5, 2.0, 0.3]))
+        n = int(rng.integers(8, 300))
+        sub = int(rng.integers(1, 2 * n))
+        p = rng.uniform(-0.2 * n * res, 1.2 * n * res, 2)
+        if rng.random() < 0.3:
+            p = (np.round(p / res) + 0.5) * res
+        cases.append((res, float(p[0]), float(p[1]), sub, n))
+    for res, px, py, sub, n in cases:
+        assert lib.ccb_selftest_make_window(res, px, py, sub, n, out.ctypes.data_as(C.POINTER(C.c_int))) == 0
+        ix, of = orc.compute_offsets(res, px, py, sub, n)
+        assert (out[0], out[1]) == (ix.left, ix.bottom)
+        x0, x1 = ix.left + of.left, ix.right + of.right
+        y0, y1 = ix.bottom + of.bottom, ix.top + of.top
+        # a window that misses the map has a negative extent in the reference and an empty one here
+        assert (out[2], out[4]) == (x0, y0)
+        assert out[3] == max(x1, x0) and out[5] == max(y1, y0)
