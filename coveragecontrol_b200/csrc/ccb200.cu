@@ -450,6 +450,8 @@ struct ccb_env {
   int vg_mode = -1;             // CCB_VG_GENERIC: 1 forces the tile-ordered kernel, 0 the site-ordered one (tests)
   bool vw_generic = false;      // CCB_VW_GENERIC: force the generic window kernel (tests)
   bool band_mode = false;       // this env holds one row band of a world tiled over several GPUs
+  bool vg_prefix = false;       // CCB_VG_PREFIX=1 (opt-in): keep row prefix sums of the world maps (vglobal.cuh k_vg_prefix)
+  VgPfx *d_vg_pfx = nullptr;    // [E][N][N] x 32 B, rebuilt for an environment whenever its world map is set
 };
 
 // kernels that need more than 48 KB of dynamic shared memory: raise the limit once per (device, kernel)
@@ -553,7 +555,12 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
     dim3 rgrid(std::max(1, (max_ctas + env->vg_griddiv - 1) / env->vg_griddiv), d.E), fgrid(148 * 2);
     if (stages & 2) {
       const int nt = env->vg_warps * 32;
-      if (src == SRC_WORLD) {
+      if (src == SRC_WORLD && !labels && env->d_vg_pfx) {
+        // opt-in: two prefix look-ups per (site, row) instead of streaming the interval; a warp takes 32 rows
+        // of a site, so an eighth of the reduce grid already gives every item its own warp
+        dim3 lgrid(std::max(1, (chunks * d.R + VG_RED_WARPS - 1) / VG_RED_WARPS / 2), d.E);
+        k_vg_lookup<<<lgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g, env->d_vg_pfx);
+      } else if (src == SRC_WORLD) {
         if (labels) k_vg_reduce<SRC_WORLD, true><<<rgrid, nt, 0, env->stream>>>(g);
         else k_vg_reduce<SRC_WORLD, false, VG_U, VG_RED_MINB, 4><<<rgrid, nt, 0, env->stream>>>(g);  // 8 rows x 16 columns per pass
       } else {
@@ -685,6 +692,14 @@ static int env_alloc(ccb_env *env) {
     CCB_CUDA(cudaEventCreateWithFlags(&env->ev_stage[k], cudaEventDisableTiming));
   }
   CCB_CUDA(cudaMemsetAsync(d.world, 0, sizeof(float) * (nn * d.E + (size_t)VOR_PAD_ROWS * d.N), env->stream));
+  if (env->vg_prefix && d.R <= VG_MAXR && (d.N & 3) == 0 && d.N < 65536) {
+    // asked for explicitly: failing to get the memory is an error, not a silent change of path
+    if (cudaMalloc(&env->d_vg_pfx, sizeof(VgPfx) * nn * d.E) != cudaSuccess) {
+      cudaGetLastError();
+      return fail("CCB_VG_PREFIX=1: cudaMalloc of the row prefix sums failed (32 bytes per map cell and environment)");
+    }
+    CCB_CUDA(cudaMemsetAsync(env->d_vg_pfx, 0, sizeof(VgPfx) * nn * d.E, env->stream));  // prefixes of the zero map
+  }
   CCB_CUDA(cudaMemsetAsync(d.seenb, 0, sizeof(uint32_t) * pw * er, env->stream));
   if (d.xseenb) CCB_CUDA(cudaMemsetAsync(d.xseenb, 0, sizeof(uint32_t) * pw * er, env->stream));
   CCB_CUDA(cudaMemsetAsync(d.sysb, 0, sizeof(uint32_t) * pw * 2 * d.E, env->stream));
@@ -738,6 +753,7 @@ extern "C" ccb_env *ccb_env_create(const ccb_params *p, int num_envs, int num_ro
   if (const char *s = getenv("CCB_VG_GENERIC")) env->vg_mode = atoi(s) != 0 ? 1 : 0;
   if (const char *s = getenv("CCB_VG_WARPS")) env->vg_warps = std::min(std::max(atoi(s), 1), VG_RED_WARPS);
   if (const char *s = getenv("CCB_VG_GRIDDIV")) env->vg_griddiv = std::max(atoi(s), 1);
+  if (const char *s = getenv("CCB_VG_PREFIX")) env->vg_prefix = atoi(s) != 0;
   if (const char *s = getenv("CCB_NO_AUX")) env->no_aux = atoi(s) != 0;
   if (const char *s = getenv("CCB_NO_GRAPH")) env->no_graph = atoi(s) != 0;
   if (const char *s = getenv("CCB_NO_WFUSE")) env->no_wfuse = atoi(s) != 0;
@@ -768,6 +784,7 @@ extern "C" void ccb_env_destroy(ccb_env *env) {
   cudaFree(env->d_objective), cudaFree(env->d_stage), cudaFree(env->d_feat), cudaFree(env->d_ratio);
   cudaFree(env->d_scratch);
   cudaFree(env->d_vg_table), cudaFree(env->d_vg_flag), cudaFree(env->d_vg_span), cudaFree(env->d_vg_items), cudaFree(env->d_xfeat);
+  cudaFree(env->d_vg_pfx);
   cudaFreeHost(env->h_pin);
   for (int k = 0; k < 2; ++k) {
     cudaFreeHost(env->h_stage[k]);
@@ -782,6 +799,16 @@ extern "C" int ccb_env_num_envs(const ccb_env *env) { return env->E; }
 extern "C" int ccb_env_num_robots(const ccb_env *env) { return env->R; }
 extern "C" const float *ccb_env_world_dev(const ccb_env *env) { return env->d.world; }
 extern "C" const double *ccb_env_positions_dev(const ccb_env *env) { return env->d.pos_g; }
+
+// the world map of environment e was just written on env->stream: refresh its row prefix sums (opt-in path)
+static int world_changed(ccb_env *env, int e) {
+  if (!env->d_vg_pfx) return 0;
+  const EnvDev &d = env->d;
+  const size_t nn = cell_count(d);
+  k_vg_prefix<<<(d.N + 7) / 8, 256, 0, env->stream>>>(d.world + nn * e, env->d_vg_pfx + nn * e, d.N, (long)d.N);
+  CCB_LAUNCH_CHECK();
+  return 0;
+}
 
 static int check_env_index(const ccb_env *env, int e) {
   if (e < 0 || e >= env->E) return fail("environment index out of range");
@@ -798,6 +825,7 @@ extern "C" int ccb_env_set_world_dev(ccb_env *env, int e, const float *map_dev) 
   if (join_aux(env)) return 1;
   size_t nn = cell_count(env->d);
   CCB_CUDA(cudaMemcpyAsync(env->d.world + nn * e, map_dev, nn * sizeof(float), cudaMemcpyDeviceToDevice, env->stream));
+  if (world_changed(env, e)) return 1;
   if (state_changed(env)) return 1;
   return 0;
 }
@@ -813,6 +841,7 @@ extern "C" int ccb_env_set_world_host(ccb_env *env, int e, const float *map) {
   size_t nn = cell_count(env->d);
   CCB_CUDA(cudaMemcpyAsync(env->d.world + nn * e, map, nn * sizeof(float), cudaMemcpyHostToDevice, env->stream));
   CCB_CUDA(cudaStreamSynchronize(env->stream));
+  if (world_changed(env, e)) return 1;
   if (state_changed(env)) return 1;
   return 0;
 }

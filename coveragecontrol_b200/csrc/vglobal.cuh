@@ -431,6 +431,95 @@ __global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a)
   }
 }
 
+// ---- opt-in (CCB_VG_PREFIX=1): row prefix sums instead of streaming the map ---------------------------
+// The world map of an environment never changes while its robots move, and a site's cells on a row are ONE
+// interval: with the inclusive row prefix sums of (v, y v, y^2 v) (y = col + 0.5, fp64) kept next to the map,
+// a (site, row) pair costs two 32-byte look-ups instead of streaming the interval -- ~0.4 MB instead of 4 MB per
+// 1024^2 environment and pass -- at 32 B of HBM per map cell (34 GB for 1024 environments of 1024^2; the part
+// has 180 GB).  The sums are differences of fp64 prefixes instead of exact sums of the interval's cells:
+// |error| <= ~N ulp of the row's prefix (observed relative differences ~1e-15, the gate is 1e-4); a run of
+// zero cells still sums to exactly 0 (equal prefixes), so the mass < 1e-10 fallback (voronoi.cpp:143-150) is
+// taken on the same cells.  Only for the world map (SRC_WORLD, no labels): the explored and robot maps change
+// with every step.  NOT the default: to be measured and gated on a GPU first.
+struct __align__(32) VgPfx {
+  double s, sy, syy, pad;
+};
+
+// one warp per map row: inclusive scan over the columns, 32 at a time
+__global__ void __launch_bounds__(256) k_vg_prefix(const float *__restrict__ world, VgPfx *__restrict__ pfx, int N, long rows) {
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float *src = world + (size_t)row * N;
+  VgPfx *dst = pfx + (size_t)row * N;
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0;  // carry: the sums of the columns before this group of 32
+  for (int cb = 0; cb < N; cb += 32) {
+    const int col = cb + lane;
+    const double v = col < N ? (double)__ldg(src + col) : 0.0;
+    const double y = (double)col + 0.5;
+    double a0 = v, a1 = y * v, a2 = (y * y) * v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double u0 = __shfl_up_sync(0xffffffffu, a0, o), u1 = __shfl_up_sync(0xffffffffu, a1, o),
+                   u2 = __shfl_up_sync(0xffffffffu, a2, o);
+      if (lane >= o) a0 += u0, a1 += u1, a2 += u2;
+    }
+    a0 += c0, a1 += c1, a2 += c2;
+    if (col < N) {
+      VgPfx out;
+      out.s = a0, out.sy = a1, out.syy = a2, out.pad = 0.0;
+      dst[col] = out;
+    }
+    c0 = __shfl_sync(0xffffffffu, a0, 31), c1 = __shfl_sync(0xffffffffu, a1, 31), c2 = __shfl_sync(0xffffffffu, a2, 31);
+  }
+}
+
+__device__ __forceinline__ void vg_pfx_load(const VgPfx *p, double &s, double &sy, double &syy) {
+  const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+  s = a.x, sy = a.y, syy = b.x;
+}
+
+// one warp per (site, 32-row chunk) item as k_vg_reduce, lane <-> row: two look-ups per row with cells
+__global__ void __launch_bounds__(VG_RED_WARPS * 32) k_vg_lookup(VgArgs a, const VgPfx *__restrict__ pfx_all) {
+  const EnvDev &d = a.d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.y;
+  const int N = d.N, R = d.R;
+  const int *its = a.items + (size_t)e * (R + 1);
+  const int total = __ldg(its + R);
+  const VgPfx *pfx = pfx_all + (size_t)e * N * N;
+#pragma unroll 1
+  for (int item = blockIdx.x * (blockDim.x >> 5) + warp; item < total; item += gridDim.x * (blockDim.x >> 5)) {
+    int k;
+    {
+      const int end0 = lane < R ? __ldg(its + lane + 1) : 0x7fffffff;
+      unsigned hit = __ballot_sync(0xffffffffu, item < end0);
+      if (hit) {
+        k = __ffs(hit) - 1;
+      } else {
+        const int end1 = lane + 32 < R ? __ldg(its + lane + 33) : 0x7fffffff;
+        hit = __ballot_sync(0xffffffffu, item < end1);
+        k = 32 + __ffs(hit) - 1;
+      }
+    }
+    const int chunk = (__ldg(a.span + ((size_t)e * R + k) * 2) - a.row0) / VG_CHUNK + (item - __ldg(its + k));
+    const int row = a.row0 + chunk * VG_CHUNK + lane;
+    const uint32_t iv = row < a.row1 ? __ldg(a.table + ((size_t)e * R + k) * N + row) : 0u;
+    const int lo = (int)(iv & 0xffffu), hi = (int)(iv >> 16);
+    double rs = 0.0, rsy = 0.0, rsyy = 0.0;
+    if (hi > lo) {
+      const VgPfx *prow = pfx + (size_t)row * N;
+      double h0, h1, h2, l0 = 0.0, l1 = 0.0, l2 = 0.0;
+      vg_pfx_load(prow + hi - 1, h0, h1, h2);
+      if (lo > 0) vg_pfx_load(prow + lo - 1, l0, l1, l2);
+      rs = h0 - l0, rsy = h1 - l1, rsyy = h2 - l2;
+    }
+    const double x = (double)row + 0.5;
+    const Sum4 tot = reduce4(rs, x * rs, rsy, fma(x * x, rs, rsyy));
+    if (lane == 0) emit(a.sums, e, d.R, k, tot.m, tot.sx, tot.sy, tot.s2);
+  }
+}
+
 // ---- flagged rows: the stated rule per cell --------------------------------------------------------
 // items = flagged (environment, row) pairs listed by k_vg_partition, each split in 256-column pieces;
 // a fixed grid strides over them.  One cell per thread per piece: 32 x R exact distances per warp.
