@@ -450,6 +450,7 @@ struct ccb_env {
   int vg_mode = -1;             // CCB_VG_GENERIC: 1 forces the tile-ordered kernel, 0 the site-ordered one (tests)
   bool vw_generic = false;      // CCB_VW_GENERIC: force the generic window kernel (tests)
   bool band_mode = false;       // this env holds one row band of a world tiled over several GPUs
+  int vg_part_rpt = 1;          // CCB_VG_PART_RPT (opt-in, 1 / 2 / 4): rows per thread of k_vg_partition
   bool vg_prefix = false;       // CCB_VG_PREFIX=1 (opt-in): keep row prefix sums of the world maps (vglobal.cuh k_vg_prefix)
   VgPfx *d_vg_pfx = nullptr;    // [E][N][N] x 32 B, rebuilt for an environment whenever its world map is set
 };
@@ -542,8 +543,12 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
     g.items = env->d_vg_items;
     const int rows = row1 - row0;
     if (stages & 1) {
-      k_vg_partition<<<dim3((rows + VG_PART_THREADS - 1) / VG_PART_THREADS, d.E), VG_PART_THREADS,
-                       sizeof(double) * d.R * d.R, env->stream>>>(g);
+      const int rpt = env->vg_part_rpt, band = rpt * VG_PART_THREADS;
+      const dim3 pgrid((rows + band - 1) / band, d.E);
+      const size_t psmem = sizeof(double) * d.R * d.R;
+      if (rpt == 2) k_vg_partition<2><<<pgrid, VG_PART_THREADS, psmem, env->stream>>>(g);
+      else if (rpt == 4) k_vg_partition<4><<<pgrid, VG_PART_THREADS, psmem, env->stream>>>(g);
+      else k_vg_partition<1><<<pgrid, VG_PART_THREADS, psmem, env->stream>>>(g);
       CCB_LAUNCH_CHECK();
       k_vg_items<<<(d.E + 3) / 4, 128, 0, env->stream>>>(env->d_vg_span, env->d_vg_items, d.E, d.R, row0);
       CCB_LAUNCH_CHECK();
@@ -754,6 +759,10 @@ extern "C" ccb_env *ccb_env_create(const ccb_params *p, int num_envs, int num_ro
   if (const char *s = getenv("CCB_VG_WARPS")) env->vg_warps = std::min(std::max(atoi(s), 1), VG_RED_WARPS);
   if (const char *s = getenv("CCB_VG_GRIDDIV")) env->vg_griddiv = std::max(atoi(s), 1);
   if (const char *s = getenv("CCB_VG_PREFIX")) env->vg_prefix = atoi(s) != 0;
+  if (const char *s = getenv("CCB_VG_PART_RPT")) {
+    const int v = atoi(s);
+    env->vg_part_rpt = (v == 2 || v == 4) ? v : 1;
+  }
   if (const char *s = getenv("CCB_NO_AUX")) env->no_aux = atoi(s) != 0;
   if (const char *s = getenv("CCB_NO_GRAPH")) env->no_graph = atoi(s) != 0;
   if (const char *s = getenv("CCB_NO_WFUSE")) env->no_wfuse = atoi(s) != 0;
@@ -1399,8 +1408,9 @@ extern "C" int ccb_selftest_make_window(double res, double px, double py, int su
 // sequentially with the kernel's expressions, band by band of VG_PART_THREADS rows.  Lets the CPU tests hold the
 // envelope intervals of every unflagged row against the stated rule without a GPU.  Not a compute path: no map
 // is read.  table[R][N] = lo | hi << 16, flag_rows[<= N], span[R][2]; returns the number of flagged rows.
-extern "C" int ccb_selftest_vg_partition(const double *pos, int R, int N, double res, int row0, int row1, uint32_t *table,
-                                         int *flag_rows, int *span) {
+extern "C" int ccb_selftest_vg_partition(const double *pos, int R, int N, double res, int row0, int row1, int band_rows,
+                                         uint32_t *table, int *flag_rows, int *span) {
+  if (band_rows <= 0) band_rows = VG_PART_THREADS;  // rows per CTA band: VG_PART_THREADS x CCB_VG_PART_RPT
   if (R < 1 || R > VG_MAXR || N < 1 || N >= 65536 || row0 < 0 || row1 > N || row0 > row1 || !(res > 0.0)) return -1;
   VgArgs a{};
   a.d.E = 1, a.d.R = R, a.d.N = N, a.d.res = res;
@@ -1421,8 +1431,8 @@ extern "C" int ccb_selftest_vg_partition(const double *pos, int R, int N, double
     }
     t_ord[rank] = k, t_x[rank] = pos[2 * k], t_y[rank] = yk;
   }
-  for (int rlo = row0; rlo < row1; rlo += VG_PART_THREADS) {
-    const int rhi = std::min(rlo + VG_PART_THREADS, row1) - 1;
+  for (int rlo = row0; rlo < row1; rlo += band_rows) {
+    const int rhi = std::min(rlo + band_rows, row1) - 1;
     const double cxs[2] = {cell_centre(rlo, res), cell_centre(rhi, res)};
     const double cys[2] = {cell_centre(0, res), cell_centre(N - 1, res)};
     for (int q = 0; q < R; ++q) {

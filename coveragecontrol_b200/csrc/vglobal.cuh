@@ -82,6 +82,9 @@ __global__ void k_vg_init_span(int *span, int n) {
   if (i < n) span[2 * i] = 0x7fffffff, span[2 * i + 1] = 0;
 }
 
+// RPT rows per thread: a CTA's band is RPT * VG_PART_THREADS rows (RPT > 1, opt-in through CCB_VG_PART_RPT: the
+// sort / twin / cull / 1 / (2 dy) preamble is paid once per band, against a taller band culling fewer sites)
+template <int RPT = 1>
 __global__ void __launch_bounds__(VG_PART_THREADS) k_vg_partition(VgArgs a) {
   __shared__ int s_ord[VG_MAXR];
   __shared__ double s_x[VG_MAXR], s_y[VG_MAXR];
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(VG_PART_THREADS) k_vg_partition(VgArgs a) {
   // below run over the ~10 sites whose cells reach the band instead of all R.
   {
     const double res = d.res;
-    const int rlo = a.row0 + blockIdx.x * VG_PART_THREADS, rhi = min(rlo + VG_PART_THREADS, a.row1) - 1;
+    const int rlo = a.row0 + blockIdx.x * (RPT * VG_PART_THREADS), rhi = min(rlo + RPT * VG_PART_THREADS, a.row1) - 1;
     const double cxs[2] = {cell_centre(rlo, res), cell_centre(rhi, res)};
     const double cys[2] = {cell_centre(0, res), cell_centre(N - 1, res)};
     // thread (q, part): site q against every parts-th site p
@@ -158,8 +161,16 @@ __global__ void __launch_bounds__(VG_PART_THREADS) k_vg_partition(VgArgs a) {
     s_inv[idx] = dy > 0.0 ? 1.0 / (2.0 * dy) : 0.0;
   }
   __syncthreads();
-  const int row = a.row0 + blockIdx.x * VG_PART_THREADS + tid;
-  if (row < a.row1) vg_partition_row(a, e, row, Rs, s_ord, s_x, s_y, s_inv, s_rmin, s_rmax);
+  if (RPT == 1) {
+    const int row = a.row0 + blockIdx.x * VG_PART_THREADS + tid;
+    if (row < a.row1) vg_partition_row(a, e, row, Rs, s_ord, s_x, s_y, s_inv, s_rmin, s_rmax);
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < RPT; ++i) {
+      const int row = a.row0 + blockIdx.x * (RPT * VG_PART_THREADS) + i * VG_PART_THREADS + tid;
+      if (row < a.row1) vg_partition_row(a, e, row, Rs, s_ord, s_x, s_y, s_inv, s_rmin, s_rmax);
+    }
+  }
   __syncthreads();
   // the CTA's rows extend every site's row span
   for (int k = tid; k < R; k += VG_PART_THREADS)

@@ -189,10 +189,10 @@ int ccb_selftest_make_window(double res, double px, double py, int sub, int map_
  * for the global cells) for ONE environment, its row sweep being the kernel's own code compiled for the
  * host.  pos[R][2] sites, rows [row0, row1) of an N x N map; table[R][N] = lo | hi << 16 (columns [lo, hi)
  * of the row belong to the site), flag_rows[<= N] = rows left to the per-cell rule, span[R][2] = first row /
- * last row + 1 on which the site owns a cell.  Returns the number of flagged rows or -1.  Touches no map
+ * last row + 1 on which the site owns a cell; band_rows = rows per CTA band (0: the kernel's default, 128).  Returns the number of flagged rows or -1.  Touches no map
  * and no device. */
-int ccb_selftest_vg_partition(const double *pos, int R, int N, double res, int row0, int row1, uint32_t *table,
-                              int *flag_rows, int *span);
+int ccb_selftest_vg_partition(const double *pos, int R, int N, double res, int row0, int row1, int band_rows,
+                              uint32_t *table, int *flag_rows, int *span);
 /* Test hook, host only: the own-cell column interval of window rows [row0, row1) as the DecentralizedCVT
  * window kernels compute it (replacing voronoi.cpp:55-150 for decentralized_cvt.h:85-143), their own code
  * compiled for the host.  px / py[K + 1]: the robot, then its K neighbours; window columns y0 .. y0 + ncols - 1.

@@ -11,6 +11,9 @@ import numpy as np
 import pytest
 
 
+BAND_ROWS = 0  # rows per CTA band of the emulated kernel (0: the default, 128; 256 / 512 = CCB_VG_PART_RPT 2 / 4)
+
+
 def _partition(pos, N, res=1.0, row0=0, row1=None):
     from coveragecontrol_b200 import _lib
 
@@ -21,7 +24,7 @@ def _partition(pos, N, res=1.0, row0=0, row1=None):
     table = np.full((R, N), 0xFFFFFFFF, np.uint32)
     flags = np.full(N, -1, np.int32)
     span = np.zeros((R, 2), np.int32)
-    n = lib.ccb_selftest_vg_partition(pos.ctypes.data_as(C.POINTER(C.c_double)), R, N, float(res), row0, row1,
+    n = lib.ccb_selftest_vg_partition(pos.ctypes.data_as(C.POINTER(C.c_double)), R, N, float(res), row0, row1, BAND_ROWS,
                                       table.ctypes.data_as(C.POINTER(C.c_uint32)),
                                       flags.ctypes.data_as(C.POINTER(C.c_int)), span.ctypes.data_as(C.POINTER(C.c_int)))
     assert n >= 0
@@ -208,6 +211,22 @@ def test_rejects_bad_arguments():
     s = np.zeros((65, 2), np.int32)
     args = (t.ctypes.data_as(C.POINTER(C.c_uint32)), f.ctypes.data_as(C.POINTER(C.c_int)), s.ctypes.data_as(C.POINTER(C.c_int)))
     dp = pos.ctypes.data_as(C.POINTER(C.c_double))
-    assert lib.ccb_selftest_vg_partition(dp, 65, 8, 1.0, 0, 8, *args) == -1   # more sites than VG_MAXR
-    assert lib.ccb_selftest_vg_partition(dp, 4, 8, 1.0, 0, 9, *args) == -1    # band beyond the map
-    assert lib.ccb_selftest_vg_partition(dp, 4, 8, 0.0, 0, 8, *args) == -1    # resolution
+    assert lib.ccb_selftest_vg_partition(dp, 65, 8, 1.0, 0, 8, 0, *args) == -1   # more sites than VG_MAXR
+    assert lib.ccb_selftest_vg_partition(dp, 4, 8, 1.0, 0, 9, 0, *args) == -1    # band beyond the map
+    assert lib.ccb_selftest_vg_partition(dp, 4, 8, 0.0, 0, 8, 0, *args) == -1    # resolution
+
+
+@pytest.mark.parametrize("band_rows", [256, 512])
+def test_taller_cta_bands(monkeypatch, band_rows):
+    """CCB_VG_PART_RPT = 2 / 4 (opt-in): a CTA's band is 256 / 512 rows, so the band cull keeps more sites; the
+    intervals of unflagged rows must not change"""
+    import sys
+
+    monkeypatch.setattr(sys.modules[__name__], "BAND_ROWS", band_rows)
+    rng = np.random.default_rng(50 + band_rows)
+    for N, R in ((1024, 32), (640, 64), (300, 9)):
+        pos = rng.uniform(0, N, (R, 2))
+        _check(pos, N)
+        _check(pos, N, row0=100, row1=N - 7)
+    g = np.arange(8, 128, 16, dtype=np.float64) + 0.5
+    _check(np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2), 128)
