@@ -561,8 +561,8 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
     if (stages & 2) {
       const int nt = env->vg_warps * 32;
       if (src == SRC_WORLD && !labels && env->d_vg_pfx) {
-        // opt-in: two prefix look-ups per (site, row) instead of streaming the interval; a warp takes 32 rows
-        // of a site, so an eighth of the reduce grid already gives every item its own warp
+        // opt-in: two prefix look-ups per (site, row) instead of streaming the interval; an item is one pass of a
+        // warp, so warps for half of the largest possible item count (the rest is reached by striding)
         dim3 lgrid(std::max(1, (chunks * d.R + VG_RED_WARPS - 1) / VG_RED_WARPS / 2), d.E);
         k_vg_lookup<<<lgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g, env->d_vg_pfx);
       } else if (src == SRC_WORLD) {
