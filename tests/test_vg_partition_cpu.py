@@ -230,3 +230,38 @@ def test_taller_cta_bands(monkeypatch, band_rows):
         _check(pos, N, row0=100, row1=N - 7)
     g = np.arange(8, 128, 16, dtype=np.float64) + 0.5
     _check(np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2), 128)
+
+
+def test_row_prefix_moments_from_the_partition_table():
+    """what k_vg_lookup (opt-in CCB_VG_PREFIX=1) computes, restated in NumPy on the host partition table: per
+    (site, row) the difference of inclusive fp64 row prefix sums of (v, y v, y^2 v).  Against the direct per-cell
+    sums of the stated rule's labels on the unflagged rows: mass, centroid and sum |c - p|^2 v agree to ~1e-12
+    (the gate of SURVEY 8d is 1e-4), and sites on an all-zero half of the map get exactly 0."""
+    rng = np.random.default_rng(60)
+    N, R = 512, 24
+    pos = rng.uniform(0, N, (R, 2))
+    v = rng.random((N, N)).astype(np.float32).astype(np.float64)
+    v[:, : N // 3] = 0.0
+    table, flags, _ = _partition(pos, N)
+    rows = np.setdiff1d(np.arange(N), flags)
+    lo, hi = (table & 0xFFFF).astype(np.int64), (table >> 16).astype(np.int64)
+    y = np.arange(N) + 0.5
+    x = np.arange(N) + 0.5
+    zero = np.zeros((N, 1))
+    P = [np.concatenate([zero, np.cumsum(v * w[None, :], axis=1)], axis=1) for w in (np.ones(N), y, y * y)]  # P[c] = sum of cols < c
+    lab = _rule_labels(pos, N, 1.0, rows)
+    for k in range(R):
+        rs, rsy, rsyy = (p[rows, hi[k, rows]] - p[rows, lo[k, rows]] for p in P)
+        got = np.array([rs.sum(), (x[rows] * rs).sum(), rsy.sum(), (x[rows] ** 2 * rs + rsyy).sum()])
+        m = lab == k
+        vv = v[rows]
+        ref = np.array([vv[m].sum(), (vv * x[rows, None])[m].sum(), (vv * y[None, :])[m].sum(),
+                        (vv * (x[rows, None] ** 2 + y[None, :] ** 2))[m].sum()])
+        if ref[0] == 0.0:
+            assert np.all(got == 0.0)
+            continue
+        assert abs(got[0] - ref[0]) <= 1e-12 * ref[0]
+        assert abs(got[1] / got[0] - ref[1] / ref[0]) <= 1e-9 and abs(got[2] / got[0] - ref[2] / ref[0]) <= 1e-9
+        px, py = pos[k]
+        obj = lambda s: s[3] - 2 * (px * s[1] + py * s[2]) + (px * px + py * py) * s[0]  # noqa: E731
+        assert abs(obj(got) - obj(ref)) <= 1e-9 * abs(obj(ref))
