@@ -202,6 +202,9 @@ def main():
     config = {"workload": workload, "envs_per_gpu": E, "world": N_WORLD, "robots": N_ROBOTS, "features": N_FEATURES,
               "l2": "state per GPU (world+seen+sys = 9 MB x envs) is larger than the 126 MB L2",
               "parallelism": f"independent environments sharded over {world} GPU(s), no data-path collective"}
+    overrides = {k: v for k, v in sorted(os.environ.items()) if k.startswith("CCB_")}
+    if overrides:  # opt-in / diagnostic kernel paths: a line measured with one says so
+        config["env_overrides"] = overrides
 
     if args.impl == "reference":
         # the reference's own CPU path cannot be built here (no Eigen/CGAL/Boost):
