@@ -131,3 +131,42 @@ def test_comm_map_rounding_differs_between_cpp_and_python_on_exact_halves():
     assert np.argwhere(cx != 0).tolist() == [[17, 16]]
     ref = _comm_maps_torch(env.neighbors(0), 32, 128.0, 1.0)
     assert np.array_equal(px, ref[0])
+
+
+def test_voronoi_features_against_numpy():
+    """robot_model.h:408-430 GetVoronoiFeatures: the single-site "Voronoi" over the clipped L-window of the robot's
+    own map.  Cell centres are taken relative to the robot (origin_shift = -site, voronoi.h:171), and the distance
+    terms subtract the site once more (voronoi.h:89-95 -- the reference's double shift, kept as it is):
+    [cx, cy, mass, sum |c - 2 s|^2 v, 0, sum |c - 2 s| v, 0] with c the centre and s the robot, both relative to the
+    window origin; zero mass -> the rectangle's centroid relative to the robot (voronoi.cpp:41-53)."""
+    rng = np.random.default_rng(4)
+    N, S, L, R = 192, 32, 64, 5
+    world = rng.random((N, N)).astype(np.float32)
+    p = orc.default_params(pWorldMapSize=N, pRobotMapSize=N, pSensorSize=S, pLocalMapSize=L, pNumRobots=R)
+    pos = rng.uniform(20, N - 20, (R, 2))
+    pos[0] = [3.2, 100.7]       # window clipped by the border
+    pos[1] = [N - 1.5, N - 2.5]
+    env = orc.Env(p, world, pos)
+    model = Model(world, env.positions(), S, L, 1.0)
+    for _ in range(6):
+        ang = rng.uniform(0, 2 * np.pi, R)
+        env.step_actions(np.stack([np.cos(ang), np.sin(ang)], 1) * 4.0)
+        model.visit(env.positions())
+    for r in range(R):
+        _, _, x0, x1, y0, y1 = _window(model.pos[r], L, N, 1.0)
+        v = model.robot_map(r)[x0:x1, y0:y1].astype(np.float64)
+        s = model.pos[r] - [x0, y0]
+        cx = np.arange(x1 - x0) + 0.5
+        cy = np.arange(y1 - y0) + 0.5
+        px, py = cx[:, None] - s[0], cy[None, :] - s[1]          # relative to the robot
+        mass = v.sum()
+        d2 = (px - s[0]) ** 2 + (py - s[1]) ** 2                   # the site subtracted a second time
+        ref = [(px * v).sum() / mass, (py * v).sum() / mass, mass, (d2 * v).sum(), 0.0, (np.sqrt(d2) * v).sum(), 0.0]
+        assert np.allclose(env.voronoi_features(r), ref, rtol=1e-10, atol=1e-9), f"robot {r}"
+    # nothing seen inside the window: the vertex mean of the window rectangle, relative to the robot
+    blank = orc.Env(p, np.zeros((N, N), np.float32), pos)
+    for r in range(R):
+        _, _, x0, x1, y0, y1 = _window(pos[r], L, N, 1.0)
+        s = blank.positions()[r] - [x0, y0]
+        f = blank.voronoi_features(r)
+        assert np.allclose(f[:2], [(x1 - x0) / 2.0 - s[0], (y1 - y0) / 2.0 - s[1]], atol=1e-12) and not f[2:].any()
