@@ -103,3 +103,50 @@ def test_clairvoyant_rollout_against_numpy(N, R, H, steps, seed):
         model.step(ma)
         assert np.allclose(env.positions(), model.pos, rtol=0, atol=1e-7), f"positions differ at step {step}"
     assert stopped > 0  # robots did reach their centroid / the oscillation rule did fire during the roll-out
+
+
+@pytest.mark.parametrize("N,R,S,L,comm,seed", [(128, 5, 24, 64, 50.0, 3), (96, 4, 16, 48, 200.0, 4)])
+def test_decentralized_rollout_against_numpy(N, R, S, L, comm, seed):
+    """decentralized_cvt.h:85-173: every robot reduces ITS OWN map (the cells its sensor has covered so far) over the
+    clipped L-window around itself, among itself and the robots strictly within pCommunicationRange; the goal is the
+    centroid of its own cell in world coordinates"""
+    from test_oracle_maps_cpu import Model as MapModel, _window
+
+    rng = np.random.default_rng(seed)
+    world = (0.1 + rng.random((N, N))).astype(np.float32)
+    p = orc.default_params(pWorldMapSize=N, pRobotMapSize=N, pSensorSize=S, pLocalMapSize=L, pNumRobots=R,
+                           pCommunicationRange=comm, pMaxRobotSpeed=3.0)
+    pos = rng.uniform(2, N - 2, (R, 2))
+    pos[0] = [4.0, 5.5]  # local window clipped by two borders
+    env = orc.Env(p, world, pos)
+    kin = Model(world, pos, 1.0, 3.0, p.pTimeStep, p.pRobotPosHistorySize)
+    maps = MapModel(world, env.positions(), S, L, 1.0)
+    c = np.arange(N) + 0.5
+    for step in range(25):
+        conv, a, g = env.compute_actions(2)
+        cur = kin.pos
+        mg = np.zeros_like(cur)
+        for r in range(R):
+            _, _, x0, x1, y0, y1 = _window(cur[r], L, N, 1.0)
+            d = cur - cur[r]
+            nb = [j for j in range(R) if j != r and np.hypot(*d[j]) < comm]
+            sites = np.vstack([cur[r:r + 1], cur[nb]])
+            cx, cy = c[x0:x1], c[y0:y1]
+            d2 = (cx[:, None, None] - sites[None, None, :, 0]) ** 2 + (cy[None, :, None] - sites[None, None, :, 1]) ** 2
+            own = np.argmin(d2, axis=2) == 0
+            v = maps.robot_map(r)[x0:x1, y0:y1].astype(np.float64) * own
+            m = v.sum()
+            assert m > 1e-10
+            mg[r] = [(v * cx[:, None]).sum() / m, (v * cy[None, :]).sum() / m]
+        assert np.allclose(g, mg, rtol=0, atol=1e-8), f"goals differ at step {step}"
+        ma = np.zeros_like(cur)
+        for r in range(R):
+            diff = mg[r] - cur[r]
+            dist = np.hypot(*diff)
+            if dist >= 1e-10 and not kin.oscillates(r):
+                ma[r] = min(3.0, dist / p.pTimeStep) * (diff / dist)
+        assert np.allclose(a, ma, rtol=0, atol=1e-7), f"actions differ at step {step}"
+        assert env.step_actions(a) == 0
+        kin.step(ma)
+        maps.visit(env.positions())
+        assert np.allclose(env.positions(), kin.pos, rtol=0, atol=1e-7)
