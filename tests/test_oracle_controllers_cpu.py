@@ -150,3 +150,28 @@ def test_decentralized_rollout_against_numpy(N, R, S, L, comm, seed):
         kin.step(ma)
         maps.visit(env.positions())
         assert np.allclose(env.positions(), kin.pos, rtol=0, atol=1e-7)
+
+
+def test_centralized_rollout_against_numpy():
+    """centralized_cvt.h:90-130: global cells over the system's explored-IDF map (the world where ANY robot's sensor
+    has been, 0 elsewhere)"""
+    from test_oracle_maps_cpu import Model as MapModel
+
+    rng = np.random.default_rng(6)
+    N, R, S = 112, 5, 24
+    world = (0.1 + rng.random((N, N))).astype(np.float32)
+    p = orc.default_params(pWorldMapSize=N, pRobotMapSize=N, pSensorSize=S, pLocalMapSize=64, pNumRobots=R, pMaxRobotSpeed=3.0)
+    pos = rng.uniform(2, N - 2, (R, 2))
+    env = orc.Env(p, world, pos)
+    kin = Model(world, pos, 1.0, 3.0, p.pTimeStep, p.pRobotPosHistorySize)
+    maps = MapModel(world, env.positions(), S, 64, 1.0)
+    for step in range(25):
+        kin.w = np.where(maps.seen.any(0), world, np.float32(0)).astype(np.float64)
+        conv, a, g = env.compute_actions(1)
+        ma, mg = kin.actions()
+        assert np.allclose(g, mg, rtol=0, atol=1e-8), f"goals differ at step {step}"
+        assert np.allclose(a, ma, rtol=0, atol=1e-7), f"actions differ at step {step}"
+        assert env.step_actions(a) == 0
+        kin.step(ma)
+        maps.visit(env.positions())
+        assert np.allclose(env.positions(), kin.pos, rtol=0, atol=1e-7)
