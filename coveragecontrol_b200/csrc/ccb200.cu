@@ -1097,19 +1097,13 @@ extern "C" int ccb_env_comm_maps_dev(ccb_env *env, int C, float *out_dev) {
 
 // torch's antialias bilinear index/weight computation (ATen UpSampleKernel.cpp,
 // _compute_indices_weights_aa with the triangle filter), float arithmetic.
-static int get_resize_table(ccb_env *env, int C, ResizeTab **out) {
-  auto it = env->resize.find(C);
-  if (it != env->resize.end()) {
-    *out = &it->second;
-    return 0;
-  }
-  const int L = env->d.L;
+static int resize_weights(int L, int C, std::vector<int> &xmin, std::vector<int> &xsize, std::vector<float> &w) {
   const float scale = (float)L / (float)C;
   const float support = scale >= 1.f ? scale : 1.f;  // interp_size/2 * scale
   const float invscale = scale >= 1.f ? 1.f / scale : 1.f;
   const int kmax = (int)std::ceil(support) * 2 + 1;
-  std::vector<int> xmin(C), xsize(C);
-  std::vector<float> w((size_t)C * kmax, 0.f);
+  xmin.assign(C, 0), xsize.assign(C, 0);
+  w.assign((size_t)C * kmax, 0.f);
   for (int i = 0; i < C; ++i) {
     float center = scale * ((float)i + 0.5f);
     int lo = std::max((int)(center - support + 0.5f), 0);
@@ -1126,6 +1120,33 @@ static int get_resize_table(ccb_env *env, int C, ResizeTab **out) {
     for (int j = 0; j < xsize[i]; ++j)
       if (total != 0.f) w[(size_t)i * kmax + j] /= total;
   }
+  return kmax;
+}
+
+// Host only (CPU tests against the installed torchvision): the taps of output index o are input indices
+// [xmin[o], xmin[o] + xsize[o]) with weights w[o][0 .. kmax); returns kmax, or -1 when w_cap floats are too few.
+extern "C" int ccb_selftest_resize_weights(int L, int C, int *xmin_out, int *xsize_out, float *w_out, int w_cap) {
+  if (L < 1 || C < 1) return -1;
+  std::vector<int> xmin, xsize;
+  std::vector<float> w;
+  const int kmax = resize_weights(L, C, xmin, xsize, w);
+  if ((size_t)w_cap < w.size()) return -1;
+  memcpy(xmin_out, xmin.data(), sizeof(int) * C);
+  memcpy(xsize_out, xsize.data(), sizeof(int) * C);
+  memcpy(w_out, w.data(), sizeof(float) * w.size());
+  return kmax;
+}
+
+static int get_resize_table(ccb_env *env, int C, ResizeTab **out) {
+  auto it = env->resize.find(C);
+  if (it != env->resize.end()) {
+    *out = &it->second;
+    return 0;
+  }
+  const int L = env->d.L;
+  std::vector<int> xmin, xsize;
+  std::vector<float> w;
+  const int kmax = resize_weights(L, C, xmin, xsize, w);
   ResizeTab t;
   t.C = C, t.kmax = kmax;
   CCB_CUDA(cudaMalloc(&t.d_xmin, sizeof(int) * C));

@@ -182,6 +182,10 @@ int ccb_env_exploration_features(ccb_env *env, int num_frontiers, double *out);
  * compiled for the host) over values[n]; candidate numbers as popped, worst first; returns their count
  * or -1.  Touches no map and no device. */
 int ccb_selftest_frontier_select(const double *values, int n, int num_frontiers, int *order_out);
+/* Test hook, host only: the separable antialiased bilinear down-sampling taps the observation kernels apply
+ * (what torchvision.transforms.functional.resize(BILINEAR, antialias=True) does, coverage_env_utils.py:97-141):
+ * output index o reads inputs [xmin[o], xmin[o] + xsize[o]) with weights w[o][0 .. kmax).  Returns kmax or -1. */
+int ccb_selftest_resize_weights(int L, int C, int *xmin_out, int *xsize_out, float *w_out, int w_cap);
 /* Test hook, host only: the window of size `sub` around a position as every window kernel derives it
  * (map_utils.h:51-87 ComputeOffsets): out6 = unclipped origin (ox, oy), clipped rows [x0, x1), columns [y0, y1). */
 int ccb_selftest_make_window(double res, double px, double py, int sub, int map_size, int *out6);
