@@ -142,7 +142,9 @@ class BatchedDataGenerator:
 def normalize_tensor(tensor: torch.Tensor, epsilon: float = 1e-6, zero_mean: bool = False, is_symmetric: bool = False):
     """data_generation.py:340-367."""
     dims = list(range(tensor.dim()))[:-1]
-    mean = torch.zeros(tensor.shape[-1]) if zero_mean else tensor.mean(dim=dims)
+    # zero_mean: the reference returns torch.zeros_like(<the index tensor of the leading dimensions>), i.e. INTEGER zeros
+    # of length dim() - 1 (which broadcasts for [n, R, 2] actions because dim() - 1 == 2); actions_mean.pt holds that
+    mean = torch.zeros_like(torch.tensor(range(tensor.dim()))[:-1]) if zero_mean else tensor.mean(dim=dims)
     std = tensor.std(dim=dims)
     if is_symmetric:
         std = torch.ones_like(std) * std.mean()
