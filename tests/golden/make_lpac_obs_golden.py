@@ -97,8 +97,12 @@ def main():
     env = StandIn()
     maps = ref.get_maps(env, cp, C, True).numpy()
     weights = ref.get_weights(env, cp).numpy()
+    # get_torch_geometric_data (coverage_env_utils.py:337-377) with the stub Data container: x is `maps` again
+    data = ref.get_torch_geometric_data(env, cp, True, True, C)
+    assert np.array_equal(data.x.numpy(), maps)
     np.savez_compressed(os.path.join(HERE, "lpac_obs_golden.npz"), start=start, actions=actions, maps=maps, weights=weights,
-                        final_positions=oenv.positions())
+                        final_positions=oenv.positions(), edge_index=data.edge_index.numpy(),
+                        edge_weight=data.edge_weight.numpy(), pos=data.pos.numpy())
     print(maps.shape, float(np.abs(maps).sum()), weights.shape)
 
 

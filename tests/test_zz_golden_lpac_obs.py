@@ -41,6 +41,10 @@ def test_fixture_is_reproduced_by_oracle_and_torchvision():
     # the pair 8 cells apart lands on an exact half: the Python semantics (half to even) are the golden ones
     assert maps[3, 1].any() and maps[2, 1].any()
     assert (GOLD["weights"] > 0).sum() == 6
+    # the graph fields follow from the weights and the positions (coverage_env_utils.py:362-369)
+    w = torch.from_numpy(GOLD["weights"]).to_sparse().coalesce()
+    assert np.array_equal(GOLD["edge_index"], w.indices().numpy()) and np.array_equal(GOLD["edge_weight"], w.values().numpy())
+    assert np.allclose(GOLD["pos"], (GOLD["final_positions"].astype(np.float32) + mk.N / 2.0) / mk.N, atol=1e-7)
 
 
 @pytest.mark.gpu
@@ -69,3 +73,9 @@ def test_cuda_observation_equals_the_reference_output():
     gw = torch.from_numpy(GOLD["weights"])
     assert torch.allclose(w_host, gw, rtol=0, atol=1e-6)
     assert torch.allclose(w_dev, gw, rtol=0, atol=1e-5) and torch.equal(w_dev != 0, gw != 0)
+    # the graph the GNN receives (coverage_env_utils.py:337-377): same edges in the same order, weights, positions
+    g = U.get_torch_geometric_data(env, p, True, True, mk.C)
+    assert torch.equal(g.edge_index.cpu(), torch.from_numpy(GOLD["edge_index"]))
+    assert torch.allclose(g.edge_weight.cpu(), torch.from_numpy(GOLD["edge_weight"]), rtol=0, atol=1e-5)
+    assert torch.allclose(g.pos.cpu(), torch.from_numpy(GOLD["pos"]), rtol=0, atol=1e-6)
+    assert torch.allclose(g.x.cpu(), maps)
