@@ -58,6 +58,7 @@ SIGNATURES = {
     "ccb_idf_get_map": (C.c_int, [C.c_void_p, c_float_p]),
     "ccb_idf_set_map": (C.c_int, [C.c_void_p, c_float_p]),
     "ccb_idf_map_dev": (C.c_void_p, [C.c_void_p]),
+    "ccb_idf_copy_map": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ccb_idf_norm_factor": (C.c_int, [C.c_void_p, c_float_p]),
     "ccb_idf_generate_band": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "ccb_idf_band_max_dev": (C.c_void_p, [C.c_void_p]),
@@ -101,6 +102,7 @@ SIGNATURES = {
     "ccb_env_voronoi_features_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ccb_env_local_voronoi_features": (C.c_int, [C.c_void_p, c_double_p]),
     "ccb_env_exploration_features": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
+    "ccb_test_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "ccb_selftest_frontier_select": (C.c_int, [c_double_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "ccb_selftest_resize_weights": (C.c_int, [C.c_int, C.c_int, c_int_p, c_int_p, c_float_p, C.c_int]),
     "ccb_selftest_make_window": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, c_int_p]),
@@ -145,8 +147,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_build.LIB):
-        _build.build()
+    if _build.needs_build():  # missing, or older than a source it is built from
+        _build.build()        # (file lock + atomic replace: safe when every rank of a torchrun starts at once)
     lib = C.CDLL(_build.LIB)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export it
@@ -156,6 +158,22 @@ def load():
         raise RuntimeError("libccb200.so ABI version mismatch; rebuild with python -m coveragecontrol_b200.build --force")
     _lib = lib
     return lib
+
+
+# Diagnostics: CCB_<OPTION>=<int> in the process environment forces a kernel choice on every environment batch created
+# afterwards (tests and A/B timing; `ccb_test_set_option`, include/ccb200_test.h).  The library itself never reads
+# the environment.
+_OVERRIDES = {"CCB_VG_GENERIC": "vg_generic", "CCB_VG_PREFIX": "vg_prefix", "CCB_VW_GENERIC": "vw_generic",
+              "CCB_CNN_GENERIC": "cnn_generic", "CCB_VOR_RPW": "vor_rpw", "CCB_VG_WARPS": "vg_warps",
+              "CCB_VG_GRIDDIV": "vg_griddiv", "CCB_VG_PART_RPT": "vg_part_rpt", "CCB_NO_AUX": "no_aux",
+              "CCB_NO_GRAPH": "no_graph", "CCB_NO_WFUSE": "no_wfuse"}
+
+
+def apply_test_overrides(env_handle) -> None:
+    for var, name in _OVERRIDES.items():
+        v = os.environ.get(var)
+        if v is not None and v.strip() != "":
+            check(load().ccb_test_set_option(env_handle, name.encode(), int(v)))
 
 
 def last_error() -> str:

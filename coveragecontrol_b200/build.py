@@ -43,6 +43,7 @@ def needs_build() -> bool:
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
     deps.append(os.path.join(_HERE, "..", "include", "ccb200.h"))
+    deps.append(os.path.join(_HERE, "..", "include", "ccb200_test.h"))
     deps.append(os.path.abspath(__file__))
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -50,15 +51,29 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    out = subprocess.run(cmd, capture_output=True, text=True)
-    log = out.stdout + out.stderr
-    with open(os.path.join(_HERE, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if out.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + log)
-    if verbose:
-        print(log)
+    import fcntl
+
+    # one builder at a time (every rank of a torchrun may get here at once); the others find the library fresh
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB
+            tmp = f"{LIB}.{os.getpid()}.tmp"
+            cmd = [_nvcc(), *NVCC_FLAGS, "-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+            out = subprocess.run(cmd, capture_output=True, text=True)
+            log = out.stdout + out.stderr
+            with open(os.path.join(_HERE, "build.log"), "w") as f:
+                f.write(" ".join(cmd) + "\n" + log)
+            if out.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + log)
+            os.replace(tmp, LIB)  # atomic: a concurrent dlopen sees the old or the new file, never a partial one
+            if verbose:
+                print(log)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

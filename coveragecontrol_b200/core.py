@@ -541,8 +541,8 @@ class WorldIDF:
             other.AddNormalDistribution(d)
         for p in self._polys:
             other.AddUniformDistributionPolygon(p)
-        _lib.check(_lib.load().ccb_idf_set_map(other._h, _fp(np.ascontiguousarray(self.GetWorldMap()))))
-        other._factor = self.GetNormalizationFactor()
+        _lib.check(_lib.load().ccb_idf_copy_map(other._h, self._h))  # device to device, no host round trip
+        other._factor = self._factor
         return other
 
 
@@ -603,6 +603,11 @@ class _EnvBase:
             raise RuntimeError(_lib.last_error())
         self._pos_cache = None
         self._ctrls = []
+        _lib.apply_test_overrides(self._h)
+
+    def set_option(self, name: str, value: int) -> None:
+        """Test / A-B hook (include/ccb200_test.h ``ccb_test_set_option``): force a kernel choice on this batch."""
+        _lib.check(_lib.load().ccb_test_set_option(self._h, name.encode(), int(value)))
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None

@@ -32,6 +32,35 @@ def _finish(t: torch.Tensor, env: _EnvBase, device):
     return t
 
 
+def _prepare(env: _EnvBase) -> None:
+    """Edits made through ``GetWorldMapMutable`` must be on the device before a kernel reads the world map."""
+    if isinstance(env, CoverageSystem):
+        env._sync_world()
+
+
+def _noisy(env: _EnvBase) -> bool:
+    """pAddNoisePositions: the reference builds the communication maps / edge weights from the NOISY getters
+    (GetRobotPositions / GetRelativePositonsNeighbors, coverage_system.cpp:340-366,626-645); the device kernels
+    read the true positions, so those quantities go through the host expressions instead."""
+    return isinstance(env, CoverageSystem) and bool(env._params.pAddNoisePositions)
+
+
+def _host_comm_maps(env, params: Parameters, map_size: int) -> torch.Tensor:
+    """reference :143-191 verbatim semantics on the host (float32, torch.round, duplicates summed)."""
+    R = env.GetNumRobots()
+    out = torch.zeros((R, 2, map_size, map_size))
+    for r in range(R):
+        rel = CoverageEnvUtils.to_tensor(env.GetRelativePositonsNeighbors(r))
+        if rel.numel() == 0:
+            continue
+        idx = torch.round(rel * map_size / (params.pCommunicationRange * params.pResolution * 2.0)
+                          + (map_size / 2.0 - params.pResolution / 2.0)).t().long()
+        val = rel / params.pCommunicationRange
+        for ch in range(2):
+            out[r][ch] = torch.sparse_coo_tensor(idx, val[:, ch], torch.Size([map_size, map_size])).to_dense()
+    return out
+
+
 class CoverageEnvUtils:
     """Utility functions for the coverage environment (reference coverage_env_utils.py:42)."""
 
@@ -52,6 +81,7 @@ class CoverageEnvUtils:
     def get_raw_local_maps(env, params: Parameters, device=None) -> torch.Tensor:
         """reference :97-117 -> [R, L, L] (or [E, R, L, L] for a batched environment)."""
         L = params.pLocalMapSize
+        _prepare(env)
         out = torch.empty((env._E, env._R, L, L), dtype=torch.float32, device=_cuda_device(env))
         _lib.check(_lib.load().ccb_env_local_maps_dev(env._h, out.data_ptr()))
         return _finish(out, env, device)
@@ -67,6 +97,9 @@ class CoverageEnvUtils:
     @staticmethod
     def get_communication_maps(env, params: Parameters, map_size: int, device=None) -> torch.Tensor:
         """reference :143-191 (float32, round-half-even) -> [R, 2, C, C]."""
+        if _noisy(env):
+            t = _host_comm_maps(env, params, int(map_size))
+            return t if device is not None and torch.device(device).type == "cpu" else t.to(device or _cuda_device(env))
         out = torch.empty((env._E, env._R, 2, map_size, map_size), dtype=torch.float32, device=_cuda_device(env))
         _lib.check(_lib.load().ccb_env_comm_maps_dev(env._h, int(map_size), out.data_ptr()))
         return _finish(out, env, device)
@@ -89,9 +122,16 @@ class CoverageEnvUtils:
         communication channels fused on the GPU."""
         C = int(resized_map_size)
         nch = 4 if use_comm_map else 2
+        _prepare(env)
         out = torch.empty((env._E, env._R, nch, C, C), dtype=torch.float32, device=_cuda_device(env))
-        _lib.check(_lib.load().ccb_env_cnn_input_dev(env._h, C, int(bool(use_comm_map)), out.data_ptr()))
-        return _finish(out, env, device)
+        noisy = bool(use_comm_map) and _noisy(env)
+        _lib.check(_lib.load().ccb_env_cnn_input_dev(env._h, C, int(bool(use_comm_map) and not noisy), out.data_ptr()))
+        out = _finish(out, env, None)
+        if noisy:  # channels 1, 2 from the noisy neighbour positions, as the reference does
+            out[:, 1:3] = _host_comm_maps(env, params, C).to(out.device)
+        if device is not None and torch.device(device) != out.device:
+            out = out.to(device)
+        return out
 
     @staticmethod
     def get_voronoi_features(env, device=None) -> torch.Tensor:
@@ -112,7 +152,7 @@ class CoverageEnvUtils:
     def get_weights(env, params: Parameters, device=None) -> torch.Tensor:
         """reference :313-335 -> [R, R] ([E, R, R] batched).  ``device=None``: host tensor computed with the
         reference's own torch expressions; any ``device``: the ``k_graph`` kernel, no host round trip."""
-        if device is not None:
+        if device is not None and not _noisy(env):
             if float(params.pCommunicationRange) != float(env._params.pCommunicationRange):
                 raise ValueError("get_weights(device=...): params.pCommunicationRange differs from the environment's")
             out = torch.empty((env._E, env._R, env._R), dtype=torch.float32, device=_cuda_device(env))
@@ -127,7 +167,7 @@ class CoverageEnvUtils:
             edge_weights.fill_diagonal_(0)
         else:
             edge_weights.diagonal(dim1=-2, dim2=-1).zero_()
-        return edge_weights
+        return edge_weights if device is None else edge_weights.to(device)
 
     @staticmethod
     def get_torch_geometric_data(env, params: Parameters, use_cnn: bool, use_comm_map: bool, map_size: int, device=None):
@@ -143,6 +183,7 @@ class CoverageEnvUtils:
                 int(params.pWorldMapSize) != int(env._params.pWorldMapSize):
             raise ValueError("get_torch_geometric_data: params differ from the environment's")
         dev = _cuda_device(env)
+        _prepare(env)
         if use_cnn:
             features = CoverageEnvUtils.get_maps(env, params, map_size, use_comm_map)
         else:
@@ -153,6 +194,10 @@ class CoverageEnvUtils:
         pos = torch.empty((1, env._R, 2), dtype=torch.float32, device=dev)
         _lib.check(_lib.load().ccb_env_graph_dev(env._h, w.data_ptr(), pos.data_ptr()))
         w, pos = _finish(w, env, None), _finish(pos, env, None)
+        if _noisy(env):  # reference :360-369: weights and positions from (separately drawn) noisy positions
+            w = CoverageEnvUtils.get_weights(env, params).to(dev)
+            half = float(params.pWorldMapSize) / 2.0
+            pos = ((CoverageEnvUtils.get_robot_positions(env) + half) / float(params.pWorldMapSize)).to(dev)
         edge_index = w.nonzero().t().contiguous()          # row-major order, as to_sparse().coalesce().indices()
         edge_weight = w[edge_index[0], edge_index[1]]
         if device is not None:

@@ -10,6 +10,7 @@
 #include <map>
 #include <memory>
 
+#include "../../include/ccb200_test.h"
 #include "common.cuh"
 #include "idf.cuh"
 #include "maps.cuh"
@@ -326,7 +327,7 @@ static int idf_generate_rows(ccb_idf *idf, int mode, int row0, int row1, bool fi
   const float trun_sq = trun * trun;                       // generate_world_map.cu:188-189
   const float one_by_sqrt2 = (float)(1. / std::sqrt(2.));  // generate_world_map.cu:190-192
   if (row1 > row0) {
-    dim3 grid((N + IDF_TY - 1) / IDF_TY, (row1 - row0 + IDF_TX - 1) / IDF_TX);
+    dim3 grid((N + IDF_TY - 1) / IDF_TY, (row1 - (row0 & ~(IDF_TX - 1)) + IDF_TX - 1) / IDF_TX);
     if (mode == 0)
       k_idf_generate<0><<<grid, IDF_THREADS, 0, st>>>(d_b, F, d_bk_start, d_bk_items, bk_nb, bk_size, pd, N, row0, row1, res, trun_sq,
                                                      one_by_sqrt2, idf->d_map, idf->d_max);
@@ -371,6 +372,17 @@ extern "C" int ccb_idf_set_map(ccb_idf *idf, const float *in) {
 }
 
 extern "C" const float *ccb_idf_map_dev(const ccb_idf *idf) { return idf->d_map; }
+
+extern "C" int ccb_idf_copy_map(ccb_idf *dst, const ccb_idf *src) {
+  if (dst->p.pWorldMapSize != src->p.pWorldMapSize) return fail("ccb_idf_copy_map: map sizes differ");
+  CCB_CUDA(cudaSetDevice(dst->device));
+  const size_t nn = (size_t)src->p.pWorldMapSize * src->p.pWorldMapSize;
+  if (src->stream != dst->stream) CCB_CUDA(cudaStreamSynchronize(src->stream));
+  CCB_CUDA(cudaMemcpyAsync(dst->d_map, src->d_map, nn * sizeof(float), cudaMemcpyDefault, dst->stream));
+  CCB_CUDA(cudaMemcpyAsync(dst->d_factor, src->d_factor, sizeof(float), cudaMemcpyDefault, dst->stream));
+  dst->h_factor = src->h_factor, dst->factor_valid = src->factor_valid;
+  return 0;
+}
 
 extern "C" int ccb_idf_norm_factor(ccb_idf *idf, float *out) {
   if (!idf->factor_valid) {
@@ -423,6 +435,8 @@ struct ccb_env {
   cudaEvent_t ev_state = nullptr;  // recorded on `stream` after every change of positions / maps
   cudaEvent_t ev_aux = nullptr;    // recorded on `aux` after the last chain launched there
   cudaEvent_t ev_cells = nullptr;  // recorded on `stream` after cells were (re)computed there
+  cudaEvent_t ev_vg = nullptr;     // recorded on `stream` after every whole-map Voronoi launched there: the partition
+                                   // tables / flag list / spans / items are ONE scratch set shared with `aux`
   bool no_aux = false;             // CCB_NO_AUX: keep everything on `stream` (debugging)
   bool no_graph = false;           // CCB_NO_GRAPH: never replay roll-outs from a CUDA graph
   // roll-out graphs are captured on and launched into `cap` (the caller's stream may be the legacy
@@ -451,8 +465,11 @@ struct ccb_env {
   bool vw_generic = false;      // CCB_VW_GENERIC: force the generic window kernel (tests)
   bool band_mode = false;       // this env holds one row band of a world tiled over several GPUs
   int vg_part_rpt = 1;          // CCB_VG_PART_RPT (opt-in, 1 / 2 / 4): rows per thread of k_vg_partition
-  bool vg_prefix = false;       // CCB_VG_PREFIX=1 (opt-in): keep row prefix sums of the world maps (vglobal.cuh k_vg_prefix)
-  VgPfx *d_vg_pfx = nullptr;    // [E][N][N] x 32 B, rebuilt for an environment whenever its world map is set
+  bool vg_prefix = true;        // block prefix sums of the world maps for the site-ordered world-map moments (vglobal.cuh)
+  VgPfx *d_vg_pfx = nullptr;    // [E][N][N / 8 + 1] x 48 B, allocated on first use, rebuilt per environment when its world map is set
+  std::vector<char> pfx_valid;  // [E]: the entries of environment e match its world map
+  int *d_pfx_list = nullptr;    // [E] environments to rebuild
+  bool cnn_generic = false;     // test option: the generic observation kernel even where the fused one applies
 };
 
 // kernels that need more than 48 KB of dynamic shared memory: raise the limit once per (device, kernel)
@@ -508,6 +525,8 @@ static int run_voronoi(ccb_env *env, const VorArgs &a, dim3 grid) {
   return 0;
 }
 
+static int ensure_prefix(ccb_env *env);
+
 // Voronoi label + reduce over the full map of every environment; sums must be a [E][R][4] buffer.
 // row0/row1 restrict the pass to a row band (row1 < 0: the whole map).
 // stages: bit 0 row partition, bit 1 per-site reduce, bit 2 flagged-row fix-up (site-ordered path; the
@@ -542,6 +561,11 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
     g.d = d, g.row0 = row0, g.row1 = row1, g.table = env->d_vg_table, g.nflag = env->d_vg_flag, g.flag_list = env->d_vg_flag + 1, g.span = env->d_vg_span, g.sums = sums, g.labels = labels;
     g.items = env->d_vg_items;
     const int rows = row1 - row0;
+    bool lookup = false;
+    if (src == SRC_WORLD && !labels && env->vg_prefix) {
+      if (ensure_prefix(env)) return 1;
+      lookup = env->d_vg_pfx != nullptr;
+    }
     if (stages & 1) {
       const int rpt = env->vg_part_rpt, band = rpt * VG_PART_THREADS;
       const dim3 pgrid((rows + band - 1) / band, d.E);
@@ -550,8 +574,10 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
       else if (rpt == 4) k_vg_partition<4><<<pgrid, VG_PART_THREADS, psmem, env->stream>>>(g);
       else k_vg_partition<1><<<pgrid, VG_PART_THREADS, psmem, env->stream>>>(g);
       CCB_LAUNCH_CHECK();
-      k_vg_items<<<(d.E + 3) / 4, 128, 0, env->stream>>>(env->d_vg_span, env->d_vg_items, d.E, d.R, row0);
-      CCB_LAUNCH_CHECK();
+      if (!lookup) {
+        k_vg_items<<<(d.E + 3) / 4, 128, 0, env->stream>>>(env->d_vg_span, env->d_vg_items, d.E, d.R, row0);
+        CCB_LAUNCH_CHECK();
+      }
     }
     // A site of a typical partition spans a fraction of the rows: a quarter of the largest possible item
     // count (every site on every chunk) covers it with about one item per warp; the warps stride beyond it.
@@ -560,11 +586,10 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
     dim3 rgrid(std::max(1, (max_ctas + env->vg_griddiv - 1) / env->vg_griddiv), d.E), fgrid(148 * 2);
     if (stages & 2) {
       const int nt = env->vg_warps * 32;
-      if (src == SRC_WORLD && !labels && env->d_vg_pfx) {
-        // opt-in: two prefix look-ups per (site, row) instead of streaming the interval; an item is one pass of a
-        // warp, so warps for half of the largest possible item count (the rest is reached by striding)
-        dim3 lgrid(std::max(1, (chunks * d.R + VG_RED_WARPS - 1) / VG_RED_WARPS / 2), d.E);
-        k_vg_lookup<<<lgrid, VG_RED_WARPS * 32, 0, env->stream>>>(g, env->d_vg_pfx);
+      if (lookup) {
+        // two block-prefix look-ups and at most two map sectors per (site, row) instead of streaming the interval;
+        // one warp per site, sums stored (no atomics)
+        k_vg_lookup<<<dim3((d.R + VG_LOOK_WARPS - 1) / VG_LOOK_WARPS, d.E), VG_LOOK_WARPS * 32, 0, env->stream>>>(g, env->d_vg_pfx);
       } else if (src == SRC_WORLD) {
         if (labels) k_vg_reduce<SRC_WORLD, true><<<rgrid, nt, 0, env->stream>>>(g);
         else k_vg_reduce<SRC_WORLD, false, VG_U, VG_RED_MINB, 4><<<rgrid, nt, 0, env->stream>>>(g);  // 8 rows x 16 columns per pass
@@ -584,6 +609,7 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
       }
       CCB_LAUNCH_CHECK();
     }
+    if (env->stream != env->aux) CCB_CUDA(cudaEventRecord(env->ev_vg, env->stream));  // `aux` waits before reusing the scratch
     return 0;
   }
   VorArgs a;
@@ -697,14 +723,7 @@ static int env_alloc(ccb_env *env) {
     CCB_CUDA(cudaEventCreateWithFlags(&env->ev_stage[k], cudaEventDisableTiming));
   }
   CCB_CUDA(cudaMemsetAsync(d.world, 0, sizeof(float) * (nn * d.E + (size_t)VOR_PAD_ROWS * d.N), env->stream));
-  if (env->vg_prefix && d.R <= VG_MAXR && (d.N & 3) == 0 && d.N < 65536) {
-    // asked for explicitly: failing to get the memory is an error, not a silent change of path
-    if (cudaMalloc(&env->d_vg_pfx, sizeof(VgPfx) * nn * d.E) != cudaSuccess) {
-      cudaGetLastError();
-      return fail("CCB_VG_PREFIX=1: cudaMalloc of the row prefix sums failed (32 bytes per map cell and environment)");
-    }
-    CCB_CUDA(cudaMemsetAsync(env->d_vg_pfx, 0, sizeof(VgPfx) * nn * d.E, env->stream));  // prefixes of the zero map
-  }
+  env->pfx_valid.assign(d.E, 0);
   CCB_CUDA(cudaMemsetAsync(d.seenb, 0, sizeof(uint32_t) * pw * er, env->stream));
   if (d.xseenb) CCB_CUDA(cudaMemsetAsync(d.xseenb, 0, sizeof(uint32_t) * pw * er, env->stream));
   CCB_CUDA(cudaMemsetAsync(d.sysb, 0, sizeof(uint32_t) * pw * 2 * d.E, env->stream));
@@ -713,11 +732,13 @@ static int env_alloc(ccb_env *env) {
   CCB_CUDA(cudaEventCreateWithFlags(&env->ev_state, cudaEventDisableTiming));
   CCB_CUDA(cudaEventCreateWithFlags(&env->ev_aux, cudaEventDisableTiming));
   CCB_CUDA(cudaEventCreateWithFlags(&env->ev_cells, cudaEventDisableTiming));
+  CCB_CUDA(cudaEventCreateWithFlags(&env->ev_vg, cudaEventDisableTiming));
   CCB_CUDA(cudaStreamCreateWithFlags(&env->cap, cudaStreamNonBlocking));
   CCB_CUDA(cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming));
   CCB_CUDA(cudaEventCreateWithFlags(&env->ev_join, cudaEventDisableTiming));
   CCB_CUDA(cudaEventRecord(env->ev_state, env->stream));
   CCB_CUDA(cudaEventRecord(env->ev_cells, env->stream));
+  CCB_CUDA(cudaEventRecord(env->ev_vg, env->stream));
   return 0;
 }
 
@@ -753,19 +774,6 @@ extern "C" ccb_env *ccb_env_create(const ccb_params *p, int num_envs, int num_ro
   d.upd_expl = p->pUpdateExplorationMap, d.upd_sys = p->pUpdateSystemMap;
   d.check_osc = p->pCheckOscillations;
   d.comm_range = p->pCommunicationRange, d.max_speed = p->pMaxRobotSpeed, d.dt = p->pTimeStep;
-  if (const char *s = getenv("CCB_VOR_RPW")) env->vor_rpw_override = atoi(s);
-  if (const char *s = getenv("CCB_VW_GENERIC")) env->vw_generic = atoi(s) != 0;
-  if (const char *s = getenv("CCB_VG_GENERIC")) env->vg_mode = atoi(s) != 0 ? 1 : 0;
-  if (const char *s = getenv("CCB_VG_WARPS")) env->vg_warps = std::min(std::max(atoi(s), 1), VG_RED_WARPS);
-  if (const char *s = getenv("CCB_VG_GRIDDIV")) env->vg_griddiv = std::max(atoi(s), 1);
-  if (const char *s = getenv("CCB_VG_PREFIX")) env->vg_prefix = atoi(s) != 0;
-  if (const char *s = getenv("CCB_VG_PART_RPT")) {
-    const int v = atoi(s);
-    env->vg_part_rpt = (v == 2 || v == 4) ? v : 1;
-  }
-  if (const char *s = getenv("CCB_NO_AUX")) env->no_aux = atoi(s) != 0;
-  if (const char *s = getenv("CCB_NO_GRAPH")) env->no_graph = atoi(s) != 0;
-  if (const char *s = getenv("CCB_NO_WFUSE")) env->no_wfuse = atoi(s) != 0;
   if (env_alloc(env.get())) {
     ccb_env_destroy(env.release());
     return nullptr;
@@ -781,6 +789,7 @@ extern "C" void ccb_env_destroy(ccb_env *env) {
   if (env->ev_state) cudaEventDestroy(env->ev_state);
   if (env->ev_aux) cudaEventDestroy(env->ev_aux);
   if (env->ev_cells) cudaEventDestroy(env->ev_cells);
+  if (env->ev_vg) cudaEventDestroy(env->ev_vg);
   if (env->cap) cudaStreamSynchronize(env->cap), cudaStreamDestroy(env->cap);
   if (env->ev_fork) cudaEventDestroy(env->ev_fork);
   if (env->ev_join) cudaEventDestroy(env->ev_join);
@@ -793,7 +802,7 @@ extern "C" void ccb_env_destroy(ccb_env *env) {
   cudaFree(env->d_objective), cudaFree(env->d_stage), cudaFree(env->d_feat), cudaFree(env->d_ratio);
   cudaFree(env->d_scratch);
   cudaFree(env->d_vg_table), cudaFree(env->d_vg_flag), cudaFree(env->d_vg_span), cudaFree(env->d_vg_items), cudaFree(env->d_xfeat);
-  cudaFree(env->d_vg_pfx);
+  cudaFree(env->d_vg_pfx), cudaFree(env->d_pfx_list);
   cudaFreeHost(env->h_pin);
   for (int k = 0; k < 2; ++k) {
     cudaFreeHost(env->h_stage[k]);
@@ -804,18 +813,69 @@ extern "C" void ccb_env_destroy(ccb_env *env) {
   delete env;
 }
 
+// test / A-B hook (include/ccb200_test.h): the library never reads the process environment
+extern "C" int ccb_test_set_option(ccb_env *env, const char *name, int value) {
+  const std::string n(name ? name : "");
+  if (n == "vor_rpw") env->vor_rpw_override = value;
+  else if (n == "vw_generic") env->vw_generic = value != 0;
+  else if (n == "vg_generic") env->vg_mode = value < 0 ? -1 : (value != 0 ? 1 : 0);
+  else if (n == "vg_warps") env->vg_warps = std::min(std::max(value, 1), VG_RED_WARPS);
+  else if (n == "vg_griddiv") env->vg_griddiv = std::max(value, 1);
+  else if (n == "vg_prefix") env->vg_prefix = value != 0;
+  else if (n == "vg_part_rpt") env->vg_part_rpt = (value == 2 || value == 4) ? value : 1;
+  else if (n == "no_aux") env->no_aux = value != 0;
+  else if (n == "no_graph") env->no_graph = value != 0;
+  else if (n == "no_wfuse") env->no_wfuse = value != 0;
+  else if (n == "cnn_generic") env->cnn_generic = value != 0;
+  else return fail("ccb_test_set_option: unknown option", name);
+  return 0;
+}
+
 extern "C" int ccb_env_num_envs(const ccb_env *env) { return env->E; }
 extern "C" int ccb_env_num_robots(const ccb_env *env) { return env->R; }
 extern "C" const float *ccb_env_world_dev(const ccb_env *env) { return env->d.world; }
 extern "C" const double *ccb_env_positions_dev(const ccb_env *env) { return env->d.pos_g; }
 
-// the world map of environment e was just written on env->stream: refresh its row prefix sums (opt-in path)
+// the world map of environment e was just written on env->stream: its block prefix sums are stale
 static int world_changed(ccb_env *env, int e) {
-  if (!env->d_vg_pfx) return 0;
+  env->pfx_valid[e] = 0;
+  return 0;
+}
+
+// Block prefix sums of every environment's world map, (re)built where stale on env->stream.  Returns with
+// env->d_vg_pfx == nullptr when the path is off or its memory cannot be had (the streaming reduce runs instead).
+static int ensure_prefix(ccb_env *env) {
   const EnvDev &d = env->d;
-  const size_t nn = cell_count(d);
-  k_vg_prefix<<<(d.N + 7) / 8, 256, 0, env->stream>>>(d.world + nn * e, env->d_vg_pfx + nn * e, d.N, (long)d.N);
+  if (!env->vg_prefix || d.R > VG_MAXR || (d.N % VG_PB) != 0 || (d.N & 3) != 0 || d.N >= 65536) return 0;
+  const size_t per_env = (size_t)d.N * vg_pfx_row_entries(d.N);
+  if (!env->d_vg_pfx) {
+    if (cudaMalloc(&env->d_vg_pfx, sizeof(VgPfx) * per_env * d.E) != cudaSuccess ||
+        cudaMalloc(&env->d_pfx_list, sizeof(int) * d.E) != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(env->d_vg_pfx);
+      env->d_vg_pfx = nullptr;
+      env->vg_prefix = false;  // 6 bytes per map cell were not available: keep streaming the maps
+      return 0;
+    }
+    env->pfx_valid.assign(d.E, 0);
+  }
+  std::vector<int> todo;
+  for (int e = 0; e < d.E; ++e)
+    if (!env->pfx_valid[e]) todo.push_back(e);
+  if (todo.empty()) return 0;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(env->stream, &cs);
+  if (cs != cudaStreamCaptureStatusNone) return fail("block prefix sums are stale inside a graph capture (internal error)");
+  const int *list = nullptr;
+  if ((int)todo.size() != d.E) {
+    // (pageable source: the copy has been staged when the call returns, so `todo` may go out of scope)
+    CCB_CUDA(cudaMemcpyAsync(env->d_pfx_list, todo.data(), sizeof(int) * todo.size(), cudaMemcpyHostToDevice, env->stream));
+    list = env->d_pfx_list;
+  }
+  const long warps = (long)todo.size() * d.N;
+  k_vg_prefix<<<(unsigned)((warps + 7) / 8), 256, 0, env->stream>>>(d.world, env->d_vg_pfx, d.N, list, (int)todo.size());
   CCB_LAUNCH_CHECK();
+  for (int e : todo) env->pfx_valid[e] = 1;
   return 0;
 }
 
@@ -1026,7 +1086,10 @@ extern "C" int ccb_env_clear_robot_maps(ccb_env *env, int e) {
   CCB_LAUNCH_CHECK();
   // the per-robot exploration maps are NOT cleared by the reference; only the robot-map bits are
   // re-marked here (mark_robot also ORs xseen bits that are already set)
-  return launch_mark(env, e, -1, 1, 0);
+  if (launch_mark(env, e, -1, 1, 0)) return 1;
+  // the robot maps changed: window moments cached by the observation kernel (d_wsums) and roll-out graphs keyed on
+  // them are stale even though no robot moved
+  return state_changed(env);
 }
 
 extern "C" int ccb_env_clear_explored_idf(ccb_env *env, int e) {
@@ -1035,7 +1098,7 @@ extern "C" int ccb_env_clear_explored_idf(ccb_env *env, int e) {
   CCB_CUDA(cudaSetDevice(env->device));
   if (join_aux(env)) return 1;
   CCB_CUDA(cudaMemsetAsync(sys_plane(env->d, e, 0), 0, sizeof(uint32_t) * plane_words(env->d), env->stream));
-  return 0;
+  return state_changed(env);
 }
 
 extern "C" int ccb_env_map_dim(const ccb_env *env, int kind) {
@@ -1183,7 +1246,7 @@ extern "C" int ccb_env_cnn_input_dev(ccb_env *env, int C, int use_comm, float *o
   size_t smem = sizeof(float) * ((size_t)t->kmax * d.L + (size_t)t->kmax * C);
   if (ensure_smem(env, k_cnn_local_obstacle, smem)) return 1;
   // channel order of coverage_env_utils.py:264-276: [local, comm_x, comm_y, obstacle]
-  if (t->d_wfull8 && (d.N & 3) == 0 && !getenv("CCB_CNN_GENERIC")) {
+  if (t->d_wfull8 && (d.N & 3) == 0 && !env->cnn_generic) {
     const bool vor = env->n_decentralized > 0 && !env->no_wfuse && d.L == 256 && env->wsums_version != env->pos_version;
     const size_t smem8 = vor ? cnn8_vor_smem_bytes(d.R) : CNN8_SMEM_BYTES;
     if (ensure_smem(env, k_cnn_fused8<false, false>, smem8) || ensure_smem(env, k_cnn_fused8<false, true>, smem8) ||
@@ -1349,6 +1412,7 @@ static int objective_aux(ccb_env *env, double *out_dev) {
   if (env->no_aux) return objective_dev(env, out_dev);
   CCB_CUDA(cudaStreamWaitEvent(env->aux, env->ev_state, 0));
   CCB_CUDA(cudaStreamWaitEvent(env->aux, env->ev_cells, 0));
+  CCB_CUDA(cudaStreamWaitEvent(env->aux, env->ev_vg, 0));  // a CentralizedCVT pass on `stream` may still be using the scratch
   int rc;
   {
     AuxScope scope(env);
@@ -1752,6 +1816,7 @@ static int rollout_obs_eager(ccb_ctrl *c, int steps, int with_objective, double 
   // fork points of this call (inside a graph capture they must belong to the capture)
   CCB_CUDA(cudaEventRecord(env->ev_state, env->stream));
   CCB_CUDA(cudaEventRecord(env->ev_cells, env->stream));
+  CCB_CUDA(cudaEventRecord(env->ev_vg, env->stream));
   for (int s = 0; s < steps; ++s) {
     if (ctrl_compute_actions_async(c)) return 1;
     if (step_actions_dev(env, c->d_actions)) return 1;
@@ -1782,6 +1847,7 @@ extern "C" int ccb_ctrl_rollout_obs(ccb_ctrl *c, int steps, int with_objective, 
     g.obs = obs_dev, g.stride = obs_step_stride, g.entry_valid = entry_valid;
   }
   if (join_aux(env)) return 1;
+  if (ensure_prefix(env)) return 1;  // never inside the captured region: world maps change between replays
   auto launch_graph = [&]() -> int {
     CCB_CUDA(cudaEventRecord(env->ev_fork, env->stream));
     CCB_CUDA(cudaStreamWaitEvent(env->cap, env->ev_fork, 0));
@@ -1791,6 +1857,7 @@ extern "C" int ccb_ctrl_rollout_obs(ccb_ctrl *c, int steps, int with_objective, 
     // the events were last recorded inside the captured region: make them real again
     CCB_CUDA(cudaEventRecord(env->ev_state, env->stream));
     CCB_CUDA(cudaEventRecord(env->ev_cells, env->stream));
+    CCB_CUDA(cudaEventRecord(env->ev_vg, env->stream));
     env->aux_pending = false;
     return 0;
   };

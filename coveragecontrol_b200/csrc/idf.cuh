@@ -34,39 +34,32 @@ constexpr int IDF_FC = 16;   // features tabulated per chunk
 constexpr int IDF_THREADS = 256;
 constexpr int IDF_MAXPOLY = 64;  // polygon pieces kept per tile before falling back to the full list
 
-// geometry_utils.cuh:44-54
-__device__ __forceinline__ int orientation_f(float px, float py, float qx, float qy, float rx, float ry) {
-  float qpx = __fsub_rn(qx, px), qpy = __fsub_rn(qy, py);
-  float rpx = __fsub_rn(rx, px), rpy = __fsub_rn(ry, py);
-  float c1 = __fmul_rn(qpx, rpy);
-  float c2 = __fmul_rn(qpy, rpx);
-  if (c1 > c2) return 1;
-  if (c1 < c2) return -1;
-  return 0;
+// Point-in-piece test with the outcome of the reference's device predicate (geometry_utils.cuh:44-101), restated
+// as a side mask.  Every edge whose closed y-range holds the point is directed upwards (from its lower to its
+// upper end; an edge with equal ends runs from the second vertex to the first, as there) and classifies the
+// point: bit 0 strictly left of it, bit 1 strictly right, both bits on its supporting line.  The two products of
+// the cross product are rounded separately and compared (no FMA), so the classification is the reference's bit
+// for bit.  The point is inside iff the OR over the edges has both bits: some edge holds it, or it has an edge
+// on either side.
+__device__ __forceinline__ unsigned idf_edge_side(float ax, float ay, float bx, float by, float rx, float ry) {
+  const bool a_low = ay < by;
+  const float lx = a_low ? ax : bx, ly = a_low ? ay : by;
+  const float ux = a_low ? bx : ax, uy = a_low ? by : ay;
+  if (ry < ly || ry > uy) return 0u;
+  const float along = __fmul_rn(__fsub_rn(ux, lx), __fsub_rn(ry, ly));
+  const float across = __fmul_rn(__fsub_rn(uy, ly), __fsub_rn(rx, lx));
+  return along > across ? 1u : (along < across ? 2u : 3u);
 }
 
-// geometry_utils.cuh:60-101
-__device__ inline bool point_in_monotone_polygon(const float *x, const float *y, int sz, float rx, float ry) {
-  bool left = false, right = false;
-  for (int ct = 0; ct < sz; ++ct) {
-    int ctp1 = ct + 1;
-    if (ctp1 == sz) ctp1 = 0;
-    float yct = y[ct], yctp1 = y[ctp1];
-    float px, py, qx, qy;
-    if (yct < yctp1) {
-      if (ry < yct || ry > yctp1) continue;
-      px = x[ct], py = yct, qx = x[ctp1], qy = yctp1;
-    } else {
-      if (ry < yctp1 || ry > yct) continue;
-      qx = x[ct], qy = yct, px = x[ctp1], py = yctp1;
-    }
-    int o = orientation_f(px, py, qx, qy, rx, ry);
-    if (o == 0) return true;
-    if (o == 1) left = true;
-    if (o == -1) right = true;
-    if (left & right) return true;
+__device__ __forceinline__ bool idf_point_in_piece(const float *x, const float *y, int n, float rx, float ry) {
+  unsigned sides = 0u;
+  float ax = x[n - 1], ay = y[n - 1];  // edge (n - 1) -> 0 first: the OR does not depend on the order
+  for (int i = 0; i < n && sides != 3u; ++i) {
+    const float bx = x[i], by = y[i];
+    sides |= idf_edge_side(ax, ay, bx, by, rx, ry);
+    ax = bx, ay = by;
   }
-  return false;
+  return sides == 3u;
 }
 
 __device__ __forceinline__ int float_to_ordered(float f) {
@@ -98,12 +91,14 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, const int *__restrict__ bk_s
   __shared__ float s_red[IDF_THREADS / 32];
 
   const int tid = threadIdx.x;
-  const int x0 = row0 + blockIdx.y * IDF_TX, y0 = blockIdx.x * IDF_TY;  // rows [row0, row1): the whole map or a row band
+  // rows [row0, row1): the whole map or a row band.  Tiles sit on the global 32-row grid whatever row0 is, so a tile
+  // never straddles two feature buckets (bk_size is a multiple of IDF_TX); rows below row0 are computed and dropped
+  const int x0 = (row0 & ~(IDF_TX - 1)) + blockIdx.y * IDF_TX, y0 = blockIdx.x * IDF_TY;
   const int lrow = tid >> 3, lcol = (tid & 7) * 4;
   const int gx = x0 + lrow, gy = y0 + lcol;
 
   // tile extent of the cell mid points, used for conservative culling
-  const float tile_xlo = x0 * res, tile_xhi = (min(x0 + IDF_TX, row1)) * res;
+  const float tile_xlo = max(x0, row0) * res, tile_xhi = (min(x0 + IDF_TX, row1)) * res;
   const float tile_ylo = y0 * res, tile_yhi = (min(y0 + IDF_TY, N)) * res;
 
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -240,7 +235,7 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, const int *__restrict__ bk_s
     }
     __syncthreads();
     const int np = s_npoly;
-    if (np > 0 && gx < row1) {
+    if (np > 0 && gx >= row0 && gx < row1) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (gy + c >= N) continue;
@@ -254,7 +249,7 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, const int *__restrict__ bk_s
           float4 b = poly.bounds[k];
           if (midx < b.x || midx > b.y || midy < b.z || midy > b.w) continue;
           int st = poly.start[k];
-          if (point_in_monotone_polygon(poly.x + st, poly.y + st, poly.sz[k], midx, midy))
+          if (idf_point_in_piece(poly.x + st, poly.y + st, poly.sz[k], midx, midy))
             pim = fmaxf(pim, poly.imp[k]);
         }
         acc[c] = __fadd_rn(acc[c], pim);  // generate_world_map.cu:161-163
@@ -264,7 +259,7 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, const int *__restrict__ bk_s
 
   // ---- store + tile max ------------------------------------------------------------------------
   float vmax = -INFINITY;
-  if (gx < row1) {
+  if (gx >= row0 && gx < row1) {
     float *row = out + (size_t)gx * N;
     if ((N & 3) == 0 && gy + 3 < N) {
       *reinterpret_cast<float4 *>(row + gy) = make_float4(acc[0], acc[1], acc[2], acc[3]);

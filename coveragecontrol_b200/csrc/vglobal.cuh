@@ -442,92 +442,161 @@ __global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a)
   }
 }
 
-// ---- opt-in (CCB_VG_PREFIX=1): row prefix sums instead of streaming the map ---------------------------
-// The world map of an environment never changes while its robots move, and a site's cells on a row are ONE
-// interval: with the inclusive row prefix sums of (v, y v, y^2 v) (y = col + 0.5, fp64) kept next to the map,
-// a (site, row) pair costs two 32-byte look-ups instead of streaming the interval -- ~0.4 MB instead of 4 MB per
-// 1024^2 environment and pass -- at 32 B of HBM per map cell (34 GB for 1024 environments of 1024^2; the part
-// has 180 GB).  The sums are differences of fp64 prefixes instead of exact sums of the interval's cells:
-// |error| <= ~N ulp of the row's prefix (observed relative differences ~1e-15, the gate is 1e-4); a run of
-// zero cells still sums to exactly 0 (equal prefixes), so the mass < 1e-10 fallback (voronoi.cpp:143-150) is
-// taken on the same cells.  Only for the world map (SRC_WORLD, no labels): the explored and robot maps change
-// with every step.  NOT the default: to be measured and gated on a GPU first.
-struct __align__(32) VgPfx {
-  double s, sy, syy, pad;
+// ---- block prefix sums: the world-map moments without streaming the map ---------------------------------
+// The world map of an environment is constant while its robots move, and a site's cells on a row are ONE column
+// interval [lo, hi).  Next to every map row the library keeps the running sums of (v, y v, y^2 v) (y = col + 0.5,
+// cell units) at every VG_PB-th column: entry b = the sum over the columns < VG_PB b, b = 0 .. N / VG_PB.  The
+// moments of [lo, hi) are then
+//     P[hi / 8] - P[ceil(lo / 8)]  +  the cells of [lo, 8 ceil(lo / 8))  +  the cells of [8 (hi / 8), hi),
+// i.e. two 48-byte entries and at most two 32-byte sectors of the map per (site, row) instead of the whole interval
+// (~190 B instead of ~700 B at N = 1024, R = 32), at 6 bytes of HBM per map cell.
+// Accuracy.  The head and tail cells are summed directly (only cells inside the interval are ever added, so a
+// cell of mass 1e-9 next to a cell of mass 1 keeps all its digits).  The entries are DOUBLE-DOUBLE (hi + lo, ~106
+// bits): the difference of two entries is the exact sum of the 8-cell block sums between them to ~1e-32 of the
+// row's total, so a cell of mass 1e-9 at the end of a row whose prefix is 1e3 is still good to ~1e-20 relative
+// and the `mass < 1e-10` fallback (voronoi.cpp:41-53) fires on the same cells as with exact sums; a run of zero
+// cells sums to exactly 0.  The block sums themselves are fp64 sums of exact products, like k_vg_reduce's.
+// Only for the world map (SRC_WORLD, no labels): the explored and robot maps change with every step.
+constexpr int VG_PB = 8;  // columns per block: one 32-byte sector of the map row
+struct __align__(16) VgPfx {
+  double s_hi, s_lo, sy_hi, sy_lo, syy_hi, syy_lo;
 };
+__host__ __device__ inline size_t vg_pfx_row_entries(int N) { return (size_t)N / VG_PB + 1; }
 
-// one warp per map row: inclusive scan over the columns, 32 at a time
-__global__ void __launch_bounds__(256) k_vg_prefix(const float *__restrict__ world, VgPfx *__restrict__ pfx, int N, long rows) {
-  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+struct DD {
+  double hi, lo;
+};
+// error-free transformations (Knuth / Dekker); -fmad=false and the explicit _rn intrinsics keep them un-contracted
+__device__ __forceinline__ DD dd_two_sum(double a, double b) {
+  const double s = __dadd_rn(a, b), bb = __dsub_rn(s, a);
+  return DD{s, __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb))};
+}
+__device__ __forceinline__ DD dd_quick(double a, double b) {  // |a| >= |b|
+  const double s = __dadd_rn(a, b);
+  return DD{s, __dsub_rn(b, __dsub_rn(s, a))};
+}
+__device__ __forceinline__ DD dd_add(DD a, DD b) {
+  DD s = dd_two_sum(a.hi, b.hi);
+  const DD t = dd_two_sum(a.lo, b.lo);
+  s = dd_quick(s.hi, __dadd_rn(s.lo, t.hi));
+  return dd_quick(s.hi, __dadd_rn(s.lo, t.lo));
+}
+__device__ __forceinline__ DD dd_shfl_up(DD v, int o) {
+  return DD{__shfl_up_sync(0xffffffffu, v.hi, o), __shfl_up_sync(0xffffffffu, v.lo, o)};
+}
+
+// eight cells y0 .. y0 + 7 (cell units) of one row, those with a bit in `keep` only
+__device__ __forceinline__ void vg_add8(float4 a, float4 b, unsigned keep, double y0, double &rs, double &rsy, double &rsyy) {
+  a.x = (keep & 1u) ? a.x : 0.f, a.y = (keep & 2u) ? a.y : 0.f, a.z = (keep & 4u) ? a.z : 0.f, a.w = (keep & 8u) ? a.w : 0.f;
+  b.x = (keep & 16u) ? b.x : 0.f, b.y = (keep & 32u) ? b.y : 0.f, b.z = (keep & 64u) ? b.z : 0.f, b.w = (keep & 128u) ? b.w : 0.f;
+  vg_add4(a, y0, rs, rsy, rsyy);
+  vg_add4(b, y0 + 4.0, rs, rsy, rsyy);
+}
+
+// one warp per map row (rows of all the listed environments): lane <-> block of 8 columns, a double-double warp scan
+// per 32 blocks, the carry handed on.  envs: the environments to (re)build, nenv of them (null: 0 .. nenv - 1).
+__global__ void __launch_bounds__(256) k_vg_prefix(const float *__restrict__ world_all, VgPfx *__restrict__ pfx_all, int N,
+                                                   const int *__restrict__ envs, int nenv) {
+  const long wid = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float *src = world + (size_t)row * N;
-  VgPfx *dst = pfx + (size_t)row * N;
-  double c0 = 0.0, c1 = 0.0, c2 = 0.0;  // carry: the sums of the columns before this group of 32
-  for (int cb = 0; cb < N; cb += 32) {
-    const int col = cb + lane;
-    const double v = col < N ? (double)__ldg(src + col) : 0.0;
-    const double y = (double)col + 0.5;
-    double a0 = v, a1 = y * v, a2 = (y * y) * v;
+  if (wid >= (long)nenv * N) return;
+  const int ei = (int)(wid / N), row = (int)(wid - (long)ei * N);
+  const int e = envs ? envs[ei] : ei;
+  const float *src = world_all + ((size_t)e * N + row) * N;
+  const int nblk = N / VG_PB;
+  VgPfx *dst = pfx_all + ((size_t)e * N + row) * vg_pfx_row_entries(N);
+  DD c0{0.0, 0.0}, c1{0.0, 0.0}, c2{0.0, 0.0};  // the sums of the blocks before this group of 32
+  for (int gb = 0; gb <= nblk; gb += 32) {
+    const int b = gb + lane;
+    double bs = 0.0, bsy = 0.0, bsyy = 0.0;
+    if (b < nblk) {
+      const float4 *p4 = reinterpret_cast<const float4 *>(src + VG_PB * b);
+      vg_add8(__ldg(p4), __ldg(p4 + 1), 0xffu, (double)(VG_PB * b) + 0.5, bs, bsy, bsyy);
+    }
+    DD a0{bs, 0.0}, a1{bsy, 0.0}, a2{bsyy, 0.0};  // inclusive scan over the lanes
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const double u0 = __shfl_up_sync(0xffffffffu, a0, o), u1 = __shfl_up_sync(0xffffffffu, a1, o),
-                   u2 = __shfl_up_sync(0xffffffffu, a2, o);
-      if (lane >= o) a0 += u0, a1 += u1, a2 += u2;
+      const DD u0 = dd_shfl_up(a0, o), u1 = dd_shfl_up(a1, o), u2 = dd_shfl_up(a2, o);
+      if (lane >= o) a0 = dd_add(a0, u0), a1 = dd_add(a1, u1), a2 = dd_add(a2, u2);
     }
-    a0 += c0, a1 += c1, a2 += c2;
-    if (col < N) {
+    // entry b = everything before block b: the carry plus the inclusive sum of the lane below
+    DD x0 = dd_shfl_up(a0, 1), x1 = dd_shfl_up(a1, 1), x2 = dd_shfl_up(a2, 1);
+    if (lane == 0) x0 = x1 = x2 = DD{0.0, 0.0};
+    x0 = dd_add(c0, x0), x1 = dd_add(c1, x1), x2 = dd_add(c2, x2);
+    if (b <= nblk) {
       VgPfx out;
-      out.s = a0, out.sy = a1, out.syy = a2, out.pad = 0.0;
-      dst[col] = out;
+      out.s_hi = x0.hi, out.s_lo = x0.lo, out.sy_hi = x1.hi, out.sy_lo = x1.lo, out.syy_hi = x2.hi, out.syy_lo = x2.lo;
+      dst[b] = out;
     }
-    c0 = __shfl_sync(0xffffffffu, a0, 31), c1 = __shfl_sync(0xffffffffu, a1, 31), c2 = __shfl_sync(0xffffffffu, a2, 31);
+    const DD t0{__shfl_sync(0xffffffffu, a0.hi, 31), __shfl_sync(0xffffffffu, a0.lo, 31)};
+    const DD t1{__shfl_sync(0xffffffffu, a1.hi, 31), __shfl_sync(0xffffffffu, a1.lo, 31)};
+    const DD t2{__shfl_sync(0xffffffffu, a2.hi, 31), __shfl_sync(0xffffffffu, a2.lo, 31)};
+    c0 = dd_add(c0, t0), c1 = dd_add(c1, t1), c2 = dd_add(c2, t2);
   }
 }
 
-__device__ __forceinline__ void vg_pfx_load(const VgPfx *p, double &s, double &sy, double &syy) {
-  const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
-  s = a.x, sy = a.y, syy = b.x;
+// entry hi - entry lo, rounded to fp64 once
+__device__ __forceinline__ void vg_pfx_diff(const VgPfx *__restrict__ ph, const VgPfx *__restrict__ pl, double &s, double &sy,
+                                            double &syy) {
+  const double2 *h = reinterpret_cast<const double2 *>(ph), *l = reinterpret_cast<const double2 *>(pl);
+  const double2 h0 = __ldg(h), h1 = __ldg(h + 1), h2 = __ldg(h + 2);
+  const double2 l0 = __ldg(l), l1 = __ldg(l + 1), l2 = __ldg(l + 2);
+  const DD d0 = dd_add(DD{h0.x, h0.y}, DD{-l0.x, -l0.y});
+  const DD d1 = dd_add(DD{h1.x, h1.y}, DD{-l1.x, -l1.y});
+  const DD d2 = dd_add(DD{h2.x, h2.y}, DD{-l2.x, -l2.y});
+  s = __dadd_rn(d0.hi, d0.lo), sy = __dadd_rn(d1.hi, d1.lo), syy = __dadd_rn(d2.hi, d2.lo);
 }
 
-// one warp per (site, 32-row chunk) item as k_vg_reduce, lane <-> row: two look-ups per row with cells
-__global__ void __launch_bounds__(VG_RED_WARPS * 32) k_vg_lookup(VgArgs a, const VgPfx *__restrict__ pfx_all) {
+// One warp per (environment, site): the warp walks the site's row span 32 rows at a time, lane <-> row; two entry
+// look-ups and at most two map sectors per row.  The per-lane sums and the shuffle tree have a fixed order and the
+// result is STORED (no atomics, no memset): the moments are bit-stable from run to run (k_vg_fixup adds the cells
+// of flagged rows afterwards).
+constexpr int VG_LOOK_WARPS = 4;
+__global__ void __launch_bounds__(VG_LOOK_WARPS * 32) k_vg_lookup(VgArgs a, const VgPfx *__restrict__ pfx_all) {
   const EnvDev &d = a.d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int e = blockIdx.y;
+  const int e = blockIdx.y, k = blockIdx.x * VG_LOOK_WARPS + warp;
   const int N = d.N, R = d.R;
-  const int *its = a.items + (size_t)e * (R + 1);
-  const int total = __ldg(its + R);
-  const VgPfx *pfx = pfx_all + (size_t)e * N * N;
-#pragma unroll 1
-  for (int item = blockIdx.x * (blockDim.x >> 5) + warp; item < total; item += gridDim.x * (blockDim.x >> 5)) {
-    int k;
-    {
-      const int end0 = lane < R ? __ldg(its + lane + 1) : 0x7fffffff;
-      unsigned hit = __ballot_sync(0xffffffffu, item < end0);
-      if (hit) {
-        k = __ffs(hit) - 1;
-      } else {
-        const int end1 = lane + 32 < R ? __ldg(its + lane + 33) : 0x7fffffff;
-        hit = __ballot_sync(0xffffffffu, item < end1);
-        k = 32 + __ffs(hit) - 1;
-      }
-    }
-    const int chunk = (__ldg(a.span + ((size_t)e * R + k) * 2) - a.row0) / VG_CHUNK + (item - __ldg(its + k));
-    const int row = a.row0 + chunk * VG_CHUNK + lane;
-    const uint32_t iv = row < a.row1 ? __ldg(a.table + ((size_t)e * R + k) * N + row) : 0u;
+  if (k >= R) return;
+  const int2 sp = __ldg(reinterpret_cast<const int2 *>(a.span) + (size_t)e * R + k);
+  const size_t pe = vg_pfx_row_entries(N);
+  const VgPfx *pfx = pfx_all + (size_t)e * N * pe;
+  const float *world = d.world + (size_t)e * N * N;
+  const uint32_t *tab = a.table + ((size_t)e * R + k) * N;
+  double M = 0.0, SX = 0.0, SY = 0.0, S2 = 0.0;
+#pragma unroll 2
+  for (int row = (sp.y > sp.x ? sp.x : sp.y) + lane; row < sp.y; row += 32) {  // (an empty span is {INT_MAX, 0})
+    const uint32_t iv = __ldg(tab + row);
     const int lo = (int)(iv & 0xffffu), hi = (int)(iv >> 16);
+    if (hi <= lo) continue;
+    const int blo = (lo + VG_PB - 1) / VG_PB, bhi = hi / VG_PB;
+    const float *wrow = world + (size_t)row * N;
     double rs = 0.0, rsy = 0.0, rsyy = 0.0;
-    if (hi > lo) {
-      const VgPfx *prow = pfx + (size_t)row * N;
-      double h0, h1, h2, l0 = 0.0, l1 = 0.0, l2 = 0.0;
-      vg_pfx_load(prow + hi - 1, h0, h1, h2);
-      if (lo > 0) vg_pfx_load(prow + lo - 1, l0, l1, l2);
-      rs = h0 - l0, rsy = h1 - l1, rsyy = h2 - l2;
+    if (blo <= bhi) {
+      if (blo < bhi) vg_pfx_diff(pfx + (size_t)row * pe + bhi, pfx + (size_t)row * pe + blo, rs, rsy, rsyy);
+      if (lo & (VG_PB - 1)) {  // head: the cells [lo, 8 blo) of block blo - 1
+        const float4 *p4 = reinterpret_cast<const float4 *>(wrow + VG_PB * (blo - 1));
+        vg_add8(__ldg(p4), __ldg(p4 + 1), 0xffu & ~((1u << (lo & (VG_PB - 1))) - 1u), (double)(VG_PB * (blo - 1)) + 0.5, rs, rsy, rsyy);
+      }
+      if (hi & (VG_PB - 1)) {  // tail: the cells [8 bhi, hi) of block bhi
+        const float4 *p4 = reinterpret_cast<const float4 *>(wrow + VG_PB * bhi);
+        vg_add8(__ldg(p4), __ldg(p4 + 1), (1u << (hi & (VG_PB - 1))) - 1u, (double)(VG_PB * bhi) + 0.5, rs, rsy, rsyy);
+      }
+    } else {  // the interval lies inside block bhi
+      const float4 *p4 = reinterpret_cast<const float4 *>(wrow + VG_PB * bhi);
+      const unsigned keep = ((1u << (hi & (VG_PB - 1))) - 1u) & ~((1u << (lo & (VG_PB - 1))) - 1u);
+      vg_add8(__ldg(p4), __ldg(p4 + 1), keep, (double)(VG_PB * bhi) + 0.5, rs, rsy, rsyy);
     }
     const double x = (double)row + 0.5;
-    const Sum4 tot = reduce4(rs, x * rs, rsy, fma(x * x, rs, rsyy));
-    if (lane == 0) emit(a.sums, e, d.R, k, tot.m, tot.sx, tot.sy, tot.s2);
+    M += rs;
+    SX = fma(x, rs, SX);
+    SY += rsy;
+    S2 += fma(x * x, rs, rsyy);
+  }
+  const Sum4 tot = reduce4(M, SX, SY, S2);
+  if (lane == 0) {
+    double *dst = a.sums + ((size_t)e * R + k) * 4;
+    dst[0] = tot.m, dst[1] = tot.sx, dst[2] = tot.sy, dst[3] = tot.s2;
   }
 }
 

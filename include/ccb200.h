@@ -89,6 +89,8 @@ float *ccb_idf_map_dev_mut(ccb_idf *idf);
 int ccb_idf_get_map(ccb_idf *idf, float *out);       /* world_idf.h:258  GetWorldMap (D2H copy) */
 int ccb_idf_set_map(ccb_idf *idf, const float *in);  /* world_idf.h:115-127 / GetWorldMapMutable */
 const float *ccb_idf_map_dev(const ccb_idf *idf);
+/* world_idf.h:173-196 copy constructor: the generated map and its normalisation factor, device to device */
+int ccb_idf_copy_map(ccb_idf *dst, const ccb_idf *src);
 int ccb_idf_norm_factor(ccb_idf *idf, float *out);   /* world_idf.h:256 */
 /* feature records back out, for WriteDistributions (world_idf.cpp:166-195) */
 int ccb_idf_get_bnds(const ccb_idf *idf, double *out6 /* F x 6 */, int cap);
@@ -178,40 +180,10 @@ int ccb_env_local_voronoi_features(ccb_env *env, double *out);
  * the num_frontiers (pNumFrontiers) best candidate points around every robot, worst first, as
  * [dx, dy] pairs relative to the robot, zero-padded: E x R x (2 num_frontiers) */
 int ccb_env_exploration_features(ccb_env *env, int num_frontiers, double *out);
-/* Test hook, host only: the frontier queue of ccb_env_exploration_features (the kernel's own heap code
- * compiled for the host) over values[n]; candidate numbers as popped, worst first; returns their count
- * or -1.  Touches no map and no device. */
-int ccb_selftest_frontier_select(const double *values, int n, int num_frontiers, int *order_out);
-/* Test hook, host only: the separable antialiased bilinear down-sampling taps the observation kernels apply
- * (what torchvision.transforms.functional.resize(BILINEAR, antialias=True) does, coverage_env_utils.py:97-141):
- * output index o reads inputs [xmin[o], xmin[o] + xsize[o]) with weights w[o][0 .. kmax).  Returns kmax or -1. */
-int ccb_selftest_resize_weights(int L, int C, int *xmin_out, int *xsize_out, float *w_out, int w_cap);
-/* Test hook, host only: the window of size `sub` around a position as every window kernel derives it
- * (map_utils.h:51-87 ComputeOffsets): out6 = unclipped origin (ox, oy), clipped rows [x0, x1), columns [y0, y1). */
-int ccb_selftest_make_window(double res, double px, double py, int sub, int map_size, int *out6);
-/* Test hook, host only: k_vg_partition (the whole-map Voronoi's row partition, replacing voronoi.cpp:55-165
- * for the global cells) for ONE environment, its row sweep being the kernel's own code compiled for the
- * host.  pos[R][2] sites, rows [row0, row1) of an N x N map; table[R][N] = lo | hi << 16 (columns [lo, hi)
- * of the row belong to the site), flag_rows[<= N] = rows left to the per-cell rule, span[R][2] = first row /
- * last row + 1 on which the site owns a cell; band_rows = rows per CTA band (0: the kernel's default, 128).  Returns the number of flagged rows or -1.  Touches no map
- * and no device. */
-int ccb_selftest_vg_partition(const double *pos, int R, int N, double res, int row0, int row1, int band_rows,
-                              uint32_t *table, int *flag_rows, int *span);
-/* Test hook, host only: the own-cell column interval of window rows [row0, row1) as the DecentralizedCVT
- * window kernels compute it (replacing voronoi.cpp:55-150 for decentralized_cvt.h:85-143), their own code
- * compiled for the host.  px / py[K + 1]: the robot, then its K neighbours; window columns y0 .. y0 + ncols - 1.
- * lo / hi / exact[row1 - row0]; exact = the kernel applies the per-cell rule inside [lo, hi) on that row.
- * words_out (optional, 9 words): the first row's interval as mask words from column word wbase.
- * Touches no map and no device. */
-int ccb_selftest_vw_row_interval(double res, int row0, int row1, int y0, int ncols, int K, const double *px,
-                                 const double *py, int *lo, int *hi, int *exact, int wbase, uint32_t *words_out);
 /* coverage_system.h:557-571 (ratio of explored cells / IDF-weighted): 2 doubles per env */
 int ccb_env_exploration_ratios(ccb_env *env, double *out /* E x 2 */);
 int ccb_env_check_oscillation(ccb_env *env, int e, int robot, int *out); /* coverage_system.h:341-363 */
 int ccb_env_sync(ccb_env *env);
-/* diagnostics: how many map rows the last whole-map Voronoi pass resolved with the exact per-cell rule
- * (csrc/vglobal.cuh k_vg_fixup) and which (entries e * N + row, at most cap) */
-int ccb_env_flagged_rows(ccb_env *env, int *count, int *rows, int cap);
 /* raw device state for zero-copy consumers (world: E x N x N floats) */
 const float *ccb_env_world_dev(const ccb_env *env);
 const double *ccb_env_positions_dev(const ccb_env *env);
@@ -253,13 +225,7 @@ int ccb_ctrl_rollout_obs(ccb_ctrl *c, int steps, int with_objective, double *obj
                          float *obs_dev, size_t obs_step_stride);
 const double *ccb_ctrl_actions_dev(const ccb_ctrl *c);
 
-/* ---- profiling hooks (bench.py) ------------------------------------------------- */
-/* launch one kernel of the step `iters` times back to back on the env stream, bypassing caches:
- * which = 0 Voronoi label+reduce (world map), 1 same on the explored-IDF map, 2 per-robot window
- * variant, 3 sensor-window marking, 4 CNN input (C = 32, scratch_dev = E x R x 4 x 32 x 32 floats),
- * 5 cell finalisation, 6 the per-site reduce of the whole-map Voronoi alone (on the row partition a
- * previous which = 0 left), 7 its row partition alone, 8 the CNN input fused with the window Voronoi */
-int ccb_bench_kernel(ccb_env *env, int which, int iters, float *scratch_dev);
+/* kernels launched by this library so far (bench.py reports the count of its timed region) */
 uint64_t ccb_kernel_launch_count(void);
 
 #ifdef __cplusplus

@@ -10,10 +10,22 @@ import pytest
 from conftest import ROOT
 
 
-def _declared():
-    src = open(os.path.join(ROOT, "include", "ccb200.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(ccb_[a-z0-9_]+)\s*\(", src)))
+def _declared(headers=("ccb200.h", "ccb200_test.h")):
+    names = set()
+    for h in headers:
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(ccb_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
+
+
+def test_public_header_has_no_test_hooks():
+    """The drop-in boundary (include/ccb200.h) declares no self-test / profiling / option hooks: those live in
+    include/ccb200_test.h."""
+    public = _declared(("ccb200.h",))
+    assert not [n for n in public if n.startswith(("ccb_selftest_", "ccb_test_", "ccb_bench_"))]
+    hooks = set(_declared(("ccb200_test.h",))) - set(public)
+    assert {"ccb_test_set_option", "ccb_bench_kernel", "ccb_selftest_vg_partition"} <= hooks
 
 
 def test_header_declares_entry_points():
