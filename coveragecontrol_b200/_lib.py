@@ -103,6 +103,7 @@ SIGNATURES = {
     "ccb_env_local_voronoi_features": (C.c_int, [C.c_void_p, c_double_p]),
     "ccb_env_exploration_features": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "ccb_test_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "ccb_selftest_triangulate": (C.c_int, [c_double_p, C.c_int, c_double_p, C.c_int]),
     "ccb_selftest_frontier_select": (C.c_int, [c_double_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "ccb_selftest_resize_weights": (C.c_int, [C.c_int, C.c_int, c_int_p, c_int_p, c_float_p, C.c_int]),
     "ccb_selftest_make_window": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, c_int_p]),

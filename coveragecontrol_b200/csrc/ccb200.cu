@@ -197,6 +197,18 @@ extern "C" int ccb_idf_add_polygon(ccb_idf *idf, const double *xy, int n, float 
   return 0;
 }
 
+// Test hook, host only: the y-monotone pieces (triangles) the library cuts a polygon into before the kernel's
+// point-in-piece test (world_idf.cpp:125-153 does this with CGAL): lets a test hand the REFERENCE kernel the
+// same pieces.  tris_out: cap x 6 doubles; returns the number of triangles or -1.
+extern "C" int ccb_selftest_triangulate(const double *xy, int n, double *tris_out, int cap) {
+  if (n < 3) return -1;
+  std::vector<std::array<double, 6>> tris;
+  triangulate(std::vector<double>(xy, xy + 2 * n), tris);
+  if ((int)tris.size() > cap) return -1;
+  for (size_t i = 0; i < tris.size(); ++i) memcpy(tris_out + 6 * i, tris[i].data(), 6 * sizeof(double));
+  return (int)tris.size();
+}
+
 extern "C" int ccb_idf_num_features(const ccb_idf *idf) { return (int)(idf->bnds.size() + idf->polys.size()); }
 extern "C" int ccb_idf_num_bnds(const ccb_idf *idf) { return (int)idf->bnds.size(); }
 extern "C" int ccb_idf_num_polygons(const ccb_idf *idf) { return (int)idf->polys.size(); }

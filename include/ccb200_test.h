@@ -25,6 +25,10 @@ extern "C" {
  *   "ordered_sums" 1: atomic-free second-stage sums (run-to-run bit-stable moments) */
 int ccb_test_set_option(ccb_env *env, const char *name, int value);
 
+/* Test hook, host only: the triangles the library cuts a polygon feature into before the IDF kernel's
+ * point-in-piece test (the reference partitions with CGAL, world_idf.cpp:125-153; polygon_utils.cpp:38-68);
+ * xy = n x 2, tris_out = cap x 6 doubles (x0 y0 x1 y1 x2 y2); returns the number of triangles or -1. */
+int ccb_selftest_triangulate(const double *xy, int n, double *tris_out, int cap);
 /* Test hook, host only: the frontier queue of ccb_env_exploration_features (the kernel's own heap code
  * compiled for the host) over values[n]; candidate numbers as popped, worst first; returns their count
  * or -1.  Touches no map and no device. */

@@ -504,6 +504,27 @@ void orc_voronoi_bruteforce(const double *sites, int n, const float *map,
   }
 }
 
+/* Labels only, rows dealt to the OpenMP threads: the same expression and tie rule as orc_voronoi_bruteforce
+ * (argmin of dx*dx + dy*dy in fp64 without contraction, strict <, ascending site index), for maps too large
+ * for the single-threaded loop (BASELINE configs 4 and 5: 8192^2 x 256 sites, 16384^2 x 64). */
+void orc_voronoi_labels_omp(const double *sites, int n, int W, int H, double res, int *labels) {
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < W; ++i) {
+    double cx = (i + 0.5) * res;
+    for (int j = 0; j < H; ++j) {
+      double cy = (j + 0.5) * res;
+      int best = 0;
+      double bd = 0;
+      for (int k = 0; k < n; ++k) {
+        double dx = cx - sites[2 * k], dy = cy - sites[2 * k + 1];
+        double d2 = dx * dx + dy * dy;
+        if (k == 0 || d2 < bd) bd = d2, best = k;
+      }
+      labels[(size_t)i * H + j] = best;
+    }
+  }
+}
+
 /* ========================================================================== */
 /* Environment: dense maps exactly as the reference keeps them                 */
 /* ========================================================================== */
@@ -719,6 +740,25 @@ int orc_env_step_actions(orc_env *e, const double *actions) {
   }
   env_post_step(e);
   return 0;
+}
+
+/* CoverageSystem::ClearRobotMaps, coverage_system.h:399-403 -> RobotModel::ClearRobotMap, robot_model.h:180-195:
+ * refill every robot map, then re-sense at the current position (the exploration maps are kept) */
+void orc_env_clear_robot_maps(orc_env *e) {
+  const orc_params *p = &e->p;
+  size_t nn = (size_t)e->N * e->N;
+  float fill = p->pRobotMapUseUnknownImportance ? (float)(p->pUnknownImportance * p->pNorm) : 0.f;
+  for (int r = 0; r < e->R; ++r) {
+    float *rm = e->robot_map + nn * r;
+    for (size_t i = 0; i < nn; ++i) rm[i] = fill;
+    if (p->pUpdateSensorView) env_update_sensor_view(e, r);
+    if (p->pUpdateRobotMap) env_update_robot_map(e, r);
+  }
+}
+
+/* CoverageSystem::ClearExploredIDF, coverage_system.h:405-408 (system_map_ is only refreshed by the next step) */
+void orc_env_clear_explored_idf(orc_env *e) {
+  memset(e->explored_idf, 0, sizeof(float) * (size_t)e->N * e->N);
 }
 
 void orc_env_set_global_positions(orc_env *e, const double *pos) {

@@ -95,6 +95,7 @@ int orc_voronoi(const double *sites, int n, const float *map, int stride,
 void orc_voronoi_bruteforce(const double *sites, int n, const float *map,
                             int stride, int W, int H, double res, int *labels,
                             double *sums);
+void orc_voronoi_labels_omp(const double *sites, int n, int W, int H, double res, int *labels);
 /* Convex polygon of site k: rectangle [0,w]x[0,h] clipped by the bisector
  * half-planes.  Returns vertex count. */
 int orc_clip_cell(const double *sites, int n, int k, double w, double h,
@@ -107,6 +108,8 @@ orc_env *orc_env_create(const orc_params *p, const float *world_map,
 void orc_env_destroy(orc_env *e);
 int orc_env_step_actions(orc_env *e, const double *actions);
 void orc_env_set_global_positions(orc_env *e, const double *pos);
+void orc_env_clear_robot_maps(orc_env *e);
+void orc_env_clear_explored_idf(orc_env *e);
 void orc_env_get_positions(const orc_env *e, double *out);
 double orc_env_objective(orc_env *e);
 void orc_env_compute_voronoi(orc_env *e, orc_cell *cells);

@@ -92,12 +92,18 @@ def lib():
         L.orc_voronoi.argtypes = [dp, C.c_int, fp, C.c_int, C.c_double, C.c_double, C.c_double,
                                   C.c_int, C.c_int, C.POINTER(Cell)]
         L.orc_voronoi_bruteforce.argtypes = [dp, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_double, ip, dp]
+        L.orc_voronoi_labels_omp.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_double, ip]
+        L.orc_voronoi_labels_omp.restype = None
         L.orc_clip_cell.argtypes = [dp, C.c_int, C.c_int, C.c_double, C.c_double, dp, C.c_int]
         L.orc_env_create.restype = C.c_void_p
         L.orc_env_create.argtypes = [C.POINTER(Params), fp, dp, C.c_int]
         L.orc_env_destroy.argtypes = [C.c_void_p]
         L.orc_env_step_actions.argtypes = [C.c_void_p, dp]
         L.orc_env_set_global_positions.argtypes = [C.c_void_p, dp]
+        L.orc_env_clear_robot_maps.argtypes = [C.c_void_p]
+        L.orc_env_clear_robot_maps.restype = None
+        L.orc_env_clear_explored_idf.argtypes = [C.c_void_p]
+        L.orc_env_clear_explored_idf.restype = None
         L.orc_env_get_positions.argtypes = [C.c_void_p, dp]
         L.orc_env_objective.restype = C.c_double
         L.orc_env_objective.argtypes = [C.c_void_p]
@@ -219,6 +225,36 @@ def voronoi_bruteforce(sites, map2d, res=1.0):
     return labels, sums
 
 
+def voronoi_labels(sites, W: int, H: int, res=1.0):
+    """Labels of a W x H grid under the stated rule, multi-threaded (large maps); == voronoi_bruteforce's labels."""
+    sites = np.ascontiguousarray(sites, np.float64).reshape(-1, 2)
+    labels = np.zeros((W, H), np.int32)
+    lib().orc_voronoi_labels_omp(_dp(sites), len(sites), int(W), int(H), float(res), _ip(labels))
+    return labels
+
+
+def moments_from_labels(labels, map2d, sites, res=1.0, chunk_rows: int = 256):
+    """[R, 4] = (sum v, sum cx v, sum cy v, sum |c - site|^2 v) per label, fp64, accumulated over chunks of rows
+    (NumPy summation order inside a chunk; memory stays bounded for 16384^2 maps)."""
+    sites = np.ascontiguousarray(sites, np.float64).reshape(-1, 2)
+    R = len(sites)
+    W, H = labels.shape
+    out = np.zeros((R, 4))
+    cyr = (np.arange(H) + 0.5) * res
+    for r0 in range(0, W, chunk_rows):
+        r1 = min(W, r0 + chunk_rows)
+        lab = labels[r0:r1].ravel()
+        v = np.asarray(map2d[r0:r1], np.float64).ravel()
+        cx = np.repeat((np.arange(r0, r1) + 0.5) * res, H)
+        cy = np.tile(cyr, r1 - r0)
+        out[:, 0] += np.bincount(lab, v, R)
+        out[:, 1] += np.bincount(lab, v * cx, R)
+        out[:, 2] += np.bincount(lab, v * cy, R)
+        d2 = (cx - sites[lab, 0]) ** 2 + (cy - sites[lab, 1]) ** 2
+        out[:, 3] += np.bincount(lab, v * d2, R)
+    return out
+
+
 def clip_cell(sites, k, w, h):
     sites = np.ascontiguousarray(sites, np.float64).reshape(-1, 2)
     v = np.zeros(256, np.float64)
@@ -253,6 +289,12 @@ class Env:
     def set_global_positions(self, pos):
         a = np.ascontiguousarray(pos, np.float64).reshape(-1, 2)
         lib().orc_env_set_global_positions(self._h, _dp(a))
+
+    def clear_robot_maps(self):
+        lib().orc_env_clear_robot_maps(self._h)
+
+    def clear_explored_idf(self):
+        lib().orc_env_clear_explored_idf(self._h)
 
     def positions(self) -> np.ndarray:
         out = np.zeros((self.R, 2), np.float64)

@@ -107,3 +107,44 @@ def test_banded_system_step_equals_plain_rollout():
         obj = banded.step(c1, with_objective=True)
         assert np.allclose(plain.positions(), banded_env.positions(), rtol=0, atol=1e-9)
         assert obj[0] == pytest.approx(plain.objective()[0], rel=1e-10)
+
+
+def test_idf_band_with_unaligned_start_and_narrow_feature_past_a_bucket_boundary():
+    """the kernel picks its feature bucket (256 x 256 cells) from the tile origin, so tiles must
+    not straddle a bucket boundary when a band starts at a row that is no multiple of 32.  A narrow Gaussian just
+    past row 256 / column 256 (truncation box inside the next bucket only) and a band starting at row 77."""
+    import torch
+
+    import coverage_control as cc
+    from coveragecontrol_b200 import _lib
+    from coveragecontrol_b200.parallel import _wrap_dev
+
+    N = 512
+    p = cc.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    feats = [(262.4, 263.1, 1.5, 7.0), (258.2, 40.3, 0.9, 9.0), (100.7, 259.6, 1.2, 8.0), (300.0, 300.0, 30.0, 6.0)]
+
+    def make():
+        idf = cc.WorldIDF(p)
+        for mx, my, sg, sc in feats:
+            idf.AddNormalDistribution(cc.BivariateNormalDistribution(cc.Point2(mx, my), sg, sc))
+        return idf
+
+    whole = make()
+    whole.GenerateMap()
+    want = np.array(whole.GetWorldMap())
+    assert want[262, 263] > 0 and want[258, 40] > 0
+    lib = _lib.load()
+    banded = make()
+    bands = [(0, 77), (77, 250), (250, 257), (257, 512)]
+    mx = []
+    for r0, r1 in bands:
+        _lib.check(lib.ccb_idf_generate_band(banded._h, 0, r0, r1))
+        t = _wrap_dev(lib.ccb_idf_band_max_dev(banded._h), (1,), torch.int32, torch.device("cuda", 0))
+        mx.append(int(t.item()))
+    t.fill_(max(mx))
+    for r0, r1 in bands:
+        _lib.check(lib.ccb_idf_normalize_band(banded._h, r0, r1))
+    banded._host = None
+    got = np.array(banded.GetWorldMap())
+    assert np.array_equal(want.view(np.int32), got.view(np.int32))

@@ -1,0 +1,252 @@
+"""BASELINE configs 4 and 5 at their full sizes ("What's missing" 1): the kernels the library picks
+for large worlds -- tile-ordered Voronoi for R > 64, site-ordered / tile-ordered at 16384^2, the IDF kernel with
+1024 Gaussians + polygons -- against the reference's own IDF kernel (oracle/_ref) and the stated Voronoi rule
+(oracle, multi-threaded), plus pResolution != 1 through the GPU kernels.
+
+Tolerances: labels bit-exact; IDF mode 0 bit-exact vs the reference CUDA kernel; mass / centroid / objective
+rel 1e-9 here (the north-star gate is 1e-4)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _c4_features(N, n_gauss, n_poly, seed=0):
+    """The C4 generator of scripts/bench_rowband.py: Gaussians sigma 40-60, star-shaped simple polygons of 4-10
+    vertices, radius <= 64 (coverage_system.cpp:83-98)."""
+    rng = np.random.default_rng(seed)
+    bnd = np.zeros((n_gauss, 6))
+    bnd[:, 0:2] = rng.uniform(0, N, (n_gauss, 2))
+    bnd[:, 2] = bnd[:, 3] = rng.uniform(40, 60, n_gauss)
+    bnd[:, 4] = rng.uniform(6, 10, n_gauss)
+    polys = []
+    for _ in range(n_poly):
+        c = rng.uniform(64, N - 64, 2)
+        nv = int(rng.integers(4, 11))
+        ang = np.sort(rng.uniform(0, 2 * np.pi, nv))
+        rad = rng.uniform(16, 64, nv)
+        pts = np.stack([c[0] + rad * np.cos(ang), c[1] + rad * np.sin(ang)], 1)
+        polys.append((pts, float(5e-5 * rng.uniform(6, 10))))
+    return bnd, polys
+
+
+def _library_pieces(polys):
+    """The triangles the library cuts the polygons into (ccb_selftest_triangulate): what the reference kernel is
+    handed instead of CGAL's y-monotone partition -- same union, and the same pieces as the CUDA path tests."""
+    from coveragecontrol_b200 import _lib
+
+    lib = _lib.load()
+    pieces = []
+    for pts, imp in polys:
+        xy = np.ascontiguousarray(pts, np.float64)
+        out = np.zeros((len(xy), 6))
+        n = lib.ccb_selftest_triangulate(xy.ctypes.data_as(_lib.c_double_p), len(xy), out.ctypes.data_as(_lib.c_double_p), len(out))
+        assert n == len(xy) - 2
+        pieces += [(out[k].reshape(3, 2).copy(), imp) for k in range(n)]
+    return pieces
+
+
+@pytest.fixture(scope="module")
+def c4_world():
+    import coverage_control as cc
+
+    N = 8192
+    p = cc.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    p.pNumRobots = 256
+    p.pUpdateExplorationMap = False
+    p.pTimeStep = 0.2
+    bnd, polys = _c4_features(N, 1024, 64)
+    idf = cc.WorldIDF(p)
+    for b in bnd:
+        idf.AddNormalDistribution(cc.BivariateNormalDistribution(cc.Point2(b[0], b[1]), float(b[2]), float(b[4])))
+    for pts, imp in polys:
+        idf.AddUniformDistributionPolygon(cc.PolygonFeature(cc.PointVector(pts), imp))
+    idf.GenerateMap()
+    return cc, p, idf, bnd, polys
+
+
+def test_c4_idf_matches_reference_cuda_kernel_bit_for_bit(c4_world):
+    """8192^2, 1024 Gaussians + 64 star polygons: the bucketed / tabulated kernel (csrc/idf.cuh) against the
+    reference's generate_world_map.cu compiled in place, every cell and the normalisation factor."""
+    from oracle import oracle as orc
+
+    cc, p, idf, bnd, polys = c4_world
+    if not orc.ref_idf_available():
+        pytest.skip("oracle/_ref/libref_idf.so not built")
+    got = idf.GetWorldMap()
+    ref, ref_f = orc.ref_idf_generate(orc.params_from(p), bnd, polys=_library_pieces(polys))
+    diff = np.flatnonzero(got.view(np.int32).ravel() != ref.view(np.int32).ravel())
+    assert diff.size == 0, f"{diff.size} cells differ, first at {np.unravel_index(diff[:3], got.shape)}"
+    assert idf.GetNormalizationFactor() == ref_f
+    assert (got > 0).mean() > 0.3 and got.max() == pytest.approx(p.pNorm)
+    # the polygons did land: some cells carry a polygon's importance on top of the Gaussians
+    pts, imp = polys[0]
+    c = pts.mean(0).astype(int)
+    assert got[c[0], c[1]] > 0
+
+
+def _clairvoyant_step(orc, p, wm, pos):
+    """clairvoyant_cvt.h:89-127 + robot_model.h:200-243 on positions alone (the dense oracle environment would
+    need R x N^2 floats = 68 GB here): goals = centroids of the scan-line cells (voronoi.cpp:55-165)."""
+    cells = orc.voronoi(pos, wm, res=p.pResolution)
+    goals = np.array([list(c.centroid) for c in cells])
+    d = goals - pos
+    dist = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])
+    speed = np.minimum(dist / p.pTimeStep, p.pMaxRobotSpeed)
+    act = np.zeros_like(pos)
+    mv = dist >= 1e-10
+    act[mv] = d[mv] / dist[mv, None] * speed[mv, None]
+    new = pos + act * p.pTimeStep
+    hi = p.pWorldMapSize * p.pResolution
+    new = np.where(new <= 0, 1e-4, new)
+    new = np.where(new >= hi, hi - 1e-4, new)
+    return goals, new, cells
+
+
+def test_c4_labels_moments_and_clairvoyant_steps(c4_world):
+    """R = 256 > 64 sites: the tile-ordered kernel (csrc/voronoi.cuh).  Labels bit for bit against the stated rule,
+    moments against sums over those labels, then 5 ClairvoyantCVT steps against the scan-line oracle."""
+    from coverage_control.algorithms import ClairvoyantCVT
+    from oracle import oracle as orc
+
+    cc, p, idf, _, _ = c4_world
+    N, R = p.pWorldMapSize, p.pNumRobots
+    wm = np.array(idf.GetWorldMap())
+    pos = np.random.default_rng(1).uniform(1e-4, N - 1e-4, (R, 2))
+    env = cc.CoverageSystem(p, idf, cc.PointVector(pos))
+    labels = env.voronoi_labels(0)[0]
+    ref_labels = orc.voronoi_labels(pos, N, N)
+    bad = np.flatnonzero(labels.ravel() != ref_labels.ravel())
+    assert bad.size == 0, f"{bad.size} labels differ, first at {np.unravel_index(bad[:3], labels.shape)}"
+    sums = orc.moments_from_labels(ref_labels, wm, pos)
+    del labels, ref_labels
+    cells = env.GetVoronoiCells()
+    mass = np.array([c.mass for c in cells])
+    assert np.allclose(mass, sums[:, 0], rtol=1e-9, atol=1e-12)
+    cen = np.array([list(c.centroid) for c in cells])
+    ok = sums[:, 0] >= 1e-10
+    assert np.allclose(cen[ok], sums[ok, 1:3] / sums[ok, :1], rtol=1e-9, atol=1e-7)
+    assert env.GetObjectiveValue() == pytest.approx(sums[:, 3].sum(), rel=1e-9)
+    ctrl = ClairvoyantCVT(p, env)
+    for _ in range(5):
+        ctrl.ComputeActions()
+        goals, pos, ocells = _clairvoyant_step(orc, p, wm, pos)
+        assert np.allclose(np.array(ctrl.GetGoals()), goals, rtol=1e-4, atol=1e-6)  # north-star gate on centroids
+        env.StepActions(ctrl.GetActions())
+        assert np.allclose(np.array(env.GetRobotPositions()), pos, rtol=0, atol=1e-6)
+    obj = sum(c.sum_idf_site_dist_sqr for c in orc.voronoi(pos, wm))
+    assert env.GetObjectiveValue() == pytest.approx(obj, rel=1e-4)
+
+
+@pytest.mark.parametrize("N,R,generic", [(16384, 64, 0), (16384, 64, 1), (2048, 1024, 1), (4096, 16, 0), (512, 1024, 1)])
+def test_c5_corners_labels_and_moments(monkeypatch, N, R, generic):
+    """Corners of the C5 sweep (512^2 - 16384^2 x 16 - 1024 robots): site-ordered (generic = 0, R <= 64) and
+    tile-ordered (generic = 1) whole-map Voronoi at sizes far beyond the other tests' 1024^2."""
+    import coverage_control as cc
+    from oracle import oracle as orc
+
+    monkeypatch.setenv("CCB_VG_GENERIC", str(generic))
+    rng = np.random.default_rng(N + R)
+    pos = rng.uniform(1e-4, N - 1e-4, (R, 2))
+    p = cc.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    p.pNumRobots = R
+    wm = rng.random((N, N), dtype=np.float32)
+    wm[: N // 3, : N // 2] = 0.0  # a zero block: cells of zero mass take the vertex-mean fallback
+    env = cc.CoverageSystem(p, cc.WorldIDF(p, wm), cc.PointVector(pos))
+    labels = env.voronoi_labels(0)[0]
+    ref_labels = orc.voronoi_labels(pos, N, N)
+    bad = np.flatnonzero(labels.ravel() != ref_labels.ravel())
+    assert bad.size == 0, f"{bad.size} labels differ, first at {np.unravel_index(bad[:3], labels.shape)}"
+    del labels
+    sums = orc.moments_from_labels(ref_labels, wm, pos)
+    del ref_labels
+    cells = env.GetVoronoiCells()
+    mass = np.array([c.mass for c in cells])
+    assert np.allclose(mass, sums[:, 0], rtol=1e-9, atol=1e-9)
+    assert np.all(mass[sums[:, 0] == 0.0] == 0.0)
+    cen = np.array([list(c.centroid) for c in cells])
+    ok = sums[:, 0] >= 1e-10
+    assert np.allclose(cen[ok], sums[ok, 1:3] / sums[ok, :1], rtol=1e-9, atol=1e-7)
+    assert env.GetObjectiveValue() == pytest.approx(sums[:, 3].sum(), rel=1e-9)
+
+
+@pytest.mark.parametrize("res", [0.5, 2.0])
+@pytest.mark.parametrize("kind,name", [(0, "ClairvoyantCVT"), (1, "CentralizedCVT"), (2, "DecentralizedCVT")])
+def test_resolution_other_than_one(monkeypatch, res, kind, name):
+    """pResolution in {0.5, 2} through the GPU kernels: IDF, window marking, the three
+    Voronoi kernels (whole map site-ordered and tile-ordered, robot windows), observation, roll-out -- step by
+    step against the dense oracle environment."""
+    import coverage_control as cc
+    import coverage_control.algorithms as algs
+    from oracle import oracle as orc
+
+    N, R, steps = 512, 9, 12
+    p = cc.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    p.pNumRobots = R
+    p.pResolution = res
+    p.pLocalMapSize = 256  # with C = 32 the fused observation kernels (csrc/obs.cuh k_cnn_fused8) apply
+    p.pSensorSize = 32
+    p.pCommunicationRange = 60.0 * res
+    p.pMaxRobotSpeed = 4.0 * res
+    rng = np.random.default_rng(int(res * 10) + kind)
+    bnd = np.zeros((7, 6))
+    bnd[:, 0:2] = rng.uniform(0, N * res, (7, 2))
+    bnd[:, 2] = bnd[:, 3] = rng.uniform(15 * res, 30 * res, 7)
+    bnd[:, 4] = rng.uniform(6, 10, 7)
+    pos = rng.uniform(1e-3, N * res - 1e-3, (R, 2))
+    op = orc.params_from(p)
+    idf = cc.WorldIDF(p)
+    for b in bnd:
+        idf.AddNormalDistribution(cc.BivariateNormalDistribution(cc.Point2(b[0], b[1]), float(b[2]), float(b[4])))
+    idf.GenerateMap()
+    wm = np.array(idf.GetWorldMap())
+    if orc.ref_idf_available():  # the reference's own kernel at this resolution (N is a multiple of 32)
+        ref, ref_f = orc.ref_idf_generate(op, bnd)
+        assert np.array_equal(wm, ref) and idf.GetNormalizationFactor() == ref_f
+    ref_cpu, _ = orc.idf_generate(op, bnd, mode=1)
+    assert np.allclose(wm, ref_cpu, atol=1e-2)
+    for generic in (0, 1):  # both whole-map kernels at this resolution
+        monkeypatch.setenv("CCB_VG_GENERIC", str(generic))
+        e2 = cc.CoverageSystem(p, idf, cc.PointVector(pos))
+        lab = e2.voronoi_labels(0)[0]
+        ref_lab, ref_sums = orc.voronoi_bruteforce(pos, wm, res=res)
+        assert np.array_equal(lab, ref_lab)
+        assert np.allclose([c.mass for c in e2.GetVoronoiCells()], ref_sums[:, 0], rtol=1e-9, atol=1e-12)
+        assert e2.GetObjectiveValue() == pytest.approx(ref_sums[:, 3].sum(), rel=1e-9)
+    monkeypatch.delenv("CCB_VG_GENERIC")
+    env = cc.CoverageSystem(p, idf, cc.PointVector(pos))
+    oenv = orc.Env(op, wm, pos)
+    ctrl = getattr(algs, name)(p, env)
+    for s in range(steps):
+        ctrl.ComputeActions()
+        a = np.array(ctrl.GetActions())
+        _, oa, og = oenv.compute_actions(kind)
+        assert np.allclose(np.array(ctrl.GetGoals()), og, rtol=1e-4, atol=1e-6), s
+        assert np.allclose(a, oa, rtol=1e-4, atol=1e-6), s
+        env.StepActions(ctrl.GetActions())
+        oenv.step_actions(oa)
+        assert np.allclose(np.array(env.GetRobotPositions()), oenv.positions(), atol=1e-7)
+        if kind == 2 and s % 2 == 0:  # the next ComputeActions takes its window moments from the fused kernel
+            cc.CoverageEnvUtils.get_maps(env, p, 32, True)
+    assert env.GetObjectiveValue() == pytest.approx(oenv.objective(), rel=1e-4)
+    assert np.array_equal(env.GetSystemMap(), oenv.system_map())
+    for r in (0, R - 1):
+        assert np.array_equal(env.GetRobotLocalMap(r), oenv.local_map(r))
+        assert np.array_equal(env.GetRobotObstacleMap(r), oenv.obstacle_map(r))
+        assert np.array_equal(env.GetRobotMap(r), oenv.robot_map(r))
+    obs = cc.CoverageEnvUtils.get_maps(env, p, 32, True, device="cpu").numpy()
+    import torch
+    import torchvision
+
+    rs = lambda t: torchvision.transforms.functional.resize(  # noqa: E731
+        t, (32, 32), interpolation=torchvision.transforms.InterpolationMode.BILINEAR, antialias=True)
+    loc = rs(torch.from_numpy(np.stack([oenv.local_map(r) for r in range(R)]))).numpy()
+    obst = rs(torch.from_numpy(np.stack([oenv.obstacle_map(r) for r in range(R)]))).numpy()
+    comm = np.stack([np.stack(oenv.comm_maps(r, 32, "py")) for r in range(R)])
+    assert np.allclose(obs[:, 0], loc, atol=1e-5) and np.allclose(obs[:, 3], obst, atol=1e-5)
+    assert np.allclose(obs[:, 1:3], comm, atol=1e-6)

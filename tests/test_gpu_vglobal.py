@@ -117,30 +117,34 @@ def test_cell_polygon_with_more_vertices_than_a_warp():
         assert c.mass == pytest.approx(o.mass, rel=1e-9)
 
 
-@pytest.mark.skipif(os.environ.get("CCB_TEST_EXPERIMENTAL") != "1",
-                    reason="opt-in path (CCB_VG_PREFIX=1), written without GPU time left in round 1: run with CCB_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("prefix", [1, 0])
 @pytest.mark.parametrize("kind,N,R,seed", [("random", 1024, 32, 0), ("random", 512, 64, 1), ("cluster", 256, 48, 2),
-                                           ("lattice", 256, 36, 3), ("halfint", 512, 24, 4), ("random", 300, 2, 5)])
-def test_row_prefix_path_matches_oracle(monkeypatch, kind, N, R, seed):
-    """CCB_VG_PREFIX=1: k_vg_lookup (differences of fp64 row prefix sums, vglobal.cuh) instead of k_vg_reduce.
-    Moments within 1e-9 of the oracle (the gate of SURVEY 8d is 1e-4); a half map of zeros keeps the mass of the
-    sites on it at exactly 0 (vertex-mean fallback, voronoi.cpp:143-150); setting a new world map refreshes the
-    prefixes."""
+                                           ("lattice", 256, 36, 3), ("halfint", 512, 24, 4), ("random", 304, 2, 5)])
+def test_block_prefix_path_matches_oracle(monkeypatch, prefix, kind, N, R, seed):
+    """k_vg_lookup (block prefix sums in double-double + head / tail cells, vglobal.cuh; the default for the
+    site-ordered world-map moments) and the streaming k_vg_reduce it replaces (prefix = 0): moments within 1e-9 of
+    the oracle (the gate of SURVEY 8d is 1e-4); a half map of zeros keeps the mass of the sites on it at exactly 0
+    (vertex-mean fallback, voronoi.cpp:143-150); setting a new world map refreshes the prefixes."""
     import coverage_control as cc
     from oracle import oracle as orc
 
     monkeypatch.setenv("CCB_VG_GENERIC", "0")
-    monkeypatch.setenv("CCB_VG_PREFIX", "1")
+    monkeypatch.setenv("CCB_VG_PREFIX", str(prefix))
     rng = np.random.default_rng(seed)
     pos = _sites(kind, N, R, rng)
     p = cc.Parameters()
     p.pWorldMapSize = p.pRobotMapSize = N
     p.pNumRobots = R
-    for variant in range(2):
+    env = None
+    for variant in range(3):
         wm = rng.random((N, N)).astype(np.float32)
         if variant == 1:
             wm[:, : N // 2] = 0.0
-        env = cc.CoverageSystem(p, cc.WorldIDF(p, wm), cc.PointVector(pos))
+        if variant < 2:
+            env = cc.CoverageSystem(p, cc.WorldIDF(p, wm), cc.PointVector(pos))
+        else:  # a new map in the SAME environment: the stale prefixes must not survive
+            env.GetWorldMapMutable()[...] = wm
+            env.StepActions(np.zeros((R, 2)))
         _, ref_sums = orc.voronoi_bruteforce(pos, wm)
         cells = env.GetVoronoiCells()
         mass = np.array([c.mass for c in cells])
@@ -151,3 +155,40 @@ def test_row_prefix_path_matches_oracle(monkeypatch, kind, N, R, seed):
         ocells = oenv.voronoi_cells()
         for c, oc in zip(cells, ocells):
             assert np.allclose(np.array(c.centroid), np.array(oc.centroid[:]), rtol=1e-9, atol=1e-7)
+
+
+@pytest.mark.parametrize("prefix", [1, 0])
+def test_low_mass_cell_behind_a_heavy_row_prefix(monkeypatch, prefix):
+    """A cell whose whole mass is ~1e-9 / ~1e-11 at the END of rows whose running sums are ~1e3:
+    plain fp64 prefix differences would lose it (ulp(1e3) ~ 1e-13) and could flip the `mass < 1e-10` vertex-mean
+    fallback of voronoi.cpp:41-53; the double-double entries + direct head / tail sums must not.  The site owns the
+    last columns of the map only: heavy cells up to column N - 24, then a few tiny ones."""
+    import coverage_control as cc
+    from oracle import oracle as orc
+
+    monkeypatch.setenv("CCB_VG_GENERIC", "0")
+    monkeypatch.setenv("CCB_VG_PREFIX", str(prefix))
+    N = 1024
+    p = cc.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    rng = np.random.default_rng(12)
+    # site 0 at the right edge, walled off by a line of sites 40 columns before it: its cell stays in the columns
+    # >= N - 28; the other sites share the heavy part of the map
+    wall = np.stack([np.arange(384.0, 641.0, 32.0) + 0.3, np.full(9, N - 44.2)], 1)
+    pos = np.concatenate([[[512.3, N - 4.2]], wall, [[500.2, 300.6], [130.9, 700.2], [880.5, 520.1], [60.2, 980.4], [990.1, 1000.3]]])
+    p.pNumRobots = len(pos)
+    for tiny, expect_fallback in ((1e-12, False), (2e-14, True)):
+        wm = (rng.random((N, N)).astype(np.float32) * 2.0 + 1.0)  # running row sums ~2e3
+        wm[:, N - 40:] = 0.0
+        wm[:, N - 13:N - 3] = np.float32(tiny) * (1.0 + rng.random((N, 10)).astype(np.float32))
+        env = cc.CoverageSystem(p, cc.WorldIDF(p, wm), cc.PointVector(pos))
+        labels, ref_sums = orc.voronoi_bruteforce(pos, wm)
+        assert (labels[:, : N - 40] != 0).all()  # the cell of site 0 sees none of the heavy cells
+        assert 0 < ref_sums[0, 0] < 1e-8 and (ref_sums[0, 0] < 1e-10) == expect_fallback
+        cells = env.GetVoronoiCells()
+        ocells = orc.voronoi(pos, wm)
+        for k, (c, oc) in enumerate(zip(cells, ocells)):
+            assert c.mass == pytest.approx(ref_sums[k, 0], rel=1e-9), k
+            # north-star gate (1e-4 on centroids), far inside it here; the fallback cell takes the vertex mean
+            assert np.allclose(np.array(c.centroid), np.array(oc.centroid[:]), rtol=1e-9, atol=1e-7), k
+        assert env.GetObjectiveValue() == pytest.approx(ref_sums[:, 3].sum(), rel=1e-9)

@@ -166,3 +166,87 @@ def test_local_voronoi_features_match_oracle():
         want = [cell.centroid[0], cell.centroid[1], cell.mass, cell.sum_idf_site_dist_sqr, 0.0, cell.sum_idf_site_dist, 0.0]
         assert np.allclose(feats[r], want, rtol=1e-6, atol=1e-6), (r, feats[r], want)
         assert np.allclose(list(env.GetLocalVoronoiFeatures(r)), feats[r])
+
+
+
+
+def _clear_setup(R, seed):
+    import coverage_control as cc
+    from oracle import oracle as orc
+
+    N = 512
+    p = cc.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    p.pNumRobots = R
+    p.pLocalMapSize = 256
+    p.pSensorSize = 32
+    p.pCommunicationRange = 128.0
+    bnd, pos = random_world(seed, N, 9, R, sigma=(50.0, 80.0))
+    op = orc.params_from(p)
+    wm, _ = orc.idf_generate(op, bnd, mode=1)
+    return cc, orc, p, op, wm, pos
+
+
+def test_clear_robot_maps_invalidates_the_fused_window_moments():
+    """the observation kernel's VOR variant caches DecentralizedCVT's window moments for the
+    current positions; ClearRobotMaps / ClearExploredIDF (coverage_system.h:399-408, called mid-run by the
+    reference's evaluators) change the robot maps without moving a robot, so the cache must not survive them.
+    Step by step against the dense oracle environment, clearing after get_maps and before ComputeActions."""
+    from coverage_control.algorithms import DecentralizedCVT
+
+    R = 10
+    cc, orc, p, op, wm, pos = _clear_setup(R, 21)
+    env = cc.CoverageSystem(p, cc.WorldIDF(p, wm), cc.PointVector(pos))
+    oenv = orc.Env(op, wm, pos)
+    ctrl = DecentralizedCVT(p, env)
+    for s in range(14):
+        cc.CoverageEnvUtils.get_maps(env, p, 32, True)  # leaves the window moments of these positions behind
+        if s in (6, 9):
+            env.ClearRobotMaps(), oenv.clear_robot_maps()
+            if s == 9:
+                env.ClearExploredIDF(), oenv.clear_explored_idf()
+            for r in (0, R - 1):
+                assert np.array_equal(env.GetRobotMap(r), oenv.robot_map(r))
+        ctrl.ComputeActions()
+        _, oa, og = oenv.compute_actions(2)
+        assert np.allclose(np.array(ctrl.GetGoals()), og, rtol=1e-9, atol=1e-7), f"goals, step {s}"
+        env.StepActions(ctrl.GetActions())
+        oenv.step_actions(oa)
+    assert np.array_equal(env.GetSystemMap(), oenv.system_map())
+    assert np.array_equal(env.GetRobotMap(3), oenv.robot_map(3))
+
+
+def test_clear_robot_maps_between_graph_replays():
+    """The same through the device roll-out, whose second identical call is captured into a CUDA graph and later
+    ones replay it: a clear between two replays must reach the replayed kernels (the graph is keyed on which cached
+    results are valid on entry)."""
+    import torch
+
+    from coveragecontrol_b200 import BatchedCoverageSystem, BatchedCVT, _lib
+
+    R, E = 8, 3
+    cc, orc, p, op, wm, _ = _clear_setup(R, 22)
+    pos = np.random.default_rng(5).uniform(1, 511, (E, R, 2))
+    env = BatchedCoverageSystem(p, E, R)
+    for e in range(E):
+        env.set_world(e, wm)
+    env.reset(pos)
+    ctrl = BatchedCVT(env, 2)
+    oenvs = [orc.Env(op, wm, pos[e]) for e in range(E)]
+    obs = torch.zeros((E, R, 4, 32, 32), device="cuda")
+    obj = torch.zeros((1, E), dtype=torch.float64, device="cuda")
+    lib = _lib.load()
+    for s in range(12):
+        ctrl.rollout_obs(1, True, obj.data_ptr(), 32, True, obs.data_ptr(), 0)
+        for oe in oenvs:
+            _, oa, _ = oe.compute_actions(2)
+            oe.step_actions(oa)
+        if s in (5, 8):  # after the graph exists (calls 0 and 1 are eager / capture)
+            _lib.check(lib.ccb_env_clear_robot_maps(env._h, 1))
+            oenvs[1].clear_robot_maps()
+        got = env.positions()
+        for e in range(E):
+            assert np.allclose(got[e], oenvs[e].positions(), atol=1e-7), f"positions, step {s}, env {e}"
+    torch.cuda.synchronize()
+    for e in range(E):
+        assert float(obj[0, e]) == pytest.approx(oenvs[e].objective(), rel=1e-9)
