@@ -131,6 +131,9 @@ SIGNATURES = {
     "ccb_ctrl_rollout_obs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "ccb_ctrl_actions_dev": (C.c_void_p, [C.c_void_p]),
     "ccb_bench_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ccb_bench_idf_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
+    "ccb_bench_fp32_peak": (C.c_int, [C.c_int, c_double_p]),
+    "ccb_test_count": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
     "ccb_kernel_launch_count": (C.c_uint64, []),
 }
 

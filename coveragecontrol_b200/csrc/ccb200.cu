@@ -240,16 +240,17 @@ static int idf_finish(ccb_idf *idf, int row0, int row1) {
   return 0;
 }
 
-// rows [row0, row1) of the map; finish = compute the factor from the map maximum and normalise
-static int idf_generate_rows(ccb_idf *idf, int mode, int row0, int row1, bool finish) {
-  if (mode != 0 && mode != 1) return fail("ccb_idf_generate: mode must be 0 or 1");
-  CCB_CUDA(cudaSetDevice(idf->device));
+// everything the integration kernel reads, packed on the host as ONE blob (one allocation, one copy)
+struct IdfInputs {
+  std::vector<unsigned char> blob;
+  size_t o_b = 0, o_bs = 0, o_bi = 0, o_px = 0, o_py = 0, o_imp = 0, o_start = 0, o_sz = 0, o_bounds = 0;
+  int F = 0, NP = 0, bk_nb = 0, bk_size = 0;
+};
+
+static void idf_pack_inputs(const ccb_idf *idf, IdfInputs &in) {
   const ccb_params &p = idf->p;
   const int N = p.pWorldMapSize;
-  if (row0 < 0 || row1 > N || row0 > row1) return fail("ccb_idf_generate: bad row band");
   const int F = (int)idf->bnds.size();
-  cudaStream_t st = idf->stream;
-
   // feature records, fp32 as the reference packs them (world_idf.cpp:111-123)
   std::vector<BndF> hb(std::max(F, 1));
   for (int i = 0; i < F; ++i) {
@@ -309,7 +310,7 @@ static int idf_generate_rows(ccb_idf *idf, int mode, int row0, int row1, bool fi
   }
   // everything the kernel reads goes up in ONE blob (one allocation, one copy): the order counter for the
   // maximum, the feature records, the bucket grid and the polygon pieces, each section 16-byte aligned
-  std::vector<unsigned char> blob;
+  std::vector<unsigned char> &blob = in.blob;
   auto put = [&blob](const void *src, size_t bytes) -> size_t {
     const size_t off = (blob.size() + 15) & ~(size_t)15;
     blob.resize(off + bytes);
@@ -323,33 +324,123 @@ static int idf_generate_rows(ccb_idf *idf, int mode, int row0, int row1, bool fi
   const size_t o_imp = put(imp.data(), sizeof(float) * imp.size());
   const size_t o_start = put(start.data(), sizeof(int) * start.size()), o_sz = put(sz.data(), sizeof(int) * sz.size());
   const size_t o_bounds = put(bounds.data(), sizeof(float4) * bounds.size());
-  unsigned char *d_blob = nullptr;
-  CCB_CUDA(cudaMallocAsync(&d_blob, blob.size(), st));
-  CCB_CUDA(cudaMemcpyAsync(d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
-  const BndF *d_b = reinterpret_cast<const BndF *>(d_blob + o_b);
-  const int *d_bk_start = reinterpret_cast<const int *>(d_blob + o_bs), *d_bk_items = reinterpret_cast<const int *>(d_blob + o_bi);
-  PolyDev pd{reinterpret_cast<const float *>(d_blob + o_px), reinterpret_cast<const float *>(d_blob + o_py),
-             reinterpret_cast<const int *>(d_blob + o_start), reinterpret_cast<const int *>(d_blob + o_sz),
-             reinterpret_cast<const float *>(d_blob + o_imp), reinterpret_cast<const float4 *>(d_blob + o_bounds), NP};
+  in.o_b = o_b, in.o_bs = o_bs, in.o_bi = o_bi, in.o_px = o_px, in.o_py = o_py, in.o_imp = o_imp;
+  in.o_start = o_start, in.o_sz = o_sz, in.o_bounds = o_bounds;
+  in.F = F, in.NP = NP, in.bk_nb = bk_nb, in.bk_size = bk_size;
+}
 
-  const int init = (int)0x80000000;
-  CCB_CUDA(cudaMemcpyAsync(idf->d_max, &init, sizeof(int), cudaMemcpyHostToDevice, st));
+static int idf_launch_kernel(ccb_idf *idf, const IdfInputs &in, const unsigned char *bl, int mode, int row0, int row1) {
+  const ccb_params &p = idf->p;
+  const int N = p.pWorldMapSize;
+  PolyDev pd{reinterpret_cast<const float *>(bl + in.o_px), reinterpret_cast<const float *>(bl + in.o_py),
+             reinterpret_cast<const int *>(bl + in.o_start), reinterpret_cast<const int *>(bl + in.o_sz),
+             reinterpret_cast<const float *>(bl + in.o_imp), reinterpret_cast<const float4 *>(bl + in.o_bounds), in.NP};
+  const BndF *d_b = reinterpret_cast<const BndF *>(bl + in.o_b);
+  const int *d_bk_start = reinterpret_cast<const int *>(bl + in.o_bs), *d_bk_items = reinterpret_cast<const int *>(bl + in.o_bi);
   const float res = (float)p.pResolution;
   const float trun = (float)p.pTruncationBND;
   const float trun_sq = trun * trun;                       // generate_world_map.cu:188-189
   const float one_by_sqrt2 = (float)(1. / std::sqrt(2.));  // generate_world_map.cu:190-192
-  if (row1 > row0) {
-    dim3 grid((N + IDF_TY - 1) / IDF_TY, (row1 - (row0 & ~(IDF_TX - 1)) + IDF_TX - 1) / IDF_TX);
-    if (mode == 0)
-      k_idf_generate<0><<<grid, IDF_THREADS, 0, st>>>(d_b, F, d_bk_start, d_bk_items, bk_nb, bk_size, pd, N, row0, row1, res, trun_sq,
-                                                     one_by_sqrt2, idf->d_map, idf->d_max);
-    else
-      k_idf_generate<1><<<grid, IDF_THREADS, 0, st>>>(d_b, F, d_bk_start, d_bk_items, bk_nb, bk_size, pd, N, row0, row1, res, trun_sq,
-                                                     one_by_sqrt2, idf->d_map, idf->d_max);
-    CCB_LAUNCH_CHECK();
-  }
+  if (row1 <= row0) return 0;
+  dim3 grid((N + IDF_TY - 1) / IDF_TY, (row1 - (row0 & ~(IDF_TX - 1)) + IDF_TX - 1) / IDF_TX);
+  if (mode == 0)
+    k_idf_generate<0><<<grid, IDF_THREADS, 0, idf->stream>>>(d_b, in.F, d_bk_start, d_bk_items, in.bk_nb, in.bk_size, pd, N, row0, row1, res,
+                                                            trun_sq, one_by_sqrt2, idf->d_map, idf->d_max);
+  else
+    k_idf_generate<1><<<grid, IDF_THREADS, 0, idf->stream>>>(d_b, in.F, d_bk_start, d_bk_items, in.bk_nb, in.bk_size, pd, N, row0, row1, res,
+                                                            trun_sq, one_by_sqrt2, idf->d_map, idf->d_max);
+  CCB_LAUNCH_CHECK();
+  return 0;
+}
+
+// rows [row0, row1) of the map; finish = compute the factor from the map maximum and normalise
+static int idf_generate_rows(ccb_idf *idf, int mode, int row0, int row1, bool finish) {
+  if (mode != 0 && mode != 1) return fail("ccb_idf_generate: mode must be 0 or 1");
+  CCB_CUDA(cudaSetDevice(idf->device));
+  const int N = idf->p.pWorldMapSize;
+  if (row0 < 0 || row1 > N || row0 > row1) return fail("ccb_idf_generate: bad row band");
+  cudaStream_t st = idf->stream;
+  IdfInputs in;
+  idf_pack_inputs(idf, in);
+  unsigned char *d_blob = nullptr;
+  CCB_CUDA(cudaMallocAsync(&d_blob, in.blob.size(), st));
+  CCB_CUDA(cudaMemcpyAsync(d_blob, in.blob.data(), in.blob.size(), cudaMemcpyHostToDevice, st));
+  const int init = (int)0x80000000;
+  CCB_CUDA(cudaMemcpyAsync(idf->d_max, &init, sizeof(int), cudaMemcpyHostToDevice, st));
+  if (idf_launch_kernel(idf, in, d_blob, mode, row0, row1)) return 1;
   if (finish && idf_finish(idf, row0, row1)) return 1;
   CCB_CUDA(cudaFreeAsync(d_blob, st));
+  return 0;
+}
+
+// Profiling hook: the integration kernel alone, `iters` times over the whole map (inputs uploaded before the timed
+// region; no maximum / normalise pass: the map is left un-normalised).  *ms_out = mean kernel time, CUDA events.
+extern "C" int ccb_bench_idf_kernel(ccb_idf *idf, int mode, int iters, float *ms_out) {
+  if (mode != 0 && mode != 1) return fail("ccb_bench_idf_kernel: mode must be 0 or 1");
+  if (iters < 1) return fail("ccb_bench_idf_kernel: iters must be positive");
+  CCB_CUDA(cudaSetDevice(idf->device));
+  cudaStream_t st = idf->stream;
+  IdfInputs in;
+  idf_pack_inputs(idf, in);
+  unsigned char *d_blob = nullptr;
+  CCB_CUDA(cudaMalloc(&d_blob, in.blob.size()));
+  CCB_CUDA(cudaMemcpyAsync(d_blob, in.blob.data(), in.blob.size(), cudaMemcpyHostToDevice, st));
+  cudaEvent_t e0, e1;
+  CCB_CUDA(cudaEventCreate(&e0));
+  CCB_CUDA(cudaEventCreate(&e1));
+  const int N = idf->p.pWorldMapSize;
+  int rc = idf_launch_kernel(idf, in, d_blob, mode, 0, N);  // warm-up
+  if (!rc) {
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < iters && !rc; ++i) rc = idf_launch_kernel(idf, in, d_blob, mode, 0, N);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / iters;
+  }
+  cudaEventDestroy(e0), cudaEventDestroy(e1), cudaFree(d_blob);
+  return rc;
+}
+
+// Profiling hook: the FP32 FMA rate this GPU sustains (the denominator of the IDF kernel's roofline; there is no
+// FP32 figure in MEASURED_PEAKS.json).  148 x 8 CTAs of 256 threads, 8 independent FFMA chains per thread.
+__global__ void __launch_bounds__(256) k_fp32_peak(float *out, int n, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fmaf(x0, a, b), x1 = fmaf(x1, a, b), x2 = fmaf(x2, a, b), x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b), x5 = fmaf(x5, a, b), x6 = fmaf(x6, a, b), x7 = fmaf(x7, a, b);
+    }
+  }
+  const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 123.456f) out[0] = s;  // keeps the chains alive
+}
+extern "C" int ccb_bench_fp32_peak(int device, double *tflops_out) {
+  if (require_gpu()) return 1;
+  CCB_CUDA(cudaSetDevice(device));
+  float *d_out = nullptr;
+  CCB_CUDA(cudaMalloc(&d_out, sizeof(float)));
+  cudaEvent_t e0, e1;
+  CCB_CUDA(cudaEventCreate(&e0));
+  CCB_CUDA(cudaEventCreate(&e1));
+  const int n = 4096, ctas = 148 * 8;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    CCB_CUDA(cudaEventRecord(e0, 0));
+    k_fp32_peak<<<ctas, 256>>>(d_out, n, 0.999f, 0.001f);
+    CCB_CUDA(cudaEventRecord(e1, 0));
+    CCB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CCB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8 * 16 * (double)n * 256 * ctas;
+    if (rep >= 1) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  g_launches.fetch_add(6);
+  cudaEventDestroy(e0), cudaEventDestroy(e1), cudaFree(d_out);
+  *tflops_out = best;
   return 0;
 }
 
@@ -1662,6 +1753,50 @@ extern "C" int ccb_env_flagged_rows(ccb_env *env, int *count, int *rows, int cap
   CCB_CUDA(cudaMemcpy(count, env->d_vg_flag, sizeof(int), cudaMemcpyDeviceToHost));
   const int n = std::min(*count, cap);
   if (rows && n > 0) CCB_CUDA(cudaMemcpy(rows, env->d_vg_flag + 1, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// Diagnostics for the roofline arithmetic (include/ccb200_test.h): what = 0 -> cells of the robots' local windows
+// that their robot maps have seen (the cells the observation / window-Voronoi kernels must read), summed over all
+// robots and environments; what = 1 -> (site, row) pairs with cells in the last site-ordered partition.
+__global__ void k_count_window_seen(EnvDev d, unsigned long long *out) {
+  const int r = blockIdx.x, e = blockIdx.y;
+  const size_t er = (size_t)e * d.R + r;
+  const Window w = make_window(d.res, d.pos_g[2 * er], d.pos_g[2 * er + 1], d.L, d.N);
+  const uint32_t *plane = robot_plane(d, d.seenb, e, r);
+  unsigned long long n = 0;
+  const int w0 = w.y0 >> 5, w1 = (w.y1 + 31) >> 5;
+  for (int t = threadIdx.x; t < (w.x1 - w.x0) * (w1 - w0); t += blockDim.x) {
+    const int row = w.x0 + t / (w1 - w0), wd = w0 + t % (w1 - w0);
+    n += __popc(__ldg(plane + (size_t)row * d.NW + wd) & vw_range_bits(w.y0, w.y1, wd << 5));
+  }
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, n);
+}
+__global__ void k_count_pairs(const uint32_t *table, size_t n, unsigned long long *out) {
+  unsigned long long c = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t iv = __ldg(table + i);
+    c += (iv >> 16) > (iv & 0xffffu) ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+extern "C" int ccb_test_count(ccb_env *env, int what, uint64_t *out) {
+  if (!env->initialised) return fail("environment has no robot positions yet");
+  CCB_CUDA(cudaSetDevice(env->device));
+  CCB_CUDA(cudaStreamSynchronize(env->aux));
+  unsigned long long *d_n = reinterpret_cast<unsigned long long *>(env->d_ratio);
+  CCB_CUDA(cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), env->stream));
+  const EnvDev &d = env->d;
+  if (what == 0) k_count_window_seen<<<dim3(d.R, d.E), 256, 0, env->stream>>>(d, d_n);
+  else if (what == 1 && env->d_vg_table) k_count_pairs<<<148 * 8, 256, 0, env->stream>>>(env->d_vg_table, (size_t)d.E * d.R * d.N, d_n);
+  else return fail("ccb_test_count: unknown counter (or no partition yet)");
+  CCB_LAUNCH_CHECK();
+  unsigned long long h = 0;
+  CCB_CUDA(cudaMemcpyAsync(&h, d_n, sizeof h, cudaMemcpyDeviceToHost, env->stream));
+  CCB_CUDA(cudaStreamSynchronize(env->stream));
+  *out = h;
   return 0;
 }
 

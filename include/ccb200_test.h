@@ -65,6 +65,15 @@ int ccb_env_flagged_rows(ccb_env *env, int *count, int *rows, int cap);
  * 5 cell finalisation, 6 the per-site reduce of the whole-map Voronoi alone (on the row partition a
  * previous which = 0 left), 7 its row partition alone, 8 the CNN input fused with the window Voronoi */
 int ccb_bench_kernel(ccb_env *env, int which, int iters, float *scratch_dev);
+/* the IDF integration kernel alone, `iters` times over the whole map (inputs uploaded before the timed region,
+ * no maximum / normalise pass; leaves the map un-normalised); *ms_out = mean kernel time by CUDA events */
+int ccb_bench_idf_kernel(ccb_idf *idf, int mode, int iters, float *ms_out);
+/* the FP32 FMA rate the GPU sustains (TFLOP/s, best of 5): denominator of the IDF kernel's FP32 roofline */
+int ccb_bench_fp32_peak(int device, double *tflops_out);
+/* roofline arithmetic: what = 0 -> cells of all robots' local windows that their robot maps have seen (what
+ * the observation / window-Voronoi kernels must read); 1 -> (site, row) pairs with cells in the last
+ * site-ordered row partition (what k_vg_lookup / k_vg_reduce walk) */
+int ccb_test_count(ccb_env *env, int what, uint64_t *out);
 
 #ifdef __cplusplus
 }
