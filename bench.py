@@ -139,11 +139,26 @@ def cpu_c2_step(orc, oenv, torchvision_resize):
     return obj, maps
 
 
+def use_all_host_threads() -> int:
+    """The CPU arm runs with every host core whatever launched it: torch.distributed.run exports OMP_NUM_THREADS=1 to
+    its workers, which halved the round-1 reference arm at N >= 2.  Returns the thread count in force."""
+    n = int(os.environ.get("CCB_REF_THREADS", os.cpu_count() or 1))
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:  # libgomp may already be loaded (and have read the old value): set it through the runtime as well
+        C.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
+
+
 def run_cpu(steps: int, warmup: int, budget_s: float):
+    threads = use_all_host_threads()
     import torch
     import torchvision
 
     from oracle import oracle as orc
+
+    torch.set_num_threads(threads)
 
     class _P:
         pass
@@ -170,9 +185,196 @@ def run_cpu(steps: int, warmup: int, budget_s: float):
     t1 = time.perf_counter()
     orc.idf_generate(op, bnd, mode=0)
     idf_ms = (time.perf_counter() - t1) * 1e3
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    cores = threads
     return {"value": done / dt, "steps_done": done, "seconds": dt, "cores": cores, "idf_cpu_ms": idf_ms,
             "torch_threads": torch.get_num_threads()}
+
+
+
+# ------------------------------------------------------------------------------------------------
+# extras
+# ------------------------------------------------------------------------------------------------
+def c4_features(n_world: int, n_gauss: int, n_poly: int, seed: int = 0):
+    """BASELINE config 4 inputs: Gaussians (sigma 40-60) + star-shaped polygons of 4-10 vertices, radius <= 64
+    (coverage_system.cpp:83-98)."""
+    rng = np.random.default_rng(seed)
+    bnd = np.zeros((n_gauss, 6))
+    bnd[:, 0:2] = rng.uniform(0, n_world, (n_gauss, 2))
+    bnd[:, 2] = bnd[:, 3] = rng.uniform(40, 60, n_gauss)
+    bnd[:, 4] = rng.uniform(6, 10, n_gauss)
+    polys = []
+    for _ in range(n_poly):
+        c = rng.uniform(64, n_world - 64, 2)
+        nv = int(rng.integers(4, 11))
+        ang = np.sort(rng.uniform(0, 2 * np.pi, nv))
+        rad = rng.uniform(16, 64, nv)
+        polys.append((np.stack([c[0] + rad * np.cos(ang), c[1] + rad * np.sin(ang)], 1), float(5e-5 * rng.uniform(6, 10))))
+    return bnd, polys
+
+
+def make_idf(ccb, p, bnd, polys=(), device=0):
+    idf = ccb.WorldIDF(p, device=device)
+    for b in bnd:
+        idf.AddNormalDistribution(ccb.BivariateNormalDistribution(ccb.Point2(b[0], b[1]), float(b[2]), float(b[4])))
+    for pts, imp in polys:
+        idf.AddUniformDistributionPolygon(ccb.PolygonFeature(ccb.PointVector(pts), imp))
+    return idf
+
+
+def idf_extras(ccb, lib, p, device, clocks):
+    """IDF generation at C1 (1024^2, 32 Gaussians) and C4 (8192^2, 1024 Gaussians + 64 polygons): the integration
+    kernel alone against a MEASURED FP32 FMA rate, the whole GenerateMap call (upload + kernel + maximum + normalise
+    + the map back on the host, which is what the reference's wrapper returns), and the reference's own
+    generate_world_map_cuda (oracle/_ref, generate_world_map.cu:175-280: 6 cudaMalloc/Free + thrust max + D2H) on the
+    same inputs, same GPU, host clock."""
+    import torch
+
+    from coveragecontrol_b200 import _lib
+
+    out = {}
+    peak = C.c_double(0.0)
+    _lib.check(lib.ccb_bench_fp32_peak(device, C.byref(peak)))
+    out["fp32_fma_peak_tflops_measured"] = peak.value
+    try:
+        from oracle import oracle as orc
+        have_ref = orc.ref_idf_available()
+    except Exception:
+        orc, have_ref = None, False
+    for tag, n, bnd, polys in (("c1", N_WORLD, synth_inputs(0)[0], []), ("c4", 8192) + c4_features(8192, 1024, 64)):
+        q = p.copy()
+        q.pWorldMapSize = q.pRobotMapSize = n
+        idf = make_idf(ccb, q, bnd, polys, device)
+        idf.GenerateMap()
+        ms = C.c_float(0.0)
+        _lib.check(lib.ccb_bench_idf_kernel(idf._h, 0, 10, C.byref(ms)))
+        # SURVEY 8(d): flops = 8 N^2 F + 16 N^2 F p_in + 2 N^2, p_in = share of (cell, feature) pairs inside the
+        # truncation radius (pi (T sigma)^2 / N^2 at the mean sigma)
+        sig = float(np.mean(bnd[:, 2]))
+        p_in = min(1.0, math.pi * (q.pTruncationBND * sig) ** 2 / (n * n))
+        flops = n * n * (8.0 * len(bnd) + 16.0 * len(bnd) * p_in + 2.0)
+        r = {"kernel_ms": ms.value, "survey_flops": flops, "achieved_tflops": flops / (ms.value * 1e-3) / 1e12,
+             "frac_of_measured_fp32_peak": flops / (ms.value * 1e-3) / 1e12 / peak.value,
+             "map_write_gbs": 4.0 * n * n / (ms.value * 1e-3) / 1e9}
+        t = []
+        for _ in range(4):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            idf.GenerateMap()
+            idf._host = None
+            np.asarray(idf.GetWorldMap())
+            t.append((time.perf_counter() - t0) * 1e3)
+        r["generate_plus_d2h_ms"] = float(np.min(t[1:]))
+        if have_ref:
+            # the reference kernel wants y-monotone pieces: the triangles this library cuts the polygons into
+            pieces = []
+            for pts, imp in polys:
+                xy = np.ascontiguousarray(pts, np.float64)
+                tri = np.zeros((len(xy), 6))
+                k = lib.ccb_selftest_triangulate(xy.ctypes.data_as(_lib.c_double_p), len(xy), tri.ctypes.data_as(_lib.c_double_p), len(tri))
+                pieces += [(tri[i].reshape(3, 2).copy(), imp) for i in range(max(k, 0))]
+            op = orc.params_from(q)
+            t = []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                ref_map, _ = orc.ref_idf_generate(op, bnd, polys=pieces)
+                t.append((time.perf_counter() - t0) * 1e3)
+            r["reference_generate_world_map_cuda_ms"] = float(np.min(t[1:]))
+            r["speedup_vs_reference_call"] = r["reference_generate_world_map_cuda_ms"] / r["generate_plus_d2h_ms"]
+            idf.GenerateMap()
+            idf._host = None
+            r["bit_identical_to_reference"] = bool(np.array_equal(np.asarray(idf.GetWorldMap()), ref_map))
+        out[f"idf_{tag}"] = r
+    return out
+
+
+def c2_reference_api(p, device, timed):
+    """One environment through the REFERENCE-facing API, call for call what an evaluator does per step
+    (python/coverage_control/algorithms/controllers.py:67-88 ControllerCVT.step + coverage_env_utils.py:227-277
+    get_maps): ComputeActions, GetActions, StepActions(PointVector), GetObjectiveValue, get_maps(32, comm).  The CPU
+    figure beside it is this line's cpu_baseline (the same workload on the oracle port)."""
+    import coverage_control as cc
+    from coverage_control.algorithms import DecentralizedCVT
+
+    bnd, pos = synth_inputs(0)
+    idf = make_idf(cc, p, bnd, device=device)
+    idf.GenerateMap()
+    env = cc.CoverageSystem(p, idf, cc.PointVector(pos))
+    ctrl = DecentralizedCVT(p, env)
+
+    def step():
+        ctrl.ComputeActions()
+        env.StepActions(ctrl.GetActions())
+        env.GetObjectiveValue()
+        cc.CoverageEnvUtils.get_maps(env, p, CNN, True)
+
+    ms, _ = timed(step, 200, 20)
+    return {"steps_per_s": 200 / (ms * 1e-3), "ms_per_step": ms / 200,
+            "calls": "ComputeActions; StepActions(GetActions()); GetObjectiveValue(); CoverageEnvUtils.get_maps(env, params, 32, True)"}
+
+
+def c4_row_bands(ccb, device, rank, world, dist, args):
+    """BASELINE config 4 on the GPUs of this run: one 8192^2 world (1024 Gaussians + 64 polygons), 256 robots, tiled
+    in row bands; per step ClairvoyantCVT ComputeActions + StepActions with the per-robot moment partials combined by
+    ONE NCCL all-reduce (coveragecontrol_b200/parallel.py).  Device time, max over ranks."""
+    import torch
+
+    from coveragecontrol_b200 import BatchedCoverageSystem, BatchedCVT
+    from coveragecontrol_b200.parallel import BandedCoverageSystem, BandedWorldIDF
+
+    n, r = 8192, 256
+    p = ccb.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = n
+    p.pNumRobots = r
+    p.pUpdateExplorationMap = False
+    p.pTimeStep = 0.2
+    bnd, polys = c4_features(n, 1024, 64)
+    idf = make_idf(ccb, p, bnd, polys, device)
+    pos = np.random.default_rng(1).uniform(1e-4, n - 1e-4, (1, r, 2))
+    s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    BandedWorldIDF(idf)
+    t.record()
+    torch.cuda.synchronize()
+    idf_ms = s.elapsed_time(t)
+    env = BatchedCoverageSystem(p, 1, r, device=device)
+    env.set_world(0, idf)
+    env.reset(pos)
+    banded = BandedCoverageSystem(env, 0)
+    ctrl = BatchedCVT(env, 0)
+    steps = 50
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = {}
+    for kind in ("clairvoyant",):
+        for _ in range(5):
+            banded.step(ctrl)
+        barrier()
+        s.record()
+        for _ in range(steps):
+            banded.step(ctrl)
+        t.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([s.elapsed_time(t)], device="cuda")
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        per = float(ms.item()) / steps
+        rows = banded.rows[1] - banded.rows[0]
+        peak, _ = measured_peak_gbs()
+        out[kind] = {"ms_per_step": per, "env_steps_per_s": 1e3 / per, "rows_per_gpu": rows,
+                     "band_map_bytes": 4.0 * n * rows, "band_hbm_floor_ms": 4.0 * n * rows / (peak * 1e9) * 1e3,
+                     "frac_of_band_hbm_floor": (4.0 * n * rows / (peak * 1e9) * 1e3) / per}
+    obj = banded.step(ctrl, with_objective=True)
+    barrier()
+    out.update({"workload": f"C4: {n}x{n} world, {r} robots, 1024 Gaussians + 64 polygons, row bands over {world} GPU(s)",
+                "n_gpus": world, "idf_gen_ms_banded": idf_ms, "objective": float(obj[0]),
+                "per_rank_state_bytes": int(4 * n * n + r * n * (n // 32) * 4 + 2 * n * (n // 32) * 4)})
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -185,8 +387,10 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=1024,
                     help="independent environments stepped together on every GPU (BASELINE config 3 batches 1024)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--episode-steps", type=int, default=600, help="steps of the whole-episode mean (value_episode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the single-environment / C1 extras")
+    ap.add_argument("--no-extras", action="store_true", help="skip the single-environment / C1 / IDF / C4 extras")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 row-band extra (8192^2 world tiled over the GPUs)")
     ap.add_argument("--step-only", action="store_true",
                     help="only the device-resident step loop (the ncu launch list of the step: no e2e arm, no per-kernel timing)")
     args = ap.parse_args()
@@ -332,67 +536,99 @@ def main():
     e2e_value = world * E * args.steps / (ms_e2e * 1e-3)
 
     # ---- per-kernel durations (same data, CUDA events on the launching stream) ----------------------
-    # algorithmic bytes per launch: SURVEY.md 8(d) per-environment figure x E
-    kernels = {}
+    # Three byte counts per kernel:
+    #   survey_bytes    SURVEY.md 8(d)'s per-environment formula x E: what the REFERENCE's dense maps would move.
+    #   required_bytes  what this design has to move for the same result, counted on the device from the live state
+    #                   (ccb_test_count): world values only where a robot-map bit is set, the bit planes themselves,
+    #                   the (site, row) look-ups of the block-prefix path.  roofline.achieved / frac use THESE: a
+    #                   physical rate that cannot exceed the HBM peak.
+    #   traffic         dram__bytes_read + dram__bytes_write of the committed `ncu --set full` capture, scaled to E.
     cells = N_WORLD * N_WORLD
-    algo = {
-        "voronoi_global(partition+reduce+fixup)": (0, 4.0 * cells * E),
-        "k_vg_reduce": (6, 4.0 * cells * E),
-        "k_vg_partition": (7, 4.0 * N_ROBOTS * N_WORLD * E),
-        "k_vg_fixup": (9, 0.0),
-        "k_voronoi_window": (2, 4.0 * N_ROBOTS * LOCAL * LOCAL * E),
-        "k_cnn_fused8(+k_comm_maps)": (4, (4.0 * N_ROBOTS * LOCAL * LOCAL + 16.0 * N_ROBOTS * CNN * CNN) * E),
-        "k_cnn_fused8<window Voronoi>(+k_comm_maps)": (8, (4.0 * N_ROBOTS * LOCAL * LOCAL + 16.0 * N_ROBOTS * CNN * CNN) * E),
-        "k_mark_windows": (3, 12.0 * N_ROBOTS * SENSOR * SENSOR * E),
-        "k_finalize_cells": (5, 32.0 * N_ROBOTS * E),
+    cnt = C.c_uint64(0)
+    _lib.check(lib.ccb_bench_kernel(batch._h, 0, 1, obs.data_ptr()))  # a fresh row partition for the pair counter
+    _lib.check(lib.ccb_test_count(batch._h, 0, C.byref(cnt)))
+    seen_cells = float(cnt.value)        # cells of all robots' local windows their robot maps have seen
+    _lib.check(lib.ccb_test_count(batch._h, 1, C.byref(cnt)))
+    pairs = float(cnt.value)             # (site, row) pairs with cells in the whole-map partition
+    ER = float(N_ROBOTS * E)
+    win_bits = LOCAL * (LOCAL // 32 + 1) * 4.0          # the mask words of one window
+    obs_out = 16.0 * CNN * CNN                          # 4 channels x C^2 floats
+    prefix_on = os.environ.get("CCB_VG_PREFIX", "1") != "0"
+    look_bytes = pairs * (4.0 + 2 * 48.0 + 2 * 32.0) if prefix_on else 4.0 * cells * E
+    survey = {
+        "voronoi_global(partition+moments+fixup)": (0, 4.0 * cells * E, look_bytes + 4.0 * N_ROBOTS * N_WORLD * E),
+        "k_vg_lookup" if prefix_on else "k_vg_reduce": (6, 4.0 * cells * E, look_bytes),
+        "k_vg_partition": (7, 4.0 * N_ROBOTS * N_WORLD * E, 4.0 * N_ROBOTS * N_WORLD * E),
+        "k_vg_fixup": (9, 0.0, 0.0),
+        "k_voronoi_window": (2, 4.0 * N_ROBOTS * LOCAL * LOCAL * E, 4.0 * seen_cells + win_bits * ER),
+        "k_cnn_fused8(+k_comm_maps)": (4, (4.0 * N_ROBOTS * LOCAL * LOCAL + 16.0 * N_ROBOTS * CNN * CNN) * E,
+                                       4.0 * seen_cells + (win_bits + obs_out) * ER),
+        "k_cnn_fused8<window Voronoi>(+k_comm_maps)": (8, (8.0 * N_ROBOTS * LOCAL * LOCAL + 16.0 * N_ROBOTS * CNN * CNN) * E,
+                                                       4.0 * seen_cells + (win_bits + obs_out) * ER),
+        "k_mark_windows": (3, 12.0 * N_ROBOTS * SENSOR * SENSOR * E, 24.0 * SENSOR * (SENSOR // 32 + 2) * ER),
+        "k_finalize_cells": (5, 32.0 * N_ROBOTS * E, 32.0 * N_ROBOTS * E),
     }
-    for name, (which, nbytes) in algo.items():
+    kernels = {}
+    for name, (which, sbytes, rbytes) in survey.items():
         iters = 10
         fn = lambda w=which: _lib.check(lib.ccb_bench_kernel(batch._h, w, 1, obs.data_ptr()))  # noqa: E731
         ms, _ = timed(fn, iters, 3)
-        kernels[name] = {"ms": ms / iters, "algorithmic_bytes": nbytes, "gbs": nbytes / (ms / iters * 1e-3) / 1e9}
+        t = ms / iters * 1e-3
+        kernels[name] = {"ms": ms / iters, "survey_bytes": sbytes, "survey_gbs": sbytes / t / 1e9,
+                         "required_bytes": rbytes, "required_gbs": rbytes / t / 1e9}
+    if prefix_on:  # the streaming kernel the look-ups replace (still the CentralizedCVT / labels path), for comparison
+        batch.set_option("vg_prefix", 0)
+        _lib.check(lib.ccb_bench_kernel(batch._h, 0, 1, obs.data_ptr()))
+        ms, _ = timed(lambda: _lib.check(lib.ccb_bench_kernel(batch._h, 6, 1, obs.data_ptr())), 10, 3)
+        batch.set_option("vg_prefix", 1)
+        _lib.check(lib.ccb_bench_kernel(batch._h, 0, 1, obs.data_ptr()))
+        kernels["k_vg_reduce(streaming, prefix off)"] = {
+            "ms": ms / 10, "survey_bytes": 4.0 * cells * E, "survey_gbs": 4.0 * cells * E / (ms / 10 * 1e-3) / 1e9,
+            "required_bytes": 4.0 * cells * E, "required_gbs": 4.0 * cells * E / (ms / 10 * 1e-3) / 1e9}
     peak, peak_src = measured_peak_gbs()
     # the dominant single kernel of the step
     # (the step itself runs the fused observation + window-Voronoi variant, not the two kernels it replaces)
-    dom = max(("k_vg_reduce", "k_cnn_fused8<window Voronoi>(+k_comm_maps)"), key=lambda k: kernels[k]["ms"])
+    look = "k_vg_lookup" if prefix_on else "k_vg_reduce"
+    dom = max((look, "k_vg_partition", "k_cnn_fused8<window Voronoi>(+k_comm_maps)"), key=lambda k: kernels[k]["ms"])
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture
         with open(tpath) as f:
             t = json.load(f)
+        for k, v in t["kernels"].items():
+            if k in kernels:
+                kernels[k]["traffic"] = v["dram_bytes_per_env"] * E
+                kernels[k]["traffic_gbs"] = v["dram_bytes_per_env"] * E / (kernels[k]["ms"] * 1e-3) / 1e9
         if dom in t["kernels"]:
             traffic = t["kernels"][dom]["dram_bytes_per_env"] * E
             traffic_src = t["source"]
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": peak_src, "kernels": kernels}
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["required_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["required_gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
+                "frac_survey_formula": kernels[dom]["survey_gbs"] / peak,
+                "note": ("achieved = bytes this design must move (counted on the device: world values under set robot-map bits, "
+                         "bit planes, prefix look-ups) / CUDA-event time: a physical rate; frac_survey_formula divides the "
+                         "reference's dense-map byte count (SURVEY 8d) by the same time and may exceed 1 -- it measures work "
+                         "avoided, not bandwidth; traffic = ncu DRAM bytes of the committed capture"),
+                "seen_cells_per_robot": seen_cells / ER, "site_row_pairs_per_env": pairs / E,
+                "kernels": kernels}
     if traffic is not None:
-        # the SURVEY 8(d) figure charges whole L x L windows; the observation kernel only touches the cells a robot
-        # has seen, so its DRAM traffic is far below the algorithmic bytes: report the rate of the bytes actually
-        # moved too.  k_vg_reduce (in `kernels`) is the kernel that streams every map byte: there traffic ~ algorithmic.
         roofline["achieved_dram"] = traffic / (kernels[dom]["ms"] * 1e-3) / 1e9
         roofline["frac_dram"] = roofline["achieved_dram"] / peak
-        roofline["note"] = ("achieved = algorithmic bytes / time; achieved_dram = measured DRAM bytes (traffic) / time; "
-                            "k_vg_reduce streams the whole map: see kernels['k_vg_reduce']")
 
-    # ---- single-environment latency (API-faithful, E = 1) and the C1 variant, reported as extras -----
+    # ---- the same step over a whole episode: seen regions grow, the window kernels slow down -------------
+    value_episode = None
+    if not args.no_extras:
+        batch.reset(positions)
+        ms_ep, _ = timed(device_step, args.episode_steps, 0)
+        value_episode = world * E * args.episode_steps / (ms_ep * 1e-3)
+
+    # ---- extras: IDF generation (ours and the reference's own kernel), single-environment API latency, C1, C4 ---
     extras = {"idf_gen_ms_1024_32f_mode0": idf_ms}
-    if idf_ms:
-        # flops_idf = 8 N^2 F + 16 N^2 F p_in + 2 N^2, p_in = share of (cell, feature) pairs inside
-        # the truncation radius (pi (T sigma)^2 / N^2 at the mean sigma); the FP32 peak is nominal
-        # (148 SMs x 128 lanes x 2 x the maximum SM clock): there is no measured FP32 figure in MEASURED_PEAKS.json.
-        # At this size the three launches of GenerateMap (integrate, maximum, normalise) dominate: the kernel
-        # itself runs 8 us (profiles/*_summary.md).
-        sig = 0.5 * (p.pMinSigma + p.pMaxSigma)
-        p_in = min(1.0, math.pi * (p.pTruncationBND * sig) ** 2 / (N_WORLD * N_WORLD))
-        flops = N_WORLD * N_WORLD * (8.0 * N_FEATURES + 16.0 * N_FEATURES * p_in + 2.0)
-        fp32_peak = 148 * 128 * 2 * (clocks or {}).get("sm_max_mhz", 1965.0) * 1e6 / 1e12
-        extras["idf_fp32_roofline"] = {"flops": flops, "achieved_tflops": flops / (idf_ms * 1e-3) / 1e12,
-                                       "peak_tflops_nominal": fp32_peak,
-                                       "frac": flops / (idf_ms * 1e-3) / 1e12 / fp32_peak}
     try:
         if args.no_extras:
             raise RuntimeError("skipped (--no-extras)")
+        extras.update(idf_extras(ccb, lib, p, local_rank, clocks))
         one = BatchedCoverageSystem(p, 1, N_ROBOTS, device=local_rank)
         bnd, pos = synth_inputs(0)
         idf = ccb.WorldIDF(p, device=local_rank)
@@ -417,8 +653,14 @@ def main():
         c1b = BatchedCVT(batch, 0)
         ms, _ = timed(lambda: c1b.rollout(1), max(5, args.steps // 2), 3)
         extras["c1_batched_device_steps_per_s"] = world * E * max(5, args.steps // 2) / (ms * 1e-3)
+        extras["c2_single_env_reference_api"] = c2_reference_api(p, local_rank, timed)
     except Exception as exc:  # extras never invalidate the headline line
-        extras["extras_error"] = str(exc)
+        extras["extras_error"] = f"{type(exc).__name__}: {exc}"
+    try:
+        if not args.no_extras and not args.no_c4:
+            extras["c4_row_bands"] = c4_row_bands(ccb, local_rank, rank, world, dist, args)
+    except Exception as exc:
+        extras["c4_error"] = f"{type(exc).__name__}: {exc}"
 
     if rank != 0:
         if dist is not None:
@@ -439,9 +681,13 @@ def main():
         "dtype": "f64 sums over f32 maps (u32 seen masks)", "data": "synthetic", "config": config,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "env_steps/s", "ms_per_step": ms_e2e / args.steps,
+                "scope": ("the batched C ABI with HOST buffers: actions D2H, StepActions H2D, objective D2H per step for all "
+                          "environments of the batch; the [E, R, 4, 32, 32] observation stays on the device by design "
+                          "(zero-copy hand-off to LPAC); extras.c2_single_env_reference_api is the per-environment API"),
                 "h2d_bytes_per_step": int(host_actions.nbytes),
                 "d2h_bytes_per_step": int(host_actions.nbytes + host_obj.nbytes)},
         "gpu_launches": int(launches),
+        "value_episode": value_episode, "episode_steps": args.episode_steps if value_episode else None,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "extras": extras,

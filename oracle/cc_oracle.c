@@ -856,6 +856,9 @@ void orc_env_comm_maps_cpp(orc_env *e, int r, int ms, float *ox, float *oy) {
     double sx = rel[2 * k] * ms / (p->pCommunicationRange * p->pResolution * 2.) + center;
     double sy = rel[2 * k + 1] * ms / (p->pCommunicationRange * p->pResolution * 2.) + center;
     int ix = (int)round(sx), iy = (int)round(sy);
+    /* the reference writes comm_map(ix, iy) unchecked (undefined behaviour once pResolution < 1 pushes the index
+     * past the map); the restatement skips such neighbours instead of corrupting the heap */
+    if (ix < 0 || ix >= ms || iy < 0 || iy >= ms) continue;
     ox[ix * ms + iy] += (float)(rel[2 * k] / p->pCommunicationRange);
     oy[ix * ms + iy] += (float)(rel[2 * k + 1] / p->pCommunicationRange);
   }
@@ -877,6 +880,9 @@ void orc_env_comm_maps_py(orc_env *e, int r, int ms, float *ox, float *oy) {
     float sx = fx * (float)ms / denom + center;
     float sy = fy * (float)ms / denom + center;
     long ix = (long)rintf(sx), iy = (long)rintf(sy); /* default rounding mode: ties-to-even */
+    /* torch.sparse_coo_tensor raises for an index outside the map (pResolution < 1 can produce one): skipped here,
+     * as the CUDA path does, instead of writing past the buffer */
+    if (ix < 0 || ix >= ms || iy < 0 || iy >= ms) continue;
     ox[ix * ms + iy] += fx / cr;
     oy[ix * ms + iy] += fy / cr;
   }

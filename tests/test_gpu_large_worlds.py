@@ -206,6 +206,10 @@ def test_resolution_other_than_one(monkeypatch, res, kind, name):
     bnd[:, 2] = bnd[:, 3] = rng.uniform(15 * res, 30 * res, 7)
     bnd[:, 4] = rng.uniform(6, 10, 7)
     pos = rng.uniform(1e-3, N * res - 1e-3, (R, 2))
+    if res > 1.0 and kind == 2:
+        # decentralized_cvt.h:127-141 throws once a goal exceeds pWorldMapSize WORLD units (the same units slip; the
+        # library keeps that check): stay where every window, hence every goal, is below it for the whole roll-out
+        pos = rng.uniform(40.0, 150.0, (R, 2))
     op = orc.params_from(p)
     idf = cc.WorldIDF(p)
     for b in bnd:
@@ -266,5 +270,10 @@ def test_resolution_other_than_one(monkeypatch, res, kind, name):
     loc = rs(torch.from_numpy(np.stack([oenv.local_map(r) for r in range(R)]))).numpy()
     obst = rs(torch.from_numpy(np.stack([oenv.obstacle_map(r) for r in range(R)]))).numpy()
     comm = np.stack([np.stack(oenv.comm_maps(r, 32, "py")) for r in range(R)])
-    assert np.allclose(obs[:, 0], loc, atol=1e-5) and np.allclose(obs[:, 3], obst, atol=1e-5)
+    err = lambda a, b: [float(np.abs(a[r] - b[r]).max()) for r in range(R)]  # noqa: E731
+    where = f"positions {oenv.positions().tolist()}"
+    assert np.allclose(obs[:, 0], loc, atol=1e-5), (err(obs[:, 0], loc), where)
+    assert np.allclose(obs[:, 3], obst, atol=1e-5), (err(obs[:, 3], obst), where)
+    # (pResolution < 1 scales the communication-map index past the map for far neighbours: the reference's torch code
+    # raises there; both sides skip such neighbours)
     assert np.allclose(obs[:, 1:3], comm, atol=1e-6)
