@@ -506,6 +506,7 @@ struct ResizeTab {
   int *d_xmin = nullptr, *d_xsize = nullptr;
   float *d_w = nullptr;
   float *d_wfull8 = nullptr;  // [C][16] weights in the (8 o - 4) frame, only when L == 8 C == 256
+  bool interior_uniform = false;  // rows 1 .. C - 2 of d_wfull8 are identical (k_obs_fused keeps them in registers)
 };
 
 struct ccb_env {
@@ -573,6 +574,7 @@ struct ccb_env {
   std::vector<char> pfx_valid;  // [E]: the entries of environment e match its world map
   int *d_pfx_list = nullptr;    // [E] environments to rebuild
   bool cnn_generic = false;     // test option: the generic observation kernel even where the fused one applies
+  bool obs_v1 = false;          // test option: the row-ordered fused observation kernel of round 1 (A/B timing)
 };
 
 // kernels that need more than 48 KB of dynamic shared memory: raise the limit once per (device, kernel)
@@ -630,6 +632,17 @@ static int run_voronoi(ccb_env *env, const VorArgs &a, dim3 grid) {
 
 static int ensure_prefix(ccb_env *env);
 
+// Which whole-map Voronoi kernel (measured: profiles/r01_sweep_c5.md).  The site-ordered path pays one sequential
+// sweep per map row (~30 us whatever the batch) and then walks every site's intervals; the tile-ordered kernel is
+// faster where most 64 x 64 regions have a single owner (cells of more than ~128 K map cells: 4.7 TB/s at N = 16384,
+// R = 64) and slower where they do not (1.5 TB/s at N = 1024, R = 32).
+static bool use_site_ordered(const ccb_env *env, int rows) {
+  const EnvDev &d = env->d;
+  const bool by_shape = (long)d.E * rows >= 32L * 1024 && (long)d.N * d.N / d.R <= 128L * 1024;
+  const bool wanted = env->vg_mode == 0 || (env->vg_mode < 0 && by_shape);
+  return d.R <= VG_MAXR && (d.N & 3) == 0 && d.N < 65536 && wanted;
+}
+
 // Voronoi label + reduce over the full map of every environment; sums must be a [E][R][4] buffer.
 // row0/row1 restrict the pass to a row band (row1 < 0: the whole map).
 // stages: bit 0 row partition, bit 1 per-site reduce, bit 2 flagged-row fix-up (site-ordered path; the
@@ -641,13 +654,7 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
   if (env->stream != env->aux && join_aux(env)) return 1;  // the partition tables are shared with `aux`
   CCB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * d.E * d.R, env->stream));
   if (row1 <= row0) return 0;
-  // Which kernel (measured: profiles/r01_sweep_c5.md).  The site-ordered path pays one sequential sweep
-  // per map row (~30 us whatever the batch) and streams every cell at the same cost; the tile-ordered
-  // kernel is faster where most 64 x 64 regions have a single owner (cells of more than ~128 K map cells:
-  // 4.7 TB/s at N = 16384, R = 64) and slower where they do not (1.5 TB/s at N = 1024, R = 32).
-  const bool site_ordered = env->vg_mode == 0 || (env->vg_mode < 0 && (long)d.E * (row1 - row0) >= 32L * 1024 &&
-                                                  (long)d.N * d.N / d.R <= 128L * 1024);
-  if (d.R <= VG_MAXR && (d.N & 3) == 0 && d.N < 65536 && site_ordered) {
+  if (use_site_ordered(env, row1 - row0)) {
     // site-ordered path: row partition -> per-site interval streaming -> exact rule on flagged rows
     if (!env->d_vg_table) {
       CCB_CUDA(cudaMalloc(&env->d_vg_table, sizeof(uint32_t) * (size_t)d.E * d.R * d.N));
@@ -930,6 +937,7 @@ extern "C" int ccb_test_set_option(ccb_env *env, const char *name, int value) {
   else if (n == "no_graph") env->no_graph = value != 0;
   else if (n == "no_wfuse") env->no_wfuse = value != 0;
   else if (n == "cnn_generic") env->cnn_generic = value != 0;
+  else if (n == "obs_v1") env->obs_v1 = value != 0;
   else return fail("ccb_test_set_option: unknown option", name);
   return 0;
 }
@@ -1328,6 +1336,8 @@ static int get_resize_table(ccb_env *env, int C, ResizeTab **out) {
         int col = 8 * o - 4 + k;
         if (col >= xmin[o] && col < xmin[o] + xsize[o]) wf[(size_t)o * 16 + k] = w[(size_t)o * kmax + (col - xmin[o])];
       }
+    t.interior_uniform = true;
+    for (int o = 2; o < C - 1; ++o) t.interior_uniform = t.interior_uniform && memcmp(&wf[(size_t)o * 16], &wf[16], sizeof(float) * 16) == 0;
     CCB_CUDA(cudaMalloc(&t.d_wfull8, sizeof(float) * C * 16));
     CCB_CUDA(cudaMemcpy(t.d_wfull8, wf.data(), sizeof(float) * C * 16, cudaMemcpyHostToDevice));
   }
@@ -1349,15 +1359,39 @@ extern "C" int ccb_env_cnn_input_dev(ccb_env *env, int C, int use_comm, float *o
   size_t smem = sizeof(float) * ((size_t)t->kmax * d.L + (size_t)t->kmax * C);
   if (ensure_smem(env, k_cnn_local_obstacle, smem)) return 1;
   // channel order of coverage_env_utils.py:264-276: [local, comm_x, comm_y, obstacle]
-  if (t->d_wfull8 && (d.N & 3) == 0 && !env->cnn_generic) {
-    const bool vor = env->n_decentralized > 0 && !env->no_wfuse && d.L == 256 && env->wsums_version != env->pos_version;
+  const bool fused_ok = t->d_wfull8 && (d.N & 3) == 0 && !env->cnn_generic;
+  const bool vor = fused_ok && env->n_decentralized > 0 && !env->no_wfuse && d.L == 256 && env->wsums_version != env->pos_version;
+  const bool dense = d.fill != 0.f;
+  const size_t oo = cc * (nch - 1);
+  const dim3 g8(d.R, d.E);
+  bool comm_done = false;
+  if (fused_ok && t->interior_uniform && !env->obs_v1) {
+    // item-ordered kernel: local + obstacle (+ communication) channels and, for DecentralizedCVT, the window moments
+    const size_t sm = obs_smem_bytes(d.R);
+    double *ws = vor ? env->d_wsums : nullptr;
+    if (vor) {
+      if (dense) {
+        if (ensure_smem(env, k_obs_fused<true, true>, sm)) return 1;
+        k_obs_fused<true, true><<<g8, OB_THREADS, sm, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, oo, cc, use_comm, ws);
+      } else {
+        if (ensure_smem(env, k_obs_fused<true, false>, sm)) return 1;
+        k_obs_fused<true, false><<<g8, OB_THREADS, sm, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, oo, cc, use_comm, ws);
+      }
+      env->wsums_version = env->pos_version;
+    } else if (dense) {
+      if (ensure_smem(env, k_obs_fused<false, true>, sm)) return 1;
+      k_obs_fused<false, true><<<g8, OB_THREADS, sm, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, oo, cc, use_comm, ws);
+    } else {
+      if (ensure_smem(env, k_obs_fused<false, false>, sm)) return 1;
+      k_obs_fused<false, false><<<g8, OB_THREADS, sm, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, oo, cc, use_comm, ws);
+    }
+    comm_done = true;
+  } else if (fused_ok) {
+    // row-ordered kernel of round 1 (kept for A/B timing: ccb_test_set_option "obs_v1")
     const size_t smem8 = vor ? cnn8_vor_smem_bytes(d.R) : CNN8_SMEM_BYTES;
     if (ensure_smem(env, k_cnn_fused8<false, false>, smem8) || ensure_smem(env, k_cnn_fused8<false, true>, smem8) ||
         ensure_smem(env, k_cnn_fused8<true, false>, smem8) || ensure_smem(env, k_cnn_fused8<true, true>, smem8))
       return 1;
-    const dim3 g8(d.R, d.E);
-    const size_t oo = cc * (nch - 1);
-    const bool dense = d.fill != 0.f;
     if (vor) {
       if (dense) k_cnn_fused8<true, true><<<g8, CNN8_THREADS, smem8, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, oo, env->d_wsums);
       else k_cnn_fused8<true, false><<<g8, CNN8_THREADS, smem8, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, oo, env->d_wsums);
@@ -1370,7 +1404,7 @@ extern "C" int ccb_env_cnn_input_dev(ccb_env *env, int C, int use_comm, float *o
     k_cnn_local_obstacle<<<dim3(C, d.R, d.E), 256, smem, env->stream>>>(d, C, tab, out_dev, stride, 0, cc * (nch - 1));
   }
   CCB_LAUNCH_CHECK();
-  if (use_comm) {
+  if (use_comm && !comm_done) {
     k_comm_maps<<<dim3(d.R, d.E), 128, 0, env->stream>>>(d, C, out_dev, stride, cc);
     CCB_LAUNCH_CHECK();
   }
@@ -1994,7 +2028,7 @@ extern "C" int ccb_ctrl_rollout_obs(ccb_ctrl *c, int steps, int with_objective, 
     g.obs = obs_dev, g.stride = obs_step_stride, g.entry_valid = entry_valid;
   }
   if (join_aux(env)) return 1;
-  if (ensure_prefix(env)) return 1;  // never inside the captured region: world maps change between replays
+  if (!env->band_mode && use_site_ordered(env, env->d.N) && ensure_prefix(env)) return 1;  // never inside the captured region: world maps change between replays
   auto launch_graph = [&]() -> int {
     CCB_CUDA(cudaEventRecord(env->ev_fork, env->stream));
     CCB_CUDA(cudaStreamWaitEvent(env->cap, env->ev_fork, 0));

@@ -62,14 +62,8 @@ __global__ void k_graph(EnvDev d, float *__restrict__ weights, float *__restrict
 // arithmetic, torch.round = round-half-even, duplicates summed.  out: E x R x 2 x C x C, or a
 // channel slice of a wider tensor (chan_stride = floats between robots, chan_off = first channel).
 // One CTA per (robot, env).
-__global__ void k_comm_maps(EnvDev d, int C, float *__restrict__ out, size_t robot_stride, size_t chan_off) {
-  const int r = blockIdx.x, e = blockIdx.y;
-  const size_t er = (size_t)e * d.R + r;
-  float *ox = out + er * robot_stride + chan_off;
-  float *oy = ox + (size_t)C * C;
-  for (int t = threadIdx.x; t < 2 * C * C; t += blockDim.x) ox[t] = 0.f;
-  __syncthreads();
-  if (threadIdx.x != 0) return;
+// one thread scatters robot r's neighbours into its two (already zeroed) C x C planes, ascending neighbour index
+__device__ __forceinline__ void comm_scatter(const EnvDev &d, int e, int r, int C, float *ox, float *oy) {
   const double *pos = d.pos_g + (size_t)e * d.R * 2;
   const float denom = (float)(d.comm_range * d.res * 2.0);
   const float center = (float)(C / 2.0 - d.res / 2.0);
@@ -90,6 +84,16 @@ __global__ void k_comm_maps(EnvDev d, int C, float *__restrict__ out, size_t rob
     ox[xi * C + yi] += __fdiv_rn(fx, cr);
     oy[xi * C + yi] += __fdiv_rn(fy, cr);
   }
+}
+
+__global__ void k_comm_maps(EnvDev d, int C, float *__restrict__ out, size_t robot_stride, size_t chan_off) {
+  const int r = blockIdx.x, e = blockIdx.y;
+  const size_t er = (size_t)e * d.R + r;
+  float *ox = out + er * robot_stride + chan_off;
+  float *oy = ox + (size_t)C * C;
+  for (int t = threadIdx.x; t < 2 * C * C; t += blockDim.x) ox[t] = 0.f;
+  __syncthreads();
+  if (threadIdx.x == 0) comm_scatter(d, e, r, C, ox, oy);
 }
 
 // Separable antialiased bilinear down-sampling weights (what torchvision resize(antialias=True)
@@ -508,6 +512,359 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
     dst[local_off] = acc;
     dst[obst_off] = acc_obs;
   }
+}
+
+
+// ---- item-ordered fused observation kernel (L = 256 -> C = 32, N % 4 == 0): the product path --------------------
+// k_cnn_fused8 above deals whole window ROWS to warps, a lane per output column: a few steps into an episode a robot
+// has seen ~70 x 70 cells of its 256 x 256 window, so three lanes out of four carry zeros through every select, FMA
+// and shuffle (ncu r02b: 24.7 K warp instructions per robot, issue-bound at 56 % issue-active, 12 % of HBM).  Here
+// the unit of work is an ITEM = one non-zero width-pass output (window row a, output column oy): the 16 taps
+// [8 oy - 4, 8 oy + 12) of row a hold a seen cell.  Items are listed in (row, oy) order and dealt to the lanes, so
+// every lane of every warp does useful work whatever the shape of the seen region.
+//   1. seen bits of the window rows inside the robot's seen box -> shared memory (11 words per row: a pad word
+//      either side so that any 20-bit field can be fetched with one funnel shift); VOR: the own-cell column
+//      interval of every window row (vw_row_interval, as k_voronoi_window);
+//   2. one thread per window row: which oy have a seen tap (nibble arithmetic on the mask words), prefix sum over
+//      the rows, item list (row << 5 | oy);
+//   3. items: a lane loads the 4 or 5 aligned float4 groups under its 16 taps (only those with a seen bit), selects
+//      the seen cells, applies the 16 weights in ascending tap order (the order torchvision's separable antialias
+//      kernel uses) and stores tmp[a][oy].  VOR: the 8 cells of the item's own column group (taps 4..11: every
+//      window cell is the own group of exactly one item) are also reduced into the robot's window-Voronoi moments:
+//      fp64 (s, t = sum i v_i, u = sum i^2 v_i) per item, folded with the group's first column and the row
+//      into five lane-private accumulators; fixed item -> lane assignment, fixed reduction tree: bit-stable sums;
+//   4. height pass: warp w owns output rows 4w .. 4w+3, skips those whose 16 tap rows hold no item, sums the
+//      taps in ascending row order;
+//   5. obstacle channel in closed form: obstacle(a, b) = 1 - in_x(a) in_y(b) is separable, so its resized value is
+//      A(ox) cy_out(oy) + B(ox) cy_all(oy) with A / B = the tap weights of the rows inside / outside the map and
+//      cy_out / cy_all = the tap weights of the columns outside the map / all columns (0 when the window lies
+//      inside the map);
+//   6. (use_comm) the two communication-map channels: zero-filled by the CTA, scattered by one thread.
+// wfull[o][k] = weight of input index 8 o - 4 + k (zero outside torch's tap range); rows 1 .. 30 are identical
+// (the host checks this before it picks the kernel): their 16 weights live in registers.
+constexpr int OB_THREADS = 256;
+constexpr int OB_WARPS = OB_THREADS / 32;
+constexpr int OB_ROWS = 256;
+constexpr int OB_WORDS = 11;  // pad + 9 mask words + pad
+
+struct ObsShared {
+  float tmp[OB_ROWS][32];               // width-pass results; entry (a, oy) valid iff need[a] bit oy
+  uint32_t mask[OB_ROWS * OB_WORDS];    // seen & in-map & in-window bits; word 1 + j <-> map word wbase + j
+  uint32_t need[OB_ROWS];
+  int rowoff[OB_ROWS + 1];
+  unsigned short items[OB_ROWS * 32];
+  float w[32][16];
+  float oA[32], oB[32];
+  int lo[OB_ROWS], hi[OB_ROWS];         // VOR: own-cell interval, map columns
+  uint32_t exact[OB_ROWS / 32];         // VOR: rows that need the per-cell rule
+  int wtot[OB_WARPS];
+  int K;
+  double red[OB_WARPS][4];
+};
+__host__ __device__ inline size_t obs_smem_bytes(int R) { return sizeof(ObsShared) + sizeof(double) * 2 * (size_t)R; }
+
+// bits [lo, hi) of an n-bit field whose bit 0 is column c0
+__device__ __forceinline__ unsigned ob_range(int lo, int hi, int c0, int n) {
+  const int a = min(max(lo - c0, 0), n), b = min(max(hi - c0, 0), n);
+  return ((1u << b) - 1u) & ~((1u << a) - 1u);
+}
+
+template <int S, bool VOR, bool DENSE>
+__device__ __forceinline__ void ob_items(const EnvDev &d, ObsShared &sh, const float *__restrict__ world, const Window &w,
+                                         int off0, int amap0, int amap1, int cy0, int cy1, const float (&wreg)[16],
+                                         const double *s_px, const double *s_py, double (&acc)[5]) {
+  constexpr int NV = S == 0 ? 4 : 5;  // aligned 4-cell groups under the 16 taps
+  const int total = sh.rowoff[OB_ROWS];
+  const float fill = d.fill;
+#pragma unroll 1
+  for (int i = threadIdx.x; i < total; i += OB_THREADS) {
+    const int it = sh.items[i];
+    const int a = it >> 5, oy = it & 31;
+    const int row = w.ox + a;
+    const int gyb = w.oy + 8 * oy - 4 - S;        // 16-byte aligned map column of the first group
+    const int pos = off0 + 8 * oy - 4 - S + 32;   // its bit in the row's 11 mask words
+    const uint32_t *m = sh.mask + a * OB_WORDS + (pos >> 5);
+    const unsigned vis = __funnelshift_r(m[0], m[1], pos & 31) & ((1u << (4 * NV)) - 1u);
+    float4 v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d.use_sensor) {
+      const float4 *src = reinterpret_cast<const float4 *>(world + (size_t)row * d.N + gyb);
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if ((vis >> (4 * j)) & 0xfu) v[j] = __ldcs(src + j);  // a set bit is an in-map cell: the whole aligned group is
+    }
+    float x[4 * NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) x[4 * j] = v[j].x, x[4 * j + 1] = v[j].y, x[4 * j + 2] = v[j].z, x[4 * j + 3] = v[j].w;
+    unsigned inm = 0u;  // DENSE: in-map, in-window cells of an in-map row carry `fill` until seen
+    if (DENSE) inm = (a >= amap0 && a < amap1) ? ob_range(cy0, cy1, gyb, 4 * NV) : 0u;
+    float c[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const float unseen = (DENSE && ((inm >> (S + q)) & 1u)) ? fill : 0.f;
+      c[q] = ((vis >> (S + q)) & 1u) ? x[S + q] : unseen;
+    }
+    float t = 0.f;
+    if (oy != 0 && oy != 31) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) t = fmaf(wreg[q], c[q], t);
+    } else {  // the two border columns: torch truncates and renormalises their taps
+#pragma unroll
+      for (int q = 0; q < 16; ++q) t = fmaf(sh.w[oy][q], c[q], t);
+    }
+    sh.tmp[a][oy] = t;
+    if (VOR) {
+      // the item's own column group (taps 4 .. 11 = window columns 8 oy .. 8 oy + 7) inside the robot's cell
+      const int c0 = w.oy + 8 * oy;
+      unsigned ob = ob_range(sh.lo[a], sh.hi[a], c0, 8) & ((DENSE ? inm : vis) >> (S + 4)) & 0xffu;
+      if (ob != 0u) {
+        if ((sh.exact[a >> 5] >> (a & 31)) & 1u) {  // per-cell rule on this row (a bisector runs along it)
+          unsigned todo = ob;
+          while (todo) {
+            const int bit = __ffs(todo) - 1;
+            todo &= todo - 1;
+            bool lost = false;
+            for (int k = 1; k <= sh.K && !lost; ++k) lost = vw_beats(d.res, row, c0 + bit, s_px[k], s_py[k], s_px[0], s_py[0]);
+            if (lost) ob &= ~(1u << bit);
+          }
+        }
+        double s = 0.0, tt = 0.0, u = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const double dv = (double)(((ob >> q) & 1u) ? c[4 + q] : 0.f);
+          s += dv;
+          if (q > 0) tt = fma((double)q, dv, tt), u = fma((double)(q * q), dv, u);
+        }
+        const double y0 = (double)c0 + 0.5, xd = (double)row + 0.5;
+        acc[0] += s;
+        acc[1] = fma(xd, s, acc[1]);
+        acc[2] += fma(y0, s, tt);
+        acc[3] = fma(xd * xd, s, acc[3]);
+        acc[4] += fma(y0 * y0, s, fma(y0 + y0, tt, u));
+      }
+    }
+  }
+}
+
+template <bool VOR, bool DENSE>
+__global__ void __launch_bounds__(OB_THREADS, 3)
+k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__restrict__ out, size_t robot_stride,
+            size_t local_off, size_t obst_off, size_t comm_off, int use_comm, double *__restrict__ wsums /* VOR: [E][R][4] */) {
+  extern __shared__ __align__(16) unsigned char ob_smem[];
+  ObsShared &sh = *reinterpret_cast<ObsShared *>(ob_smem);
+  double *s_px = reinterpret_cast<double *>(ob_smem + sizeof(ObsShared));
+  double *s_py = s_px + d.R;
+  const int r = blockIdx.x, e = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t er = (size_t)e * d.R + r;
+  float *dst = out + er * robot_stride;
+  for (int t = tid; t < 32 * 16; t += OB_THREADS) sh.w[t >> 4][t & 15] = wfull[t];
+  if (use_comm) {  // the communication channels start as zeros (scattered into at the very end)
+    float4 *cz = reinterpret_cast<float4 *>(dst + comm_off);
+    for (int t = tid; t < 2 * 32 * 32 / 4; t += OB_THREADS) cz[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const double *p = d.pos_g + er * 2;
+  const Window w = make_window(d.res, p[0], p[1], 256, d.N);
+  const float *world = d.world + (size_t)e * cell_count(d);
+  const uint32_t *plane = robot_plane(d, d.seenb, e, r);
+  // window rows / columns inside the map, and (unless unseen cells carry a value) inside the robot's seen box
+  const int amap0 = max(0, -w.ox), amap1 = min(256, d.N - w.ox);
+  const int cy0 = max(w.oy, 0), cy1 = min(w.oy + 256, d.N);
+  const int wbase = w.oy >> 5;  // arithmetic shift: floor for negative origins
+  const int off0 = w.oy - 32 * wbase;
+  int alo = amap0, ahi = amap1, wlo = 0, whi = 9;
+  if (!DENSE) {
+    const int *box = d.seen_box + 4 * er;
+    alo = max(alo, box[0] - w.ox), ahi = min(ahi, box[1] - w.ox);
+    wlo = max(0, (box[2] >> 5) - wbase), whi = min(9, ((box[3] - 1) >> 5) - wbase + 1);
+  }
+  if (VOR) {
+    if (tid < OB_ROWS / 32) sh.exact[tid] = 0u;
+    if (warp == 0) {
+      // sites: self, then the neighbours within communication range in ascending index (decentralized_cvt.h:100-120)
+      const double *pos = d.pos_g + (size_t)e * d.R * 2;
+      const double sx = p[0], sy = p[1];
+      if (lane == 0) s_px[0] = sx, s_py[0] = sy;
+      int n = 1;
+      for (int base = 0; base < d.R; base += 32) {
+        const int j = base + lane;
+        bool keep = false;
+        double jx = 0, jy = 0;
+        if (j < d.R && j != r) {
+          jx = pos[2 * j], jy = pos[2 * j + 1];
+          const double dx = __dsub_rn(jx, sx), dy = __dsub_rn(jy, sy);
+          keep = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) < d.comm_range;
+        }
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+          const int slot = n + __popc(km & ((1u << lane) - 1u));
+          s_px[slot] = jx, s_py[slot] = jy;
+        }
+        n += __popc(km);
+      }
+      if (lane == 0) sh.K = n - 1;
+    }
+  }
+  // ---- 1. mask words: zeros everywhere, then the words inside the box -----------------------------------------
+  for (int t = tid; t < OB_ROWS * OB_WORDS; t += OB_THREADS) sh.mask[t] = 0u;
+  __syncthreads();
+  if (VOR) {  // own-cell interval of the rows that can hold a cell (thread a <-> window row a)
+    const int a = tid, ncols = w.y1 - w.y0;
+    int lo = 0, hi = 0;
+    if (a >= alo && a < ahi && ncols > 0) {
+      if (sh.K == 0) lo = 0, hi = ncols;
+      else if (vw_row_interval(d.res, w.ox + a, w.y0, ncols, sh.K, s_px, s_py, lo, hi)) atomicOr(&sh.exact[a >> 5], 1u << (a & 31));
+    }
+    sh.lo[a] = w.y0 + lo, sh.hi[a] = w.y0 + max(hi, lo);
+  }
+  {
+    const int nrow_s = max(ahi - alo, 0), nw_s = max(whi - wlo, 0), nstage = nrow_s * nw_s;
+    constexpr int STAGE = 4;
+#pragma unroll 1
+    for (int t0 = 0; t0 < nstage; t0 += STAGE * OB_THREADS) {
+      uint32_t mw[STAGE];
+#pragma unroll
+      for (int k = 0; k < STAGE; ++k) {
+        const int t = t0 + tid + k * OB_THREADS;
+        const int ar = t / nw_s, j = wlo + t - ar * nw_s;
+        const int wd = wbase + j;
+        uint32_t mv = 0u;
+        if (t < nstage && wd >= 0 && wd < d.NW) {
+          const uint32_t keep = vw_range_bits(cy0, cy1, wd << 5);
+          if (keep) mv = __ldg(plane + (size_t)(w.ox + alo + ar) * d.NW + wd) & keep;
+        }
+        mw[k] = mv;
+      }
+#pragma unroll
+      for (int k = 0; k < STAGE; ++k) {
+        const int t = t0 + tid + k * OB_THREADS;
+        if (t >= nstage) continue;
+        const int ar = t / nw_s, j = wlo + t - ar * nw_s;
+        sh.mask[(alo + ar) * OB_WORDS + 1 + j] = mw[k];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 2. which outputs of row a are non-zero; item list ------------------------------------------------------
+  {
+    const int a = tid;
+    uint32_t nd = 0u;
+    if (a >= alo && a < ahi) {
+      if (DENSE) {
+        // every output whose 16 taps touch an in-map column of this in-map row
+        for (int oy = 0; oy < 32; ++oy)
+          if (ob_range(cy0, cy1, w.oy + 8 * oy - 4, 16)) nd |= 1u << oy;
+      } else {
+        const uint32_t *mrow = sh.mask + a * OB_WORDS + 1;
+        uint32_t tprev = 0u, tcur, tnext;
+        {
+          const uint32_t x0 = __funnelshift_r(mrow[0], mrow[1], off0);
+          uint32_t t = x0 | (x0 >> 1);
+          tcur = (t | (t >> 2)) & 0x11111111u;  // bit 4 n: nibble n (4 window columns) holds a seen cell
+        }
+#pragma unroll
+        for (int mI = 0; mI < 8; ++mI) {
+          tnext = 0u;
+          if (mI < 7) {
+            const uint32_t x1 = __funnelshift_r(mrow[mI + 1], mrow[mI + 2], off0);
+            uint32_t t = x1 | (x1 >> 1);
+            tnext = (t | (t >> 2)) & 0x11111111u;
+          }
+          // output 4 mI + g reads nibbles 2 g - 1 .. 2 g + 2 of this word (and of its neighbours at the ends)
+          const uint32_t u = tcur | (tcur >> 4) | (tcur << 4) | (tcur >> 8) | (tprev >> 28) | (tnext << 24);
+          nd |= ((((u & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << (4 * mI);
+          tprev = tcur, tcur = tnext;
+        }
+      }
+    }
+    sh.need[a] = nd;
+    // exclusive prefix sum of the item counts over the 256 rows
+    const int cnt = __popc(nd);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) sh.wtot[warp] = incl;
+    __syncthreads();
+    int before = 0;
+#pragma unroll
+    for (int k = 0; k < OB_WARPS; ++k) before += k < warp ? sh.wtot[k] : 0;
+    int off = before + incl - cnt;
+    sh.rowoff[a] = off;
+    if (a == OB_ROWS - 1) sh.rowoff[OB_ROWS] = off + cnt;
+    while (nd) {
+      const int oy = __ffs(nd) - 1;
+      nd &= nd - 1;
+      sh.items[off++] = (unsigned short)((a << 5) | oy);
+    }
+  }
+  __syncthreads();
+  // ---- 3. items ----------------------------------------------------------------------------------------------
+  float wreg[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) wreg[q] = sh.w[15][q];
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  switch (w.oy & 3) {
+    case 0: ob_items<0, VOR, DENSE>(d, sh, world, w, off0, amap0, amap1, cy0, cy1, wreg, s_px, s_py, acc); break;
+    case 1: ob_items<1, VOR, DENSE>(d, sh, world, w, off0, amap0, amap1, cy0, cy1, wreg, s_px, s_py, acc); break;
+    case 2: ob_items<2, VOR, DENSE>(d, sh, world, w, off0, amap0, amap1, cy0, cy1, wreg, s_px, s_py, acc); break;
+    default: ob_items<3, VOR, DENSE>(d, sh, world, w, off0, amap0, amap1, cy0, cy1, wreg, s_px, s_py, acc); break;
+  }
+  if (VOR) {
+    const Sum4 tot = reduce4(acc[0], acc[1], acc[2], acc[3] + acc[4]);
+    if (lane == 0) sh.red[warp][0] = tot.m, sh.red[warp][1] = tot.sx, sh.red[warp][2] = tot.sy, sh.red[warp][3] = tot.s2;
+  }
+  // obstacle channel, row part: A = weight of the tap rows inside the map, B = of those outside it
+  if (tid < 32) {
+    float A = 0.f, B = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int a = 8 * tid - 4 + k;
+      const float wk = sh.w[tid][k];  // zero outside torch's tap range (in particular outside the window)
+      if (a >= amap0 && a < amap1) A += wk;
+      else B += wk;
+    }
+    sh.oA[tid] = A, sh.oB[tid] = B;
+  }
+  __syncthreads();
+  if (VOR && tid < 4) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < OB_WARPS; ++k) t += sh.red[k][tid];
+    wsums[er * 4 + tid] = t;
+  }
+  // ---- 4. height pass + 5. obstacle channel: lane = output column, warp w -> output rows 4 w .. 4 w + 3 ---------
+  float cy_out = 0.f, cy_all = 0.f;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int gy = w.oy + 8 * lane - 4 + q;
+    const float wq = sh.w[lane][q];
+    cy_all += wq;
+    if (!(gy >= 0 && gy < d.N)) cy_out += wq;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ox = warp * 4 + i;
+    const int a0 = 8 * ox - 4;
+    const int ak = a0 + (lane & 15);
+    const uint32_t ndl = (ak >= 0 && ak < OB_ROWS) ? sh.need[ak] : 0u;
+    float acc_l = 0.f;
+    if (__any_sync(0xffffffffu, ndl != 0u)) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const uint32_t nk = __shfl_sync(0xffffffffu, ndl, k);
+        if ((nk >> lane) & 1u) acc_l = fmaf(sh.w[ox][k], sh.tmp[a0 + k][lane], acc_l);
+      }
+    }
+    float *o = dst + (size_t)ox * 32 + lane;
+    o[local_off] = acc_l;
+    o[obst_off] = fmaf(sh.oA[ox], cy_out, sh.oB[ox] * cy_all);
+  }
+  // ---- 6. communication maps ---------------------------------------------------------------------------------
+  if (use_comm && tid == 0) comm_scatter(d, e, r, 32, dst + comm_off, dst + comm_off + 32 * 32);
 }
 
 }  // namespace ccb

@@ -20,6 +20,7 @@ extern "C" {
  *   "vg_generic"  1: tile-ordered whole-map Voronoi (csrc/voronoi.cuh), 0: site-ordered (csrc/vglobal.cuh), -1: by shape
  *   "vg_prefix"   1/0: block prefix sums for the world-map moments (csrc/vglobal.cuh k_vg_lookup) on / off
  *   "vw_generic"  1: generic window Voronoi kernel      "cnn_generic" 1: generic observation kernel
+ *   "obs_v1"      1: the row-ordered fused observation kernel of round 1 instead of the item-ordered one
  *   "vor_rpw"     rows per warp region of the tile-ordered kernel   "vg_warps" / "vg_griddiv" / "vg_part_rpt"
  *   "no_aux" / "no_graph" / "no_wfuse"   1: single stream / no CUDA-graph replay / no fused window moments
  *   "ordered_sums" 1: atomic-free second-stage sums (run-to-run bit-stable moments) */

@@ -151,10 +151,16 @@ def test_block_prefix_path_matches_oracle(monkeypatch, prefix, kind, N, R, seed)
         assert np.allclose(mass, ref_sums[:, 0], rtol=1e-9, atol=1e-9)
         assert np.all(mass[ref_sums[:, 0] == 0.0] == 0.0)
         assert env.GetObjectiveValue() == pytest.approx(ref_sums[:, 3].sum(), rel=1e-9)
-        oenv = orc.Env(orc.params_from(p), wm, pos)
-        ocells = oenv.voronoi_cells()
-        for c, oc in zip(cells, ocells):
-            assert np.allclose(np.array(c.centroid), np.array(oc.centroid[:]), rtol=1e-9, atol=1e-7)
+        cen = np.array([list(c.centroid) for c in cells])
+        ok = ref_sums[:, 0] >= 1e-10
+        assert np.allclose(cen[ok], ref_sums[ok, 1:3] / ref_sums[ok, :1], rtol=1e-9, atol=1e-7)
+        if kind in ("random", "cluster"):
+            # the reference-faithful scan-line cells as well (vertex-mean fallback included); on the lattice / half-integer
+            # sets bisectors run through cell centres, where the scan-line rule (voronoi.cpp:137-141) and the stated
+            # lowest-index rule assign the tie cells differently
+            ocells = orc.Env(orc.params_from(p), wm, pos).voronoi_cells()
+            for c, oc in zip(cells, ocells):
+                assert np.allclose(np.array(c.centroid), np.array(oc.centroid[:]), rtol=1e-9, atol=1e-7)
 
 
 @pytest.mark.parametrize("prefix", [1, 0])

@@ -250,3 +250,52 @@ def test_clear_robot_maps_between_graph_replays():
     torch.cuda.synchronize()
     for e in range(E):
         assert float(obj[0, e]) == pytest.approx(oenvs[e].objective(), rel=1e-9)
+
+
+@pytest.mark.parametrize("fill", [False, True])
+def test_item_ordered_observation_kernel_equals_the_row_ordered_one(monkeypatch, fill):
+    """k_obs_fused (items = non-zero width-pass outputs dealt to the lanes; the product path) against round 1's
+    k_cnn_fused8 (whole window rows per warp; CCB_OBS_V1=1): the same 16-tap order, so the local channel is bit-identical;
+    the obstacle channel is closed-form in the new kernel (different summation order, 1e-6); window moments -> goals
+    equal to 1e-11; 40 steps so that seen regions grow past the 128-column mark, clipped windows, exact ties."""
+    import torch
+
+    import coverage_control as cc
+    from coveragecontrol_b200 import BatchedCoverageSystem, BatchedCVT, _lib
+
+    N, R, E, C = 512, 12, 4, 32
+    p = cc.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    p.pNumRobots = R
+    p.pRobotMapUseUnknownImportance = fill
+    rng = np.random.default_rng(31)
+    worlds = [rng.random((N, N)).astype(np.float32) for _ in range(E)]
+    pos = rng.uniform(1, N - 1, (E, R, 2))
+    c = N / 2.0
+    pos[0, 0], pos[0, 1], pos[0, 2] = [c, c], [c + 11.0, c], [c, c + 11.0]
+    pos[1, 0], pos[1, 1], pos[1, 2] = [2.5, 3.5], [N - 1.5, N - 9.0], [N - 0.7, 0.4]
+    runs = []
+    for v1 in ("1", "0"):
+        monkeypatch.setenv("CCB_OBS_V1", v1)
+        monkeypatch.setenv("CCB_NO_GRAPH", "1")
+        env = BatchedCoverageSystem(p, E, R)
+        for e in range(E):
+            env.set_world(e, worlds[e])
+        env.reset(pos)
+        ctrl = BatchedCVT(env, 2)
+        obs = torch.zeros((E, R, 4, C, C), dtype=torch.float32, device="cuda")
+        trace = []
+        for s in range(40):
+            ctrl.compute_actions()
+            trace.append(ctrl.goals().copy())
+            env.step_actions(ctrl.actions())
+            _lib.check(_lib.load().ccb_env_cnn_input_dev(env._h, C, 1, obs.data_ptr()))
+            if s % 4 == 3:
+                trace.append(obs.cpu().numpy().copy())
+        runs.append(trace)
+    for a, b in zip(*runs):
+        if a.ndim == 3:
+            assert np.allclose(a, b, rtol=1e-11, atol=1e-9), "goals differ"
+        else:
+            assert np.array_equal(a[:, :, 0:3], b[:, :, 0:3]), "local / communication channels differ"
+            assert np.allclose(a[:, :, 3], b[:, :, 3], rtol=1e-5, atol=1e-7), "obstacle channel differs"
