@@ -522,42 +522,49 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
 // the unit of work is an ITEM = one non-zero width-pass output (window row a, output column oy): the 16 taps
 // [8 oy - 4, 8 oy + 12) of row a hold a seen cell.  Items are listed in (row, oy) order and dealt to the lanes, so
 // every lane of every warp does useful work whatever the shape of the seen region.
-//   1. seen bits of the window rows inside the robot's seen box -> shared memory (11 words per row: a pad word
-//      either side so that any 20-bit field can be fetched with one funnel shift); VOR: the own-cell column
-//      interval of every window row (vw_row_interval, as k_voronoi_window);
-//   2. one thread per window row: which oy have a seen tap (nibble arithmetic on the mask words), prefix sum over
-//      the rows, item list (row << 5 | oy);
+// What bounds such a kernel is the chain of dependent memory latencies of ONE robot (position -> window and seen box
+// -> mask words -> map values), not its arithmetic (ncu r02d: 15 K warp instructions, 3 resident CTAs of 256 threads
+// per SM, 24 % warps active): the CTA is therefore small -- 128 threads, ~24 KB of shared memory, 6+ per SM -- and
+// walks the window in four CHUNKS of 8 output rows (64 window rows + 12 rows of tap halo); chunks without a seen
+// row cost nothing.  Per chunk:
+//   1. seen bits of the chunk's rows inside the robot's seen box -> shared memory (11 words per row: a pad word
+//      either side so that any 20-bit field can be fetched with one funnel shift);
+//   2. one thread per row: which oy have a seen tap (nibble arithmetic on the mask words), prefix sum over the
+//      rows, item list (row << 5 | oy);
 //   3. items: a lane loads the 4 or 5 aligned float4 groups under its 16 taps (only those with a seen bit), selects
 //      the seen cells, applies the 16 weights in ascending tap order (the order torchvision's separable antialias
-//      kernel uses) and stores tmp[a][oy].  VOR: the 8 cells of the item's own column group (taps 4..11: every
-//      window cell is the own group of exactly one item) are also reduced into the robot's window-Voronoi moments:
-//      fp64 (s, t = sum i v_i, u = sum i^2 v_i) per item, folded with the group's first column and the row
-//      into five lane-private accumulators; fixed item -> lane assignment, fixed reduction tree: bit-stable sums;
-//   4. height pass: warp w owns output rows 4w .. 4w+3, skips those whose 16 tap rows hold no item, sums the
-//      taps in ascending row order;
-//   5. obstacle channel in closed form: obstacle(a, b) = 1 - in_x(a) in_y(b) is separable, so its resized value is
-//      A(ox) cy_out(oy) + B(ox) cy_all(oy) with A / B = the tap weights of the rows inside / outside the map and
-//      cy_out / cy_all = the tap weights of the columns outside the map / all columns (0 when the window lies
-//      inside the map);
-//   6. (use_comm) the two communication-map channels: zero-filled by the CTA, scattered by one thread.
+//      kernel uses) and stores tmp[row][oy].  VOR: the 8 cells of the item's own column group (taps 4..11: every
+//      window cell is the own group of exactly one item of the chunk that owns its row) are also reduced into the
+//      robot's window-Voronoi moments: fp64 (s, t = sum i v_i, u = sum i^2 v_i) per item, folded with the group's
+//      first column and the row into five lane-private accumulators; fixed item -> lane assignment, fixed
+//      reduction tree: bit-stable sums;
+//   4. height pass: warp w owns two of the chunk's output rows, sums the taps in ascending row order.
+// Around the chunks: the own-cell column interval of every window row (VOR; vw_row_interval, as k_voronoi_window),
+// the obstacle channel in closed form -- obstacle(a, b) = 1 - in_x(a) in_y(b) is separable, so its resized value
+// is A(ox) cy_out(oy) + B(ox) cy_all(oy) with A / B = the tap weights of the rows inside / outside the map and
+// cy_out / cy_all = the tap weights of the columns outside the map / all columns (exactly 0 when the window lies
+// inside the map) -- and (use_comm) the two communication-map channels by one warp: a lane per neighbour, cells hit
+// by several neighbours summed in ascending neighbour order.
 // wfull[o][k] = weight of input index 8 o - 4 + k (zero outside torch's tap range); rows 1 .. 30 are identical
 // (the host checks this before it picks the kernel): their 16 weights live in registers.
-constexpr int OB_THREADS = 256;
+constexpr int OB_THREADS = 128;
 constexpr int OB_WARPS = OB_THREADS / 32;
-constexpr int OB_ROWS = 256;
-constexpr int OB_WORDS = 11;  // pad + 9 mask words + pad
+constexpr int OB_CHUNKS = 4;                  // 8 output rows = 64 window rows each
+constexpr int OB_CROWS = 64 + 12;             // chunk rows incl. the tap halo: window rows 64 c - 4 .. 64 c + 71
+constexpr int OB_WORDS = 11;                  // pad + 9 mask words + pad
+constexpr int OB_CAP = OB_CROWS * 32;         // items of a chunk at most
 
 struct ObsShared {
-  float tmp[OB_ROWS][32];               // width-pass results; entry (a, oy) valid iff need[a] bit oy
-  uint32_t mask[OB_ROWS * OB_WORDS];    // seen & in-map & in-window bits; word 1 + j <-> map word wbase + j
-  uint32_t need[OB_ROWS];
-  int rowoff[OB_ROWS + 1];
-  unsigned short items[OB_ROWS * 32];
+  float tmp[OB_CROWS][32];              // width-pass results; entry (row, oy) valid iff need[row] bit oy
+  uint32_t mask[OB_CROWS * OB_WORDS];   // seen & in-map & in-window bits; word 1 + j <-> map word wbase + j
+  uint32_t need[OB_CROWS];
+  unsigned short items[OB_CAP];
   float w[32][16];
   float oA[32], oB[32];
-  int lo[OB_ROWS], hi[OB_ROWS];         // VOR: own-cell interval, map columns
-  uint32_t exact[OB_ROWS / 32];         // VOR: rows that need the per-cell rule
+  int lo[256], hi[256];                 // VOR: own-cell interval of every window row, map columns
+  uint32_t exact[8];                    // VOR: rows that need the per-cell rule
   int wtot[OB_WARPS];
+  int total;
   int K;
   double red[OB_WARPS][4];
 };
@@ -569,21 +576,22 @@ __device__ __forceinline__ unsigned ob_range(int lo, int hi, int c0, int n) {
   return ((1u << b) - 1u) & ~((1u << a) - 1u);
 }
 
+// items of one chunk; rbase = window row of the chunk's row 0, [own0, own1) = window rows whose moments this chunk adds
 template <int S, bool VOR, bool DENSE>
 __device__ __forceinline__ void ob_items(const EnvDev &d, ObsShared &sh, const float *__restrict__ world, const Window &w,
-                                         int off0, int amap0, int amap1, int cy0, int cy1, const float (&wreg)[16],
-                                         const double *s_px, const double *s_py, double (&acc)[5]) {
+                                         int off0, int rbase, int own0, int own1, int amap0, int amap1, int cy0, int cy1,
+                                         const float (&wreg)[16], const double *s_px, const double *s_py, double (&acc)[5]) {
   constexpr int NV = S == 0 ? 4 : 5;  // aligned 4-cell groups under the 16 taps
-  const int total = sh.rowoff[OB_ROWS];
+  const int total = sh.total;
   const float fill = d.fill;
 #pragma unroll 1
   for (int i = threadIdx.x; i < total; i += OB_THREADS) {
     const int it = sh.items[i];
-    const int a = it >> 5, oy = it & 31;
-    const int row = w.ox + a;
+    const int cr = it >> 5, oy = it & 31;         // chunk row, output column
+    const int a = rbase + cr, row = w.ox + a;
     const int gyb = w.oy + 8 * oy - 4 - S;        // 16-byte aligned map column of the first group
     const int pos = off0 + 8 * oy - 4 - S + 32;   // its bit in the row's 11 mask words
-    const uint32_t *m = sh.mask + a * OB_WORDS + (pos >> 5);
+    const uint32_t *m = sh.mask + cr * OB_WORDS + (pos >> 5);
     const unsigned vis = __funnelshift_r(m[0], m[1], pos & 31) & ((1u << (4 * NV)) - 1u);
     float4 v[NV];
 #pragma unroll
@@ -613,8 +621,8 @@ __device__ __forceinline__ void ob_items(const EnvDev &d, ObsShared &sh, const f
 #pragma unroll
       for (int q = 0; q < 16; ++q) t = fmaf(sh.w[oy][q], c[q], t);
     }
-    sh.tmp[a][oy] = t;
-    if (VOR) {
+    sh.tmp[cr][oy] = t;
+    if (VOR && a >= own0 && a < own1) {
       // the item's own column group (taps 4 .. 11 = window columns 8 oy .. 8 oy + 7) inside the robot's cell
       const int c0 = w.oy + 8 * oy;
       unsigned ob = ob_range(sh.lo[a], sh.hi[a], c0, 8) & ((DENSE ? inm : vis) >> (S + 4)) & 0xffu;
@@ -647,8 +655,53 @@ __device__ __forceinline__ void ob_items(const EnvDev &d, ObsShared &sh, const f
   }
 }
 
+// the two communication-map planes of robot r (already zeroed), by ONE warp: a lane per other robot, 32 at a time;
+// a cell hit by several robots of a group of 32 receives their sum in ascending index (what a sequential loop adds)
+__device__ __forceinline__ void comm_scatter_warp(const EnvDev &d, int e, int r, int C, float *ox, float *oy) {
+  const int lane = threadIdx.x & 31;
+  const double *pos = d.pos_g + (size_t)e * d.R * 2;
+  const float denom = (float)(d.comm_range * d.res * 2.0);
+  const float center = (float)(C / 2.0 - d.res / 2.0);
+  const float cr = (float)d.comm_range;
+  const double sx = pos[2 * r], sy = pos[2 * r + 1];
+  for (int base = 0; base < d.R; base += 32) {
+    const int j = base + lane;
+    int idx = -1;
+    float vx = 0.f, vy = 0.f;
+    if (j < d.R && j != r) {
+      // coverage_system.cpp:274-291: relative position p_j - p_r (stored negated for j < r)
+      double dx, dy;
+      if (j > r) dx = pos[2 * j] - sx, dy = pos[2 * j + 1] - sy;
+      else dx = -(sx - pos[2 * j]), dy = -(sy - pos[2 * j + 1]);
+      if (sqrt(dx * dx + dy * dy) < d.comm_range) {
+        const float fx = (float)dx, fy = (float)dy;
+        const float ix = rintf(__fadd_rn(__fdiv_rn(__fmul_rn(fx, (float)C), denom), center));
+        const float iy = rintf(__fadd_rn(__fdiv_rn(__fmul_rn(fy, (float)C), denom), center));
+        const int xi = (int)ix, yi = (int)iy;
+        if (xi >= 0 && xi < C && yi >= 0 && yi < C) idx = xi * C + yi, vx = __fdiv_rn(fx, cr), vy = __fdiv_rn(fy, cr);
+      }
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, idx >= 0);
+    if (any == 0u) continue;  // warp-uniform
+    // ordered sum over the lanes that hit my cell; the lowest of them writes
+    float ax = 0.f, ay = 0.f;
+    bool first = true;
+    for (unsigned todo = any; todo; todo &= todo - 1) {
+      const int k = __ffs(todo) - 1;
+      const int ik = __shfl_sync(0xffffffffu, idx, k);
+      const float xk = __shfl_sync(0xffffffffu, vx, k), yk = __shfl_sync(0xffffffffu, vy, k);
+      if (ik == idx) {
+        if (k < lane) first = false;
+        ax = __fadd_rn(ax, xk), ay = __fadd_rn(ay, yk);
+      }
+    }
+    if (idx >= 0 && first) ox[idx] = __fadd_rn(ox[idx], ax), oy[idx] = __fadd_rn(oy[idx], ay);
+    __syncwarp();
+  }
+}
+
 template <bool VOR, bool DENSE>
-__global__ void __launch_bounds__(OB_THREADS, 3)
+__global__ void __launch_bounds__(OB_THREADS, 6)
 k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__restrict__ out, size_t robot_stride,
             size_t local_off, size_t obst_off, size_t comm_off, int use_comm, double *__restrict__ wsums /* VOR: [E][R][4] */) {
   extern __shared__ __align__(16) unsigned char ob_smem[];
@@ -660,7 +713,7 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
   const size_t er = (size_t)e * d.R + r;
   float *dst = out + er * robot_stride;
   for (int t = tid; t < 32 * 16; t += OB_THREADS) sh.w[t >> 4][t & 15] = wfull[t];
-  if (use_comm) {  // the communication channels start as zeros (scattered into at the very end)
+  if (use_comm) {  // the communication channels start as zeros
     float4 *cz = reinterpret_cast<float4 *>(dst + comm_off);
     for (int t = tid; t < 2 * 32 * 32 / 4; t += OB_THREADS) cz[t] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -679,8 +732,9 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
     alo = max(alo, box[0] - w.ox), ahi = min(ahi, box[1] - w.ox);
     wlo = max(0, (box[2] >> 5) - wbase), whi = min(9, ((box[3] - 1) >> 5) - wbase + 1);
   }
+  const int nw_s = max(whi - wlo, 0);
   if (VOR) {
-    if (tid < OB_ROWS / 32) sh.exact[tid] = 0u;
+    if (tid < 8) sh.exact[tid] = 0u;
     if (warp == 0) {
       // sites: self, then the neighbours within communication range in ascending index (decentralized_cvt.h:100-120)
       const double *pos = d.pos_g + (size_t)e * d.R * 2;
@@ -706,118 +760,22 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
       if (lane == 0) sh.K = n - 1;
     }
   }
-  // ---- 1. mask words: zeros everywhere, then the words inside the box -----------------------------------------
-  for (int t = tid; t < OB_ROWS * OB_WORDS; t += OB_THREADS) sh.mask[t] = 0u;
-  __syncthreads();
-  if (VOR) {  // own-cell interval of the rows that can hold a cell (thread a <-> window row a)
-    const int a = tid, ncols = w.y1 - w.y0;
-    int lo = 0, hi = 0;
-    if (a >= alo && a < ahi && ncols > 0) {
-      if (sh.K == 0) lo = 0, hi = ncols;
-      else if (vw_row_interval(d.res, w.ox + a, w.y0, ncols, sh.K, s_px, s_py, lo, hi)) atomicOr(&sh.exact[a >> 5], 1u << (a & 31));
-    }
-    sh.lo[a] = w.y0 + lo, sh.hi[a] = w.y0 + max(hi, lo);
-  }
-  {
-    const int nrow_s = max(ahi - alo, 0), nw_s = max(whi - wlo, 0), nstage = nrow_s * nw_s;
-    constexpr int STAGE = 4;
-#pragma unroll 1
-    for (int t0 = 0; t0 < nstage; t0 += STAGE * OB_THREADS) {
-      uint32_t mw[STAGE];
-#pragma unroll
-      for (int k = 0; k < STAGE; ++k) {
-        const int t = t0 + tid + k * OB_THREADS;
-        const int ar = t / nw_s, j = wlo + t - ar * nw_s;
-        const int wd = wbase + j;
-        uint32_t mv = 0u;
-        if (t < nstage && wd >= 0 && wd < d.NW) {
-          const uint32_t keep = vw_range_bits(cy0, cy1, wd << 5);
-          if (keep) mv = __ldg(plane + (size_t)(w.ox + alo + ar) * d.NW + wd) & keep;
-        }
-        mw[k] = mv;
+  __syncthreads();  // weights, neighbour list, zeroed communication planes
+  if (use_comm && warp == OB_WARPS - 1) comm_scatter_warp(d, e, r, 32, dst + comm_off, dst + comm_off + 32 * 32);
+  if (VOR) {  // own-cell interval of the rows that can hold a cell
+    const int ncols = w.y1 - w.y0;
+    for (int a = alo + tid; a < ahi; a += OB_THREADS) {
+      int lo = 0, hi = 0;
+      if (ncols > 0) {
+        if (sh.K == 0) lo = 0, hi = ncols;
+        else if (vw_row_interval(d.res, w.ox + a, w.y0, ncols, sh.K, s_px, s_py, lo, hi)) atomicOr(&sh.exact[a >> 5], 1u << (a & 31));
       }
-#pragma unroll
-      for (int k = 0; k < STAGE; ++k) {
-        const int t = t0 + tid + k * OB_THREADS;
-        if (t >= nstage) continue;
-        const int ar = t / nw_s, j = wlo + t - ar * nw_s;
-        sh.mask[(alo + ar) * OB_WORDS + 1 + j] = mw[k];
-      }
+      sh.lo[a] = w.y0 + lo, sh.hi[a] = w.y0 + max(hi, lo);
     }
   }
-  __syncthreads();
-  // ---- 2. which outputs of row a are non-zero; item list ------------------------------------------------------
-  {
-    const int a = tid;
-    uint32_t nd = 0u;
-    if (a >= alo && a < ahi) {
-      if (DENSE) {
-        // every output whose 16 taps touch an in-map column of this in-map row
-        for (int oy = 0; oy < 32; ++oy)
-          if (ob_range(cy0, cy1, w.oy + 8 * oy - 4, 16)) nd |= 1u << oy;
-      } else {
-        const uint32_t *mrow = sh.mask + a * OB_WORDS + 1;
-        uint32_t tprev = 0u, tcur, tnext;
-        {
-          const uint32_t x0 = __funnelshift_r(mrow[0], mrow[1], off0);
-          uint32_t t = x0 | (x0 >> 1);
-          tcur = (t | (t >> 2)) & 0x11111111u;  // bit 4 n: nibble n (4 window columns) holds a seen cell
-        }
-#pragma unroll
-        for (int mI = 0; mI < 8; ++mI) {
-          tnext = 0u;
-          if (mI < 7) {
-            const uint32_t x1 = __funnelshift_r(mrow[mI + 1], mrow[mI + 2], off0);
-            uint32_t t = x1 | (x1 >> 1);
-            tnext = (t | (t >> 2)) & 0x11111111u;
-          }
-          // output 4 mI + g reads nibbles 2 g - 1 .. 2 g + 2 of this word (and of its neighbours at the ends)
-          const uint32_t u = tcur | (tcur >> 4) | (tcur << 4) | (tcur >> 8) | (tprev >> 28) | (tnext << 24);
-          nd |= ((((u & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << (4 * mI);
-          tprev = tcur, tcur = tnext;
-        }
-      }
-    }
-    sh.need[a] = nd;
-    // exclusive prefix sum of the item counts over the 256 rows
-    const int cnt = __popc(nd);
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int up = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += up;
-    }
-    if (lane == 31) sh.wtot[warp] = incl;
-    __syncthreads();
-    int before = 0;
-#pragma unroll
-    for (int k = 0; k < OB_WARPS; ++k) before += k < warp ? sh.wtot[k] : 0;
-    int off = before + incl - cnt;
-    sh.rowoff[a] = off;
-    if (a == OB_ROWS - 1) sh.rowoff[OB_ROWS] = off + cnt;
-    while (nd) {
-      const int oy = __ffs(nd) - 1;
-      nd &= nd - 1;
-      sh.items[off++] = (unsigned short)((a << 5) | oy);
-    }
-  }
-  __syncthreads();
-  // ---- 3. items ----------------------------------------------------------------------------------------------
-  float wreg[16];
-#pragma unroll
-  for (int q = 0; q < 16; ++q) wreg[q] = sh.w[15][q];
-  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  switch (w.oy & 3) {
-    case 0: ob_items<0, VOR, DENSE>(d, sh, world, w, off0, amap0, amap1, cy0, cy1, wreg, s_px, s_py, acc); break;
-    case 1: ob_items<1, VOR, DENSE>(d, sh, world, w, off0, amap0, amap1, cy0, cy1, wreg, s_px, s_py, acc); break;
-    case 2: ob_items<2, VOR, DENSE>(d, sh, world, w, off0, amap0, amap1, cy0, cy1, wreg, s_px, s_py, acc); break;
-    default: ob_items<3, VOR, DENSE>(d, sh, world, w, off0, amap0, amap1, cy0, cy1, wreg, s_px, s_py, acc); break;
-  }
-  if (VOR) {
-    const Sum4 tot = reduce4(acc[0], acc[1], acc[2], acc[3] + acc[4]);
-    if (lane == 0) sh.red[warp][0] = tot.m, sh.red[warp][1] = tot.sx, sh.red[warp][2] = tot.sy, sh.red[warp][3] = tot.s2;
-  }
-  // obstacle channel, row part: A = weight of the tap rows inside the map, B = of those outside it
+  // obstacle channel: A = weight of the tap rows inside the map, B = of those outside it (per output row);
+  // cy_out / cy_all = weight of the tap columns outside the map / of all of them (per output column = lane)
+  const bool inside = w.ox >= 0 && w.ox + 256 <= d.N && w.oy >= 0 && w.oy + 256 <= d.N;
   if (tid < 32) {
     float A = 0.f, B = 0.f;
 #pragma unroll
@@ -829,42 +787,166 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
     }
     sh.oA[tid] = A, sh.oB[tid] = B;
   }
-  __syncthreads();
-  if (VOR && tid < 4) {
-    double t = 0.0;
-#pragma unroll
-    for (int k = 0; k < OB_WARPS; ++k) t += sh.red[k][tid];
-    wsums[er * 4 + tid] = t;
-  }
-  // ---- 4. height pass + 5. obstacle channel: lane = output column, warp w -> output rows 4 w .. 4 w + 3 ---------
   float cy_out = 0.f, cy_all = 0.f;
+  if (!inside) {
 #pragma unroll
-  for (int q = 0; q < 16; ++q) {
-    const int gy = w.oy + 8 * lane - 4 + q;
-    const float wq = sh.w[lane][q];
-    cy_all += wq;
-    if (!(gy >= 0 && gy < d.N)) cy_out += wq;
+    for (int q = 0; q < 16; ++q) {
+      const int gy = w.oy + 8 * lane - 4 + q;
+      const float wq = sh.w[lane][q];
+      cy_all += wq;
+      if (!(gy >= 0 && gy < d.N)) cy_out += wq;
+    }
   }
+  float wreg[16];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int ox = warp * 4 + i;
-    const int a0 = 8 * ox - 4;
-    const int ak = a0 + (lane & 15);
-    const uint32_t ndl = (ak >= 0 && ak < OB_ROWS) ? sh.need[ak] : 0u;
-    float acc_l = 0.f;
-    if (__any_sync(0xffffffffu, ndl != 0u)) {
+  for (int q = 0; q < 16; ++q) wreg[q] = sh.w[15][q];
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+
+#pragma unroll 1
+  for (int ch = 0; ch < OB_CHUNKS; ++ch) {
+    const int rbase = 64 * ch - 4;                                   // window row of chunk row 0
+    const int r0 = max(alo, rbase), r1 = min(ahi, rbase + OB_CROWS);  // window rows of this chunk that can hold a cell
+    const int ox0 = 8 * ch;
+    if (r1 <= r0) {  // CTA-uniform: nothing seen under these 8 output rows
+      for (int t = tid; t < 8 * 32; t += OB_THREADS) {
+        const int ox = ox0 + (t >> 5);  // (t & 31 == lane: the thread's own output column)
+        float *o = dst + (size_t)ox * 32 + lane;
+        o[local_off] = 0.f;
+        o[obst_off] = inside ? 0.f : fmaf(sh.oA[ox], cy_out, sh.oB[ox] * cy_all);
+      }
+      continue;
+    }
+    __syncthreads();  // the previous chunk's height pass is done with tmp / need / mask
+    // ---- 1. mask words of rows r0 .. r1 - 1 (chunk rows r0 - rbase ..); pad words and words outside the box are zero
+    {
+      const int nrow = r1 - r0;
+      for (int t = tid; t < nrow * OB_WORDS; t += OB_THREADS) {
+        const int ar = t / OB_WORDS, j = t - ar * OB_WORDS;  // j = 0 / 10: pads; 1 + wlo .. whi: loaded below
+        if (j < 1 + wlo || j >= 1 + whi) sh.mask[(r0 - rbase + ar) * OB_WORDS + j] = 0u;
+      }
+      const int nstage = nrow * nw_s;
+      constexpr int STAGE = 4;
+#pragma unroll 1
+      for (int t0 = 0; t0 < nstage; t0 += STAGE * OB_THREADS) {
+        uint32_t mw[STAGE];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const uint32_t nk = __shfl_sync(0xffffffffu, ndl, k);
-        if ((nk >> lane) & 1u) acc_l = fmaf(sh.w[ox][k], sh.tmp[a0 + k][lane], acc_l);
+        for (int k = 0; k < STAGE; ++k) {
+          const int t = t0 + tid + k * OB_THREADS;
+          const int ar = t / nw_s, j = wlo + t - ar * nw_s;
+          const int wd = wbase + j;
+          uint32_t mv = 0u;
+          if (t < nstage && wd >= 0 && wd < d.NW) {
+            const uint32_t keep = vw_range_bits(cy0, cy1, wd << 5);
+            if (keep) mv = __ldg(plane + (size_t)(w.ox + r0 + ar) * d.NW + wd) & keep;
+          }
+          mw[k] = mv;
+        }
+#pragma unroll
+        for (int k = 0; k < STAGE; ++k) {
+          const int t = t0 + tid + k * OB_THREADS;
+          if (t >= nstage) continue;
+          const int ar = t / nw_s, j = wlo + t - ar * nw_s;
+          sh.mask[(r0 - rbase + ar) * OB_WORDS + 1 + j] = mw[k];
+        }
       }
     }
-    float *o = dst + (size_t)ox * 32 + lane;
-    o[local_off] = acc_l;
-    o[obst_off] = fmaf(sh.oA[ox], cy_out, sh.oB[ox] * cy_all);
+    __syncthreads();
+    // ---- 2. which outputs of a row are non-zero; item list (thread <-> chunk row) ---------------------------
+    {
+      const int cr = tid, a = rbase + cr;
+      uint32_t nd = 0u;
+      if (cr < OB_CROWS && a >= r0 && a < r1) {
+        if (DENSE) {
+          // every output whose 16 taps touch an in-map column of this in-map row
+          for (int oy = 0; oy < 32; ++oy)
+            if (ob_range(cy0, cy1, w.oy + 8 * oy - 4, 16)) nd |= 1u << oy;
+        } else {
+          const uint32_t *mrow = sh.mask + cr * OB_WORDS + 1;
+          uint32_t tprev = 0u, tcur, tnext;
+          {
+            const uint32_t x0 = __funnelshift_r(mrow[0], mrow[1], off0);
+            uint32_t t = x0 | (x0 >> 1);
+            tcur = (t | (t >> 2)) & 0x11111111u;  // bit 4 n: nibble n (4 window columns) holds a seen cell
+          }
+#pragma unroll
+          for (int mI = 0; mI < 8; ++mI) {
+            tnext = 0u;
+            if (mI < 7) {
+              const uint32_t x1 = __funnelshift_r(mrow[mI + 1], mrow[mI + 2], off0);
+              uint32_t t = x1 | (x1 >> 1);
+              tnext = (t | (t >> 2)) & 0x11111111u;
+            }
+            // output 4 mI + g reads nibbles 2 g - 1 .. 2 g + 2 of this word (and of its neighbours at the ends)
+            const uint32_t u = tcur | (tcur >> 4) | (tcur << 4) | (tcur >> 8) | (tprev >> 28) | (tnext << 24);
+            nd |= ((((u & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << (4 * mI);
+            tprev = tcur, tcur = tnext;
+          }
+        }
+      }
+      if (cr < OB_CROWS) sh.need[cr] = nd;
+      // exclusive prefix sum of the item counts over the chunk's rows
+      const int cnt = __popc(nd);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      if (lane == 31) sh.wtot[warp] = incl;
+      __syncthreads();
+      int before = 0;
+#pragma unroll
+      for (int k = 0; k < OB_WARPS; ++k) before += k < warp ? sh.wtot[k] : 0;
+      int off = before + incl - cnt;
+      if (tid == OB_THREADS - 1) sh.total = off + cnt;
+      while (nd) {
+        const int oy = __ffs(nd) - 1;
+        nd &= nd - 1;
+        sh.items[off++] = (unsigned short)((cr << 5) | oy);
+      }
+    }
+    __syncthreads();
+    // ---- 3. items: rows 64 ch .. 64 ch + 63 also add their own-cell moments (every window row belongs to one chunk)
+    {
+      const int own0 = 64 * ch, own1 = 64 * ch + 64;
+      switch (w.oy & 3) {
+        case 0: ob_items<0, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, wreg, s_px, s_py, acc); break;
+        case 1: ob_items<1, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, wreg, s_px, s_py, acc); break;
+        case 2: ob_items<2, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, wreg, s_px, s_py, acc); break;
+        default: ob_items<3, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, wreg, s_px, s_py, acc); break;
+      }
+    }
+    __syncthreads();
+    // ---- 4. height pass: lane = output column, warp -> output rows ox0 + 2 warp, + 1 ---------------------------
+#pragma unroll
+    for (int i = 0; i < 8 / OB_WARPS; ++i) {
+      const int oxl = warp * (8 / OB_WARPS) + i, ox = ox0 + oxl;
+      const int c0r = 8 * oxl;  // chunk row of tap 0 (window row 8 ox - 4)
+      const uint32_t ndl = sh.need[c0r + (lane & 15)];
+      float acc_l = 0.f;
+      if (__any_sync(0xffffffffu, ndl != 0u)) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const uint32_t nk = __shfl_sync(0xffffffffu, ndl, k);
+          if ((nk >> lane) & 1u) acc_l = fmaf(sh.w[ox][k], sh.tmp[c0r + k][lane], acc_l);
+        }
+      }
+      float *o = dst + (size_t)ox * 32 + lane;
+      o[local_off] = acc_l;
+      o[obst_off] = inside ? 0.f : fmaf(sh.oA[ox], cy_out, sh.oB[ox] * cy_all);
+    }
   }
-  // ---- 6. communication maps ---------------------------------------------------------------------------------
-  if (use_comm && tid == 0) comm_scatter(d, e, r, 32, dst + comm_off, dst + comm_off + 32 * 32);
+  if (VOR) {
+    const Sum4 tot = reduce4(acc[0], acc[1], acc[2], acc[3] + acc[4]);
+    if (lane == 0) sh.red[warp][0] = tot.m, sh.red[warp][1] = tot.sx, sh.red[warp][2] = tot.sy, sh.red[warp][3] = tot.s2;
+    __syncthreads();
+    if (tid < 4) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < OB_WARPS; ++k) t += sh.red[k][tid];
+      wsums[er * 4 + tid] = t;
+    }
+  }
 }
 
 }  // namespace ccb
