@@ -554,42 +554,66 @@ def main():
     win_bits = LOCAL * (LOCAL // 32 + 1) * 4.0          # the mask words of one window
     obs_out = 16.0 * CNN * CNN                          # 4 channels x C^2 floats
     prefix_on = os.environ.get("CCB_VG_PREFIX", "1") != "0"
-    look_bytes = pairs * (4.0 + 2 * 48.0 + 2 * 32.0) if prefix_on else 4.0 * cells * E
+    fused_on = prefix_on and os.environ.get("CCB_VG_FUSED", "1") != "0"
+    rows_all = float(N_WORLD * E)
+    # fused partition + moments: one 64-byte prefix entry + one 32-byte map sector per Voronoi boundary of a row, one
+    # entry per row for its total, the band moments out; look-up kernel: two entries + two sectors + the table word per pair
+    part_bytes = 4.0 * N_ROBOTS * N_WORLD * E
+    if fused_on:
+        chain_bytes = (pairs - rows_all) * 96.0 + rows_all * 64.0 + 32.0 * N_ROBOTS * (N_WORLD / 128) * E
+    elif prefix_on:
+        chain_bytes = part_bytes + pairs * (4.0 + 2 * 64.0 + 2 * 32.0)
+    else:
+        chain_bytes = part_bytes + 4.0 * cells * E
     survey = {
-        "voronoi_global(partition+moments+fixup)": (0, 4.0 * cells * E, look_bytes + 4.0 * N_ROBOTS * N_WORLD * E),
-        "k_vg_lookup" if prefix_on else "k_vg_reduce": (6, 4.0 * cells * E, look_bytes),
-        "k_vg_partition": (7, 4.0 * N_ROBOTS * N_WORLD * E, 4.0 * N_ROBOTS * N_WORLD * E),
+        "voronoi_global(whole chain)": (0, 4.0 * cells * E, chain_bytes),
+        ("k_vg_partition<moments>" if fused_on else "k_vg_partition"): (7, 4.0 * cells * E if fused_on else part_bytes,
+                                                                         chain_bytes if fused_on else part_bytes),
+        ("k_vg_bandsum" if fused_on else "k_vg_lookup" if prefix_on else "k_vg_reduce"):
+            (6, 0.0 if fused_on else 4.0 * cells * E, 64.0 * N_ROBOTS * (N_WORLD / 128) * E if fused_on else chain_bytes - part_bytes),
         "k_vg_fixup": (9, 0.0, 0.0),
         "k_voronoi_window": (2, 4.0 * N_ROBOTS * LOCAL * LOCAL * E, 4.0 * seen_cells + win_bits * ER),
-        "k_cnn_fused8(+k_comm_maps)": (4, (4.0 * N_ROBOTS * LOCAL * LOCAL + 16.0 * N_ROBOTS * CNN * CNN) * E,
-                                       4.0 * seen_cells + (win_bits + obs_out) * ER),
-        "k_cnn_fused8<window Voronoi>(+k_comm_maps)": (8, (8.0 * N_ROBOTS * LOCAL * LOCAL + 16.0 * N_ROBOTS * CNN * CNN) * E,
-                                                       4.0 * seen_cells + (win_bits + obs_out) * ER),
+        "k_obs_fused(local+obstacle+comm)": (4, (4.0 * N_ROBOTS * LOCAL * LOCAL + 16.0 * N_ROBOTS * CNN * CNN) * E,
+                                             4.0 * seen_cells + (win_bits + obs_out) * ER),
+        "k_obs_fused<window Voronoi>": (8, (8.0 * N_ROBOTS * LOCAL * LOCAL + 16.0 * N_ROBOTS * CNN * CNN) * E,
+                                        4.0 * seen_cells + (win_bits + obs_out) * ER),
         "k_mark_windows": (3, 12.0 * N_ROBOTS * SENSOR * SENSOR * E, 24.0 * SENSOR * (SENSOR // 32 + 2) * ER),
         "k_finalize_cells": (5, 32.0 * N_ROBOTS * E, 32.0 * N_ROBOTS * E),
     }
     kernels = {}
-    for name, (which, sbytes, rbytes) in survey.items():
-        iters = 10
-        fn = lambda w=which: _lib.check(lib.ccb_bench_kernel(batch._h, w, 1, obs.data_ptr()))  # noqa: E731
+
+    def time_kernel(which, sbytes, rbytes, iters=10):
+        fn = lambda: _lib.check(lib.ccb_bench_kernel(batch._h, which, 1, obs.data_ptr()))  # noqa: E731
         ms, _ = timed(fn, iters, 3)
         t = ms / iters * 1e-3
-        kernels[name] = {"ms": ms / iters, "survey_bytes": sbytes, "survey_gbs": sbytes / t / 1e9,
-                         "required_bytes": rbytes, "required_gbs": rbytes / t / 1e9}
-    if prefix_on:  # the streaming kernel the look-ups replace (still the CentralizedCVT / labels path), for comparison
+        return {"ms": ms / iters, "survey_bytes": sbytes, "survey_gbs": sbytes / t / 1e9,
+                "required_bytes": rbytes, "required_gbs": rbytes / t / 1e9}
+
+    for name, (which, sbytes, rbytes) in survey.items():
+        kernels[name] = time_kernel(which, sbytes, rbytes)
+    # the kernels the default path replaces, timed on the same state (A/B): the interval table + site-ordered look-ups,
+    # and the streaming reduce (still the CentralizedCVT / labels path)
+    if fused_on:
+        batch.set_option("vg_fused", 0)
+        _lib.check(lib.ccb_bench_kernel(batch._h, 0, 1, obs.data_ptr()))
+        kernels["A/B k_vg_partition(table only)"] = time_kernel(7, part_bytes, part_bytes)
+        kernels["A/B k_vg_lookup(site-ordered)"] = time_kernel(6, 4.0 * cells * E, pairs * (4.0 + 2 * 64.0 + 2 * 32.0))
+        batch.set_option("vg_fused", 1)
+    if prefix_on:
         batch.set_option("vg_prefix", 0)
         _lib.check(lib.ccb_bench_kernel(batch._h, 0, 1, obs.data_ptr()))
-        ms, _ = timed(lambda: _lib.check(lib.ccb_bench_kernel(batch._h, 6, 1, obs.data_ptr())), 10, 3)
+        kernels["A/B k_vg_reduce(streaming)"] = time_kernel(6, 4.0 * cells * E, 4.0 * cells * E)
         batch.set_option("vg_prefix", 1)
         _lib.check(lib.ccb_bench_kernel(batch._h, 0, 1, obs.data_ptr()))
-        kernels["k_vg_reduce(streaming, prefix off)"] = {
-            "ms": ms / 10, "survey_bytes": 4.0 * cells * E, "survey_gbs": 4.0 * cells * E / (ms / 10 * 1e-3) / 1e9,
-            "required_bytes": 4.0 * cells * E, "required_gbs": 4.0 * cells * E / (ms / 10 * 1e-3) / 1e9}
+    batch.set_option("obs_v1", 1)
+    kernels["A/B k_cnn_fused8<window Voronoi>(+k_comm_maps), round 1"] = time_kernel(
+        8, (8.0 * N_ROBOTS * LOCAL * LOCAL + 16.0 * N_ROBOTS * CNN * CNN) * E, 4.0 * seen_cells + (win_bits + obs_out) * ER)
+    batch.set_option("obs_v1", 0)
     peak, peak_src = measured_peak_gbs()
     # the dominant single kernel of the step
     # (the step itself runs the fused observation + window-Voronoi variant, not the two kernels it replaces)
-    look = "k_vg_lookup" if prefix_on else "k_vg_reduce"
-    dom = max((look, "k_vg_partition", "k_cnn_fused8<window Voronoi>(+k_comm_maps)"), key=lambda k: kernels[k]["ms"])
+    part = "k_vg_partition<moments>" if fused_on else "k_vg_partition"
+    dom = max((part, "k_obs_fused<window Voronoi>"), key=lambda k: kernels[k]["ms"])
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture

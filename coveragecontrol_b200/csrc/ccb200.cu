@@ -573,6 +573,8 @@ struct ccb_env {
   VgPfx *d_vg_pfx = nullptr;    // [E][N][N / 8 + 1] x 48 B, allocated on first use, rebuilt per environment when its world map is set
   std::vector<char> pfx_valid;  // [E]: the entries of environment e match its world map
   int *d_pfx_list = nullptr;    // [E] environments to rebuild
+  double *d_vg_band = nullptr;  // [E][ceil(N / 128)][R][4] band moments of the fused partition + moments kernel
+  bool vg_fused = true;         // world-map moments inside the row partition kernel (off: interval table + k_vg_lookup)
   bool cnn_generic = false;     // test option: the generic observation kernel even where the fused one applies
   bool obs_v1 = false;          // test option: the row-ordered fused observation kernel of round 1 (A/B timing)
 };
@@ -662,7 +664,17 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
       CCB_CUDA(cudaMalloc(&env->d_vg_span, sizeof(int) * 2 * (size_t)d.E * d.R));
       CCB_CUDA(cudaMalloc(&env->d_vg_items, sizeof(int) * (size_t)d.E * (d.R + 1)));
     }
-    if (stages & 1) {
+    bool lookup = false;
+    if (src == SRC_WORLD && !labels && env->vg_prefix) {
+      if (ensure_prefix(env)) return 1;
+      lookup = env->d_vg_pfx != nullptr;
+    }
+    const int rows = row1 - row0;
+    const int nbands = (rows + VG_PART_THREADS - 1) / VG_PART_THREADS;
+    const bool fused = lookup && env->vg_fused;
+    if (fused && !env->d_vg_band)
+      CCB_CUDA(cudaMalloc(&env->d_vg_band, sizeof(double) * 4 * d.E * d.R * ((d.N + VG_PART_THREADS - 1) / VG_PART_THREADS)));
+    if ((stages & 1) && !fused) {
       k_vg_init_span<<<(d.E * d.R + 255) / 256, 256, 0, env->stream>>>(env->d_vg_span, d.E * d.R);
       CCB_LAUNCH_CHECK();
     }
@@ -670,16 +682,23 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
     VgArgs g;
     g.d = d, g.row0 = row0, g.row1 = row1, g.table = env->d_vg_table, g.nflag = env->d_vg_flag, g.flag_list = env->d_vg_flag + 1, g.span = env->d_vg_span, g.sums = sums, g.labels = labels;
     g.items = env->d_vg_items;
-    const int rows = row1 - row0;
-    bool lookup = false;
-    if (src == SRC_WORLD && !labels && env->vg_prefix) {
-      if (ensure_prefix(env)) return 1;
-      lookup = env->d_vg_pfx != nullptr;
-    }
+    g.pfx = env->d_vg_pfx, g.band = env->d_vg_band;
+    const size_t psmem = sizeof(double) * d.R * d.R;
+    if (fused) {
+      // world-map moments inside the row partition: one prefix entry + one map sector per boundary, band moments
+      // stored, bands added in order (no table, no spans, no atomics)
+      if (stages & 1) {
+        k_vg_partition<1, true><<<dim3(nbands, d.E), VG_PART_THREADS, psmem, env->stream>>>(g);
+        CCB_LAUNCH_CHECK();
+      }
+      if (stages & 2) {
+        k_vg_bandsum<<<(d.E * d.R * 4 + 255) / 256, 256, 0, env->stream>>>(env->d_vg_band, sums, d.E, d.R, nbands);
+        CCB_LAUNCH_CHECK();
+      }
+    } else {
     if (stages & 1) {
       const int rpt = env->vg_part_rpt, band = rpt * VG_PART_THREADS;
       const dim3 pgrid((rows + band - 1) / band, d.E);
-      const size_t psmem = sizeof(double) * d.R * d.R;
       if (rpt == 2) k_vg_partition<2><<<pgrid, VG_PART_THREADS, psmem, env->stream>>>(g);
       else if (rpt == 4) k_vg_partition<4><<<pgrid, VG_PART_THREADS, psmem, env->stream>>>(g);
       else k_vg_partition<1><<<pgrid, VG_PART_THREADS, psmem, env->stream>>>(g);
@@ -693,12 +712,11 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
     // count (every site on every chunk) covers it with about one item per warp; the warps stride beyond it.
     const int chunks = (rows + VG_CHUNK - 1) / VG_CHUNK;
     const int max_ctas = (chunks * d.R + env->vg_warps - 1) / env->vg_warps;
-    dim3 rgrid(std::max(1, (max_ctas + env->vg_griddiv - 1) / env->vg_griddiv), d.E), fgrid(148 * 2);
+    dim3 rgrid(std::max(1, (max_ctas + env->vg_griddiv - 1) / env->vg_griddiv), d.E);
     if (stages & 2) {
       const int nt = env->vg_warps * 32;
       if (lookup) {
-        // two block-prefix look-ups and at most two map sectors per (site, row) instead of streaming the interval;
-        // one warp per site, sums stored (no atomics)
+        // site-ordered look-ups on the interval table (the parity reference of the fused kernel)
         k_vg_lookup<<<dim3((d.R + VG_LOOK_WARPS - 1) / VG_LOOK_WARPS, d.E), VG_LOOK_WARPS * 32, 0, env->stream>>>(g, env->d_vg_pfx);
       } else if (src == SRC_WORLD) {
         if (labels) k_vg_reduce<SRC_WORLD, true><<<rgrid, nt, 0, env->stream>>>(g);
@@ -709,6 +727,8 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
       }
       CCB_LAUNCH_CHECK();
     }
+    }
+    const dim3 fgrid(148 * 2);
     if (stages & 4) {
       if (src == SRC_WORLD) {
         if (labels) k_vg_fixup<SRC_WORLD, true><<<fgrid, 256, 0, env->stream>>>(g);
@@ -912,7 +932,7 @@ extern "C" void ccb_env_destroy(ccb_env *env) {
   cudaFree(env->d_objective), cudaFree(env->d_stage), cudaFree(env->d_feat), cudaFree(env->d_ratio);
   cudaFree(env->d_scratch);
   cudaFree(env->d_vg_table), cudaFree(env->d_vg_flag), cudaFree(env->d_vg_span), cudaFree(env->d_vg_items), cudaFree(env->d_xfeat);
-  cudaFree(env->d_vg_pfx), cudaFree(env->d_pfx_list);
+  cudaFree(env->d_vg_pfx), cudaFree(env->d_pfx_list), cudaFree(env->d_vg_band);
   cudaFreeHost(env->h_pin);
   for (int k = 0; k < 2; ++k) {
     cudaFreeHost(env->h_stage[k]);
@@ -932,6 +952,7 @@ extern "C" int ccb_test_set_option(ccb_env *env, const char *name, int value) {
   else if (n == "vg_warps") env->vg_warps = std::min(std::max(value, 1), VG_RED_WARPS);
   else if (n == "vg_griddiv") env->vg_griddiv = std::max(value, 1);
   else if (n == "vg_prefix") env->vg_prefix = value != 0;
+  else if (n == "vg_fused") env->vg_fused = value != 0;
   else if (n == "vg_part_rpt") env->vg_part_rpt = (value == 2 || value == 4) ? value : 1;
   else if (n == "no_aux") env->no_aux = value != 0;
   else if (n == "no_graph") env->no_graph = value != 0;
@@ -983,8 +1004,8 @@ static int ensure_prefix(ccb_env *env) {
     CCB_CUDA(cudaMemcpyAsync(env->d_pfx_list, todo.data(), sizeof(int) * todo.size(), cudaMemcpyHostToDevice, env->stream));
     list = env->d_pfx_list;
   }
-  const long warps = (long)todo.size() * d.N;
-  k_vg_prefix<<<(unsigned)((warps + 7) / 8), 256, 0, env->stream>>>(d.world, env->d_vg_pfx, d.N, list, (int)todo.size());
+  const long threads = (long)todo.size() * d.N;  // one per map row: a sequential double-double scan
+  k_vg_prefix<<<(unsigned)((threads + 127) / 128), 128, 0, env->stream>>>(d.world, env->d_vg_pfx, d.N, list, (int)todo.size());
   CCB_LAUNCH_CHECK();
   for (int e : todo) env->pfx_valid[e] = 1;
   return 0;
@@ -1338,6 +1359,7 @@ static int get_resize_table(ccb_env *env, int C, ResizeTab **out) {
       }
     t.interior_uniform = true;
     for (int o = 2; o < C - 1; ++o) t.interior_uniform = t.interior_uniform && memcmp(&wf[(size_t)o * 16], &wf[16], sizeof(float) * 16) == 0;
+    if (t.interior_uniform) CCB_CUDA(cudaMemcpyToSymbol(c_ob_w, &wf[16], sizeof(float) * 16));  // (the same values whatever the environment)
     CCB_CUDA(cudaMalloc(&t.d_wfull8, sizeof(float) * C * 16));
     CCB_CUDA(cudaMemcpy(t.d_wfull8, wf.data(), sizeof(float) * C * 16, cudaMemcpyHostToDevice));
   }
@@ -1688,7 +1710,7 @@ extern "C" int ccb_selftest_vg_partition(const double *pos, int R, int N, double
     }
     for (int k = 0; k < R; ++k) s_rmin[k] = 0x7fffffff, s_rmax[k] = 0;
     for (int row = rlo; row <= rhi; ++row)
-      vg_partition_row(a, 0, row, Rs, s_ord.data(), s_x.data(), s_y.data(), s_inv.data(), s_rmin.data(), s_rmax.data());
+      vg_partition_row<false>(a, 0, row, true, Rs, s_ord.data(), s_x.data(), s_y.data(), s_inv.data(), s_rmin.data(), s_rmax.data(), nullptr);
     for (int k = 0; k < R; ++k)
       if (s_rmax[k] > s_rmin[k]) {
         span[2 * k] = std::min(span[2 * k], s_rmin[k]);

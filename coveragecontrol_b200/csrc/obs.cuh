@@ -547,6 +547,10 @@ k_cnn_fused8(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__
 // by several neighbours summed in ascending neighbour order.
 // wfull[o][k] = weight of input index 8 o - 4 + k (zero outside torch's tap range); rows 1 .. 30 are identical
 // (the host checks this before it picks the kernel): their 16 weights live in registers.
+// the 16 tap weights of the interior output columns (rows 1 .. 30 of wfull, identical): FFMA reads them straight from
+// the constant bank, no register each (set once per device by the host when the resize table is built)
+__constant__ float c_ob_w[16];
+
 constexpr int OB_THREADS = 128;
 constexpr int OB_WARPS = OB_THREADS / 32;
 constexpr int OB_CHUNKS = 4;                  // 8 output rows = 64 window rows each
@@ -580,7 +584,7 @@ __device__ __forceinline__ unsigned ob_range(int lo, int hi, int c0, int n) {
 template <int S, bool VOR, bool DENSE>
 __device__ __forceinline__ void ob_items(const EnvDev &d, ObsShared &sh, const float *__restrict__ world, const Window &w,
                                          int off0, int rbase, int own0, int own1, int amap0, int amap1, int cy0, int cy1,
-                                         const float (&wreg)[16], const double *s_px, const double *s_py, double (&acc)[5]) {
+                                         const double *s_px, const double *s_py, double (&acc)[5]) {
   constexpr int NV = S == 0 ? 4 : 5;  // aligned 4-cell groups under the 16 taps
   const int total = sh.total;
   const float fill = d.fill;
@@ -616,7 +620,7 @@ __device__ __forceinline__ void ob_items(const EnvDev &d, ObsShared &sh, const f
     float t = 0.f;
     if (oy != 0 && oy != 31) {
 #pragma unroll
-      for (int q = 0; q < 16; ++q) t = fmaf(wreg[q], c[q], t);
+      for (int q = 0; q < 16; ++q) t = fmaf(c_ob_w[q], c[q], t);
     } else {  // the two border columns: torch truncates and renormalises their taps
 #pragma unroll
       for (int q = 0; q < 16; ++q) t = fmaf(sh.w[oy][q], c[q], t);
@@ -701,7 +705,7 @@ __device__ __forceinline__ void comm_scatter_warp(const EnvDev &d, int e, int r,
 }
 
 template <bool VOR, bool DENSE>
-__global__ void __launch_bounds__(OB_THREADS, 6)
+__global__ void __launch_bounds__(OB_THREADS, 8)
 k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__restrict__ out, size_t robot_stride,
             size_t local_off, size_t obst_off, size_t comm_off, int use_comm, double *__restrict__ wsums /* VOR: [E][R][4] */) {
   extern __shared__ __align__(16) unsigned char ob_smem[];
@@ -797,10 +801,8 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
       if (!(gy >= 0 && gy < d.N)) cy_out += wq;
     }
   }
-  float wreg[16];
-#pragma unroll
-  for (int q = 0; q < 16; ++q) wreg[q] = sh.w[15][q];
   double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  __syncthreads();  // oA / oB, the row intervals
 
 #pragma unroll 1
   for (int ch = 0; ch < OB_CHUNKS; ++ch) {
@@ -825,14 +827,15 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
         if (j < 1 + wlo || j >= 1 + whi) sh.mask[(r0 - rbase + ar) * OB_WORDS + j] = 0u;
       }
       const int nstage = nrow * nw_s;
-      constexpr int STAGE = 4;
+      const float inv_nw = 1.f / (float)max(nw_s, 1);  // t / nw_s for t < 76 * 9 through a float product: (t + 0.5) / nw_s
+      constexpr int STAGE = 4;                          // is at least 0.05 away from an integer, the product is good to 1e-4
 #pragma unroll 1
       for (int t0 = 0; t0 < nstage; t0 += STAGE * OB_THREADS) {
         uint32_t mw[STAGE];
 #pragma unroll
         for (int k = 0; k < STAGE; ++k) {
           const int t = t0 + tid + k * OB_THREADS;
-          const int ar = t / nw_s, j = wlo + t - ar * nw_s;
+          const int ar = (int)(((float)t + 0.5f) * inv_nw), j = wlo + t - ar * nw_s;
           const int wd = wbase + j;
           uint32_t mv = 0u;
           if (t < nstage && wd >= 0 && wd < d.NW) {
@@ -845,7 +848,7 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
         for (int k = 0; k < STAGE; ++k) {
           const int t = t0 + tid + k * OB_THREADS;
           if (t >= nstage) continue;
-          const int ar = t / nw_s, j = wlo + t - ar * nw_s;
+          const int ar = (int)(((float)t + 0.5f) * inv_nw), j = wlo + t - ar * nw_s;
           sh.mask[(r0 - rbase + ar) * OB_WORDS + 1 + j] = mw[k];
         }
       }
@@ -910,10 +913,10 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
     {
       const int own0 = 64 * ch, own1 = 64 * ch + 64;
       switch (w.oy & 3) {
-        case 0: ob_items<0, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, wreg, s_px, s_py, acc); break;
-        case 1: ob_items<1, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, wreg, s_px, s_py, acc); break;
-        case 2: ob_items<2, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, wreg, s_px, s_py, acc); break;
-        default: ob_items<3, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, wreg, s_px, s_py, acc); break;
+        case 0: ob_items<0, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, s_px, s_py, acc); break;
+        case 1: ob_items<1, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, s_px, s_py, acc); break;
+        case 2: ob_items<2, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, s_px, s_py, acc); break;
+        default: ob_items<3, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, s_px, s_py, acc); break;
       }
     }
     __syncthreads();

@@ -48,11 +48,14 @@ struct VgArgs {
   int *items;           // [E][R + 1]: first (site, 32-row chunk) item of every site, then the total (k_vg_items)
   double *sums;         // [E][R][4]
   int *labels;          // optional [E][N*N]
+  const struct VgPfx *pfx;  // SUM mode: block prefix sums of the world maps, [E][N][N / 8 + 1]
+  double *band;         // SUM mode: [E][bands][R][4] moments of every CTA's row band
 };
 
-__host__ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row, int Rs, const int *s_ord,
+template <bool SUM>
+__host__ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row, bool active, int Rs, const int *s_ord,
                                                           const double *s_x, const double *s_y, const double *s_inv,
-                                                          int *s_rmin, int *s_rmax);
+                                                          int *s_rmin, int *s_rmax, double *s_wacc);
 
 // The row sweep also runs on the host (ccb_selftest_vg_partition, CPU tests): one thread, plain updates there.
 __host__ __device__ __forceinline__ void vg_min(int *p, int v) {
@@ -82,9 +85,89 @@ __global__ void k_vg_init_span(int *span, int n) {
   if (i < n) span[2 * i] = 0x7fffffff, span[2 * i + 1] = 0;
 }
 
+// ---- block prefix sums: the world-map moments without streaming the map ---------------------------------
+// The world map of an environment is constant while its robots move, and a site's cells on a row are ONE column
+// interval [lo, hi).  Next to every map row the library keeps the running sums of (v, y v, y^2 v) (y = col + 0.5,
+// cell units) at every VG_PB-th column: entry b = the sum over the columns < VG_PB b, b = 0 .. N / VG_PB, one
+// 64-byte record each (8 bytes of HBM per map cell; the unit DRAM hands out is 64 bytes).  The moments of a cell
+// are then differences of entries plus the few cells between a boundary and the next block edge, so a whole-map
+// pass reads one entry and one 32-byte map sector per Voronoi BOUNDARY of a row instead of every map cell
+// (~0.8 MB instead of 4.2 MB per 1024^2 environment with 32 robots).
+// Accuracy.  Only cells inside an interval are ever added directly, and the entries are DOUBLE-DOUBLE (hi + lo,
+// ~106 bits) built by a SEQUENTIAL scan E[b + 1] = E[b] (+) blocksum(b): the difference of two entries is the
+// exact sum of the 8-cell block sums between them to ~1e-32 of the row's total -- a cell of mass 1e-9 at the end
+// of a row whose prefix is 1e3 keeps ~20 digits, so the `mass < 1e-10` fallback (voronoi.cpp:41-53) fires on
+// the same cells as with exact sums -- and a run of zero cells leaves the entries bitwise unchanged, so it sums
+// to exactly 0.  The block sums themselves are fp64 sums of exact products, like k_vg_reduce's.
+// Only for the world map (SRC_WORLD, no labels): the explored and robot maps change with every step.
+constexpr int VG_PB = 8;  // columns per block: one 32-byte sector of the map row
+struct __align__(64) VgPfx {
+  double s_hi, s_lo, sy_hi, sy_lo, syy_hi, syy_lo, pad0, pad1;
+};
+__host__ __device__ inline size_t vg_pfx_row_entries(int N) { return (size_t)N / VG_PB + 1; }
+
+#ifdef __CUDACC__
+// four cells y0 .. y0 + 3 (cell units) of one row into the row's sums
+__device__ __forceinline__ void vg_add4(const float4 x, const double y0, double &rs, double &rsy, double &rsyy) {
+  const double v0 = (double)x.x, v1 = (double)x.y, v2 = (double)x.z, v3 = (double)x.w;
+  const double s = (v0 + v1) + (v2 + v3);
+  const double t = fma(3.0, v3, fma(2.0, v2, v1));   // sum i v_i
+  const double u = fma(9.0, v3, fma(4.0, v2, v1));   // sum i^2 v_i
+  rs += s;
+  rsy += fma(y0, s, t);
+  rsyy += fma(y0 * y0, s, fma(y0 + y0, t, u));
+}
+
+
+struct DD {
+  double hi, lo;
+};
+// error-free transformations (Knuth / Dekker); -fmad=false and the explicit _rn intrinsics keep them un-contracted
+__device__ __forceinline__ DD dd_two_sum(double a, double b) {
+  const double s = __dadd_rn(a, b), bb = __dsub_rn(s, a);
+  return DD{s, __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb))};
+}
+__device__ __forceinline__ DD dd_quick(double a, double b) {  // |a| >= |b|
+  const double s = __dadd_rn(a, b);
+  return DD{s, __dsub_rn(b, __dsub_rn(s, a))};
+}
+__device__ __forceinline__ DD dd_add(DD a, DD b) {
+  DD s = dd_two_sum(a.hi, b.hi);
+  const DD t = dd_two_sum(a.lo, b.lo);
+  s = dd_quick(s.hi, __dadd_rn(s.lo, t.hi));
+  return dd_quick(s.hi, __dadd_rn(s.lo, t.lo));
+}
+__device__ __forceinline__ double dd_diff(DD a, DD b) {  // a - b, rounded to fp64 once
+  const DD d = dd_add(a, DD{-b.hi, -b.lo});
+  return __dadd_rn(d.hi, d.lo);
+}
+
+// eight cells y0 .. y0 + 7 (cell units) of one row, those with a bit in `keep` only
+__device__ __forceinline__ void vg_add8(float4 a, float4 b, unsigned keep, double y0, double &rs, double &rsy, double &rsyy) {
+  a.x = (keep & 1u) ? a.x : 0.f, a.y = (keep & 2u) ? a.y : 0.f, a.z = (keep & 4u) ? a.z : 0.f, a.w = (keep & 8u) ? a.w : 0.f;
+  b.x = (keep & 16u) ? b.x : 0.f, b.y = (keep & 32u) ? b.y : 0.f, b.z = (keep & 64u) ? b.z : 0.f, b.w = (keep & 128u) ? b.w : 0.f;
+  vg_add4(a, y0, rs, rsy, rsyy);
+  vg_add4(b, y0 + 4.0, rs, rsy, rsyy);
+}
+
+// E[b + 1] from E[b] and the eight cells of block b: THE step of the sequential scan (k_vg_prefix); the partition
+// kernel repeats it to get the entry after a boundary without a second look-up, bit for bit
+__device__ __forceinline__ void vg_pfx_step(DD &s, DD &sy, DD &syy, float4 a, float4 b, int blk) {
+  double bs = 0.0, bsy = 0.0, bsyy = 0.0;
+  vg_add8(a, b, 0xffu, (double)(VG_PB * blk) + 0.5, bs, bsy, bsyy);
+  s = dd_add(s, DD{bs, 0.0}), sy = dd_add(sy, DD{bsy, 0.0}), syy = dd_add(syy, DD{bsyy, 0.0});
+}
+#endif  // __CUDACC__
+
 // RPT rows per thread: a CTA's band is RPT * VG_PART_THREADS rows (RPT > 1, opt-in through CCB_VG_PART_RPT: the
 // sort / twin / cull / 1 / (2 dy) preamble is paid once per band, against a taller band culling fewer sites)
-template <int RPT = 1>
+// SUM (world-map moments with valid block prefix sums, RPT = 1): instead of writing the interval table for a second
+// kernel, every row thread walks its owners left to right and turns the breakpoints into moments on the spot -- one
+// prefix entry and one map sector per boundary, prefetched as soon as the breakpoints are known; a segmented warp
+// reduction (by site, fixed shuffle tree) adds the 32 rows of a warp into per-warp accumulators, the CTA adds its
+// four warps in order and STORES the band's moments; k_vg_bandsum then adds the bands in order.  No table, no
+// spans, no item list, no atomics: run-to-run bit-stable (flagged rows still go through k_vg_fixup's atomics).
+template <int RPT = 1, bool SUM = false>
 __global__ void __launch_bounds__(VG_PART_THREADS) k_vg_partition(VgArgs a) {
   __shared__ int s_ord[VG_MAXR];
   __shared__ double s_x[VG_MAXR], s_y[VG_MAXR];
@@ -98,6 +181,9 @@ __global__ void __launch_bounds__(VG_PART_THREADS) k_vg_partition(VgArgs a) {
   __shared__ double t_x[VG_MAXR], t_y[VG_MAXR];
   __shared__ unsigned char t_keep[VG_MAXR];
   __shared__ int s_nkeep;
+  __shared__ double s_wacc[SUM ? VG_PART_THREADS / 32 * VG_MAXR * 4 : 1];
+  if (SUM)
+    for (int k = tid; k < VG_PART_THREADS / 32 * VG_MAXR * 4; k += VG_PART_THREADS) s_wacc[k] = 0.0;
   for (int k = tid; k < R; k += VG_PART_THREADS) {
     const double yk = pos[2 * k + 1];
     int rank = 0;
@@ -161,14 +247,29 @@ __global__ void __launch_bounds__(VG_PART_THREADS) k_vg_partition(VgArgs a) {
     s_inv[idx] = dy > 0.0 ? 1.0 / (2.0 * dy) : 0.0;
   }
   __syncthreads();
+  if (SUM) {
+    // (every thread takes part in the warp reductions: rows beyond the band are inactive)
+    const int row = a.row0 + blockIdx.x * VG_PART_THREADS + tid;
+    vg_partition_row<true>(a, e, min(row, a.row1 - 1), row < a.row1, Rs, s_ord, s_x, s_y, s_inv, s_rmin, s_rmax, s_wacc);
+    __syncthreads();
+    // band moments = the four warps' accumulators in order; sites without cells in the band store zeros
+    double *dst = a.band + ((size_t)e * gridDim.x + blockIdx.x) * R * 4;
+    for (int i = tid; i < R * 4; i += VG_PART_THREADS) {
+      double t = 0.0;
+#pragma unroll
+      for (int wq = 0; wq < VG_PART_THREADS / 32; ++wq) t += s_wacc[wq * VG_MAXR * 4 + i];
+      dst[i] = t;
+    }
+    return;
+  }
   if (RPT == 1) {
     const int row = a.row0 + blockIdx.x * VG_PART_THREADS + tid;
-    if (row < a.row1) vg_partition_row(a, e, row, Rs, s_ord, s_x, s_y, s_inv, s_rmin, s_rmax);
+    if (row < a.row1) vg_partition_row<false>(a, e, row, true, Rs, s_ord, s_x, s_y, s_inv, s_rmin, s_rmax, nullptr);
   } else {
 #pragma unroll 1
     for (int i = 0; i < RPT; ++i) {
       const int row = a.row0 + blockIdx.x * (RPT * VG_PART_THREADS) + i * VG_PART_THREADS + tid;
-      if (row < a.row1) vg_partition_row(a, e, row, Rs, s_ord, s_x, s_y, s_inv, s_rmin, s_rmax);
+      if (row < a.row1) vg_partition_row<false>(a, e, row, true, Rs, s_ord, s_x, s_y, s_inv, s_rmin, s_rmax, nullptr);
     }
   }
   __syncthreads();
@@ -181,9 +282,10 @@ __global__ void __launch_bounds__(VG_PART_THREADS) k_vg_partition(VgArgs a) {
 }
 
 // Rs sorted sites survive the band cull (s_ord: their site indices); the table is written for all R
-__host__ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row, int Rs, const int *s_ord,
+template <bool SUM>
+__host__ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e, int row, bool active, int Rs, const int *s_ord,
                                                           const double *s_x, const double *s_y, const double *s_inv,
-                                                          int *s_rmin, int *s_rmax) {
+                                                          int *s_rmin, int *s_rmax, double *s_wacc) {
   const EnvDev &d = a.d;
   const int R = d.R, N = d.N;
   const double res = d.res;
@@ -245,33 +347,113 @@ __host__ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e
     }
   }
 
-  // integer breakpoints: v[m] owns columns [T[m], T[m+1]); a cell centre within the error bound of a
+  // integer breakpoints: v[m] owns columns [tc[m], tc[m + 1]); a cell centre within the error bound of a
   // boundary flags the row
-  uint32_t *t = a.table + (size_t)e * R * N + row;
-  unsigned long long owned = 0ull;  // sites whose interval has been written (R <= VG_MAXR = 64)
-  int lo = 0;
-  for (int m = 0; m <= top && !flagged; ++m) {
-    int hi = N;
-    if (m < top) {
-      const double b = z[m + 1], berr = zerr[m + 1] + 1e-13 * (fabs(b) + res);
-      const double t = ceil(b / res - 0.5);  // first column whose centre is >= b
-      const double tc = fmin(fmax(t, 0.0), (double)N);
-      hi = (int)tc;
-      // centres of the cells next to the boundary
-      if (t >= 1.0 && t <= (double)N && fabs(cell_centre((int)t - 1, res) - b) <= berr) flagged = true;
-      if (t >= 0.0 && t < (double)N && fabs(cell_centre((int)t, res) - b) <= berr) flagged = true;
+  unsigned short tc[VG_MAXR + 1];
+  tc[0] = 0;
+  {
+    int lo = 0;
+    for (int m = 0; m <= top && !flagged; ++m) {
+      int hi = N;
+      if (m < top) {
+        const double b = z[m + 1], berr = zerr[m + 1] + 1e-13 * (fabs(b) + res);
+        const double t = ceil(b / res - 0.5);  // first column whose centre is >= b
+        const double tcl = fmin(fmax(t, 0.0), (double)N);
+        hi = (int)tcl;
+        // centres of the cells next to the boundary
+        if (t >= 1.0 && t <= (double)N && fabs(cell_centre((int)t - 1, res) - b) <= berr) flagged = true;
+        if (t >= 0.0 && t < (double)N && fabs(cell_centre((int)t, res) - b) <= berr) flagged = true;
+      }
+      if (hi < lo) hi = lo;
+      tc[m + 1] = (unsigned short)hi;
+      lo = hi;
     }
-    if (hi < lo) hi = lo;
-    const int site = s_ord[v[m]];
-    t[(size_t)site * N] = (uint32_t)lo | ((uint32_t)hi << 16);
-    owned |= 1ull << site;
-    if (hi > lo) vg_min(&s_rmin[site], row), vg_max(&s_rmax[site], row + 1);
-    lo = hi;
   }
-  // everyone else owns nothing on this row; a flagged row is left to k_vg_fixup entirely
-  if (flagged) a.flag_list[vg_next(a.nflag)] = e * N + row, owned = 0ull;
-  for (int k = 0; k < R; ++k)
-    if (!((owned >> k) & 1ull)) t[(size_t)k * N] = 0u;
+  // a flagged row is left to k_vg_fixup entirely
+  if (flagged && active) a.flag_list[vg_next(a.nflag)] = e * N + row;
+  if (!SUM) {
+    uint32_t *t = a.table + (size_t)e * R * N + row;
+    unsigned long long owned = 0ull;  // sites whose interval has been written (R <= VG_MAXR = 64)
+    if (!flagged)
+      for (int m = 0; m <= top; ++m) {
+        const int lo = tc[m], hi = tc[m + 1];
+        const int site = s_ord[v[m]];
+        t[(size_t)site * N] = (uint32_t)lo | ((uint32_t)hi << 16);
+        owned |= 1ull << site;
+        if (hi > lo) vg_min(&s_rmin[site], row), vg_max(&s_rmax[site], row + 1);
+      }
+    // everyone else owns nothing on this row
+    for (int k = 0; k < R; ++k)
+      if (!((owned >> k) & 1ull)) t[(size_t)k * N] = 0u;
+    return;
+  }
+#ifdef __CUDA_ARCH__
+  if (SUM) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nown = (active && !flagged) ? top + 1 : 0;
+    const VgPfx *prow = a.pfx + ((size_t)e * N + row) * vg_pfx_row_entries(N);
+    const float *wrow = d.world + ((size_t)e * N + row) * N;
+    // everything the walk reads, requested into L2 now: one entry per boundary, one sector per unaligned boundary
+    for (int m = 1; m <= nown; ++m) {
+      const int T = tc[m];
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + (T >> 3)));
+      if (T & (VG_PB - 1)) asm volatile("prefetch.global.L2 [%0];" ::"l"(wrow + (T & ~(VG_PB - 1))));
+    }
+    const int maxown = __reduce_max_sync(0xffffffffu, nown);
+    const double x = (double)row + 0.5;
+    DD Ls{0.0, 0.0}, Lsy{0.0, 0.0}, Lsyy{0.0, 0.0};  // the entry at the block edge at or after the left boundary
+    double hs = 0.0, hsy = 0.0, hsyy = 0.0;          // the cells between the left boundary and that edge
+    int Tl = 0;
+    for (int m = 0; m < maxown; ++m) {
+      int slot = -1;
+      double vm = 0.0, vsx = 0.0, vsy = 0.0, vs2 = 0.0;
+      if (m < nown) {
+        const int T = tc[m + 1], b = T >> 3, f = T & (VG_PB - 1);
+        const double2 *ep = reinterpret_cast<const double2 *>(prow + b);
+        const double2 e0 = __ldg(ep), e1 = __ldg(ep + 1), e2 = __ldg(ep + 2);
+        const DD Es{e0.x, e0.y}, Esy{e1.x, e1.y}, Esyy{e2.x, e2.y};
+        DD Ns = Es, Nsy = Esy, Nsyy = Esyy;
+        double rs = 0.0, rsy = 0.0, rsyy = 0.0, nhs = 0.0, nhsy = 0.0, nhsyy = 0.0;
+        bool direct = false;
+        if (f) {
+          const float4 *p4 = reinterpret_cast<const float4 *>(wrow + VG_PB * b);
+          const float4 A = __ldg(p4), B = __ldg(p4 + 1);
+          const double y0 = (double)(VG_PB * b) + 0.5;
+          const unsigned below = (1u << f) - 1u;
+          if ((Tl >> 3) == b && (Tl & (VG_PB - 1))) {  // the whole interval lies inside this block: its cells, directly
+            vg_add8(A, B, below & ~((1u << (Tl & (VG_PB - 1))) - 1u), y0, rs, rsy, rsyy);
+            direct = true;
+          } else {
+            vg_add8(A, B, below, y0, rs, rsy, rsyy);    // tail: the cells [8 b, T)
+          }
+          vg_add8(A, B, 0xffu & ~below, y0, nhs, nhsy, nhsyy);  // head of the next owner: [T, 8 b + 8)
+          vg_pfx_step(Ns, Nsy, Nsyy, A, B, b);                  // E[b + 1], as the scan built it
+        }
+        if (!direct) {
+          rs += dd_diff(Es, Ls) + hs;
+          rsy += dd_diff(Esy, Lsy) + hsy;
+          rsyy += dd_diff(Esyy, Lsyy) + hsyy;
+        }
+        Ls = Ns, Lsy = Nsy, Lsyy = Nsyy, hs = nhs, hsy = nhsy, hsyy = nhsyy, Tl = T;
+        vm = rs, vsx = x * rs, vsy = rsy, vs2 = fma(x * x, rs, rsyy);
+        slot = s_ord[v[m]];
+      }
+      // the warp's rows by site: neighbouring rows mostly share their m-th owner
+      unsigned todo = __ballot_sync(0xffffffffu, slot >= 0);
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int sl = __shfl_sync(0xffffffffu, slot, leader);
+        const bool mine = slot == sl;
+        const Sum4 tot = reduce4(mine ? vm : 0.0, mine ? vsx : 0.0, mine ? vsy : 0.0, mine ? vs2 : 0.0);
+        if (lane == leader) {
+          double *acc = s_wacc + ((size_t)warp * VG_MAXR + sl) * 4;
+          acc[0] += tot.m, acc[1] += tot.sx, acc[2] += tot.sy, acc[3] += tot.s2;
+        }
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+      }
+    }
+  }
+#endif
 }
 
 // ---- reduce ----------------------------------------------------------------------------------------
@@ -305,17 +487,6 @@ __global__ void k_vg_items(const int *__restrict__ span, int *__restrict__ items
 __device__ __forceinline__ unsigned vg_keep4(int col, int lo, int hi) {
   const int a = min(max(lo - col, 0), 4), b = min(max(hi - col, 0), 4);
   return ((1u << b) - 1u) & ~((1u << a) - 1u);
-}
-
-// four cells y0 .. y0 + 3 (cell units) of one row into the row's sums
-__device__ __forceinline__ void vg_add4(const float4 x, const double y0, double &rs, double &rsy, double &rsyy) {
-  const double v0 = (double)x.x, v1 = (double)x.y, v2 = (double)x.z, v3 = (double)x.w;
-  const double s = (v0 + v1) + (v2 + v3);
-  const double t = fma(3.0, v3, fma(2.0, v2, v1));   // sum i v_i
-  const double u = fma(9.0, v3, fma(4.0, v2, v1));   // sum i^2 v_i
-  rs += s;
-  rsy += fma(y0, s, t);
-  rsyy += fma(y0 * y0, s, fma(y0 + y0, t, u));
 }
 
 constexpr int VG_RED_MINB = 8;  // resident CTAs of VG_RED_WARPS warps per SM the register allocation aims for (64 registers)
@@ -442,97 +613,41 @@ __global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a)
   }
 }
 
-// ---- block prefix sums: the world-map moments without streaming the map ---------------------------------
-// The world map of an environment is constant while its robots move, and a site's cells on a row are ONE column
-// interval [lo, hi).  Next to every map row the library keeps the running sums of (v, y v, y^2 v) (y = col + 0.5,
-// cell units) at every VG_PB-th column: entry b = the sum over the columns < VG_PB b, b = 0 .. N / VG_PB.  The
-// moments of [lo, hi) are then
-//     P[hi / 8] - P[ceil(lo / 8)]  +  the cells of [lo, 8 ceil(lo / 8))  +  the cells of [8 (hi / 8), hi),
-// i.e. two 48-byte entries and at most two 32-byte sectors of the map per (site, row) instead of the whole interval
-// (~190 B instead of ~700 B at N = 1024, R = 32), at 6 bytes of HBM per map cell.
-// Accuracy.  The head and tail cells are summed directly (only cells inside the interval are ever added, so a
-// cell of mass 1e-9 next to a cell of mass 1 keeps all its digits).  The entries are DOUBLE-DOUBLE (hi + lo, ~106
-// bits): the difference of two entries is the exact sum of the 8-cell block sums between them to ~1e-32 of the
-// row's total, so a cell of mass 1e-9 at the end of a row whose prefix is 1e3 is still good to ~1e-20 relative
-// and the `mass < 1e-10` fallback (voronoi.cpp:41-53) fires on the same cells as with exact sums; a run of zero
-// cells sums to exactly 0.  The block sums themselves are fp64 sums of exact products, like k_vg_reduce's.
-// Only for the world map (SRC_WORLD, no labels): the explored and robot maps change with every step.
-constexpr int VG_PB = 8;  // columns per block: one 32-byte sector of the map row
-struct __align__(16) VgPfx {
-  double s_hi, s_lo, sy_hi, sy_lo, syy_hi, syy_lo;
-};
-__host__ __device__ inline size_t vg_pfx_row_entries(int N) { return (size_t)N / VG_PB + 1; }
-
-struct DD {
-  double hi, lo;
-};
-// error-free transformations (Knuth / Dekker); -fmad=false and the explicit _rn intrinsics keep them un-contracted
-__device__ __forceinline__ DD dd_two_sum(double a, double b) {
-  const double s = __dadd_rn(a, b), bb = __dsub_rn(s, a);
-  return DD{s, __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb))};
-}
-__device__ __forceinline__ DD dd_quick(double a, double b) {  // |a| >= |b|
-  const double s = __dadd_rn(a, b);
-  return DD{s, __dsub_rn(b, __dsub_rn(s, a))};
-}
-__device__ __forceinline__ DD dd_add(DD a, DD b) {
-  DD s = dd_two_sum(a.hi, b.hi);
-  const DD t = dd_two_sum(a.lo, b.lo);
-  s = dd_quick(s.hi, __dadd_rn(s.lo, t.hi));
-  return dd_quick(s.hi, __dadd_rn(s.lo, t.lo));
-}
-__device__ __forceinline__ DD dd_shfl_up(DD v, int o) {
-  return DD{__shfl_up_sync(0xffffffffu, v.hi, o), __shfl_up_sync(0xffffffffu, v.lo, o)};
-}
-
-// eight cells y0 .. y0 + 7 (cell units) of one row, those with a bit in `keep` only
-__device__ __forceinline__ void vg_add8(float4 a, float4 b, unsigned keep, double y0, double &rs, double &rsy, double &rsyy) {
-  a.x = (keep & 1u) ? a.x : 0.f, a.y = (keep & 2u) ? a.y : 0.f, a.z = (keep & 4u) ? a.z : 0.f, a.w = (keep & 8u) ? a.w : 0.f;
-  b.x = (keep & 16u) ? b.x : 0.f, b.y = (keep & 32u) ? b.y : 0.f, b.z = (keep & 64u) ? b.z : 0.f, b.w = (keep & 128u) ? b.w : 0.f;
-  vg_add4(a, y0, rs, rsy, rsyy);
-  vg_add4(b, y0 + 4.0, rs, rsy, rsyy);
-}
-
-// one warp per map row (rows of all the listed environments): lane <-> block of 8 columns, a double-double warp scan
-// per 32 blocks, the carry handed on.  envs: the environments to (re)build, nenv of them (null: 0 .. nenv - 1).
-__global__ void __launch_bounds__(256) k_vg_prefix(const float *__restrict__ world_all, VgPfx *__restrict__ pfx_all, int N,
+// ---- block prefix sums: build, band sums, and the site-ordered (bit-stable) look-up kernel -------------------
+// one thread per map row of the listed environments: the sequential double-double scan (see VgPfx above).
+// envs: the environments to (re)build, nenv of them (null: 0 .. nenv - 1).
+__global__ void __launch_bounds__(128) k_vg_prefix(const float *__restrict__ world_all, VgPfx *__restrict__ pfx_all, int N,
                                                    const int *__restrict__ envs, int nenv) {
-  const long wid = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (wid >= (long)nenv * N) return;
-  const int ei = (int)(wid / N), row = (int)(wid - (long)ei * N);
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)nenv * N) return;
+  const int ei = (int)(t / N), row = (int)(t - (long)ei * N);
   const int e = envs ? envs[ei] : ei;
-  const float *src = world_all + ((size_t)e * N + row) * N;
+  const float4 *src = reinterpret_cast<const float4 *>(world_all + ((size_t)e * N + row) * N);
   const int nblk = N / VG_PB;
-  VgPfx *dst = pfx_all + ((size_t)e * N + row) * vg_pfx_row_entries(N);
-  DD c0{0.0, 0.0}, c1{0.0, 0.0}, c2{0.0, 0.0};  // the sums of the blocks before this group of 32
-  for (int gb = 0; gb <= nblk; gb += 32) {
-    const int b = gb + lane;
-    double bs = 0.0, bsy = 0.0, bsyy = 0.0;
-    if (b < nblk) {
-      const float4 *p4 = reinterpret_cast<const float4 *>(src + VG_PB * b);
-      vg_add8(__ldg(p4), __ldg(p4 + 1), 0xffu, (double)(VG_PB * b) + 0.5, bs, bsy, bsyy);
-    }
-    DD a0{bs, 0.0}, a1{bsy, 0.0}, a2{bsyy, 0.0};  // inclusive scan over the lanes
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const DD u0 = dd_shfl_up(a0, o), u1 = dd_shfl_up(a1, o), u2 = dd_shfl_up(a2, o);
-      if (lane >= o) a0 = dd_add(a0, u0), a1 = dd_add(a1, u1), a2 = dd_add(a2, u2);
-    }
-    // entry b = everything before block b: the carry plus the inclusive sum of the lane below
-    DD x0 = dd_shfl_up(a0, 1), x1 = dd_shfl_up(a1, 1), x2 = dd_shfl_up(a2, 1);
-    if (lane == 0) x0 = x1 = x2 = DD{0.0, 0.0};
-    x0 = dd_add(c0, x0), x1 = dd_add(c1, x1), x2 = dd_add(c2, x2);
-    if (b <= nblk) {
-      VgPfx out;
-      out.s_hi = x0.hi, out.s_lo = x0.lo, out.sy_hi = x1.hi, out.sy_lo = x1.lo, out.syy_hi = x2.hi, out.syy_lo = x2.lo;
-      dst[b] = out;
-    }
-    const DD t0{__shfl_sync(0xffffffffu, a0.hi, 31), __shfl_sync(0xffffffffu, a0.lo, 31)};
-    const DD t1{__shfl_sync(0xffffffffu, a1.hi, 31), __shfl_sync(0xffffffffu, a1.lo, 31)};
-    const DD t2{__shfl_sync(0xffffffffu, a2.hi, 31), __shfl_sync(0xffffffffu, a2.lo, 31)};
-    c0 = dd_add(c0, t0), c1 = dd_add(c1, t1), c2 = dd_add(c2, t2);
+  double2 *dst = reinterpret_cast<double2 *>(pfx_all + ((size_t)e * N + row) * vg_pfx_row_entries(N));
+  DD s{0.0, 0.0}, sy{0.0, 0.0}, syy{0.0, 0.0};
+  float4 a = __ldg(src), b = __ldg(src + 1);
+  for (int blk = 0; blk < nblk; ++blk) {
+    dst[4 * blk] = make_double2(s.hi, s.lo), dst[4 * blk + 1] = make_double2(sy.hi, sy.lo);
+    dst[4 * blk + 2] = make_double2(syy.hi, syy.lo), dst[4 * blk + 3] = make_double2(0.0, 0.0);
+    float4 na = a, nb = b;
+    if (blk + 1 < nblk) na = __ldg(src + 2 * blk + 2), nb = __ldg(src + 2 * blk + 3);  // next block in flight during the scan step
+    vg_pfx_step(s, sy, syy, a, b, blk);
+    a = na, b = nb;
   }
+  dst[4 * nblk] = make_double2(s.hi, s.lo), dst[4 * nblk + 1] = make_double2(sy.hi, sy.lo);
+  dst[4 * nblk + 2] = make_double2(syy.hi, syy.lo), dst[4 * nblk + 3] = make_double2(0.0, 0.0);
+}
+
+// the moments of every site = the sum of its band moments in ascending band order (plain stores: no memset, no atomics)
+__global__ void k_vg_bandsum(const double *__restrict__ band, double *__restrict__ sums, int E, int R, int nbands) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (e, k, c)
+  if (i >= E * R * 4) return;
+  const int e = i / (R * 4), kc = i - e * (R * 4);
+  const double *src = band + (size_t)e * nbands * R * 4 + kc;
+  double t = 0.0;
+  for (int b = 0; b < nbands; ++b) t += src[(size_t)b * R * 4];
+  sums[i] = t;
 }
 
 // entry hi - entry lo, rounded to fp64 once
@@ -541,16 +656,13 @@ __device__ __forceinline__ void vg_pfx_diff(const VgPfx *__restrict__ ph, const 
   const double2 *h = reinterpret_cast<const double2 *>(ph), *l = reinterpret_cast<const double2 *>(pl);
   const double2 h0 = __ldg(h), h1 = __ldg(h + 1), h2 = __ldg(h + 2);
   const double2 l0 = __ldg(l), l1 = __ldg(l + 1), l2 = __ldg(l + 2);
-  const DD d0 = dd_add(DD{h0.x, h0.y}, DD{-l0.x, -l0.y});
-  const DD d1 = dd_add(DD{h1.x, h1.y}, DD{-l1.x, -l1.y});
-  const DD d2 = dd_add(DD{h2.x, h2.y}, DD{-l2.x, -l2.y});
-  s = __dadd_rn(d0.hi, d0.lo), sy = __dadd_rn(d1.hi, d1.lo), syy = __dadd_rn(d2.hi, d2.lo);
+  s = dd_diff(DD{h0.x, h0.y}, DD{l0.x, l0.y}), sy = dd_diff(DD{h1.x, h1.y}, DD{l1.x, l1.y}), syy = dd_diff(DD{h2.x, h2.y}, DD{l2.x, l2.y});
 }
 
-// One warp per (environment, site): the warp walks the site's row span 32 rows at a time, lane <-> row; two entry
+// Site-ordered variant (test option "ordered_sums" and the parity reference of the fused kernel): one warp per
+// (environment, site) walks the site's row span of the partition TABLE 32 rows at a time, lane <-> row; two entry
 // look-ups and at most two map sectors per row.  The per-lane sums and the shuffle tree have a fixed order and the
-// result is STORED (no atomics, no memset): the moments are bit-stable from run to run (k_vg_fixup adds the cells
-// of flagged rows afterwards).
+// result is STORED (no atomics, no memset) (k_vg_fixup adds the cells of flagged rows afterwards).
 constexpr int VG_LOOK_WARPS = 4;
 __global__ void __launch_bounds__(VG_LOOK_WARPS * 32) k_vg_lookup(VgArgs a, const VgPfx *__restrict__ pfx_all) {
   const EnvDev &d = a.d;

@@ -18,12 +18,12 @@ extern "C" {
 /* Force a kernel choice / diagnostics switch on one environment batch (tests and A/B timing only; the library
  * itself never reads the process environment).  Returns 0, or 1 for an unknown name.  Names:
  *   "vg_generic"  1: tile-ordered whole-map Voronoi (csrc/voronoi.cuh), 0: site-ordered (csrc/vglobal.cuh), -1: by shape
- *   "vg_prefix"   1/0: block prefix sums for the world-map moments (csrc/vglobal.cuh k_vg_lookup) on / off
+ *   "vg_prefix"   1/0: block prefix sums for the world-map moments (csrc/vglobal.cuh) on / off (off: k_vg_reduce streams the map)
+ *   "vg_fused"    1/0: with prefix sums, moments inside the row partition kernel / interval table + k_vg_lookup
  *   "vw_generic"  1: generic window Voronoi kernel      "cnn_generic" 1: generic observation kernel
  *   "obs_v1"      1: the row-ordered fused observation kernel of round 1 instead of the item-ordered one
  *   "vor_rpw"     rows per warp region of the tile-ordered kernel   "vg_warps" / "vg_griddiv" / "vg_part_rpt"
- *   "no_aux" / "no_graph" / "no_wfuse"   1: single stream / no CUDA-graph replay / no fused window moments
- *   "ordered_sums" 1: atomic-free second-stage sums (run-to-run bit-stable moments) */
+ *   "no_aux" / "no_graph" / "no_wfuse"   1: single stream / no CUDA-graph replay / no fused window moments */
 int ccb_test_set_option(ccb_env *env, const char *name, int value);
 
 /* Test hook, host only: the triangles the library cuts a polygon feature into before the IDF kernel's

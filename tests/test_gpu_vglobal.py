@@ -117,19 +117,24 @@ def test_cell_polygon_with_more_vertices_than_a_warp():
         assert c.mass == pytest.approx(o.mass, rel=1e-9)
 
 
-@pytest.mark.parametrize("prefix", [1, 0])
+_MODES = {"fused": ("1", "1"), "lookup": ("1", "0"), "stream": ("0", "0")}  # CCB_VG_PREFIX, CCB_VG_FUSED
+
+
+@pytest.mark.parametrize("mode", list(_MODES))
 @pytest.mark.parametrize("kind,N,R,seed", [("random", 1024, 32, 0), ("random", 512, 64, 1), ("cluster", 256, 48, 2),
                                            ("lattice", 256, 36, 3), ("halfint", 512, 24, 4), ("random", 304, 2, 5)])
-def test_block_prefix_path_matches_oracle(monkeypatch, prefix, kind, N, R, seed):
-    """k_vg_lookup (block prefix sums in double-double + head / tail cells, vglobal.cuh; the default for the
-    site-ordered world-map moments) and the streaming k_vg_reduce it replaces (prefix = 0): moments within 1e-9 of
-    the oracle (the gate of SURVEY 8d is 1e-4); a half map of zeros keeps the mass of the sites on it at exactly 0
-    (vertex-mean fallback, voronoi.cpp:143-150); setting a new world map refreshes the prefixes."""
+def test_block_prefix_path_matches_oracle(monkeypatch, mode, kind, N, R, seed):
+    """The three ways to the site-ordered world-map moments (vglobal.cuh): "fused" (the default: block prefix sums in
+    double-double walked inside the row partition kernel), "lookup" (interval table + site-ordered k_vg_lookup) and
+    "stream" (k_vg_reduce reads every cell).  Moments within 1e-9 of the oracle (the gate of SURVEY 8d is 1e-4); a
+    map with zero stretches (left half, and a band in the middle of every row) keeps the mass of the sites on them at
+    exactly 0 (vertex-mean fallback, voronoi.cpp:143-150); setting a new world map refreshes the prefixes."""
     import coverage_control as cc
     from oracle import oracle as orc
 
     monkeypatch.setenv("CCB_VG_GENERIC", "0")
-    monkeypatch.setenv("CCB_VG_PREFIX", str(prefix))
+    monkeypatch.setenv("CCB_VG_PREFIX", _MODES[mode][0])
+    monkeypatch.setenv("CCB_VG_FUSED", _MODES[mode][1])
     rng = np.random.default_rng(seed)
     pos = _sites(kind, N, R, rng)
     p = cc.Parameters()
@@ -140,6 +145,7 @@ def test_block_prefix_path_matches_oracle(monkeypatch, prefix, kind, N, R, seed)
         wm = rng.random((N, N)).astype(np.float32)
         if variant == 1:
             wm[:, : N // 2] = 0.0
+            wm[:, 5 * N // 8: 7 * N // 8] = 0.0  # zeros AFTER non-zero cells: the prefix entries must not move
         if variant < 2:
             env = cc.CoverageSystem(p, cc.WorldIDF(p, wm), cc.PointVector(pos))
         else:  # a new map in the SAME environment: the stale prefixes must not survive
@@ -163,8 +169,8 @@ def test_block_prefix_path_matches_oracle(monkeypatch, prefix, kind, N, R, seed)
                 assert np.allclose(np.array(c.centroid), np.array(oc.centroid[:]), rtol=1e-9, atol=1e-7)
 
 
-@pytest.mark.parametrize("prefix", [1, 0])
-def test_low_mass_cell_behind_a_heavy_row_prefix(monkeypatch, prefix):
+@pytest.mark.parametrize("mode", list(_MODES))
+def test_low_mass_cell_behind_a_heavy_row_prefix(monkeypatch, mode):
     """A cell whose whole mass is ~1e-9 / ~1e-11 at the END of rows whose running sums are ~1e3:
     plain fp64 prefix differences would lose it (ulp(1e3) ~ 1e-13) and could flip the `mass < 1e-10` vertex-mean
     fallback of voronoi.cpp:41-53; the double-double entries + direct head / tail sums must not.  The site owns the
@@ -173,7 +179,8 @@ def test_low_mass_cell_behind_a_heavy_row_prefix(monkeypatch, prefix):
     from oracle import oracle as orc
 
     monkeypatch.setenv("CCB_VG_GENERIC", "0")
-    monkeypatch.setenv("CCB_VG_PREFIX", str(prefix))
+    monkeypatch.setenv("CCB_VG_PREFIX", _MODES[mode][0])
+    monkeypatch.setenv("CCB_VG_FUSED", _MODES[mode][1])
     N = 1024
     p = cc.Parameters()
     p.pWorldMapSize = p.pRobotMapSize = N
