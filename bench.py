@@ -338,11 +338,13 @@ def c4_row_bands(ccb, device, rank, world, dist, args):
     t.record()
     torch.cuda.synchronize()
     idf_ms = s.elapsed_time(t)
-    env = BatchedCoverageSystem(p, 1, r, device=device)
+    stream = torch.cuda.Stream(device=device)
+    env = BatchedCoverageSystem(p, 1, r, device=device, stream=stream.cuda_stream)
     env.set_world(0, idf)
     env.reset(pos)
-    banded = BandedCoverageSystem(env, 0)
-    ctrl = BatchedCVT(env, 0)
+    banded = BandedCoverageSystem(env, 0, stream=stream, graph=True)
+    banded.compute_cells()
+    ctrls = {"clairvoyant": BatchedCVT(env, 0), "decentralized": BatchedCVT(env, 2)}
     steps = 50
 
     def barrier():
@@ -351,29 +353,36 @@ def c4_row_bands(ccb, device, rank, world, dist, args):
         torch.cuda.synchronize()
 
     out = {}
-    for kind in ("clairvoyant",):
+    peak, _ = measured_peak_gbs()
+    for kind, ctrl in ctrls.items():
         for _ in range(5):
             banded.step(ctrl)
         barrier()
-        s.record()
-        for _ in range(steps):
-            banded.step(ctrl)
-        t.record()
+        with torch.cuda.stream(stream):
+            s.record()
+            for _ in range(steps):
+                banded.step(ctrl)
+            t.record()
         torch.cuda.synchronize()
         ms = torch.tensor([s.elapsed_time(t)], device="cuda")
         if dist is not None:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         per = float(ms.item()) / steps
         rows = banded.rows[1] - banded.rows[0]
-        peak, _ = measured_peak_gbs()
-        out[kind] = {"ms_per_step": per, "env_steps_per_s": 1e3 / per, "rows_per_gpu": rows,
-                     "band_map_bytes": 4.0 * n * rows, "band_hbm_floor_ms": 4.0 * n * rows / (peak * 1e9) * 1e3,
-                     "frac_of_band_hbm_floor": (4.0 * n * rows / (peak * 1e9) * 1e3) / per}
+        out[kind] = {"ms_per_step": per, "env_steps_per_s": 1e3 / per}
+        if kind == "clairvoyant":
+            out[kind].update({"rows_per_gpu": rows, "band_map_bytes": 4.0 * n * rows,
+                              "band_hbm_floor_ms": 4.0 * n * rows / (peak * 1e9) * 1e3,
+                              "frac_of_band_hbm_floor": (4.0 * n * rows / (peak * 1e9) * 1e3) / per})
+        else:
+            out[kind]["robots_per_gpu"] = banded.robots[1] - banded.robots[0]
+    ctrl = ctrls["clairvoyant"]
     obj = banded.step(ctrl, with_objective=True)
     barrier()
     out.update({"workload": f"C4: {n}x{n} world, {r} robots, 1024 Gaussians + 64 polygons, row bands over {world} GPU(s)",
                 "n_gpus": world, "idf_gen_ms_banded": idf_ms, "objective": float(obj[0]),
-                "per_rank_state_bytes": int(4 * n * n + r * n * (n // 32) * 4 + 2 * n * (n // 32) * 4)})
+                "step": "partials -> NCCL all-reduce -> finalise -> actions -> move + window marks, ONE captured CUDA graph",
+                "per_rank_state_bytes": int(banded.per_rank_bytes)})
     return out
 
 
@@ -545,11 +554,13 @@ def main():
     #   traffic         dram__bytes_read + dram__bytes_write of the committed `ncu --set full` capture, scaled to E.
     cells = N_WORLD * N_WORLD
     cnt = C.c_uint64(0)
-    _lib.check(lib.ccb_bench_kernel(batch._h, 0, 1, obs.data_ptr()))  # a fresh row partition for the pair counter
     _lib.check(lib.ccb_test_count(batch._h, 0, C.byref(cnt)))
     seen_cells = float(cnt.value)        # cells of all robots' local windows their robot maps have seen
+    batch.set_option("vg_fused", 0)      # (the fused kernel writes no interval table: count the pairs on the table path)
+    _lib.check(lib.ccb_bench_kernel(batch._h, 0, 1, obs.data_ptr()))
     _lib.check(lib.ccb_test_count(batch._h, 1, C.byref(cnt)))
     pairs = float(cnt.value)             # (site, row) pairs with cells in the whole-map partition
+    batch.set_option("vg_fused", int(os.environ.get("CCB_VG_FUSED", "1") != "0"))
     ER = float(N_ROBOTS * E)
     win_bits = LOCAL * (LOCAL // 32 + 1) * 4.0          # the mask words of one window
     obs_out = 16.0 * CNN * CNN                          # 4 channels x C^2 floats

@@ -97,6 +97,7 @@ SIGNATURES = {
                                     c_int_p, c_double_p]),
     "ccb_env_get_cells_all": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
     "ccb_env_objective": (C.c_int, [C.c_void_p, c_double_p]),
+    "ccb_env_objective_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ccb_env_voronoi_labels": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]),
     "ccb_env_voronoi_features": (C.c_int, [C.c_void_p, c_double_p]),
     "ccb_env_voronoi_features_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -121,6 +122,8 @@ SIGNATURES = {
     "ccb_env_voronoi_partials_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ccb_env_finalize_from_partials_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ccb_env_step_actions_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ccb_env_window_partials_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ccb_env_set_window_sums_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ccb_ctrl_create": (C.c_void_p, [C.c_void_p, C.c_int]),
     "ccb_ctrl_destroy": (None, [C.c_void_p]),
     "ccb_ctrl_compute_actions": (C.c_int, [C.c_void_p]),

@@ -763,7 +763,7 @@ static int launch_voronoi_single(ccb_env *env, double *sums) {
   if (d.L <= VW_MAXL && (d.N & 3) == 0 && !env->vw_generic) {
     const size_t smem = vw_smem_bytes(d.R);
     if (ensure_smem(env, k_voronoi_window, smem)) return 1;
-    k_voronoi_window<<<dim3(d.R, d.E), VW_THREADS, smem, env->stream>>>(d, sums);
+    k_voronoi_window<<<dim3(d.R, d.E), VW_THREADS, smem, env->stream>>>(d, sums, 0);
     CCB_LAUNCH_CHECK();
     return 0;
   }
@@ -1546,6 +1546,34 @@ extern "C" int ccb_env_finalize_from_partials_dev(ccb_env *env, const double *su
   return 0;
 }
 
+// DecentralizedCVT over several GPUs: the robots' windows are independent, so they are dealt to the ranks by ROBOT.
+// Window moments (decentralized_cvt.h:85-143) of robots [robot0, robot1) into sums_dev (E x R x 4, zeros elsewhere)...
+extern "C" int ccb_env_window_partials_dev(ccb_env *env, int robot0, int robot1, double *sums_dev) {
+  if (!env->initialised) return fail("environment has no robot positions yet");
+  const EnvDev &d = env->d;
+  if (robot0 < 0 || robot1 > d.R || robot0 > robot1) return fail("window partials: bad robot range");
+  if (!(d.L <= VW_MAXL && (d.N & 3) == 0)) return fail("window partials: needs pLocalMapSize <= 256 and pWorldMapSize % 4 == 0");
+  CCB_CUDA(cudaSetDevice(env->device));
+  if (join_aux(env)) return 1;
+  CCB_CUDA(cudaMemsetAsync(sums_dev, 0, sizeof(double) * 4 * d.E * d.R, env->stream));
+  if (robot1 > robot0) {
+    const size_t smem = vw_smem_bytes(d.R);
+    if (ensure_smem(env, k_voronoi_window, smem)) return 1;
+    k_voronoi_window<<<dim3(robot1 - robot0, d.E), VW_THREADS, smem, env->stream>>>(d, sums_dev, robot0);
+    CCB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+// ... and, once all-reduced, handed back as the window moments of the current positions: the next
+// DecentralizedCVT ComputeActions uses them instead of reducing the windows itself
+extern "C" int ccb_env_set_window_sums_dev(ccb_env *env, const double *sums_dev) {
+  if (!env->initialised) return fail("environment has no robot positions yet");
+  CCB_CUDA(cudaSetDevice(env->device));
+  CCB_CUDA(cudaMemcpyAsync(env->d_wsums, sums_dev, sizeof(double) * 4 * env->E * env->R, cudaMemcpyDeviceToDevice, env->stream));
+  env->wsums_version = env->pos_version;
+  return 0;
+}
+
 extern "C" int ccb_env_set_band_mode(ccb_env *env, int on) {
   env->band_mode = on != 0;
   env->cells_version = 0;
@@ -1581,6 +1609,12 @@ static int objective_aux(ccb_env *env, double *out_dev) {
   CCB_CUDA(cudaEventRecord(env->ev_aux, env->aux));
   env->aux_pending = true;
   return 0;
+}
+
+// GetObjectiveValue for every environment, left on the device (E doubles), on the env stream
+extern "C" int ccb_env_objective_dev(ccb_env *env, double *out_dev) {
+  CCB_CUDA(cudaSetDevice(env->device));
+  return objective_dev(env, out_dev);
 }
 
 extern "C" int ccb_env_objective(ccb_env *env, double *out) {

@@ -168,7 +168,7 @@ __device__ __forceinline__ void vg_pfx_step(DD &s, DD &sy, DD &syy, float4 a, fl
 // four warps in order and STORES the band's moments; k_vg_bandsum then adds the bands in order.  No table, no
 // spans, no item list, no atomics: run-to-run bit-stable (flagged rows still go through k_vg_fixup's atomics).
 template <int RPT = 1, bool SUM = false>
-__global__ void __launch_bounds__(VG_PART_THREADS) k_vg_partition(VgArgs a) {
+__global__ void __launch_bounds__(VG_PART_THREADS, SUM ? 6 : 1) k_vg_partition(VgArgs a) {
   __shared__ int s_ord[VG_MAXR];
   __shared__ double s_x[VG_MAXR], s_y[VG_MAXR];
   __shared__ int s_rmin[VG_MAXR], s_rmax[VG_MAXR];
@@ -393,31 +393,46 @@ __host__ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e
     const int nown = (active && !flagged) ? top + 1 : 0;
     const VgPfx *prow = a.pfx + ((size_t)e * N + row) * vg_pfx_row_entries(N);
     const float *wrow = d.world + ((size_t)e * N + row) * N;
-    // everything the walk reads, requested into L2 now: one entry per boundary, one sector per unaligned boundary
-    for (int m = 1; m <= nown; ++m) {
-      const int T = tc[m];
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + (T >> 3)));
-      if (T & (VG_PB - 1)) asm volatile("prefetch.global.L2 [%0];" ::"l"(wrow + (T & ~(VG_PB - 1))));
-    }
     const int maxown = __reduce_max_sync(0xffffffffu, nown);
     const double x = (double)row + 0.5;
     DD Ls{0.0, 0.0}, Lsy{0.0, 0.0}, Lsyy{0.0, 0.0};  // the entry at the block edge at or after the left boundary
     double hs = 0.0, hsy = 0.0, hsyy = 0.0;          // the cells between the left boundary and that edge
     int Tl = 0;
+    // the right boundary of owner m: its prefix entry and (unless it sits on a block edge) its map sector; the loads of
+    // owner m + 1 are issued before owner m is worked on, so one boundary per row is always in flight
+    double2 n0, n1, n2;
+    float4 nA, nB;
+    n0 = n1 = n2 = make_double2(0.0, 0.0), nA = nB = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nown > 0) {
+      const int T = tc[1];
+      const double2 *ep = reinterpret_cast<const double2 *>(prow + (T >> 3));
+      n0 = __ldg(ep), n1 = __ldg(ep + 1), n2 = __ldg(ep + 2);
+      if (T & (VG_PB - 1)) {
+        const float4 *p4 = reinterpret_cast<const float4 *>(wrow + (T & ~(VG_PB - 1)));
+        nA = __ldg(p4), nB = __ldg(p4 + 1);
+      }
+    }
     for (int m = 0; m < maxown; ++m) {
       int slot = -1;
       double vm = 0.0, vsx = 0.0, vsy = 0.0, vs2 = 0.0;
+      const double2 e0 = n0, e1 = n1, e2 = n2;
+      const float4 A = nA, B = nB;
+      if (m + 1 < nown) {
+        const int T = tc[m + 2];
+        const double2 *ep = reinterpret_cast<const double2 *>(prow + (T >> 3));
+        n0 = __ldg(ep), n1 = __ldg(ep + 1), n2 = __ldg(ep + 2);
+        if (T & (VG_PB - 1)) {
+          const float4 *p4 = reinterpret_cast<const float4 *>(wrow + (T & ~(VG_PB - 1)));
+          nA = __ldg(p4), nB = __ldg(p4 + 1);
+        }
+      }
       if (m < nown) {
         const int T = tc[m + 1], b = T >> 3, f = T & (VG_PB - 1);
-        const double2 *ep = reinterpret_cast<const double2 *>(prow + b);
-        const double2 e0 = __ldg(ep), e1 = __ldg(ep + 1), e2 = __ldg(ep + 2);
         const DD Es{e0.x, e0.y}, Esy{e1.x, e1.y}, Esyy{e2.x, e2.y};
         DD Ns = Es, Nsy = Esy, Nsyy = Esyy;
         double rs = 0.0, rsy = 0.0, rsyy = 0.0, nhs = 0.0, nhsy = 0.0, nhsyy = 0.0;
         bool direct = false;
         if (f) {
-          const float4 *p4 = reinterpret_cast<const float4 *>(wrow + VG_PB * b);
-          const float4 A = __ldg(p4), B = __ldg(p4 + 1);
           const double y0 = (double)(VG_PB * b) + 0.5;
           const unsigned below = (1u << f) - 1u;
           if ((Tl >> 3) == b && (Tl & (VG_PB - 1))) {  // the whole interval lies inside this block: its cells, directly

@@ -163,12 +163,13 @@ __device__ __forceinline__ void vw_accumulate(const EnvDev &d, VwShared &sh, con
   }
 }
 
-__global__ void __launch_bounds__(VW_THREADS, 3) k_voronoi_window(EnvDev d, double *__restrict__ sums) {
+// robot0: first robot of the launch (a shard of the robots when the windows are dealt over several GPUs)
+__global__ void __launch_bounds__(VW_THREADS, 3) k_voronoi_window(EnvDev d, double *__restrict__ sums, int robot0) {
   extern __shared__ __align__(16) unsigned char vw_smem[];
   VwShared &sh = *reinterpret_cast<VwShared *>(vw_smem);
   double *s_px = reinterpret_cast<double *>(vw_smem + sizeof(VwShared));
   double *s_py = s_px + d.R;
-  const int r = blockIdx.x, e = blockIdx.y;
+  const int r = robot0 + blockIdx.x, e = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t er = (size_t)e * d.R + r;
   const double res = d.res;

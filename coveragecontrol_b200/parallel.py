@@ -134,14 +134,27 @@ def _wrap_dev(ptr: int, shape, dtype, device):
 
 
 class BandedCoverageSystem:
-    """One large world tiled in row bands over the ranks (BASELINE config 4).
+    """One large world tiled over the ranks (BASELINE config 4).
 
-    Every rank constructs the same :class:`BatchedCoverageSystem` (replicated positions; controllers
-    are deterministic, so the replicas stay bit-identical) and calls :meth:`compute_cells` instead of
-    relying on the env-level lazy Voronoi: partials over the rank's rows -> all-reduce -> finalise.
+    Every rank constructs the same :class:`BatchedCoverageSystem` (replicated positions and maps; the controllers are
+    deterministic, so the replicas stay bit-identical) and shares out the *work* of a step:
+
+    * ClairvoyantCVT / CentralizedCVT / the objective: rank g labels and reduces map rows ``band_rows(N, G, g)`` only
+      (``ccb_env_voronoi_partials_dev``), the per-robot moment partials ``[E][R][4]`` float64 are combined with ONE
+      ``all_reduce(SUM)`` and every rank finalises the cells (``ccb_env_finalize_from_partials_dev``);
+    * DecentralizedCVT: the robots' local windows are independent, so they are dealt out by ROBOT: rank g reduces the
+      windows of robots ``shard_envs(R, G, g)`` (``ccb_env_window_partials_dev``), the same all-reduce, and every rank
+      takes the result as its window moments (``ccb_env_set_window_sums_dev``).
+
+    Memory is NOT sharded: every rank holds the whole world map and all robot bit planes (``per_rank_bytes``); a band
+    owner would otherwise need a halo of L/2 rows for the windows of robots near its band edge.
+
+    ``graph=True``: a step (partials, the NCCL all-reduce, finalisation, actions, kinematics, window marks) is captured
+    into ONE CUDA graph on its second call and replayed afterwards -- the environment must then have been created on
+    ``stream`` (a ``torch.cuda.Stream``), which the all-reduce is issued on as well.
     """
 
-    def __init__(self, env, src: int = 0):
+    def __init__(self, env, src: int = 0, stream=None, graph: bool = False):
         import torch
 
         self.env = env
@@ -149,8 +162,34 @@ class BandedCoverageSystem:
         rank, world = _rank_world()
         self.rank, self.world = rank, world
         self.rows = band_rows(env._params.pWorldMapSize, world, rank)
-        self._sums = torch.zeros((env._E, env._R, 4), dtype=torch.float64, device=torch.device("cuda", env._device))
+        r = shard_envs(env._R, world, rank)
+        self.robots = (r.start, r.stop)
+        dev = torch.device("cuda", env._device)
+        self._sums = torch.zeros((env._E, env._R, 4), dtype=torch.float64, device=dev)
+        self._obj = torch.zeros((env._E,), dtype=torch.float64, device=dev)
+        self.stream = stream
+        if graph and stream is None:
+            raise ValueError("graph=True needs the torch.cuda.Stream the environment was created on")
+        if stream is not None and int(stream.cuda_stream) != int(env._stream):
+            raise ValueError("the environment was not created on `stream`")
+        self.graph = bool(graph)
+        self._graphs = {}
+        self._seen = {}
         _lib.check(_lib.load().ccb_env_set_band_mode(env._h, 1))
+
+    @property
+    def per_rank_bytes(self) -> int:
+        """Device bytes of the replicated state: world map, robot bit planes (+ exploration planes), system planes."""
+        n, r, e = self.env._params.pWorldMapSize, self.env._R, self.env._E
+        planes = r * (2 if self.env._params.pUpdateExplorationMap else 1) + 2
+        return e * (4 * n * n + planes * n * ((n + 31) // 32) * 4)
+
+    def _ctx(self):
+        import contextlib
+
+        import torch
+
+        return torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
 
     def compute_cells(self, src: int | None = None):
         """voronoi.cpp:55-327 over the whole world: band partials, one all-reduce, finalisation.
@@ -158,20 +197,61 @@ class BandedCoverageSystem:
         lib = _lib.load()
         r0, r1 = self.rows
         src = self.src if src is None else int(src)
-        _lib.check(lib.ccb_env_voronoi_partials_dev(self.env._h, src, r0, r1, self._sums.data_ptr()))
-        allreduce_sum_(self._sums)
-        _lib.check(lib.ccb_env_finalize_from_partials_dev(self.env._h, self._sums.data_ptr()))
+        with self._ctx():
+            _lib.check(lib.ccb_env_voronoi_partials_dev(self.env._h, src, r0, r1, self._sums.data_ptr()))
+            allreduce_sum_(self._sums)
+            _lib.check(lib.ccb_env_finalize_from_partials_dev(self.env._h, self._sums.data_ptr()))
         return self._sums
 
-    def step(self, ctrl, with_objective: bool = False):
-        """``ComputeActions(); StepActions(GetActions())`` of a Clairvoyant/Centralized controller on the
-        banded world, device-resident.  Returns the objective (E,) at the new positions if asked."""
+    def compute_window_moments(self):
+        """decentralized_cvt.h:85-143 for every robot: this rank's robots, one all-reduce, handed to the controller."""
         lib = _lib.load()
-        self.compute_cells()
-        _lib.check(lib.ccb_ctrl_compute_actions(ctrl._h))
-        _lib.check(lib.ccb_env_step_actions_dev(self.env._h, lib.ccb_ctrl_actions_dev(ctrl._h)))
+        with self._ctx():
+            _lib.check(lib.ccb_env_window_partials_dev(self.env._h, self.robots[0], self.robots[1], self._sums.data_ptr()))
+            allreduce_sum_(self._sums)
+            _lib.check(lib.ccb_env_set_window_sums_dev(self.env._h, self._sums.data_ptr()))
+        return self._sums
+
+    def _step_eager(self, ctrl, with_objective: bool):
+        lib = _lib.load()
+        with self._ctx():
+            if ctrl._KIND == 2:
+                self.compute_window_moments()
+            else:
+                self.compute_cells(1 if ctrl._KIND == 1 else 0)
+            _lib.check(lib.ccb_ctrl_compute_actions(ctrl._h))
+            _lib.check(lib.ccb_env_step_actions_dev(self.env._h, lib.ccb_ctrl_actions_dev(ctrl._h)))
+            if with_objective:  # coverage_system.h:598-601: always on the world map
+                self.compute_cells(0)
+                _lib.check(lib.ccb_env_objective_dev(self.env._h, self._obj.data_ptr()))
         self.env._invalidate()
-        if with_objective:  # coverage_system.h:598-601: always on the world map
-            self.compute_cells(0)
-            return self.env.objective()
-        return None
+
+    def step(self, ctrl, with_objective: bool = False):
+        """``ComputeActions(); StepActions(GetActions())`` of a CVT controller on the tiled world, device-resident.
+        Returns the objective (E,) at the new positions if asked (a device tensor, valid once the stream has run)."""
+        if not self.graph:
+            self._step_eager(ctrl, with_objective)
+            return self._obj if with_objective else None
+        import torch
+
+        key = (id(ctrl), bool(with_objective))
+        g = self._graphs.get(key)
+        if g is not None:
+            with self._ctx():
+                g.replay()  # (the library's version counters keep their relative state: nothing to update on the host)
+            self.env._invalidate()
+            return self._obj if with_objective else None
+        n = self._seen.get(key, 0)
+        self._seen[key] = n + 1
+        if n < 1:  # first call: eager (allocates whatever the kernels need; NCCL warms up)
+            self._step_eager(ctrl, with_objective)
+            return self._obj if with_objective else None
+        g = torch.cuda.CUDAGraph()
+        self.stream.synchronize()
+        with torch.cuda.graph(g, stream=self.stream):
+            self._step_eager(ctrl, with_objective)
+        self._graphs[key] = g
+        with self._ctx():  # nothing ran during the capture: run the step this call asked for
+            g.replay()
+        self.env._invalidate()
+        return self._obj if with_objective else None

@@ -167,6 +167,7 @@ int ccb_env_get_cells(ccb_env *env, int e, double *mass, double *centroid, doubl
 /* the same for every environment at once: mass E x R, centroid E x R x 2, sum_dist_sqr E x R (any may be NULL) */
 int ccb_env_get_cells_all(ccb_env *env, double *mass, double *centroid, double *sum_dist_sqr);
 int ccb_env_objective(ccb_env *env, double *out /* E */); /* coverage_system.h:598-601 */
+int ccb_env_objective_dev(ccb_env *env, double *out_dev); /* the same, left on the device (env stream) */
 /* parity-test accessor: the site index the fused label+reduce kernel assigns to every cell
  * (src 0: world map, 1: explored-IDF map); out = E x N x N int32 on the host.  The product path
  * never stores labels. */
@@ -199,6 +200,12 @@ int ccb_env_set_band_mode(ccb_env *env, int on);
 int ccb_env_voronoi_partials_dev(ccb_env *env, int src, int row0, int row1, double *sums_dev);
 /* voronoi.cpp:41-53 + voronoi.h:89-95 from all-reduced moments; the env-level cells become current */
 int ccb_env_finalize_from_partials_dev(ccb_env *env, const double *sums_dev);
+/* DecentralizedCVT over several GPUs: robots' windows are independent, so the ranks share them out by robot.
+ * Window moments (decentralized_cvt.h:85-143) of robots [robot0, robot1) -> sums_dev (E x R x 4, zeros elsewhere);
+ * after the caller's all-reduce(SUM), ccb_env_set_window_sums_dev makes them the window moments of the current
+ * positions (the next DecentralizedCVT ComputeActions uses them instead of reducing the windows itself). */
+int ccb_env_window_partials_dev(ccb_env *env, int robot0, int robot1, double *sums_dev);
+int ccb_env_set_window_sums_dev(ccb_env *env, const double *sums_dev);
 /* coverage_system.h:279-291 StepActions with the actions already on the device (E x R x 2) */
 int ccb_env_step_actions_dev(ccb_env *env, const double *actions_dev);
 

@@ -44,20 +44,28 @@ def main():
     a, b = np.array(whole.GetWorldMap()), np.array(banded_idf.GetWorldMap())
     assert np.array_equal(a.view(np.int32), b.view(np.int32)), "banded IDF differs from the whole-map IDF"
 
-    plain = BatchedCoverageSystem(p, 1, R, device=local)
-    plain.set_world(0, whole)
-    plain.reset(pos[None])
-    benv = BatchedCoverageSystem(p, 1, R, device=local)
-    benv.set_world(0, banded_idf)
-    benv.reset(pos[None])
-    banded = BandedCoverageSystem(benv, 0)
-    banded.compute_cells()
-    c0, c1 = BatchedCVT(plain, 0), BatchedCVT(benv, 0)
-    for _ in range(10):
-        c0.rollout(1)
-        obj = banded.step(c1, with_objective=True)
-        assert np.allclose(plain.positions(), benv.positions(), rtol=0, atol=1e-9)
-        assert abs(obj[0] - plain.objective()[0]) <= 1e-10 * abs(obj[0])
+    # every controller family on the tiled world against the same roll-out on rank-local whole-map kernels:
+    # eager launches first, then the captured graph (partials -> ncclAllReduce -> finalise -> actions -> move, one graph)
+    stream = torch.cuda.Stream(device=local)
+    for kind, name in ((0, "ClairvoyantCVT"), (1, "CentralizedCVT"), (2, "DecentralizedCVT")):
+        for graph in (False, True):
+            plain = BatchedCoverageSystem(p, 1, R, device=local)
+            plain.set_world(0, whole)
+            plain.reset(pos[None])
+            benv = BatchedCoverageSystem(p, 1, R, device=local, stream=stream.cuda_stream)
+            benv.set_world(0, banded_idf)
+            benv.reset(pos[None])
+            banded = BandedCoverageSystem(benv, 0, stream=stream, graph=graph)
+            banded.compute_cells()
+            c0, c1 = BatchedCVT(plain, kind), BatchedCVT(benv, kind)
+            for it in range(10):
+                c0.rollout(1)
+                obj = banded.step(c1, with_objective=(it % 2 == 1))
+                stream.synchronize()
+                assert np.allclose(plain.positions(), benv.positions(), rtol=0, atol=1e-9), (name, graph, it)
+                if obj is not None:
+                    o = float(obj[0])
+                    assert abs(o - plain.objective()[0]) <= 1e-10 * abs(o), (name, graph, it)
     # replicas stay identical across ranks
     mine = torch.from_numpy(benv.positions()).cuda()
     ref = mine.clone()
