@@ -641,13 +641,13 @@ __device__ __forceinline__ void ob_items(const EnvDev &d, ObsShared &sh, const f
             if (lost) ob &= ~(1u << bit);
           }
         }
-        double s = 0.0, tt = 0.0, u = 0.0;
+        // (s, t, u) = sum (1, q, q^2) v_q over the group's own cells: pairwise trees, three short dependency chains
+        double dv[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const double dv = (double)(((ob >> q) & 1u) ? c[4 + q] : 0.f);
-          s += dv;
-          if (q > 0) tt = fma((double)q, dv, tt), u = fma((double)(q * q), dv, u);
-        }
+        for (int q = 0; q < 8; ++q) dv[q] = (double)(((ob >> q) & 1u) ? c[4 + q] : 0.f);
+        const double s = ((dv[0] + dv[1]) + (dv[2] + dv[3])) + ((dv[4] + dv[5]) + (dv[6] + dv[7]));
+        const double tt = (fma(3.0, dv[3], fma(2.0, dv[2], dv[1]))) + (fma(7.0, dv[7], fma(6.0, dv[6], fma(5.0, dv[5], 4.0 * dv[4]))));
+        const double u = (fma(9.0, dv[3], fma(4.0, dv[2], dv[1]))) + (fma(49.0, dv[7], fma(36.0, dv[6], fma(25.0, dv[5], 16.0 * dv[4]))));
         const double y0 = (double)c0 + 0.5, xd = (double)row + 0.5;
         acc[0] += s;
         acc[1] = fma(xd, s, acc[1]);
