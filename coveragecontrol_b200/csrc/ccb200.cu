@@ -1049,9 +1049,8 @@ extern "C" int ccb_env_set_world_host(ccb_env *env, int e, const float *map) {
 
 static int launch_mark(ccb_env *env, int e, int robot, int mark_robot, int mark_sys) {
   const EnvDev &d = env->d;
-  const int words = d.S * (d.S / 32 + 2);  // window rows x words a row can touch
-  dim3 grid(std::max(1, std::min(8, (words + 255) / 256)), robot >= 0 ? 1 : d.R, e >= 0 ? 1 : d.E);
-  k_mark_windows<<<grid, 256, 0, env->stream>>>(d, e, robot, mark_robot, mark_sys);
+  const long warps = (long)(robot >= 0 ? 1 : d.R) * (e >= 0 ? 1 : d.E);  // one warp per (robot, environment)
+  k_mark_windows<<<(unsigned)((warps + MARK_WARPS - 1) / MARK_WARPS), MARK_WARPS * 32, 0, env->stream>>>(d, e, robot, mark_robot, mark_sys);
   CCB_LAUNCH_CHECK();
   return 0;
 }

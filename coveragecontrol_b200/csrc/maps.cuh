@@ -198,11 +198,20 @@ __global__ void __launch_bounds__(256) k_exploration_features(EnvDev d, int K, d
 
 // ---- sensor window marking ---------------------------------------------------------------------
 // robot_model.h:98-122 (UpdateRobotMap / UpdateExplorationMap) and coverage_system.h:104-118
-// (explored_idf / exploration windows).  grid = (1, R, E); env_sel/robot_sel >= 0 select one.
-// A thread ORs one word of one window row: S x S cells are S x ceil(S/32 + 1) word updates.
-__global__ void k_mark_windows(EnvDev d, int env_sel, int robot_sel, int mark_robot, int mark_sys) {
-  const int e = env_sel >= 0 ? env_sel : blockIdx.z;
-  const int r = robot_sel >= 0 ? robot_sel : blockIdx.y;
+// (explored_idf / exploration windows).  One WARP per (robot, environment), MARK_WARPS of them per CTA;
+// env_sel / robot_sel >= 0 select one.  A lane ORs one word of one window row: S x S cells are S x (S / 32 + 1)
+// word updates.  A robot moves a cell or so per step, so all but one row / one bit column of its window is marked
+// already: every word is READ first and only written when the OR would change it (the robot's own planes with a
+// plain store -- no other warp writes them -- the shared system planes with an atomic).
+constexpr int MARK_WARPS = 8;
+__global__ void __launch_bounds__(MARK_WARPS * 32) k_mark_windows(EnvDev d, int env_sel, int robot_sel, int mark_robot, int mark_sys) {
+  const int nr = robot_sel >= 0 ? 1 : d.R;
+  const long wid = (long)blockIdx.x * MARK_WARPS + (threadIdx.x >> 5);
+  const long total_w = (long)nr * (env_sel >= 0 ? 1 : d.E);
+  if (wid >= total_w) return;
+  const int e = env_sel >= 0 ? env_sel : (int)(wid / nr);
+  const int r = robot_sel >= 0 ? robot_sel : (int)(wid % nr);
+  const int lane = threadIdx.x & 31;
   const double *p = d.pos_g + ((size_t)e * d.R + r) * 2;
   const Window w = make_window(d.res, p[0], p[1], d.S, d.N);
   if (w.x1 <= w.x0 || w.y1 <= w.y0) return;
@@ -211,23 +220,23 @@ __global__ void k_mark_windows(EnvDev d, int env_sel, int robot_sel, int mark_ro
   uint32_t *seen = robot_plane(d, d.seenb, e, r);
   uint32_t *xseen = d.xseenb ? robot_plane(d, d.xseenb, e, r) : nullptr;
   uint32_t *sys0 = sys_plane(d, e, 0), *sys1 = sys_plane(d, e, 1);
-  if (mark_robot && d.upd_robot && blockIdx.x == 0 && threadIdx.x == 0) {
-    int *box = d.seen_box + ((size_t)e * d.R + r) * 4;
-    atomicMin(box, w.x0), atomicMax(box + 1, w.x1), atomicMin(box + 2, w.y0), atomicMax(box + 3, w.y1);
+  if (mark_robot && d.upd_robot && lane == 0) {
+    int *box = d.seen_box + ((size_t)e * d.R + r) * 4;  // only this warp touches this robot's box
+    box[0] = min(box[0], w.x0), box[1] = max(box[1], w.x1), box[2] = min(box[2], w.y0), box[3] = max(box[3], w.y1);
   }
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+  const bool do_robot = mark_robot && d.upd_robot, do_expl = mark_robot && d.upd_expl, do_sys = mark_sys && d.upd_sys;
+  for (int t = lane; t < total; t += 32) {
     const int a = t / nwords, wd = w0 + (t - a * nwords);
     const int lo = max(w.y0, wd * 32) - wd * 32, hi = min(w.y1, wd * 32 + 32) - wd * 32;  // bits [lo, hi)
     const uint32_t m = (hi - lo >= 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
     const size_t idx = (size_t)(w.x0 + a) * d.NW + wd;
-    if (mark_robot) {
-      if (d.upd_robot) atomicOr(seen + idx, m);
-      if (d.upd_expl) atomicOr(xseen + idx, m);
-    }
-    if (mark_sys && d.upd_sys) {
-      atomicOr(sys0 + idx, m);
-      atomicOr(sys1 + idx, m);
-    }
+    // all the reads first: four independent loads per word in flight
+    const uint32_t o_seen = do_robot ? seen[idx] : m, o_x = do_expl ? xseen[idx] : m;
+    const uint32_t o_s0 = do_sys ? sys0[idx] : m, o_s1 = do_sys ? sys1[idx] : m;
+    if ((o_seen & m) != m) seen[idx] = o_seen | m;
+    if ((o_x & m) != m) xseen[idx] = o_x | m;
+    if ((o_s0 & m) != m) atomicOr(sys0 + idx, m);
+    if ((o_s1 & m) != m) atomicOr(sys1 + idx, m);
   }
 }
 
