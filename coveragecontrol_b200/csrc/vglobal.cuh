@@ -161,11 +161,21 @@ __device__ __forceinline__ void vg_pfx_step(DD &s, DD &sy, DD &syy, float4 a, fl
 
 // RPT rows per thread: a CTA's band is RPT * VG_PART_THREADS rows (RPT > 1, opt-in through CCB_VG_PART_RPT: the
 // sort / twin / cull / 1 / (2 dy) preamble is paid once per band, against a taller band culling fewer sites)
+constexpr int VG_LMAX = 16;  // owners of one row the fused walk lists (rows with more go to k_vg_fixup)
+struct VgRowLists {           // shared memory of k_vg_partition<1, true>: the rows' owner lists, then the accumulators
+  double wacc[VG_PART_THREADS / 32][VG_MAXR][4];
+  unsigned short tc[VG_LMAX + 1][VG_PART_THREADS];
+  unsigned char slot[VG_LMAX][VG_PART_THREADS];
+  unsigned char nown[VG_PART_THREADS];
+  int maxown;
+};
+
 // SUM (world-map moments with valid block prefix sums, RPT = 1): instead of writing the interval table for a second
-// kernel, every row thread walks its owners left to right and turns the breakpoints into moments on the spot -- one
-// prefix entry and one map sector per boundary, prefetched as soon as the breakpoints are known; a segmented warp
-// reduction (by site, fixed shuffle tree) adds the 32 rows of a warp into per-warp accumulators, the CTA adds its
-// four warps in order and STORES the band's moments; k_vg_bandsum then adds the bands in order.  No table, no
+// kernel, the row threads leave their owners and breakpoints in shared memory and the CTA walks them as ITEMS (m-th
+// owner of 32 consecutive rows): a lane turns its row's two breakpoints into moments -- one prefix entry and one map
+// sector per boundary, all loads of an item independent -- and a segmented warp reduction (by site, fixed shuffle
+// tree: neighbouring rows mostly share their m-th owner) adds the 32 rows into per-warp accumulators; the CTA adds
+// its four warps in order and STORES the band's moments; k_vg_bandsum then adds the bands in order.  No table, no
 // spans, no item list, no atomics: run-to-run bit-stable (flagged rows still go through k_vg_fixup's atomics).
 template <int RPT = 1, bool SUM = false>
 __global__ void __launch_bounds__(VG_PART_THREADS, SUM ? 6 : 1) k_vg_partition(VgArgs a) {
@@ -181,9 +191,12 @@ __global__ void __launch_bounds__(VG_PART_THREADS, SUM ? 6 : 1) k_vg_partition(V
   __shared__ double t_x[VG_MAXR], t_y[VG_MAXR];
   __shared__ unsigned char t_keep[VG_MAXR];
   __shared__ int s_nkeep;
-  __shared__ double s_wacc[SUM ? VG_PART_THREADS / 32 * VG_MAXR * 4 : 1];
-  if (SUM)
+  __shared__ __align__(16) unsigned char s_lists_raw[SUM ? sizeof(VgRowLists) : 16];
+  double *s_wacc = reinterpret_cast<double *>(s_lists_raw);  // (VgRowLists::wacc comes first)
+  if (SUM) {
     for (int k = tid; k < VG_PART_THREADS / 32 * VG_MAXR * 4; k += VG_PART_THREADS) s_wacc[k] = 0.0;
+    if (tid == 0) reinterpret_cast<VgRowLists *>(s_lists_raw)->maxown = 0;
+  }
   for (int k = tid; k < R; k += VG_PART_THREADS) {
     const double yk = pos[2 * k + 1];
     int rank = 0;
@@ -248,17 +261,71 @@ __global__ void __launch_bounds__(VG_PART_THREADS, SUM ? 6 : 1) k_vg_partition(V
   }
   __syncthreads();
   if (SUM) {
-    // (every thread takes part in the warp reductions: rows beyond the band are inactive)
-    const int row = a.row0 + blockIdx.x * VG_PART_THREADS + tid;
-    vg_partition_row<true>(a, e, min(row, a.row1 - 1), row < a.row1, Rs, s_ord, s_x, s_y, s_inv, s_rmin, s_rmax, s_wacc);
+    VgRowLists &L = *reinterpret_cast<VgRowLists *>(s_lists_raw);
+    const int row_t = a.row0 + blockIdx.x * VG_PART_THREADS + tid;
+    vg_partition_row<true>(a, e, min(row_t, a.row1 - 1), row_t < a.row1, Rs, s_ord, s_x, s_y, s_inv, s_rmin, s_rmax, s_wacc);
+    atomicMax(&L.maxown, (int)L.nown[tid]);
+    __syncthreads();
+    // ---- the walk: item = (m, group of 32 rows); lane <-> row -------------------------------------------------
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nitems = L.maxown * (VG_PART_THREADS / 32);
+    const size_t pe = vg_pfx_row_entries(N);
+#pragma unroll 1
+    for (int item = warp; item < nitems; item += VG_PART_THREADS / 32) {
+      const int m = item / (VG_PART_THREADS / 32), t = (item % (VG_PART_THREADS / 32)) * 32 + lane;
+      int slot = -1;
+      double vm = 0.0, vsx = 0.0, vsy = 0.0, vs2 = 0.0;
+      if (m < (int)L.nown[t]) {
+        const int row = a.row0 + blockIdx.x * VG_PART_THREADS + t;
+        const int Tl = L.tc[m][t], T = L.tc[m + 1][t];
+        const int bl = Tl >> 3, fl = Tl & (VG_PB - 1), b = T >> 3, f = T & (VG_PB - 1);
+        const VgPfx *prow = a.pfx + ((size_t)e * N + row) * pe;
+        const float4 *wrow = reinterpret_cast<const float4 *>(d.world + ((size_t)e * N + row) * N);
+        double rs = 0.0, rsy = 0.0, rsyy = 0.0;
+        if (fl && bl == b) {  // the whole interval lies inside one block: its cells, directly
+          const float4 A = __ldg(wrow + 2 * b), B = __ldg(wrow + 2 * b + 1);
+          vg_add8(A, B, ((1u << f) - 1u) & ~((1u << fl) - 1u), (double)(VG_PB * b) + 0.5, rs, rsy, rsyy);
+        } else {
+          // every load of the item first: the two prefix entries and the (at most) two map sectors
+          const double2 *el = reinterpret_cast<const double2 *>(prow + bl), *er = reinterpret_cast<const double2 *>(prow + b);
+          const double2 l0 = __ldg(el), l1 = __ldg(el + 1), l2 = __ldg(el + 2);
+          const double2 r0 = __ldg(er), r1 = __ldg(er + 1), r2 = __ldg(er + 2);
+          float4 LA = make_float4(0.f, 0.f, 0.f, 0.f), LB = LA, RA = LA, RB = LA;
+          if (fl) LA = __ldg(wrow + 2 * bl), LB = __ldg(wrow + 2 * bl + 1);
+          if (f) RA = __ldg(wrow + 2 * b), RB = __ldg(wrow + 2 * b + 1);
+          DD Ls{l0.x, l0.y}, Lsy{l1.x, l1.y}, Lsyy{l2.x, l2.y};
+          if (fl) {  // head: the cells [Tl, 8 bl + 8); the entry at that block edge = the scan's next step
+            vg_add8(LA, LB, 0xffu & ~((1u << fl) - 1u), (double)(VG_PB * bl) + 0.5, rs, rsy, rsyy);
+            vg_pfx_step(Ls, Lsy, Lsyy, LA, LB, bl);
+          }
+          if (f) vg_add8(RA, RB, (1u << f) - 1u, (double)(VG_PB * b) + 0.5, rs, rsy, rsyy);  // tail: the cells [8 b, T)
+          rs += dd_diff(DD{r0.x, r0.y}, Ls), rsy += dd_diff(DD{r1.x, r1.y}, Lsy), rsyy += dd_diff(DD{r2.x, r2.y}, Lsyy);
+        }
+        const double x = (double)row + 0.5;
+        vm = rs, vsx = x * rs, vsy = rsy, vs2 = fma(x * x, rs, rsyy);
+        slot = L.slot[m][t];
+      }
+      unsigned todo = __ballot_sync(0xffffffffu, slot >= 0);
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int sl = __shfl_sync(0xffffffffu, slot, leader);
+        const bool mine = slot == sl;
+        const Sum4 tot = reduce4(mine ? vm : 0.0, mine ? vsx : 0.0, mine ? vsy : 0.0, mine ? vs2 : 0.0);
+        if (lane == leader) {
+          double *acc = &L.wacc[warp][sl][0];
+          acc[0] += tot.m, acc[1] += tot.sx, acc[2] += tot.sy, acc[3] += tot.s2;
+        }
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+      }
+    }
     __syncthreads();
     // band moments = the four warps' accumulators in order; sites without cells in the band store zeros
     double *dst = a.band + ((size_t)e * gridDim.x + blockIdx.x) * R * 4;
     for (int i = tid; i < R * 4; i += VG_PART_THREADS) {
-      double t = 0.0;
+      double tsum = 0.0;
 #pragma unroll
-      for (int wq = 0; wq < VG_PART_THREADS / 32; ++wq) t += s_wacc[wq * VG_MAXR * 4 + i];
-      dst[i] = t;
+      for (int wq = 0; wq < VG_PART_THREADS / 32; ++wq) tsum += s_wacc[wq * VG_MAXR * 4 + i];
+      dst[i] = tsum;
     }
     return;
   }
@@ -369,6 +436,7 @@ __host__ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e
       lo = hi;
     }
   }
+  if (SUM && top + 1 > VG_LMAX) flagged = true;  // more owners than the walk's lists hold: the per-cell rule takes the row
   // a flagged row is left to k_vg_fixup entirely
   if (flagged && active) a.flag_list[vg_next(a.nflag)] = e * N + row;
   if (!SUM) {
@@ -389,84 +457,13 @@ __host__ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e
   }
 #ifdef __CUDA_ARCH__
   if (SUM) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the row's owners and breakpoints for the CTA's walk (k_vg_partition): m-major, a row per thread
+    VgRowLists &L = *reinterpret_cast<VgRowLists *>(s_wacc);
+    const int t = threadIdx.x;
     const int nown = (active && !flagged) ? top + 1 : 0;
-    const VgPfx *prow = a.pfx + ((size_t)e * N + row) * vg_pfx_row_entries(N);
-    const float *wrow = d.world + ((size_t)e * N + row) * N;
-    const int maxown = __reduce_max_sync(0xffffffffu, nown);
-    const double x = (double)row + 0.5;
-    DD Ls{0.0, 0.0}, Lsy{0.0, 0.0}, Lsyy{0.0, 0.0};  // the entry at the block edge at or after the left boundary
-    double hs = 0.0, hsy = 0.0, hsyy = 0.0;          // the cells between the left boundary and that edge
-    int Tl = 0;
-    // the right boundary of owner m: its prefix entry and (unless it sits on a block edge) its map sector; the loads of
-    // owner m + 1 are issued before owner m is worked on, so one boundary per row is always in flight
-    double2 n0, n1, n2;
-    float4 nA, nB;
-    n0 = n1 = n2 = make_double2(0.0, 0.0), nA = nB = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (nown > 0) {
-      const int T = tc[1];
-      const double2 *ep = reinterpret_cast<const double2 *>(prow + (T >> 3));
-      n0 = __ldg(ep), n1 = __ldg(ep + 1), n2 = __ldg(ep + 2);
-      if (T & (VG_PB - 1)) {
-        const float4 *p4 = reinterpret_cast<const float4 *>(wrow + (T & ~(VG_PB - 1)));
-        nA = __ldg(p4), nB = __ldg(p4 + 1);
-      }
-    }
-    for (int m = 0; m < maxown; ++m) {
-      int slot = -1;
-      double vm = 0.0, vsx = 0.0, vsy = 0.0, vs2 = 0.0;
-      const double2 e0 = n0, e1 = n1, e2 = n2;
-      const float4 A = nA, B = nB;
-      if (m + 1 < nown) {
-        const int T = tc[m + 2];
-        const double2 *ep = reinterpret_cast<const double2 *>(prow + (T >> 3));
-        n0 = __ldg(ep), n1 = __ldg(ep + 1), n2 = __ldg(ep + 2);
-        if (T & (VG_PB - 1)) {
-          const float4 *p4 = reinterpret_cast<const float4 *>(wrow + (T & ~(VG_PB - 1)));
-          nA = __ldg(p4), nB = __ldg(p4 + 1);
-        }
-      }
-      if (m < nown) {
-        const int T = tc[m + 1], b = T >> 3, f = T & (VG_PB - 1);
-        const DD Es{e0.x, e0.y}, Esy{e1.x, e1.y}, Esyy{e2.x, e2.y};
-        DD Ns = Es, Nsy = Esy, Nsyy = Esyy;
-        double rs = 0.0, rsy = 0.0, rsyy = 0.0, nhs = 0.0, nhsy = 0.0, nhsyy = 0.0;
-        bool direct = false;
-        if (f) {
-          const double y0 = (double)(VG_PB * b) + 0.5;
-          const unsigned below = (1u << f) - 1u;
-          if ((Tl >> 3) == b && (Tl & (VG_PB - 1))) {  // the whole interval lies inside this block: its cells, directly
-            vg_add8(A, B, below & ~((1u << (Tl & (VG_PB - 1))) - 1u), y0, rs, rsy, rsyy);
-            direct = true;
-          } else {
-            vg_add8(A, B, below, y0, rs, rsy, rsyy);    // tail: the cells [8 b, T)
-          }
-          vg_add8(A, B, 0xffu & ~below, y0, nhs, nhsy, nhsyy);  // head of the next owner: [T, 8 b + 8)
-          vg_pfx_step(Ns, Nsy, Nsyy, A, B, b);                  // E[b + 1], as the scan built it
-        }
-        if (!direct) {
-          rs += dd_diff(Es, Ls) + hs;
-          rsy += dd_diff(Esy, Lsy) + hsy;
-          rsyy += dd_diff(Esyy, Lsyy) + hsyy;
-        }
-        Ls = Ns, Lsy = Nsy, Lsyy = Nsyy, hs = nhs, hsy = nhsy, hsyy = nhsyy, Tl = T;
-        vm = rs, vsx = x * rs, vsy = rsy, vs2 = fma(x * x, rs, rsyy);
-        slot = s_ord[v[m]];
-      }
-      // the warp's rows by site: neighbouring rows mostly share their m-th owner
-      unsigned todo = __ballot_sync(0xffffffffu, slot >= 0);
-      while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const int sl = __shfl_sync(0xffffffffu, slot, leader);
-        const bool mine = slot == sl;
-        const Sum4 tot = reduce4(mine ? vm : 0.0, mine ? vsx : 0.0, mine ? vsy : 0.0, mine ? vs2 : 0.0);
-        if (lane == leader) {
-          double *acc = s_wacc + ((size_t)warp * VG_MAXR + sl) * 4;
-          acc[0] += tot.m, acc[1] += tot.sx, acc[2] += tot.sy, acc[3] += tot.s2;
-        }
-        todo &= ~__ballot_sync(0xffffffffu, mine);
-      }
-    }
+    L.nown[t] = (unsigned char)nown;
+    for (int m = 0; m < nown; ++m) L.tc[m][t] = tc[m], L.slot[m][t] = (unsigned char)s_ord[v[m]];
+    if (nown > 0) L.tc[nown][t] = tc[nown];
   }
 #endif
 }
