@@ -570,7 +570,7 @@ struct ccb_env {
   bool band_mode = false;       // this env holds one row band of a world tiled over several GPUs
   int vg_part_rpt = 1;          // CCB_VG_PART_RPT (opt-in, 1 / 2 / 4): rows per thread of k_vg_partition
   bool vg_prefix = true;        // block prefix sums of the world maps for the site-ordered world-map moments (vglobal.cuh)
-  VgPfx *d_vg_pfx = nullptr;    // [E][N][N / 8 + 1] x 48 B, allocated on first use, rebuilt per environment when its world map is set
+  VgPfx *d_vg_pfx = nullptr;    // [E][N][N / 16 + 1] x 128 B, allocated on first use, rebuilt per environment when its world map is set
   std::vector<char> pfx_valid;  // [E]: the entries of environment e match its world map
   int *d_pfx_list = nullptr;    // [E] environments to rebuild
   double *d_vg_band = nullptr;  // [E][ceil(N / 128)][R][4] band moments of the fused partition + moments kernel
@@ -688,6 +688,12 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
       // world-map moments inside the row partition: one prefix entry + one map sector per boundary, band moments
       // stored, bands added in order (no table, no spans, no atomics)
       if (stages & 1) {
+        // (static + dynamic shared memory pass 48 KB at R = 64: the opt-in covers the dynamic part)
+        size_t &have = env->func_smem[reinterpret_cast<const void *>(k_vg_partition<1, true>)];
+        if (have < psmem + 1) {
+          CCB_CUDA(cudaFuncSetAttribute(k_vg_partition<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(psmem, 40 * 1024)));
+          have = psmem + 1;
+        }
         k_vg_partition<1, true><<<dim3(nbands, d.E), VG_PART_THREADS, psmem, env->stream>>>(g);
         CCB_LAUNCH_CHECK();
       }
