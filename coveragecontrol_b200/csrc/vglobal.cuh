@@ -87,28 +87,23 @@ __global__ void k_vg_init_span(int *span, int n) {
 
 // ---- block prefix sums: the world-map moments without streaming the map ---------------------------------
 // The world map of an environment is constant while its robots move, and a site's cells on a row are ONE column
-// interval [lo, hi).  Next to every map row the library keeps, for every block of VG_PB = 16 columns, ONE 128-byte
-// record (8 bytes of HBM per map cell): the running sums of (v, y v, y^2 v) (y = col + 0.5, cell units) over the
-// columns before the block AND the block's 16 map values.  The moments of a cell are then differences of records
-// plus the few cells between a boundary and the next block edge, all of which sit in the boundary's record: a
-// whole-map pass reads ONE 128-byte line per Voronoi boundary of a row -- the unit the memory system moves for a
-// random access anyway (ncu r02h: a 64-byte entry plus a 32-byte map sector cost 256 bytes of DRAM traffic) --
-// instead of every map cell: ~0.9 MB instead of 4.2 MB per 1024^2 environment with 32 robots.
-// Accuracy.  Only cells inside an interval are ever added directly, and the running sums are DOUBLE-DOUBLE (hi +
-// lo, ~106 bits) built by a SEQUENTIAL scan E[b + 1] = E[b] (+) blocksum(b): the difference of two records is the
-// exact sum of the block sums between them to ~1e-32 of the row's total -- a cell of mass 1e-9 at the end of a row
-// whose prefix is 1e3 keeps ~20 digits, so the `mass < 1e-10` fallback (voronoi.cpp:41-53) fires on the same
-// cells as with exact sums -- and a run of zero cells leaves the running sums bitwise unchanged, so it sums to
-// exactly 0.  The block sums themselves are fp64 sums of exact products, like k_vg_reduce's.
+// interval [lo, hi).  Next to every map row the library keeps the running sums of (v, y v, y^2 v) (y = col + 0.5,
+// cell units) at every VG_PB-th column: entry b = the sum over the columns < VG_PB b, b = 0 .. N / VG_PB, one
+// 64-byte record each (8 bytes of HBM per map cell; the unit DRAM hands out is 64 bytes).  The moments of a cell
+// are then differences of entries plus the few cells between a boundary and the next block edge, so a whole-map
+// pass reads one entry and one 32-byte map sector per Voronoi BOUNDARY of a row instead of every map cell
+// (~0.8 MB instead of 4.2 MB per 1024^2 environment with 32 robots).
+// Accuracy.  Only cells inside an interval are ever added directly, and the entries are DOUBLE-DOUBLE (hi + lo,
+// ~106 bits) built by a SEQUENTIAL scan E[b + 1] = E[b] (+) blocksum(b): the difference of two entries is the
+// exact sum of the 8-cell block sums between them to ~1e-32 of the row's total -- a cell of mass 1e-9 at the end
+// of a row whose prefix is 1e3 keeps ~20 digits, so the `mass < 1e-10` fallback (voronoi.cpp:41-53) fires on
+// the same cells as with exact sums -- and a run of zero cells leaves the entries bitwise unchanged, so it sums
+// to exactly 0.  The block sums themselves are fp64 sums of exact products, like k_vg_reduce's.
 // Only for the world map (SRC_WORLD, no labels): the explored and robot maps change with every step.
-constexpr int VG_PB = 16;  // columns per block
-constexpr int VG_PSH = 4;  // log2(VG_PB)
-struct __align__(128) VgPfx {
-  double s_hi, s_lo, sy_hi, sy_lo, syy_hi, syy_lo;  // sums over the columns < VG_PB b of this row
-  float v[VG_PB];                                   // the map values of columns VG_PB b .. VG_PB b + 15
-  double pad[2];
+constexpr int VG_PB = 8;  // columns per block: one 32-byte sector of the map row
+struct __align__(64) VgPfx {
+  double s_hi, s_lo, sy_hi, sy_lo, syy_hi, syy_lo, pad0, pad1;
 };
-static_assert(sizeof(VgPfx) == 128, "one record per 128-byte line");
 __host__ __device__ inline size_t vg_pfx_row_entries(int N) { return (size_t)N / VG_PB + 1; }
 
 #ifdef __CUDACC__
@@ -142,9 +137,11 @@ __device__ __forceinline__ DD dd_add(DD a, DD b) {
   s = dd_quick(s.hi, __dadd_rn(s.lo, t.hi));
   return dd_quick(s.hi, __dadd_rn(s.lo, t.lo));
 }
-__device__ __forceinline__ double dd_diff(DD a, DD b) {  // a - b, rounded to fp64 once
-  const DD d = dd_add(a, DD{-b.hi, -b.lo});
-  return __dadd_rn(d.hi, d.lo);
+// a - b rounded to fp64: the high parts by an error-free subtraction, the low parts and its error added in fp64
+// (|error| <= ~2^-104 |a|: the entries are running sums, the result is rounded to 53 bits anyway)
+__device__ __forceinline__ double dd_diff(DD a, DD b) {
+  const DD d = dd_two_sum(a.hi, -b.hi);
+  return __dadd_rn(d.hi, __dadd_rn(d.lo, __dsub_rn(a.lo, b.lo)));
 }
 
 // eight cells y0 .. y0 + 7 (cell units) of one row, those with a bit in `keep` only
@@ -155,26 +152,11 @@ __device__ __forceinline__ void vg_add8(float4 a, float4 b, unsigned keep, doubl
   vg_add4(b, y0 + 4.0, rs, rsy, rsyy);
 }
 
-// sixteen cells y0 .. y0 + 15 of one row (a record's map values), those with a bit in `keep` only
-struct VgBlk {
-  float4 q[4];
-};
-__device__ __forceinline__ void vg_add16(const VgBlk &v, unsigned keep, double y0, double &rs, double &rsy, double &rsyy) {
-  vg_add8(v.q[0], v.q[1], keep & 0xffu, y0, rs, rsy, rsyy);
-  vg_add8(v.q[2], v.q[3], (keep >> 8) & 0xffu, y0 + 8.0, rs, rsy, rsyy);
-}
-__device__ __forceinline__ VgBlk vg_blk_load(const VgPfx *rec) {
-  const float4 *p4 = reinterpret_cast<const float4 *>(rec->v);
-  VgBlk b;
-  b.q[0] = __ldg(p4), b.q[1] = __ldg(p4 + 1), b.q[2] = __ldg(p4 + 2), b.q[3] = __ldg(p4 + 3);
-  return b;
-}
-
-// E[b + 1] from E[b] and the sixteen cells of block b: THE step of the sequential scan (k_vg_prefix); the partition
-// kernel repeats it to get the running sums at the block edge after a boundary without a second look-up, bit for bit
-__device__ __forceinline__ void vg_pfx_step(DD &s, DD &sy, DD &syy, const VgBlk &v, int blk) {
+// E[b + 1] from E[b] and the eight cells of block b: THE step of the sequential scan (k_vg_prefix); the partition
+// kernel repeats it to get the entry after a boundary without a second look-up, bit for bit
+__device__ __forceinline__ void vg_pfx_step(DD &s, DD &sy, DD &syy, float4 a, float4 b, int blk) {
   double bs = 0.0, bsy = 0.0, bsyy = 0.0;
-  vg_add16(v, 0xffffu, (double)(VG_PB * blk) + 0.5, bs, bsy, bsyy);
+  vg_add8(a, b, 0xffu, (double)(VG_PB * blk) + 0.5, bs, bsy, bsyy);
   s = dd_add(s, DD{bs, 0.0}), sy = dd_add(sy, DD{bsy, 0.0}), syy = dd_add(syy, DD{bsyy, 0.0});
 }
 #endif  // __CUDACC__
@@ -193,7 +175,8 @@ struct VgRowLists {           // shared memory of k_vg_partition<1, true>: the r
 // SUM (world-map moments with valid block prefix sums, RPT = 1): instead of writing the interval table for a second
 // kernel, the row threads leave their owners and breakpoints in shared memory and the CTA walks them as ITEMS (m-th
 // owner of 32 consecutive rows): a lane turns its row's two breakpoints into moments -- one prefix entry and one map
-// sector per boundary, all loads of an item independent -- and a segmented warp reduction (by site, fixed shuffle
+// sector per boundary (the entries at the block edges just inside the interval, the cells between the boundaries
+// and those edges), all loads of an item independent -- and a segmented warp reduction (by site, fixed shuffle
 // tree: neighbouring rows mostly share their m-th owner) adds the 32 rows into per-warp accumulators; the CTA adds
 // its four warps in order and STORES the band's moments; k_vg_bandsum then adds the bands in order.  No table, no
 // spans, no item list, no atomics: run-to-run bit-stable (flagged rows still go through k_vg_fixup's atomics).
@@ -298,26 +281,28 @@ __global__ void __launch_bounds__(VG_PART_THREADS, SUM ? 6 : 1) k_vg_partition(V
       if (m < (int)L.nown[t]) {
         const int row = a.row0 + blockIdx.x * VG_PART_THREADS + t;
         const int Tl = L.tc[m][t], T = L.tc[m + 1][t];
-        const int bl = Tl >> VG_PSH, fl = Tl & (VG_PB - 1), b = T >> VG_PSH, f = T & (VG_PB - 1);
+        const int bl = Tl >> 3, fl = Tl & (VG_PB - 1), b = T >> 3, f = T & (VG_PB - 1);
         const VgPfx *prow = a.pfx + ((size_t)e * N + row) * pe;
+        const float4 *wrow = reinterpret_cast<const float4 *>(d.world + ((size_t)e * N + row) * N);
         double rs = 0.0, rsy = 0.0, rsyy = 0.0;
         if (fl && bl == b) {  // the whole interval lies inside one block: its cells, directly
-          vg_add16(vg_blk_load(prow + b), ((1u << f) - 1u) & ~((1u << fl) - 1u), (double)(VG_PB * b) + 0.5, rs, rsy, rsyy);
+          const float4 A = __ldg(wrow + 2 * b), B = __ldg(wrow + 2 * b + 1);
+          vg_add8(A, B, ((1u << f) - 1u) & ~((1u << fl) - 1u), (double)(VG_PB * b) + 0.5, rs, rsy, rsyy);
         } else {
-          // every load of the item first: the two records (running sums; map values only where a block is cut)
-          const double2 *el = reinterpret_cast<const double2 *>(prow + bl), *er = reinterpret_cast<const double2 *>(prow + b);
+          // every load of the item first: the entries at the block edges just inside the interval -- at or after Tl,
+          // at or before T -- and the (at most) two map sectors the boundaries cut
+          const int blo = bl + (fl ? 1 : 0);
+          const double2 *el = reinterpret_cast<const double2 *>(prow + blo), *er = reinterpret_cast<const double2 *>(prow + b);
           const double2 l0 = __ldg(el), l1 = __ldg(el + 1), l2 = __ldg(el + 2);
           const double2 r0 = __ldg(er), r1 = __ldg(er + 1), r2 = __ldg(er + 2);
-          VgBlk LV, RV;
-          if (fl) LV = vg_blk_load(prow + bl);
-          if (f) RV = vg_blk_load(prow + b);
-          DD Ls{l0.x, l0.y}, Lsy{l1.x, l1.y}, Lsyy{l2.x, l2.y};
-          if (fl) {  // head: the cells [Tl, 16 bl + 16); the running sums at that block edge = the scan's next step
-            vg_add16(LV, 0xffffu & ~((1u << fl) - 1u), (double)(VG_PB * bl) + 0.5, rs, rsy, rsyy);
-            vg_pfx_step(Ls, Lsy, Lsyy, LV, bl);
-          }
-          if (f) vg_add16(RV, (1u << f) - 1u, (double)(VG_PB * b) + 0.5, rs, rsy, rsyy);  // tail: the cells [16 b, T)
-          rs += dd_diff(DD{r0.x, r0.y}, Ls), rsy += dd_diff(DD{r1.x, r1.y}, Lsy), rsyy += dd_diff(DD{r2.x, r2.y}, Lsyy);
+          float4 LA = make_float4(0.f, 0.f, 0.f, 0.f), LB = LA, RA = LA, RB = LA;
+          if (fl) LA = __ldg(wrow + 2 * bl), LB = __ldg(wrow + 2 * bl + 1);
+          if (f) RA = __ldg(wrow + 2 * b), RB = __ldg(wrow + 2 * b + 1);
+          if (fl) vg_add8(LA, LB, 0xffu & ~((1u << fl) - 1u), (double)(VG_PB * bl) + 0.5, rs, rsy, rsyy);  // head: [Tl, 8 bl + 8)
+          if (f) vg_add8(RA, RB, (1u << f) - 1u, (double)(VG_PB * b) + 0.5, rs, rsy, rsyy);                 // tail: [8 b, T)
+          rs += dd_diff(DD{r0.x, r0.y}, DD{l0.x, l0.y});
+          rsy += dd_diff(DD{r1.x, r1.y}, DD{l1.x, l1.y});
+          rsyy += dd_diff(DD{r2.x, r2.y}, DD{l2.x, l2.y});
         }
         const double x = (double)row + 0.5;
         vm = rs, vsx = x * rs, vsy = rsy, vs2 = fma(x * x, rs, rsyy);
@@ -654,31 +639,19 @@ __global__ void __launch_bounds__(128) k_vg_prefix(const float *__restrict__ wor
   const int e = envs ? envs[ei] : ei;
   const float4 *src = reinterpret_cast<const float4 *>(world_all + ((size_t)e * N + row) * N);
   const int nblk = N / VG_PB;
-  VgPfx *dst = pfx_all + ((size_t)e * N + row) * vg_pfx_row_entries(N);
+  double2 *dst = reinterpret_cast<double2 *>(pfx_all + ((size_t)e * N + row) * vg_pfx_row_entries(N));
   DD s{0.0, 0.0}, sy{0.0, 0.0}, syy{0.0, 0.0};
-  VgBlk cur;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) cur.q[k] = __ldg(src + k);
-  for (int blk = 0; blk <= nblk; ++blk) {
-    double2 *d2 = reinterpret_cast<double2 *>(dst + blk);
-    float4 *d4 = reinterpret_cast<float4 *>(dst[blk].v);
-    d2[0] = make_double2(s.hi, s.lo), d2[1] = make_double2(sy.hi, sy.lo), d2[2] = make_double2(syy.hi, syy.lo);
-    d2[7] = make_double2(0.0, 0.0);
-    if (blk == nblk) {  // the row total: no block behind it
-#pragma unroll
-      for (int k = 0; k < 4; ++k) d4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      break;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) d4[k] = cur.q[k];
-    VgBlk nxt = cur;
-    if (blk + 1 < nblk) {  // next block in flight during the scan step
-#pragma unroll
-      for (int k = 0; k < 4; ++k) nxt.q[k] = __ldg(src + 4 * (blk + 1) + k);
-    }
-    vg_pfx_step(s, sy, syy, cur, blk);
-    cur = nxt;
+  float4 a = __ldg(src), b = __ldg(src + 1);
+  for (int blk = 0; blk < nblk; ++blk) {
+    dst[4 * blk] = make_double2(s.hi, s.lo), dst[4 * blk + 1] = make_double2(sy.hi, sy.lo);
+    dst[4 * blk + 2] = make_double2(syy.hi, syy.lo), dst[4 * blk + 3] = make_double2(0.0, 0.0);
+    float4 na = a, nb = b;
+    if (blk + 1 < nblk) na = __ldg(src + 2 * blk + 2), nb = __ldg(src + 2 * blk + 3);  // next block in flight during the scan step
+    vg_pfx_step(s, sy, syy, a, b, blk);
+    a = na, b = nb;
   }
+  dst[4 * nblk] = make_double2(s.hi, s.lo), dst[4 * nblk + 1] = make_double2(sy.hi, sy.lo);
+  dst[4 * nblk + 2] = make_double2(syy.hi, syy.lo), dst[4 * nblk + 3] = make_double2(0.0, 0.0);
 }
 
 // the moments of every site = the sum of its band moments in ascending band order (plain stores: no memset, no atomics)
@@ -715,6 +688,7 @@ __global__ void __launch_bounds__(VG_LOOK_WARPS * 32) k_vg_lookup(VgArgs a, cons
   const int2 sp = __ldg(reinterpret_cast<const int2 *>(a.span) + (size_t)e * R + k);
   const size_t pe = vg_pfx_row_entries(N);
   const VgPfx *pfx = pfx_all + (size_t)e * N * pe;
+  const float *world = d.world + (size_t)e * N * N;
   const uint32_t *tab = a.table + ((size_t)e * R + k) * N;
   double M = 0.0, SX = 0.0, SY = 0.0, S2 = 0.0;
 #pragma unroll 2
@@ -723,17 +697,22 @@ __global__ void __launch_bounds__(VG_LOOK_WARPS * 32) k_vg_lookup(VgArgs a, cons
     const int lo = (int)(iv & 0xffffu), hi = (int)(iv >> 16);
     if (hi <= lo) continue;
     const int blo = (lo + VG_PB - 1) / VG_PB, bhi = hi / VG_PB;
-    const VgPfx *prow = pfx + (size_t)row * pe;
+    const float *wrow = world + (size_t)row * N;
     double rs = 0.0, rsy = 0.0, rsyy = 0.0;
     if (blo <= bhi) {
-      if (blo < bhi) vg_pfx_diff(prow + bhi, prow + blo, rs, rsy, rsyy);
-      if (lo & (VG_PB - 1))  // head: the cells [lo, 16 blo) of block blo - 1
-        vg_add16(vg_blk_load(prow + blo - 1), 0xffffu & ~((1u << (lo & (VG_PB - 1))) - 1u), (double)(VG_PB * (blo - 1)) + 0.5, rs, rsy, rsyy);
-      if (hi & (VG_PB - 1))  // tail: the cells [16 bhi, hi) of block bhi
-        vg_add16(vg_blk_load(prow + bhi), (1u << (hi & (VG_PB - 1))) - 1u, (double)(VG_PB * bhi) + 0.5, rs, rsy, rsyy);
+      if (blo < bhi) vg_pfx_diff(pfx + (size_t)row * pe + bhi, pfx + (size_t)row * pe + blo, rs, rsy, rsyy);
+      if (lo & (VG_PB - 1)) {  // head: the cells [lo, 8 blo) of block blo - 1
+        const float4 *p4 = reinterpret_cast<const float4 *>(wrow + VG_PB * (blo - 1));
+        vg_add8(__ldg(p4), __ldg(p4 + 1), 0xffu & ~((1u << (lo & (VG_PB - 1))) - 1u), (double)(VG_PB * (blo - 1)) + 0.5, rs, rsy, rsyy);
+      }
+      if (hi & (VG_PB - 1)) {  // tail: the cells [8 bhi, hi) of block bhi
+        const float4 *p4 = reinterpret_cast<const float4 *>(wrow + VG_PB * bhi);
+        vg_add8(__ldg(p4), __ldg(p4 + 1), (1u << (hi & (VG_PB - 1))) - 1u, (double)(VG_PB * bhi) + 0.5, rs, rsy, rsyy);
+      }
     } else {  // the interval lies inside block bhi
+      const float4 *p4 = reinterpret_cast<const float4 *>(wrow + VG_PB * bhi);
       const unsigned keep = ((1u << (hi & (VG_PB - 1))) - 1u) & ~((1u << (lo & (VG_PB - 1))) - 1u);
-      vg_add16(vg_blk_load(prow + bhi), keep, (double)(VG_PB * bhi) + 0.5, rs, rsy, rsyy);
+      vg_add8(__ldg(p4), __ldg(p4 + 1), keep, (double)(VG_PB * bhi) + 0.5, rs, rsy, rsyy);
     }
     const double x = (double)row + 0.5;
     M += rs;
