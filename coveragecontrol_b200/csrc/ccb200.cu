@@ -243,7 +243,7 @@ static int idf_finish(ccb_idf *idf, int row0, int row1) {
 // everything the integration kernel reads, packed on the host as ONE blob (one allocation, one copy)
 struct IdfInputs {
   std::vector<unsigned char> blob;
-  size_t o_b = 0, o_bs = 0, o_bi = 0, o_px = 0, o_py = 0, o_imp = 0, o_start = 0, o_sz = 0, o_bounds = 0;
+  size_t o_b = 0, o_bs = 0, o_bi = 0, o_px = 0, o_py = 0, o_imp = 0, o_start = 0, o_sz = 0, o_bounds = 0, o_pks = 0, o_pki = 0;
   int F = 0, NP = 0, bk_nb = 0, bk_size = 0;
 };
 
@@ -308,6 +308,27 @@ static void idf_pack_inputs(const ccb_idf *idf, IdfInputs &in) {
       for (int bx = span[i][0]; bx <= span[i][1]; ++bx)
         for (int by = span[i][2]; by <= span[i][3]; ++by) bk_items[fill[(size_t)bx * bk_nb + by]++] = i;
   }
+  // the same grid for the polygon pieces, by bounding box (closed, one cell of margin)
+  std::vector<int> pk_start((size_t)bk_nb * bk_nb + 1, 0), pk_items;
+  {
+    const double cell = p.pResolution * bk_size, mg = p.pResolution;
+    std::vector<std::array<int, 4>> span(NP);
+    for (int i = 0; i < NP; ++i) {
+      const float4 &b = bounds[i];
+      int x0 = (int)std::floor((b.x - mg) / cell), x1 = (int)std::floor((b.y + mg) / cell);
+      int y0 = (int)std::floor((b.z - mg) / cell), y1 = (int)std::floor((b.w + mg) / cell);
+      x0 = std::max(x0, 0), y0 = std::max(y0, 0), x1 = std::min(x1, bk_nb - 1), y1 = std::min(y1, bk_nb - 1);
+      span[i] = {x0, x1, y0, y1};
+      for (int bx = x0; bx <= x1; ++bx)
+        for (int by = y0; by <= y1; ++by) pk_start[(size_t)bx * bk_nb + by + 1]++;
+    }
+    for (size_t k = 1; k < pk_start.size(); ++k) pk_start[k] += pk_start[k - 1];
+    pk_items.resize(std::max<size_t>(pk_start.back(), 1));
+    std::vector<int> fill(pk_start.begin(), pk_start.end() - 1);
+    for (int i = 0; i < NP; ++i)
+      for (int bx = span[i][0]; bx <= span[i][1]; ++bx)
+        for (int by = span[i][2]; by <= span[i][3]; ++by) pk_items[fill[(size_t)bx * bk_nb + by]++] = i;
+  }
   // everything the kernel reads goes up in ONE blob (one allocation, one copy): the order counter for the
   // maximum, the feature records, the bucket grid and the polygon pieces, each section 16-byte aligned
   std::vector<unsigned char> &blob = in.blob;
@@ -324,6 +345,7 @@ static void idf_pack_inputs(const ccb_idf *idf, IdfInputs &in) {
   const size_t o_imp = put(imp.data(), sizeof(float) * imp.size());
   const size_t o_start = put(start.data(), sizeof(int) * start.size()), o_sz = put(sz.data(), sizeof(int) * sz.size());
   const size_t o_bounds = put(bounds.data(), sizeof(float4) * bounds.size());
+  in.o_pks = put(pk_start.data(), sizeof(int) * pk_start.size()), in.o_pki = put(pk_items.data(), sizeof(int) * pk_items.size());
   in.o_b = o_b, in.o_bs = o_bs, in.o_bi = o_bi, in.o_px = o_px, in.o_py = o_py, in.o_imp = o_imp;
   in.o_start = o_start, in.o_sz = o_sz, in.o_bounds = o_bounds;
   in.F = F, in.NP = NP, in.bk_nb = bk_nb, in.bk_size = bk_size;
@@ -334,7 +356,8 @@ static int idf_launch_kernel(ccb_idf *idf, const IdfInputs &in, const unsigned c
   const int N = p.pWorldMapSize;
   PolyDev pd{reinterpret_cast<const float *>(bl + in.o_px), reinterpret_cast<const float *>(bl + in.o_py),
              reinterpret_cast<const int *>(bl + in.o_start), reinterpret_cast<const int *>(bl + in.o_sz),
-             reinterpret_cast<const float *>(bl + in.o_imp), reinterpret_cast<const float4 *>(bl + in.o_bounds), in.NP};
+             reinterpret_cast<const float *>(bl + in.o_imp), reinterpret_cast<const float4 *>(bl + in.o_bounds), in.NP,
+             reinterpret_cast<const int *>(bl + in.o_pks), reinterpret_cast<const int *>(bl + in.o_pki)};
   const BndF *d_b = reinterpret_cast<const BndF *>(bl + in.o_b);
   const int *d_bk_start = reinterpret_cast<const int *>(bl + in.o_bs), *d_bk_items = reinterpret_cast<const int *>(bl + in.o_bi);
   const float res = (float)p.pResolution;
@@ -574,6 +597,7 @@ struct ccb_env {
   std::vector<char> pfx_valid;  // [E]: the entries of environment e match its world map
   int *d_pfx_list = nullptr;    // [E] environments to rebuild
   double *d_vg_band = nullptr;  // [E][ceil(N / 128)][R][4] band moments of the fused partition + moments kernel
+  bool vg_bulk = false;         // A/B: k_vg_reduce_bulk (cp.async.bulk + mbarrier ring) instead of k_vg_reduce
   bool vg_fused = true;         // world-map moments inside the row partition kernel (off: interval table + k_vg_lookup)
   bool cnn_generic = false;     // test option: the generic observation kernel even where the fused one applies
   bool obs_v1 = false;          // test option: the row-ordered fused observation kernel of round 1 (A/B timing)
@@ -724,6 +748,12 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
       if (lookup) {
         // site-ordered look-ups on the interval table (the parity reference of the fused kernel)
         k_vg_lookup<<<dim3((d.R + VG_LOOK_WARPS - 1) / VG_LOOK_WARPS, d.E), VG_LOOK_WARPS * 32, 0, env->stream>>>(g, env->d_vg_pfx);
+      } else if (src == SRC_WORLD && !labels && env->vg_bulk) {
+        // A/B variant: bulk-asynchronous copies into a shared-memory ring (ccb_test_set_option "vg_bulk")
+        if (ensure_smem(env, k_vg_reduce_bulk, VGB_SMEM)) return 1;
+        const int items_max = chunks * d.R;
+        dim3 bgrid(std::max(1, std::min(148 * 1 * 8, (items_max + VGB_WARPS - 1) / VGB_WARPS)), d.E);
+        k_vg_reduce_bulk<<<bgrid, VGB_WARPS * 32, VGB_SMEM, env->stream>>>(g);
       } else if (src == SRC_WORLD) {
         if (labels) k_vg_reduce<SRC_WORLD, true><<<rgrid, nt, 0, env->stream>>>(g);
         else k_vg_reduce<SRC_WORLD, false, VG_U, VG_RED_MINB, 4><<<rgrid, nt, 0, env->stream>>>(g);  // 8 rows x 16 columns per pass
@@ -959,6 +989,7 @@ extern "C" int ccb_test_set_option(ccb_env *env, const char *name, int value) {
   else if (n == "vg_griddiv") env->vg_griddiv = std::max(value, 1);
   else if (n == "vg_prefix") env->vg_prefix = value != 0;
   else if (n == "vg_fused") env->vg_fused = value != 0;
+  else if (n == "vg_bulk") env->vg_bulk = value != 0;
   else if (n == "vg_part_rpt") env->vg_part_rpt = (value == 2 || value == 4) ? value : 1;
   else if (n == "no_aux") env->no_aux = value != 0;
   else if (n == "no_graph") env->no_graph = value != 0;

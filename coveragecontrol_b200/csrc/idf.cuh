@@ -26,6 +26,8 @@ struct PolyDev {
   const float *imp;
   const float4 *bounds; // xmin, xmax, ymin, ymax
   int num;
+  const int *bk_start;  // the pieces whose bounding box touches a bucket of the feature grid: bucket b lists
+  const int *bk_items;  // bk_items[bk_start[b] .. bk_start[b + 1])
 };
 
 constexpr int IDF_TX = 32;   // tile rows (x)
@@ -224,7 +226,10 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, const int *__restrict__ bk_s
   if (poly.num > 0) {
     if (tid == 0) s_npoly = 0;
     __syncthreads();
-    for (int k = tid; k < poly.num; k += IDF_THREADS) {
+    // only the pieces listed for this tile's bucket (a 64-polygon world has hundreds of pieces, a tile sees a few)
+    const int pk0 = poly.bk_start[bucket], pk1 = poly.bk_start[bucket + 1];
+    for (int kk = pk0 + tid; kk < pk1; kk += IDF_THREADS) {
+      const int k = poly.bk_items[kk];
       float4 b = poly.bounds[k];
       // mid points of the tile span [lo + res/2, hi - res/2]; test against the closed bbox
       bool keep = !(tile_xhi < b.x || tile_xlo > b.y || tile_yhi < b.z || tile_ylo > b.w);
@@ -243,9 +248,9 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, const int *__restrict__ bk_s
         float midx = __fmul_rn(fmaf(fx, res, fmaf(fx, res, res)), 0.5f);
         float midy = __fmul_rn(fmaf(fy, res, fmaf(fy, res, res)), 0.5f);
         float pim = 0.f;
-        int cnt = np <= IDF_MAXPOLY ? np : poly.num;
+        int cnt = np <= IDF_MAXPOLY ? np : pk1 - pk0;
         for (int q = 0; q < cnt; ++q) {
-          int k = np <= IDF_MAXPOLY ? s_poly[q] : q;
+          int k = np <= IDF_MAXPOLY ? s_poly[q] : poly.bk_items[pk0 + q];
           float4 b = poly.bounds[k];
           if (midx < b.x || midx > b.y || midy < b.z || midy > b.w) continue;
           int st = poly.start[k];

@@ -628,6 +628,141 @@ __global__ void __launch_bounds__(VG_RED_WARPS * 32, MINB) k_vg_reduce(VgArgs a)
   }
 }
 
+// ---- A/B: the same reduce with bulk-asynchronous copies (TMA engine) instead of per-lane loads ---------------
+// k_vg_reduce_bulk<SRC_WORLD>: one warp per (site, 32-row chunk) item as above, but a row's interval travels as ONE
+// `cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes` per (row, 256-column piece) into a per-warp
+// ring of shared-memory stages (8 rows x 1 KB each, two stages): the copies of stage s + 1 are issued before stage s
+// is consumed, an mbarrier per stage counts the bytes in, and the lanes then read their cells from shared memory
+// (row stride padded by 16 bytes: conflict-free).  No per-lane address arithmetic for the loads, no L2 prefetch loop,
+// no `want` predicates -- what VERDICT r01 (next 6) asked to try.  Selected with ccb_test_set_option("vg_bulk", 1);
+// profiles/r02_tma_ab.md has the timing against k_vg_reduce and the SASS evidence (UBLKCP).
+constexpr int VGB_ROWS = 8;                        // rows per stage (4 lanes per row when consumed)
+constexpr int VGB_COLS = 256;                      // columns per piece
+constexpr int VGB_STRIDE = VGB_COLS * 4 + 16;      // bytes between the rows of a stage
+constexpr int VGB_STAGE = VGB_ROWS * VGB_STRIDE;   // 8.1 KB: 65 KB per CTA of four warps, three CTAs per SM
+constexpr int VGB_STAGES = 2;
+constexpr int VGB_WARPS = 4;
+constexpr size_t VGB_SMEM = (size_t)VGB_WARPS * VGB_STAGES * VGB_STAGE + 16 * VGB_WARPS * VGB_STAGES;
+
+__device__ __forceinline__ uint32_t vgb_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void vgb_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "VGB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra VGB_DONE;\n"
+      "bra VGB_WAIT;\n"
+      "VGB_DONE:\n"
+      "}\n" ::"r"(mbar), "r"(parity)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(VGB_WARPS * 32) k_vg_reduce_bulk(VgArgs a) {
+  extern __shared__ __align__(128) unsigned char vgb_smem[];
+  const EnvDev &d = a.d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.y;
+  const int N = d.N, R = d.R;
+  const int *its = a.items + (size_t)e * (R + 1);
+  const int total = __ldg(its + R);
+  const float *world = d.world + (size_t)e * N * N;
+  unsigned char *stage_base = vgb_smem + (size_t)warp * VGB_STAGES * VGB_STAGE;
+  const uint32_t mbar0 = vgb_smem_addr(vgb_smem + (size_t)VGB_WARPS * VGB_STAGES * VGB_STAGE + 16 * VGB_STAGES * warp);
+  if (lane == 0) {
+#pragma unroll
+    for (int sidx = 0; sidx < VGB_STAGES; ++sidx)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar0 + 16 * sidx), "r"(VGB_ROWS));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t phase[VGB_STAGES] = {0u, 0u};
+  const int g = lane >> 2, c4 = lane & 3;  // consumer mapping: 4 lanes per row
+#pragma unroll 1
+  for (int item = blockIdx.x * VGB_WARPS + warp; item < total; item += gridDim.x * VGB_WARPS) {
+    int k;
+    {
+      const int end0 = lane < R ? __ldg(its + lane + 1) : 0x7fffffff;
+      unsigned hit = __ballot_sync(0xffffffffu, item < end0);
+      if (hit) {
+        k = __ffs(hit) - 1;
+      } else {
+        const int end1 = lane + 32 < R ? __ldg(its + lane + 33) : 0x7fffffff;
+        hit = __ballot_sync(0xffffffffu, item < end1);
+        k = 32 + __ffs(hit) - 1;
+      }
+    }
+    const int chunk = (__ldg(a.span + ((size_t)e * R + k) * 2) - a.row0) / VG_CHUNK + (item - __ldg(its + k));
+    const int rbase = a.row0 + chunk * VG_CHUNK;
+    const int myrow = rbase + lane;
+    const uint32_t iv = myrow < a.row1 ? __ldg(a.table + ((size_t)e * R + k) * N + myrow) : 0u;
+    const int lo_l = (int)(iv & 0xffffu), hi_l = (int)(iv >> 16);
+    // the item's column range, in pieces of VGB_COLS columns from an aligned start
+    const bool has_l = hi_l > lo_l;
+    const int ilo = __reduce_min_sync(0xffffffffu, has_l ? lo_l : 0x7fffffff), ihi = __reduce_max_sync(0xffffffffu, has_l ? hi_l : 0);
+    double M = 0.0, SX = 0.0, SY = 0.0, S2 = 0.0;
+    if (ihi > ilo) {
+      const int cb0 = ilo & ~3, npiece = (ihi - cb0 + VGB_COLS - 1) / VGB_COLS;
+      const int nstage = (VG_CHUNK / VGB_ROWS) * npiece;  // stage index = row group * npiece + piece
+      // issue: lanes 0 .. 7 own the rows of the stage's group
+      auto issue = [&](int st, int slot) {
+        const int q = st / npiece, pc = st - q * npiece;
+        const int lo = __shfl_sync(0xffffffffu, lo_l, VGB_ROWS * q + (lane & 7)), hi = __shfl_sync(0xffffffffu, hi_l, VGB_ROWS * q + (lane & 7));
+        if (lane < VGB_ROWS) {
+          const int p0 = cb0 + VGB_COLS * pc, p1 = p0 + VGB_COLS;
+          const int s0 = max(lo & ~3, p0), s1 = min((hi + 3) & ~3, p1);  // 16-byte aligned column range of this row's piece
+          const uint32_t mb = mbar0 + 16 * slot;
+          if (hi > lo && s1 > s0) {
+            const uint32_t bytes = (uint32_t)(s1 - s0) * 4u;
+            const uint32_t dst = vgb_smem_addr(stage_base + (size_t)slot * VGB_STAGE + (size_t)lane * VGB_STRIDE + (size_t)(s0 - p0) * 4);
+            const float *src = world + (size_t)(rbase + VGB_ROWS * q + lane) * N + s0;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                         "r"(bytes), "r"(mb)
+                         : "memory");
+          } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory");
+          }
+        }
+      };
+      issue(0, 0);
+#pragma unroll 1
+      for (int st = 0; st < nstage; ++st) {
+        const int slot = st & 1;
+        if (st + 1 < nstage) issue(st + 1, slot ^ 1);
+        vgb_wait(mbar0 + 16 * slot, phase[slot]);
+        phase[slot] ^= 1u;
+        // consume: lane (g, c4) adds the cells of row g of the stage, 4 at a time, 16 columns apart
+        const int q = st / npiece, pc = st - q * npiece;
+        const int lo = __shfl_sync(0xffffffffu, lo_l, VGB_ROWS * q + g), hi = __shfl_sync(0xffffffffu, hi_l, VGB_ROWS * q + g);
+        const int p0 = cb0 + VGB_COLS * pc;
+        const int s0 = max(lo & ~3, p0), s1 = min((hi + 3) & ~3, p0 + VGB_COLS);
+        if (hi > lo && s1 > s0) {
+          const float4 *srow = reinterpret_cast<const float4 *>(stage_base + (size_t)slot * VGB_STAGE + (size_t)g * VGB_STRIDE);
+          double rs = 0.0, rsy = 0.0, rsyy = 0.0;
+          for (int col = s0 + 4 * c4; col < s1; col += 16) {
+            float4 w = srow[(col - p0) >> 2];
+            if (col < lo || col + 4 > hi) {  // an end of the interval
+              const unsigned keep = vg_keep4(col, lo, hi);
+              w.x = (keep & 1u) ? w.x : 0.f, w.y = (keep & 2u) ? w.y : 0.f, w.z = (keep & 4u) ? w.z : 0.f, w.w = (keep & 8u) ? w.w : 0.f;
+            }
+            vg_add4(w, (double)col + 0.5, rs, rsy, rsyy);
+          }
+          const double x = (double)(rbase + VGB_ROWS * q + g) + 0.5;
+          M += rs;
+          SX = fma(x, rs, SX);
+          SY += rsy;
+          S2 += fma(x * x, rs, rsyy);
+        }
+        __syncwarp();  // every lane is done with this slot before it is refilled (next iteration's issue)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads before async-proxy writes
+      }
+    }
+    const Sum4 tot = reduce4(M, SX, SY, S2);
+    if (lane == 0) emit(a.sums, e, d.R, k, tot.m, tot.sx, tot.sy, tot.s2);
+  }
+}
+
 // ---- block prefix sums: build, band sums, and the site-ordered (bit-stable) look-up kernel -------------------
 // one thread per map row of the listed environments: the sequential double-double scan (see VgPfx above).
 // envs: the environments to (re)build, nenv of them (null: 0 .. nenv - 1).

@@ -19,6 +19,7 @@ extern "C" {
  * itself never reads the process environment).  Returns 0, or 1 for an unknown name.  Names:
  *   "vg_generic"  1: tile-ordered whole-map Voronoi (csrc/voronoi.cuh), 0: site-ordered (csrc/vglobal.cuh), -1: by shape
  *   "vg_prefix"   1/0: block prefix sums for the world-map moments (csrc/vglobal.cuh) on / off (off: k_vg_reduce streams the map)
+ *   "vg_bulk"     1: (prefix off) k_vg_reduce_bulk -- cp.async.bulk + mbarrier ring -- instead of k_vg_reduce (A/B)
  *   "vg_fused"    1/0: with prefix sums, moments inside the row partition kernel / interval table + k_vg_lookup
  *   "vw_generic"  1: generic window Voronoi kernel      "cnn_generic" 1: generic observation kernel
  *   "obs_v1"      1: the row-ordered fused observation kernel of round 1 instead of the item-ordered one

@@ -16,12 +16,20 @@ python bench.py --steps 4 --warmup 3 --step-only > $out/bench_short_$tag.json 2>
 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(?!k_idf).*' -c 600 --csv --log-file $out/launches_$tag.csv \
     python bench.py --steps 4 --warmup 3 --step-only > $out/ncu_launches_$tag.log 2>&1
 echo "launch list rc=$?"
-# one `ncu --set full` capture per hot kernel, at the bench's batch size (E = 128)
-for spec in 0:k_vg_reduce 7:k_vg_partition 2:k_voronoi_window 8:k_cnn_fused8; do
-  which=${spec%%:*}; kern=${spec##*:}
-  python scripts/prof_kernels.py --which $which --envs 128 --iters 3 > $out/prof_plain_${tag}_$kern.log 2>&1 &&
+# one `ncu --set full` capture per hot kernel, 256 environments (PROFILE_ENVS of make_profile_summary.py)
+for spec in 7:k_vg_partition:part 8:k_obs_fused:obsvor 4:k_obs_fused:obs 2:k_voronoi_window:vwin 3:k_mark_windows:mark; do
+  which=$(echo $spec | cut -d: -f1); kern=$(echo $spec | cut -d: -f2); name=$(echo $spec | cut -d: -f3)
+  python scripts/prof_kernels.py --which $which --envs 256 --iters 3 > $out/prof_plain_${tag}_$name.log 2>&1 &&
   ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"$kern" -s 1 -c 1 -f \
-      -o $out/prof_${tag}_$kern python scripts/prof_kernels.py --which $which --envs 128 --iters 3 \
-      > $out/ncu_${tag}_$kern.log 2>&1
-  echo "ncu $kern rc=$?"
+      -o $out/prof_${tag}_$name python scripts/prof_kernels.py --which $which --envs 256 --iters 3 \
+      > $out/ncu_${tag}_$name.log 2>&1
+  echo "ncu $name rc=$?"
+done
+# the IDF integration kernel at C1 and C4 (FP32 / XU pipe fractions)
+for spec in "c1:--world 1024 --features 32" "c4:--world 8192 --features 1024 --polygons 64"; do
+  name=idf_${spec%%:*}; args=${spec#*:}
+  python scripts/prof_idf.py $args > $out/prof_plain_${tag}_$name.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_idf_generate -c 1 -f \
+      -o $out/prof_${tag}_$name python scripts/prof_idf.py $args > $out/ncu_${tag}_$name.log 2>&1
+  echo "ncu $name rc=$?"
 done

@@ -74,10 +74,13 @@ KEYS = [
     "smsp__thread_inst_executed_per_inst_executed.ratio",
 ]
 traffic = {}
-TRAFFIC_KEYS = {"k_vg_reduce": "k_vg_reduce", "k_vg_partition": "k_vg_partition", "k_voronoi_window": "k_voronoi_window",
-                "k_cnn_fused8<1": "k_cnn_fused8<window Voronoi>(+k_comm_maps)", "k_cnn_fused8<(bool)1": "k_cnn_fused8<window Voronoi>(+k_comm_maps)",
-                "k_cnn_fused8<0": "k_cnn_fused8(+k_comm_maps)", "k_cnn_fused8<(bool)0": "k_cnn_fused8(+k_comm_maps)"}
-PROFILE_ENVS = 128  # scripts/gpu_evidence.sh profiles at the bench's batch size
+# kernel-name fragment of the capture -> key of bench.py's roofline.kernels
+TRAFFIC_KEYS = {"k_vg_reduce<": "A/B k_vg_reduce(streaming)", "k_vg_partition<1, 1>": "k_vg_partition<moments>",
+                "k_vg_partition<(int)1, (bool)1>": "k_vg_partition<moments>", "k_voronoi_window": "k_voronoi_window",
+                "k_obs_fused<1": "k_obs_fused<window Voronoi>", "k_obs_fused<(bool)1": "k_obs_fused<window Voronoi>",
+                "k_obs_fused<0": "k_obs_fused(local+obstacle+comm)", "k_obs_fused<(bool)0": "k_obs_fused(local+obstacle+comm)",
+                "k_mark_windows": "k_mark_windows"}
+PROFILE_ENVS = int(os.environ.get("PROFILE_ENVS", 256))  # scripts/gpu_evidence.sh profiles with this many environments
 
 
 def _num(x):

@@ -117,7 +117,8 @@ def test_cell_polygon_with_more_vertices_than_a_warp():
         assert c.mass == pytest.approx(o.mass, rel=1e-9)
 
 
-_MODES = {"fused": ("1", "1"), "lookup": ("1", "0"), "stream": ("0", "0")}  # CCB_VG_PREFIX, CCB_VG_FUSED
+_MODES = {"fused": ("1", "1", "0"), "lookup": ("1", "0", "0"), "stream": ("0", "0", "0"),
+          "bulk": ("0", "0", "1")}  # CCB_VG_PREFIX, CCB_VG_FUSED, CCB_VG_BULK
 
 
 @pytest.mark.parametrize("mode", list(_MODES))
@@ -126,7 +127,7 @@ _MODES = {"fused": ("1", "1"), "lookup": ("1", "0"), "stream": ("0", "0")}  # CC
 def test_block_prefix_path_matches_oracle(monkeypatch, mode, kind, N, R, seed):
     """The three ways to the site-ordered world-map moments (vglobal.cuh): "fused" (the default: block prefix sums in
     double-double walked inside the row partition kernel), "lookup" (interval table + site-ordered k_vg_lookup) and
-    "stream" (k_vg_reduce reads every cell).  Moments within 1e-9 of the oracle (the gate of SURVEY 8d is 1e-4); a
+    "stream" (k_vg_reduce reads every cell) and "bulk" (the same with cp.async.bulk + mbarrier staging, the TMA A/B).  Moments within 1e-9 of the oracle (the gate of SURVEY 8d is 1e-4); a
     map with zero stretches (left half, and a band in the middle of every row) keeps the mass of the sites on them at
     exactly 0 (vertex-mean fallback, voronoi.cpp:143-150); setting a new world map refreshes the prefixes."""
     import coverage_control as cc
@@ -135,6 +136,7 @@ def test_block_prefix_path_matches_oracle(monkeypatch, mode, kind, N, R, seed):
     monkeypatch.setenv("CCB_VG_GENERIC", "0")
     monkeypatch.setenv("CCB_VG_PREFIX", _MODES[mode][0])
     monkeypatch.setenv("CCB_VG_FUSED", _MODES[mode][1])
+    monkeypatch.setenv("CCB_VG_BULK", _MODES[mode][2])
     rng = np.random.default_rng(seed)
     pos = _sites(kind, N, R, rng)
     p = cc.Parameters()
@@ -181,6 +183,7 @@ def test_low_mass_cell_behind_a_heavy_row_prefix(monkeypatch, mode):
     monkeypatch.setenv("CCB_VG_GENERIC", "0")
     monkeypatch.setenv("CCB_VG_PREFIX", _MODES[mode][0])
     monkeypatch.setenv("CCB_VG_FUSED", _MODES[mode][1])
+    monkeypatch.setenv("CCB_VG_BULK", _MODES[mode][2])
     N = 1024
     p = cc.Parameters()
     p.pWorldMapSize = p.pRobotMapSize = N
