@@ -379,8 +379,10 @@ def c4_row_bands(ccb, device, rank, world, dist, args):
     ctrl = ctrls["clairvoyant"]
     obj = banded.step(ctrl, with_objective=True)
     barrier()
+    objective = float(obj[0])
+    banded.close()  # graphs with a captured all-reduce must go before the process group does
     out.update({"workload": f"C4: {n}x{n} world, {r} robots, 1024 Gaussians + 64 polygons, row bands over {world} GPU(s)",
-                "n_gpus": world, "idf_gen_ms_banded": idf_ms, "objective": float(obj[0]),
+                "n_gpus": world, "idf_gen_ms_banded": idf_ms, "objective": objective,
                 "step": "partials -> NCCL all-reduce -> finalise -> actions -> move + window marks, ONE captured CUDA graph",
                 "per_rank_state_bytes": int(banded.per_rank_bytes)})
     return out

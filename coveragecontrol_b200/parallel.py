@@ -177,6 +177,17 @@ class BandedCoverageSystem:
         self._seen = {}
         _lib.check(_lib.load().ccb_env_set_band_mode(env._h, 1))
 
+    def close(self) -> None:
+        """Release the captured graphs.  Call before ``torch.distributed.destroy_process_group()``: a graph that
+        holds a captured NCCL all-reduce keeps the communicator busy and the teardown waits for it forever."""
+        import torch
+
+        if self.stream is not None:
+            self.stream.synchronize()
+        self._graphs.clear()
+        self._seen.clear()
+        torch.cuda.synchronize()
+
     @property
     def per_rank_bytes(self) -> int:
         """Device bytes of the replicated state: world map, robot bit planes (+ exploration planes), system planes."""

@@ -66,6 +66,7 @@ def main():
                 if obj is not None:
                     o = float(obj[0])
                     assert abs(o - plain.objective()[0]) <= 1e-10 * abs(o), (name, graph, it)
+            banded.close()  # graphs with a captured all-reduce must go before the process group does
     # replicas stay identical across ranks
     mine = torch.from_numpy(benv.positions()).cuda()
     ref = mine.clone()
@@ -74,6 +75,7 @@ def main():
     dist.barrier()
     if rank == 0:
         print(f"multigpu_check ok: world_size={dist.get_world_size()} N={N} R={R} rows/rank={banded.rows}")
+    torch.cuda.synchronize()
     dist.destroy_process_group()
 
 
