@@ -426,9 +426,15 @@ __device__ inline int clip_cell_warp(const double *sx, const double *sy, int str
   int na = 4;
   double vx = (lane == 1 || lane == 2) ? w : 0.0, vy = (lane == 2 || lane == 3) ? h : 0.0;
   const double kx = sx[k * stride], ky = sy[k * stride];
+  double cjx = 0.0, cjy = 0.0;  // the sites 32 at a time: one coalesced load per chunk, then shuffles (a load per
+                                // site inside this sequential loop costs an L2 latency each: 60 us at R = 256)
   for (int j = 0; j < n && na > 0; ++j) {
+    if ((j & 31) == 0) {
+      const int jj = min(j + lane, n - 1);
+      cjx = sx[jj * stride], cjy = sy[jj * stride];
+    }
+    const double jx = __shfl_sync(0xffffffffu, cjx, j & 31), jy = __shfl_sync(0xffffffffu, cjy, j & 31);
     if (j == k) continue;
-    const double jx = sx[j * stride], jy = sy[j * stride];
     const double nx = jx - kx, ny = jy - ky;
     if (nx == 0 && ny == 0) continue;
     const double c = ((jx * jx + jy * jy) - (kx * kx + ky * ky)) / 2.;

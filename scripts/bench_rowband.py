@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--polygons", type=int, default=64)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--kind", type=int, default=0, help="0 ClairvoyantCVT, 1 CentralizedCVT, 2 DecentralizedCVT")
+    ap.add_argument("--eager", action="store_true", help="no CUDA graph (the ncu launch list shows every kernel)")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -67,12 +69,13 @@ def main():
     torch.cuda.synchronize()
     idf_ms = s.elapsed_time(t)
 
-    env = BatchedCoverageSystem(p, 1, R, device=local)
+    stream = torch.cuda.Stream(device=local)
+    env = BatchedCoverageSystem(p, 1, R, device=local, stream=stream.cuda_stream)
     env.set_world(0, idf)
     env.reset(pos)
-    banded = BandedCoverageSystem(env, 0)
+    banded = BandedCoverageSystem(env, 0, stream=stream, graph=not a.eager)
     banded.compute_cells()
-    ctrl = BatchedCVT(env, 0)
+    ctrl = BatchedCVT(env, a.kind)
 
     def barrier():
         if world > 1:
@@ -82,16 +85,19 @@ def main():
     for _ in range(a.warmup):
         banded.step(ctrl)
     barrier()
-    s.record()
-    for _ in range(a.steps):
-        banded.step(ctrl)
-    t.record()
+    with torch.cuda.stream(stream):
+        s.record()
+        for _ in range(a.steps):
+            banded.step(ctrl)
+        t.record()
     torch.cuda.synchronize()
     ms = torch.tensor([s.elapsed_time(t)], device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     obj = banded.step(ctrl, with_objective=True)
     barrier()
+    obj = [float(obj[0])]
+    banded.close()
     if rank == 0:
         per = float(ms.item()) / a.steps
         print(json.dumps({"workload": f"C4 row bands: {N}x{N} world, {R} robots, {a.features} Gaussians + {a.polygons} polygons, ClairvoyantCVT",
