@@ -267,23 +267,37 @@ __global__ void __launch_bounds__(VG_PART_THREADS, SUM ? 6 : 1) k_vg_partition(V
     VgRowLists &L = *reinterpret_cast<VgRowLists *>(s_lists_raw);
     const int row_t = a.row0 + blockIdx.x * VG_PART_THREADS + tid;
     vg_partition_row<true>(a, e, min(row_t, a.row1 - 1), row_t < a.row1, Rs, s_ord, s_x, s_y, s_inv, s_rmin, s_rmax, s_wacc);
-    atomicMax(&L.maxown, (int)L.nown[tid]);
-    __syncthreads();
-    // ---- the walk: item = (m, group of 32 rows); lane <-> row -------------------------------------------------
+    // ---- the walk: item = the m-th owner of the warp's own 32 rows; lane <-> row.  Every warp walks the lists its
+    //      own threads wrote, so it starts as soon as ITS rows are swept (no CTA barrier between sweep and walk).
     const int lane = tid & 31, warp = tid >> 5;
-    const int nitems = L.maxown * (VG_PART_THREADS / 32);
+    const int t = tid;
+    const int nown_t = (int)L.nown[t];
+    const int nitems = __reduce_max_sync(0xffffffffu, nown_t);
     const size_t pe = vg_pfx_row_entries(N);
-#pragma unroll 1
-    for (int item = warp; item < nitems; item += VG_PART_THREADS / 32) {
-      const int m = item / (VG_PART_THREADS / 32), t = (item % (VG_PART_THREADS / 32)) * 32 + lane;
-      int slot = -1;
-      double vm = 0.0, vsx = 0.0, vsy = 0.0, vs2 = 0.0;
-      if (m < (int)L.nown[t]) {
-        const int row = a.row0 + blockIdx.x * VG_PART_THREADS + t;
+    const int row = a.row0 + blockIdx.x * VG_PART_THREADS + t;
+    const VgPfx *prow = a.pfx + ((size_t)e * N + min(row, a.row1 - 1)) * pe;
+    const float4 *wrow = reinterpret_cast<const float4 *>(d.world + ((size_t)e * N + min(row, a.row1 - 1)) * N);
+    // what item m reads: the entries at the block edges just inside [Tl, T) and the map sectors its ends cut
+    auto request = [&](int m) {
+      if (m < nown_t) {
         const int Tl = L.tc[m][t], T = L.tc[m + 1][t];
         const int bl = Tl >> 3, fl = Tl & (VG_PB - 1), b = T >> 3, f = T & (VG_PB - 1);
-        const VgPfx *prow = a.pfx + ((size_t)e * N + row) * pe;
-        const float4 *wrow = reinterpret_cast<const float4 *>(d.world + ((size_t)e * N + row) * N);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + bl + (fl ? 1 : 0)));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + b));
+        if (fl) asm volatile("prefetch.global.L2 [%0];" ::"l"(wrow + 2 * bl));
+        if (f) asm volatile("prefetch.global.L2 [%0];" ::"l"(wrow + 2 * b));
+      }
+    };
+    request(0);
+    request(1);
+#pragma unroll 1
+    for (int m = 0; m < nitems; ++m) {
+      request(m + 2);  // two items ahead are on their way to L2 while this one is worked on
+      int slot = -1;
+      double vm = 0.0, vsx = 0.0, vsy = 0.0, vs2 = 0.0;
+      if (m < nown_t) {
+        const int Tl = L.tc[m][t], T = L.tc[m + 1][t];
+        const int bl = Tl >> 3, fl = Tl & (VG_PB - 1), b = T >> 3, f = T & (VG_PB - 1);
         double rs = 0.0, rsy = 0.0, rsyy = 0.0;
         if (fl && bl == b) {  // the whole interval lies inside one block: its cells, directly
           const float4 A = __ldg(wrow + 2 * b), B = __ldg(wrow + 2 * b + 1);
@@ -318,6 +332,7 @@ __global__ void __launch_bounds__(VG_PART_THREADS, SUM ? 6 : 1) k_vg_partition(V
           double *acc = &L.wacc[warp][sl][0];
           acc[0] += tot.m, acc[1] += tot.sx, acc[2] += tot.sy, acc[3] += tot.s2;
         }
+        __syncwarp();  // the next leader (another lane) may add to the same accumulator
         todo &= ~__ballot_sync(0xffffffffu, mine);
       }
     }
