@@ -152,6 +152,23 @@ __device__ __forceinline__ void vg_add8(float4 a, float4 b, unsigned keep, doubl
   vg_add4(b, y0 + 4.0, rs, rsy, rsyy);
 }
 
+// 256-bit read-only loads (sm_100: LDG.E.256): a prefix entry is one of these plus a 128-bit load, a map sector one
+struct VgEntry {
+  DD s, sy, syy;
+};
+__device__ __forceinline__ VgEntry vg_entry_load(const VgPfx *p) {
+  VgEntry e;
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(e.s.hi), "=d"(e.s.lo), "=d"(e.sy.hi), "=d"(e.sy.lo) : "l"(p));
+  const double2 t = __ldg(reinterpret_cast<const double2 *>(p) + 2);
+  e.syy.hi = t.x, e.syy.lo = t.y;
+  return e;
+}
+__device__ __forceinline__ void vg_sector_load(const float *p, float4 &a, float4 &b) {  // 8 floats, 32-byte aligned
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+
 // E[b + 1] from E[b] and the eight cells of block b: THE step of the sequential scan (k_vg_prefix); the partition
 // kernel repeats it to get the entry after a boundary without a second look-up, bit for bit
 __device__ __forceinline__ void vg_pfx_step(DD &s, DD &sy, DD &syy, float4 a, float4 b, int blk) {
@@ -300,23 +317,21 @@ __global__ void __launch_bounds__(VG_PART_THREADS, SUM ? 6 : 1) k_vg_partition(V
         const int bl = Tl >> 3, fl = Tl & (VG_PB - 1), b = T >> 3, f = T & (VG_PB - 1);
         double rs = 0.0, rsy = 0.0, rsyy = 0.0;
         if (fl && bl == b) {  // the whole interval lies inside one block: its cells, directly
-          const float4 A = __ldg(wrow + 2 * b), B = __ldg(wrow + 2 * b + 1);
+          float4 A, B;
+          vg_sector_load(reinterpret_cast<const float *>(wrow + 2 * b), A, B);
           vg_add8(A, B, ((1u << f) - 1u) & ~((1u << fl) - 1u), (double)(VG_PB * b) + 0.5, rs, rsy, rsyy);
         } else {
           // every load of the item first: the entries at the block edges just inside the interval -- at or after Tl,
-          // at or before T -- and the (at most) two map sectors the boundaries cut
-          const int blo = bl + (fl ? 1 : 0);
-          const double2 *el = reinterpret_cast<const double2 *>(prow + blo), *er = reinterpret_cast<const double2 *>(prow + b);
-          const double2 l0 = __ldg(el), l1 = __ldg(el + 1), l2 = __ldg(el + 2);
-          const double2 r0 = __ldg(er), r1 = __ldg(er + 1), r2 = __ldg(er + 2);
+          // at or before T -- and the (at most) two map sectors the boundaries cut; six requests in all
+          const VgEntry el = vg_entry_load(prow + bl + (fl ? 1 : 0)), er = vg_entry_load(prow + b);
           float4 LA = make_float4(0.f, 0.f, 0.f, 0.f), LB = LA, RA = LA, RB = LA;
-          if (fl) LA = __ldg(wrow + 2 * bl), LB = __ldg(wrow + 2 * bl + 1);
-          if (f) RA = __ldg(wrow + 2 * b), RB = __ldg(wrow + 2 * b + 1);
+          if (fl) vg_sector_load(reinterpret_cast<const float *>(wrow + 2 * bl), LA, LB);
+          if (f) vg_sector_load(reinterpret_cast<const float *>(wrow + 2 * b), RA, RB);
           if (fl) vg_add8(LA, LB, 0xffu & ~((1u << fl) - 1u), (double)(VG_PB * bl) + 0.5, rs, rsy, rsyy);  // head: [Tl, 8 bl + 8)
           if (f) vg_add8(RA, RB, (1u << f) - 1u, (double)(VG_PB * b) + 0.5, rs, rsy, rsyy);                 // tail: [8 b, T)
-          rs += dd_diff(DD{r0.x, r0.y}, DD{l0.x, l0.y});
-          rsy += dd_diff(DD{r1.x, r1.y}, DD{l1.x, l1.y});
-          rsyy += dd_diff(DD{r2.x, r2.y}, DD{l2.x, l2.y});
+          rs += dd_diff(er.s, el.s);
+          rsy += dd_diff(er.sy, el.sy);
+          rsyy += dd_diff(er.syy, el.syy);
         }
         const double x = (double)row + 0.5;
         vm = rs, vsx = x * rs, vsy = rsy, vs2 = fma(x * x, rs, rsyy);
