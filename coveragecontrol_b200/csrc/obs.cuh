@@ -580,6 +580,19 @@ __device__ __forceinline__ unsigned ob_range(int lo, int hi, int c0, int n) {
   return ((1u << b) - 1u) & ~((1u << a) - 1u);
 }
 
+// per-cell rule on a row a bisector runs along (rare: kept out of line, the item loop is instantiated four times)
+__device__ __noinline__ unsigned ob_exact_rule(double res, int row, int c0, unsigned ob, int K, const double *s_px, const double *s_py) {
+  unsigned todo = ob;
+  while (todo) {
+    const int bit = __ffs(todo) - 1;
+    todo &= todo - 1;
+    bool lost = false;
+    for (int k = 1; k <= K && !lost; ++k) lost = vw_beats(res, row, c0 + bit, s_px[k], s_py[k], s_px[0], s_py[0]);
+    if (lost) ob &= ~(1u << bit);
+  }
+  return ob;
+}
+
 // items of one chunk; rbase = window row of the chunk's row 0, [own0, own1) = window rows whose moments this chunk adds
 template <int S, bool VOR, bool DENSE>
 __device__ __forceinline__ void ob_items(const EnvDev &d, ObsShared &sh, const float *__restrict__ world, const Window &w,
@@ -631,16 +644,7 @@ __device__ __forceinline__ void ob_items(const EnvDev &d, ObsShared &sh, const f
       const int c0 = w.oy + 8 * oy;
       unsigned ob = ob_range(sh.lo[a], sh.hi[a], c0, 8) & ((DENSE ? inm : vis) >> (S + 4)) & 0xffu;
       if (ob != 0u) {
-        if ((sh.exact[a >> 5] >> (a & 31)) & 1u) {  // per-cell rule on this row (a bisector runs along it)
-          unsigned todo = ob;
-          while (todo) {
-            const int bit = __ffs(todo) - 1;
-            todo &= todo - 1;
-            bool lost = false;
-            for (int k = 1; k <= sh.K && !lost; ++k) lost = vw_beats(d.res, row, c0 + bit, s_px[k], s_py[k], s_px[0], s_py[0]);
-            if (lost) ob &= ~(1u << bit);
-          }
-        }
+        if ((sh.exact[a >> 5] >> (a & 31)) & 1u) ob = ob_exact_rule(d.res, row, c0, ob, sh.K, s_px, s_py);
         // (s, t, u) = sum (1, q, q^2) v_q over the group's own cells: pairwise trees, three short dependency chains
         double dv[8];
 #pragma unroll
