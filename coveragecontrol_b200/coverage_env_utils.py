@@ -56,6 +56,8 @@ def _host_comm_maps(env, params: Parameters, map_size: int) -> torch.Tensor:
         idx = torch.round(rel * map_size / (params.pCommunicationRange * params.pResolution * 2.0)
                           + (map_size / 2.0 - params.pResolution / 2.0)).t().long()
         val = rel / params.pCommunicationRange
+        ok = ((idx >= 0) & (idx < map_size)).all(0)  # (an index past the map -- pResolution < 1 -- is dropped, as the kernel does)
+        idx, val = idx[:, ok], val[ok]
         for ch in range(2):
             out[r][ch] = torch.sparse_coo_tensor(idx, val[:, ch], torch.Size([map_size, map_size])).to_dense()
     return out

@@ -71,6 +71,11 @@ def _comm_maps_torch(rel, C, comm_range, res):
     scaled = torch.round(neighbors_pos * C / (comm_range * res * 2.0) + (C / 2.0 - res / 2.0))
     idx = torch.transpose(scaled, 1, 0).long()
     val = neighbors_pos / comm_range
+    # pResolution < 1 pushes the index of a far neighbour past the map; torch's unchecked sparse -> dense conversion
+    # then writes at the wrapped linear offset (or past the buffer): undefined behaviour the restatement and the CUDA
+    # path do not imitate -- such neighbours are dropped
+    ok = ((idx >= 0) & (idx < C)).all(0)
+    idx, val = idx[:, ok], val[ok]
     maps[0] = torch.sparse_coo_tensor(idx, val[:, 0], torch.Size([C, C])).to_dense()
     maps[1] = torch.sparse_coo_tensor(idx, val[:, 1], torch.Size([C, C])).to_dense()
     return maps.numpy()
