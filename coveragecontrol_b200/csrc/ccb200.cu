@@ -2056,13 +2056,20 @@ static int d2h_doubles(ccb_env *env, const double *dev, double *out, size_t n) {
 
 extern "C" int ccb_ctrl_get_actions(ccb_ctrl *c, double *out) {
   CCB_CUDA(cudaSetDevice(c->env->device));
-  if (d2h_doubles(c->env, c->d_actions, out, (size_t)c->env->E * c->env->R * 2)) return 1;
-  if (c->kind == CCB_DECENTRALIZED) {
+  ccb_env *env = c->env;
+  const size_t n = (size_t)env->E * env->R * 2;
+  const bool dec = c->kind == CCB_DECENTRALIZED;
+  // the actions and (DecentralizedCVT) the environments' status words in ONE round trip
+  if (n * sizeof(double) + (dec ? sizeof(int) * env->E : 0) > env->h_pin_bytes) return fail("staging buffer too small");
+  CCB_CUDA(cudaMemcpyAsync(env->h_pin, c->d_actions, n * sizeof(double), cudaMemcpyDeviceToHost, env->stream));
+  int *h_status = reinterpret_cast<int *>(env->h_pin + n);
+  if (dec) CCB_CUDA(cudaMemcpyAsync(h_status, env->d.status, sizeof(int) * env->E, cudaMemcpyDeviceToHost, env->stream));
+  CCB_CUDA(cudaStreamSynchronize(env->stream));
+  memcpy(out, env->h_pin, n * sizeof(double));
+  if (dec) {
     // surface the reference's "Goal out of bounds" exception (decentralized_cvt.h:127-141)
-    std::vector<int> st(c->env->E);
-    CCB_CUDA(cudaMemcpy(st.data(), c->env->d.status, sizeof(int) * c->env->E, cudaMemcpyDeviceToHost));
-    for (int e = 0; e < c->env->E; ++e)
-      if (st[e] & 1) {
+    for (int e = 0; e < env->E; ++e)
+      if (h_status[e] & 1) {
         fail("Goal out of bounds: this should not have happened for convex environments");
         return 2;
       }

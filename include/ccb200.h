@@ -113,8 +113,10 @@ int ccb_env_set_world_dev(ccb_env *env, int e, const float *map_dev);
 int ccb_env_reset(ccb_env *env, const double *positions);
 /* the same for ONE environment of the batch (a fresh episode in slot e; set its world map first) */
 int ccb_env_reset_env(ccb_env *env, int e, const double *positions /* R x 2 */);
-/* coverage_system.h:279-291 StepActions; actions = E x R x 2.  Returns 0, or 1 when a
- * control is invalid (the reference's `true`): bad_env receives the first such env. */
+/* coverage_system.h:279-291 StepActions; actions = E x R x 2.  The reference splits an action into (direction,
+ * speed = |action|) and StepControl rejects speed < 0 or a zero direction with speed > 0 (robot_model.h:208-216):
+ * neither can happen for an action vector, so the batch call never reports an invalid control -- it returns 0 (or 1
+ * with ccb_last_error for a CUDA failure) and leaves *bad_env = -1.  ccb_env_step_control keeps the check. */
 int ccb_env_step_actions(ccb_env *env, const double *actions, int *bad_env);
 /* coverage_system.h:303-333 StepAction / StepControl (single robot of env e) */
 int ccb_env_step_control(ccb_env *env, int e, int robot, double dir_x, double dir_y, double speed);

@@ -118,9 +118,9 @@ def test_banded_system_step_equals_plain_rollout(kind, graph):
 
 
 def test_multi_gpu_row_bands_and_robot_shards():
-    """scripts/multigpu_check.py under torchrun on 2 GPUs (skipped on a 1-GPU box; profiles/ holds the logs of the
-    2- and 8-GPU runs): banded IDF bit-identical, the three controllers eager and graph-captured with the NCCL all-reduce
-    inside the graph, replicas identical across ranks."""
+    """scripts/multigpu_check.py under torchrun on the GPUs of the box, two ranks where two are visible, else one
+    (profiles/ holds the logs of the 2- and 8-GPU runs): banded IDF bit-identical, the three controllers eager and
+    graph-captured with the NCCL all-reduce inside the graph, replicas identical across ranks."""
     import os
     import subprocess
     import sys
@@ -129,12 +129,11 @@ def test_multi_gpu_row_bands_and_robot_shards():
 
     from conftest import ROOT
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    ranks = 2 if torch.cuda.device_count() >= 2 else 1
     env = dict(os.environ, CHECK_N="1024")
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(ranks),
                           "--master-addr", "127.0.0.1", "--master-port", "29533",
-                          os.path.join(ROOT, "scripts", "multigpu_check.py")], capture_output=True, text=True, env=env, timeout=600)
+                          os.path.join(ROOT, "scripts", "multigpu_check.py")], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and "multigpu_check ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
