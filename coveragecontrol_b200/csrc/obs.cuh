@@ -809,11 +809,14 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
   __syncthreads();  // oA / oB, the row intervals
 
 #pragma unroll 1
+  bool carry = false;  // the previous chunk ran: its last 12 rows (this chunk's tap halo) are kept, not recomputed
   for (int ch = 0; ch < OB_CHUNKS; ++ch) {
     const int rbase = 64 * ch - 4;                                   // window row of chunk row 0
-    const int r0 = max(alo, rbase), r1 = min(ahi, rbase + OB_CROWS);  // window rows of this chunk that can hold a cell
+    // window rows this chunk computes (every window row is computed by exactly one chunk)
+    const int r0 = max(alo, rbase + (carry ? 12 : 0)), r1 = min(ahi, rbase + OB_CROWS);
     const int ox0 = 8 * ch;
-    if (r1 <= r0) {  // CTA-uniform: nothing seen under these 8 output rows
+    if (r1 <= r0 && !carry) {  // CTA-uniform: nothing seen under these 8 output rows
+      carry = false;
       for (int t = tid; t < 8 * 32; t += OB_THREADS) {
         const int ox = ox0 + (t >> 5);  // (t & 31 == lane: the thread's own output column)
         float *o = dst + (size_t)ox * 32 + lane;
@@ -823,9 +826,13 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
       continue;
     }
     __syncthreads();  // the previous chunk's height pass is done with tmp / need / mask
+    if (carry) {  // chunk rows 64 .. 75 of the previous chunk are rows 0 .. 11 of this one
+      for (int t = tid; t < 12 * 32; t += OB_THREADS) sh.tmp[t >> 5][t & 31] = sh.tmp[64 + (t >> 5)][t & 31];
+      if (tid < 12) sh.need[tid] = sh.need[64 + tid];
+    }
     // ---- 1. mask words of rows r0 .. r1 - 1 (chunk rows r0 - rbase ..); pad words and words outside the box are zero
     {
-      const int nrow = r1 - r0;
+      const int nrow = max(r1 - r0, 0);
       for (int t = tid; t < nrow * OB_WORDS; t += OB_THREADS) {
         const int ar = t / OB_WORDS, j = t - ar * OB_WORDS;  // j = 0 / 10: pads; 1 + wlo .. whi: loaded below
         if (j < 1 + wlo || j >= 1 + whi) sh.mask[(r0 - rbase + ar) * OB_WORDS + j] = 0u;
@@ -890,7 +897,7 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
           }
         }
       }
-      if (cr < OB_CROWS) sh.need[cr] = nd;
+      if (cr < OB_CROWS && !(carry && cr < 12)) sh.need[cr] = nd;
       // exclusive prefix sum of the item counts over the chunk's rows
       const int cnt = __popc(nd);
       int incl = cnt;
@@ -913,9 +920,9 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
       }
     }
     __syncthreads();
-    // ---- 3. items: rows 64 ch .. 64 ch + 63 also add their own-cell moments (every window row belongs to one chunk)
+    // ---- 3. items (every window row is computed, and its own-cell moments added, by exactly one chunk)
     {
-      const int own0 = 64 * ch, own1 = 64 * ch + 64;
+      const int own0 = -4, own1 = 260;
       switch (w.oy & 3) {
         case 0: ob_items<0, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, s_px, s_py, acc); break;
         case 1: ob_items<1, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, s_px, s_py, acc); break;
@@ -942,6 +949,7 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
       o[local_off] = acc_l;
       o[obst_off] = inside ? 0.f : fmaf(sh.oA[ox], cy_out, sh.oB[ox] * cy_all);
     }
+    carry = r1 > r0;  // (no new row in this chunk: everything from its row 12 on is unseen, so is the next chunk's halo)
   }
   if (VOR) {
     const Sum4 tot = reduce4(acc[0], acc[1], acc[2], acc[3] + acc[4]);
