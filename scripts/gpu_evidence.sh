@@ -1,26 +1,26 @@
 #!/bin/bash
 # Round evidence on one B200 (run under gpurun): GPU parity tests, the bench line, the ncu launch
 # list of the same bench command and one `ncu --set full` capture per hot kernel.
-#   gpurun --timeout 1500 -- 'bash scripts/gpu_evidence.sh r01'
+#   gpurun --timeout 1500 -- 'bash scripts/gpu_evidence.sh r02'
 set -u
 tag=${1:-r01}
 out=gpurun_out
 mkdir -p $out
-python -m pytest tests -m gpu -x -q > $out/pytest_$tag.log 2>&1
+timeout 600 python -m pytest tests -m gpu -x -q > $out/pytest_$tag.log 2>&1
 echo "pytest rc=$?" | tee -a $out/pytest_$tag.log
 tail -3 $out/pytest_$tag.log
-python bench.py --steps 10 --warmup 3 > $out/bench_$tag.json 2> $out/bench_$tag.err
+timeout 600 python bench.py --steps 10 --warmup 3 > $out/bench_$tag.json 2> $out/bench_$tag.err
 echo "bench rc=$?"
 # the step loop alone (no e2e arm, no per-kernel timing loops), IDF set-up launches filtered out
-python bench.py --steps 4 --warmup 3 --step-only > $out/bench_short_$tag.json 2> $out/bench_short_$tag.err &&
-ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(?!k_idf).*' -c 600 --csv --log-file $out/launches_$tag.csv \
+timeout 300 python bench.py --steps 4 --warmup 3 --step-only > $out/bench_short_$tag.json 2> $out/bench_short_$tag.err &&
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(?!k_idf).*' -c 600 --csv --log-file $out/launches_$tag.csv \
     python bench.py --steps 4 --warmup 3 --step-only > $out/ncu_launches_$tag.log 2>&1
 echo "launch list rc=$?"
 # one `ncu --set full` capture per hot kernel, 256 environments (PROFILE_ENVS of make_profile_summary.py)
 for spec in 7:k_vg_partition:part 8:k_obs_fused:obsvor 4:k_obs_fused:obs 2:k_voronoi_window:vwin 3:k_mark_windows:mark; do
   which=$(echo $spec | cut -d: -f1); kern=$(echo $spec | cut -d: -f2); name=$(echo $spec | cut -d: -f3)
-  python scripts/prof_kernels.py --which $which --envs 256 --iters 3 > $out/prof_plain_${tag}_$name.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"$kern" -s 1 -c 1 -f \
+  timeout 200 python scripts/prof_kernels.py --which $which --envs 256 --iters 3 > $out/prof_plain_${tag}_$name.log 2>&1 &&
+  timeout 400 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"$kern" -s 1 -c 1 -f \
       -o $out/prof_${tag}_$name python scripts/prof_kernels.py --which $which --envs 256 --iters 3 \
       > $out/ncu_${tag}_$name.log 2>&1
   echo "ncu $name rc=$?"
@@ -28,8 +28,8 @@ done
 # the IDF integration kernel at C1 and C4 (FP32 / XU pipe fractions)
 for spec in "c1:--world 1024 --features 32" "c4:--world 8192 --features 1024 --polygons 64"; do
   name=idf_${spec%%:*}; args=${spec#*:}
-  python scripts/prof_idf.py $args > $out/prof_plain_${tag}_$name.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_idf_generate -c 1 -f \
+  timeout 200 python scripts/prof_idf.py $args > $out/prof_plain_${tag}_$name.log 2>&1 &&
+  timeout 400 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_idf_generate -c 1 -f \
       -o $out/prof_${tag}_$name python scripts/prof_idf.py $args > $out/ncu_${tag}_$name.log 2>&1
   echo "ncu $name rc=$?"
 done
