@@ -365,13 +365,21 @@ static int idf_launch_kernel(ccb_idf *idf, const IdfInputs &in, const unsigned c
   const float trun_sq = trun * trun;                       // generate_world_map.cu:188-189
   const float one_by_sqrt2 = (float)(1. / std::sqrt(2.));  // generate_world_map.cu:190-192
   if (row1 <= row0) return 0;
-  dim3 grid((N + IDF_TY - 1) / IDF_TY, (row1 - (row0 & ~(IDF_TX - 1)) + IDF_TX - 1) / IDF_TX);
-  if (mode == 0)
-    k_idf_generate<0><<<grid, IDF_THREADS, 0, idf->stream>>>(d_b, in.F, d_bk_start, d_bk_items, in.bk_nb, in.bk_size, pd, N, row0, row1, res,
-                                                            trun_sq, one_by_sqrt2, idf->d_map, idf->d_max);
-  else
-    k_idf_generate<1><<<grid, IDF_THREADS, 0, idf->stream>>>(d_b, in.F, d_bk_start, d_bk_items, in.bk_nb, in.bk_size, pd, N, row0, row1, res,
-                                                            trun_sq, one_by_sqrt2, idf->d_map, idf->d_max);
+  const int rows_t = (row1 - (row0 & ~(IDF_TX - 1)) + IDF_TX - 1) / IDF_TX;
+  // 32 x 128 tiles once there are several waves of them (148 SMs x ~8 CTAs), 32 x 32 below that
+  const bool wide = (long)rows_t * ((N + 4 * IDF_TY - 1) / (4 * IDF_TY)) >= 4L * 148 * 8;
+  dim3 grid((N + (wide ? 4 : 1) * IDF_TY - 1) / ((wide ? 4 : 1) * IDF_TY), rows_t);
+#define CCB_IDF_LAUNCH(MODE, NTY)                                                                                              \
+  k_idf_generate<MODE, NTY><<<grid, IDF_THREADS, 0, idf->stream>>>(d_b, in.F, d_bk_start, d_bk_items, in.bk_nb, in.bk_size, pd, N, row0, \
+                                                                    row1, res, trun_sq, one_by_sqrt2, idf->d_map, idf->d_max)
+  if (mode == 0) {
+    if (wide) CCB_IDF_LAUNCH(0, 4);
+    else CCB_IDF_LAUNCH(0, 1);
+  } else {
+    if (wide) CCB_IDF_LAUNCH(1, 4);
+    else CCB_IDF_LAUNCH(1, 1);
+  }
+#undef CCB_IDF_LAUNCH
   CCB_LAUNCH_CHECK();
   return 0;
 }

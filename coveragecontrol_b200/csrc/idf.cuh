@@ -72,9 +72,12 @@ __device__ __forceinline__ float ordered_to_float(int i) {
   return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff);
 }
 
-// One CTA per IDF_TX x IDF_TY tile.  MODE 0: reference operation order.  MODE 1: separable
-// differences tabulated in fp64 (more accurate than the reference, same truncation support).
-template <int MODE>
+// One CTA per IDF_TX x (NTY IDF_TY) tile: NTY = 1 for small maps (more CTAs than SMs matters more than the fixed
+// cost per CTA), 4 for large ones (one feature cull, one set of barriers and one x-side tabulation per 32 x 128
+// cells: the C4 map took 65 536 CTAs of ~4 us each).  A thread owns 4 consecutive cells in each of the NTY sub-tiles.
+// MODE 0: reference operation order.  MODE 1: separable differences tabulated in fp64 (more accurate than the
+// reference, same truncation support).
+template <int MODE, int NTY>
 __global__ void __launch_bounds__(IDF_THREADS)
 k_idf_generate(const BndF *__restrict__ bnd, int F, const int *__restrict__ bk_start, const int *__restrict__ bk_items, int bk_nb,
                int bk_size, PolyDev poly, int N, int row0, int row1, float res, float trun_sq, float one_by_sqrt2,
@@ -85,9 +88,10 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, const int *__restrict__ bk_s
   __shared__ float s_tx[IDF_FC][IDF_TX];    // (mid.x - mu_x)/sigma_x
   __shared__ float s_axl[IDF_FC][IDF_TX];   // MODE0: scale*erfc(left x) ; MODE1: scale/4*(erfc l - erfc r)
   __shared__ float s_axr[IDF_FC][IDF_TX];   // MODE0: scale*erfc(right x)
-  __shared__ float s_ty2[IDF_FC][IDF_TY];   // ((mid.y - mu_y)/sigma_y)^2
-  __shared__ float s_eyl[IDF_FC][IDF_TY];   // MODE0: erfc(lower y)      ; MODE1: erfc l - erfc r
-  __shared__ float s_eyr[IDF_FC][IDF_TY];   // MODE0: erfc(upper y)
+  constexpr int TYW = IDF_TY * NTY;         // columns of the CTA's tile
+  __shared__ float s_ty2[IDF_FC][TYW];      // ((mid.y - mu_y)/sigma_y)^2
+  __shared__ float s_eyl[IDF_FC][TYW];      // MODE0: erfc(lower y)      ; MODE1: erfc l - erfc r
+  __shared__ float s_eyr[IDF_FC][MODE == 0 ? TYW : 1];  // MODE0: erfc(upper y)
   __shared__ int s_poly[IDF_MAXPOLY];
   __shared__ int s_npoly;
   __shared__ float s_red[IDF_THREADS / 32];
@@ -95,15 +99,17 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, const int *__restrict__ bk_s
   const int tid = threadIdx.x;
   // rows [row0, row1): the whole map or a row band.  Tiles sit on the global 32-row grid whatever row0 is, so a tile
   // never straddles two feature buckets (bk_size is a multiple of IDF_TX); rows below row0 are computed and dropped
-  const int x0 = (row0 & ~(IDF_TX - 1)) + blockIdx.y * IDF_TX, y0 = blockIdx.x * IDF_TY;
+  const int x0 = (row0 & ~(IDF_TX - 1)) + blockIdx.y * IDF_TX, y0 = blockIdx.x * TYW;
   const int lrow = tid >> 3, lcol = (tid & 7) * 4;
   const int gx = x0 + lrow, gy = y0 + lcol;
 
   // tile extent of the cell mid points, used for conservative culling
   const float tile_xlo = max(x0, row0) * res, tile_xhi = (min(x0 + IDF_TX, row1)) * res;
-  const float tile_ylo = y0 * res, tile_yhi = (min(y0 + IDF_TY, N)) * res;
+  const float tile_ylo = y0 * res, tile_yhi = (min(y0 + TYW, N)) * res;
 
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[NTY][4];
+#pragma unroll
+  for (int u = 0; u < NTY; ++u) acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f;
 
   // The host sorted the features into a coarse grid of bk_size x bk_size-cell buckets (ascending feature
   // index inside a bucket): the tile only scans the features whose truncation box touches its bucket.
@@ -157,9 +163,9 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, const int *__restrict__ bk_s
     __syncthreads();
     const int nl = s_nlist;
     // ---- tabulate the 1-D factors ------------------------------------------------------------
-    for (int t = tid; t < nl * (IDF_TX + IDF_TY); t += IDF_THREADS) {
-      int k = t / (IDF_TX + IDF_TY);
-      int u = t - k * (IDF_TX + IDF_TY);
+    for (int t = tid; t < nl * (IDF_TX + TYW); t += IDF_THREADS) {
+      int k = t / (IDF_TX + TYW);
+      int u = t - k * (IDF_TX + TYW);
       BndF b = bnd[s_list[k]];
       bool is_x = u < IDF_TX;
       int li = is_x ? u : u - IDF_TX;
@@ -203,19 +209,23 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, const int *__restrict__ bk_s
     for (int k = 0; k < nl; ++k) {
       float tx = s_tx[k][lrow];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float r2 = fmaf(tx, tx, s_ty2[k][lcol + c]);  // generate_world_map.cu:113 as compiled
-        if (r2 > trun_sq) continue;
-        if (MODE == 0) {
-          float axl = s_axl[k][lrow], axr = s_axr[k][lrow];
-          float eyl = s_eyl[k][lcol + c], eyr = s_eyr[k][lcol + c];
-          // generate_world_map.cu:116-119: +Q(bl) -Q(br) -Q(tl) +Q(tr), Q = (sc*ex)*ey/4
-          acc[c] = fmaf(__fmul_rn(axl, eyl), 0.25f, acc[c]);
-          acc[c] = fmaf(__fmul_rn(axr, eyl), -0.25f, acc[c]);
-          acc[c] = fmaf(__fmul_rn(axl, eyr), -0.25f, acc[c]);
-          acc[c] = fmaf(__fmul_rn(axr, eyr), 0.25f, acc[c]);
-        } else {
-          acc[c] = fmaf(s_axl[k][lrow], s_eyl[k][lcol + c], acc[c]);
+      for (int u = 0; u < NTY; ++u) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int yc = IDF_TY * u + lcol + c;
+          float r2 = fmaf(tx, tx, s_ty2[k][yc]);  // generate_world_map.cu:113 as compiled
+          if (r2 > trun_sq) continue;
+          if (MODE == 0) {
+            float axl = s_axl[k][lrow], axr = s_axr[k][lrow];
+            float eyl = s_eyl[k][yc], eyr = s_eyr[k][yc];
+            // generate_world_map.cu:116-119: +Q(bl) -Q(br) -Q(tl) +Q(tr), Q = (sc*ex)*ey/4
+            acc[u][c] = fmaf(__fmul_rn(axl, eyl), 0.25f, acc[u][c]);
+            acc[u][c] = fmaf(__fmul_rn(axr, eyl), -0.25f, acc[u][c]);
+            acc[u][c] = fmaf(__fmul_rn(axl, eyr), -0.25f, acc[u][c]);
+            acc[u][c] = fmaf(__fmul_rn(axr, eyr), 0.25f, acc[u][c]);
+          } else {
+            acc[u][c] = fmaf(s_axl[k][lrow], s_eyl[k][yc], acc[u][c]);
+          }
         }
       }
     }
@@ -242,22 +252,26 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, const int *__restrict__ bk_s
     const int np = s_npoly;
     if (np > 0 && gx >= row0 && gx < row1) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (gy + c >= N) continue;
-        float fx = (float)gx, fy = (float)(gy + c);
-        float midx = __fmul_rn(fmaf(fx, res, fmaf(fx, res, res)), 0.5f);
-        float midy = __fmul_rn(fmaf(fy, res, fmaf(fy, res, res)), 0.5f);
-        float pim = 0.f;
-        int cnt = np <= IDF_MAXPOLY ? np : pk1 - pk0;
-        for (int q = 0; q < cnt; ++q) {
-          int k = np <= IDF_MAXPOLY ? s_poly[q] : poly.bk_items[pk0 + q];
-          float4 b = poly.bounds[k];
-          if (midx < b.x || midx > b.y || midy < b.z || midy > b.w) continue;
-          int st = poly.start[k];
-          if (idf_point_in_piece(poly.x + st, poly.y + st, poly.sz[k], midx, midy))
-            pim = fmaxf(pim, poly.imp[k]);
+      for (int u = 0; u < NTY; ++u) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int gyc = gy + IDF_TY * u + c;
+          if (gyc >= N) continue;
+          float fx = (float)gx, fy = (float)gyc;
+          float midx = __fmul_rn(fmaf(fx, res, fmaf(fx, res, res)), 0.5f);
+          float midy = __fmul_rn(fmaf(fy, res, fmaf(fy, res, res)), 0.5f);
+          float pim = 0.f;
+          int cnt = np <= IDF_MAXPOLY ? np : pk1 - pk0;
+          for (int q = 0; q < cnt; ++q) {
+            int k = np <= IDF_MAXPOLY ? s_poly[q] : poly.bk_items[pk0 + q];
+            float4 b = poly.bounds[k];
+            if (midx < b.x || midx > b.y || midy < b.z || midy > b.w) continue;
+            int st = poly.start[k];
+            if (idf_point_in_piece(poly.x + st, poly.y + st, poly.sz[k], midx, midy))
+              pim = fmaxf(pim, poly.imp[k]);
+          }
+          acc[u][c] = __fadd_rn(acc[u][c], pim);  // generate_world_map.cu:161-163
         }
-        acc[c] = __fadd_rn(acc[c], pim);  // generate_world_map.cu:161-163
       }
     }
   }
@@ -266,16 +280,20 @@ k_idf_generate(const BndF *__restrict__ bnd, int F, const int *__restrict__ bk_s
   float vmax = -INFINITY;
   if (gx >= row0 && gx < row1) {
     float *row = out + (size_t)gx * N;
-    if ((N & 3) == 0 && gy + 3 < N) {
-      *reinterpret_cast<float4 *>(row + gy) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      vmax = fmaxf(fmaxf(acc[0], acc[1]), fmaxf(acc[2], acc[3]));
-    } else {
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (gy + c < N) {
-          row[gy + c] = acc[c];
-          vmax = fmaxf(vmax, acc[c]);
-        }
+    for (int u = 0; u < NTY; ++u) {
+      const int gyu = gy + IDF_TY * u;
+      if ((N & 3) == 0 && gyu + 3 < N) {
+        *reinterpret_cast<float4 *>(row + gyu) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+        vmax = fmaxf(vmax, fmaxf(fmaxf(acc[u][0], acc[u][1]), fmaxf(acc[u][2], acc[u][3])));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (gyu + c < N) {
+            row[gyu + c] = acc[u][c];
+            vmax = fmaxf(vmax, acc[u][c]);
+          }
+      }
     }
   }
 #pragma unroll
