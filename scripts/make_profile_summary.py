@@ -47,14 +47,14 @@ if os.path.exists(lpath):
         name = r[ki].split("(")[0]
         if name.startswith("void "):
             name = name[5:]
-        if "k_idf" in name:
-            continue  # world generation is set-up, not part of the step
+        if "k_idf" in name or "k_vg_prefix" in name or "k_init_positions" in name:
+            continue  # world generation, its prefix sums and the reset are set-up, not part of the step
         agg[name][0] += 1
         agg[name][1] += float(r[vi].replace(",", ""))
     tot = sum(v[1] for v in agg.values()) or 1.0
     out.append("## ncu launch list of `bench.py --steps 4 --warmup 3 --step-only` (the bench's step loop alone)\n")
     out.append("Per-launch times under ncu are cold-cache and serialised: compare shares, not absolutes. "
-               "IDF generation launches (environment set-up) are left out of the shares.\n")
+               "Set-up launches (IDF generation, `k_vg_prefix` -- 4.8 ms once per world set for 1024 environments --, the reset) are left out of the shares.\n")
     out.append("| kernel | launches | total us | share |\n|---|---:|---:|---:|")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append(f"| `{k}` | {n} | {t / 1e3:.1f} | {100 * t / tot:.1f}% |")
