@@ -252,9 +252,23 @@ def idf_extras(ccb, lib, p, device, clocks):
         sig = float(np.mean(bnd[:, 2]))
         p_in = min(1.0, math.pi * (q.pTruncationBND * sig) ** 2 / (n * n))
         flops = n * n * (8.0 * len(bnd) + 16.0 * len(bnd) * p_in + 2.0)
-        r = {"kernel_ms": ms.value, "survey_flops": flops, "achieved_tflops": flops / (ms.value * 1e-3) / 1e12,
-             "frac_of_measured_fp32_peak": flops / (ms.value * 1e-3) / 1e12 / peak.value,
-             "map_write_gbs": 4.0 * n * n / (ms.value * 1e-3) / 1e9}
+        # what the kernel actually evaluates after the tile cull and the 1-D tabulation: 2 flops (truncation test) per
+        # (cell, feature) pair whose feature survives the cull of the cell's 32 x 32 tile, 8 more when inside the
+        # truncation ellipse (4 products + 4 FMAs of tabulated factors), 2 x 33 erfcf per (tile, feature)
+        tsig = q.pTruncationBND * bnd[:, 2]
+        pairs_in = float(np.sum(np.minimum(math.pi * tsig * tsig, n * n)))
+        pairs_tested = float(np.sum(np.minimum((2 * tsig + 64.0) ** 2, n * n)))
+        useful = 8.0 * pairs_in + 2.0 * pairs_tested + 2.0 * n * n
+        hbm, _ = measured_peak_gbs()
+        r = {"kernel_ms": ms.value, "map_write_gbs": 4.0 * n * n / (ms.value * 1e-3) / 1e9,
+             "frac_of_hbm_write_floor": (4.0 * n * n / (hbm * 1e9)) / (ms.value * 1e-3),
+             "useful_flops": useful, "useful_tflops": useful / (ms.value * 1e-3) / 1e12,
+             "useful_frac_of_measured_fp32_peak": useful / (ms.value * 1e-3) / 1e12 / peak.value,
+             "survey_flops": flops, "survey_formula_tflops": flops / (ms.value * 1e-3) / 1e12,
+             "survey_formula_frac_of_fp32_peak": flops / (ms.value * 1e-3) / 1e12 / peak.value,
+             "note": ("survey_flops = SURVEY 8(d): 8 N^2 F + ... counts every (cell, feature) pair, which is what the reference's "
+                      "kernel evaluates; this kernel culls features per tile, so the formula over-counts its work (a fraction above "
+                      "1 measures work avoided); useful_flops / the HBM write floor are the physical bounds")}
         t = []
         for _ in range(4):
             torch.cuda.synchronize()
