@@ -37,15 +37,28 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: coveragecontrol_b200 needs the CUDA toolkit to build")
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
+HASH = LIB + ".srchash"
+
+
+def _source_hash() -> str:
+    """sha256 over every file the library is built from and the flags: staleness by CONTENT, not by mtime (a copied
+    tree -- the GPU box gets a snapshot -- need not keep the order of modification times)."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
-    deps.append(os.path.join(_HERE, "..", "include", "ccb200.h"))
-    deps.append(os.path.join(_HERE, "..", "include", "ccb200_test.h"))
-    deps.append(os.path.abspath(__file__))
-    return any(os.path.getmtime(d) > t for d in deps)
+    deps += [os.path.join(_HERE, "..", "include", "ccb200.h"), os.path.join(_HERE, "..", "include", "ccb200_test.h")]
+    for d in deps:
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB) or not os.path.exists(HASH):
+        return True
+    with open(HASH) as f:
+        return f.read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -70,6 +83,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     os.remove(tmp)
                 raise RuntimeError("nvcc failed:\n" + log)
             os.replace(tmp, LIB)  # atomic: a concurrent dlopen sees the old or the new file, never a partial one
+            with open(HASH, "w") as f:
+                f.write(_source_hash() + "\n")
             if verbose:
                 print(log)
         finally:
