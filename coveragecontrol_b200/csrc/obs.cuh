@@ -568,7 +568,7 @@ struct ObsShared {
   int lo[256], hi[256];                 // VOR: own-cell interval of every window row, map columns
   uint32_t exact[8];                    // VOR: rows that need the per-cell rule
   int wtot[OB_WARPS];
-  int total, nfull;
+  int total;
   int K;
   double red[OB_WARPS][4];
 };
@@ -594,38 +594,30 @@ __device__ __noinline__ unsigned ob_exact_rule(double res, int row, int c0, unsi
 }
 
 // items of one chunk; rbase = window row of the chunk's row 0, [own0, own1) = window rows whose moments this chunk adds
-// FULL: the items [begin, end) have all 16 taps seen (and are interior output columns): unconditional loads, no
-// per-tap selects, the interior weights; same 16 products in the same order, so the same bits as the general path
-template <int S, bool VOR, bool DENSE, bool FULL>
+template <int S, bool VOR, bool DENSE>
 __device__ __forceinline__ void ob_items(const EnvDev &d, ObsShared &sh, const float *__restrict__ world, const Window &w,
-                                         int off0, int rbase, int begin, int end, int amap0, int amap1, int cy0, int cy1,
+                                         int off0, int rbase, int own0, int own1, int amap0, int amap1, int cy0, int cy1,
                                          const double *s_px, const double *s_py, double (&acc)[5]) {
   constexpr int NV = S == 0 ? 4 : 5;  // aligned 4-cell groups under the 16 taps
+  const int total = sh.total;
   const float fill = d.fill;
 #pragma unroll 1
-  for (int i = begin + threadIdx.x; i < end; i += OB_THREADS) {
+  for (int i = threadIdx.x; i < total; i += OB_THREADS) {
     const int it = sh.items[i];
     const int cr = it >> 5, oy = it & 31;         // chunk row, output column
     const int a = rbase + cr, row = w.ox + a;
     const int gyb = w.oy + 8 * oy - 4 - S;        // 16-byte aligned map column of the first group
     const int pos = off0 + 8 * oy - 4 - S + 32;   // its bit in the row's 11 mask words
-    unsigned vis = 0xffffu << S;  // FULL: the 16 taps are seen (the cells of the end groups beyond them are not used)
+    const uint32_t *m = sh.mask + cr * OB_WORDS + (pos >> 5);
+    const unsigned vis = __funnelshift_r(m[0], m[1], pos & 31) & ((1u << (4 * NV)) - 1u);
     float4 v[NV];
-    if (FULL) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d.use_sensor) {
       const float4 *src = reinterpret_cast<const float4 *>(world + (size_t)row * d.N + gyb);
 #pragma unroll
-      for (int j = 0; j < NV; ++j) v[j] = __ldcs(src + j);
-    } else {
-      const uint32_t *m = sh.mask + cr * OB_WORDS + (pos >> 5);
-      vis = __funnelshift_r(m[0], m[1], pos & 31) & ((1u << (4 * NV)) - 1u);
-#pragma unroll
-      for (int j = 0; j < NV; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (d.use_sensor) {
-        const float4 *src = reinterpret_cast<const float4 *>(world + (size_t)row * d.N + gyb);
-#pragma unroll
-        for (int j = 0; j < NV; ++j)
-          if ((vis >> (4 * j)) & 0xfu) v[j] = __ldcs(src + j);  // a set bit is an in-map cell: the whole aligned group is
-      }
+      for (int j = 0; j < NV; ++j)
+        if ((vis >> (4 * j)) & 0xfu) v[j] = __ldcs(src + j);  // a set bit is an in-map cell: the whole aligned group is
     }
     float x[4 * NV];
 #pragma unroll
@@ -635,15 +627,11 @@ __device__ __forceinline__ void ob_items(const EnvDev &d, ObsShared &sh, const f
     float c[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
-      if (FULL) {
-        c[q] = x[S + q];
-      } else {
-        const float unseen = (DENSE && ((inm >> (S + q)) & 1u)) ? fill : 0.f;
-        c[q] = ((vis >> (S + q)) & 1u) ? x[S + q] : unseen;
-      }
+      const float unseen = (DENSE && ((inm >> (S + q)) & 1u)) ? fill : 0.f;
+      c[q] = ((vis >> (S + q)) & 1u) ? x[S + q] : unseen;
     }
     float t = 0.f;
-    if (FULL || (oy != 0 && oy != 31)) {
+    if (oy != 0 && oy != 31) {
 #pragma unroll
       for (int q = 0; q < 16; ++q) t = fmaf(c_ob_w[q], c[q], t);
     } else {  // the two border columns: torch truncates and renormalises their taps
@@ -651,7 +639,7 @@ __device__ __forceinline__ void ob_items(const EnvDev &d, ObsShared &sh, const f
       for (int q = 0; q < 16; ++q) t = fmaf(sh.w[oy][q], c[q], t);
     }
     sh.tmp[cr][oy] = t;
-    if (VOR) {
+    if (VOR && a >= own0 && a < own1) {
       // the item's own column group (taps 4 .. 11 = window columns 8 oy .. 8 oy + 7) inside the robot's cell
       const int c0 = w.oy + 8 * oy;
       unsigned ob = ob_range(sh.lo[a], sh.hi[a], c0, 8) & ((DENSE ? inm : vis) >> (S + 4)) & 0xffu;
@@ -880,7 +868,7 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
     // ---- 2. which outputs of a row are non-zero; item list (thread <-> chunk row) ---------------------------
     {
       const int cr = tid, a = rbase + cr;
-      uint32_t nd = 0u, ndf = 0u;  // outputs with a seen tap / with all 16 taps seen
+      uint32_t nd = 0u;
       if (cr < OB_CROWS && a >= r0 && a < r1) {
         if (DENSE) {
           // every output whose 16 taps touch an in-map column of this in-map row
@@ -888,37 +876,30 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
             if (ob_range(cy0, cy1, w.oy + 8 * oy - 4, 16)) nd |= 1u << oy;
         } else {
           const uint32_t *mrow = sh.mask + cr * OB_WORDS + 1;
-          uint32_t tprev = 0u, tcur, tnext, fprev = 0u, fcur, fnext;
+          uint32_t tprev = 0u, tcur, tnext;
           {
             const uint32_t x0 = __funnelshift_r(mrow[0], mrow[1], off0);
-            uint32_t t = x0 | (x0 >> 1), f = x0 & (x0 >> 1);
+            uint32_t t = x0 | (x0 >> 1);
             tcur = (t | (t >> 2)) & 0x11111111u;  // bit 4 n: nibble n (4 window columns) holds a seen cell
-            fcur = (f & (f >> 2)) & 0x11111111u;  // bit 4 n: all four cells of nibble n are seen
           }
 #pragma unroll
           for (int mI = 0; mI < 8; ++mI) {
-            tnext = fnext = 0u;
+            tnext = 0u;
             if (mI < 7) {
               const uint32_t x1 = __funnelshift_r(mrow[mI + 1], mrow[mI + 2], off0);
-              uint32_t t = x1 | (x1 >> 1), f = x1 & (x1 >> 1);
+              uint32_t t = x1 | (x1 >> 1);
               tnext = (t | (t >> 2)) & 0x11111111u;
-              fnext = (f & (f >> 2)) & 0x11111111u;
             }
             // output 4 mI + g reads nibbles 2 g - 1 .. 2 g + 2 of this word (and of its neighbours at the ends)
             const uint32_t u = tcur | (tcur >> 4) | (tcur << 4) | (tcur >> 8) | (tprev >> 28) | (tnext << 24);
             nd |= ((((u & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << (4 * mI);
-            const uint32_t uf = fcur & (fcur >> 4) & ((fcur << 4) | (fprev >> 28)) & ((fcur >> 8) | (fnext << 24));
-            ndf |= ((((uf & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << (4 * mI);
-            tprev = tcur, tcur = tnext, fprev = fcur, fcur = fnext;
+            tprev = tcur, tcur = tnext;
           }
-          if (!d.use_sensor) ndf = 0u;  // (no map values to load: the general path writes the zeros)
         }
       }
       if (cr < OB_CROWS && !(carry && cr < 12)) sh.need[cr] = nd;
-      // exclusive prefix sums of the two item counts over the chunk's rows, packed (full | other << 16): the full
-      // items are listed first, so that the warps of either loop are homogeneous
-      const uint32_t nde = nd & ~ndf;
-      const int cnt = __popc(ndf) | (__popc(nde) << 16);
+      // exclusive prefix sum of the item counts over the chunk's rows
+      const int cnt = __popc(nd);
       int incl = cnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -927,31 +908,27 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
       }
       if (lane == 31) sh.wtot[warp] = incl;
       __syncthreads();
-      int before = 0, all = 0;
+      int before = 0;
 #pragma unroll
-      for (int k = 0; k < OB_WARPS; ++k) before += k < warp ? sh.wtot[k] : 0, all += sh.wtot[k];
-      const int excl = before + incl - cnt, nfull = all & 0xffff;
-      if (tid == 0) sh.nfull = nfull, sh.total = nfull + (all >> 16);
-      int off = excl & 0xffff;
-      for (uint32_t b = ndf; b; b &= b - 1) sh.items[off++] = (unsigned short)((cr << 5) | (__ffs(b) - 1));
-      off = nfull + (excl >> 16);
-      for (uint32_t b = nde; b; b &= b - 1) sh.items[off++] = (unsigned short)((cr << 5) | (__ffs(b) - 1));
+      for (int k = 0; k < OB_WARPS; ++k) before += k < warp ? sh.wtot[k] : 0;
+      int off = before + incl - cnt;
+      if (tid == OB_THREADS - 1) sh.total = off + cnt;
+      while (nd) {
+        const int oy = __ffs(nd) - 1;
+        nd &= nd - 1;
+        sh.items[off++] = (unsigned short)((cr << 5) | oy);
+      }
     }
     __syncthreads();
-    // ---- 3. items (every window row is computed, and its own-cell moments added, by exactly one chunk): first those
-    //         with all 16 taps seen, then the rest
+    // ---- 3. items (every window row is computed, and its own-cell moments added, by exactly one chunk)
     {
-      const int nfull = sh.nfull, total = sh.total;
-#define CCB_OB_ITEMS(SS)                                                                                                        \
-  ob_items<SS, VOR, DENSE, true>(d, sh, world, w, off0, rbase, 0, nfull, amap0, amap1, cy0, cy1, s_px, s_py, acc);              \
-  ob_items<SS, VOR, DENSE, false>(d, sh, world, w, off0, rbase, nfull, total, amap0, amap1, cy0, cy1, s_px, s_py, acc)
+      const int own0 = -4, own1 = 260;
       switch (w.oy & 3) {
-        case 0: CCB_OB_ITEMS(0); break;
-        case 1: CCB_OB_ITEMS(1); break;
-        case 2: CCB_OB_ITEMS(2); break;
-        default: CCB_OB_ITEMS(3); break;
+        case 0: ob_items<0, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, s_px, s_py, acc); break;
+        case 1: ob_items<1, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, s_px, s_py, acc); break;
+        case 2: ob_items<2, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, s_px, s_py, acc); break;
+        default: ob_items<3, VOR, DENSE>(d, sh, world, w, off0, rbase, own0, own1, amap0, amap1, cy0, cy1, s_px, s_py, acc); break;
       }
-#undef CCB_OB_ITEMS
     }
     __syncthreads();
     // ---- 4. height pass: lane = output column, warp -> output rows ox0 + 2 warp, + 1 ---------------------------
