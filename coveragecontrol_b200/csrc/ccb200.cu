@@ -608,6 +608,8 @@ struct ccb_env {
   bool vg_bulk = false;         // A/B: k_vg_reduce_bulk (cp.async.bulk + mbarrier ring) instead of k_vg_reduce
   bool vg_fused = true;         // world-map moments inside the row partition kernel (off: interval table + k_vg_lookup)
   bool cnn_generic = false;     // test option: the generic observation kernel even where the fused one applies
+  int *d_obs_order = nullptr;   // [2 E R + 4]: CTA order of k_obs_fused, class words, class counters
+  bool obs_sorted = true;       // test option: launch k_obs_fused's CTAs grouped by window misalignment
   bool obs_v1 = false;          // test option: the row-ordered fused observation kernel of round 1 (A/B timing)
 };
 
@@ -976,7 +978,7 @@ extern "C" void ccb_env_destroy(ccb_env *env) {
   cudaFree(env->d_objective), cudaFree(env->d_stage), cudaFree(env->d_feat), cudaFree(env->d_ratio);
   cudaFree(env->d_scratch);
   cudaFree(env->d_vg_table), cudaFree(env->d_vg_flag), cudaFree(env->d_vg_span), cudaFree(env->d_vg_items), cudaFree(env->d_xfeat);
-  cudaFree(env->d_vg_pfx), cudaFree(env->d_pfx_list), cudaFree(env->d_vg_band);
+  cudaFree(env->d_vg_pfx), cudaFree(env->d_pfx_list), cudaFree(env->d_vg_band), cudaFree(env->d_obs_order);
   cudaFreeHost(env->h_pin);
   for (int k = 0; k < 2; ++k) {
     cudaFreeHost(env->h_stage[k]);
@@ -1004,6 +1006,7 @@ extern "C" int ccb_test_set_option(ccb_env *env, const char *name, int value) {
   else if (n == "no_wfuse") env->no_wfuse = value != 0;
   else if (n == "cnn_generic") env->cnn_generic = value != 0;
   else if (n == "obs_v1") env->obs_v1 = value != 0;
+  else if (n == "obs_sorted") env->obs_sorted = value != 0;
   else return fail("ccb_test_set_option: unknown option", name);
   return 0;
 }
@@ -1435,22 +1438,33 @@ extern "C" int ccb_env_cnn_input_dev(ccb_env *env, int C, int use_comm, float *o
     // item-ordered kernel: local + obstacle (+ communication) channels and, for DecentralizedCVT, the window moments
     const size_t sm = obs_smem_bytes(d.R);
     double *ws = vor ? env->d_wsums : nullptr;
+    const int n_er = d.E * d.R;
+    int *order = nullptr;
+    if (env->obs_sorted && n_er >= 4 * 148) {  // (a few CTAs per SM at least: below that the order does not matter)
+      if (!env->d_obs_order) CCB_CUDA(cudaMalloc(&env->d_obs_order, sizeof(int) * (2 * (size_t)n_er + 4)));
+      int *cls = env->d_obs_order + n_er, *counts = env->d_obs_order + 2 * n_er;
+      order = env->d_obs_order;
+      CCB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * 4, env->stream));
+      k_obs_classify<<<(n_er + 255) / 256, 256, 0, env->stream>>>(d, cls, counts);
+      CCB_LAUNCH_CHECK();
+      k_obs_order<<<(n_er + 255) / 256, 256, 0, env->stream>>>(n_er, cls, counts, order);
+      CCB_LAUNCH_CHECK();
+    }
+#define CCB_OBS_LAUNCH(V, D)                                                                                                   \
+  do {                                                                                                                         \
+    if (ensure_smem(env, k_obs_fused<V, D>, sm)) return 1;                                                                      \
+    k_obs_fused<V, D><<<g8, OB_THREADS, sm, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, oo, cc, use_comm, ws, order);    \
+  } while (0)
     if (vor) {
-      if (dense) {
-        if (ensure_smem(env, k_obs_fused<true, true>, sm)) return 1;
-        k_obs_fused<true, true><<<g8, OB_THREADS, sm, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, oo, cc, use_comm, ws);
-      } else {
-        if (ensure_smem(env, k_obs_fused<true, false>, sm)) return 1;
-        k_obs_fused<true, false><<<g8, OB_THREADS, sm, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, oo, cc, use_comm, ws);
-      }
+      if (dense) CCB_OBS_LAUNCH(true, true);
+      else CCB_OBS_LAUNCH(true, false);
       env->wsums_version = env->pos_version;
     } else if (dense) {
-      if (ensure_smem(env, k_obs_fused<false, true>, sm)) return 1;
-      k_obs_fused<false, true><<<g8, OB_THREADS, sm, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, oo, cc, use_comm, ws);
+      CCB_OBS_LAUNCH(false, true);
     } else {
-      if (ensure_smem(env, k_obs_fused<false, false>, sm)) return 1;
-      k_obs_fused<false, false><<<g8, OB_THREADS, sm, env->stream>>>(d, t->d_wfull8, out_dev, stride, 0, oo, cc, use_comm, ws);
+      CCB_OBS_LAUNCH(false, false);
     }
+#undef CCB_OBS_LAUNCH
     comm_done = true;
   } else if (fused_ok) {
     // row-ordered kernel of round 1 (kept for A/B timing: ccb_test_set_option "obs_v1")

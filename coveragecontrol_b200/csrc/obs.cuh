@@ -708,15 +708,37 @@ __device__ __forceinline__ void comm_scatter_warp(const EnvDev &d, int e, int r,
   }
 }
 
+// The item loop is instantiated once per 16-byte misalignment S = (window origin column) & 3, so a CTA runs one of four
+// code paths; CTAs resident on an SM at the same time share its instruction cache.  These two kernels order the CTAs by
+// S (robots of one class are launched next to each other): cls[e R + r] = S | slot << 2, then order[base(S) + slot].
+__global__ void k_obs_classify(EnvDev d, int *__restrict__ cls, int *__restrict__ counts /* [4], zeroed */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.E * d.R) return;
+  const Window w = make_window(d.res, d.pos_g[2 * (size_t)i], d.pos_g[2 * (size_t)i + 1], 256, d.N);
+  const int S = w.oy & 3;
+  cls[i] = S | (atomicAdd(counts + S, 1) << 2);
+}
+__global__ void k_obs_order(int n, const int *__restrict__ cls, const int *__restrict__ counts, int *__restrict__ order) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = cls[i], S = c & 3;
+  int base = 0;
+  for (int k = 0; k < S; ++k) base += counts[k];
+  order[base + (c >> 2)] = i;
+}
+
 template <bool VOR, bool DENSE>
 __global__ void __launch_bounds__(OB_THREADS, 8)
 k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__restrict__ out, size_t robot_stride,
-            size_t local_off, size_t obst_off, size_t comm_off, int use_comm, double *__restrict__ wsums /* VOR: [E][R][4] */) {
+            size_t local_off, size_t obst_off, size_t comm_off, int use_comm, double *__restrict__ wsums /* VOR: [E][R][4] */,
+            const int *__restrict__ order /* optional: CTA -> e R + r, robots of one window misalignment together */) {
   extern __shared__ __align__(16) unsigned char ob_smem[];
   ObsShared &sh = *reinterpret_cast<ObsShared *>(ob_smem);
   double *s_px = reinterpret_cast<double *>(ob_smem + sizeof(ObsShared));
   double *s_py = s_px + d.R;
-  const int r = blockIdx.x, e = blockIdx.y;
+  const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+  const int er_i = order ? __ldg(order + cta) : cta;
+  const int r = er_i % d.R, e = er_i / d.R;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t er = (size_t)e * d.R + r;
   float *dst = out + er * robot_stride;

@@ -22,6 +22,7 @@ extern "C" {
  *   "vg_bulk"     1: (prefix off) k_vg_reduce_bulk -- cp.async.bulk + mbarrier ring -- instead of k_vg_reduce (A/B)
  *   "vg_fused"    1/0: with prefix sums, moments inside the row partition kernel / interval table + k_vg_lookup
  *   "vw_generic"  1: generic window Voronoi kernel      "cnn_generic" 1: generic observation kernel
+ *   "obs_sorted"  0: launch the observation kernel's CTAs in robot order instead of grouped by window misalignment
  *   "obs_v1"      1: the row-ordered fused observation kernel of round 1 instead of the item-ordered one
  *   "vor_rpw"     rows per warp region of the tile-ordered kernel   "vg_warps" / "vg_griddiv" / "vg_part_rpt"
  *   "no_aux" / "no_graph" / "no_wfuse"   1: single stream / no CUDA-graph replay / no fused window moments */
