@@ -86,6 +86,10 @@ class _TypedList(list):
     def extend(self, it):
         super().extend(self._coerce(x) for x in it)
 
+    def __iadd__(self, it):
+        self.extend(it)
+        return self
+
     def insert(self, i, x):
         super().insert(i, self._coerce(x))
 
@@ -110,8 +114,42 @@ class PointVector(_TypedList):
     def _default():
         return (0.0, 0.0)
 
+    def __init__(self, it=()):
+        # [n, 2] arrays and other PointVectors (what GetActions returns and StepActions takes every step): one
+        # private copy, the items are its rows.  Writes through an item land in the copy; anything that changes
+        # the list itself drops it (to_numpy then gathers the items again).
+        self._arr = None
+        if type(it) is PointVector:
+            it = it.to_numpy()
+        if isinstance(it, np.ndarray) and it.ndim == 2 and it.shape[1] == 2:
+            arr = np.array(it, np.float64, order="C")
+            list.__init__(self, arr)
+            self._arr = arr
+        else:
+            super().__init__(it)
+
     def to_numpy(self) -> np.ndarray:
+        if self._arr is not None:
+            return self._arr.copy()
         return np.array(self, np.float64).reshape(-1, 2)
+
+    def __reduce__(self):  # copy / deepcopy / pickle rebuild the rows over ONE new array
+        return (PointVector, (self.to_numpy(),))
+
+    def _structural(name):  # noqa: N805 - builds the list mutators that invalidate the backing array
+        base = getattr(_TypedList, name)
+
+        def method(self, *a, **k):
+            self._arr = None
+            return base(self, *a, **k)
+
+        method.__name__ = name
+        return method
+
+    for _n in ("append", "extend", "insert", "__setitem__", "__delitem__", "pop", "remove", "clear", "sort", "reverse",
+               "__iadd__", "__imul__"):
+        locals()[_n] = _structural(_n)
+    del _n, _structural
 
 
 class Point3Vector(_TypedList):
@@ -721,7 +759,10 @@ class CoverageSystem(_EnvBase):
 
     # ---- stepping (coverage_system.h:279-333) ----
     def StepActions(self, actions) -> bool:
-        a = np.ascontiguousarray(PointVector(actions).to_numpy() if not isinstance(actions, np.ndarray) else actions, np.float64)
+        if isinstance(actions, np.ndarray):
+            a = np.ascontiguousarray(actions, np.float64)
+        else:
+            a = (actions if type(actions) is PointVector else PointVector(actions)).to_numpy()
         if a.shape != (self._R, 2):
             raise ValueError("The size of the actions don't match with the number of robots")
         self._sync_world()

@@ -949,6 +949,7 @@ extern "C" ccb_env *ccb_env_create(const ccb_params *p, int num_envs, int num_ro
   d.use_sensor = p->pUpdateSensorView, d.upd_robot = p->pUpdateRobotMap;
   d.upd_expl = p->pUpdateExplorationMap, d.upd_sys = p->pUpdateSystemMap;
   d.check_osc = p->pCheckOscillations;
+  d.obs_prefetch = 1;
   d.comm_range = p->pCommunicationRange, d.max_speed = p->pMaxRobotSpeed, d.dt = p->pTimeStep;
   if (env_alloc(env.get())) {
     ccb_env_destroy(env.release());
@@ -1007,6 +1008,7 @@ extern "C" int ccb_test_set_option(ccb_env *env, const char *name, int value) {
   else if (n == "cnn_generic") env->cnn_generic = value != 0;
   else if (n == "obs_v1") env->obs_v1 = value != 0;
   else if (n == "obs_sorted") env->obs_sorted = value != 0;
+  else if (n == "obs_prefetch") env->d.obs_prefetch = value != 0;
   else return fail("ccb_test_set_option: unknown option", name);
   return 0;
 }
@@ -1095,10 +1097,10 @@ extern "C" int ccb_env_set_world_host(ccb_env *env, int e, const float *map) {
   return 0;
 }
 
-static int launch_mark(ccb_env *env, int e, int robot, int mark_robot, int mark_sys) {
+static int launch_mark(ccb_env *env, int e, int robot, int mark_robot, int mark_sys, const double *move_actions = nullptr) {
   const EnvDev &d = env->d;
   const long warps = (long)(robot >= 0 ? 1 : d.R) * (e >= 0 ? 1 : d.E);  // one warp per (robot, environment)
-  k_mark_windows<<<(unsigned)((warps + MARK_WARPS - 1) / MARK_WARPS), MARK_WARPS * 32, 0, env->stream>>>(d, e, robot, mark_robot, mark_sys);
+  k_mark_windows<<<(unsigned)((warps + MARK_WARPS - 1) / MARK_WARPS), MARK_WARPS * 32, 0, env->stream>>>(d, e, robot, mark_robot, mark_sys, move_actions);
   CCB_LAUNCH_CHECK();
   return 0;
 }
@@ -1162,9 +1164,7 @@ extern "C" int ccb_env_step_actions(ccb_env *env, const double *actions, int *ba
   const size_t er = (size_t)d.E * d.R;
   if (bad_env) *bad_env = -1;
   if (stage_to_device(env, actions, 2 * er, env->d_stage)) return 1;
-  k_move<<<(int)((er + 255) / 256), 256, 0, env->stream>>>(d, env->d_stage, nullptr);
-  CCB_LAUNCH_CHECK();
-  if (launch_mark(env, -1, -1, 1, 1)) return 1;
+  if (launch_mark(env, -1, -1, 1, 1, env->d_stage)) return 1;  // move + mark, one warp per robot
   if (state_changed(env)) return 1;
   return 0;
 }
@@ -1174,9 +1174,7 @@ static int step_actions_dev(ccb_env *env, const double *actions_dev) {
   if (join_aux(env)) return 1;
   const EnvDev &d = env->d;
   const size_t er = (size_t)d.E * d.R;
-  k_move<<<(int)((er + 255) / 256), 256, 0, env->stream>>>(d, actions_dev, nullptr);
-  CCB_LAUNCH_CHECK();
-  if (launch_mark(env, -1, -1, 1, 1)) return 1;
+  if (launch_mark(env, -1, -1, 1, 1, actions_dev)) return 1;  // move + mark, one warp per robot
   if (state_changed(env)) return 1;
   return 0;
 }
@@ -1983,23 +1981,30 @@ struct ccb_ctrl {
   } rg;
 };
 
-static int ctrl_compute_goals(ccb_ctrl *c) {
+// `centroids` (optional): where the goals are left when they are a cell set's centroids -- the caller (k_actions)
+// then copies them into d_goals itself instead of a separate device-to-device copy.
+static int ctrl_compute_goals(ccb_ctrl *c, const double **centroids = nullptr) {
   ccb_env *env = c->env;
   const EnvDev &d = env->d;
   const size_t er = (size_t)d.E * d.R;
+  const double *src = nullptr;
   if (c->kind == CCB_CLAIRVOYANT) {
     // clairvoyant_cvt.h:89-98: Voronoi on the world map == the env-level cells
     if (ensure_cells(env, false)) return 1;
-    CCB_CUDA(cudaMemcpyAsync(c->d_goals, env->cells.centroid, sizeof(double) * 2 * er, cudaMemcpyDeviceToDevice, env->stream));
+    src = env->cells.centroid;
   } else if (c->kind == CCB_CENTRALIZED && env->band_mode) {
     // row-band mode: the caller all-reduced the explored-IDF partials into the env-level cells
     if (ensure_cells(env, false)) return 1;
-    CCB_CUDA(cudaMemcpyAsync(c->d_goals, env->cells.centroid, sizeof(double) * 2 * er, cudaMemcpyDeviceToDevice, env->stream));
+    src = env->cells.centroid;
   } else if (c->kind == CCB_CENTRALIZED) {
     // centralized_cvt.h:90-100: Voronoi on the explored-IDF map
     if (launch_voronoi_global(env, SRC_EXPLORED, c->d_sums)) return 1;
     if (launch_finalize(env, c->d_sums, c->cells, 0)) return 1;
-    CCB_CUDA(cudaMemcpyAsync(c->d_goals, c->cells.centroid, sizeof(double) * 2 * er, cudaMemcpyDeviceToDevice, env->stream));
+    src = c->cells.centroid;
+  }
+  if (src) {
+    if (centroids) *centroids = src;
+    else CCB_CUDA(cudaMemcpyAsync(c->d_goals, src, sizeof(double) * 2 * er, cudaMemcpyDeviceToDevice, env->stream));
   } else {
     if (launch_voronoi_single(env, c->d_sums)) return 1;
     const int warps = d.E * d.R;
@@ -2056,9 +2061,11 @@ extern "C" void ccb_ctrl_destroy(ccb_ctrl *c) {
 static int ctrl_compute_actions_async(ccb_ctrl *c) {
   ccb_env *env = c->env;
   const EnvDev &d = env->d;
-  if (ctrl_compute_goals(c)) return 1;
+  const double *centroids = nullptr;
+  if (ctrl_compute_goals(c, &centroids)) return 1;
   int threads = std::min(1024, ((d.R + 31) / 32) * 32);
-  k_actions<<<d.E, threads, 0, env->stream>>>(d, c->d_goals, c->d_actions, c->d_conv);
+  k_actions<<<d.E, threads, 0, env->stream>>>(d, centroids ? centroids : c->d_goals, c->d_actions, c->d_conv,
+                                              centroids ? c->d_goals : nullptr);
   CCB_LAUNCH_CHECK();
   return 0;
 }

@@ -69,6 +69,7 @@ struct EnvDev {
   int upd_expl;     // pUpdateExplorationMap
   int upd_sys;      // pUpdateSystemMap
   int check_osc;    // pCheckOscillations
+  int obs_prefetch; // observation kernel: L2 prefetch of the seen box (test option, default on)
   double comm_range, max_speed, dt;
   float *world;
   uint32_t *seenb;

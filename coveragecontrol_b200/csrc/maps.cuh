@@ -203,8 +203,12 @@ __global__ void __launch_bounds__(256) k_exploration_features(EnvDev d, int K, d
 // word updates.  A robot moves a cell or so per step, so all but one row / one bit column of its window is marked
 // already: every word is READ first and only written when the OR would change it (the robot's own planes with a
 // plain store -- no other warp writes them -- the shared system planes with an atomic).
+// move_actions (optional, [E][R][2]): StepActions in the same launch -- the robot's warp first applies its action
+// (robot_model.h:200-226, move_robot below), then marks the window at the new position.
 constexpr int MARK_WARPS = 8;
-__global__ void __launch_bounds__(MARK_WARPS * 32) k_mark_windows(EnvDev d, int env_sel, int robot_sel, int mark_robot, int mark_sys) {
+__device__ inline void move_robot(const EnvDev &d, int e, int r, double ax, double ay, bool post, double &gx, double &gy);
+__global__ void __launch_bounds__(MARK_WARPS * 32) k_mark_windows(EnvDev d, int env_sel, int robot_sel, int mark_robot, int mark_sys,
+                                                                  const double *__restrict__ move_actions) {
   const int nr = robot_sel >= 0 ? 1 : d.R;
   const long wid = (long)blockIdx.x * MARK_WARPS + (threadIdx.x >> 5);
   const long total_w = (long)nr * (env_sel >= 0 ? 1 : d.E);
@@ -213,7 +217,15 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) k_mark_windows(EnvDev d, int 
   const int r = robot_sel >= 0 ? robot_sel : (int)(wid % nr);
   const int lane = threadIdx.x & 31;
   const double *p = d.pos_g + ((size_t)e * d.R + r) * 2;
-  const Window w = make_window(d.res, p[0], p[1], d.S, d.N);
+  double px, py;
+  if (move_actions) {
+    px = py = 0.0;
+    if (lane == 0) move_robot(d, e, r, move_actions[2 * ((size_t)e * d.R + r)], move_actions[2 * ((size_t)e * d.R + r) + 1], true, px, py);
+    px = __shfl_sync(0xffffffffu, px, 0), py = __shfl_sync(0xffffffffu, py, 0);
+  } else {
+    px = p[0], py = p[1];
+  }
+  const Window w = make_window(d.res, px, py, d.S, d.N);
   if (w.x1 <= w.x0 || w.y1 <= w.y0) return;
   const int w0 = w.y0 >> 5, nwords = ((w.y1 - 1) >> 5) - w0 + 1;
   const int total = (w.x1 - w.x0) * nwords;
@@ -298,18 +310,14 @@ __device__ __forceinline__ void eigen_normalize(double &x, double &y) {
 // coverage_system.h:279-291 StepActions + robot_model.h:200-256 StepControl/SetRobotPosition.
 // One thread per (env, robot).  limit[e] (may be null) = number of leading robots to move when the
 // host found an invalid control (the reference returns before PostStepCommands in that case).
-__global__ void k_move(EnvDev d, const double *__restrict__ actions, const int *__restrict__ limit) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= d.E * d.R) return;
-  const int e = idx / d.R, r = idx - e * d.R;
-  const int lim = limit ? limit[e] : d.R;
-  if (r >= lim) return;
-  const size_t er = (size_t)idx;
-  double ax = actions[2 * er], ay = actions[2 * er + 1];
-  double speed = sqrt(ax * ax + ay * ay);
+// One robot of StepActions (coverage_system.h:236-247 -> robot_model.h:200-226): speed = |action| capped at
+// pMaxRobotSpeed, direction normalised, local position advanced, global position clamped into the map;
+// post: PostStepCommands' history push.
+__device__ inline void move_robot(const EnvDev &d, int e, int r, double ax, double ay, bool post, double &gx, double &gy) {
+  const size_t er = (size_t)e * d.R + r;
+  double sp = sqrt(ax * ax + ay * ay);
   double dx = ax, dy = ay;
   eigen_normalize(dx, dy);
-  double sp = speed;
   if (sp > d.max_speed) sp = d.max_speed;
   eigen_normalize(dx, dy);
   double lx = d.pos_l[2 * er], ly = d.pos_l[2 * er + 1];
@@ -317,13 +325,23 @@ __global__ void k_move(EnvDev d, const double *__restrict__ actions, const int *
     lx = lx + dx * sp * d.dt;
     ly = ly + dy * sp * d.dt;
   }
-  double gx = lx + d.pos_s[2 * er], gy = ly + d.pos_s[2 * er + 1];
+  gx = lx + d.pos_s[2 * er], gy = ly + d.pos_s[2 * er + 1];
   clamp_global(d, gx, gy);
   d.pos_l[2 * er] = gx - d.pos_s[2 * er];
   d.pos_l[2 * er + 1] = gy - d.pos_s[2 * er + 1];
   d.pos_g[2 * er] = gx;
   d.pos_g[2 * er + 1] = gy;
-  if (lim == d.R) history_post_step(d, e, r, gx, gy);
+  if (post) history_post_step(d, e, r, gx, gy);
+}
+
+__global__ void k_move(EnvDev d, const double *__restrict__ actions, const int *__restrict__ limit) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= d.E * d.R) return;
+  const int e = idx / d.R, r = idx - e * d.R;
+  const int lim = limit ? limit[e] : d.R;
+  if (r >= lim) return;
+  double gx, gy;
+  move_robot(d, e, r, actions[2 * (size_t)idx], actions[2 * (size_t)idx + 1], lim == d.R, gx, gy);
 }
 
 // robot_model.h:228-286 SetRobotPosition (local != 0) / SetGlobalRobotPosition; positions are
@@ -426,59 +444,79 @@ __device__ inline int clip_cell_warp(const double *sx, const double *sy, int str
   int na = 4;
   double vx = (lane == 1 || lane == 2) ? w : 0.0, vy = (lane == 2 || lane == 3) ? h : 0.0;
   const double kx = sx[k * stride], ky = sy[k * stride];
-  double cjx = 0.0, cjy = 0.0;  // the sites 32 at a time: one coalesced load per chunk, then shuffles (a load per
-                                // site inside this sequential loop costs an L2 latency each: 60 us at R = 256)
-  for (int j = 0; j < n && na > 0; ++j) {
-    if ((j & 31) == 0) {
-      const int jj = min(j + lane, n - 1);
-      cjx = sx[jj * stride], cjy = sy[jj * stride];
-    }
-    const double jx = __shfl_sync(0xffffffffu, cjx, j & 31), jy = __shfl_sync(0xffffffffu, cjy, j & 31);
-    if (j == k) continue;
-    const double nx = jx - kx, ny = jy - ky;
-    if (nx == 0 && ny == 0) continue;
-    const double c = ((jx * jx + jy * jy) - (kx * kx + ky * ky)) / 2.;
-    const double dv = nx * vx + ny * vy - c;
-    const bool act = lane < na;
-    if (!__any_sync(0xffffffffu, act && dv > 0)) continue;  // the bisector does not reach the cell
-    const int u = (lane + 1 == na) ? 0 : lane + 1;
-    const double ux = __shfl_sync(0xffffffffu, vx, u & 31), uy = __shfl_sync(0xffffffffu, vy, u & 31);
-    const double du = __shfl_sync(0xffffffffu, dv, u & 31);
-    const bool vin = act && dv <= 0, uin = du <= 0;
-    const bool cross = act && ((dv <= 0) != uin);
-    const int cnt = (vin ? 1 : 0) + (cross ? 1 : 0);
-    int incl = cnt;
+  // The sites 32 at a time: one coalesced load per chunk, then shuffles (a load per site inside this sequential
+  // loop costs an L2 latency each: 60 us at R = 256).  A site farther from k than twice the polygon's
+  // circumradius about k (plus a margin above the rounding error of the half-plane test below) cannot cut it:
+  // the lanes test their own site of the chunk against that bound, and only the others go through the
+  // sequential loop, in ascending order as before.  Skipping is exactly "the bisector does not reach the cell",
+  // so the vertices stay bit for bit those of clip_cell; after each cut the bound shrinks and the test is repeated.
+  const double margin = 1e-6 * (w + h);
+  double reach2;  // (2 circumradius + margin)^2, warp-uniform
+  auto update_reach = [&]() {
+    double r2 = 0.0;
+    if (lane < na) r2 = (vx - kx) * (vx - kx) + (vy - ky) * (vy - ky);
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int up = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += up;
+    for (int o = 16; o; o >>= 1) r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+    const double rr = 2.0 * sqrt(r2) + margin;
+    reach2 = rr * rr;
+  };
+  update_reach();
+  for (int base = 0; base < n && na > 0; base += 32) {
+    const int jj = min(base + lane, n - 1);
+    const double cjx = sx[jj * stride], cjy = sy[jj * stride];
+    const double d2 = (cjx - kx) * (cjx - kx) + (cjy - ky) * (cjy - ky);
+    unsigned todo = __ballot_sync(0xffffffffu, base + lane < n && base + lane != k && d2 <= reach2);
+    while (todo && na > 0) {
+      const int jl = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const double jx = __shfl_sync(0xffffffffu, cjx, jl), jy = __shfl_sync(0xffffffffu, cjy, jl);
+      const double nx = jx - kx, ny = jy - ky;
+      if (nx == 0 && ny == 0) continue;
+      const double c = ((jx * jx + jy * jy) - (kx * kx + ky * ky)) / 2.;
+      const double dv = nx * vx + ny * vy - c;
+      const bool act = lane < na;
+      if (!__any_sync(0xffffffffu, act && dv > 0)) continue;  // the bisector does not reach the cell
+      const int u = (lane + 1 == na) ? 0 : lane + 1;
+      const double ux = __shfl_sync(0xffffffffu, vx, u & 31), uy = __shfl_sync(0xffffffffu, vy, u & 31);
+      const double du = __shfl_sync(0xffffffffu, dv, u & 31);
+      const bool vin = act && dv <= 0, uin = du <= 0;
+      const bool cross = act && ((dv <= 0) != uin);
+      const int cnt = (vin ? 1 : 0) + (cross ? 1 : 0);
+      int incl = cnt;
+  #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      const int nb = __shfl_sync(0xffffffffu, incl, 31);
+      if (nb > CLIPW_MAX) return -1;
+      int off = incl - cnt;
+      if (vin) tmp[off][0] = vx, tmp[off][1] = vy, ++off;
+      if (cross) {
+        const double t = dv / (dv - du);
+        tmp[off][0] = vx + t * (ux - vx), tmp[off][1] = vy + t * (uy - vy);
+      }
+      __syncwarp();
+      // drop a vertex equal to its predecessor (cyclically), keep the order
+      bool keep = false;
+      double tx = 0, ty = 0;
+      if (lane < nb) {
+        tx = tmp[lane][0], ty = tmp[lane][1];
+        const int pv = lane == 0 ? nb - 1 : lane - 1;
+        keep = !(nb > 1 && tx == tmp[pv][0] && ty == tmp[pv][1]);
+      }
+      const unsigned km = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int pos = __popc(km & ((1u << lane) - 1u));
+        poly[pos][0] = tx, poly[pos][1] = ty;
+      }
+      na = __popc(km);
+      __syncwarp();
+      vx = lane < na ? poly[lane][0] : 0.0, vy = lane < na ? poly[lane][1] : 0.0;
+      __syncwarp();
+      update_reach();
+      todo &= __ballot_sync(0xffffffffu, d2 <= reach2);
     }
-    const int nb = __shfl_sync(0xffffffffu, incl, 31);
-    if (nb > CLIPW_MAX) return -1;
-    int off = incl - cnt;
-    if (vin) tmp[off][0] = vx, tmp[off][1] = vy, ++off;
-    if (cross) {
-      const double t = dv / (dv - du);
-      tmp[off][0] = vx + t * (ux - vx), tmp[off][1] = vy + t * (uy - vy);
-    }
-    __syncwarp();
-    // drop a vertex equal to its predecessor (cyclically), keep the order
-    bool keep = false;
-    double tx = 0, ty = 0;
-    if (lane < nb) {
-      tx = tmp[lane][0], ty = tmp[lane][1];
-      const int pv = lane == 0 ? nb - 1 : lane - 1;
-      keep = !(nb > 1 && tx == tmp[pv][0] && ty == tmp[pv][1]);
-    }
-    const unsigned km = __ballot_sync(0xffffffffu, keep);
-    if (keep) {
-      const int pos = __popc(km & ((1u << lane) - 1u));
-      poly[pos][0] = tx, poly[pos][1] = ty;
-    }
-    na = __popc(km);
-    __syncwarp();
-    vx = lane < na ? poly[lane][0] : 0.0, vy = lane < na ? poly[lane][1] : 0.0;
-    __syncwarp();
   }
   if (lane < na) poly[lane][0] = vx, poly[lane][1] = vy;
   __syncwarp();
@@ -608,14 +646,17 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) k_finalize_single(EnvDev d, co
 }
 
 // clairvoyant_cvt.h:100-127 ComputeActions (identical in centralized_cvt.h / decentralized_cvt.h)
+// goals_out (optional): the controller's own copy of the goals when `goals` are the cells' centroids
 __global__ void k_actions(EnvDev d, const double *__restrict__ goals, double *__restrict__ actions,
-                          int *__restrict__ converged) {
+                          int *__restrict__ converged, double *__restrict__ goals_out) {
   const int e = blockIdx.x;
   int all_zero = 1;
   for (int r = threadIdx.x; r < d.R; r += blockDim.x) {
     const size_t er = (size_t)e * d.R + r;
     double ax = 0, ay = 0;
-    double dx = goals[2 * er] - d.pos_g[2 * er], dy = goals[2 * er + 1] - d.pos_g[2 * er + 1];
+    const double gx = goals[2 * er], gy = goals[2 * er + 1];
+    if (goals_out) goals_out[2 * er] = gx, goals_out[2 * er + 1] = gy;
+    double dx = gx - d.pos_g[2 * er], dy = gy - d.pos_g[2 * er + 1];
     double dist = sqrt(dx * dx + dy * dy);
     if (!(dist < kEps) && !check_oscillation(d, e, r)) {
       double speed = dist / d.dt;

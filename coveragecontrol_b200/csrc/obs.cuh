@@ -763,6 +763,21 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
     wlo = max(0, (box[2] >> 5) - wbase), whi = min(9, ((box[3] - 1) >> 5) - wbase + 1);
   }
   const int nw_s = max(whi - wlo, 0);
+  if (d.obs_prefetch) {
+    // The map values and mask words under the seen box go DRAM -> L2 while the masks are staged and the items
+    // listed: the tap loads of the width pass then wait an L2 hit, not a DRAM access.
+    int c0 = cy0, c1 = cy1;
+    if (!DENSE) c0 = max(c0, d.seen_box[4 * er + 2]), c1 = min(c1, d.seen_box[4 * er + 3]);
+    const int nrow = ahi - alo, per = c1 > c0 ? ((c1 - c0 + 31) >> 5) + 1 : 0;
+    for (int t = tid; t < nrow * per; t += OB_THREADS) {
+      const int ar = t / per, k = t - ar * per;
+      const float *rowp = world + (size_t)(w.ox + alo + ar) * d.N;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + min(c0 + 32 * k, c1 - 1)));
+    }
+    if (!DENSE && per)
+      for (int a = alo + tid; a < ahi; a += OB_THREADS)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(plane + (size_t)(w.ox + a) * d.NW + max(wbase + wlo, 0)));
+  }
   if (VOR) {
     if (tid < 8) sh.exact[tid] = 0u;
     if (warp == 0) {

@@ -186,3 +186,38 @@ def test_io_utils(tmp_path, monkeypatch):
     for fn in (IOUtils.load_toml, IOUtils.load_yaml, IOUtils.load_tensor):
         with pytest.raises(FileNotFoundError):
             fn(str(tmp_path / "absent"))
+
+
+def test_point_vector_array_backed_semantics():
+    """PointVector (core_binds.h:82 bind_vector<Point2>) keeps one private array when built from an [n, 2] array or
+    another PointVector (the per-step GetActions -> StepActions path); it must still behave like a list of Point2."""
+    import copy
+    import pickle
+
+    from coveragecontrol_b200.core import Point2, PointVector
+
+    a = np.arange(12, dtype=np.float64).reshape(6, 2)
+    pv = PointVector(a)
+    assert len(pv) == 6 and np.array_equal(pv.to_numpy(), a) and np.array_equal(pv[2], a[2])
+    pv[3][0] = 70.0  # through an item: visible in to_numpy, not in the source
+    assert pv.to_numpy()[3, 0] == 70.0 and a[3, 0] == 6.0
+    out = pv.to_numpy()
+    out[0, 0] = -1.0  # to_numpy is a copy
+    assert pv[0][0] == 0.0
+    pv[4] = Point2(1, 2)  # replacing an item, then growing the list
+    pv.append((5, 6))
+    pv += [(7, 8)]
+    got = pv.to_numpy()
+    assert got.shape == (8, 2) and got[4].tolist() == [1, 2] and got[3, 0] == 70.0 and got[-1].tolist() == [7, 8]
+    assert pv.pop().tolist() == [7, 8] and pv.to_numpy().shape == (7, 2)
+    q = PointVector(pv)
+    q[0][1] = 99.0
+    assert pv[0][1] == 1.0 and q.to_numpy()[0, 1] == 99.0
+    for clone in (copy.copy, copy.deepcopy, lambda x: pickle.loads(pickle.dumps(x))):
+        c = clone(q)
+        c[1][0] = 5.0
+        assert isinstance(c, PointVector) and c.to_numpy()[1, 0] == 5.0 and q.to_numpy()[1, 0] == 2.0
+    assert PointVector().to_numpy().shape == (0, 2) and PointVector(3).to_numpy().tolist() == [[0, 0]] * 3
+    assert PointVector([(1, 2), [3, 4]]).to_numpy().tolist() == [[1, 2], [3, 4]]
+    with pytest.raises(TypeError):
+        PointVector([(1, 2, 3)])
