@@ -356,9 +356,6 @@ def c4_row_bands(ccb, device, rank, world, dist, args):
     env = BatchedCoverageSystem(p, 1, r, device=device, stream=stream.cuda_stream)
     env.set_world(0, idf)
     env.reset(pos)
-    banded = BandedCoverageSystem(env, 0, stream=stream, graph=True)
-    banded.compute_cells()
-    ctrls = {"clairvoyant": BatchedCVT(env, 0), "decentralized": BatchedCVT(env, 2)}
     steps = 50
 
     def barrier():
@@ -366,23 +363,43 @@ def c4_row_bands(ccb, device, rank, world, dist, args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    out = {}
     peak, _ = measured_peak_gbs()
-    for kind, ctrl in ctrls.items():
-        for _ in range(5):
-            banded.step(ctrl)
-        barrier()
-        with torch.cuda.stream(stream):
-            s.record()
-            for _ in range(steps):
+    ctrls = None
+
+    def run(banded):
+        res = {}
+        for kind, ctrl in ctrls.items():
+            for _ in range(5):
                 banded.step(ctrl)
-            t.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([s.elapsed_time(t)], device="cuda")
-        if dist is not None:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        per = float(ms.item()) / steps
-        rows = banded.rows[1] - banded.rows[0]
+            barrier()
+            with torch.cuda.stream(stream):
+                s.record()
+                for _ in range(steps):
+                    banded.step(ctrl)
+                t.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([s.elapsed_time(t)], device="cuda")
+            if dist is not None:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            res[kind] = float(ms.item()) / steps
+        return res
+
+    # the step's all-reduce: one kernel over peer memory (default where the ranks can map each other's buffers),
+    # with NCCL's all_reduce timed beside it on the same state
+    banded = BandedCoverageSystem(env, 0, stream=stream, graph=True)
+    banded.compute_cells()
+    ctrls = {"clairvoyant": BatchedCVT(env, 0), "decentralized": BatchedCVT(env, 2)}
+    per_default = run(banded)
+    out = {"collective": banded.collective}
+    if banded.collective == "peer":
+        banded.close()
+        banded_nccl = BandedCoverageSystem(env, 0, stream=stream, graph=True, collective="nccl")
+        per_nccl = run(banded_nccl)
+        banded_nccl.close()
+        banded = BandedCoverageSystem(env, 0, stream=stream, graph=True)
+        out["ms_per_step_with_nccl_all_reduce"] = per_nccl
+    rows = banded.rows[1] - banded.rows[0]
+    for kind, per in per_default.items():
         out[kind] = {"ms_per_step": per, "env_steps_per_s": 1e3 / per}
         if kind == "clairvoyant":
             out[kind].update({"rows_per_gpu": rows, "band_map_bytes": 4.0 * n * rows,
@@ -397,7 +414,7 @@ def c4_row_bands(ccb, device, rank, world, dist, args):
     banded.close()  # graphs with a captured all-reduce must go before the process group does
     out.update({"workload": f"C4: {n}x{n} world, {r} robots, 1024 Gaussians + 64 polygons, row bands over {world} GPU(s)",
                 "n_gpus": world, "idf_gen_ms_banded": idf_ms, "objective": objective,
-                "step": "partials -> NCCL all-reduce -> finalise -> actions -> move + window marks, ONE captured CUDA graph",
+                "step": "partials -> all-reduce (peer-memory kernel, or NCCL) -> finalise -> actions -> move + window marks, ONE captured CUDA graph",
                 "per_rank_state_bytes": int(banded.per_rank_bytes)})
     return out
 

@@ -124,6 +124,9 @@ SIGNATURES = {
     "ccb_env_step_actions_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ccb_env_window_partials_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ccb_env_set_window_sums_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ccb_peer_buffer_bytes": (C.c_size_t, [C.c_int, C.c_size_t]),
+    "ccb_peer_allreduce_sum": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_int,
+                                         C.c_int, C.c_void_p]),
     "ccb_ctrl_create": (C.c_void_p, [C.c_void_p, C.c_int]),
     "ccb_ctrl_destroy": (None, [C.c_void_p]),
     "ccb_ctrl_compute_actions": (C.c_int, [C.c_void_p]),

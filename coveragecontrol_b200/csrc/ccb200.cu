@@ -18,6 +18,7 @@
 #include "voronoi.cuh"
 #include "vglobal.cuh"
 #include "vwindow.cuh"
+#include "peer.cuh"
 
 namespace ccb {
 thread_local std::string g_last_error;
@@ -1633,6 +1634,24 @@ extern "C" int ccb_env_set_window_sums_dev(ccb_env *env, const double *sums_dev)
 extern "C" int ccb_env_set_band_mode(ccb_env *env, int on) {
   env->band_mode = on != 0;
   env->cells_version = 0;
+  return 0;
+}
+
+// ---- one-shot all-reduce over peer memory (csrc/peer.cuh) --------------------------------------------------
+extern "C" size_t ccb_peer_buffer_bytes(int world, size_t count) { return peer_buffer_bytes(world, count); }
+extern "C" int ccb_peer_allreduce_sum(int device, void *stream, const double *in_dev, double *out_dev, size_t count,
+                                      const void *const *peer_bufs, int rank, int world, void *state_dev) {
+  if (world < 1 || world > PEER_MAX || rank < 0 || rank >= world) return fail("ccb_peer_allreduce_sum: bad rank / world size");
+  if (!in_dev || !out_dev || !peer_bufs || !state_dev || count == 0) return fail("ccb_peer_allreduce_sum: null argument");
+  CCB_CUDA(cudaSetDevice(device));
+  PeerArgs a;
+  for (int p = 0; p < world; ++p) {
+    if (!peer_bufs[p]) return fail("ccb_peer_allreduce_sum: a peer buffer is not mapped");
+    a.buf[p] = static_cast<unsigned char *>(const_cast<void *>(peer_bufs[p]));
+  }
+  a.rank = rank, a.world = world, a.count = count, a.state = static_cast<unsigned long long *>(state_dev);
+  k_peer_allreduce<<<1, PEER_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a, in_dev, out_dev);
+  CCB_LAUNCH_CHECK();
   return 0;
 }
 

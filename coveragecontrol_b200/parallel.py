@@ -21,7 +21,7 @@ import numpy as np
 from . import _lib
 
 __all__ = ["band_rows", "shard_envs", "float_to_ordered", "ordered_to_float", "allreduce_sum_", "allreduce_max_",
-           "BandedWorldIDF", "BandedCoverageSystem"]
+           "BandedWorldIDF", "BandedCoverageSystem", "PeerExchange"]
 
 
 def band_rows(n_rows: int, world_size: int, rank: int, align: int = 64) -> tuple[int, int]:
@@ -133,6 +133,75 @@ def _wrap_dev(ptr: int, shape, dtype, device):
     return torch.as_tensor(h, device=device)
 
 
+class PeerExchange:
+    """The step's all-reduce(SUM) as ONE kernel over peer memory (``csrc/peer.cuh``, ``ccb_peer_allreduce_sum``).
+
+    The partials of a step are E x R x 4 doubles (8 KB at R = 256): latency, not bandwidth.  Every rank allocates the
+    same exchange buffer from torch's symmetric-memory allocator, the rendezvous maps every peer's buffer into this
+    process (NVLink peer access), and the kernel stores / flags / waits / adds in rank order -- no NCCL call on the
+    data path, bit-identical sums on every rank and from run to run.  :meth:`create` returns ``None`` (on EVERY rank
+    alike) when the buffers cannot be set up -- single process, CPU backend, no peer access -- and the caller keeps
+    NCCL's ``all_reduce``."""
+
+    def __init__(self, hdl, buf, state, count, device, rank, world):
+        self._hdl, self._buf, self._state = hdl, buf, state  # keep the mappings alive
+        self.count, self.device, self.rank, self.world = count, device, rank, world
+        import ctypes as C
+
+        self._ptrs = (C.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+
+    @classmethod
+    def create(cls, count: int, device: int):
+        import torch
+
+        dist = _dist()
+        if dist is None or dist.get_world_size() < 2 or dist.get_backend() != "nccl":
+            return None
+        rank, world = dist.get_rank(), dist.get_world_size()
+        lib = _lib.load()
+        dev = torch.device("cuda", device)
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        hdl = buf = None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            nbytes = int(lib.ccb_peer_buffer_bytes(world, count))
+            buf = symm_mem.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            if len(hdl.buffer_ptrs) != world or not all(int(p) for p in hdl.buffer_ptrs):
+                ok.zero_()
+        except Exception:  # noqa: BLE001 - any failure here means "no peer path": all ranks must still agree below
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # also orders the zero_() of every rank before the first exchange
+        torch.cuda.synchronize(dev)
+        if int(ok.item()) == 0:
+            return None
+        state = torch.zeros(2, dtype=torch.int64, device=dev)
+        dist.barrier()
+        return cls(hdl, buf, state, count, device, rank, world)
+
+    def allreduce_sum_(self, t, stream=None):
+        """In-place rank-ordered SUM of the float64 tensor ``t`` (``count`` elements) on ``stream``."""
+        import torch
+
+        if t.numel() != self.count or t.dtype != torch.float64 or not t.is_contiguous():
+            raise ValueError("PeerExchange.allreduce_sum_: tensor does not match the exchange buffer")
+        st = stream if stream is not None else torch.cuda.current_stream(t.device)
+        _lib.check(_lib.load().ccb_peer_allreduce_sum(self.device, st.cuda_stream, t.data_ptr(), t.data_ptr(), self.count,
+                                                      self._ptrs, self.rank, self.world, self._state.data_ptr()))
+        return t
+
+    def check(self) -> None:
+        """Raise if a peer failed to arrive in some exchange (the kernel gives up after ~3 s instead of hanging)."""
+        import torch
+
+        torch.cuda.synchronize(self.device)
+        done, bad = (int(v) for v in self._state.tolist())
+        if bad:
+            raise RuntimeError(f"peer all-reduce: exchange {bad} of {done} timed out waiting for a peer")
+
+
 class BandedCoverageSystem:
     """One large world tiled over the ranks (BASELINE config 4).
 
@@ -154,8 +223,11 @@ class BandedCoverageSystem:
     ``stream`` (a ``torch.cuda.Stream``), which the all-reduce is issued on as well.
     """
 
-    def __init__(self, env, src: int = 0, stream=None, graph: bool = False):
+    def __init__(self, env, src: int = 0, stream=None, graph: bool = False, collective: str = "auto"):
         import torch
+
+        if collective not in ("auto", "peer", "nccl"):
+            raise ValueError("collective: 'auto', 'peer' or 'nccl'")
 
         self.env = env
         self.src = int(src)
@@ -176,6 +248,17 @@ class BandedCoverageSystem:
         self._graphs = {}
         self._seen = {}
         _lib.check(_lib.load().ccb_env_set_band_mode(env._h, 1))
+        # the all-reduce of a step: one kernel over peer memory where the ranks can map each other's buffers,
+        # NCCL (gloo in the CPU tests) otherwise; `collective` says which one is in use
+        self._peer = PeerExchange.create(self._sums.numel(), env._device) if collective != "nccl" else None
+        if collective == "peer" and self._peer is None and world > 1:
+            raise RuntimeError("collective='peer': the peer exchange buffers could not be set up")
+        self.collective = "peer" if self._peer is not None else ("nccl" if world > 1 else "none")
+
+    def _allreduce(self, t):
+        if self._peer is not None:
+            return self._peer.allreduce_sum_(t, self.stream)
+        return allreduce_sum_(t)
 
     def close(self) -> None:
         """Release the captured graphs.  Call before ``torch.distributed.destroy_process_group()``: a graph that
@@ -187,6 +270,8 @@ class BandedCoverageSystem:
         self._graphs.clear()
         self._seen.clear()
         torch.cuda.synchronize()
+        if self._peer is not None:
+            self._peer.check()
 
     @property
     def per_rank_bytes(self) -> int:
@@ -210,7 +295,7 @@ class BandedCoverageSystem:
         src = self.src if src is None else int(src)
         with self._ctx():
             _lib.check(lib.ccb_env_voronoi_partials_dev(self.env._h, src, r0, r1, self._sums.data_ptr()))
-            allreduce_sum_(self._sums)
+            self._allreduce(self._sums)
             _lib.check(lib.ccb_env_finalize_from_partials_dev(self.env._h, self._sums.data_ptr()))
         return self._sums
 
@@ -219,7 +304,7 @@ class BandedCoverageSystem:
         lib = _lib.load()
         with self._ctx():
             _lib.check(lib.ccb_env_window_partials_dev(self.env._h, self.robots[0], self.robots[1], self._sums.data_ptr()))
-            allreduce_sum_(self._sums)
+            self._allreduce(self._sums)
             _lib.check(lib.ccb_env_set_window_sums_dev(self.env._h, self._sums.data_ptr()))
         return self._sums
 

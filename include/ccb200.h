@@ -208,6 +208,16 @@ int ccb_env_finalize_from_partials_dev(ccb_env *env, const double *sums_dev);
  * positions (the next DecentralizedCVT ComputeActions uses them instead of reducing the windows itself). */
 int ccb_env_window_partials_dev(ccb_env *env, int robot0, int robot1, double *sums_dev);
 int ccb_env_set_window_sums_dev(ccb_env *env, const double *sums_dev);
+/* The all-reduce(SUM) of those partials as ONE kernel over peer memory (NVLink / NVSwitch; csrc/peer.cuh): every rank
+ * stores its vector into its slot of every peer's exchange buffer, raises a flag, waits for the others' flags and adds
+ * the slots in RANK ORDER -- bit-identical sums on every rank and from run to run (NCCL's order is not
+ * fixed), capturable in a CUDA graph (the exchange counter lives in state_dev).  peer_bufs: `world` device pointers,
+ * entry p = rank p's exchange buffer (ccb_peer_buffer_bytes(world, count) bytes, zeroed before the first call, the
+ * same symmetric allocation on every rank) as mapped in THIS process; state_dev: 16 zeroed bytes of local device
+ * memory ([0] exchanges done, [1] non-zero once a peer failed to arrive within ~3 s).  in_dev may equal out_dev. */
+size_t ccb_peer_buffer_bytes(int world, size_t count);
+int ccb_peer_allreduce_sum(int device, void *stream, const double *in_dev, double *out_dev, size_t count,
+                           const void *const *peer_bufs, int rank, int world, void *state_dev);
 /* coverage_system.h:279-291 StepActions with the actions already on the device (E x R x 2) */
 int ccb_env_step_actions_dev(ccb_env *env, const double *actions_dev);
 

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--kind", type=int, default=0, help="0 ClairvoyantCVT, 1 CentralizedCVT, 2 DecentralizedCVT")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph (the ncu launch list shows every kernel)")
+    ap.add_argument("--collective", default="auto", choices=["auto", "peer", "nccl"])
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -73,7 +74,7 @@ def main():
     env = BatchedCoverageSystem(p, 1, R, device=local, stream=stream.cuda_stream)
     env.set_world(0, idf)
     env.reset(pos)
-    banded = BandedCoverageSystem(env, 0, stream=stream, graph=not a.eager)
+    banded = BandedCoverageSystem(env, 0, stream=stream, graph=not a.eager, collective=a.collective)
     banded.compute_cells()
     ctrl = BatchedCVT(env, a.kind)
 
@@ -101,7 +102,7 @@ def main():
     if rank == 0:
         per = float(ms.item()) / a.steps
         print(json.dumps({"workload": f"C4 row bands: {N}x{N} world, {R} robots, {a.features} Gaussians + {a.polygons} polygons, ClairvoyantCVT",
-                          "n_gpus": world, "rows_per_gpu": banded.rows[1] - banded.rows[0], "ms_per_step": per,
+                          "n_gpus": world, "collective": banded.collective, "rows_per_gpu": banded.rows[1] - banded.rows[0], "ms_per_step": per,
                           "env_steps_per_s": 1e3 / per, "algorithmic_GBps_per_gpu": 4.0 * N * (banded.rows[1] - banded.rows[0]) / (per * 1e-3) / 1e9,
                           "idf_gen_ms_banded": idf_ms, "objective": float(obj[0])}))
     if world > 1:

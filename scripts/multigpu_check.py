@@ -44,6 +44,51 @@ def main():
     a, b = np.array(whole.GetWorldMap()), np.array(banded_idf.GetWorldMap())
     assert np.array_equal(a.view(np.int32), b.view(np.int32)), "banded IDF differs from the whole-map IDF"
 
+    # the peer-memory all-reduce alone: random vectors, bit-exact against the rank-ordered sum of an all-gather,
+    # launch by launch and replayed from a CUDA graph; a deliberately late rank must not change a bit
+    from coveragecontrol_b200.parallel import PeerExchange
+
+    world = dist.get_world_size()
+    n = 4 * R
+    px = PeerExchange.create(n, local)
+    collective = "nccl"
+    if px is not None:
+        collective = "peer"
+        st = torch.cuda.Stream(device=local)
+        gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+        for it in range(40):
+            v = (torch.rand(n, dtype=torch.float64, device="cuda", generator=gen) - 0.5) * 10.0 ** (it % 7)
+            parts = [torch.empty_like(v) for _ in range(world)]
+            dist.all_gather(parts, v)
+            want = torch.zeros_like(v)
+            for q in parts:
+                want = want + q  # rank order
+            if it % 5 == rank % 5:
+                torch.cuda._sleep(2_000_000)  # ~1 ms late
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                px.allreduce_sum_(v, st)
+            st.synchronize()
+            assert torch.equal(v, want), ("peer all-reduce differs from the rank-ordered sum", it)
+        v = torch.zeros(n, dtype=torch.float64, device="cuda")
+        src = torch.rand(n, dtype=torch.float64, device="cuda", generator=gen)
+        g = torch.cuda.CUDAGraph()
+        st.synchronize()
+        with torch.cuda.graph(g, stream=st):
+            v.copy_(src)
+            px.allreduce_sum_(v, st)
+        parts = [torch.empty_like(src) for _ in range(world)]
+        dist.all_gather(parts, src)
+        want = torch.zeros_like(src)
+        for q in parts:
+            want = want + q
+        for it in range(25):
+            with torch.cuda.stream(st):
+                g.replay()
+            st.synchronize()
+            assert torch.equal(v, want), ("graph replay of the peer all-reduce", it)
+        del g
+        px.check()
     # every controller family on the tiled world against the same roll-out on rank-local whole-map kernels:
     # eager launches first, then the captured graph (partials -> ncclAllReduce -> finalise -> actions -> move, one graph)
     stream = torch.cuda.Stream(device=local)
@@ -56,6 +101,7 @@ def main():
             benv.set_world(0, banded_idf)
             benv.reset(pos[None])
             banded = BandedCoverageSystem(benv, 0, stream=stream, graph=graph)
+            assert banded.collective == collective, (banded.collective, collective)
             banded.compute_cells()
             c0, c1 = BatchedCVT(plain, kind), BatchedCVT(benv, kind)
             for it in range(10):
@@ -74,7 +120,7 @@ def main():
     assert torch.equal(mine, ref), "replicated robot state diverged between ranks"
     dist.barrier()
     if rank == 0:
-        print(f"multigpu_check ok: world_size={dist.get_world_size()} N={N} R={R} rows/rank={banded.rows}")
+        print(f"multigpu_check ok: world_size={dist.get_world_size()} N={N} R={R} rows/rank={banded.rows} collective={collective}")
     torch.cuda.synchronize()
     dist.destroy_process_group()
 

@@ -87,6 +87,11 @@ def _worker(rank, world, port, q):
         # objective from the all-reduced moments == the oracle's direct sum
         obj = tot[:, 3] - 2 * (pos[:, 0] * tot[:, 1] + pos[:, 1] * tot[:, 2]) + (pos ** 2).sum(1) * tot[:, 0]
         assert np.allclose(obj, full[:, 3], rtol=1e-9, atol=1e-6)
+        # the peer-memory exchange needs NCCL ranks with mapped device buffers: on a gloo group every rank gets
+        # None alike and the all-reduce above stays the collective
+        from coveragecontrol_b200.parallel import PeerExchange
+
+        assert PeerExchange.create(4 * R, 0) is None
         q.put((rank, "ok"))
     except Exception as exc:  # surface the failure in the parent
         q.put((rank, repr(exc)))
@@ -108,3 +113,14 @@ def test_row_band_reduce_world_size_2_gloo():
     for pr in procs:
         pr.join(timeout=60)
     assert res == [(0, "ok"), (1, "ok")], res
+
+
+def test_peer_exchange_buffer_layout():
+    """csrc/peer.cuh: [2 parities][G ranks][count] doubles, flags [2][G] u64 after them on a 128-byte boundary."""
+    from coveragecontrol_b200 import _lib
+
+    lib = _lib.load()
+    for world, count in ((2, 1024), (8, 1024), (8, 3), (1, 1)):
+        data = 2 * world * count * 8
+        flags = (data + 127) // 128 * 128
+        assert lib.ccb_peer_buffer_bytes(world, count) == flags + 2 * world * 8
