@@ -807,9 +807,10 @@ k_obs_fused(EnvDev d, const float *__restrict__ wfull /* [32][16] */, float *__r
   }
   __syncthreads();  // weights, neighbour list, zeroed communication planes
   if (use_comm && warp == OB_WARPS - 1) comm_scatter_warp(d, e, r, 32, dst + comm_off, dst + comm_off + 32 * 32);
-  if (VOR) {  // own-cell interval of the rows that can hold a cell
+  if (VOR) {  // own-cell interval of the rows that can hold a cell (the warp that scattered the neighbours sits out)
     const int ncols = w.y1 - w.y0;
-    for (int a = alo + tid; a < ahi; a += OB_THREADS) {
+    const int nthr = use_comm ? OB_THREADS - 32 : OB_THREADS;
+    for (int a = alo + tid; a < ahi && tid < nthr; a += nthr) {
       int lo = 0, hi = 0;
       if (ncols > 0) {
         if (sh.K == 0) lo = 0, hi = ncols;
