@@ -174,7 +174,7 @@ def load():
 # afterwards (tests and A/B timing; `ccb_test_set_option`, include/ccb200_test.h).  The library itself never reads
 # the environment.
 _OVERRIDES = {"CCB_VG_GENERIC": "vg_generic", "CCB_VG_PREFIX": "vg_prefix", "CCB_VG_FUSED": "vg_fused", "CCB_VG_BULK": "vg_bulk", "CCB_VW_GENERIC": "vw_generic",
-              "CCB_CNN_GENERIC": "cnn_generic", "CCB_OBS_V1": "obs_v1", "CCB_OBS_SORTED": "obs_sorted", "CCB_OBS_PREFETCH": "obs_prefetch", "CCB_VOR_RPW": "vor_rpw", "CCB_VG_WARPS": "vg_warps",
+              "CCB_CNN_GENERIC": "cnn_generic", "CCB_OBS_V1": "obs_v1", "CCB_OBS_SORTED": "obs_sorted", "CCB_OBS_PREFETCH": "obs_prefetch", "CCB_VG_PF": "vg_pf", "CCB_VOR_RPW": "vor_rpw", "CCB_VG_WARPS": "vg_warps",
               "CCB_VG_GRIDDIV": "vg_griddiv", "CCB_VG_PART_RPT": "vg_part_rpt", "CCB_NO_AUX": "no_aux",
               "CCB_NO_GRAPH": "no_graph", "CCB_NO_WFUSE": "no_wfuse"}
 

@@ -600,6 +600,7 @@ struct ccb_env {
   int vg_mode = -1;             // CCB_VG_GENERIC: 1 forces the tile-ordered kernel, 0 the site-ordered one (tests)
   bool vw_generic = false;      // CCB_VW_GENERIC: force the generic window kernel (tests)
   bool band_mode = false;       // this env holds one row band of a world tiled over several GPUs
+  int vg_pf = 1;                // test option: L2 prefetch distance of the fused partition walk (items)
   int vg_part_rpt = 1;          // CCB_VG_PART_RPT (opt-in, 1 / 2 / 4): rows per thread of k_vg_partition
   bool vg_prefix = true;        // block prefix sums of the world maps for the site-ordered world-map moments (vglobal.cuh)
   VgPfx *d_vg_pfx = nullptr;    // [E][N][N / 16 + 1] x 128 B, allocated on first use, rebuilt per environment when its world map is set
@@ -717,7 +718,7 @@ static int launch_voronoi_global(ccb_env *env, int src, double *sums, int *label
     VgArgs g;
     g.d = d, g.row0 = row0, g.row1 = row1, g.table = env->d_vg_table, g.nflag = env->d_vg_flag, g.flag_list = env->d_vg_flag + 1, g.span = env->d_vg_span, g.sums = sums, g.labels = labels;
     g.items = env->d_vg_items;
-    g.pfx = env->d_vg_pfx, g.band = env->d_vg_band;
+    g.pfx = env->d_vg_pfx, g.band = env->d_vg_band, g.pf = env->vg_pf;
     const size_t psmem = sizeof(double) * d.R * d.R;
     if (fused) {
       // world-map moments inside the row partition: one prefix entry + one map sector per boundary, band moments
@@ -1002,6 +1003,7 @@ extern "C" int ccb_test_set_option(ccb_env *env, const char *name, int value) {
   else if (n == "vg_prefix") env->vg_prefix = value != 0;
   else if (n == "vg_fused") env->vg_fused = value != 0;
   else if (n == "vg_bulk") env->vg_bulk = value != 0;
+  else if (n == "vg_pf") env->vg_pf = std::max(0, std::min(value, 8));
   else if (n == "vg_part_rpt") env->vg_part_rpt = (value == 2 || value == 4) ? value : 1;
   else if (n == "no_aux") env->no_aux = value != 0;
   else if (n == "no_graph") env->no_graph = value != 0;

@@ -50,6 +50,7 @@ struct VgArgs {
   int *labels;          // optional [E][N*N]
   const struct VgPfx *pfx;  // SUM mode: block prefix sums of the world maps, [E][N][N / 8 + 1]
   double *band;         // SUM mode: [E][bands][R][4] moments of every CTA's row band
+  int pf;               // SUM mode: L2 prefetch distance of the walk in items (0: none)
 };
 
 template <bool SUM>
@@ -294,45 +295,38 @@ __global__ void __launch_bounds__(VG_PART_THREADS, SUM ? 6 : 1) k_vg_partition(V
     const int row = a.row0 + blockIdx.x * VG_PART_THREADS + t;
     const VgPfx *prow = a.pfx + ((size_t)e * N + min(row, a.row1 - 1)) * pe;
     const float4 *wrow = reinterpret_cast<const float4 *>(d.world + ((size_t)e * N + min(row, a.row1 - 1)) * N);
-    // what item m reads: the entries at the block edges just inside [Tl, T) and the map sectors its ends cut
+    // Item m = [T_m, T_{m+1}) of the lane's row.  The row's owners partition [0, N), so the lane carries
+    // P(T) = the row's running sums up to its last boundary -- the prefix entry of T's block (+) the cells between
+    // the block edge and T, double-double -- and an item is P(T_{m+1}) (-) P(T_m): ONE entry and ONE map sector per
+    // boundary (the boundary between two owners is loaded once, not once per side).
     auto request = [&](int m) {
       if (m < nown_t) {
-        const int Tl = L.tc[m][t], T = L.tc[m + 1][t];
-        const int bl = Tl >> 3, fl = Tl & (VG_PB - 1), b = T >> 3, f = T & (VG_PB - 1);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + bl + (fl ? 1 : 0)));
+        const int T = L.tc[m + 1][t], b = T >> 3;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + b));
-        if (fl) asm volatile("prefetch.global.L2 [%0];" ::"l"(wrow + 2 * bl));
-        if (f) asm volatile("prefetch.global.L2 [%0];" ::"l"(wrow + 2 * b));
+        if (T & (VG_PB - 1)) asm volatile("prefetch.global.L2 [%0];" ::"l"(wrow + 2 * b));
       }
     };
-    request(0);
-    request(1);
+    const int pf = a.pf;
+    for (int k = 0; k < pf; ++k) request(k);
+    DD ps{0.0, 0.0}, psy{0.0, 0.0}, psyy{0.0, 0.0};  // P(T_m); T_0 = 0
 #pragma unroll 1
     for (int m = 0; m < nitems; ++m) {
-      request(m + 2);  // two items ahead are on their way to L2 while this one is worked on
+      if (pf) request(m + pf);  // pf items ahead are on their way to L2 while this one is worked on
       int slot = -1;
       double vm = 0.0, vsx = 0.0, vsy = 0.0, vs2 = 0.0;
       if (m < nown_t) {
-        const int Tl = L.tc[m][t], T = L.tc[m + 1][t];
-        const int bl = Tl >> 3, fl = Tl & (VG_PB - 1), b = T >> 3, f = T & (VG_PB - 1);
-        double rs = 0.0, rsy = 0.0, rsyy = 0.0;
-        if (fl && bl == b) {  // the whole interval lies inside one block: its cells, directly
-          float4 A, B;
-          vg_sector_load(reinterpret_cast<const float *>(wrow + 2 * b), A, B);
-          vg_add8(A, B, ((1u << f) - 1u) & ~((1u << fl) - 1u), (double)(VG_PB * b) + 0.5, rs, rsy, rsyy);
-        } else {
-          // every load of the item first: the entries at the block edges just inside the interval -- at or after Tl,
-          // at or before T -- and the (at most) two map sectors the boundaries cut; six requests in all
-          const VgEntry el = vg_entry_load(prow + bl + (fl ? 1 : 0)), er = vg_entry_load(prow + b);
-          float4 LA = make_float4(0.f, 0.f, 0.f, 0.f), LB = LA, RA = LA, RB = LA;
-          if (fl) vg_sector_load(reinterpret_cast<const float *>(wrow + 2 * bl), LA, LB);
-          if (f) vg_sector_load(reinterpret_cast<const float *>(wrow + 2 * b), RA, RB);
-          if (fl) vg_add8(LA, LB, 0xffu & ~((1u << fl) - 1u), (double)(VG_PB * bl) + 0.5, rs, rsy, rsyy);  // head: [Tl, 8 bl + 8)
-          if (f) vg_add8(RA, RB, (1u << f) - 1u, (double)(VG_PB * b) + 0.5, rs, rsy, rsyy);                 // tail: [8 b, T)
-          rs += dd_diff(er.s, el.s);
-          rsy += dd_diff(er.sy, el.sy);
-          rsyy += dd_diff(er.syy, el.syy);
+        const int T = L.tc[m + 1][t], b = T >> 3, f = T & (VG_PB - 1);
+        const VgEntry er = vg_entry_load(prow + b);
+        DD ns = er.s, nsy = er.sy, nsyy = er.syy;
+        if (f) {
+          float4 RA, RB;
+          vg_sector_load(reinterpret_cast<const float *>(wrow + 2 * b), RA, RB);
+          double hs = 0.0, hsy = 0.0, hsyy = 0.0;
+          vg_add8(RA, RB, (1u << f) - 1u, (double)(VG_PB * b) + 0.5, hs, hsy, hsyy);  // [8 b, T)
+          ns = dd_add(ns, DD{hs, 0.0}), nsy = dd_add(nsy, DD{hsy, 0.0}), nsyy = dd_add(nsyy, DD{hsyy, 0.0});
         }
+        const double rs = dd_diff(ns, ps), rsy = dd_diff(nsy, psy), rsyy = dd_diff(nsyy, psyy);
+        ps = ns, psy = nsy, psyy = nsyy;
         const double x = (double)row + 0.5;
         vm = rs, vsx = x * rs, vsy = rsy, vs2 = fma(x * x, rs, rsyy);
         slot = L.slot[m][t];
@@ -457,7 +451,8 @@ __host__ __device__ __forceinline__ void vg_partition_row(const VgArgs &a, int e
       int hi = N;
       if (m < top) {
         const double b = z[m + 1], berr = zerr[m + 1] + 1e-13 * (fabs(b) + res);
-        const double t = ceil(b / res - 0.5);  // first column whose centre is >= b
+        // first column whose centre is >= b (at the default resolution 1 the quotient is b itself: no fp64 division)
+        const double t = ceil((res == 1.0 ? b : b / res) - 0.5);
         const double tcl = fmin(fmax(t, 0.0), (double)N);
         hi = (int)tcl;
         // centres of the cells next to the boundary

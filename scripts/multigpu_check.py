@@ -51,7 +51,7 @@ def main():
     world = dist.get_world_size()
     n = 4 * R
     px = PeerExchange.create(n, local)
-    collective = "nccl"
+    collective = "nccl" if world > 1 else "none"
     if px is not None:
         collective = "peer"
         st = torch.cuda.Stream(device=local)
