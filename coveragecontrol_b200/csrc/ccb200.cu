@@ -603,7 +603,7 @@ struct ccb_env {
   int vg_pf = 1;                // test option: L2 prefetch distance of the fused partition walk (items)
   int vg_part_rpt = 1;          // CCB_VG_PART_RPT (opt-in, 1 / 2 / 4): rows per thread of k_vg_partition
   bool vg_prefix = true;        // block prefix sums of the world maps for the site-ordered world-map moments (vglobal.cuh)
-  VgPfx *d_vg_pfx = nullptr;    // [E][N][N / 16 + 1] x 128 B, allocated on first use, rebuilt per environment when its world map is set
+  VgPfx *d_vg_pfx = nullptr;    // [E][N][N / 8 + 1] x 128 B, allocated on first use, rebuilt per environment when its world map is set
   std::vector<char> pfx_valid;  // [E]: the entries of environment e match its world map
   int *d_pfx_list = nullptr;    // [E] environments to rebuild
   double *d_vg_band = nullptr;  // [E][ceil(N / 128)][R][4] band moments of the fused partition + moments kernel
@@ -1039,7 +1039,7 @@ static int ensure_prefix(ccb_env *env) {
       cudaGetLastError();
       cudaFree(env->d_vg_pfx);
       env->d_vg_pfx = nullptr;
-      env->vg_prefix = false;  // 6 bytes per map cell were not available: keep streaming the maps
+      env->vg_prefix = false;  // 16 bytes per map cell were not available: keep streaming the maps
       return 0;
     }
     env->pfx_valid.assign(d.E, 0);

@@ -102,9 +102,15 @@ __global__ void k_vg_init_span(int *span, int n) {
 // to exactly 0.  The block sums themselves are fp64 sums of exact products, like k_vg_reduce's.
 // Only for the world map (SRC_WORLD, no labels): the explored and robot maps change with every step.
 constexpr int VG_PB = 8;  // columns per block: one 32-byte sector of the map row
-struct __align__(64) VgPfx {
+// One 128-byte line per block: the running sums (48 bytes) and, at byte 64, the block's own 8 map values, so that a
+// boundary costs ONE line of DRAM traffic (entry and cells come together; as two arrays every boundary pulled a
+// 128-byte line of each).  16 bytes of HBM per map cell.
+struct __align__(128) VgPfx {
   double s_hi, s_lo, sy_hi, sy_lo, syy_hi, syy_lo, pad0, pad1;
+  float v[VG_PB];  // the map values of columns [VG_PB b, VG_PB b + VG_PB) (zeros in the row's last entry)
+  float pad2[8];
 };
+static_assert(sizeof(VgPfx) == 128, "one line per block");
 __host__ __device__ inline size_t vg_pfx_row_entries(int N) { return (size_t)N / VG_PB + 1; }
 
 #ifdef __CUDACC__
@@ -294,7 +300,6 @@ __global__ void __launch_bounds__(VG_PART_THREADS, SUM ? 6 : 1) k_vg_partition(V
     const size_t pe = vg_pfx_row_entries(N);
     const int row = a.row0 + blockIdx.x * VG_PART_THREADS + t;
     const VgPfx *prow = a.pfx + ((size_t)e * N + min(row, a.row1 - 1)) * pe;
-    const float4 *wrow = reinterpret_cast<const float4 *>(d.world + ((size_t)e * N + min(row, a.row1 - 1)) * N);
     // Item m = [T_m, T_{m+1}) of the lane's row.  The row's owners partition [0, N), so the lane carries
     // P(T) = the row's running sums up to its last boundary -- the prefix entry of T's block (+) the cells between
     // the block edge and T, double-double -- and an item is P(T_{m+1}) (-) P(T_m): ONE entry and ONE map sector per
@@ -302,8 +307,7 @@ __global__ void __launch_bounds__(VG_PART_THREADS, SUM ? 6 : 1) k_vg_partition(V
     auto request = [&](int m) {
       if (m < nown_t) {
         const int T = L.tc[m + 1][t], b = T >> 3;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + b));
-        if (T & (VG_PB - 1)) asm volatile("prefetch.global.L2 [%0];" ::"l"(wrow + 2 * b));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + b));  // the entry and the block's cells: one line
       }
     };
     const int pf = a.pf;
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(VG_PART_THREADS, SUM ? 6 : 1) k_vg_partition(V
         DD ns = er.s, nsy = er.sy, nsyy = er.syy;
         if (f) {
           float4 RA, RB;
-          vg_sector_load(reinterpret_cast<const float *>(wrow + 2 * b), RA, RB);
+          vg_sector_load(prow[b].v, RA, RB);
           double hs = 0.0, hsy = 0.0, hsyy = 0.0;
           vg_add8(RA, RB, (1u << f) - 1u, (double)(VG_PB * b) + 0.5, hs, hsy, hsyy);  // [8 b, T)
           ns = dd_add(ns, DD{hs, 0.0}), nsy = dd_add(nsy, DD{hsy, 0.0}), nsyy = dd_add(nsyy, DD{hsyy, 0.0});
@@ -803,15 +807,18 @@ __global__ void __launch_bounds__(128) k_vg_prefix(const float *__restrict__ wor
   DD s{0.0, 0.0}, sy{0.0, 0.0}, syy{0.0, 0.0};
   float4 a = __ldg(src), b = __ldg(src + 1);
   for (int blk = 0; blk < nblk; ++blk) {
-    dst[4 * blk] = make_double2(s.hi, s.lo), dst[4 * blk + 1] = make_double2(sy.hi, sy.lo);
-    dst[4 * blk + 2] = make_double2(syy.hi, syy.lo), dst[4 * blk + 3] = make_double2(0.0, 0.0);
+    dst[8 * blk] = make_double2(s.hi, s.lo), dst[8 * blk + 1] = make_double2(sy.hi, sy.lo);
+    dst[8 * blk + 2] = make_double2(syy.hi, syy.lo);
+    reinterpret_cast<float4 *>(dst + 8 * blk + 4)[0] = a, reinterpret_cast<float4 *>(dst + 8 * blk + 4)[1] = b;
     float4 na = a, nb = b;
     if (blk + 1 < nblk) na = __ldg(src + 2 * blk + 2), nb = __ldg(src + 2 * blk + 3);  // next block in flight during the scan step
     vg_pfx_step(s, sy, syy, a, b, blk);
     a = na, b = nb;
   }
-  dst[4 * nblk] = make_double2(s.hi, s.lo), dst[4 * nblk + 1] = make_double2(sy.hi, sy.lo);
-  dst[4 * nblk + 2] = make_double2(syy.hi, syy.lo), dst[4 * nblk + 3] = make_double2(0.0, 0.0);
+  dst[8 * nblk] = make_double2(s.hi, s.lo), dst[8 * nblk + 1] = make_double2(sy.hi, sy.lo);
+  dst[8 * nblk + 2] = make_double2(syy.hi, syy.lo);
+  reinterpret_cast<float4 *>(dst + 8 * nblk + 4)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+  reinterpret_cast<float4 *>(dst + 8 * nblk + 4)[1] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // the moments of every site = the sum of its band moments in ascending band order (plain stores: no memset, no atomics)
