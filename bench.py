@@ -562,7 +562,9 @@ def main():
         return
 
     # ---- end to end through the host-buffer API: actions D2H -> host -> H2D, objective D2H ----------
-    host_actions = np.empty((E, N_ROBOTS, 2))
+    # page-locked host buffers (the library copies straight from / to a caller's buffer when it is pinned)
+    host_actions_t = torch.empty((E, N_ROBOTS, 2), dtype=torch.float64).pin_memory()
+    host_actions = host_actions_t.numpy()
     host_obj = np.empty(E)
 
     def e2e_step():
@@ -749,7 +751,7 @@ def main():
         "dtype": "f64 sums over f32 maps (u32 seen masks)", "data": "synthetic", "config": config,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "env_steps/s", "ms_per_step": ms_e2e / args.steps,
-                "scope": ("the batched C ABI with HOST buffers: actions D2H, StepActions H2D, objective D2H per step for all "
+                "scope": ("the batched C ABI with HOST buffers (page-locked): actions D2H, StepActions H2D, objective D2H per step for all "
                           "environments of the batch; the [E, R, 4, 32, 32] observation stays on the device by design "
                           "(zero-copy hand-off to LPAC); extras.c2_single_env_reference_api is the per-environment API"),
                 "h2d_bytes_per_step": int(host_actions.nbytes),

@@ -1108,7 +1108,27 @@ static int launch_mark(ccb_env *env, int e, int robot, int mark_robot, int mark_
   return 0;
 }
 
+// A caller's buffer that is page-locked itself (cudaHostAlloc / cudaHostRegister, a pinned torch tensor) is copied
+// from / to directly: no pass through the library's own pinned slots.  Asked only for transfers large enough for the
+// extra host memcpy to matter.
+static bool user_buffer_is_pinned(const void *p, size_t bytes) {
+  if (bytes < 32 * 1024) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
 static int stage_to_device(ccb_env *env, const double *host, size_t count, double *dev) {
+  if (user_buffer_is_pinned(host, count * sizeof(double))) {
+    // the call still returns only when the buffer has been read (the caller may reuse it at once)
+    CCB_CUDA(cudaMemcpyAsync(dev, host, count * sizeof(double), cudaMemcpyHostToDevice, env->stream));
+    CCB_CUDA(cudaEventRecord(env->ev_stage[env->stage_next], env->stream));
+    CCB_CUDA(cudaEventSynchronize(env->ev_stage[env->stage_next]));
+    return 0;
+  }
   // host -> pinned slot -> device on the env stream, without waiting for the copy: two slots are used in
   // turn and a slot is only rewritten once the copy that last read it has finished
   if (count > 2 * (size_t)env->E * env->R) return fail("staging buffer too small");
@@ -2098,9 +2118,10 @@ extern "C" int ccb_ctrl_compute_actions(ccb_ctrl *c) {
 
 static int d2h_doubles(ccb_env *env, const double *dev, double *out, size_t n) {
   if (n * sizeof(double) > env->h_pin_bytes) return fail("staging buffer too small");
-  CCB_CUDA(cudaMemcpyAsync(env->h_pin, dev, n * sizeof(double), cudaMemcpyDeviceToHost, env->stream));
+  const bool direct = user_buffer_is_pinned(out, n * sizeof(double));
+  CCB_CUDA(cudaMemcpyAsync(direct ? out : env->h_pin, dev, n * sizeof(double), cudaMemcpyDeviceToHost, env->stream));
   CCB_CUDA(cudaStreamSynchronize(env->stream));
-  memcpy(out, env->h_pin, n * sizeof(double));
+  if (!direct) memcpy(out, env->h_pin, n * sizeof(double));
   return 0;
 }
 
@@ -2111,11 +2132,12 @@ extern "C" int ccb_ctrl_get_actions(ccb_ctrl *c, double *out) {
   const bool dec = c->kind == CCB_DECENTRALIZED;
   // the actions and (DecentralizedCVT) the environments' status words in ONE round trip
   if (n * sizeof(double) + (dec ? sizeof(int) * env->E : 0) > env->h_pin_bytes) return fail("staging buffer too small");
-  CCB_CUDA(cudaMemcpyAsync(env->h_pin, c->d_actions, n * sizeof(double), cudaMemcpyDeviceToHost, env->stream));
+  const bool direct = user_buffer_is_pinned(out, n * sizeof(double));
+  CCB_CUDA(cudaMemcpyAsync(direct ? out : env->h_pin, c->d_actions, n * sizeof(double), cudaMemcpyDeviceToHost, env->stream));
   int *h_status = reinterpret_cast<int *>(env->h_pin + n);
   if (dec) CCB_CUDA(cudaMemcpyAsync(h_status, env->d.status, sizeof(int) * env->E, cudaMemcpyDeviceToHost, env->stream));
   CCB_CUDA(cudaStreamSynchronize(env->stream));
-  memcpy(out, env->h_pin, n * sizeof(double));
+  if (!direct) memcpy(out, env->h_pin, n * sizeof(double));
   if (dec) {
     // surface the reference's "Goal out of bounds" exception (decentralized_cvt.h:127-141)
     for (int e = 0; e < env->E; ++e)

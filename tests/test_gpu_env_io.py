@@ -79,3 +79,53 @@ def test_parity():
     # the plot switches of the evaluators must not crash (python/evaluators/eval_single_env.py:85-151)
     assert env_cuda.PlotInitMap("/tmp", "InitMap") is None
     assert env_cuda.RecordPlotData() is None
+
+
+@pytest.mark.gpu
+def test_page_locked_host_buffers_are_copied_directly_and_agree():
+    """ccb_ctrl_get_actions / ccb_env_step_actions copy straight from / to a caller's buffer when it is page-locked
+    (transfers of 32 KB and more); the results must be those of the staged path with pageable buffers."""
+    import ctypes as C
+
+    import torch
+
+    import coveragecontrol_b200 as ccb
+    from conftest import random_world
+    from coveragecontrol_b200 import BatchedCoverageSystem, BatchedCVT, _lib
+
+    lib = _lib.load()
+    E, R, N = 80, 32, 256  # E R 2 doubles = 40 KB
+    p = ccb.Parameters()
+    p.pWorldMapSize = p.pRobotMapSize = N
+    p.pNumRobots = R
+    p.pLocalMapSize = 64
+    p.pSensorSize = 16
+    bnd, _ = random_world(3, N, 6, R)
+    idf = ccb.WorldIDF(p, device=0)
+    for b in bnd:
+        idf.AddNormalDistribution(ccb.BivariateNormalDistribution(ccb.Point2(b[0], b[1]), float(b[2]), float(b[4])))
+    idf.GenerateMap()
+    pos = np.random.default_rng(5).uniform(1, N - 1, (E, R, 2))
+    envs = []
+    for _ in range(2):
+        env = BatchedCoverageSystem(p, E, R, device=0)
+        for e in range(E):
+            env.set_world(e, idf)
+        env.reset(pos)
+        envs.append((env, BatchedCVT(env, 0)))
+    pinned = torch.empty((E, R, 2), dtype=torch.float64).pin_memory()
+    pv = pinned.numpy()
+    dp = C.POINTER(C.c_double)
+    for step in range(4):
+        (e0, c0), (e1, c1) = envs
+        c0.compute_actions(), c1.compute_actions()
+        a0 = c0.actions()  # pageable destination: staged
+        _lib.check(lib.ccb_ctrl_get_actions(c1._h, pv.ctypes.data_as(dp)))  # page-locked destination: direct
+        assert np.array_equal(a0, pv), step
+        e0.step_actions(a0)
+        bad = C.c_int(-1)
+        _lib.check(lib.ccb_env_step_actions(e1._h, pv.ctypes.data_as(dp), C.byref(bad)))
+        pv[:] = -1.0  # the call has consumed the buffer: overwriting it must not change the step
+        e1._invalidate()
+        assert np.array_equal(e0.positions(), e1.positions()), step
+    assert np.array_equal(e0.objective(), e1.objective())
