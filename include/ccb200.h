@@ -229,6 +229,9 @@ void ccb_ctrl_destroy(ccb_ctrl *c);
 /* ComputeActions (clairvoyant_cvt.h:100-127, centralized_cvt.h:102-130, decentralized_cvt.h:145-173);
  * returns 0, or 2 if a decentralized goal left the world (the reference throws) */
 int ccb_ctrl_compute_actions(ccb_ctrl *c);
+/* Host buffers of 32 KB and more that are page-locked (cudaHostAlloc / cudaHostRegister) are copied from / to
+ * directly by ccb_ctrl_get_actions, ccb_ctrl_get_goals and ccb_env_step_actions; pageable ones pass through the
+ * library's pinned slots.  Either way the call returns once the buffer has been written / read. */
 int ccb_ctrl_get_actions(ccb_ctrl *c, double *out /* E x R x 2 */);
 int ccb_ctrl_get_goals(ccb_ctrl *c, double *out /* E x R x 2 */);
 int ccb_ctrl_is_converged(ccb_ctrl *c, int *out /* E */);
