@@ -334,16 +334,6 @@ __device__ inline void move_robot(const EnvDev &d, int e, int r, double ax, doub
   if (post) history_post_step(d, e, r, gx, gy);
 }
 
-__global__ void k_move(EnvDev d, const double *__restrict__ actions, const int *__restrict__ limit) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= d.E * d.R) return;
-  const int e = idx / d.R, r = idx - e * d.R;
-  const int lim = limit ? limit[e] : d.R;
-  if (r >= lim) return;
-  double gx, gy;
-  move_robot(d, e, r, actions[2 * (size_t)idx], actions[2 * (size_t)idx + 1], lim == d.R, gx, gy);
-}
-
 // robot_model.h:228-286 SetRobotPosition (local != 0) / SetGlobalRobotPosition; positions are
 // R x 2 for env e (robot < 0) or one pair.  post != 0 pushes the history (PostStepCommands).
 __global__ void k_set_positions(EnvDev d, int e, int robot, int local, const double *__restrict__ pos,
