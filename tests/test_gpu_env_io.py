@@ -106,26 +106,31 @@ def test_page_locked_host_buffers_are_copied_directly_and_agree():
         idf.AddNormalDistribution(ccb.BivariateNormalDistribution(ccb.Point2(b[0], b[1]), float(b[2]), float(b[4])))
     idf.GenerateMap()
     pos = np.random.default_rng(5).uniform(1, N - 1, (E, R, 2))
+    # Two replicas driven by ONE controller's actions: the whole-map moments of this small batch come from the
+    # tile-ordered kernel, whose fp64 atomics make two independent computations differ in the last bits -- only
+    # the copies are under test, so both replicas get the same device buffer, once staged and once directly.
     envs = []
     for _ in range(2):
         env = BatchedCoverageSystem(p, E, R, device=0)
         for e in range(E):
             env.set_world(e, idf)
         env.reset(pos)
-        envs.append((env, BatchedCVT(env, 0)))
+        envs.append(env)
+    e0, e1 = envs
+    c0 = BatchedCVT(e0, 0)
     pinned = torch.empty((E, R, 2), dtype=torch.float64).pin_memory()
     pv = pinned.numpy()
     dp = C.POINTER(C.c_double)
     for step in range(4):
-        (e0, c0), (e1, c1) = envs
-        c0.compute_actions(), c1.compute_actions()
-        a0 = c0.actions()  # pageable destination: staged
-        _lib.check(lib.ccb_ctrl_get_actions(c1._h, pv.ctypes.data_as(dp)))  # page-locked destination: direct
+        c0.compute_actions()
+        a0 = c0.actions()  # pageable destination: staged through the library's pinned slot
+        _lib.check(lib.ccb_ctrl_get_actions(c0._h, pv.ctypes.data_as(dp)))  # page-locked destination: direct
         assert np.array_equal(a0, pv), step
+        assert np.abs(a0).max() > 0
         e0.step_actions(a0)
         bad = C.c_int(-1)
         _lib.check(lib.ccb_env_step_actions(e1._h, pv.ctypes.data_as(dp), C.byref(bad)))
         pv[:] = -1.0  # the call has consumed the buffer: overwriting it must not change the step
         e1._invalidate()
         assert np.array_equal(e0.positions(), e1.positions()), step
-    assert np.array_equal(e0.objective(), e1.objective())
+    assert np.allclose(e0.objective(), e1.objective(), rtol=1e-12, atol=0)
