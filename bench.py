@@ -446,7 +446,7 @@ def main():
     workload = (f"C2: {N_WORLD}x{N_WORLD} world, {N_ROBOTS} robots, {N_FEATURES} Gaussian features, TOML params, "
                 f"DecentralizedCVT step + objective + LPAC observation (S={SENSOR}, L={LOCAL}, C={CNN})")
     config = {"workload": workload, "envs_per_gpu": E, "world": N_WORLD, "robots": N_ROBOTS, "features": N_FEATURES,
-              "l2": "state per GPU (world+seen+sys = 9 MB x envs) is larger than the 126 MB L2",
+              "l2": "state per GPU (world + seen + sys planes = 9 MB, prefix records 17 MB, x envs) is larger than the 126 MB L2",
               "parallelism": f"independent environments sharded over {world} GPU(s), no data-path collective"}
     overrides = {k: v for k, v in sorted(os.environ.items()) if k.startswith("CCB_")}
     if overrides:  # opt-in / diagnostic kernel paths: a line measured with one says so
