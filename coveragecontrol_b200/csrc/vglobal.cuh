@@ -90,16 +90,17 @@ __global__ void k_vg_init_span(int *span, int n) {
 // The world map of an environment is constant while its robots move, and a site's cells on a row are ONE column
 // interval [lo, hi).  Next to every map row the library keeps the running sums of (v, y v, y^2 v) (y = col + 0.5,
 // cell units) at every VG_PB-th column: entry b = the sum over the columns < VG_PB b, b = 0 .. N / VG_PB, one
-// 64-byte record each (8 bytes of HBM per map cell; the unit DRAM hands out is 64 bytes).  The moments of a cell
-// are then differences of entries plus the few cells between a boundary and the next block edge, so a whole-map
-// pass reads one entry and one 32-byte map sector per Voronoi BOUNDARY of a row instead of every map cell
-// (~0.8 MB instead of 4.2 MB per 1024^2 environment with 32 robots).
-// Accuracy.  Only cells inside an interval are ever added directly, and the entries are DOUBLE-DOUBLE (hi + lo,
-// ~106 bits) built by a SEQUENTIAL scan E[b + 1] = E[b] (+) blocksum(b): the difference of two entries is the
-// exact sum of the 8-cell block sums between them to ~1e-32 of the row's total -- a cell of mass 1e-9 at the end
-// of a row whose prefix is 1e3 keeps ~20 digits, so the `mass < 1e-10` fallback (voronoi.cpp:41-53) fires on
-// the same cells as with exact sums -- and a run of zero cells leaves the entries bitwise unchanged, so it sums
-// to exactly 0.  The block sums themselves are fp64 sums of exact products, like k_vg_reduce's.
+// record each (struct VgPfx below).  The moments of a cell are then differences of entries plus the few cells
+// between a boundary and its block edge, so a whole-map pass reads one record per Voronoi BOUNDARY of a row instead
+// of every map cell (~1.1 MB of DRAM traffic instead of 4.2 MB per 1024^2 environment with 32 robots).
+// Accuracy.  The entries are DOUBLE-DOUBLE (hi + lo, ~106 bits) built by a SEQUENTIAL scan
+// E[b + 1] = E[b] (+) blocksum(b); the fused walk adds the partial block [8 b, T) of a boundary (a plain fp64 sum of
+// at most 7 cells, like the block sums) to the entry in double-double too and takes P(T2) (-) P(T1): the sum of
+// [T1, T2) up to ~1e-32 of the row's running sums and a few ulp of the two PARTIAL BLOCKS -- never an ulp of the
+// running sums.  A cell of mass 1e-9 at the end of a row whose prefix is 1e3 keeps its digits, so the
+// `mass < 1e-10` fallback (voronoi.cpp:41-53) fires on the same cells as with exact sums -- and a run of zero cells
+// leaves P bitwise unchanged (the partial block is the scan's own expression with the other cells masked to zero), so
+// it sums to exactly 0.  (k_vg_lookup adds only the cells inside the interval to a difference of entries.)
 // Only for the world map (SRC_WORLD, no labels): the explored and robot maps change with every step.
 constexpr int VG_PB = 8;  // columns per block: one 32-byte sector of the map row
 // One 128-byte line per block: the running sums (48 bytes) and, at byte 64, the block's own 8 map values, so that a
