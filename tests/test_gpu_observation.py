@@ -214,8 +214,9 @@ def test_controller_nn_steps_on_the_device():
         with torch.no_grad():
             a = ctrl.model(data) * ctrl.actions_std + ctrl.actions_mean
         assert not twin.StepActions(cc.PointVector(a.cpu().numpy()))
-        assert np.array_equal(np.array(env.GetRobotPositions()), np.array(twin.GetRobotPositions()))
-        assert obj == pytest.approx(twin.GetObjectiveValue(), rel=1e-12)
+        # (the toy network's index_add_ is an atomic float32 sum: two evaluations may differ in the last bit)
+        assert np.allclose(np.array(env.GetRobotPositions()), np.array(twin.GetRobotPositions()), rtol=0, atol=1e-5)
+        assert obj == pytest.approx(twin.GetObjectiveValue(), rel=1e-7)
         assert converged is False
     with pytest.raises(ImportError):
         ControllerNN(cfg, p, env)
